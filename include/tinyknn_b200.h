@@ -1,0 +1,153 @@
+/*
+ * tinyknn_b200.h -- C ABI of the B200-native tinyknn query hot path.
+ *
+ * This is the drop-in boundary: plain C types, raw pointers + extents, no torch / numpy types.
+ * Every entry point returns an int status (TKB_OK == 0) and never throws; tkb_last_error() gives
+ * the message of the last failure on the calling thread. Paths cited as "ref:" are relative to
+ * the upstream repository thomasahle/tinyknn.
+ *
+ * Two families:
+ *   *_host : the exact surface of the reference's Cython kernel modules (tinyknn._fast_pq,
+ *            tinyknn._fast_pq_avx). Pointers are HOST memory owned by the caller (numpy buffers);
+ *            the call copies in, runs the CUDA kernels on the current device, copies out and
+ *            returns when the result is in the caller's buffer. This is what a reference
+ *            maintainer binds.
+ *   *_dev  : the same operations (and their batched forms) on DEVICE pointers and a CUDA stream
+ *            (cudaStream_t passed as void*). Asynchronous; used by the tinyknn_b200 host layer to
+ *            keep indexes resident in HBM.
+ *
+ * Data layouts (ref: tinyknn/_transform.py:53-77, :114-138; pinned by tests/test_transform.py:80-101)
+ *   codes  uint64[n_chunks][M] : chunk = 16 vectors; the 16 bytes at &codes[c][2p] hold one byte per
+ *          vector of the chunk, low nibble = code of sub-quantizer 2p, high nibble = 2p+1.
+ *   tables uint64[2M] == uint8[M][16] : row j = LUT of sub-quantizer j (int8 when signd).
+ *   est    one byte per (padded) vector position, int8 when signd, else uint8.
+ *   heap   indices int64[R] + vals int32[R], array-layout binary max-heap (root = largest value).
+ */
+#ifndef TINYKNN_B200_H
+#define TINYKNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TKB_API __attribute__((visibility("default")))
+#else
+#define TKB_API
+#endif
+
+#define TKB_OK            0
+#define TKB_ERR_INVALID   1   /* bad argument (null pointer, M not a multiple of 2/4, ...) */
+#define TKB_ERR_CUDA      2   /* CUDA runtime/driver error, see tkb_last_error() */
+#define TKB_ERR_NO_DEVICE 3   /* no usable CUDA device: there is NO CPU fallback */
+
+#define TKB_ORDER_SSE 0       /* ref: tinyknn/_fast_pq.pyx:209-236  (one accumulator)            */
+#define TKB_ORDER_AVX 1       /* ref: tinyknn/_fast_pq_256.pyx:126-156 (two lanes, default)      */
+
+#define TKB_DTYPE_F32 0
+#define TKB_DTYPE_F64 1
+
+TKB_API int         tkb_version(void);
+TKB_API const char *tkb_last_error(void);
+TKB_API int         tkb_device_count(int *count);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Host-buffer surface == the reference's Cython modules                                       */
+/* ------------------------------------------------------------------------------------------ */
+
+/* replaces estimate_pq_sse (ref: tinyknn/_fast_pq.pyx:101-111) and
+ *          estimate_pq_avx (ref: tinyknn/_fast_pq_256.pyx:52-62).
+ * data: uint64[n_chunks][M]; tables: uint64[2M]; out: uint64[2*n_chunks]. */
+TKB_API int tkb_estimate_pq_host(const uint64_t *data, int64_t n_chunks, int M, const uint64_t *tables,
+                         uint64_t *out, int order, int signd);
+
+/* replaces query_pq_sse (ref: tinyknn/_fast_pq.pyx:114-206) and
+ *          query_pq_avx (ref: tinyknn/_fast_pq_256.pyx:65-123).
+ * indices/vals: caller-owned heap of R slots, updated in place (state persists across calls,
+ * ref: tinyknn/ivf.py:137-150). labels: int64[>= n] or NULL (label = position). */
+TKB_API int tkb_query_pq_host(const uint64_t *data, int64_t n_chunks, int M, int n, const uint64_t *tables,
+                      int64_t *indices, int32_t *vals, int R, int order, int signd,
+                      const int64_t *labels);
+
+/* replaces init_heap / insert / insert_is (ref: tinyknn/_fast_pq.pyx:240-252, :274-307, :256-271).
+ * Pure host functions on the caller's arrays (they are O(R) scalar updates of host memory; the
+ * same insert code is compiled as the device function the replay kernel uses). */
+TKB_API int tkb_init_heap(int64_t *indices, int32_t *vals, int R, int signd);
+TKB_API int tkb_insert(int64_t *indices, int32_t *vals, int R, int64_t label, int v);
+TKB_API int tkb_insert_is(int64_t *indices, int32_t *vals, int R, int64_t label, int v);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Device surface (all pointers are device memory unless stated; stream = cudaStream_t)        */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Batched LUT construction: replaces FastPQ.distance_table (ref: tinyknn/fast_pq.py:186-222) when
+ * signd != 0 and FastPQ.udistance_table (ref: tinyknn/fast_pq.py:224-252) when signd == 0, for Q
+ * queries at once, including pad1 (ref: tinyknn/utils.py:6-11), the optional rotation q @ R.T and
+ * transform_tables (ref: tinyknn/_transform.py:114-138).
+ *   queries  f32[Q][d]            raw queries
+ *   normalize != 0                first q /= ||q|| in f32 (ref: tinyknn/ivf.py:126-127); the
+ *                                 normalised query is written to q_out f32[Q][d] (may alias queries)
+ *   centers  f32[16][Dp]          FastPQ.centers
+ *   R        f64[Dp][Dpad] or NULL
+ *   sqrt_n_blocks, log_n_blocks   host-computed np.sqrt(M) / np.log(M) (f64)
+ *   tables   uint8[Q][M][16]      out (== uint64[Q][2M])
+ *   q_rot    f64[Q][Dp] or NULL   out: rotated (padded) query, as f64
+ *   shift, scale f64[Q] or NULL   out: _FastDistanceTable.mean / .scale
+ */
+TKB_API int tkb_lut_build_dev(const float *queries, int Q, int d, int normalize, float *q_out,
+                      const float *centers, int Dp, int dpb, const double *R, int Dpad,
+                      double sqrt_n_blocks, double log_n_blocks, int signd,
+                      uint8_t *tables, double *q_rot, double *shift, double *scale, void *stream);
+
+/* Batched estimate: est[q][pos] for Q LUTs over the same codes.
+ *   tables uint8[Q][M][16]; est uint8[Q][est_stride], est_stride >= 16*n_chunks. */
+TKB_API int tkb_estimate_dev(const uint64_t *codes, int64_t n_chunks, int M, const uint8_t *tables, int Q,
+                     uint8_t *est, int64_t est_stride, int order, int signd, void *stream);
+
+/* IVF scan: for query q and probe slot s, estimates of every vector of list probes[q][s] with
+ * LUT q. Lists live in one codes array: list l = chunks [list_chunk_off[l], list_chunk_off[l+1]).
+ *   probes int32[Q][P]  (negative entries index from the end, like a Python list)
+ *   est    uint8[Q][P][slot_stride], slot_stride >= 16 * (largest list in chunks) */
+TKB_API int tkb_ivf_scan_dev(const uint64_t *codes, const int64_t *list_chunk_off, int n_lists, int M,
+                     const uint8_t *tables, const int32_t *probes, int Q, int P,
+                     uint8_t *est, int64_t slot_stride, int order, int signd, void *stream);
+
+/* Exact replay of the reference heap (ref: tinyknn/_fast_pq.pyx:153-206, :274-307) over
+ * precomputed estimates, one heap per query.
+ *   heap_idx int64[Q][R], heap_val int32[Q][R]: in/out (call tkb_heap_fill_dev first for a fresh heap)
+ * tkb_replay_dev : one segment per query: est[q][0..16*n_chunks), true size n, labels int64[>=n] or NULL
+ * tkb_ivf_replay_dev : P segments per query in probe order; segment s = list probes[q][s] with
+ *   n = list_size[l] and labels = ids + 16*list_chunk_off[l] (ids are stored padded like the codes). */
+TKB_API int tkb_heap_fill_dev(int64_t *heap_idx, int32_t *heap_val, int64_t count, int signd, void *stream);
+TKB_API int tkb_replay_dev(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n,
+                   int64_t *heap_idx, int32_t *heap_val, int Q, int R, int signd,
+                   const int64_t *labels, void *stream);
+TKB_API int tkb_ivf_replay_dev(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+                       const int32_t *list_size, int n_lists, const int64_t *ids,
+                       const int32_t *probes, int Q, int P,
+                       int64_t *heap_idx, int32_t *heap_val, int R, int signd, void *stream);
+
+/* Exact rescoring distances: replaces the arithmetic of knn_brute1 (ref: tinyknn/utils.py:89-92).
+ *   dists[q][r] = sum_i (rows[idx[q][r]][i] - queries[q][i])^2, computed in the rows' dtype
+ *   (f32 rows: f32 like numpy; f64 rows: f64). Negative idx index from the end (numpy semantics:
+ *   the reference rescoring may see -1 heap padding, ref: tinyknn/fast_pq.py:311). */
+TKB_API int tkb_gather_dists_dev(const void *rows, int rows_dtype, int64_t n_rows, int d,
+                         const float *queries, const int64_t *idx, int Q, int R,
+                         void *dists, void *stream);
+
+/* Device-side selection (deterministic order: ascending distance, ties by slot).
+ * tkb_select_probes_dev replaces `indices[best]` of _FastDistanceTable.top (ref: tinyknn/fast_pq.py:307-312)
+ *   for the probe lists: out int32[Q][P]; when R <= P the raw heap is returned (first R slots).
+ * tkb_select_topk_dev replaces ivf.py:154-163: drops -1, returns all survivors when <= k, else the
+ *   k nearest. out_ids int64[Q][k] (padded with -1), out_dists f32/f64[Q][k], out_count int32[Q]. */
+TKB_API int tkb_select_probes_dev(const int64_t *heap_idx, const void *dists, int dists_dtype, int Q, int R,
+                          int P, int32_t *probes, void *stream);
+TKB_API int tkb_select_topk_dev(const int64_t *heap_idx, const void *dists, int dists_dtype, int Q, int R,
+                        int k, int64_t *out_ids, void *out_dists, int32_t *out_count, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TINYKNN_B200_H */

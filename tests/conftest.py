@@ -1,0 +1,45 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    # GPU tests skip themselves cleanly when collected on a machine without a device.
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("scan", "lut", "ivf")}
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _build_native():
+    """The CUDA library and the C oracle are built in-tree before any test runs."""
+    from tinyknn_b200 import build as tkb_build
+    from oracle import build_oracle
+    if tkb_build.needs_build():
+        tkb_build.build()
+    build_oracle.build()

@@ -1,0 +1,101 @@
+"""Device plumbing: torch owns HBM allocations and streams; the kernels are reached only through
+the C ABI (`_lib.lib`) with raw device pointers. No torch op computes anything on the hot path.
+"""
+import weakref
+
+import numpy as np
+
+from . import _lib
+
+_torch = None
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
+
+
+def require_cuda():
+    t = torch()
+    if not t.cuda.is_available():
+        raise _lib.TinyKnnError(
+            "tinyknn_b200: no CUDA device is available; the query path has no CPU fallback")
+    return t
+
+
+def device():
+    t = require_cuda()
+    return t.device("cuda", t.cuda.current_device())
+
+
+def stream_ptr():
+    return torch().cuda.current_stream().cuda_stream
+
+
+_TORCH_DTYPES = None
+
+
+def _tdtype(np_dtype):
+    global _TORCH_DTYPES
+    t = torch()
+    if _TORCH_DTYPES is None:
+        _TORCH_DTYPES = {
+            np.dtype(np.uint8): t.uint8, np.dtype(np.int8): t.int8, np.dtype(np.int32): t.int32,
+            np.dtype(np.int64): t.int64, np.dtype(np.float32): t.float32, np.dtype(np.float64): t.float64,
+        }
+    return _TORCH_DTYPES[np.dtype(np_dtype)]
+
+
+def empty(shape, np_dtype):
+    return torch().empty(shape, dtype=_tdtype(np_dtype), device=device())
+
+
+def upload(arr, non_blocking=False):
+    """numpy -> device tensor (uint64 travels as int64 bit patterns)."""
+    t = require_cuda()
+    arr = np.ascontiguousarray(arr)
+    if arr.dtype == np.uint64:
+        arr = arr.view(np.int64)
+    if not arr.flags.writeable:
+        arr = arr.copy()
+    return t.from_numpy(arr).to(device(), non_blocking=non_blocking)
+
+
+def ptr(tensor):
+    return 0 if tensor is None else tensor.data_ptr()
+
+
+# ---- mirrors of caller-owned host arrays -------------------------------------------------------
+# The reference API hands the same host arrays (TransformedData.packed, the raw data matrix) to
+# every call. We keep one device copy per array object, dropped when the host array dies. A cheap
+# fingerprint (address, shape, strided sample) guards against in-place modification.
+
+_mirrors = {}
+
+
+def _fingerprint(arr):
+    flat = arr.reshape(-1).view(np.uint8)
+    step = max(1, flat.size // 257)
+    return (arr.ctypes.data, arr.shape, arr.dtype.str, flat[::step][:512].tobytes())
+
+
+def mirror(arr):
+    key = id(arr)
+    fp = _fingerprint(arr)
+    hit = _mirrors.get(key)
+    if hit is not None and hit[0] == fp:
+        return hit[1]
+    dev = upload(arr)
+    _mirrors[key] = (fp, dev)
+    try:
+        weakref.finalize(arr, _mirrors.pop, key, None)
+    except TypeError:
+        pass
+    return dev
+
+
+def drop_mirrors():
+    _mirrors.clear()

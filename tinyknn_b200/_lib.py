@@ -1,0 +1,79 @@
+"""ctypes binding of libtinyknn_b200.so (the C ABI in include/tinyknn_b200.h).
+
+There is no CPU fallback: if the shared library is missing the import of any kernel-facing module
+fails loudly, and if no CUDA device is present every compute entry point raises RuntimeError.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtinyknn_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE = 0, 1, 2, 3
+ORDER_SSE, ORDER_AVX = 0, 1
+DTYPE_F32, DTYPE_F64 = 0, 1
+PROBE_SKIP = -(2 ** 31)
+
+_c = ctypes
+_vp, _i, _i64, _dbl = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double
+
+# name -> argtypes ; every function returns int status unless noted
+SIGNATURES = {
+    "tkb_version": [],
+    "tkb_last_error": [],
+    "tkb_device_count": [_c.POINTER(_c.c_int)],
+    "tkb_estimate_pq_host": [_vp, _i64, _i, _vp, _vp, _i, _i],
+    "tkb_query_pq_host": [_vp, _i64, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "tkb_init_heap": [_vp, _vp, _i, _i],
+    "tkb_insert": [_vp, _vp, _i, _i64, _i],
+    "tkb_insert_is": [_vp, _vp, _i, _i64, _i],
+    "tkb_lut_build_dev": [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _dbl, _dbl, _i, _vp, _vp, _vp, _vp, _vp],
+    "tkb_estimate_dev": [_vp, _i64, _i, _vp, _i, _vp, _i64, _i, _i, _vp],
+    "tkb_ivf_scan_dev": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _i64, _i, _i, _vp],
+    "tkb_heap_fill_dev": [_vp, _vp, _i64, _i, _vp],
+    "tkb_replay_dev": [_vp, _i64, _i64, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "tkb_ivf_replay_dev": [_vp, _i64, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp],
+    "tkb_gather_dists_dev": [_vp, _i, _i64, _i, _vp, _vp, _i, _i, _vp, _vp],
+    "tkb_select_probes_dev": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "tkb_select_topk_dev": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+}
+
+
+class TinyKnnError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "tinyknn_b200: %s is missing. Build it with `python -m tinyknn_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export the symbol
+        fn.argtypes = argtypes
+        fn.restype = _c.c_char_p if name == "tkb_last_error" else _c.c_int
+    return lib
+
+
+lib = _load()
+
+
+def last_error():
+    msg = lib.tkb_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc):
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc == ERR_INVALID:
+        raise ValueError("tinyknn_b200: " + msg)
+    raise TinyKnnError("tinyknn_b200: " + msg)
+
+
+def device_count():
+    n = _c.c_int(0)
+    check(lib.tkb_device_count(_c.byref(n)))
+    return n.value

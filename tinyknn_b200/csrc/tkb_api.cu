@@ -1,0 +1,225 @@
+// tkb_api.cu -- extern "C" boundary of libtinyknn_b200.so (see include/tinyknn_b200.h).
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "tkb_common.cuh"
+
+namespace tkb {
+
+static thread_local char g_err[512] = "";
+
+char *err_buf() { return g_err; }
+
+int set_err(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// Grow-only device scratch for the host-buffer surface (one set per host thread and device).
+struct Scratch {
+    void *p = nullptr;
+    size_t cap = 0;
+    int dev = -1;
+    int reserve(size_t bytes)
+    {
+        int cur = 0;
+        TKB_CUDA(cudaGetDevice(&cur));
+        if (p && cur == dev && bytes <= cap) return TKB_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes < 4096 ? 4096 : bytes + bytes / 4;
+        TKB_CUDA(cudaMalloc(&p, want));
+        cap = want; dev = cur;
+        return TKB_OK;
+    }
+};
+
+static thread_local Scratch s_codes, s_tables, s_est, s_heap, s_labels;
+
+static int require_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return set_err(TKB_ERR_NO_DEVICE,
+                       "no CUDA device available (%s): tinyknn_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    return TKB_OK;
+}
+
+}  // namespace tkb
+
+using namespace tkb;
+
+extern "C" {
+
+int tkb_version(void) { return 100; }
+
+const char *tkb_last_error(void) { return tkb::err_buf(); }
+
+int tkb_device_count(int *count)
+{
+    TKB_REQUIRE(count, "null pointer");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *count = n;
+    return TKB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer surface
+// ---------------------------------------------------------------------------------------------
+
+int tkb_estimate_pq_host(const uint64_t *data, int64_t n_chunks, int M, const uint64_t *tables,
+                         uint64_t *out, int order, int signd)
+{
+    TKB_REQUIRE(n_chunks >= 0 && M > 0, "bad extent");
+    if (n_chunks == 0) return TKB_OK;
+    TKB_REQUIRE(data && tables && out, "null pointer");
+    if (int rc = require_device()) return rc;
+    const size_t code_bytes = (size_t)n_chunks * M * 8, tab_bytes = (size_t)M * 16, est_bytes = (size_t)n_chunks * 16;
+    if (int rc = s_codes.reserve(code_bytes)) return rc;
+    if (int rc = s_tables.reserve(tab_bytes)) return rc;
+    if (int rc = s_est.reserve(est_bytes)) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    TKB_CUDA(cudaMemcpyAsync(s_codes.p, data, code_bytes, cudaMemcpyHostToDevice, st));
+    TKB_CUDA(cudaMemcpyAsync(s_tables.p, tables, tab_bytes, cudaMemcpyHostToDevice, st));
+    if (int rc = launch_estimate((const uint64_t *)s_codes.p, n_chunks, M, (const uint8_t *)s_tables.p, 1,
+                                 (uint8_t *)s_est.p, 16 * n_chunks, order, signd, st)) return rc;
+    TKB_CUDA(cudaMemcpyAsync(out, s_est.p, est_bytes, cudaMemcpyDeviceToHost, st));
+    TKB_CUDA(cudaStreamSynchronize(st));
+    return TKB_OK;
+}
+
+int tkb_query_pq_host(const uint64_t *data, int64_t n_chunks, int M, int n, const uint64_t *tables,
+                      int64_t *indices, int32_t *vals, int R, int order, int signd,
+                      const int64_t *labels)
+{
+    TKB_REQUIRE(n_chunks >= 0 && M > 0 && R >= 0 && n >= 0, "bad extent");
+    if (n_chunks == 0 || R == 0) return TKB_OK;
+    TKB_REQUIRE(data && tables && indices && vals, "null pointer");
+    if (int rc = require_device()) return rc;
+    const size_t code_bytes = (size_t)n_chunks * M * 8, tab_bytes = (size_t)M * 16, est_bytes = (size_t)n_chunks * 16;
+    // labels are only dereferenced for positions < n (ref: _fast_pq.pyx:193-197)
+    const int64_t n_lab = n < 16 * n_chunks ? n : 16 * n_chunks;
+    const size_t heap_bytes = (size_t)R * 12;
+    if (int rc = s_codes.reserve(code_bytes)) return rc;
+    if (int rc = s_tables.reserve(tab_bytes)) return rc;
+    if (int rc = s_est.reserve(est_bytes)) return rc;
+    if (int rc = s_heap.reserve(heap_bytes + 16)) return rc;
+    if (labels) if (int rc = s_labels.reserve((size_t)n_lab * 8 + 8)) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    int64_t *d_idx = (int64_t *)s_heap.p;
+    int32_t *d_val = (int32_t *)((char *)s_heap.p + (size_t)R * 8);
+    TKB_CUDA(cudaMemcpyAsync(s_codes.p, data, code_bytes, cudaMemcpyHostToDevice, st));
+    TKB_CUDA(cudaMemcpyAsync(s_tables.p, tables, tab_bytes, cudaMemcpyHostToDevice, st));
+    TKB_CUDA(cudaMemcpyAsync(d_idx, indices, (size_t)R * 8, cudaMemcpyHostToDevice, st));
+    TKB_CUDA(cudaMemcpyAsync(d_val, vals, (size_t)R * 4, cudaMemcpyHostToDevice, st));
+    if (labels && n_lab > 0)
+        TKB_CUDA(cudaMemcpyAsync(s_labels.p, labels, (size_t)n_lab * 8, cudaMemcpyHostToDevice, st));
+    if (int rc = launch_estimate((const uint64_t *)s_codes.p, n_chunks, M, (const uint8_t *)s_tables.p, 1,
+                                 (uint8_t *)s_est.p, 16 * n_chunks, order, signd, st)) return rc;
+    if (int rc = launch_replay((const uint8_t *)s_est.p, 16 * n_chunks, n_chunks, n, d_idx, d_val, 1, R, signd,
+                               labels ? (const int64_t *)s_labels.p : nullptr, st)) return rc;
+    TKB_CUDA(cudaMemcpyAsync(indices, d_idx, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
+    TKB_CUDA(cudaMemcpyAsync(vals, d_val, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+    TKB_CUDA(cudaStreamSynchronize(st));
+    return TKB_OK;
+}
+
+int tkb_init_heap(int64_t *indices, int32_t *vals, int R, int signd)
+{
+    TKB_REQUIRE(R >= 0 && (R == 0 || (indices && vals)), "bad heap");
+    for (int i = 0; i < R; i++) { indices[i] = -1; vals[i] = signd ? 127 : 255; }
+    return TKB_OK;
+}
+
+int tkb_insert(int64_t *indices, int32_t *vals, int R, int64_t label, int v)
+{
+    TKB_REQUIRE(R > 0 && indices && vals, "bad heap");
+    heap_insert(indices, vals, R, label, v);
+    return TKB_OK;
+}
+
+int tkb_insert_is(int64_t *indices, int32_t *vals, int R, int64_t label, int v)
+{
+    TKB_REQUIRE(R > 0 && indices && vals, "bad heap");
+    heap_insert_is(indices, vals, R, label, v);
+    return TKB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device surface
+// ---------------------------------------------------------------------------------------------
+
+int tkb_lut_build_dev(const float *queries, int Q, int d, int normalize, float *q_out,
+                      const float *centers, int Dp, int dpb, const double *R, int Dpad,
+                      double sqrt_n_blocks, double log_n_blocks, int signd,
+                      uint8_t *tables, double *q_rot, double *shift, double *scale, void *stream)
+{
+    return launch_lut_build(queries, Q, d, normalize, q_out, centers, Dp, dpb, R, Dpad, sqrt_n_blocks,
+                            log_n_blocks, signd, tables, q_rot, shift, scale, (cudaStream_t)stream);
+}
+
+int tkb_estimate_dev(const uint64_t *codes, int64_t n_chunks, int M, const uint8_t *tables, int Q,
+                     uint8_t *est, int64_t est_stride, int order, int signd, void *stream)
+{
+    return launch_estimate(codes, n_chunks, M, tables, Q, est, est_stride, order, signd, (cudaStream_t)stream);
+}
+
+int tkb_ivf_scan_dev(const uint64_t *codes, const int64_t *list_chunk_off, int n_lists, int M,
+                     const uint8_t *tables, const int32_t *probes, int Q, int P,
+                     uint8_t *est, int64_t slot_stride, int order, int signd, void *stream)
+{
+    return launch_ivf_scan(codes, list_chunk_off, n_lists, M, tables, probes, Q, P, est, slot_stride, order,
+                           signd, (cudaStream_t)stream);
+}
+
+int tkb_heap_fill_dev(int64_t *heap_idx, int32_t *heap_val, int64_t count, int signd, void *stream)
+{
+    return launch_heap_fill(heap_idx, heap_val, count, signd, (cudaStream_t)stream);
+}
+
+int tkb_replay_dev(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n,
+                   int64_t *heap_idx, int32_t *heap_val, int Q, int R, int signd,
+                   const int64_t *labels, void *stream)
+{
+    return launch_replay(est, est_stride, n_chunks, n, heap_idx, heap_val, Q, R, signd, labels, (cudaStream_t)stream);
+}
+
+int tkb_ivf_replay_dev(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+                       const int32_t *list_size, int n_lists, const int64_t *ids,
+                       const int32_t *probes, int Q, int P,
+                       int64_t *heap_idx, int32_t *heap_val, int R, int signd, void *stream)
+{
+    return launch_ivf_replay(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
+                             heap_val, R, signd, (cudaStream_t)stream);
+}
+
+int tkb_gather_dists_dev(const void *rows, int rows_dtype, int64_t n_rows, int d,
+                         const float *queries, const int64_t *idx, int Q, int R,
+                         void *dists, void *stream)
+{
+    return launch_gather_dists(rows, rows_dtype, n_rows, d, queries, idx, Q, R, dists, (cudaStream_t)stream);
+}
+
+int tkb_select_probes_dev(const int64_t *heap_idx, const void *dists, int dists_dtype, int Q, int R,
+                          int P, int32_t *probes, void *stream)
+{
+    return launch_select_probes(heap_idx, dists, dists_dtype, Q, R, P, probes, (cudaStream_t)stream);
+}
+
+int tkb_select_topk_dev(const int64_t *heap_idx, const void *dists, int dists_dtype, int Q, int R,
+                        int k, int64_t *out_ids, void *out_dists, int32_t *out_count, void *stream)
+{
+    return launch_select_topk(heap_idx, dists, dists_dtype, Q, R, k, out_ids, out_dists, out_count, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+"""IVF index with the reference's API (ref: tinyknn/ivf.py); the query path runs on B200.
+
+`fit` / `build` are build-time host code (numpy + sklearn, same algorithm and RNG call order as the
+reference). `query` (ref: ivf.py:106-163) is a batch of one through `query_batch`, which keeps the
+whole index resident in HBM and runs, per batch of queries:
+
+  LUT build -> scan of the PQ-encoded centroids -> exact heap replay (2*n_probes+10 candidates) ->
+  exact centroid distances -> probe lists -> scan of the probed inverted lists -> ordered exact heap
+  replay ((n_probes+1)*k+1 candidates) -> exact rescoring distances -> k nearest.
+
+Selection order (`order=`): the reference picks probe lists and the final k with np.argpartition,
+whose output ORDER is numpy-build/CPU specific while the visiting order of the lists changes the
+heap contents.
+  order="numpy"  : the two tiny selections (<= 2*n_probes+10 and <= pass_1 floats per query) are done
+                   by numpy's own argpartition on the host, exactly like the reference -- bit-exact
+                   ids on the machine that runs it. `IVF.query` uses this.
+  order="device" : everything stays on the GPU; ties and order are resolved as "ascending distance,
+                   then heap slot". One host sync per batch. This is the throughput mode.
+"""
+import numpy as np
+
+from . import _device as D
+from . import fast_pq as _fp
+from ._lib import lib, check, DTYPE_F32, DTYPE_F64, PROBE_SKIP
+from .fast_pq import FastPQ, TransformedData, query_pq  # noqa: F401  (ivf.py:5 re-export)
+from .utils import timer, knn_brute, group_data_by_indices, bottom_k
+
+_WORKSPACE_BYTES = 2 << 30          # cap of the per-batch estimate buffer (queries are sub-batched)
+
+
+class IVF:
+    def __init__(self, metric, n_clusters, pq=None):
+        assert metric in ["euclidean", "angular"]
+        self.metric = metric
+        self.pq = FastPQ(dims_per_block=2) if pq is None else pq
+        assert self.pq.centers is None, "PQ should not be pre-fitted"
+        self.pq_transformed_points = [None] * n_clusters
+        self.pq_transformed_centers = [None] * n_clusters
+        self.n_clusters = n_clusters
+        self.ids = [None] * n_clusters
+
+    # ------------------------------------------------------------------ build time (host) ----
+    def fit(self, X, verbose=False):
+        """Coarse centroids by k-means on the raw vectors, then the PQ codebooks (ref: ivf.py:19-51)."""
+        import sklearn.cluster
+        assert X.shape[0] >= 1
+        with timer(verbose, "Fitting IVF cluster centers..."):
+            km = sklearn.cluster.KMeans(n_clusters=self.n_clusters, n_init=1, verbose=verbose)
+            if self.metric == "angular":
+                X = X / np.linalg.norm(X, axis=1, keepdims=True)
+            self.all_centers = km.fit(X).cluster_centers_
+            if self.metric == "angular":
+                self.all_centers /= np.linalg.norm(self.all_centers, axis=1, keepdims=True)
+        with timer(verbose, "Fitting PQ to data..."):
+            self.pq.fit(X, verbose=verbose)
+        return self
+
+    def build(self, X, n_probes=2, verbose=False):
+        """Put every point into the lists of its n_probes nearest centroids (ref: ivf.py:53-104)."""
+        assert n_probes <= self.n_clusters, \
+            f"Can't assign points to {n_probes} clusters, as index only has {self.n_clusters}"
+        self.data = data = X.copy()
+        if self.metric == "angular":
+            data /= np.linalg.norm(data, axis=1, keepdims=True)
+        with timer(verbose, "Computing nearest clusters..."):
+            nearest = knn_brute(data, self.all_centers, k=n_probes, metric=self.metric)
+        with timer(verbose, "PQ Transforming active centers..."):
+            self.active_centers = np.ascontiguousarray(self.all_centers[np.unique(nearest)], dtype=np.float32)
+            self.pq_transformed_centers = self.pq.transform(self.active_centers)
+        with timer(verbose, "Transforming points..."):
+            n_active = self.active_centers.shape[0]
+            groups, self.ids = group_data_by_indices(data, nearest, n_active)
+            for i, g in enumerate(groups):
+                self.pq_transformed_points[i] = self.pq.transform(g)
+        self.__dict__.pop("_dev", None)
+        return self
+
+    # ------------------------------------------------------------------ device index ---------
+    def __getstate__(self):
+        return {k: v for k, v in self.__dict__.items() if k not in ("_dev", "_last")}
+
+    def invalidate(self):
+        """Forget the device copy (call after replacing index arrays by hand)."""
+        self.__dict__.pop("_dev", None)
+
+    def to_device(self):
+        """Upload the index once: all inverted lists in ONE codes array (each list padded to whole
+        16-vector chunks), CSR chunk offsets, true sizes, padded ids, centroid codes, centroids, raw data."""
+        dev = self.__dict__.get("_dev")
+        if dev is not None:
+            return dev
+        D.require_cuda()
+        ctd = self.pq_transformed_centers
+        C = int(ctd.size)
+        M = ctd.packed.shape[1]
+        n_lists = len(self.pq_transformed_points)
+        sizes = np.zeros(n_lists, dtype=np.int32)
+        chunks = np.zeros(n_lists + 1, dtype=np.int64)
+        parts, id_parts = [], []
+        for l, td in enumerate(self.pq_transformed_points):
+            n_l, packed = (0, None) if td is None or not isinstance(td, tuple) else td
+            nc = 0 if packed is None else packed.shape[0]
+            if nc:
+                assert packed.shape[1] == M and packed.dtype == np.uint64
+                parts.append(packed)
+                ids_l = np.full(16 * nc, -1, dtype=np.int64)
+                ids_l[:n_l] = np.asarray(self.ids[l], dtype=np.int64)[:n_l]
+                id_parts.append(ids_l)
+            sizes[l] = n_l
+            chunks[l + 1] = chunks[l] + nc
+        codes = np.concatenate(parts) if parts else np.zeros((1, M), dtype=np.uint64)
+        ids = np.concatenate(id_parts) if id_parts else np.zeros(16, dtype=np.int64)
+        data = self.data
+        if not isinstance(data, np.ndarray) or data.dtype not in (np.float32, np.float64):
+            data = np.ascontiguousarray(data, dtype=np.float64)
+        dev = dict(
+            C=C, M=M, n_lists=n_lists, max_chunks=int(np.max(np.diff(chunks))) if n_lists else 0,
+            codes=D.upload(codes), list_chunk_off=D.upload(chunks), list_size=D.upload(sizes), ids=D.upload(ids),
+            center_codes=D.upload(ctd.packed), centers=D.upload(np.ascontiguousarray(self.active_centers, dtype=np.float32)),
+            data=D.upload(data), data_dtype=DTYPE_F32 if data.dtype == np.float32 else DTYPE_F64,
+            d=int(data.shape[1]), host_sizes=sizes, host_chunks=chunks)
+        self.__dict__["_dev"] = dev
+        return dev
+
+    # ------------------------------------------------------------------ query time -----------
+    def query(self, q, k, n_probes=1, pass_1=None):
+        """ref: ivf.py:106-163. Returns an unordered int64 array of at most k ids."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        assert q.ndim == 1
+        ids, counts = self.query_batch(q[None], k, n_probes=n_probes, pass_1=pass_1, order="numpy")
+        return ids[0][:counts[0]]
+
+    def query_batch(self, queries, k, n_probes=1, pass_1=None, order="device", return_distances=False):
+        """Batched IVF.query (new, additive API). queries: f32 (Q, d), host array or device tensor.
+        Returns (ids, counts[, dists]): ids int64 (Q, k) padded with -1, counts int32 (Q,)."""
+        assert order in ("device", "numpy")
+        dev = self.to_device()
+        t = D.torch()
+        if isinstance(queries, np.ndarray):
+            queries = np.ascontiguousarray(queries, dtype=np.float32)
+        Q, d = queries.shape
+        assert dev["d"] == d                                            # ref: ivf.py:161
+        C = dev["C"]
+        P = min(n_probes, C)                                            # ref: fast_pq.py:291
+        Rc = min(2 * P + 10, C)                                         # ref: fast_pq.py:293-295
+        if pass_1 is None:
+            pass_1 = (n_probes + 1) * k + 1                             # ref: ivf.py:135-136
+        slot_stride = 16 * max(dev["max_chunks"], 1)
+        qb = int(max(1, min(Q, _WORKSPACE_BYTES // max(1, P * slot_stride))))
+        out_ids = np.full((Q, k), -1, dtype=np.int64)
+        out_cnt = np.zeros(Q, dtype=np.int32)
+        out_dst = np.full((Q, k), np.inf, dtype=np.float32 if dev["data_dtype"] == DTYPE_F32 else np.float64)
+        for lo in range(0, Q, qb):
+            hi = min(Q, lo + qb)
+            qs = queries[lo:hi]
+            if isinstance(qs, np.ndarray):
+                qs = D.upload(qs)
+            ids_b, cnt_b, dst_b = self._query_block(dev, qs, k, P, Rc, pass_1, slot_stride, order)
+            out_ids[lo:hi], out_cnt[lo:hi], out_dst[lo:hi] = ids_b, cnt_b, dst_b
+        if return_distances:
+            return out_ids, out_cnt, out_dst
+        return out_ids, out_cnt
+
+    def _query_block(self, dev, qs, k, P, Rc, pass_1, slot_stride, order):
+        t = D.torch()
+        st = D.stream_ptr()
+        Q = qs.shape[0]
+        C, M, n_lists = dev["C"], dev["M"], dev["n_lists"]
+        sg = 1                                                           # IVF.query hard-codes signed=True (ivf.py:138,148)
+        # 1. LUTs (ref: ivf.py:125-128)
+        lut = self.pq.distance_tables(qs, signed=True, normalize=(self.metric == "angular"))
+        tables, qn = lut["tables"], lut["q"]
+        # 2. probe selection (ref: ivf.py:131 -> fast_pq.py:284-312)
+        cc = dev["center_codes"]
+        nck = cc.shape[0]
+        est_c = D.empty((Q, 16 * nck), np.uint8)
+        check(lib.tkb_estimate_dev(D.ptr(cc), nck, M, D.ptr(tables), Q, D.ptr(est_c), 16 * nck, _fp._order(), sg, st))
+        hci, hcv = D.empty((Q, Rc), np.int64), D.empty((Q, Rc), np.int32)
+        check(lib.tkb_heap_fill_dev(D.ptr(hci), D.ptr(hcv), Q * Rc, sg, st))
+        check(lib.tkb_replay_dev(D.ptr(est_c), 16 * nck, nck, C, D.ptr(hci), D.ptr(hcv), Q, Rc, sg, None, st))
+        probes = D.empty((Q, P), np.int32)
+        if Rc <= P:
+            check(lib.tkb_select_probes_dev(D.ptr(hci), None, DTYPE_F32, Q, Rc, P, D.ptr(probes), st))
+        else:
+            dc = D.empty((Q, Rc), np.float32)
+            check(lib.tkb_gather_dists_dev(D.ptr(dev["centers"]), DTYPE_F32, C, dev["d"], D.ptr(qn), D.ptr(hci),
+                                           Q, Rc, D.ptr(dc), st))
+            if order == "device":
+                check(lib.tkb_select_probes_dev(D.ptr(hci), D.ptr(dc), DTYPE_F32, Q, Rc, P, D.ptr(probes), st))
+            else:
+                hci_h, dc_h = hci.cpu().numpy(), dc.cpu().numpy()
+                best = np.argpartition(dc_h, P, axis=1)[:, :P]           # == per-row bottom_k (utils.py:22-25)
+                probes = D.upload(np.take_along_axis(hci_h, best, axis=1).astype(np.int32))
+        # 3. scan of the probed lists + ordered replay (ref: ivf.py:137-150)
+        est = D.empty((Q, P, slot_stride), np.uint8)
+        check(lib.tkb_ivf_scan_dev(D.ptr(dev["codes"]), D.ptr(dev["list_chunk_off"]), n_lists, M, D.ptr(tables),
+                                   D.ptr(probes), Q, P, D.ptr(est), slot_stride, _fp._order(), sg, st))
+        hi_, hv_ = D.empty((Q, pass_1), np.int64), D.empty((Q, pass_1), np.int32)
+        check(lib.tkb_heap_fill_dev(D.ptr(hi_), D.ptr(hv_), Q * pass_1, sg, st))
+        check(lib.tkb_ivf_replay_dev(D.ptr(est), slot_stride, D.ptr(dev["list_chunk_off"]), D.ptr(dev["list_size"]),
+                                     n_lists, D.ptr(dev["ids"]), D.ptr(probes), Q, P, D.ptr(hi_), D.ptr(hv_),
+                                     pass_1, sg, st))
+        # 4. exact rescoring (ref: ivf.py:154-163)
+        ddt = np.float32 if dev["data_dtype"] == DTYPE_F32 else np.float64
+        dd = D.empty((Q, pass_1), ddt)
+        check(lib.tkb_gather_dists_dev(D.ptr(dev["data"]), dev["data_dtype"], dev["data"].shape[0], dev["d"],
+                                       D.ptr(qn), D.ptr(hi_), Q, pass_1, D.ptr(dd), st))
+        self._last = dict(probes=probes, heap_idx=hi_, heap_val=hv_, tables=tables, center_heap=hci)
+        if order == "device":
+            oi, od, oc = D.empty((Q, k), np.int64), D.empty((Q, k), ddt), D.empty((Q,), np.int32)
+            check(lib.tkb_select_topk_dev(D.ptr(hi_), D.ptr(dd), dev["data_dtype"], Q, pass_1, k,
+                                          D.ptr(oi), D.ptr(od), D.ptr(oc), st))
+            return oi.cpu().numpy(), oc.cpu().numpy(), od.cpu().numpy()
+        hi_h, dd_h = hi_.cpu().numpy(), dd.cpu().numpy()
+        ids = np.full((Q, k), -1, dtype=np.int64)
+        dst = np.full((Q, k), np.inf, dtype=ddt)
+        cnt = np.zeros(Q, dtype=np.int32)
+        for i in range(Q):
+            keep = hi_h[i] != -1                                         # ref: ivf.py:154-155
+            cand, cd = hi_h[i][keep], dd_h[i][keep]
+            if len(cand) > k:                                            # ref: ivf.py:158-163
+                best = bottom_k(cd, k)
+                cand, cd = cand[best], cd[best]
+            cnt[i] = len(cand)
+            ids[i, :len(cand)], dst[i, :len(cand)] = cand, cd
+        return ids, cnt, dst
