@@ -64,8 +64,13 @@ def last_error():
     return msg.decode("utf-8", "replace") if msg else ""
 
 
+n_calls = 0          # C-ABI calls that returned OK (each *_dev call launches one kernel per <=65535 queries)
+
+
 def check(rc):
+    global n_calls
     if rc == OK:
+        n_calls += 1
         return
     msg = last_error()
     if rc == ERR_INVALID:

@@ -17,6 +17,8 @@ heap contents.
   order="device" : everything stays on the GPU; ties and order are resolved as "ascending distance,
                    then heap slot". One host sync per batch. This is the throughput mode.
 """
+from contextlib import contextmanager
+
 import numpy as np
 
 from . import _device as D
@@ -77,7 +79,7 @@ class IVF:
 
     # ------------------------------------------------------------------ device index ---------
     def __getstate__(self):
-        return {k: v for k, v in self.__dict__.items() if k not in ("_dev", "_last")}
+        return {k: v for k, v in self.__dict__.items() if k not in ("_dev", "_last", "_prof")}
 
     def invalidate(self):
         """Forget the device copy (call after replacing index arrays by hand)."""
@@ -122,6 +124,30 @@ class IVF:
         self.__dict__["_dev"] = dev
         return dev
 
+    # ------------------------------------------------------------------ profiling hooks -----
+    def profile(self, enabled=True):
+        """Record a CUDA-event pair around every stage of the following query_batch calls
+        (on the launching stream). Read them back with `stage_times()`."""
+        self.__dict__["_prof"] = {} if enabled else None
+
+    @contextmanager
+    def _stage(self, name):
+        prof = self.__dict__.get("_prof")
+        if prof is None:
+            yield
+            return
+        t = D.torch()
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        prof.setdefault(name, []).append((e0, e1))
+
+    def stage_times(self):
+        """{stage: [ms, ...]} for the events recorded since profile(True); synchronises."""
+        D.torch().cuda.synchronize()
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in (self.__dict__.get("_prof") or {}).items()}
+
     # ------------------------------------------------------------------ query time -----------
     def query(self, q, k, n_probes=1, pass_1=None):
         """ref: ivf.py:106-163. Returns an unordered int64 array of at most k ids."""
@@ -130,10 +156,13 @@ class IVF:
         ids, counts = self.query_batch(q[None], k, n_probes=n_probes, pass_1=pass_1, order="numpy")
         return ids[0][:counts[0]]
 
-    def query_batch(self, queries, k, n_probes=1, pass_1=None, order="device", return_distances=False):
+    def query_batch(self, queries, k, n_probes=1, pass_1=None, order="device", return_distances=False,
+                    to_host=True):
         """Batched IVF.query (new, additive API). queries: f32 (Q, d), host array or device tensor.
-        Returns (ids, counts[, dists]): ids int64 (Q, k) padded with -1, counts int32 (Q,)."""
+        Returns (ids, counts[, dists]): ids int64 (Q, k) padded with -1, counts int32 (Q,).
+        With to_host=False (order="device" only) the results stay on the GPU as torch tensors."""
         assert order in ("device", "numpy")
+        assert to_host or order == "device"
         dev = self.to_device()
         t = D.torch()
         if isinstance(queries, np.ndarray):
@@ -147,19 +176,21 @@ class IVF:
             pass_1 = (n_probes + 1) * k + 1                             # ref: ivf.py:135-136
         slot_stride = 16 * max(dev["max_chunks"], 1)
         qb = int(max(1, min(Q, _WORKSPACE_BYTES // max(1, P * slot_stride))))
-        out_ids = np.full((Q, k), -1, dtype=np.int64)
-        out_cnt = np.zeros(Q, dtype=np.int32)
-        out_dst = np.full((Q, k), np.inf, dtype=np.float32 if dev["data_dtype"] == DTYPE_F32 else np.float64)
+        outs = []
         for lo in range(0, Q, qb):
-            hi = min(Q, lo + qb)
-            qs = queries[lo:hi]
+            qs = queries[lo:min(Q, lo + qb)]
             if isinstance(qs, np.ndarray):
                 qs = D.upload(qs)
-            ids_b, cnt_b, dst_b = self._query_block(dev, qs, k, P, Rc, pass_1, slot_stride, order)
-            out_ids[lo:hi], out_cnt[lo:hi], out_dst[lo:hi] = ids_b, cnt_b, dst_b
+            outs.append(self._query_block(dev, qs, k, P, Rc, pass_1, slot_stride, order))
+        if order == "device":
+            ids, cnt, dst = (outs[0] if len(outs) == 1 else tuple(t.cat([o[i] for o in outs]) for i in range(3)))
+            if to_host:
+                ids, cnt, dst = ids.cpu().numpy(), cnt.cpu().numpy(), dst.cpu().numpy()
+        else:
+            ids, cnt, dst = (np.concatenate([o[i] for o in outs]) for i in range(3))
         if return_distances:
-            return out_ids, out_cnt, out_dst
-        return out_ids, out_cnt
+            return ids, cnt, dst
+        return ids, cnt
 
     def _query_block(self, dev, qs, k, P, Rc, pass_1, slot_stride, order):
         t = D.torch()
@@ -168,16 +199,19 @@ class IVF:
         C, M, n_lists = dev["C"], dev["M"], dev["n_lists"]
         sg = 1                                                           # IVF.query hard-codes signed=True (ivf.py:138,148)
         # 1. LUTs (ref: ivf.py:125-128)
-        lut = self.pq.distance_tables(qs, signed=True, normalize=(self.metric == "angular"))
+        with self._stage("lut"):
+            lut = self.pq.distance_tables(qs, signed=True, normalize=(self.metric == "angular"))
         tables, qn = lut["tables"], lut["q"]
         # 2. probe selection (ref: ivf.py:131 -> fast_pq.py:284-312)
         cc = dev["center_codes"]
         nck = cc.shape[0]
         est_c = D.empty((Q, 16 * nck), np.uint8)
-        check(lib.tkb_estimate_dev(D.ptr(cc), nck, M, D.ptr(tables), Q, D.ptr(est_c), 16 * nck, _fp._order(), sg, st))
+        with self._stage("coarse_scan"):
+            check(lib.tkb_estimate_dev(D.ptr(cc), nck, M, D.ptr(tables), Q, D.ptr(est_c), 16 * nck, _fp._order(), sg, st))
         hci, hcv = D.empty((Q, Rc), np.int64), D.empty((Q, Rc), np.int32)
-        check(lib.tkb_heap_fill_dev(D.ptr(hci), D.ptr(hcv), Q * Rc, sg, st))
-        check(lib.tkb_replay_dev(D.ptr(est_c), 16 * nck, nck, C, D.ptr(hci), D.ptr(hcv), Q, Rc, sg, None, st))
+        with self._stage("coarse_replay"):
+            check(lib.tkb_heap_fill_dev(D.ptr(hci), D.ptr(hcv), Q * Rc, sg, st))
+            check(lib.tkb_replay_dev(D.ptr(est_c), 16 * nck, nck, C, D.ptr(hci), D.ptr(hcv), Q, Rc, sg, None, st))
         probes = D.empty((Q, P), np.int32)
         if Rc <= P:
             check(lib.tkb_select_probes_dev(D.ptr(hci), None, DTYPE_F32, Q, Rc, P, D.ptr(probes), st))
@@ -193,24 +227,27 @@ class IVF:
                 probes = D.upload(np.take_along_axis(hci_h, best, axis=1).astype(np.int32))
         # 3. scan of the probed lists + ordered replay (ref: ivf.py:137-150)
         est = D.empty((Q, P, slot_stride), np.uint8)
-        check(lib.tkb_ivf_scan_dev(D.ptr(dev["codes"]), D.ptr(dev["list_chunk_off"]), n_lists, M, D.ptr(tables),
-                                   D.ptr(probes), Q, P, D.ptr(est), slot_stride, _fp._order(), sg, st))
+        with self._stage("scan"):
+            check(lib.tkb_ivf_scan_dev(D.ptr(dev["codes"]), D.ptr(dev["list_chunk_off"]), n_lists, M, D.ptr(tables),
+                                       D.ptr(probes), Q, P, D.ptr(est), slot_stride, _fp._order(), sg, st))
         hi_, hv_ = D.empty((Q, pass_1), np.int64), D.empty((Q, pass_1), np.int32)
-        check(lib.tkb_heap_fill_dev(D.ptr(hi_), D.ptr(hv_), Q * pass_1, sg, st))
-        check(lib.tkb_ivf_replay_dev(D.ptr(est), slot_stride, D.ptr(dev["list_chunk_off"]), D.ptr(dev["list_size"]),
-                                     n_lists, D.ptr(dev["ids"]), D.ptr(probes), Q, P, D.ptr(hi_), D.ptr(hv_),
-                                     pass_1, sg, st))
+        with self._stage("replay"):
+            check(lib.tkb_heap_fill_dev(D.ptr(hi_), D.ptr(hv_), Q * pass_1, sg, st))
+            check(lib.tkb_ivf_replay_dev(D.ptr(est), slot_stride, D.ptr(dev["list_chunk_off"]), D.ptr(dev["list_size"]),
+                                         n_lists, D.ptr(dev["ids"]), D.ptr(probes), Q, P, D.ptr(hi_), D.ptr(hv_),
+                                         pass_1, sg, st))
         # 4. exact rescoring (ref: ivf.py:154-163)
         ddt = np.float32 if dev["data_dtype"] == DTYPE_F32 else np.float64
         dd = D.empty((Q, pass_1), ddt)
-        check(lib.tkb_gather_dists_dev(D.ptr(dev["data"]), dev["data_dtype"], dev["data"].shape[0], dev["d"],
-                                       D.ptr(qn), D.ptr(hi_), Q, pass_1, D.ptr(dd), st))
+        with self._stage("rescore"):
+            check(lib.tkb_gather_dists_dev(D.ptr(dev["data"]), dev["data_dtype"], dev["data"].shape[0], dev["d"],
+                                           D.ptr(qn), D.ptr(hi_), Q, pass_1, D.ptr(dd), st))
         self._last = dict(probes=probes, heap_idx=hi_, heap_val=hv_, tables=tables, center_heap=hci)
         if order == "device":
             oi, od, oc = D.empty((Q, k), np.int64), D.empty((Q, k), ddt), D.empty((Q,), np.int32)
             check(lib.tkb_select_topk_dev(D.ptr(hi_), D.ptr(dd), dev["data_dtype"], Q, pass_1, k,
                                           D.ptr(oi), D.ptr(od), D.ptr(oc), st))
-            return oi.cpu().numpy(), oc.cpu().numpy(), od.cpu().numpy()
+            return oi, oc, od
         hi_h, dd_h = hi_.cpu().numpy(), dd.cpu().numpy()
         ids = np.full((Q, k), -1, dtype=np.int64)
         dst = np.full((Q, k), np.inf, dtype=ddt)

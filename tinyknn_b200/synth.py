@@ -1,0 +1,195 @@
+"""Synthetic index construction for benchmarks and large parity tests (BUILD-TIME TOOLING).
+
+The reference builds indexes with sklearn KMeans and a Python loop of tiny GEMMs
+(ref: tinyknn/ivf.py:19-104, tinyknn/fast_pq.py:50-184) -- hours at 10M-100M vectors. The hot path
+this repository rebuilds only *consumes* an index, so to make inputs of the BASELINE.json shapes
+this module builds one with plain torch ops on the GPU (Lloyd iterations, nearest-of-16 encoding,
+list grouping) and hands back an ordinary `IVF` object whose attributes have exactly the
+reference's types and layouts (ref: ivf.py:77, 91-102), so the oracle / the compiled reference can
+query the very same index on the CPU. Nothing here is on the timed path.
+"""
+import numpy as np
+
+from . import _device as D
+from .fast_pq import FastPQ, TransformedData
+from .ivf import IVF
+
+
+def clustered(n, d, n_components, seed, normalize=False, sigma=1.0, device=None, dtype=None):
+    """Gaussian mixture: means ~ N(0, 4I), points = mean + N(0, sigma^2 I)."""
+    t = D.require_cuda()
+    device = device or D.device()
+    g = t.Generator(device=device).manual_seed(seed)
+    means = t.randn(n_components, d, generator=g, device=device) * 2
+    comp = t.randint(n_components, (n,), generator=g, device=device)
+    X = means[comp]
+    X += t.randn(n, d, generator=g, device=device) * sigma
+    if normalize:
+        X /= X.norm(dim=1, keepdim=True)
+    return X
+
+
+def _nearest(X, C, chunk=1 << 18):
+    t = D.torch()
+    out = t.empty(X.shape[0], dtype=t.int64, device=X.device)
+    cn = (C * C).sum(1)
+    for lo in range(0, X.shape[0], chunk):
+        x = X[lo:lo + chunk]
+        out[lo:lo + chunk] = (cn[None] - 2 * x @ C.T).argmin(1)
+    return out
+
+
+def kmeans(X, k, iters, seed):
+    """A few Lloyd iterations (empty clusters are re-seeded from random points)."""
+    t = D.torch()
+    g = t.Generator(device=X.device).manual_seed(seed)
+    C = X[t.randperm(X.shape[0], generator=g, device=X.device)[:k]].clone()
+    for _ in range(iters):
+        a = _nearest(X, C)
+        cnt = t.bincount(a, minlength=k)
+        S = t.zeros_like(C).index_add_(0, a, X)
+        C = t.where(cnt[:, None] > 0, S / cnt.clamp(min=1)[:, None], C)
+        empty = (cnt == 0).nonzero().flatten()
+        if len(empty):
+            C[empty] = X[t.randint(X.shape[0], (len(empty),), generator=g, device=X.device)]
+    return C
+
+
+def fit_pq(X_sample, dims_per_block=2, rotate_dim=64, iters=8, seed=0, dpad=4):
+    """FastPQ with torch-fitted codebooks: attributes as after FastPQ.fit (ref: fast_pq.py:50-104)."""
+    t = D.torch()
+    n, true_d = X_sample.shape
+    dpb = dims_per_block
+    Dpad = -(-true_d // (dpad * dpb)) * (dpad * dpb)
+    Xp = t.zeros(n, Dpad, device=X_sample.device, dtype=t.float32)
+    Xp[:, :true_d] = X_sample
+    pq = FastPQ(dpb, use_kmeans=True, rotate_dim=rotate_dim)
+    d = Dpad
+    if rotate_dim is not None and true_d != 100:                  # ref: fast_pq.py:77-82
+        g = t.Generator(device="cpu").manual_seed(seed)
+        Qm, _ = t.linalg.qr(t.randn(Dpad, Dpad, generator=g, dtype=t.float64))
+        R = Qm.T.contiguous()
+        if Dpad > rotate_dim:
+            d = rotate_dim
+            R = R[:d].contiguous()
+        pq.R = R.numpy()
+        Xp = (Xp.double() @ R.to(Xp.device).T).float()
+    M = d // dpb
+    blocks = Xp.reshape(n, M, dpb).permute(1, 0, 2).contiguous()   # (M, n, dpb)
+    g = t.Generator(device=Xp.device).manual_seed(seed + 1)
+    C = blocks[:, t.randperm(n, generator=g, device=Xp.device)[:16]].clone()     # (M, 16, dpb)
+    for _ in range(iters):
+        a = t.cdist(blocks, C).argmin(2)                           # (M, n)
+        oh = t.nn.functional.one_hot(a, 16).to(blocks.dtype)       # (M, n, 16)
+        cnt = oh.sum(1)                                            # (M, 16)
+        S = oh.transpose(1, 2) @ blocks                            # (M, 16, dpb)
+        C = t.where(cnt[..., None] > 0, S / cnt.clamp(min=1)[..., None], C)
+    pq.centers = np.ascontiguousarray(C.permute(1, 0, 2).reshape(16, d).cpu().numpy(), dtype=np.float32)
+    pq.sqrt_n_blocks = np.sqrt(d // dpb)
+    return pq
+
+
+def encode(pq, X, dpad=4, chunk=1 << 17):
+    """Nearest-of-16 codes per block, uint8 (n, M), on the device (ref: fast_pq.py:147-184)."""
+    t = D.torch()
+    dpb = pq.dims_per_block
+    n, true_d = X.shape
+    Dpad = -(-true_d // (dpad * dpb)) * (dpad * dpb)
+    d = pq.centers.shape[1]
+    M = d // dpb
+    C = t.from_numpy(pq.centers).to(X.device).reshape(16, M, dpb).permute(1, 0, 2).contiguous()   # (M,16,dpb)
+    R = None if pq.R is None else t.from_numpy(pq.R).to(X.device).float()
+    codes = t.empty(n, M, dtype=t.uint8, device=X.device)
+    for lo in range(0, n, chunk):
+        x = X[lo:lo + chunk].float()
+        if Dpad != true_d:
+            x = t.nn.functional.pad(x, (0, Dpad - true_d))
+        if R is not None:
+            x = x @ R.T
+        xb = x.reshape(-1, M, dpb).permute(1, 0, 2)                # (M, rows, dpb)
+        codes[lo:lo + chunk] = t.cdist(xb, C).argmin(2).T.to(t.uint8)
+    return codes
+
+
+def pack_codes(codes):
+    """torch version of transform_data (ref: _transform.py:4-77): uint8 (n16, M) -> int64 bit patterns (n16/16, M)."""
+    t = D.torch()
+    n, M = codes.shape
+    assert n % 16 == 0 and M % 2 == 0
+    c = codes.reshape(n // 16, 16, M // 2, 2)
+    byte = c[..., 0] | (c[..., 1] << 4)                            # (chunks, 16, M/2)
+    return byte.permute(0, 2, 1).contiguous().reshape(n // 16, M * 8).view(t.int64)
+
+
+def build_ivf(X, metric, n_clusters, pq=None, kmeans_iters=6, fit_sample=200_000, seed=0, keep_device=True):
+    """IVF index over device data X (f32, (n, d)); one list per point (build_probes = 1).
+    Returns an `IVF` whose host attributes mirror the reference's and whose device copy is in place."""
+    t = D.require_cuda()
+    n, d = X.shape
+    if metric == "angular":
+        X = X / X.norm(dim=1, keepdim=True)
+    g = t.Generator(device=X.device).manual_seed(seed)
+    sample = X[t.randperm(n, generator=g, device=X.device)[:min(n, fit_sample)]]
+    centers = kmeans(sample, n_clusters, kmeans_iters, seed)
+    if metric == "angular":
+        centers = centers / centers.norm(dim=1, keepdim=True)
+    if pq is None:
+        pq = fit_pq(sample[:100_000], seed=seed)
+    assign = _nearest(X, centers)
+    used = t.unique(assign)                                        # active centres (ref: ivf.py:91-93)
+    remap = t.full((n_clusters,), -1, dtype=t.int64, device=X.device)
+    remap[used] = t.arange(len(used), device=X.device)
+    assign = remap[assign]
+    C = len(used)
+    active = centers[used].contiguous()
+    order = t.argsort(assign, stable=True)
+    sizes = t.bincount(assign, minlength=C)
+    chunks = (sizes + 15) // 16
+    chunk_off = t.zeros(C + 1, dtype=t.int64, device=X.device)
+    chunk_off[1:] = chunks.cumsum(0)
+    start = t.zeros(C + 1, dtype=t.int64, device=X.device)
+    start[1:] = sizes.cumsum(0)
+    total_slots = int(chunk_off[-1].item()) * 16
+    sorted_list = assign[order]
+    slot = 16 * chunk_off[sorted_list] + (t.arange(n, device=X.device) - start[sorted_list])
+    codes = encode(pq, X)
+    zero_code = encode(pq, t.zeros(1, d, device=X.device))[0]      # padding rows are zero vectors (fast_pq.py:165)
+    all_codes = zero_code[None].repeat(total_slots, 1)
+    all_codes[slot] = codes[order]
+    packed = pack_codes(all_codes)
+    ids_padded = t.full((total_slots,), -1, dtype=t.int64, device=X.device)
+    ids_padded[slot] = order
+    center_td = pq_transform_small(pq, active)
+
+    ivf = IVF(metric, n_clusters, FastPQ(pq.dims_per_block, rotate_dim=pq.rotate_dim))
+    ivf.pq.centers, ivf.pq.R, ivf.pq.sqrt_n_blocks = pq.centers, pq.R, pq.sqrt_n_blocks
+    ivf.all_centers = centers.cpu().numpy()
+    ivf.active_centers = np.ascontiguousarray(active.cpu().numpy(), dtype=np.float32)
+    ivf.pq_transformed_centers = center_td
+    packed_h = packed.cpu().numpy().view(np.uint64)
+    order_h, sizes_h, off_h, start_h = order.cpu().numpy(), sizes.cpu().numpy(), chunk_off.cpu().numpy(), start.cpu().numpy()
+    ivf.pq_transformed_points = [TransformedData(int(sizes_h[l]), packed_h[off_h[l]:off_h[l + 1]]) for l in range(C)] \
+        + [None] * (n_clusters - C)
+    ivf.ids = [order_h[start_h[l]:start_h[l + 1]] for l in range(C)] + [None] * (n_clusters - C)
+    ivf.data = X.cpu().numpy()
+    if keep_device:
+        from ._lib import DTYPE_F32
+        M = packed.shape[1]
+        off_full = t.cat([chunk_off, chunk_off[-1:].repeat(n_clusters - C)])
+        sizes_full = t.cat([sizes, t.zeros(n_clusters - C, dtype=sizes.dtype, device=X.device)]).to(t.int32)
+        ivf.__dict__["_dev"] = dict(
+            C=C, M=M, n_lists=n_clusters, max_chunks=int(chunks.max().item()), codes=packed, list_chunk_off=off_full,
+            list_size=sizes_full, ids=ids_padded, center_codes=D.upload(center_td.packed),
+            centers=active.float().contiguous(), data=X.contiguous(), data_dtype=DTYPE_F32, d=d,
+            host_sizes=sizes_full.cpu().numpy(), host_chunks=off_full.cpu().numpy())
+    return ivf
+
+
+def pq_transform_small(pq, rows):
+    """TransformedData of a small device matrix (used for the centroid codes)."""
+    t = D.torch()
+    n = rows.shape[0]
+    n16 = -(-n // 16) * 16
+    padded = t.zeros(n16, rows.shape[1], device=rows.device, dtype=rows.dtype)
+    padded[:n] = rows
+    return TransformedData(n, pack_codes(encode(pq, padded)).cpu().numpy().view(np.uint64))
