@@ -283,8 +283,8 @@ def main():
         # (query, vector) + 1 B estimate written; scanned vectors counted from the probe lists of the last step
         probes = ivf._last["probes"].cpu().numpy().astype(np.int64)
         probes = np.where(probes < 0, probes + dev["n_lists"], probes)
-        chunks = np.diff(dev["host_chunks"])
-        scanned = int(16 * chunks[probes].sum())
+        real_chunks = (dev["host_sizes"].astype(np.int64) + 15) // 16      # the reference pads each list to 16 (not to our tiles)
+        scanned = int(16 * real_chunks[probes].sum())
         scan_ms = float(np.mean(stages["scan"]))
         alg_bytes = scanned * (M // 2 + 1)
         peaks = {}

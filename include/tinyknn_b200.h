@@ -114,6 +114,27 @@ TKB_API int tkb_ivf_scan_dev(const uint64_t *codes, const int64_t *list_chunk_of
                      const uint8_t *tables, const int32_t *probes, int Q, int P,
                      uint8_t *est, int64_t slot_stride, int order, int signd, void *stream);
 
+/* Device-native code layout for the fast scan (chosen at upload, round-trips to the reference layout).
+ * tile = 8 chunks; the 16 bytes of (tile t, pair p, chunk slot s) sit at ((t*M/2 + p)*8 + s)*16 and hold
+ * 8 halfwords: halfword g = codes of sub-quantizer 2p for vectors 4g..4g+3 (nibble i = vector 4g+i),
+ * halfword 4+g = the same for sub-quantizer 2p+1. `native` needs ceil(n_chunks/8)*8 * M*8 bytes; padding
+ * chunks are zero codes. In a native IVF array every list starts on a tile boundary (list_chunk_off % 8 == 0). */
+TKB_API int tkb_codes_to_native_dev(const uint64_t *codes, int64_t n_chunks, int M, void *native, void *stream);
+TKB_API int tkb_codes_from_native_dev(const void *native, int64_t n_chunks, int M, uint64_t *codes, void *stream);
+
+/* Fast scan on the native layout: same results as tkb_estimate_dev / tkb_ivf_scan_dev, bit for bit.
+ * LUT rows live in registers and are looked up with PRMT; sums are accumulated without per-step clamps
+ * and a per-vector certificate decides which chunks the exact patch pass recomputes.
+ * workspace: device scratch of at least 16 + 8 * (number of (query, chunk) units) bytes:
+ *   estimate: Q * n_chunks units;  ivf_scan: Q * P * (slot_stride / 16) units. */
+TKB_API int tkb_estimate_native_dev(const void *native, int64_t n_chunks, int M, const uint8_t *tables, int Q,
+                            uint8_t *est, int64_t est_stride, int order, int signd,
+                            void *workspace, int64_t workspace_bytes, void *stream);
+TKB_API int tkb_ivf_scan_native_dev(const void *native, const int64_t *list_chunk_off, int n_lists, int M,
+                            const uint8_t *tables, const int32_t *probes, int Q, int P,
+                            uint8_t *est, int64_t slot_stride, int order, int signd,
+                            void *workspace, int64_t workspace_bytes, void *stream);
+
 /* Exact replay of the reference heap (ref: tinyknn/_fast_pq.pyx:153-206, :274-307) over
  * precomputed estimates, one heap per query.
  *   heap_idx int64[Q][R], heap_val int32[Q][R]: in/out (call tkb_heap_fill_dev first for a fresh heap)
@@ -128,6 +149,19 @@ TKB_API int tkb_ivf_replay_dev(const uint8_t *est, int64_t slot_stride, const in
                        const int32_t *list_size, int n_lists, const int64_t *ids,
                        const int32_t *probes, int Q, int P,
                        int64_t *heap_idx, int32_t *heap_val, int R, int signd, void *stream);
+
+/* Same replays for a FRESH heap (init_heap + query_pq in one call; the heap arrays are outputs only).
+ * These use the thread-per-query kernel (one query per thread, heaps in shared memory) when its
+ * preconditions hold and fall back to the warp-per-query kernel otherwise; results are identical.
+ * unique_labels != 0 certifies that no label occurs twice among the lists (an index built with one list per
+ * point), which makes the reference's label dedupe a no-op. fallback: int32[Q] device scratch. */
+TKB_API int tkb_replay_fresh_dev(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n,
+                         int64_t *heap_idx, int32_t *heap_val, int Q, int R, int signd, void *stream);
+TKB_API int tkb_ivf_replay_fresh_dev(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+                             const int32_t *list_size, int n_lists, const int64_t *ids,
+                             const int32_t *probes, int Q, int P,
+                             int64_t *heap_idx, int32_t *heap_val, int R, int signd,
+                             int unique_labels, int32_t *fallback, void *stream);
 
 /* Exact rescoring distances: replaces the arithmetic of knn_brute1 (ref: tinyknn/utils.py:89-92).
  *   dists[q][r] = sum_i (rows[idx[q][r]][i] - queries[q][i])^2, computed in the rows' dtype

@@ -366,3 +366,136 @@ def test_ivf_recall_floors():                              # ref: tests/test_ivf
     for metric in ("angular", "euclidean"):
         assert _recall(1000, 10, 30, 10, metric, 10, build_probes=4) >= 0.9
         assert _recall(1000, 10, 30, 10, metric, 4, build_probes=10) >= 0.9
+
+
+# ---- fast scan (device-native layout) vs generic scan vs oracle --------------------------------------------
+
+def _dev_estimates(packed, tables_u8, order, signd, impl):
+    """est (Q, 16*n_chunks) uint8 through the device entry points."""
+    from tinyknn_b200._lib import lib, check, ORDER_AVX, ORDER_SSE
+    n_chunks, M = packed.shape
+    Q = tables_u8.shape[0]
+    tdev = D.upload(tables_u8)
+    est = D.empty((Q, 16 * n_chunks), np.uint8)
+    o = ORDER_AVX if order == "avx" else ORDER_SSE
+    if impl == "fast":
+        nat = D.to_native(D.upload(packed), n_chunks, M)
+        back = D.from_native(nat, n_chunks, M).cpu().numpy().view(np.uint64)
+        assert np.array_equal(back, packed)                      # the native layout round-trips
+        ws = D.scan_workspace(Q * n_chunks)
+        check(lib.tkb_estimate_native_dev(D.ptr(nat), n_chunks, M, D.ptr(tdev), Q, D.ptr(est), 16 * n_chunks, o,
+                                          int(signd), D.ptr(ws), ws.numel(), D.stream_ptr()))
+        npatched = int(ws[:8].cpu().numpy().view(np.uint64)[0])
+    else:
+        check(lib.tkb_estimate_dev(D.ptr(D.upload(packed)), n_chunks, M, D.ptr(tdev), Q, D.ptr(est), 16 * n_chunks, o,
+                                   int(signd), D.stream_ptr()))
+        npatched = 0
+    return est.cpu().numpy(), npatched
+
+
+def test_fast_scan_bit_exact_all_table_kinds():
+    """The PRMT/deferred-clamp kernel must equal the step-by-step fold for every table: tables inside the
+    fast-path preconditions (certificate mostly passes), saturating tables (patch pass), and arbitrary
+    full-range tables (per-query exact path)."""
+    rng = np.random.default_rng(7)
+    for trial in range(48):
+        order = ("avx", "sse")[trial % 2]
+        signd = bool((trial // 2) % 2)
+        M = int(rng.integers(1, 17)) * 4
+        n = int(rng.integers(1, 6000))
+        kind = ("lut", "narrow", "full", "hot")[trial % 4]
+        Q = 3
+        tabs = []
+        for _ in range(Q):
+            if kind == "hot":                                    # small range but large values: many saturations
+                t = rng.integers(8, 30, size=(M, 16)).astype(np.int16)
+                t = (t - (20 if signd else 0)).astype(np.int8).view(np.uint8)
+            else:
+                t = _rand_case(rng, order, signd, M, 16, kind)[1]
+            tabs.append(t)
+        tabs = np.stack(tabs)
+        packed = _rand_case(rng, order, signd, M, n, "lut")[2]
+        fast, npatched = _dev_estimates(packed, tabs, order, signd, "fast")
+        for q in range(Q):
+            exp = np.zeros(2 * len(packed), np.uint64)
+            O.estimate_pq(packed, O.transform_tables(tabs[q]), exp, signd, order)
+            assert np.array_equal(fast[q], exp.view(np.uint8)), (trial, order, signd, M, n, kind, q, npatched)
+
+
+def test_fast_scan_large_and_patch_rate():
+    rng = np.random.default_rng(8)
+    n, M = 1_000_000, 32
+    codes = rng.integers(0, 16, size=(n, M), dtype=np.uint8)
+    packed = transform_data(codes)
+    tabs = np.stack([np.round(rng.exponential(6.0, size=(M, 16)) - 4).clip(-4, 23).astype(np.int8).view(np.uint8) for _ in range(2)])
+    fast, npatched = _dev_estimates(packed, tabs, "avx", True, "fast")
+    gen, _ = _dev_estimates(packed, tabs, "avx", True, "generic")
+    assert np.array_equal(fast, gen)
+    exp = np.zeros(2 * len(packed), np.uint64)
+    O.estimate_pq(packed, O.transform_tables(tabs[0]), exp, True, "avx")
+    assert np.array_equal(fast[0], exp.view(np.uint8))
+    print(f"fast scan: {npatched} of {2 * len(packed)} chunks went through the patch pass")
+
+
+def test_ivf_fast_equals_generic(golden):
+    z = golden["ivf"]
+    S = O.ivf_state_from_arrays(z, "euc128_")
+    ivf = _ivf_from_state(S)
+    qs = z["euc128_q"]
+    import tinyknn_b200.fast_pq as fp
+    try:
+        fp.SCAN_IMPL = "generic"
+        a = ivf.query_batch(qs, 10, n_probes=8, order="device", return_distances=True)
+        ha = ivf._last["heap_idx"].cpu().numpy()
+        fp.SCAN_IMPL = "fast"
+        b = ivf.query_batch(qs, 10, n_probes=8, order="device", return_distances=True)
+        hb = ivf._last["heap_idx"].cpu().numpy()
+    finally:
+        fp.SCAN_IMPL = "fast"
+    assert np.array_equal(ha, hb)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_replay_kernels_agree_with_oracle_fresh_heap():
+    """Thread-per-query replay (fresh heap, unique labels) == warp-per-query replay == oracle heap arrays."""
+    from tinyknn_b200._lib import lib, check
+    rng = np.random.default_rng(11)
+    for trial in range(12):
+        signd = bool(trial % 2)
+        Q, R = int(rng.integers(1, 70)), int(rng.integers(1, 200))
+        n = int(rng.integers(1, 4000))
+        nck = -(-n // 16)
+        est = rng.integers(0, 256, size=(Q, 16 * nck), dtype=np.uint8)
+        if trial % 3 == 0:
+            est = (est.astype(np.int16) // 8 + (100 if not signd else 0)).astype(np.uint8)     # many ties
+        edev = D.upload(est)
+        hi, hv = D.empty((Q, R), np.int64), D.empty((Q, R), np.int32)
+        check(lib.tkb_replay_fresh_dev(D.ptr(edev), 16 * nck, nck, n, D.ptr(hi), D.ptr(hv), Q, R, int(signd), D.stream_ptr()))
+        hi2, hv2 = D.empty((Q, R), np.int64), D.empty((Q, R), np.int32)
+        check(lib.tkb_heap_fill_dev(D.ptr(hi2), D.ptr(hv2), Q * R, int(signd), D.stream_ptr()))
+        check(lib.tkb_replay_dev(D.ptr(edev), 16 * nck, nck, n, D.ptr(hi2), D.ptr(hv2), Q, R, int(signd), None, D.stream_ptr()))
+        a, b, a2, b2 = hi.cpu().numpy(), hv.cpu().numpy(), hi2.cpu().numpy(), hv2.cpu().numpy()
+        for q in range(Q):
+            oi, ov = np.zeros(R, np.int64), np.zeros(R, np.int32)
+            O.init_heap(oi, ov, signd)
+            O.replay(est[q], n, oi, ov, signd)
+            assert np.array_equal(a[q], oi) and np.array_equal(b[q], ov), (trial, q)
+            assert np.array_equal(a2[q], oi) and np.array_equal(b2[q], ov), (trial, q)
+
+
+def test_ivf_duplicate_labels_use_dedupe_path():
+    """build_probes=2 puts every point in two lists: labels repeat, the reference dedupes on insert."""
+    np.random.seed(5)
+    X = np.random.randn(1500, 16).astype(np.float32)
+    qs = np.random.randn(24, 16).astype(np.float32)
+    ivf = tinyknn.IVF("euclidean", 20, tinyknn.FastPQ(2))
+    ivf.fit(X).build(X, n_probes=2)
+    S = O.IVFState.from_ivf(ivf)
+    assert not ivf.to_device()["unique_ids"]
+    ids, cnt = ivf.query_batch(qs, 10, n_probes=6, order="numpy")
+    heaps = ivf._last["heap_idx"].cpu().numpy()
+    for i, q in enumerate(qs):
+        tr = {}
+        exp = O.ivf_query(S, q, 10, n_probes=6, trace=tr)
+        assert np.array_equal(heaps[i], tr["heap_indices"]) and set(ids[i][:cnt[i]]) == set(exp)

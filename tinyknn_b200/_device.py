@@ -97,5 +97,48 @@ def mirror(arr):
     return dev
 
 
+def native_bytes(n_chunks, M):
+    """Size of the device-native code array for n_chunks chunks (tiles of 8 chunks)."""
+    return -(-n_chunks // 8) * 8 * M * 8
+
+
+def to_native(codes_dev, n_chunks, M):
+    """Device reference-layout codes (int64 bit patterns, (n_chunks, M)) -> native layout (uint8 tensor)."""
+    nat = empty((max(native_bytes(n_chunks, M), 16),), np.uint8)
+    _lib.check(_lib.lib.tkb_codes_to_native_dev(ptr(codes_dev), n_chunks, M, ptr(nat), stream_ptr()))
+    return nat
+
+
+def from_native(nat_dev, n_chunks, M):
+    out = empty((n_chunks, M), np.int64)
+    _lib.check(_lib.lib.tkb_codes_from_native_dev(ptr(nat_dev), n_chunks, M, ptr(out), stream_ptr()))
+    return out
+
+
+_native_mirrors = {}
+
+
+def mirror_native(packed):
+    """Native-layout device mirror of a host `packed` (uint64 (n_chunks, M)) array."""
+    key = id(packed)
+    fp = _fingerprint(packed)
+    hit = _native_mirrors.get(key)
+    if hit is not None and hit[0] == fp:
+        return hit[1]
+    nat = to_native(upload(packed), packed.shape[0], packed.shape[1])
+    _native_mirrors[key] = (fp, nat)
+    try:
+        weakref.finalize(packed, _native_mirrors.pop, key, None)
+    except TypeError:
+        pass
+    return nat
+
+
+def scan_workspace(units):
+    """Scratch for the fast scan's patch list: 16 + 8 bytes per (query, chunk) unit."""
+    return empty((16 + 8 * max(int(units), 1),), np.uint8)
+
+
 def drop_mirrors():
     _mirrors.clear()
+    _native_mirrors.clear()

@@ -30,9 +30,15 @@ SIGNATURES = {
     "tkb_lut_build_dev": [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _dbl, _dbl, _i, _vp, _vp, _vp, _vp, _vp],
     "tkb_estimate_dev": [_vp, _i64, _i, _vp, _i, _vp, _i64, _i, _i, _vp],
     "tkb_ivf_scan_dev": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _i64, _i, _i, _vp],
+    "tkb_codes_to_native_dev": [_vp, _i64, _i, _vp, _vp],
+    "tkb_codes_from_native_dev": [_vp, _i64, _i, _vp, _vp],
+    "tkb_estimate_native_dev": [_vp, _i64, _i, _vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp],
+    "tkb_ivf_scan_native_dev": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _i64, _i, _i, _vp, _i64, _vp],
     "tkb_heap_fill_dev": [_vp, _vp, _i64, _i, _vp],
     "tkb_replay_dev": [_vp, _i64, _i64, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
     "tkb_ivf_replay_dev": [_vp, _i64, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp],
+    "tkb_replay_fresh_dev": [_vp, _i64, _i64, _i, _vp, _vp, _i, _i, _i, _vp],
+    "tkb_ivf_replay_fresh_dev": [_vp, _i64, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
     "tkb_gather_dists_dev": [_vp, _i, _i64, _i, _vp, _vp, _i, _i, _vp, _vp],
     "tkb_select_probes_dev": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "tkb_select_topk_dev": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
@@ -44,10 +50,16 @@ class TinyKnnError(RuntimeError):
 
 
 def _load():
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            "tinyknn_b200: %s is missing. Build it with `python -m tinyknn_b200.build` "
-            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    from . import build as _build
+    if _build.needs_build():
+        # sources changed (or first use): rebuild in-tree when a compiler is around
+        try:
+            _build.build(force=True)
+        except Exception as e:                                   # noqa: BLE001
+            if not os.path.exists(LIB_PATH):
+                raise ImportError(
+                    "tinyknn_b200: %s is missing and could not be built (%s). Build it with "
+                    "`python -m tinyknn_b200.build` (nvcc, sm_100a). There is no CPU fallback." % (LIB_PATH, e))
     lib = ctypes.CDLL(LIB_PATH)
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export the symbol

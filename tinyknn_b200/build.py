@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtinyknn_b200.so")
-SOURCES = ["tkb_api.cu", "tkb_scan.cu", "tkb_heap.cu", "tkb_lut.cu", "tkb_rescore.cu"]
+SOURCES = ["tkb_api.cu", "tkb_scan.cu", "tkb_scan_fast.cu", "tkb_heap.cu", "tkb_lut.cu", "tkb_rescore.cu"]
 HEADERS = [os.path.join(CSRC, "tkb_common.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "tinyknn_b200.h")]
 
@@ -27,12 +27,24 @@ def find_nvcc():
     raise RuntimeError("nvcc not found: cannot build libtinyknn_b200.so")
 
 
+STAMP = LIB + ".srchash"
+
+
+def source_hash():
+    """Content hash of every source that goes into the library (mtimes do not survive the trip to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for path in [os.path.join(CSRC, s) for s in SOURCES] + HEADERS:
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    if not (os.path.exists(LIB) and os.path.exists(STAMP)):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -58,6 +70,8 @@ def build(force=False, verbose=False):
     subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
                           + ["-Xcompiler", "-fvisibility=hidden"])
     os.replace(tmp, LIB)
+    with open(STAMP, "w") as f:
+        f.write(source_hash())
     return LIB
 
 

@@ -182,6 +182,33 @@ int tkb_ivf_scan_dev(const uint64_t *codes, const int64_t *list_chunk_off, int n
                            signd, (cudaStream_t)stream);
 }
 
+int tkb_codes_to_native_dev(const uint64_t *codes, int64_t n_chunks, int M, void *native, void *stream)
+{
+    return launch_codes_to_native(codes, n_chunks, M, native, (cudaStream_t)stream);
+}
+
+int tkb_codes_from_native_dev(const void *native, int64_t n_chunks, int M, uint64_t *codes, void *stream)
+{
+    return launch_codes_from_native(native, n_chunks, M, codes, (cudaStream_t)stream);
+}
+
+int tkb_estimate_native_dev(const void *native, int64_t n_chunks, int M, const uint8_t *tables, int Q,
+                            uint8_t *est, int64_t est_stride, int order, int signd,
+                            void *workspace, int64_t workspace_bytes, void *stream)
+{
+    return launch_estimate_native(native, n_chunks, M, tables, Q, est, est_stride, order, signd, workspace,
+                                  workspace_bytes, (cudaStream_t)stream);
+}
+
+int tkb_ivf_scan_native_dev(const void *native, const int64_t *list_chunk_off, int n_lists, int M,
+                            const uint8_t *tables, const int32_t *probes, int Q, int P,
+                            uint8_t *est, int64_t slot_stride, int order, int signd,
+                            void *workspace, int64_t workspace_bytes, void *stream)
+{
+    return launch_ivf_scan_native(native, list_chunk_off, n_lists, M, tables, probes, Q, P, est, slot_stride, order,
+                                  signd, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int tkb_heap_fill_dev(int64_t *heap_idx, int32_t *heap_val, int64_t count, int signd, void *stream)
 {
     return launch_heap_fill(heap_idx, heap_val, count, signd, (cudaStream_t)stream);
@@ -201,6 +228,22 @@ int tkb_ivf_replay_dev(const uint8_t *est, int64_t slot_stride, const int64_t *l
 {
     return launch_ivf_replay(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
                              heap_val, R, signd, (cudaStream_t)stream);
+}
+
+int tkb_replay_fresh_dev(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n,
+                         int64_t *heap_idx, int32_t *heap_val, int Q, int R, int signd, void *stream)
+{
+    return launch_replay_fresh(est, est_stride, n_chunks, n, heap_idx, heap_val, Q, R, signd, (cudaStream_t)stream);
+}
+
+int tkb_ivf_replay_fresh_dev(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+                             const int32_t *list_size, int n_lists, const int64_t *ids,
+                             const int32_t *probes, int Q, int P,
+                             int64_t *heap_idx, int32_t *heap_val, int R, int signd,
+                             int unique_labels, int32_t *fallback, void *stream)
+{
+    return launch_ivf_replay_fresh(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
+                                   heap_val, R, signd, unique_labels, fallback, (cudaStream_t)stream);
 }
 
 int tkb_gather_dists_dev(const void *rows, int rows_dtype, int64_t n_rows, int d,

@@ -122,6 +122,156 @@ ivf_replay_kernel(const uint8_t *__restrict__ est, int64_t slot_stride,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Thread-per-query replay ("tpq"): one THREAD owns one query and its heap, 32 queries per warp.
+//
+// The sift-down of the reference heap is single-threaded by nature; giving it a whole warp (above)
+// leaves 31 lanes idle for ~90 % of the instructions. Here every lane replays its own query, the
+// heaps live in shared memory interleaved by lane (entry j of lane t at word j*32+t: every lane
+// stays in its own bank whatever j it touches), and an entry is 8 bytes: value | slot<<16, position.
+// Labels are looked up once, at the end. Preconditions (checked by the launcher / the kernel):
+//   * fresh heap (filled here), * labels are unique across the segments of a query, so the
+//     reference's label dedupe (ref: _fast_pq.pyx:284-287) can never fire -- the host certifies this
+//     for the index, and a query whose probe list contains negative (Python-wrapped) entries is
+//     handed to the warp-per-query kernel through `fallback`, * 256*R bytes of shared memory per warp.
+// ------------------------------------------------------------------------------------------------
+template <bool SIGNED>
+__device__ __forceinline__ uint32_t cand_mask16(const uint4 e, int bound)
+{
+    const uint32_t b4 = (uint32_t)(bound & 0xff) * 0x01010101u;
+    const uint32_t m0 = cmp_lt4<SIGNED>(e.x, b4) & 0x80808080u, m1 = cmp_lt4<SIGNED>(e.y, b4) & 0x80808080u;
+    const uint32_t m2 = cmp_lt4<SIGNED>(e.z, b4) & 0x80808080u, m3 = cmp_lt4<SIGNED>(e.w, b4) & 0x80808080u;
+    // gather the 4 sign bits of each word into a nibble: bit 7,15,23,31 -> 0..3
+    auto pack = [](uint32_t m) { return ((m >> 7) | (m >> 14) | (m >> 21) | (m >> 28)) & 0xfu; };
+    return pack(m0) | (pack(m1) << 4) | (pack(m2) << 8) | (pack(m3) << 12);
+}
+
+// mode 0: one segment per query (est row q, n vectors, label = position)      [probe selection]
+// mode 1: P segments per query taken from the probe list, labels from `ids`   [IVF.query]
+template <bool SIGNED>
+__global__ void __launch_bounds__(32)
+replay_tpq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, int64_t n_chunks0, int n0,
+                  const int64_t *__restrict__ list_chunk_off, const int32_t *__restrict__ list_size, int n_lists,
+                  const int64_t *__restrict__ ids, const int32_t *__restrict__ probes, int Q, int P,
+                  int64_t *__restrict__ heap_idx, int32_t *__restrict__ heap_val, int R, int *__restrict__ fallback)
+{
+    extern __shared__ uint32_t tpq_sm[];
+    const int lane = threadIdx.x;
+    uint32_t *A = tpq_sm + lane;                    // value (low 16, two's complement) | slot << 16
+    uint32_t *B = tpq_sm + 32 * R + lane;           // position inside the segment
+    const int q = blockIdx.x * 32 + lane;
+    if (q >= Q) return;
+    const int init = SIGNED ? 127 : 255;
+    for (int j = 0; j < R; j++) { A[32 * j] = (uint32_t)init | 0xffff0000u; B[32 * j] = 0; }
+#define TPQ_VAL(j) ((int)(int16_t)(A[32 * (j)] & 0xffffu))
+    bool ok = true;
+    if (mode == 1)
+        for (int s = 0; s < P; s++) {
+            const int l = probes[(size_t)q * P + s];
+            if (l < 0 && l != PROBE_SKIP) ok = false;          // Python-wrapped index: lists may repeat
+        }
+    if (fallback) fallback[q] = ok ? 0 : 1;
+    if (!ok) return;
+
+    int bound = init;
+    for (int s = 0; s < P; s++) {
+        int64_t nc;
+        int n;
+        const uint4 *ep;
+        if (mode == 1) {
+            const int l = probes[(size_t)q * P + s];
+            if (l == PROBE_SKIP) continue;
+            const int64_t c0 = list_chunk_off[l];
+            nc = list_chunk_off[l + 1] - c0;
+            n = list_size[l];
+            ep = reinterpret_cast<const uint4 *>(est + ((size_t)q * P + s) * stride);
+        } else {
+            nc = n_chunks0; n = n0;
+            ep = reinterpret_cast<const uint4 *>(est + (size_t)q * stride);
+        }
+        const int64_t nc_real = ((int64_t)n + 15) >> 4;        // chunks holding real vectors (tile padding is skipped)
+        if (nc > nc_real) nc = nc_real;
+        if (nc <= 0) continue;
+        uint4 nxt = ldg_nc_u4(ep);
+        for (int64_t c = 0; c < nc; c++) {
+            const uint4 e = nxt;
+            if (c + 1 < nc) nxt = ldg_nc_u4(ep + c + 1);       // prefetch: hides the load behind the inserts
+            uint32_t m = cand_mask16<SIGNED>(e, bound);
+            if (m == 0) continue;
+            const int frozen = bound;                          // bound is frozen for the chunk
+            const uint32_t ws[4] = {e.x, e.y, e.z, e.w};
+            while (m) {
+                const int v = __ffs(m) - 1;
+                m &= m - 1;
+                const int64_t pos = 16 * c + v;
+                if (pos >= n) break;                           // padding positions are the last ones
+                const uint32_t byte = (ws[v >> 2] >> (8 * (v & 3))) & 0xffu;
+                const int ev = SIGNED ? (int)(int8_t)byte : (int)byte;
+                if (ev >= frozen) continue;                    // (cannot happen: mask was built with frozen)
+                // replace the root and sift down (ref: _fast_pq.pyx:290-307)
+                int j = 0;
+                for (;;) {
+                    int nx = j, nv = ev;
+                    const int l_ = 2 * j + 1, r_ = 2 * j + 2;
+                    if (l_ < R) { const int lv = TPQ_VAL(l_); if (lv > nv) { nx = l_; nv = lv; } }
+                    if (r_ < R) { const int rv = TPQ_VAL(r_); if (rv > nv) { nx = r_; nv = rv; } }
+                    if (nx == j) break;
+                    A[32 * j] = A[32 * nx]; B[32 * j] = B[32 * nx];
+                    j = nx;
+                }
+                A[32 * j] = ((uint32_t)ev & 0xffffu) | ((uint32_t)s << 16);
+                B[32 * j] = (uint32_t)pos;
+            }
+            bound = TPQ_VAL(0);
+            bound = SIGNED ? (int)(int8_t)bound : (int)(uint8_t)bound;
+        }
+    }
+    // resolve labels and write the heap arrays
+    int64_t *hi = heap_idx + (size_t)q * R;
+    int32_t *hv = heap_val + (size_t)q * R;
+    for (int j = 0; j < R; j++) {
+        const uint32_t a = A[32 * j];
+        const uint32_t s = a >> 16;
+        int64_t label = -1;
+        if (s != 0xffffu) {
+            const int64_t pos = (int64_t)B[32 * j];
+            if (mode == 1) {
+                const int l = probes[(size_t)q * P + s];
+                label = ids[16 * list_chunk_off[l] + pos];
+            } else {
+                label = pos;
+            }
+        }
+        hi[j] = label;
+        hv[j] = (int)(int16_t)(a & 0xffffu);
+    }
+#undef TPQ_VAL
+}
+
+// warp-per-query IVF replay restricted to the queries flagged by the tpq kernel
+template <bool SIGNED>
+__global__ void __launch_bounds__(32 * REPLAY_WARPS)
+ivf_replay_fallback_kernel(const uint8_t *__restrict__ est, int64_t slot_stride,
+                           const int64_t *__restrict__ list_chunk_off, const int32_t *__restrict__ list_size,
+                           int n_lists, const int64_t *__restrict__ ids, const int32_t *__restrict__ probes,
+                           int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, const int *__restrict__ fallback)
+{
+    const int q = blockIdx.x * REPLAY_WARPS + (threadIdx.x >> 5);
+    if (q >= Q || !fallback[q]) return;
+    const int lane = threadIdx.x & 31;
+    for (int j = lane; j < R; j += 32) { heap_idx[(size_t)q * R + j] = -1; heap_val[(size_t)q * R + j] = SIGNED ? 127 : 255; }
+    __syncwarp();
+    for (int s = 0; s < P; s++) {
+        int l = probes[(size_t)q * P + s];
+        if (l == PROBE_SKIP) continue;
+        if (l < 0) l += n_lists;
+        const int64_t c0 = list_chunk_off[l];
+        const int64_t nc = list_chunk_off[l + 1] - c0;
+        replay_segment<SIGNED>(est + ((size_t)q * P + s) * slot_stride, nc, list_size[l], ids + 16 * c0,
+                               heap_idx + (size_t)q * R, heap_val + (size_t)q * R, R, lane);
+    }
+}
+
 __global__ void heap_fill_kernel(int64_t *heap_idx, int32_t *heap_val, int64_t count, int init_val)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,6 +316,67 @@ int launch_ivf_replay(const uint8_t *est, int64_t slot_stride, const int64_t *li
     const unsigned blocks = (unsigned)((Q + REPLAY_WARPS - 1) / REPLAY_WARPS);
     if (signd) ivf_replay_kernel<true><<<blocks, 32 * REPLAY_WARPS, 0, st>>>(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R);
     else       ivf_replay_kernel<false><<<blocks, 32 * REPLAY_WARPS, 0, st>>>(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R);
+    TKB_LAUNCH_CHECK();
+    return TKB_OK;
+}
+
+
+// Fresh-heap replays with certified-unique labels: thread-per-query kernel + fallback for flagged queries.
+static bool tpq_fits(int R) { return R > 0 && (size_t)R * 256 <= 200 * 1024 && R < 0xffff; }
+
+int launch_replay_fresh(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n, int64_t *heap_idx,
+                        int32_t *heap_val, int Q, int R, int signd, cudaStream_t st)
+{
+    TKB_REQUIRE(Q >= 0 && R >= 0 && n_chunks >= 0, "negative extent");
+    if (Q == 0 || R == 0) return TKB_OK;
+    TKB_REQUIRE(heap_idx && heap_val, "null pointer");
+    if (!tpq_fits(R) || n_chunks == 0) {
+        if (int rc = launch_heap_fill(heap_idx, heap_val, (int64_t)Q * R, signd, st)) return rc;
+        return launch_replay(est, est_stride, n_chunks, n, heap_idx, heap_val, Q, R, signd, nullptr, st);
+    }
+    TKB_REQUIRE(est && est_stride % 16 == 0 && (uintptr_t)est % 16 == 0, "est must be 16-byte aligned/strided");
+    const size_t smem = (size_t)R * 256;
+    const unsigned blocks = (unsigned)((Q + 31) / 32);
+    if (signd) {
+        TKB_CUDA(cudaFuncSetAttribute(replay_tpq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        replay_tpq_kernel<true><<<blocks, 32, smem, st>>>(0, est, est_stride, n_chunks, n, nullptr, nullptr, 0, nullptr, nullptr, Q, 1, heap_idx, heap_val, R, nullptr);
+    } else {
+        TKB_CUDA(cudaFuncSetAttribute(replay_tpq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        replay_tpq_kernel<false><<<blocks, 32, smem, st>>>(0, est, est_stride, n_chunks, n, nullptr, nullptr, 0, nullptr, nullptr, Q, 1, heap_idx, heap_val, R, nullptr);
+    }
+    TKB_LAUNCH_CHECK();
+    return TKB_OK;
+}
+
+int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+                            const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
+                            int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int signd,
+                            int unique_labels, int *fallback, cudaStream_t st)
+{
+    TKB_REQUIRE(Q >= 0 && R >= 0 && P >= 0 && n_lists > 0, "bad extent");
+    if (Q == 0 || R == 0) return TKB_OK;
+    TKB_REQUIRE(heap_idx && heap_val, "null pointer");
+    if (!unique_labels || !tpq_fits(R) || P == 0 || P >= 0xffff || !fallback) {
+        if (int rc = launch_heap_fill(heap_idx, heap_val, (int64_t)Q * R, signd, st)) return rc;
+        return launch_ivf_replay(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
+                                 heap_val, R, signd, st);
+    }
+    TKB_REQUIRE(est && list_chunk_off && list_size && ids && probes, "null pointer");
+    TKB_REQUIRE(slot_stride % 16 == 0 && (uintptr_t)est % 16 == 0, "est must be 16-byte aligned/strided");
+    const size_t smem = (size_t)R * 256;
+    const unsigned blocks = (unsigned)((Q + 31) / 32);
+    const unsigned fblocks = (unsigned)((Q + REPLAY_WARPS - 1) / REPLAY_WARPS);
+    if (signd) {
+        TKB_CUDA(cudaFuncSetAttribute(replay_tpq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        replay_tpq_kernel<true><<<blocks, 32, smem, st>>>(1, est, slot_stride, 0, 0, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
+        TKB_LAUNCH_CHECK();
+        ivf_replay_fallback_kernel<true><<<fblocks, 32 * REPLAY_WARPS, 0, st>>>(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
+    } else {
+        TKB_CUDA(cudaFuncSetAttribute(replay_tpq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        replay_tpq_kernel<false><<<blocks, 32, smem, st>>>(1, est, slot_stride, 0, 0, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
+        TKB_LAUNCH_CHECK();
+        ivf_replay_fallback_kernel<false><<<fblocks, 32 * REPLAY_WARPS, 0, st>>>(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
+    }
     TKB_LAUNCH_CHECK();
     return TKB_OK;
 }

@@ -46,6 +46,11 @@ def _order():
     return ORDER_AVX if avx else ORDER_SSE
 
 
+# "fast": PRMT/register-LUT kernel on the device-native layout (default).
+# "generic": the step-by-step kernel on the reference layout (kept for A/B parity checks).
+SCAN_IMPL = "fast"
+
+
 TransformedData = namedtuple("TransformedData", "size packed")
 
 _GAUSS_CODE = np.array(
@@ -227,7 +232,12 @@ class _FastDistanceTable:
             raise ValueError("transformed data must be a C-contiguous 2-D uint64 array")
         n_chunks, M = packed.shape
         est = D.empty((16 * n_chunks,), np.uint8)
-        if n_chunks:
+        if n_chunks and SCAN_IMPL == "fast":
+            ws = D.scan_workspace(n_chunks)
+            check(lib.tkb_estimate_native_dev(D.ptr(D.mirror_native(packed)), n_chunks, M, D.ptr(self._tables_dev(M)), 1,
+                                              D.ptr(est), 16 * n_chunks, _order(), int(bool(self.signed)),
+                                              D.ptr(ws), ws.numel(), D.stream_ptr()))
+        elif n_chunks:
             check(lib.tkb_estimate_dev(D.ptr(D.mirror(packed)), n_chunks, M, D.ptr(self._tables_dev(M)), 1,
                                        D.ptr(est), 16 * n_chunks, _order(), int(bool(self.signed)), D.stream_ptr()))
         return est
@@ -256,10 +266,8 @@ class _FastDistanceTable:
         true_n, packed = transformed_data
         est = self._scan_dev(packed)
         hidx, hval = D.empty((rescore,), np.int64), D.empty((rescore,), np.int32)
-        st = D.stream_ptr()
-        check(lib.tkb_heap_fill_dev(D.ptr(hidx), D.ptr(hval), rescore, int(bool(self.signed)), st))
-        check(lib.tkb_replay_dev(D.ptr(est), 16 * len(packed), len(packed), true_n, D.ptr(hidx), D.ptr(hval),
-                                 1, rescore, int(bool(self.signed)), None, st))
+        check(lib.tkb_replay_fresh_dev(D.ptr(est), 16 * len(packed), len(packed), true_n, D.ptr(hidx), D.ptr(hval),
+                                       1, rescore, int(bool(self.signed)), D.stream_ptr()))
         return hidx, hval
 
     def top(self, transformed_data, data, k=1, rescore=None):

@@ -102,27 +102,42 @@ class IVF:
         for l, td in enumerate(self.pq_transformed_points):
             n_l, packed = (0, None) if td is None or not isinstance(td, tuple) else td
             nc = 0 if packed is None else packed.shape[0]
+            nc8 = -(-nc // 8) * 8                       # every list starts on a tile (8-chunk) boundary
             if nc:
                 assert packed.shape[1] == M and packed.dtype == np.uint64
                 parts.append(packed)
-                ids_l = np.full(16 * nc, -1, dtype=np.int64)
+                if nc8 > nc:
+                    parts.append(np.zeros((nc8 - nc, M), dtype=np.uint64))
+                ids_l = np.full(16 * nc8, -1, dtype=np.int64)
                 ids_l[:n_l] = np.asarray(self.ids[l], dtype=np.int64)[:n_l]
                 id_parts.append(ids_l)
             sizes[l] = n_l
-            chunks[l + 1] = chunks[l] + nc
+            chunks[l + 1] = chunks[l] + nc8
         codes = np.concatenate(parts) if parts else np.zeros((1, M), dtype=np.uint64)
         ids = np.concatenate(id_parts) if id_parts else np.zeros(16, dtype=np.int64)
+        real = ids[ids >= 0]
+        unique_ids = bool(len(np.unique(real)) == len(real))     # one list per point: the heap's label dedupe is a no-op
         data = self.data
         if not isinstance(data, np.ndarray) or data.dtype not in (np.float32, np.float64):
             data = np.ascontiguousarray(data, dtype=np.float64)
         dev = dict(
             C=C, M=M, n_lists=n_lists, max_chunks=int(np.max(np.diff(chunks))) if n_lists else 0,
-            codes=D.upload(codes), list_chunk_off=D.upload(chunks), list_size=D.upload(sizes), ids=D.upload(ids),
-            center_codes=D.upload(ctd.packed), centers=D.upload(np.ascontiguousarray(self.active_centers, dtype=np.float32)),
+            codes=D.to_native(D.upload(codes), codes.shape[0], M), n_chunks_total=int(codes.shape[0]),
+            list_chunk_off=D.upload(chunks), list_size=D.upload(sizes), ids=D.upload(ids),
+            center_codes=D.to_native(D.upload(ctd.packed), ctd.packed.shape[0], M), center_chunks=int(ctd.packed.shape[0]),
+            centers=D.upload(np.ascontiguousarray(self.active_centers, dtype=np.float32)),
             data=D.upload(data), data_dtype=DTYPE_F32 if data.dtype == np.float32 else DTYPE_F64,
-            d=int(data.shape[1]), host_sizes=sizes, host_chunks=chunks)
+            d=int(data.shape[1]), host_sizes=sizes, host_chunks=chunks, unique_ids=unique_ids)
         self.__dict__["_dev"] = dev
         return dev
+
+    @staticmethod
+    def _ref_codes(dev, key, n_chunks):
+        """Reference-layout copy of a native code array (generic scan A/B mode only; exercises the round trip)."""
+        ck = key + "_ref"
+        if ck not in dev:
+            dev[ck] = D.from_native(dev[key], n_chunks, dev["M"])
+        return dev[ck]
 
     # ------------------------------------------------------------------ profiling hooks -----
     def profile(self, enabled=True):
@@ -204,14 +219,20 @@ class IVF:
         tables, qn = lut["tables"], lut["q"]
         # 2. probe selection (ref: ivf.py:131 -> fast_pq.py:284-312)
         cc = dev["center_codes"]
-        nck = cc.shape[0]
+        nck = dev["center_chunks"]
         est_c = D.empty((Q, 16 * nck), np.uint8)
+        fast = _fp.SCAN_IMPL == "fast"
         with self._stage("coarse_scan"):
-            check(lib.tkb_estimate_dev(D.ptr(cc), nck, M, D.ptr(tables), Q, D.ptr(est_c), 16 * nck, _fp._order(), sg, st))
+            if fast:
+                ws = D.scan_workspace(Q * nck)
+                check(lib.tkb_estimate_native_dev(D.ptr(cc), nck, M, D.ptr(tables), Q, D.ptr(est_c), 16 * nck,
+                                                  _fp._order(), sg, D.ptr(ws), ws.numel(), st))
+            else:
+                check(lib.tkb_estimate_dev(D.ptr(self._ref_codes(dev, "center_codes", nck)), nck, M, D.ptr(tables), Q,
+                                           D.ptr(est_c), 16 * nck, _fp._order(), sg, st))
         hci, hcv = D.empty((Q, Rc), np.int64), D.empty((Q, Rc), np.int32)
         with self._stage("coarse_replay"):
-            check(lib.tkb_heap_fill_dev(D.ptr(hci), D.ptr(hcv), Q * Rc, sg, st))
-            check(lib.tkb_replay_dev(D.ptr(est_c), 16 * nck, nck, C, D.ptr(hci), D.ptr(hcv), Q, Rc, sg, None, st))
+            check(lib.tkb_replay_fresh_dev(D.ptr(est_c), 16 * nck, nck, C, D.ptr(hci), D.ptr(hcv), Q, Rc, sg, st))
         probes = D.empty((Q, P), np.int32)
         if Rc <= P:
             check(lib.tkb_select_probes_dev(D.ptr(hci), None, DTYPE_F32, Q, Rc, P, D.ptr(probes), st))
@@ -228,14 +249,22 @@ class IVF:
         # 3. scan of the probed lists + ordered replay (ref: ivf.py:137-150)
         est = D.empty((Q, P, slot_stride), np.uint8)
         with self._stage("scan"):
-            check(lib.tkb_ivf_scan_dev(D.ptr(dev["codes"]), D.ptr(dev["list_chunk_off"]), n_lists, M, D.ptr(tables),
-                                       D.ptr(probes), Q, P, D.ptr(est), slot_stride, _fp._order(), sg, st))
+            if fast:
+                ws = D.scan_workspace(Q * P * (slot_stride // 16))
+                check(lib.tkb_ivf_scan_native_dev(D.ptr(dev["codes"]), D.ptr(dev["list_chunk_off"]), n_lists, M,
+                                                  D.ptr(tables), D.ptr(probes), Q, P, D.ptr(est), slot_stride,
+                                                  _fp._order(), sg, D.ptr(ws), ws.numel(), st))
+            else:
+                check(lib.tkb_ivf_scan_dev(D.ptr(self._ref_codes(dev, "codes", dev["n_chunks_total"])),
+                                           D.ptr(dev["list_chunk_off"]), n_lists, M, D.ptr(tables),
+                                           D.ptr(probes), Q, P, D.ptr(est), slot_stride, _fp._order(), sg, st))
         hi_, hv_ = D.empty((Q, pass_1), np.int64), D.empty((Q, pass_1), np.int32)
+        fb = D.empty((Q,), np.int32)
         with self._stage("replay"):
-            check(lib.tkb_heap_fill_dev(D.ptr(hi_), D.ptr(hv_), Q * pass_1, sg, st))
-            check(lib.tkb_ivf_replay_dev(D.ptr(est), slot_stride, D.ptr(dev["list_chunk_off"]), D.ptr(dev["list_size"]),
-                                         n_lists, D.ptr(dev["ids"]), D.ptr(probes), Q, P, D.ptr(hi_), D.ptr(hv_),
-                                         pass_1, sg, st))
+            check(lib.tkb_ivf_replay_fresh_dev(D.ptr(est), slot_stride, D.ptr(dev["list_chunk_off"]),
+                                               D.ptr(dev["list_size"]), n_lists, D.ptr(dev["ids"]), D.ptr(probes), Q, P,
+                                               D.ptr(hi_), D.ptr(hv_), pass_1, sg, int(dev.get("unique_ids", False)),
+                                               D.ptr(fb), st))
         # 4. exact rescoring (ref: ivf.py:154-163)
         ddt = np.float32 if dev["data_dtype"] == DTYPE_F32 else np.float64
         dd = D.empty((Q, pass_1), ddt)

@@ -144,7 +144,7 @@ def build_ivf(X, metric, n_clusters, pq=None, kmeans_iters=6, fit_sample=200_000
     active = centers[used].contiguous()
     order = t.argsort(assign, stable=True)
     sizes = t.bincount(assign, minlength=C)
-    chunks = (sizes + 15) // 16
+    chunks = ((sizes + 127) // 128) * 8                            # whole tiles of 8 chunks (native layout)
     chunk_off = t.zeros(C + 1, dtype=t.int64, device=X.device)
     chunk_off[1:] = chunks.cumsum(0)
     start = t.zeros(C + 1, dtype=t.int64, device=X.device)
@@ -168,8 +168,9 @@ def build_ivf(X, metric, n_clusters, pq=None, kmeans_iters=6, fit_sample=200_000
     ivf.pq_transformed_centers = center_td
     packed_h = packed.cpu().numpy().view(np.uint64)
     order_h, sizes_h, off_h, start_h = order.cpu().numpy(), sizes.cpu().numpy(), chunk_off.cpu().numpy(), start.cpu().numpy()
-    ivf.pq_transformed_points = [TransformedData(int(sizes_h[l]), packed_h[off_h[l]:off_h[l + 1]]) for l in range(C)] \
-        + [None] * (n_clusters - C)
+    # host views hold exactly ceil(n/16) chunks per list, like the reference (tile padding is device-only)
+    ivf.pq_transformed_points = [TransformedData(int(sizes_h[l]), packed_h[off_h[l]:off_h[l] + (int(sizes_h[l]) + 15) // 16])
+                                 for l in range(C)] + [None] * (n_clusters - C)
     ivf.ids = [order_h[start_h[l]:start_h[l + 1]] for l in range(C)] + [None] * (n_clusters - C)
     ivf.data = X.cpu().numpy()
     if keep_device:
@@ -178,10 +179,13 @@ def build_ivf(X, metric, n_clusters, pq=None, kmeans_iters=6, fit_sample=200_000
         off_full = t.cat([chunk_off, chunk_off[-1:].repeat(n_clusters - C)])
         sizes_full = t.cat([sizes, t.zeros(n_clusters - C, dtype=sizes.dtype, device=X.device)]).to(t.int32)
         ivf.__dict__["_dev"] = dict(
-            C=C, M=M, n_lists=n_clusters, max_chunks=int(chunks.max().item()), codes=packed, list_chunk_off=off_full,
-            list_size=sizes_full, ids=ids_padded, center_codes=D.upload(center_td.packed),
+            C=C, M=M, n_lists=n_clusters, max_chunks=int(chunks.max().item()),
+            codes=D.to_native(packed, packed.shape[0], M), n_chunks_total=int(packed.shape[0]), list_chunk_off=off_full,
+            list_size=sizes_full, ids=ids_padded,
+            center_codes=D.to_native(D.upload(center_td.packed), center_td.packed.shape[0], M),
+            center_chunks=int(center_td.packed.shape[0]),
             centers=active.float().contiguous(), data=X.contiguous(), data_dtype=DTYPE_F32, d=d,
-            host_sizes=sizes_full.cpu().numpy(), host_chunks=off_full.cpu().numpy())
+            host_sizes=sizes_full.cpu().numpy(), host_chunks=off_full.cpu().numpy(), unique_ids=True)
     return ivf
 
 
