@@ -248,11 +248,13 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    torch.cuda.profiler.start()                 # `ncu --profile-from-start off` captures exactly the timed steps
     e0.record()
     for i in range(args.steps):
         ivf.query_batch(dev_batches[i % 4], to_host=False, **kw)
     e1.record()
     sync_all()
+    torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
     launches = _lib.n_calls - calls0
