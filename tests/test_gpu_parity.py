@@ -499,3 +499,45 @@ def test_ivf_duplicate_labels_use_dedupe_path():
         tr = {}
         exp = O.ivf_query(S, q, 10, n_probes=6, trace=tr)
         assert np.array_equal(heaps[i], tr["heap_indices"]) and set(ids[i][:cnt[i]]) == set(exp)
+
+
+def test_ivf_replay_fresh_random_segments():
+    """IVF-mode fresh replay over random est bytes, random (also empty / tiny) lists, skipped probe slots and
+    heaps small enough that the queue-replay kernel has to cut its rounds: heap arrays == oracle, per query."""
+    from tinyknn_b200._lib import lib, check, PROBE_SKIP
+    rng = np.random.default_rng(21)
+    for trial in range(10):
+        signd = bool(trial % 2)
+        n_lists = int(rng.integers(3, 40))
+        sizes = rng.integers(0, 700, size=n_lists).astype(np.int32)
+        sizes[rng.integers(0, n_lists)] = 0
+        sizes[rng.integers(0, n_lists)] = 1
+        nc8 = (-(-sizes.astype(np.int64) // 128)) * 8                   # lists start on 8-chunk tiles
+        off = np.zeros(n_lists + 1, np.int64)
+        off[1:] = np.cumsum(nc8)
+        ids = rng.permutation(16 * int(off[-1]) + 5).astype(np.int64)[:16 * int(off[-1])] + 10 ** 11
+        Q, P, R = int(rng.integers(1, 60)), int(rng.integers(1, min(n_lists, 12) + 1)), int(rng.integers(1, 160))
+        probes = np.stack([rng.permutation(n_lists)[:P] for _ in range(Q)]).astype(np.int32)
+        if trial % 3 == 0:
+            probes[rng.integers(0, Q), P - 1] = PROBE_SKIP
+        stride = 16 * int(max(nc8.max(), 1))
+        est = rng.integers(0, 256, size=(Q, P, stride), dtype=np.uint8)
+        if trial % 2 == 0:
+            est = (est // 16 + (60 if not signd else 0)).astype(np.uint8)  # few distinct values: ties, long queues
+        hi, hv, fb = D.empty((Q, R), np.int64), D.empty((Q, R), np.int32), D.empty((Q,), np.int32)
+        d_est, d_off, d_sizes, d_ids, d_probes = (D.upload(x) for x in (est, off, sizes, ids, probes))
+        check(lib.tkb_ivf_replay_fresh_dev(D.ptr(d_est), stride, D.ptr(d_off), D.ptr(d_sizes), n_lists,
+                                           D.ptr(d_ids), D.ptr(d_probes), Q, P, D.ptr(hi), D.ptr(hv), R,
+                                           int(signd), 1, D.ptr(fb), D.stream_ptr()))
+        a, b = hi.cpu().numpy(), hv.cpu().numpy()
+        for q in range(Q):
+            oi, ov = np.zeros(R, np.int64), np.zeros(R, np.int32)
+            O.init_heap(oi, ov, signd)
+            for s in range(P):
+                l = int(probes[q, s])
+                if l == PROBE_SKIP or sizes[l] == 0:
+                    continue
+                ncr = -(-int(sizes[l]) // 16)
+                O.replay(est[q, s, :16 * ncr], int(sizes[l]), oi, ov, signd,
+                         np.ascontiguousarray(ids[16 * off[l]:16 * off[l] + 16 * ncr]))
+            assert np.array_equal(a[q], oi) and np.array_equal(b[q], ov), (trial, q)

@@ -10,6 +10,8 @@
 // can test 32 chunks (512 estimates) against the current bound with byte-SIMD compares and one
 // ballot, jump to the first chunk that admits anything, process exactly that chunk with the frozen
 // bound, refresh the bound and re-test only the chunks after it. Cost ~ number of inserts, not N.
+#include <stdlib.h>
+
 #include "tkb_common.cuh"
 
 namespace tkb {
@@ -248,6 +250,220 @@ replay_tpq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, int
 #undef TPQ_VAL
 }
 
+// ------------------------------------------------------------------------------------------------
+// Queue replay ("rq"): the fresh-heap replay used by the query path.
+//
+// The thread-per-query kernel above is instruction-efficient (32 queries per warp) but every lane walks
+// ALL of its query's chunks, 32 unrelated 16-byte loads per step, and the lanes of a warp only rarely
+// need the sift at the same time. Here a CTA owns QPC queries and alternates two phases per round:
+//   produce : each warp takes whole queries; its 32 lanes read 32 consecutive chunks of the query's
+//             estimate stream (one coalesced 512-byte read), compare them with the query's bound AS OF
+//             THE START OF THE ROUND and append the surviving (value, payload) records, in stream
+//             order, to the query's queue in shared memory. The bound is monotone non-increasing
+//             (SURVEY.md H1), so a stale bound admits a superset of the true candidates, never misses one.
+//   consume : warp 0, one LANE per query, walks its queue in order and applies the reference rule
+//             exactly (bound frozen when the first record of a new chunk arrives, strict <, replace the
+//             root, sift down), heaps interleaved by lane in shared memory.
+// Round windows double (the admission rate after n vectors is ~R/n), so a query needs ~log2(n/R) rounds
+// and the lanes only ever touch records that had a real chance. payload = position inside the `ids`
+// array (mode 1) or inside the segment (mode 0); labels are resolved once, at the end.
+// Same preconditions as the tpq kernel: fresh heap, labels unique across a query's segments.
+// ------------------------------------------------------------------------------------------------
+constexpr int RQ_THREADS = 256;
+constexpr uint64_t RQ_PAY_MASK = (1ULL << 56) - 1;
+
+__device__ __forceinline__ int rq_val(uint64_t e) { return (int)(uint32_t)(e >> 32) >> 24; }     // top 8 bits, signed
+
+struct RqSeg {            // one segment of a query's stream, resolved for a lane
+    const uint4 *ep;      // its estimates
+    int64_t pay0;         // payload of position 0
+    int n;                // true number of vectors
+};
+
+template <bool SIGNED>
+__global__ void __launch_bounds__(RQ_THREADS)
+replay_rq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, const int64_t *__restrict__ seg_off,
+                 int64_t n_chunks0, int n0, const int64_t *__restrict__ list_chunk_off,
+                 const int32_t *__restrict__ list_size, int n_lists, const int64_t *__restrict__ ids,
+                 const int32_t *__restrict__ probes, int Q, int P, int64_t *__restrict__ heap_idx,
+                 int32_t *__restrict__ heap_val, int R, int *__restrict__ fallback, int QPC, int QCAP)
+{
+    extern __shared__ __align__(16) unsigned char rq_sm[];
+    uint64_t *H = reinterpret_cast<uint64_t *>(rq_sm);                     // [R][QPC]  entry j of query t at j*QPC+t
+    uint64_t *QU = H + (size_t)R * QPC;                                    // [QPC][QCAP+1]
+    int *cum = reinterpret_cast<int *>(QU + (size_t)QPC * (QCAP + 1));     // [QPC][P+1] real chunks before segment s
+    int *s_cursor = cum + (size_t)QPC * (P + 1);
+    int *s_seg = s_cursor + QPC, *s_bound = s_seg + QPC, *s_count = s_bound + QPC, *s_round = s_count + QPC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = RQ_THREADS / 32;
+    const int q0 = blockIdx.x * QPC;
+    const int init = SIGNED ? 127 : 255;
+    const uint64_t empty = ((uint64_t)(uint32_t)init << 56) | RQ_PAY_MASK;
+
+    // ---- set-up: heaps, segment tables ------------------------------------------------------------
+    for (int i = tid; i < R * QPC; i += RQ_THREADS) H[i] = empty;
+    for (int t = tid; t < QPC; t += RQ_THREADS) {
+        const int q = q0 + t;
+        int *c = cum + (size_t)t * (P + 1);
+        bool ok = q < Q;
+        int run = 0;
+        c[0] = 0;
+        for (int s = 0; s < P; s++) {
+            int nc = 0;
+            if (ok) {
+                if (mode == 1) {
+                    const int l = probes[(size_t)q * P + s];
+                    if (l < 0 && l != PROBE_SKIP) ok = false;              // Python-wrapped index: lists may repeat
+                    else if (l != PROBE_SKIP) nc = (list_size[l] + 15) >> 4;
+                } else {
+                    int64_t r = ((int64_t)n0 + 15) >> 4;
+                    nc = (int)(r < n_chunks0 ? r : n_chunks0);
+                }
+            }
+            run += nc;
+            c[s + 1] = run;
+        }
+        if (q < Q && fallback) fallback[q] = ok ? 0 : 1;
+        if (!ok) for (int s = 0; s <= P; s++) c[s] = 0;                    // nothing to do here
+        s_cursor[t] = 0; s_seg[t] = 0; s_bound[t] = init; s_count[t] = 0; s_round[t] = 0;
+    }
+    __syncthreads();
+
+    for (;;) {
+        // ---- produce ------------------------------------------------------------------------------
+        bool more = false;
+        for (int t = warp; t < QPC; t += n_warps) {
+            const int *c = cum + (size_t)t * (P + 1);
+            const int total = c[P];
+            const int cursor = s_cursor[t];
+            if (cursor >= total) { if (lane == 0) s_count[t] = 0; continue; }
+            const int q = q0 + t;
+            const int bound = s_bound[t];
+            // first window: just enough to fill the heap; then the stream position doubles every round
+            int W = s_round[t] == 0 ? ((R + 15) >> 4) + 1 : (cursor < 32 ? 32 : cursor);
+            if (W > (1 << 16)) W = 1 << 16;
+            int end = (total - cursor < W) ? total : cursor + W;
+            int count = 0, sg = s_seg[t];
+            uint64_t *qu = QU + (size_t)t * (QCAP + 1);
+            for (int base = cursor; base < end; base += 32) {
+                const int cc = base + lane;
+                const bool act = cc < end;
+                uint32_t m = 0;
+                uint4 e = make_uint4(0, 0, 0, 0);
+                int64_t pay = 0;
+                int sl = sg;
+                if (act) {
+                    while (cc >= c[sl + 1]) sl++;
+                    const int local = cc - c[sl];
+                    int n;
+                    const uint8_t *ep;
+                    if (mode == 1) {
+                        const int l = probes[(size_t)q * P + sl];
+                        n = list_size[l];
+                        pay = 16 * (list_chunk_off[l] + local);
+                        ep = est + (seg_off ? seg_off[(size_t)q * P + sl] : ((int64_t)q * P + sl) * stride);
+                    } else {
+                        n = n0; pay = 16 * (int64_t)local;
+                        ep = est + (int64_t)q * stride;
+                    }
+                    e = ldg_nc_u4(reinterpret_cast<const uint4 *>(ep) + local);
+                    const int rem = n - 16 * local;                        // >= 1 (only real chunks are in the stream)
+                    m = cand_mask16<SIGNED>(e, bound) & (rem >= 16 ? 0xffffu : ((1u << rem) - 1u));
+                }
+                sg = __shfl_sync(FULL, sl, 31 < end - 1 - base ? 31 : end - 1 - base);   // segment of the last active lane
+                const int cnt = __popc(m);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                const int tot = __shfl_sync(FULL, incl, 31);
+                bool cut = false;
+                int keep_tot = tot;
+                if (count + tot > QCAP) {                                  // queue full: stop at a chunk boundary
+                    const unsigned over = __ballot_sync(FULL, count + incl > QCAP);
+                    const int cl = __ffs(over) - 1;                        // first chunk that does not fit
+                    keep_tot = __shfl_sync(FULL, incl - cnt, cl);
+                    sg = __shfl_sync(FULL, sl, cl);                       // the next round resumes at chunk base+cl
+                    if (lane >= cl) m = 0;
+                    end = base + cl;
+                    cut = true;
+                }
+                int k = count + incl - cnt;
+                const uint32_t ws[4] = {e.x, e.y, e.z, e.w};
+                while (m) {
+                    const int v = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t byte = (ws[v >> 2] >> (8 * (v & 3))) & 0xffu;
+                    qu[k++] = ((uint64_t)byte << 56) | (uint64_t)(pay + v);
+                }
+                count += keep_tot;
+                if (cut) break;
+            }
+            if (lane == 0) { s_cursor[t] = end; s_seg[t] = sg; s_count[t] = count; s_round[t] = 1; }
+            more = true;
+        }
+        if (!__syncthreads_or(more)) break;
+        // ---- consume ------------------------------------------------------------------------------
+        if (warp == 0) {
+            const int t = lane;
+            const int cnt = t < QPC ? s_count[t] : 0;
+            int mx = cnt;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+            const uint64_t *qu = QU + (size_t)t * (QCAP + 1);
+            uint64_t *h = H + t;
+            int64_t cur_chunk = -1;
+            int frozen = 0;
+            for (int i = 0; i < mx; i++) {
+                if (i >= cnt) continue;
+                const uint64_t rec = qu[i];
+                const int ev = SIGNED ? rq_val(rec) : (int)(rec >> 56);
+                const int64_t ch = (int64_t)((rec & RQ_PAY_MASK) >> 4);
+                if (ch != cur_chunk) {                                     // first candidate of a chunk: freeze the bound
+                    cur_chunk = ch;
+                    const uint64_t root = h[0];
+                    frozen = SIGNED ? rq_val(root) : (int)(root >> 56);
+                }
+                if (ev >= frozen) continue;
+                // replace the root and sift down (ref: _fast_pq.pyx:290-307)
+                int j = 0;
+                for (;;) {
+                    const int l_ = 2 * j + 1, r_ = 2 * j + 2;
+                    if (l_ >= R) break;
+                    const uint64_t el = h[(size_t)l_ * QPC];
+                    const uint64_t er = h[(size_t)(r_ < R ? r_ : l_) * QPC];
+                    const int lv = SIGNED ? rq_val(el) : (int)(el >> 56);
+                    const int rv = r_ < R ? (SIGNED ? rq_val(er) : (int)(er >> 56)) : INT32_MIN;
+                    int nx = j, nv = ev;
+                    uint64_t en = 0;
+                    if (lv > nv) { nx = l_; nv = lv; en = el; }
+                    if (rv > nv) { nx = r_; nv = rv; en = er; }
+                    if (nx == j) break;
+                    h[(size_t)j * QPC] = en;
+                    j = nx;
+                }
+                h[(size_t)j * QPC] = rec;
+            }
+            if (t < QPC) {
+                const uint64_t root = h[0];
+                s_bound[t] = SIGNED ? rq_val(root) : (int)(root >> 56);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- resolve labels and write the heap arrays --------------------------------------------------
+    for (int i = tid; i < R * QPC; i += RQ_THREADS) {
+        const int t = i / R, j = i - t * R;
+        const int q = q0 + t;
+        if (q >= Q) continue;
+        const uint64_t e = H[(size_t)j * QPC + t];
+        const uint64_t pay = e & RQ_PAY_MASK;
+        int64_t label = -1;
+        if (pay != RQ_PAY_MASK) label = (mode == 1) ? ids[pay] : (int64_t)pay;
+        heap_idx[(size_t)q * R + j] = label;
+        heap_val[(size_t)q * R + j] = SIGNED ? rq_val(e) : (int)(e >> 56);
+    }
+}
+
 // warp-per-query IVF replay restricted to the queries flagged by the tpq kernel
 template <bool SIGNED>
 __global__ void __launch_bounds__(32 * REPLAY_WARPS)
@@ -324,17 +540,70 @@ int launch_ivf_replay(const uint8_t *est, int64_t slot_stride, const int64_t *li
 // Fresh-heap replays with certified-unique labels: thread-per-query kernel + fallback for flagged queries.
 static bool tpq_fits(int R) { return R > 0 && (size_t)R * 256 <= 200 * 1024 && R < 0xffff; }
 
+// Queue-replay launch geometry: QPC queries per CTA (a power of two <= 32), queue capacity QCAP records.
+struct RqGeom { int qpc, qcap; size_t smem; };
+
+static size_t rq_smem(int R, int P, int qpc, int qcap)
+{
+    return (size_t)qpc * (8 * (size_t)R + 8 * ((size_t)qcap + 1) + 4 * ((size_t)P + 1) + 20) + 16;
+}
+
+static bool rq_geometry(int Q, int R, int P, RqGeom &g)
+{
+    if (R <= 0 || P <= 0) return false;
+    g.qcap = 2 * R < 64 ? 64 : 2 * R;
+    // enough CTAs to cover the machine about twice, as many queries per CTA as that allows (<= 16:
+    // the consumer warp pays for the slowest of its lanes), and at most ~45 KB so several CTAs share an SM
+    int qpc = 16;
+    while (qpc > 1 && (Q + qpc - 1) / qpc < 2 * 148) qpc >>= 1;
+    while (qpc > 1 && rq_smem(R, P, qpc, g.qcap) > 45 * 1024) qpc >>= 1;
+    g.qpc = qpc;
+    g.smem = rq_smem(R, P, qpc, g.qcap);
+    return g.smem <= 200 * 1024;
+}
+
+static int replay_impl()
+{
+    static int impl = -1;                      // 0 = queue replay (default), 1 = thread-per-query (A/B measurements)
+    if (impl < 0) {
+        const char *e = getenv("TKB_REPLAY");
+        impl = (e && strcmp(e, "tpq") == 0) ? 1 : 0;
+    }
+    return impl;
+}
+
+template <bool SIGNED>
+static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t *seg_off, int64_t n_chunks0, int n0,
+                     const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, const int64_t *ids,
+                     const int32_t *probes, int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int *fallback,
+                     const RqGeom &g, cudaStream_t st)
+{
+    TKB_CUDA(cudaFuncSetAttribute(replay_rq_kernel<SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    const unsigned blocks = (unsigned)((Q + g.qpc - 1) / g.qpc);
+    replay_rq_kernel<SIGNED><<<blocks, RQ_THREADS, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off,
+                                                                 list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val,
+                                                                 R, fallback, g.qpc, g.qcap);
+    TKB_LAUNCH_CHECK();
+    return TKB_OK;
+}
+
 int launch_replay_fresh(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n, int64_t *heap_idx,
                         int32_t *heap_val, int Q, int R, int signd, cudaStream_t st)
 {
     TKB_REQUIRE(Q >= 0 && R >= 0 && n_chunks >= 0, "negative extent");
     if (Q == 0 || R == 0) return TKB_OK;
     TKB_REQUIRE(heap_idx && heap_val, "null pointer");
-    if (!tpq_fits(R) || n_chunks == 0) {
+    RqGeom g;
+    const bool use_rq = replay_impl() == 0 && n_chunks < (1LL << 27) && rq_geometry(Q, R, 1, g);
+    if (n_chunks == 0 || (!use_rq && !tpq_fits(R))) {
         if (int rc = launch_heap_fill(heap_idx, heap_val, (int64_t)Q * R, signd, st)) return rc;
         return launch_replay(est, est_stride, n_chunks, n, heap_idx, heap_val, Q, R, signd, nullptr, st);
     }
     TKB_REQUIRE(est && est_stride % 16 == 0 && (uintptr_t)est % 16 == 0, "est must be 16-byte aligned/strided");
+    if (use_rq) {
+        if (signd) return launch_rq<true>(0, est, est_stride, nullptr, n_chunks, n, nullptr, nullptr, 0, nullptr, nullptr, Q, 1, heap_idx, heap_val, R, nullptr, g, st);
+        return launch_rq<false>(0, est, est_stride, nullptr, n_chunks, n, nullptr, nullptr, 0, nullptr, nullptr, Q, 1, heap_idx, heap_val, R, nullptr, g, st);
+    }
     const size_t smem = (size_t)R * 256;
     const unsigned blocks = (unsigned)((Q + 31) / 32);
     if (signd) {
@@ -348,6 +617,29 @@ int launch_replay_fresh(const uint8_t *est, int64_t est_stride, int64_t n_chunks
     return TKB_OK;
 }
 
+template <bool SIGNED>
+static int ivf_replay_fresh_t(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+                              const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
+                              int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int *fallback,
+                              bool use_rq, const RqGeom &g, cudaStream_t st)
+{
+    if (use_rq) {
+        if (int rc = launch_rq<SIGNED>(1, est, slot_stride, nullptr, 0, 0, list_chunk_off, list_size, n_lists, ids, probes,
+                                       Q, P, heap_idx, heap_val, R, fallback, g, st)) return rc;
+    } else {
+        const size_t smem = (size_t)R * 256;
+        TKB_CUDA(cudaFuncSetAttribute(replay_tpq_kernel<SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        replay_tpq_kernel<SIGNED><<<(unsigned)((Q + 31) / 32), 32, smem, st>>>(1, est, slot_stride, 0, 0, list_chunk_off, list_size,
+                                                                             n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
+        TKB_LAUNCH_CHECK();
+    }
+    // queries whose probe list holds Python-wrapped (negative) entries: warp-per-query kernel with label dedupe
+    ivf_replay_fallback_kernel<SIGNED><<<(unsigned)((Q + REPLAY_WARPS - 1) / REPLAY_WARPS), 32 * REPLAY_WARPS, 0, st>>>(
+        est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
+    TKB_LAUNCH_CHECK();
+    return TKB_OK;
+}
+
 int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
                             const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
                             int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int signd,
@@ -356,29 +648,19 @@ int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64
     TKB_REQUIRE(Q >= 0 && R >= 0 && P >= 0 && n_lists > 0, "bad extent");
     if (Q == 0 || R == 0) return TKB_OK;
     TKB_REQUIRE(heap_idx && heap_val, "null pointer");
-    if (!unique_labels || !tpq_fits(R) || P == 0 || P >= 0xffff || !fallback) {
+    RqGeom g;
+    const bool use_rq = replay_impl() == 0 && rq_geometry(Q, R, P, g);
+    if (!unique_labels || P == 0 || P >= 0xffff || !fallback || (!use_rq && !tpq_fits(R))) {
         if (int rc = launch_heap_fill(heap_idx, heap_val, (int64_t)Q * R, signd, st)) return rc;
         return launch_ivf_replay(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
                                  heap_val, R, signd, st);
     }
     TKB_REQUIRE(est && list_chunk_off && list_size && ids && probes, "null pointer");
     TKB_REQUIRE(slot_stride % 16 == 0 && (uintptr_t)est % 16 == 0, "est must be 16-byte aligned/strided");
-    const size_t smem = (size_t)R * 256;
-    const unsigned blocks = (unsigned)((Q + 31) / 32);
-    const unsigned fblocks = (unsigned)((Q + REPLAY_WARPS - 1) / REPLAY_WARPS);
-    if (signd) {
-        TKB_CUDA(cudaFuncSetAttribute(replay_tpq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        replay_tpq_kernel<true><<<blocks, 32, smem, st>>>(1, est, slot_stride, 0, 0, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
-        TKB_LAUNCH_CHECK();
-        ivf_replay_fallback_kernel<true><<<fblocks, 32 * REPLAY_WARPS, 0, st>>>(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
-    } else {
-        TKB_CUDA(cudaFuncSetAttribute(replay_tpq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        replay_tpq_kernel<false><<<blocks, 32, smem, st>>>(1, est, slot_stride, 0, 0, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
-        TKB_LAUNCH_CHECK();
-        ivf_replay_fallback_kernel<false><<<fblocks, 32 * REPLAY_WARPS, 0, st>>>(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
-    }
-    TKB_LAUNCH_CHECK();
-    return TKB_OK;
+    if (signd) return ivf_replay_fresh_t<true>(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P,
+                                               heap_idx, heap_val, R, fallback, use_rq, g, st);
+    return ivf_replay_fresh_t<false>(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P,
+                                     heap_idx, heap_val, R, fallback, use_rq, g, st);
 }
 
 }  // namespace tkb
