@@ -270,37 +270,30 @@ replay_tpq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, int
 // Same preconditions as the tpq kernel: fresh heap, labels unique across a query's segments.
 // ------------------------------------------------------------------------------------------------
 constexpr int RQ_THREADS = 256;
-constexpr uint64_t RQ_PAY_MASK = (1ULL << 56) - 1;
+constexpr uint32_t RQ_EMPTY = 0xffffffffu;        // payload of a heap slot that was never filled
 
-__device__ __forceinline__ int rq_val(uint64_t e) { return (int)(uint32_t)(e >> 32) >> 24; }     // top 8 bits, signed
-
-struct RqSeg {            // one segment of a query's stream, resolved for a lane
-    const uint4 *ep;      // its estimates
-    int64_t pay0;         // payload of position 0
-    int n;                // true number of vectors
-};
-
+// heap entry / queue record: .x = payload (stream position: 16 * stream chunk + lane), .y = value (int32)
 template <bool SIGNED>
 __global__ void __launch_bounds__(RQ_THREADS)
 replay_rq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, const int64_t *__restrict__ seg_off,
                  int64_t n_chunks0, int n0, const int64_t *__restrict__ list_chunk_off,
                  const int32_t *__restrict__ list_size, int n_lists, const int64_t *__restrict__ ids,
                  const int32_t *__restrict__ probes, int Q, int P, int64_t *__restrict__ heap_idx,
-                 int32_t *__restrict__ heap_val, int R, int *__restrict__ fallback, int QPC, int QCAP)
+                 int32_t *__restrict__ heap_val, int R, int *__restrict__ fallback, int QPC, int QCAP, int LPW)
 {
     extern __shared__ __align__(16) unsigned char rq_sm[];
-    uint64_t *H = reinterpret_cast<uint64_t *>(rq_sm);                     // [R][QPC]  entry j of query t at j*QPC+t
-    uint64_t *QU = H + (size_t)R * QPC;                                    // [QPC][QCAP+1]
+    uint2 *H = reinterpret_cast<uint2 *>(rq_sm);                           // [R+1][QPC] slot j of query t at j*QPC+t; slot R = sentinel
+    uint2 *QU = H + (size_t)(R + 1) * QPC;                                 // [QPC][QCAP+1]
     int *cum = reinterpret_cast<int *>(QU + (size_t)QPC * (QCAP + 1));     // [QPC][P+1] real chunks before segment s
     int *s_cursor = cum + (size_t)QPC * (P + 1);
     int *s_seg = s_cursor + QPC, *s_bound = s_seg + QPC, *s_count = s_bound + QPC, *s_round = s_count + QPC;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = RQ_THREADS / 32;
     const int q0 = blockIdx.x * QPC;
     const int init = SIGNED ? 127 : 255;
-    const uint64_t empty = ((uint64_t)(uint32_t)init << 56) | RQ_PAY_MASK;
 
     // ---- set-up: heaps, segment tables ------------------------------------------------------------
-    for (int i = tid; i < R * QPC; i += RQ_THREADS) H[i] = empty;
+    for (int i = tid; i < (R + 1) * QPC; i += RQ_THREADS)
+        H[i] = i < R * QPC ? make_uint2(RQ_EMPTY, (uint32_t)init) : make_uint2(RQ_EMPTY, (uint32_t)INT32_MIN);
     for (int t = tid; t < QPC; t += RQ_THREADS) {
         const int q = q0 + t;
         int *c = cum + (size_t)t * (P + 1);
@@ -343,13 +336,12 @@ replay_rq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, cons
             if (W > (1 << 16)) W = 1 << 16;
             int end = (total - cursor < W) ? total : cursor + W;
             int count = 0, sg = s_seg[t];
-            uint64_t *qu = QU + (size_t)t * (QCAP + 1);
+            uint2 *qu = QU + (size_t)t * (QCAP + 1);
             for (int base = cursor; base < end; base += 32) {
                 const int cc = base + lane;
                 const bool act = cc < end;
                 uint32_t m = 0;
                 uint4 e = make_uint4(0, 0, 0, 0);
-                int64_t pay = 0;
                 int sl = sg;
                 if (act) {
                     while (cc >= c[sl + 1]) sl++;
@@ -357,19 +349,18 @@ replay_rq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, cons
                     int n;
                     const uint8_t *ep;
                     if (mode == 1) {
-                        const int l = probes[(size_t)q * P + sl];
-                        n = list_size[l];
-                        pay = 16 * (list_chunk_off[l] + local);
+                        n = list_size[probes[(size_t)q * P + sl]];
                         ep = est + (seg_off ? seg_off[(size_t)q * P + sl] : ((int64_t)q * P + sl) * stride);
                     } else {
-                        n = n0; pay = 16 * (int64_t)local;
+                        n = n0;
                         ep = est + (int64_t)q * stride;
                     }
                     e = ldg_nc_u4(reinterpret_cast<const uint4 *>(ep) + local);
                     const int rem = n - 16 * local;                        // >= 1 (only real chunks are in the stream)
                     m = cand_mask16<SIGNED>(e, bound) & (rem >= 16 ? 0xffffu : ((1u << rem) - 1u));
                 }
-                sg = __shfl_sync(FULL, sl, 31 < end - 1 - base ? 31 : end - 1 - base);   // segment of the last active lane
+                const int last = end - 1 - base;
+                sg = __shfl_sync(FULL, sl, last < 31 ? last : 31);         // segment of the last active lane
                 const int cnt = __popc(m);
                 int incl = cnt;
 #pragma unroll
@@ -381,7 +372,7 @@ replay_rq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, cons
                     const unsigned over = __ballot_sync(FULL, count + incl > QCAP);
                     const int cl = __ffs(over) - 1;                        // first chunk that does not fit
                     keep_tot = __shfl_sync(FULL, incl - cnt, cl);
-                    sg = __shfl_sync(FULL, sl, cl);                       // the next round resumes at chunk base+cl
+                    sg = __shfl_sync(FULL, sl, cl);                        // the next round resumes at chunk base+cl
                     if (lane >= cl) m = 0;
                     end = base + cl;
                     cut = true;
@@ -392,7 +383,7 @@ replay_rq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, cons
                     const int v = __ffs(m) - 1;
                     m &= m - 1;
                     const uint32_t byte = (ws[v >> 2] >> (8 * (v & 3))) & 0xffu;
-                    qu[k++] = ((uint64_t)byte << 56) | (uint64_t)(pay + v);
+                    qu[k++] = make_uint2(16u * (uint32_t)cc + v, SIGNED ? (uint32_t)(int)(int8_t)byte : byte);
                 }
                 count += keep_tot;
                 if (cut) break;
@@ -401,50 +392,47 @@ replay_rq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, cons
             more = true;
         }
         if (!__syncthreads_or(more)) break;
-        // ---- consume ------------------------------------------------------------------------------
-        if (warp == 0) {
-            const int t = lane;
-            const int cnt = t < QPC ? s_count[t] : 0;
+        // ---- consume: warp w replays queries [w*LPW, (w+1)*LPW), one lane each (LPW = a power of two) ----
+        if (warp * LPW < QPC) {
+            const int t = warp * LPW + lane;
+            const bool mine = lane < LPW && t < QPC;
+            const int cnt = mine ? s_count[t] : 0;
             int mx = cnt;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
-            const uint64_t *qu = QU + (size_t)t * (QCAP + 1);
-            uint64_t *h = H + t;
-            int64_t cur_chunk = -1;
-            int frozen = 0;
-            for (int i = 0; i < mx; i++) {
-                if (i >= cnt) continue;
-                const uint64_t rec = qu[i];
-                const int ev = SIGNED ? rq_val(rec) : (int)(rec >> 56);
-                const int64_t ch = (int64_t)((rec & RQ_PAY_MASK) >> 4);
-                if (ch != cur_chunk) {                                     // first candidate of a chunk: freeze the bound
-                    cur_chunk = ch;
-                    const uint64_t root = h[0];
-                    frozen = SIGNED ? rq_val(root) : (int)(root >> 56);
+            if (mine) {
+                const uint2 *qu = QU + (size_t)t * (QCAP + 1);
+                unsigned char *hb = reinterpret_cast<unsigned char *>(H + t);   // slot j at hb + j*S
+                const uint32_t S = (uint32_t)QPC * 8u, lim = (uint32_t)R * S;
+                uint32_t cur_chunk = RQ_EMPTY;
+                int frozen = 0;
+                for (int i = 0; i < mx; i++) {
+                    if (i >= cnt) continue;
+                    const uint2 rec = qu[i];
+                    const int ev = (int)rec.y;
+                    if ((rec.x >> 4) != cur_chunk) {                       // first candidate of a chunk: freeze the bound
+                        cur_chunk = rec.x >> 4;
+                        frozen = (int)reinterpret_cast<const uint2 *>(hb)->y;
+                    }
+                    if (ev >= frozen) continue;
+                    // replace the root and sift down (ref: _fast_pq.pyx:290-307): the larger child moves up while
+                    // it is strictly greater than the new value; the right child wins only when strictly greater
+                    // than the left one. Slot R is a sentinel (INT32_MIN), so a right child always exists.
+                    uint32_t jo = 0;
+                    for (;;) {
+                        const uint32_t lo = 2 * jo + S;
+                        if (lo >= lim) break;
+                        const uint2 el = *reinterpret_cast<const uint2 *>(hb + lo);
+                        const uint2 er = *reinterpret_cast<const uint2 *>(hb + lo + S);
+                        const bool pr = (int)er.y > (int)el.y;
+                        const uint2 ce = pr ? er : el;
+                        if ((int)ce.y <= ev) break;
+                        *reinterpret_cast<uint2 *>(hb + jo) = ce;
+                        jo = pr ? lo + S : lo;
+                    }
+                    *reinterpret_cast<uint2 *>(hb + jo) = rec;
                 }
-                if (ev >= frozen) continue;
-                // replace the root and sift down (ref: _fast_pq.pyx:290-307)
-                int j = 0;
-                for (;;) {
-                    const int l_ = 2 * j + 1, r_ = 2 * j + 2;
-                    if (l_ >= R) break;
-                    const uint64_t el = h[(size_t)l_ * QPC];
-                    const uint64_t er = h[(size_t)(r_ < R ? r_ : l_) * QPC];
-                    const int lv = SIGNED ? rq_val(el) : (int)(el >> 56);
-                    const int rv = r_ < R ? (SIGNED ? rq_val(er) : (int)(er >> 56)) : INT32_MIN;
-                    int nx = j, nv = ev;
-                    uint64_t en = 0;
-                    if (lv > nv) { nx = l_; nv = lv; en = el; }
-                    if (rv > nv) { nx = r_; nv = rv; en = er; }
-                    if (nx == j) break;
-                    h[(size_t)j * QPC] = en;
-                    j = nx;
-                }
-                h[(size_t)j * QPC] = rec;
-            }
-            if (t < QPC) {
-                const uint64_t root = h[0];
-                s_bound[t] = SIGNED ? rq_val(root) : (int)(root >> 56);
+                s_bound[t] = (int)reinterpret_cast<const uint2 *>(hb)->y;
             }
         }
         __syncthreads();
@@ -455,12 +443,22 @@ replay_rq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, cons
         const int t = i / R, j = i - t * R;
         const int q = q0 + t;
         if (q >= Q) continue;
-        const uint64_t e = H[(size_t)j * QPC + t];
-        const uint64_t pay = e & RQ_PAY_MASK;
+        const uint2 e = H[(size_t)j * QPC + t];
         int64_t label = -1;
-        if (pay != RQ_PAY_MASK) label = (mode == 1) ? ids[pay] : (int64_t)pay;
+        if (e.x != RQ_EMPTY) {
+            const int cc = (int)(e.x >> 4), v = (int)(e.x & 15u);
+            if (mode == 1) {
+                const int *c = cum + (size_t)t * (P + 1);
+                int lo = 0, hi = P;                                        // segment s with c[s] <= cc < c[s+1]
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (c[mid] <= cc) lo = mid; else hi = mid; }
+                const int l = probes[(size_t)q * P + lo];
+                label = ids[16 * (list_chunk_off[l] + (cc - c[lo])) + v];
+            } else {
+                label = 16 * (int64_t)cc + v;
+            }
+        }
         heap_idx[(size_t)q * R + j] = label;
-        heap_val[(size_t)q * R + j] = SIGNED ? rq_val(e) : (int)(e >> 56);
+        heap_val[(size_t)q * R + j] = (int)e.y;
     }
 }
 
@@ -541,11 +539,11 @@ int launch_ivf_replay(const uint8_t *est, int64_t slot_stride, const int64_t *li
 static bool tpq_fits(int R) { return R > 0 && (size_t)R * 256 <= 200 * 1024 && R < 0xffff; }
 
 // Queue-replay launch geometry: QPC queries per CTA (a power of two <= 32), queue capacity QCAP records.
-struct RqGeom { int qpc, qcap; size_t smem; };
+struct RqGeom { int qpc, qcap, lpw; size_t smem; };
 
 static size_t rq_smem(int R, int P, int qpc, int qcap)
 {
-    return (size_t)qpc * (8 * (size_t)R + 8 * ((size_t)qcap + 1) + 4 * ((size_t)P + 1) + 20) + 16;
+    return (size_t)qpc * (8 * ((size_t)R + 1) + 8 * ((size_t)qcap + 1) + 4 * ((size_t)P + 1) + 20) + 16;
 }
 
 static bool rq_geometry(int Q, int R, int P, RqGeom &g)
@@ -558,6 +556,11 @@ static bool rq_geometry(int Q, int R, int P, RqGeom &g)
     while (qpc > 1 && (Q + qpc - 1) / qpc < 2 * 148) qpc >>= 1;
     while (qpc > 1 && rq_smem(R, P, qpc, g.qcap) > 45 * 1024) qpc >>= 1;
     g.qpc = qpc;
+    // lanes per consumer warp: few lanes = little lock-step waste but more warps to issue; all 8 warps can consume
+    static int lpw_env = -1;
+    if (lpw_env < 0) { const char *e = getenv("TKB_RQ_LPW"); lpw_env = e ? atoi(e) : 0; }
+    g.lpw = (lpw_env == 1 || lpw_env == 2 || lpw_env == 4 || lpw_env == 8 || lpw_env == 16) ? lpw_env : 4;
+    while (g.lpw * (RQ_THREADS / 32) < qpc) g.lpw <<= 1;
     g.smem = rq_smem(R, P, qpc, g.qcap);
     return g.smem <= 200 * 1024;
 }
@@ -582,7 +585,7 @@ static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t
     const unsigned blocks = (unsigned)((Q + g.qpc - 1) / g.qpc);
     replay_rq_kernel<SIGNED><<<blocks, RQ_THREADS, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off,
                                                                  list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val,
-                                                                 R, fallback, g.qpc, g.qcap);
+                                                                 R, fallback, g.qpc, g.qcap, g.lpw);
     TKB_LAUNCH_CHECK();
     return TKB_OK;
 }
