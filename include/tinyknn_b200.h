@@ -52,6 +52,8 @@ extern "C" {
 TKB_API int         tkb_version(void);
 TKB_API const char *tkb_last_error(void);
 TKB_API int         tkb_device_count(int *count);
+/* number of CUDA kernels this library has launched so far in this process (all threads) */
+TKB_API long long   tkb_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Host-buffer surface == the reference's Cython modules                                       */
@@ -106,13 +108,36 @@ TKB_API int tkb_lut_build_dev(const float *queries, int Q, int d, int normalize,
 TKB_API int tkb_estimate_dev(const uint64_t *codes, int64_t n_chunks, int M, const uint8_t *tables, int Q,
                      uint8_t *est, int64_t est_stride, int order, int signd, void *stream);
 
-/* IVF scan: for query q and probe slot s, estimates of every vector of list probes[q][s] with
- * LUT q. Lists live in one codes array: list l = chunks [list_chunk_off[l], list_chunk_off[l+1]).
- *   probes int32[Q][P]  (negative entries index from the end, like a Python list)
- *   est    uint8[Q][P][slot_stride], slot_stride >= 16 * (largest list in chunks) */
-TKB_API int tkb_ivf_scan_dev(const uint64_t *codes, const int64_t *list_chunk_off, int n_lists, int M,
+/* Where the estimates of an IVF scan live. Segment (q, s) = the estimates of list probes[q][s] under LUT q,
+ * one byte per vector position, 16 * ceil(list_size / 16) bytes (the reference pads a list to whole chunks,
+ * ref: tinyknn/fast_pq.py:165-169). Two addressing modes, chosen by `seg_off`:
+ *   seg_off == NULL : est + (q * P + s) * slot_stride            (slot_stride >= 16 * chunks of the largest list)
+ *   seg_off != NULL : est + seg_off[q * P + s], int64[Q][P] from tkb_ivf_plan_dev; a negative offset means the
+ *                     segment is not in this buffer (list owned by another rank) and is skipped.
+ * Lists live in one codes array: list l = chunks [list_chunk_off[l], list_chunk_off[l+1]); list_size int32[n_lists]
+ * (may be NULL for the scans: then every stored chunk of the list is scanned, padding included).
+ * probes int32[Q][P]: negative entries index from the end, like a Python list (ref: tinyknn/ivf.py:141);
+ * INT32_MIN marks a probe slot that does not exist. */
+
+/* IVF scan on the reference layout (step-by-step kernel). max_list_chunks: chunks of the largest list (0: slot_stride/16). */
+TKB_API int tkb_ivf_scan_dev(const uint64_t *codes, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                      const uint8_t *tables, const int32_t *probes, int Q, int P,
-                     uint8_t *est, int64_t slot_stride, int order, int signd, void *stream);
+                     uint8_t *est, int64_t slot_stride, const int64_t *seg_off, int64_t max_list_chunks,
+                     int order, int signd, void *stream);
+
+/* Segment planning (compact estimate buffers; the exchange of a list-sharded index, DESIGN.md "multi-GPU").
+ *   list_owner int32[n_lists] or NULL (n_ranks == 1): the rank that stores each list
+ *   TKB_PLAN_SEND: all Q queries, segments whose list this rank owns, grouped by the home rank of the query
+ *                  (q / q_per_rank), then (q, s)         -> seg_off int64[Q][P]
+ *   TKB_PLAN_RECV: the home queries [rank*q_per_rank, (rank+1)*q_per_rank), every segment, grouped by the owner
+ *                  of the list, then (q, s)              -> seg_off int64[q_per_rank][P]  (row 0 = first home query)
+ *   group_bytes int64[2*n_ranks+1] out: bytes per group (the all-to-all split sizes), the total, the group bases
+ *   workspace: 8 * queries * n_ranks bytes */
+#define TKB_PLAN_SEND 0
+#define TKB_PLAN_RECV 1
+TKB_API int tkb_ivf_plan_dev(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner,
+                     int n_lists, int mode, int rank, int n_ranks, int q_per_rank,
+                     int64_t *seg_off, int64_t *group_bytes, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* Device-native code layout for the fast scan (chosen at upload, round-trips to the reference layout).
  * tile = 8 chunks; the 16 bytes of (tile t, pair p, chunk slot s) sit at ((t*M/2 + p)*8 + s)*16 and hold
@@ -123,41 +148,43 @@ TKB_API int tkb_codes_to_native_dev(const uint64_t *codes, int64_t n_chunks, int
 TKB_API int tkb_codes_from_native_dev(const void *native, int64_t n_chunks, int M, uint64_t *codes, void *stream);
 
 /* Fast scan on the native layout: same results as tkb_estimate_dev / tkb_ivf_scan_dev, bit for bit.
- * LUT rows live in registers and are looked up with PRMT; sums are accumulated without per-step clamps
- * and a per-vector certificate decides which chunks the exact patch pass recomputes.
- * workspace: device scratch of at least 16 + 8 * (number of (query, chunk) units) bytes:
- *   estimate: Q * n_chunks units;  ivf_scan: Q * P * (slot_stride / 16) units. */
+ * LUT rows are looked up with PRMT; sums are accumulated without per-step clamps and a per-vector
+ * certificate decides which chunks the exact patch pass recomputes.
+ * workspace: 16-byte aligned device scratch, 16 + 8 bytes per chunk that may fail the certificate; chunks that
+ * do not fit are recomputed inside the scan kernel (slower, still exact), so any size >= 24 is valid.
+ * max_chunks_per_query (ivf): upper bound used to size the grid (0: P * slot_stride / 16). */
 TKB_API int tkb_estimate_native_dev(const void *native, int64_t n_chunks, int M, const uint8_t *tables, int Q,
                             uint8_t *est, int64_t est_stride, int order, int signd,
                             void *workspace, int64_t workspace_bytes, void *stream);
-TKB_API int tkb_ivf_scan_native_dev(const void *native, const int64_t *list_chunk_off, int n_lists, int M,
+TKB_API int tkb_ivf_scan_native_dev(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                             const uint8_t *tables, const int32_t *probes, int Q, int P,
-                            uint8_t *est, int64_t slot_stride, int order, int signd,
-                            void *workspace, int64_t workspace_bytes, void *stream);
+                            uint8_t *est, int64_t slot_stride, const int64_t *seg_off, int64_t max_chunks_per_query,
+                            int order, int signd, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* Exact replay of the reference heap (ref: tinyknn/_fast_pq.pyx:153-206, :274-307) over
  * precomputed estimates, one heap per query.
  *   heap_idx int64[Q][R], heap_val int32[Q][R]: in/out (call tkb_heap_fill_dev first for a fresh heap)
  * tkb_replay_dev : one segment per query: est[q][0..16*n_chunks), true size n, labels int64[>=n] or NULL
  * tkb_ivf_replay_dev : P segments per query in probe order; segment s = list probes[q][s] with
- *   n = list_size[l] and labels = ids + 16*list_chunk_off[l] (ids are stored padded like the codes). */
+ *   n = list_size[l] and labels = ids + 16*list_chunk_off[l] (ids are stored padded like the codes; here
+ *   list_chunk_off addresses `ids`, which a rank of a sharded index keeps for ALL lists). */
 TKB_API int tkb_heap_fill_dev(int64_t *heap_idx, int32_t *heap_val, int64_t count, int signd, void *stream);
 TKB_API int tkb_replay_dev(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n,
                    int64_t *heap_idx, int32_t *heap_val, int Q, int R, int signd,
                    const int64_t *labels, void *stream);
-TKB_API int tkb_ivf_replay_dev(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+TKB_API int tkb_ivf_replay_dev(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                        const int32_t *list_size, int n_lists, const int64_t *ids,
                        const int32_t *probes, int Q, int P,
                        int64_t *heap_idx, int32_t *heap_val, int R, int signd, void *stream);
 
 /* Same replays for a FRESH heap (init_heap + query_pq in one call; the heap arrays are outputs only).
- * These use the thread-per-query kernel (one query per thread, heaps in shared memory) when its
- * preconditions hold and fall back to the warp-per-query kernel otherwise; results are identical.
+ * These use the queue-replay kernel (producer warps filter the estimates, one lane per query replays; heaps
+ * in shared memory) when its preconditions hold and the warp-per-query kernel otherwise; results are identical.
  * unique_labels != 0 certifies that no label occurs twice among the lists (an index built with one list per
  * point), which makes the reference's label dedupe a no-op. fallback: int32[Q] device scratch. */
 TKB_API int tkb_replay_fresh_dev(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n,
                          int64_t *heap_idx, int32_t *heap_val, int Q, int R, int signd, void *stream);
-TKB_API int tkb_ivf_replay_fresh_dev(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+TKB_API int tkb_ivf_replay_fresh_dev(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                              const int32_t *list_size, int n_lists, const int64_t *ids,
                              const int32_t *probes, int Q, int P,
                              int64_t *heap_idx, int32_t *heap_val, int R, int signd,

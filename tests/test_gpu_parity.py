@@ -504,7 +504,8 @@ def test_ivf_duplicate_labels_use_dedupe_path():
 def test_ivf_replay_fresh_random_segments():
     """IVF-mode fresh replay over random est bytes, random (also empty / tiny) lists, skipped probe slots and
     heaps small enough that the queue-replay kernel has to cut its rounds: heap arrays == oracle, per query."""
-    from tinyknn_b200._lib import lib, check, PROBE_SKIP
+    from tinyknn_b200._lib import lib, check, PROBE_SKIP, PLAN_SEND
+    from tinyknn_b200 import sharded as SH
     rng = np.random.default_rng(21)
     for trial in range(10):
         signd = bool(trial % 2)
@@ -526,10 +527,33 @@ def test_ivf_replay_fresh_random_segments():
             est = (est // 16 + (60 if not signd else 0)).astype(np.uint8)  # few distinct values: ties, long queues
         hi, hv, fb = D.empty((Q, R), np.int64), D.empty((Q, R), np.int32), D.empty((Q,), np.int32)
         d_est, d_off, d_sizes, d_ids, d_probes = (D.upload(x) for x in (est, off, sizes, ids, probes))
-        check(lib.tkb_ivf_replay_fresh_dev(D.ptr(d_est), stride, D.ptr(d_off), D.ptr(d_sizes), n_lists,
+        check(lib.tkb_ivf_replay_fresh_dev(D.ptr(d_est), stride, None, D.ptr(d_off), D.ptr(d_sizes), n_lists,
                                            D.ptr(d_ids), D.ptr(d_probes), Q, P, D.ptr(hi), D.ptr(hv), R,
                                            int(signd), 1, D.ptr(fb), D.stream_ptr()))
         a, b = hi.cpu().numpy(), hv.cpu().numpy()
+        # the same segments packed by the device plan (compact buffer) give the same heaps, in both replay kernels
+        seg, gb, _ = SH.plan_host(probes, sizes, None, PLAN_SEND, 0, 1, 0)
+        d_seg, d_gb, d_ws = D.empty((Q, P), np.int64), D.empty((3,), np.int64), D.empty((Q,), np.int64)
+        check(lib.tkb_ivf_plan_dev(D.ptr(d_probes), Q, P, D.ptr(d_sizes), None, n_lists, PLAN_SEND, 0, 1, 0,
+                                   D.ptr(d_seg), D.ptr(d_gb), D.ptr(d_ws), 8 * Q, D.stream_ptr()))
+        assert np.array_equal(d_seg.cpu().numpy(), seg) and int(d_gb.cpu().numpy()[1]) == int(gb.sum())
+        packed_est = np.zeros(max(int(gb.sum()), 16), np.uint8)
+        for q in range(Q):
+            for s_ in range(P):
+                if seg[q, s_] >= 0:
+                    nb = 16 * (-(-int(sizes[probes[q, s_]]) // 16))
+                    packed_est[seg[q, s_]:seg[q, s_] + nb] = est[q, s_, :nb]
+        d_pe = D.upload(packed_est)
+        hi2, hv2 = D.empty((Q, R), np.int64), D.empty((Q, R), np.int32)
+        check(lib.tkb_ivf_replay_fresh_dev(D.ptr(d_pe), 0, D.ptr(d_seg), D.ptr(d_off), D.ptr(d_sizes), n_lists,
+                                           D.ptr(d_ids), D.ptr(d_probes), Q, P, D.ptr(hi2), D.ptr(hv2), R,
+                                           int(signd), 1, D.ptr(fb), D.stream_ptr()))
+        hi3, hv3 = D.empty((Q, R), np.int64), D.empty((Q, R), np.int32)
+        check(lib.tkb_heap_fill_dev(D.ptr(hi3), D.ptr(hv3), Q * R, int(signd), D.stream_ptr()))
+        check(lib.tkb_ivf_replay_dev(D.ptr(d_pe), 0, D.ptr(d_seg), D.ptr(d_off), D.ptr(d_sizes), n_lists,
+                                     D.ptr(d_ids), D.ptr(d_probes), Q, P, D.ptr(hi3), D.ptr(hv3), R, int(signd), D.stream_ptr()))
+        for x, y in ((hi2, hv2), (hi3, hv3)):
+            assert np.array_equal(x.cpu().numpy(), a) and np.array_equal(y.cpu().numpy(), b), trial
         for q in range(Q):
             oi, ov = np.zeros(R, np.int64), np.zeros(R, np.int32)
             O.init_heap(oi, ov, signd)
@@ -541,3 +565,85 @@ def test_ivf_replay_fresh_random_segments():
                 O.replay(est[q, s, :16 * ncr], int(sizes[l]), oi, ov, signd,
                          np.ascontiguousarray(ids[16 * off[l]:16 * off[l] + 16 * ncr]))
             assert np.array_equal(a[q], oi) and np.array_equal(b[q], ov), (trial, q)
+
+
+def test_fast_scan_tiny_workspace_recomputes_inline():
+    """A patch list that cannot hold the flagged chunks must not change results (the excess is folded exactly inline)."""
+    from tinyknn_b200._lib import lib, check, ORDER_AVX
+    rng = np.random.default_rng(31)
+    M, n = 32, 40_000
+    t = rng.integers(-4, 13, size=(2, M, 16)).astype(np.int8).view(np.uint8)     # eligible for the fast path, sums near 127
+    packed = _rand_case(rng, "avx", True, M, n, "lut")[2]
+    nck = len(packed)
+    nat, tdev = D.to_native(D.upload(packed), nck, M), D.upload(t)
+    outs = []
+    for ws_bytes in (16 + 8 * 2 * nck, 16 + 8 * 3):
+        est, ws = D.empty((2, 16 * nck), np.uint8), D.empty((ws_bytes,), np.uint8)
+        check(lib.tkb_estimate_native_dev(D.ptr(nat), nck, M, D.ptr(tdev), 2, D.ptr(est), 16 * nck, ORDER_AVX, 1,
+                                          D.ptr(ws), ws_bytes, D.stream_ptr()))
+        outs.append((est.cpu().numpy(), int(ws[:8].cpu().numpy().view(np.uint64)[0])))
+    assert outs[0][1] > 100 and outs[0][1] == outs[1][1]           # same chunks flagged; the second run had room for 3
+    assert np.array_equal(outs[0][0], outs[1][0])
+    for q in range(2):
+        exp = np.zeros(2 * nck, np.uint64)
+        O.estimate_pq(packed, O.transform_tables(t[q]), exp, True, "avx")
+        assert np.array_equal(outs[1][0][q], exp.view(np.uint8))
+
+
+@pytest.mark.parametrize("G", [1, 2, 4])
+def test_plan_device_matches_host_restatement(G):
+    from tinyknn_b200._lib import lib, check, PROBE_SKIP, PLAN_SEND, PLAN_RECV
+    from tinyknn_b200 import sharded as SH
+    rng = np.random.default_rng(40 + G)
+    n_lists, Qh, P = 61, 37, 7
+    sizes = rng.integers(0, 900, size=n_lists).astype(np.int32)
+    owner = SH.assign_owners(sizes, G)
+    Q = G * Qh
+    probes = np.stack([rng.permutation(n_lists)[:P] for _ in range(Q)]).astype(np.int32)
+    probes[5 % Q, 1] = PROBE_SKIP
+    probes[7 % Q, 0] = -1                                            # Python-wrapped: the last list
+    d_probes, d_sizes, d_owner = D.upload(probes), D.upload(sizes), D.upload(owner)
+    for r in range(G):
+        for mode, rows in ((PLAN_SEND, Q), (PLAN_RECV, Qh)):
+            seg, gb, base = SH.plan_host(probes, sizes, owner if G > 1 else None, mode, r, G, Qh)
+            d_seg, d_gb, d_ws = D.empty((rows, P), np.int64), D.empty((2 * G + 1,), np.int64), D.empty((rows * G,), np.int64)
+            check(lib.tkb_ivf_plan_dev(D.ptr(d_probes), Q, P, D.ptr(d_sizes), D.ptr(d_owner) if G > 1 else None, n_lists,
+                                       mode, r, G, Qh, D.ptr(d_seg), D.ptr(d_gb), D.ptr(d_ws), 8 * rows * G, D.stream_ptr()))
+            g = d_gb.cpu().numpy()
+            assert np.array_equal(d_seg.cpu().numpy(), seg), (G, r, mode)
+            assert np.array_equal(g[:G], gb) and g[G] == gb.sum() and np.array_equal(g[G + 1:], base)
+
+
+@pytest.mark.parametrize("G", [2, 3])
+def test_sharded_phases_equal_single_gpu(golden, G):
+    """List-sharded query path driven rank by rank on ONE GPU (buffers moved by hand instead of NCCL): heaps,
+    ids and distances must equal the unsharded path's."""
+    from tinyknn_b200.sharded import ShardedIVF
+    import torch
+    z = golden["ivf"]
+    S = O.ivf_state_from_arrays(z, "euc128_")
+    ivf = _ivf_from_state(S)
+    qs = np.ascontiguousarray(z["euc128_q"][:48 // G * G])
+    Qh = len(qs) // G
+    k, n_probes = 10, 8
+    ref_ids, ref_cnt, ref_d = ivf.query_batch(qs, k, n_probes=n_probes, order="device", return_distances=True)
+    ref_heap = ivf._last["heap_idx"].cpu().numpy()
+    shards = [ShardedIVF(ivf, rank=r, world=G, drop_full_codes=False) for r in range(G)]
+    assert sum(int(sh.dev["n_chunks_total"]) for sh in shards) == ivf.to_device()["n_chunks_total"]
+    homes = [sh._home(qs[r * Qh:(r + 1) * Qh], n_probes) for r, sh in enumerate(shards)]
+    tables = torch.cat([h["lut"]["tables"] for h in homes])
+    probes = torch.cat([h["probes"] for h in homes])
+    scans = [sh._scan_owned(tables, probes, Qh, homes[0]["P"]) for sh in shards]
+    for b, sh in enumerate(shards):                                 # all-to-all by hand: home b receives from every a
+        parts = []
+        for a in range(G):
+            est_s, send_splits = scans[a][0], scans[a][1]
+            o = int(np.sum(send_splits[:b]))
+            parts.append(est_s[o:o + int(send_splits[b])])
+            assert int(send_splits[b]) == int(scans[b][3][a])
+        est_r = torch.cat(parts) if sum(p.numel() for p in parts) else D.empty((16,), np.uint8)
+        ids, cnt, dst = sh._finish(homes[b], est_r, scans[b][2], k, (n_probes + 1) * k + 1)
+        sl = slice(b * Qh, (b + 1) * Qh)
+        assert np.array_equal(ivf._last["heap_idx"].cpu().numpy(), ref_heap[sl])
+        assert np.array_equal(ids.cpu().numpy(), ref_ids[sl]) and np.array_equal(cnt.cpu().numpy(), ref_cnt[sl])
+        assert np.array_equal(dst.cpu().numpy(), ref_d[sl])

@@ -1,0 +1,157 @@
+"""World-size-2 `gloo` test of the list-sharded query path's HOST logic (runs on CPU, no CUDA):
+list->rank assignment, the segment plan (numpy restatement of tkb_ivf_plan_dev), the all-gather of LUTs/probe
+lists and the uneven all-to-all of estimates. The scan and the heap are played by the oracle here; the GPU
+tests check the device plan/scan/replay against the same restatement."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden", "ivf.npz")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, prefix, n_probes, k, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from oracle import restate as O
+    from tinyknn_b200 import sharded as SH
+    from tinyknn_b200._lib import PLAN_SEND, PLAN_RECV
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        z = np.load(GOLDEN)
+        S = O.ivf_state_from_arrays(z, prefix)
+        K = O.Kernels("port", "avx")
+        qs = np.asarray(z[prefix + "q"], dtype=np.float32)
+        Qh = len(qs) // world
+        home = qs[rank * Qh:(rank + 1) * Qh]
+        sizes = np.array([t[0] for t in S.pq_transformed_points], dtype=np.int32)
+        owner = SH.assign_owners(sizes, world)
+        C = S.pq_transformed_centers[0]
+        P = min(n_probes, C)
+        M = S.pq_transformed_centers[1].shape[1]
+
+        # home phase: LUTs + probe lists of my own queries (reference semantics through the oracle)
+        tabs = np.zeros((Qh, 2 * M), dtype=np.uint64)
+        probes_h = np.zeros((Qh, P), dtype=np.int32)
+        qn = []
+        for i, q in enumerate(home):
+            q = np.array(q, dtype=np.float32)
+            if S.metric == "angular":
+                q /= np.linalg.norm(q)
+            dt = O.make_dtable(S.pq, q, K)
+            tabs[i] = dt.tables[:2 * M]
+            probes_h[i] = dt.top(S.pq_transformed_centers, S.active_centers, k=n_probes)
+            qn.append(q)
+        tables = SH.all_gather_rows(torch.from_numpy(tabs.view(np.int64)), None).numpy().view(np.uint64)
+        probes = SH.all_gather_rows(torch.from_numpy(probes_h), None).numpy()
+        Q = world * Qh
+        assert tables.shape == (Q, 2 * M) and probes.shape == (Q, P)
+
+        # scan of the lists I own, for every query, into the planned send buffer
+        seg_s, gb_s, _ = SH.plan_host(probes, sizes, owner, PLAN_SEND, rank, world, Qh)
+        seg_r, gb_r, _ = SH.plan_host(probes, sizes, owner, PLAN_RECV, rank, world, Qh)
+        send = np.zeros(max(int(gb_s.sum()), 1), dtype=np.uint8)
+        for q in range(Q):
+            for s in range(P):
+                if seg_s[q, s] < 0:
+                    continue
+                l = int(probes[q, s])
+                assert owner[l] == rank
+                n, packed = S.pq_transformed_points[l]
+                est = np.zeros(2 * len(packed), dtype=np.uint64)
+                K.estimate_pq(packed, np.ascontiguousarray(tables[q]), est, True)
+                send[seg_s[q, s]:seg_s[q, s] + 16 * len(packed)] = est.view(np.uint8)
+        recv = SH.all_to_all_bytes(torch.from_numpy(send), gb_s, gb_r, None).numpy()
+        assert len(recv) == int(gb_r.sum())
+
+        # home phase 2: ordered replay of the received estimates, exact rescoring
+        bad = 0
+        for i in range(Qh):
+            R = (n_probes + 1) * k + 1
+            hi, hv = np.zeros(R, np.int64), np.zeros(R, np.int32)
+            O.init_heap(hi, hv, True)
+            for s in range(P):
+                l = int(probes_h[i, s])
+                n = int(sizes[l])
+                if n == 0:
+                    continue
+                nb = 16 * ((n + 15) // 16)
+                assert seg_r[i, s] >= 0
+                O.replay(recv[seg_r[i, s]:seg_r[i, s] + nb], n, hi, hv, True, np.ascontiguousarray(S.ids[l], dtype=np.int64))
+            tr = {}
+            exp = O.ivf_query(S, home[i], k, n_probes=n_probes, kernels=K, trace=tr)
+            if not (np.array_equal(hi, tr["heap_indices"]) and np.array_equal(hv, tr["heap_values"])):
+                bad += 1
+            cand = hi[hi != -1]
+            got = cand if len(cand) <= k else cand[O.bottom_k(O.exact_dists(qn[i], S.data[cand]), k)]
+            if set(got) != set(exp):
+                bad += 1
+        np.save(out, np.array([bad, Qh, int(gb_s.sum()), int(gb_r.sum())]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("prefix,n_probes", [("euc128_", 8), ("ang_", 3)])
+def test_sharded_host_logic_gloo_world2(tmp_path, prefix, n_probes):
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    outs = [str(tmp_path / ("r%d.npy" % r)) for r in range(world)]
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_worker, args=(r, world, port, prefix, n_probes, 10, outs[r])) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    res = [np.load(o) for o in outs]
+    assert all(r[0] == 0 for r in res), res                   # every home query: heap arrays and ids == single-process oracle
+    assert sum(r[2] for r in res) == sum(r[3] for r in res)   # bytes sent == bytes received over the box
+    assert all(r[2] > 0 for r in res)                         # both ranks own probed lists
+
+
+def test_assign_owners_balanced_and_deterministic():
+    from tinyknn_b200.sharded import assign_owners
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(0, 5000, size=1000)
+    for g in (1, 2, 4, 8):
+        o = assign_owners(sizes, g)
+        assert np.array_equal(o, assign_owners(sizes.copy(), g)) and o.min() >= 0 and o.max() < g
+        load = np.bincount(o, weights=sizes, minlength=g)
+        assert load.max() - load.min() <= sizes.max()
+
+
+def test_plan_host_layout_properties():
+    """Send layout of rank a towards home b and receive layout of b from a describe the same byte stream."""
+    from tinyknn_b200.sharded import plan_host, assign_owners
+    from tinyknn_b200._lib import PLAN_SEND, PLAN_RECV, PROBE_SKIP
+    rng = np.random.default_rng(1)
+    n_lists, G, Qh, P = 37, 4, 9, 6
+    sizes = rng.integers(0, 300, size=n_lists).astype(np.int32)
+    owner = assign_owners(sizes, G)
+    probes = np.stack([rng.permutation(n_lists)[:P] for _ in range(G * Qh)]).astype(np.int32)
+    probes[3, 2] = PROBE_SKIP
+    send = [plan_host(probes, sizes, owner, PLAN_SEND, r, G, Qh) for r in range(G)]
+    recv = [plan_host(probes, sizes, owner, PLAN_RECV, r, G, Qh) for r in range(G)]
+    for a in range(G):
+        for b in range(G):
+            assert send[a][1][b] == recv[b][1][a]             # split sizes agree
+            # walking b's queries in (q, s) order visits the same segments at the same relative offsets
+            for i in range(Qh):
+                q = b * Qh + i
+                for s in range(P):
+                    l = probes[q, s]
+                    if l == PROBE_SKIP or owner[l] != a or sizes[l] == 0:
+                        continue
+                    assert send[a][0][q, s] - send[a][2][b] == recv[b][0][i, s] - recv[b][2][a]

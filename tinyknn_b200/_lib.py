@@ -29,16 +29,18 @@ SIGNATURES = {
     "tkb_insert_is": [_vp, _vp, _i, _i64, _i],
     "tkb_lut_build_dev": [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _dbl, _dbl, _i, _vp, _vp, _vp, _vp, _vp],
     "tkb_estimate_dev": [_vp, _i64, _i, _vp, _i, _vp, _i64, _i, _i, _vp],
-    "tkb_ivf_scan_dev": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _i64, _i, _i, _vp],
+    "tkb_launch_count": [],
+    "tkb_ivf_scan_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _i64, _vp, _i64, _i, _i, _vp],
+    "tkb_ivf_plan_dev": [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _vp],
     "tkb_codes_to_native_dev": [_vp, _i64, _i, _vp, _vp],
     "tkb_codes_from_native_dev": [_vp, _i64, _i, _vp, _vp],
     "tkb_estimate_native_dev": [_vp, _i64, _i, _vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp],
-    "tkb_ivf_scan_native_dev": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _i64, _i, _i, _vp, _i64, _vp],
+    "tkb_ivf_scan_native_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _i64, _vp, _i64, _i, _i, _vp, _i64, _vp],
     "tkb_heap_fill_dev": [_vp, _vp, _i64, _i, _vp],
     "tkb_replay_dev": [_vp, _i64, _i64, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
-    "tkb_ivf_replay_dev": [_vp, _i64, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp],
+    "tkb_ivf_replay_dev": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp],
     "tkb_replay_fresh_dev": [_vp, _i64, _i64, _i, _vp, _vp, _i, _i, _i, _vp],
-    "tkb_ivf_replay_fresh_dev": [_vp, _i64, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "tkb_ivf_replay_fresh_dev": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
     "tkb_gather_dists_dev": [_vp, _i, _i64, _i, _vp, _vp, _i, _i, _vp, _vp],
     "tkb_select_probes_dev": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "tkb_select_topk_dev": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
@@ -64,7 +66,7 @@ def _load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export the symbol
         fn.argtypes = argtypes
-        fn.restype = _c.c_char_p if name == "tkb_last_error" else _c.c_int
+        fn.restype = {"tkb_last_error": _c.c_char_p, "tkb_launch_count": _c.c_longlong}.get(name, _c.c_int)
     return lib
 
 
@@ -76,7 +78,13 @@ def last_error():
     return msg.decode("utf-8", "replace") if msg else ""
 
 
-n_calls = 0          # C-ABI calls that returned OK (each *_dev call launches one kernel per <=65535 queries)
+n_calls = 0          # C-ABI calls that returned OK
+PLAN_SEND, PLAN_RECV = 0, 1
+
+
+def launch_count():
+    """CUDA kernels launched by the library so far (counted where they are launched, in C)."""
+    return int(lib.tkb_launch_count())
 
 
 def check(rc):

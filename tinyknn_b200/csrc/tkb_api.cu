@@ -1,7 +1,7 @@
 // tkb_api.cu -- extern "C" boundary of libtinyknn_b200.so (see include/tinyknn_b200.h).
 #include <stdarg.h>
 
-#include <mutex>
+#include <atomic>
 
 #include "tkb_common.cuh"
 
@@ -10,6 +10,9 @@ namespace tkb {
 static thread_local char g_err[512] = "";
 
 char *err_buf() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int set_err(int code, const char *fmt, ...)
 {
@@ -62,6 +65,8 @@ extern "C" {
 int tkb_version(void) { return 100; }
 
 const char *tkb_last_error(void) { return tkb::err_buf(); }
+
+long long tkb_launch_count(void) { return tkb::g_launches.load(std::memory_order_relaxed); }
 
 int tkb_device_count(int *count)
 {
@@ -174,12 +179,21 @@ int tkb_estimate_dev(const uint64_t *codes, int64_t n_chunks, int M, const uint8
     return launch_estimate(codes, n_chunks, M, tables, Q, est, est_stride, order, signd, (cudaStream_t)stream);
 }
 
-int tkb_ivf_scan_dev(const uint64_t *codes, const int64_t *list_chunk_off, int n_lists, int M,
+int tkb_ivf_scan_dev(const uint64_t *codes, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                      const uint8_t *tables, const int32_t *probes, int Q, int P,
-                     uint8_t *est, int64_t slot_stride, int order, int signd, void *stream)
+                     uint8_t *est, int64_t slot_stride, const int64_t *seg_off, int64_t max_list_chunks,
+                     int order, int signd, void *stream)
 {
-    return launch_ivf_scan(codes, list_chunk_off, n_lists, M, tables, probes, Q, P, est, slot_stride, order,
-                           signd, (cudaStream_t)stream);
+    return launch_ivf_scan(codes, list_chunk_off, list_size, n_lists, M, tables, probes, Q, P, est, slot_stride, seg_off,
+                           max_list_chunks, order, signd, (cudaStream_t)stream);
+}
+
+int tkb_ivf_plan_dev(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner,
+                     int n_lists, int mode, int rank, int n_ranks, int q_per_rank,
+                     int64_t *seg_off, int64_t *group_bytes, void *workspace, int64_t workspace_bytes, void *stream)
+{
+    return launch_ivf_plan(probes, Q, P, list_size, list_owner, n_lists, mode, rank, n_ranks, q_per_rank, seg_off,
+                           group_bytes, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int tkb_codes_to_native_dev(const uint64_t *codes, int64_t n_chunks, int M, void *native, void *stream)
@@ -200,13 +214,13 @@ int tkb_estimate_native_dev(const void *native, int64_t n_chunks, int M, const u
                                   workspace_bytes, (cudaStream_t)stream);
 }
 
-int tkb_ivf_scan_native_dev(const void *native, const int64_t *list_chunk_off, int n_lists, int M,
+int tkb_ivf_scan_native_dev(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                             const uint8_t *tables, const int32_t *probes, int Q, int P,
-                            uint8_t *est, int64_t slot_stride, int order, int signd,
-                            void *workspace, int64_t workspace_bytes, void *stream)
+                            uint8_t *est, int64_t slot_stride, const int64_t *seg_off, int64_t max_chunks_per_query,
+                            int order, int signd, void *workspace, int64_t workspace_bytes, void *stream)
 {
-    return launch_ivf_scan_native(native, list_chunk_off, n_lists, M, tables, probes, Q, P, est, slot_stride, order,
-                                  signd, workspace, workspace_bytes, (cudaStream_t)stream);
+    return launch_ivf_scan_native(native, list_chunk_off, list_size, n_lists, M, tables, probes, Q, P, est, slot_stride,
+                                  seg_off, max_chunks_per_query, order, signd, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int tkb_heap_fill_dev(int64_t *heap_idx, int32_t *heap_val, int64_t count, int signd, void *stream)
@@ -221,12 +235,12 @@ int tkb_replay_dev(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int
     return launch_replay(est, est_stride, n_chunks, n, heap_idx, heap_val, Q, R, signd, labels, (cudaStream_t)stream);
 }
 
-int tkb_ivf_replay_dev(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+int tkb_ivf_replay_dev(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                        const int32_t *list_size, int n_lists, const int64_t *ids,
                        const int32_t *probes, int Q, int P,
                        int64_t *heap_idx, int32_t *heap_val, int R, int signd, void *stream)
 {
-    return launch_ivf_replay(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
+    return launch_ivf_replay(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
                              heap_val, R, signd, (cudaStream_t)stream);
 }
 
@@ -236,13 +250,13 @@ int tkb_replay_fresh_dev(const uint8_t *est, int64_t est_stride, int64_t n_chunk
     return launch_replay_fresh(est, est_stride, n_chunks, n, heap_idx, heap_val, Q, R, signd, (cudaStream_t)stream);
 }
 
-int tkb_ivf_replay_fresh_dev(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+int tkb_ivf_replay_fresh_dev(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                              const int32_t *list_size, int n_lists, const int64_t *ids,
                              const int32_t *probes, int Q, int P,
                              int64_t *heap_idx, int32_t *heap_val, int R, int signd,
                              int unique_labels, int32_t *fallback, void *stream)
 {
-    return launch_ivf_replay_fresh(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
+    return launch_ivf_replay_fresh(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
                                    heap_val, R, signd, unique_labels, fallback, (cudaStream_t)stream);
 }
 

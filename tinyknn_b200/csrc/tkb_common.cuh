@@ -12,6 +12,7 @@ namespace tkb {
 // ---- per-thread error message ---------------------------------------------------------------
 char *err_buf();                       // defined in tkb_api.cu
 int set_err(int code, const char *fmt, ...);
+void count_launch();                   // bumps the process-wide kernel launch counter (tkb_launch_count)
 
 #define TKB_CUDA(expr)                                                                      \
     do {                                                                                    \
@@ -32,6 +33,7 @@ int set_err(int code, const char *fmt, ...);
         if (_e != cudaSuccess)                                                              \
             return ::tkb::set_err(TKB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",         \
                                   cudaGetErrorString(_e), __FILE__, __LINE__);              \
+        ::tkb::count_launch();                                                              \
     } while (0)
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -97,28 +99,31 @@ __device__ __forceinline__ uint4 ldg_nc_u4(const uint4 *p)
 // kernels' host-side launchers (one per .cu file), used by tkb_api.cu
 int launch_estimate(const uint64_t *codes, int64_t n_chunks, int M, const uint8_t *tables, int Q,
                     uint8_t *est, int64_t est_stride, int order, int signd, cudaStream_t st);
-int launch_ivf_scan(const uint64_t *codes, const int64_t *list_chunk_off, int n_lists, int M,
+int launch_ivf_scan(const uint64_t *codes, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                     const uint8_t *tables, const int32_t *probes, int Q, int P, uint8_t *est,
-                    int64_t slot_stride, int order, int signd, cudaStream_t st);
+                    int64_t slot_stride, const int64_t *seg_off, int64_t max_list_chunks, int order, int signd, cudaStream_t st);
+int launch_ivf_plan(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner, int n_lists,
+                    int mode, int rank, int n_ranks, int q_per_rank, int64_t *seg_off, int64_t *group_bytes,
+                    void *workspace, int64_t workspace_bytes, cudaStream_t st);
 int launch_codes_to_native(const uint64_t *ref, int64_t n_chunks, int M, void *native, cudaStream_t st);
 int launch_codes_from_native(const void *native, int64_t n_chunks, int M, uint64_t *ref, cudaStream_t st);
 int launch_estimate_native(const void *native, int64_t n_chunks, int M, const uint8_t *tables, int Q, uint8_t *est,
                            int64_t est_stride, int order, int signd, void *workspace, int64_t workspace_bytes,
                            cudaStream_t st);
-int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, int n_lists, int M,
+int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                            const uint8_t *tables, const int32_t *probes, int Q, int P, uint8_t *est,
-                           int64_t slot_stride, int order, int signd, void *workspace, int64_t workspace_bytes,
-                           cudaStream_t st);
+                           int64_t slot_stride, const int64_t *seg_off, int64_t max_chunks_per_query, int order, int signd,
+                           void *workspace, int64_t workspace_bytes, cudaStream_t st);
 int launch_heap_fill(int64_t *heap_idx, int32_t *heap_val, int64_t count, int signd, cudaStream_t st);
 int launch_replay(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n, int64_t *heap_idx,
                   int32_t *heap_val, int Q, int R, int signd, const int64_t *labels, cudaStream_t st);
-int launch_ivf_replay(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+int launch_ivf_replay(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                       const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
                       int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int signd,
                       cudaStream_t st);
 int launch_replay_fresh(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n, int64_t *heap_idx,
                         int32_t *heap_val, int Q, int R, int signd, cudaStream_t st);
-int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                             const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
                             int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int signd,
                             int unique_labels, int *fallback, cudaStream_t st);

@@ -105,7 +105,7 @@ replay_kernel(const uint8_t *__restrict__ est, int64_t est_stride, int64_t n_chu
 // ref: tinyknn/ivf.py:140-150 -- the probed lists are visited in `top` order with labels=ids[cl]
 template <bool SIGNED>
 __global__ void __launch_bounds__(32 * REPLAY_WARPS)
-ivf_replay_kernel(const uint8_t *__restrict__ est, int64_t slot_stride,
+ivf_replay_kernel(const uint8_t *__restrict__ est, int64_t slot_stride, const int64_t *__restrict__ seg_off,
                   const int64_t *__restrict__ list_chunk_off, const int32_t *__restrict__ list_size,
                   int n_lists, const int64_t *__restrict__ ids, const int32_t *__restrict__ probes,
                   int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R)
@@ -118,25 +118,14 @@ ivf_replay_kernel(const uint8_t *__restrict__ est, int64_t slot_stride,
         if (l == PROBE_SKIP) continue;
         if (l < 0) l += n_lists;
         const int64_t c0 = list_chunk_off[l];
-        const int64_t nc = list_chunk_off[l + 1] - c0;
-        replay_segment<SIGNED>(est + ((size_t)q * P + s) * slot_stride, nc, list_size[l], ids + 16 * c0,
+        const int64_t nc = ((int64_t)list_size[l] + 15) >> 4;              // real chunks (tile padding is not stored)
+        const int64_t so = seg_off ? seg_off[(size_t)q * P + s] : ((int64_t)q * P + s) * slot_stride;
+        if (so < 0) continue;
+        replay_segment<SIGNED>(est + so, nc, list_size[l], ids + 16 * c0,
                                heap_idx + (size_t)q * R, heap_val + (size_t)q * R, R, lane);
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Thread-per-query replay ("tpq"): one THREAD owns one query and its heap, 32 queries per warp.
-//
-// The sift-down of the reference heap is single-threaded by nature; giving it a whole warp (above)
-// leaves 31 lanes idle for ~90 % of the instructions. Here every lane replays its own query, the
-// heaps live in shared memory interleaved by lane (entry j of lane t at word j*32+t: every lane
-// stays in its own bank whatever j it touches), and an entry is 8 bytes: value | slot<<16, position.
-// Labels are looked up once, at the end. Preconditions (checked by the launcher / the kernel):
-//   * fresh heap (filled here), * labels are unique across the segments of a query, so the
-//     reference's label dedupe (ref: _fast_pq.pyx:284-287) can never fire -- the host certifies this
-//     for the index, and a query whose probe list contains negative (Python-wrapped) entries is
-//     handed to the warp-per-query kernel through `fallback`, * 256*R bytes of shared memory per warp.
-// ------------------------------------------------------------------------------------------------
 template <bool SIGNED>
 __device__ __forceinline__ uint32_t cand_mask16(const uint4 e, int bound)
 {
@@ -148,126 +137,28 @@ __device__ __forceinline__ uint32_t cand_mask16(const uint4 e, int bound)
     return pack(m0) | (pack(m1) << 4) | (pack(m2) << 8) | (pack(m3) << 12);
 }
 
-// mode 0: one segment per query (est row q, n vectors, label = position)      [probe selection]
-// mode 1: P segments per query taken from the probe list, labels from `ids`   [IVF.query]
-template <bool SIGNED>
-__global__ void __launch_bounds__(32)
-replay_tpq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, int64_t n_chunks0, int n0,
-                  const int64_t *__restrict__ list_chunk_off, const int32_t *__restrict__ list_size, int n_lists,
-                  const int64_t *__restrict__ ids, const int32_t *__restrict__ probes, int Q, int P,
-                  int64_t *__restrict__ heap_idx, int32_t *__restrict__ heap_val, int R, int *__restrict__ fallback)
-{
-    extern __shared__ uint32_t tpq_sm[];
-    const int lane = threadIdx.x;
-    uint32_t *A = tpq_sm + lane;                    // value (low 16, two's complement) | slot << 16
-    uint32_t *B = tpq_sm + 32 * R + lane;           // position inside the segment
-    const int q = blockIdx.x * 32 + lane;
-    if (q >= Q) return;
-    const int init = SIGNED ? 127 : 255;
-    for (int j = 0; j < R; j++) { A[32 * j] = (uint32_t)init | 0xffff0000u; B[32 * j] = 0; }
-#define TPQ_VAL(j) ((int)(int16_t)(A[32 * (j)] & 0xffffu))
-    bool ok = true;
-    if (mode == 1)
-        for (int s = 0; s < P; s++) {
-            const int l = probes[(size_t)q * P + s];
-            if (l < 0 && l != PROBE_SKIP) ok = false;          // Python-wrapped index: lists may repeat
-        }
-    if (fallback) fallback[q] = ok ? 0 : 1;
-    if (!ok) return;
-
-    int bound = init;
-    for (int s = 0; s < P; s++) {
-        int64_t nc;
-        int n;
-        const uint4 *ep;
-        if (mode == 1) {
-            const int l = probes[(size_t)q * P + s];
-            if (l == PROBE_SKIP) continue;
-            const int64_t c0 = list_chunk_off[l];
-            nc = list_chunk_off[l + 1] - c0;
-            n = list_size[l];
-            ep = reinterpret_cast<const uint4 *>(est + ((size_t)q * P + s) * stride);
-        } else {
-            nc = n_chunks0; n = n0;
-            ep = reinterpret_cast<const uint4 *>(est + (size_t)q * stride);
-        }
-        const int64_t nc_real = ((int64_t)n + 15) >> 4;        // chunks holding real vectors (tile padding is skipped)
-        if (nc > nc_real) nc = nc_real;
-        if (nc <= 0) continue;
-        uint4 nxt = ldg_nc_u4(ep);
-        for (int64_t c = 0; c < nc; c++) {
-            const uint4 e = nxt;
-            if (c + 1 < nc) nxt = ldg_nc_u4(ep + c + 1);       // prefetch: hides the load behind the inserts
-            uint32_t m = cand_mask16<SIGNED>(e, bound);
-            if (m == 0) continue;
-            const int frozen = bound;                          // bound is frozen for the chunk
-            const uint32_t ws[4] = {e.x, e.y, e.z, e.w};
-            while (m) {
-                const int v = __ffs(m) - 1;
-                m &= m - 1;
-                const int64_t pos = 16 * c + v;
-                if (pos >= n) break;                           // padding positions are the last ones
-                const uint32_t byte = (ws[v >> 2] >> (8 * (v & 3))) & 0xffu;
-                const int ev = SIGNED ? (int)(int8_t)byte : (int)byte;
-                if (ev >= frozen) continue;                    // (cannot happen: mask was built with frozen)
-                // replace the root and sift down (ref: _fast_pq.pyx:290-307)
-                int j = 0;
-                for (;;) {
-                    int nx = j, nv = ev;
-                    const int l_ = 2 * j + 1, r_ = 2 * j + 2;
-                    if (l_ < R) { const int lv = TPQ_VAL(l_); if (lv > nv) { nx = l_; nv = lv; } }
-                    if (r_ < R) { const int rv = TPQ_VAL(r_); if (rv > nv) { nx = r_; nv = rv; } }
-                    if (nx == j) break;
-                    A[32 * j] = A[32 * nx]; B[32 * j] = B[32 * nx];
-                    j = nx;
-                }
-                A[32 * j] = ((uint32_t)ev & 0xffffu) | ((uint32_t)s << 16);
-                B[32 * j] = (uint32_t)pos;
-            }
-            bound = TPQ_VAL(0);
-            bound = SIGNED ? (int)(int8_t)bound : (int)(uint8_t)bound;
-        }
-    }
-    // resolve labels and write the heap arrays
-    int64_t *hi = heap_idx + (size_t)q * R;
-    int32_t *hv = heap_val + (size_t)q * R;
-    for (int j = 0; j < R; j++) {
-        const uint32_t a = A[32 * j];
-        const uint32_t s = a >> 16;
-        int64_t label = -1;
-        if (s != 0xffffu) {
-            const int64_t pos = (int64_t)B[32 * j];
-            if (mode == 1) {
-                const int l = probes[(size_t)q * P + s];
-                label = ids[16 * list_chunk_off[l] + pos];
-            } else {
-                label = pos;
-            }
-        }
-        hi[j] = label;
-        hv[j] = (int)(int16_t)(a & 0xffffu);
-    }
-#undef TPQ_VAL
-}
-
 // ------------------------------------------------------------------------------------------------
 // Queue replay ("rq"): the fresh-heap replay used by the query path.
 //
-// The thread-per-query kernel above is instruction-efficient (32 queries per warp) but every lane walks
-// ALL of its query's chunks, 32 unrelated 16-byte loads per step, and the lanes of a warp only rarely
-// need the sift at the same time. Here a CTA owns QPC queries and alternates two phases per round:
+// The sift-down of the reference heap is sequential by nature; giving it a whole warp (above) leaves 31
+// lanes idle, giving every query one lane for everything makes each lane walk ALL of its query's chunks
+// with 32 unrelated 16-byte loads per step. Here a CTA owns QPC queries and alternates two phases per round:
 //   produce : each warp takes whole queries; its 32 lanes read 32 consecutive chunks of the query's
 //             estimate stream (one coalesced 512-byte read), compare them with the query's bound AS OF
 //             THE START OF THE ROUND and append the surviving (value, payload) records, in stream
 //             order, to the query's queue in shared memory. The bound is monotone non-increasing
 //             (SURVEY.md H1), so a stale bound admits a superset of the true candidates, never misses one.
-//   consume : warp 0, one LANE per query, walks its queue in order and applies the reference rule
-//             exactly (bound frozen when the first record of a new chunk arrives, strict <, replace the
-//             root, sift down), heaps interleaved by lane in shared memory.
+//   consume : one LANE per query walks its queue in order and applies the reference rule exactly (bound
+//             frozen when the first record of a new chunk arrives, strict <, replace the root, sift
+//             down), heaps interleaved by query in shared memory.
 // Round windows double (the admission rate after n vectors is ~R/n), so a query needs ~log2(n/R) rounds
-// and the lanes only ever touch records that had a real chance. payload = position inside the `ids`
-// array (mode 1) or inside the segment (mode 0); labels are resolved once, at the end.
-// Same preconditions as the tpq kernel: fresh heap, labels unique across a query's segments.
+// and the lanes only ever touch records that had a real chance. payload = position in the query's stream
+// of real chunks; labels are resolved once, at the end. Preconditions: fresh heap (filled here); labels
+// unique across a query's segments, so that the reference's label dedupe (ref: _fast_pq.pyx:284-287)
+// can never fire -- the host certifies this for the index, and a query whose probe list contains negative
+// (Python-wrapped) entries is handed to the warp-per-query kernel through `fallback`.
+// mode 0: one segment per query (est row q, n vectors, label = position)      [probe selection, top()]
+// mode 1: P segments per query taken from the probe list, labels from `ids`   [IVF.query]
 // ------------------------------------------------------------------------------------------------
 constexpr int RQ_THREADS = 256;
 constexpr uint32_t RQ_EMPTY = 0xffffffffu;        // payload of a heap slot that was never filled
@@ -462,10 +353,10 @@ replay_rq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, cons
     }
 }
 
-// warp-per-query IVF replay restricted to the queries flagged by the tpq kernel
+// warp-per-query IVF replay restricted to the queries flagged by the queue-replay kernel
 template <bool SIGNED>
 __global__ void __launch_bounds__(32 * REPLAY_WARPS)
-ivf_replay_fallback_kernel(const uint8_t *__restrict__ est, int64_t slot_stride,
+ivf_replay_fallback_kernel(const uint8_t *__restrict__ est, int64_t slot_stride, const int64_t *__restrict__ seg_off,
                            const int64_t *__restrict__ list_chunk_off, const int32_t *__restrict__ list_size,
                            int n_lists, const int64_t *__restrict__ ids, const int32_t *__restrict__ probes,
                            int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, const int *__restrict__ fallback)
@@ -480,8 +371,10 @@ ivf_replay_fallback_kernel(const uint8_t *__restrict__ est, int64_t slot_stride,
         if (l == PROBE_SKIP) continue;
         if (l < 0) l += n_lists;
         const int64_t c0 = list_chunk_off[l];
-        const int64_t nc = list_chunk_off[l + 1] - c0;
-        replay_segment<SIGNED>(est + ((size_t)q * P + s) * slot_stride, nc, list_size[l], ids + 16 * c0,
+        const int64_t nc = ((int64_t)list_size[l] + 15) >> 4;              // real chunks (tile padding is not stored)
+        const int64_t so = seg_off ? seg_off[(size_t)q * P + s] : ((int64_t)q * P + s) * slot_stride;
+        if (so < 0) continue;
+        replay_segment<SIGNED>(est + so, nc, list_size[l], ids + 16 * c0,
                                heap_idx + (size_t)q * R, heap_val + (size_t)q * R, R, lane);
     }
 }
@@ -518,7 +411,7 @@ int launch_replay(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int 
     return TKB_OK;
 }
 
-int launch_ivf_replay(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+int launch_ivf_replay(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                       const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
                       int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int signd,
                       cudaStream_t st)
@@ -528,17 +421,14 @@ int launch_ivf_replay(const uint8_t *est, int64_t slot_stride, const int64_t *li
     TKB_REQUIRE(est && list_chunk_off && list_size && ids && probes && heap_idx && heap_val, "null pointer");
     TKB_REQUIRE(slot_stride % 16 == 0 && (uintptr_t)est % 16 == 0, "est must be 16-byte aligned/strided");
     const unsigned blocks = (unsigned)((Q + REPLAY_WARPS - 1) / REPLAY_WARPS);
-    if (signd) ivf_replay_kernel<true><<<blocks, 32 * REPLAY_WARPS, 0, st>>>(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R);
-    else       ivf_replay_kernel<false><<<blocks, 32 * REPLAY_WARPS, 0, st>>>(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R);
+    if (signd) ivf_replay_kernel<true><<<blocks, 32 * REPLAY_WARPS, 0, st>>>(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R);
+    else       ivf_replay_kernel<false><<<blocks, 32 * REPLAY_WARPS, 0, st>>>(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R);
     TKB_LAUNCH_CHECK();
     return TKB_OK;
 }
 
-
-// Fresh-heap replays with certified-unique labels: thread-per-query kernel + fallback for flagged queries.
-static bool tpq_fits(int R) { return R > 0 && (size_t)R * 256 <= 200 * 1024 && R < 0xffff; }
-
-// Queue-replay launch geometry: QPC queries per CTA (a power of two <= 32), queue capacity QCAP records.
+// Queue-replay launch geometry: QPC queries per CTA (a power of two <= 16), queue capacity QCAP records,
+// LPW lanes (queries) per consumer warp.
 struct RqGeom { int qpc, qcap, lpw; size_t smem; };
 
 static size_t rq_smem(int R, int P, int qpc, int qcap)
@@ -550,29 +440,19 @@ static bool rq_geometry(int Q, int R, int P, RqGeom &g)
 {
     if (R <= 0 || P <= 0) return false;
     g.qcap = 2 * R < 64 ? 64 : 2 * R;
-    // enough CTAs to cover the machine about twice, as many queries per CTA as that allows (<= 16:
-    // the consumer warp pays for the slowest of its lanes), and at most ~45 KB so several CTAs share an SM
+    // enough CTAs to cover the machine about twice, as many queries per CTA as that allows, and at most
+    // ~45 KB of shared memory so that several CTAs share an SM
     int qpc = 16;
     while (qpc > 1 && (Q + qpc - 1) / qpc < 2 * 148) qpc >>= 1;
     while (qpc > 1 && rq_smem(R, P, qpc, g.qcap) > 45 * 1024) qpc >>= 1;
     g.qpc = qpc;
-    // lanes per consumer warp: few lanes = little lock-step waste but more warps to issue; all 8 warps can consume
+    // few lanes per consumer warp = little lock-step waste, more warps to issue (measured flat from 2 to 16)
     static int lpw_env = -1;
     if (lpw_env < 0) { const char *e = getenv("TKB_RQ_LPW"); lpw_env = e ? atoi(e) : 0; }
     g.lpw = (lpw_env == 1 || lpw_env == 2 || lpw_env == 4 || lpw_env == 8 || lpw_env == 16) ? lpw_env : 4;
     while (g.lpw * (RQ_THREADS / 32) < qpc) g.lpw <<= 1;
     g.smem = rq_smem(R, P, qpc, g.qcap);
     return g.smem <= 200 * 1024;
-}
-
-static int replay_impl()
-{
-    static int impl = -1;                      // 0 = queue replay (default), 1 = thread-per-query (A/B measurements)
-    if (impl < 0) {
-        const char *e = getenv("TKB_REPLAY");
-        impl = (e && strcmp(e, "tpq") == 0) ? 1 : 0;
-    }
-    return impl;
 }
 
 template <bool SIGNED>
@@ -590,6 +470,7 @@ static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t
     return TKB_OK;
 }
 
+// Fresh-heap replays: queue-replay kernel when its preconditions hold, the warp-per-query kernel otherwise.
 int launch_replay_fresh(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n, int64_t *heap_idx,
                         int32_t *heap_val, int Q, int R, int signd, cudaStream_t st)
 {
@@ -597,53 +478,31 @@ int launch_replay_fresh(const uint8_t *est, int64_t est_stride, int64_t n_chunks
     if (Q == 0 || R == 0) return TKB_OK;
     TKB_REQUIRE(heap_idx && heap_val, "null pointer");
     RqGeom g;
-    const bool use_rq = replay_impl() == 0 && n_chunks < (1LL << 27) && rq_geometry(Q, R, 1, g);
-    if (n_chunks == 0 || (!use_rq && !tpq_fits(R))) {
+    if (n_chunks == 0 || n_chunks >= (1LL << 27) || !rq_geometry(Q, R, 1, g)) {
         if (int rc = launch_heap_fill(heap_idx, heap_val, (int64_t)Q * R, signd, st)) return rc;
         return launch_replay(est, est_stride, n_chunks, n, heap_idx, heap_val, Q, R, signd, nullptr, st);
     }
     TKB_REQUIRE(est && est_stride % 16 == 0 && (uintptr_t)est % 16 == 0, "est must be 16-byte aligned/strided");
-    if (use_rq) {
-        if (signd) return launch_rq<true>(0, est, est_stride, nullptr, n_chunks, n, nullptr, nullptr, 0, nullptr, nullptr, Q, 1, heap_idx, heap_val, R, nullptr, g, st);
-        return launch_rq<false>(0, est, est_stride, nullptr, n_chunks, n, nullptr, nullptr, 0, nullptr, nullptr, Q, 1, heap_idx, heap_val, R, nullptr, g, st);
-    }
-    const size_t smem = (size_t)R * 256;
-    const unsigned blocks = (unsigned)((Q + 31) / 32);
-    if (signd) {
-        TKB_CUDA(cudaFuncSetAttribute(replay_tpq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        replay_tpq_kernel<true><<<blocks, 32, smem, st>>>(0, est, est_stride, n_chunks, n, nullptr, nullptr, 0, nullptr, nullptr, Q, 1, heap_idx, heap_val, R, nullptr);
-    } else {
-        TKB_CUDA(cudaFuncSetAttribute(replay_tpq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        replay_tpq_kernel<false><<<blocks, 32, smem, st>>>(0, est, est_stride, n_chunks, n, nullptr, nullptr, 0, nullptr, nullptr, Q, 1, heap_idx, heap_val, R, nullptr);
-    }
-    TKB_LAUNCH_CHECK();
-    return TKB_OK;
+    if (signd) return launch_rq<true>(0, est, est_stride, nullptr, n_chunks, n, nullptr, nullptr, 0, nullptr, nullptr, Q, 1, heap_idx, heap_val, R, nullptr, g, st);
+    return launch_rq<false>(0, est, est_stride, nullptr, n_chunks, n, nullptr, nullptr, 0, nullptr, nullptr, Q, 1, heap_idx, heap_val, R, nullptr, g, st);
 }
 
 template <bool SIGNED>
-static int ivf_replay_fresh_t(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+static int ivf_replay_fresh_t(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                               const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
                               int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int *fallback,
-                              bool use_rq, const RqGeom &g, cudaStream_t st)
+                              const RqGeom &g, cudaStream_t st)
 {
-    if (use_rq) {
-        if (int rc = launch_rq<SIGNED>(1, est, slot_stride, nullptr, 0, 0, list_chunk_off, list_size, n_lists, ids, probes,
-                                       Q, P, heap_idx, heap_val, R, fallback, g, st)) return rc;
-    } else {
-        const size_t smem = (size_t)R * 256;
-        TKB_CUDA(cudaFuncSetAttribute(replay_tpq_kernel<SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        replay_tpq_kernel<SIGNED><<<(unsigned)((Q + 31) / 32), 32, smem, st>>>(1, est, slot_stride, 0, 0, list_chunk_off, list_size,
-                                                                             n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
-        TKB_LAUNCH_CHECK();
-    }
+    if (int rc = launch_rq<SIGNED>(1, est, slot_stride, seg_off, 0, 0, list_chunk_off, list_size, n_lists, ids, probes,
+                                   Q, P, heap_idx, heap_val, R, fallback, g, st)) return rc;
     // queries whose probe list holds Python-wrapped (negative) entries: warp-per-query kernel with label dedupe
     ivf_replay_fallback_kernel<SIGNED><<<(unsigned)((Q + REPLAY_WARPS - 1) / REPLAY_WARPS), 32 * REPLAY_WARPS, 0, st>>>(
-        est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
+        est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
     TKB_LAUNCH_CHECK();
     return TKB_OK;
 }
 
-int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64_t *list_chunk_off,
+int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                             const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
                             int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int signd,
                             int unique_labels, int *fallback, cudaStream_t st)
@@ -652,18 +511,17 @@ int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64
     if (Q == 0 || R == 0) return TKB_OK;
     TKB_REQUIRE(heap_idx && heap_val, "null pointer");
     RqGeom g;
-    const bool use_rq = replay_impl() == 0 && rq_geometry(Q, R, P, g);
-    if (!unique_labels || P == 0 || P >= 0xffff || !fallback || (!use_rq && !tpq_fits(R))) {
+    if (!unique_labels || P == 0 || P >= 0xffff || !fallback || !rq_geometry(Q, R, P, g)) {
         if (int rc = launch_heap_fill(heap_idx, heap_val, (int64_t)Q * R, signd, st)) return rc;
-        return launch_ivf_replay(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
+        return launch_ivf_replay(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
                                  heap_val, R, signd, st);
     }
     TKB_REQUIRE(est && list_chunk_off && list_size && ids && probes, "null pointer");
     TKB_REQUIRE(slot_stride % 16 == 0 && (uintptr_t)est % 16 == 0, "est must be 16-byte aligned/strided");
-    if (signd) return ivf_replay_fresh_t<true>(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P,
-                                               heap_idx, heap_val, R, fallback, use_rq, g, st);
-    return ivf_replay_fresh_t<false>(est, slot_stride, list_chunk_off, list_size, n_lists, ids, probes, Q, P,
-                                     heap_idx, heap_val, R, fallback, use_rq, g, st);
+    if (signd) return ivf_replay_fresh_t<true>(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P,
+                                               heap_idx, heap_val, R, fallback, g, st);
+    return ivf_replay_fresh_t<false>(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P,
+                                     heap_idx, heap_val, R, fallback, g, st);
 }
 
 }  // namespace tkb

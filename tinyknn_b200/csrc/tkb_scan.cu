@@ -81,9 +81,9 @@ estimate_generic_kernel(const uint4 *__restrict__ codes, int64_t n_chunks, int M
 template <int ORDER, bool SIGNED>
 __global__ void __launch_bounds__(SCAN_THREADS)
 ivf_scan_generic_kernel(const uint4 *__restrict__ codes, const int64_t *__restrict__ list_chunk_off,
-                        int n_lists, int M, const uint8_t *__restrict__ tables,
+                        const int32_t *__restrict__ list_size, int n_lists, int M, const uint8_t *__restrict__ tables,
                         const int32_t *__restrict__ probes, int P, uint8_t *__restrict__ est,
-                        int64_t slot_stride)
+                        int64_t slot_stride, const int64_t *__restrict__ seg_off)
 {
     extern __shared__ __align__(16) uint8_t lut[];
     const int q = blockIdx.z, s = blockIdx.y;
@@ -91,8 +91,10 @@ ivf_scan_generic_kernel(const uint4 *__restrict__ codes, const int64_t *__restri
     if (l == PROBE_SKIP) return;
     if (l < 0) l += n_lists;                                   // Python list indexing (ref: ivf.py:141)
     const int64_t c0 = list_chunk_off[l];
-    const int64_t nc = list_chunk_off[l + 1] - c0;
-    if ((int64_t)blockIdx.x * SCAN_THREADS >= nc) return;
+    int64_t nc = list_chunk_off[l + 1] - c0;
+    if (list_size) { const int64_t real = ((int64_t)list_size[l] + 15) >> 4; if (real < nc) nc = real; }
+    const int64_t so = seg_off ? seg_off[(size_t)q * P + s] : ((int64_t)q * P + s) * slot_stride;
+    if (so < 0 || (int64_t)blockIdx.x * SCAN_THREADS >= nc) return;
 
     const uint4 *tq = reinterpret_cast<const uint4 *>(tables + (size_t)q * M * 16);
     for (int i = threadIdx.x; i < M; i += blockDim.x) reinterpret_cast<uint4 *>(lut)[i] = tq[i];
@@ -102,7 +104,7 @@ ivf_scan_generic_kernel(const uint4 *__restrict__ codes, const int64_t *__restri
     if (c >= nc) return;
     uint4 o;
     scan_chunk<ORDER, SIGNED>(codes + (c0 + c) * (M >> 1), M, lut, o);
-    *reinterpret_cast<uint4 *>(est + ((size_t)q * P + s) * slot_stride + 16 * c) = o;
+    *reinterpret_cast<uint4 *>(est + so + 16 * c) = o;
 }
 
 static int check_scan_args(int M, int order)
@@ -148,24 +150,26 @@ int launch_estimate(const uint64_t *codes, int64_t n_chunks, int M, const uint8_
     return TKB_OK;
 }
 
-int launch_ivf_scan(const uint64_t *codes, const int64_t *list_chunk_off, int n_lists, int M,
+int launch_ivf_scan(const uint64_t *codes, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                     const uint8_t *tables, const int32_t *probes, int Q, int P, uint8_t *est,
-                    int64_t slot_stride, int order, int signd, cudaStream_t st)
+                    int64_t slot_stride, const int64_t *seg_off, int64_t max_list_chunks, int order, int signd, cudaStream_t st)
 {
     if (int rc = check_scan_args(M, order)) return rc;
     TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists > 0, "bad extent");
-    if (Q == 0 || P == 0 || slot_stride == 0) return TKB_OK;
+    if (max_list_chunks <= 0) max_list_chunks = slot_stride / 16;
+    if (Q == 0 || P == 0 || max_list_chunks == 0) return TKB_OK;
     TKB_REQUIRE(codes && list_chunk_off && tables && probes && est, "null pointer");
     TKB_REQUIRE(slot_stride % 16 == 0, "slot_stride must be a multiple of 16");
     TKB_REQUIRE(P <= 65535, "too many probes");
-    const int64_t tiles = (slot_stride / 16 + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int64_t tiles = (max_list_chunks + SCAN_THREADS - 1) / SCAN_THREADS;
     const uint4 *c4 = reinterpret_cast<const uint4 *>(codes);
     for (int q0 = 0; q0 < Q; q0 += 65535) {
         const int qn = (Q - q0 < 65535) ? (Q - q0) : 65535;
         dim3 grid((unsigned)tiles, (unsigned)P, (unsigned)qn);
-        TKB_DISPATCH_SCAN(ivf_scan_generic_kernel, grid, (size_t)M * 16, st, c4, list_chunk_off, n_lists, M,
+        TKB_DISPATCH_SCAN(ivf_scan_generic_kernel, grid, (size_t)M * 16, st, c4, list_chunk_off, list_size, n_lists, M,
                           tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P,
-                          est + (size_t)q0 * P * slot_stride, slot_stride);
+                          seg_off ? est : est + (size_t)q0 * P * slot_stride, slot_stride,
+                          seg_off ? seg_off + (size_t)q0 * P : nullptr);
         TKB_LAUNCH_CHECK();
     }
     return TKB_OK;

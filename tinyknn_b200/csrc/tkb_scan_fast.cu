@@ -279,16 +279,34 @@ __device__ __forceinline__ uint4 scan_chunk_exact(const uint4 *__restrict__ nat,
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// cold path (patch list full): same fold, kept out of line so that it does not cost the hot loop registers
+template <int ORDER, bool SIGNED>
+__device__ __noinline__ uint4 scan_chunk_exact_cold(const uint4 *__restrict__ nat, int64_t chunk, int Ph,
+                                                    const uint8_t *__restrict__ raw)
+{
+    return scan_chunk_exact<ORDER, SIGNED>(nat, chunk, Ph, raw);
+}
+
 struct PatchList {
-    unsigned long long *count;     // number of queued chunks
-    int64_t *est_off;              // byte offset of the chunk's 16 estimates inside the est buffer
+    unsigned long long *count;     // number of flagged chunks (may exceed `cap`: the excess was recomputed inline)
+    uint2 *entry;                  // .x = unit (query, or query * P + probe slot), .y = chunk inside the unit's segment
+    unsigned long long cap;        // entries that fit
 };
+
+// queue a flagged chunk for the patch pass; false = list full, the caller recomputes the chunk itself
+__device__ __forceinline__ bool patch_push(const PatchList &pl, uint32_t unit, uint32_t local)
+{
+    const unsigned long long i = atomicAdd(pl.count, 1ULL);
+    if (i >= pl.cap) return false;
+    pl.entry[i] = make_uint2(unit, local);
+    return true;
+}
 
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
 template <int ORDER, bool SIGNED>
-__global__ void __launch_bounds__(FAST_THREADS)
+__global__ void __launch_bounds__(FAST_THREADS, 3)
 estimate_fast_kernel(const uint4 *__restrict__ nat, int64_t n_chunks, int M, const uint8_t *__restrict__ tables,
                      uint8_t *__restrict__ est, int64_t est_stride, PatchList patch)
 {
@@ -308,7 +326,8 @@ estimate_fast_kernel(const uint4 *__restrict__ nat, int64_t n_chunks, int M, con
         if (m.eligible) {
             bool flagged;
             o = scan_chunk_fast<SIGNED>(nat, c, Ph, rows, m, flagged);
-            if (flagged) patch.est_off[atomicAdd(patch.count, 1ULL)] = off;
+            if (flagged && !patch_push(patch, (uint32_t)q, (uint32_t)c))
+                o = scan_chunk_exact_cold<ORDER, SIGNED>(nat, c, Ph, reinterpret_cast<const uint8_t *>(raw));
         } else {
             o = scan_chunk_exact<ORDER, SIGNED>(nat, c, Ph, reinterpret_cast<const uint8_t *>(raw));
         }
@@ -317,12 +336,16 @@ estimate_fast_kernel(const uint4 *__restrict__ nat, int64_t n_chunks, int M, con
 }
 
 // One CTA column per query: the P probed lists are walked as one flat range of chunks, so the LUT is
-// prepared once per (query, split) and short lists do not leave lanes idle.
+// prepared once per (query, split) and short lists do not leave lanes idle. Segment (q, s) is written at
+// est + seg_off[q*P+s] (absent when negative) or, without a plan, at est + (q*P+s)*slot_stride. With
+// list_size the walk covers only the chunks that hold real vectors (the reference's ceil(n/16)), not the
+// tile padding of the native layout.
 template <int ORDER, bool SIGNED>
-__global__ void __launch_bounds__(FAST_THREADS)
-ivf_scan_fast_kernel(const uint4 *__restrict__ nat, const int64_t *__restrict__ list_chunk_off, int n_lists, int M,
+__global__ void __launch_bounds__(FAST_THREADS, 3)
+ivf_scan_fast_kernel(const uint4 *__restrict__ nat, const int64_t *__restrict__ list_chunk_off,
+                     const int32_t *__restrict__ list_size, int n_lists, int M,
                      const uint8_t *__restrict__ tables, const int32_t *__restrict__ probes, int P,
-                     uint8_t *__restrict__ est, int64_t slot_stride, PatchList patch)
+                     uint8_t *__restrict__ est, int64_t slot_stride, const int64_t *__restrict__ seg_off, PatchList patch)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     uint4 *rows = reinterpret_cast<uint4 *>(smem);
@@ -330,19 +353,23 @@ ivf_scan_fast_kernel(const uint4 *__restrict__ nat, const int64_t *__restrict__ 
     LutMeta *meta = reinterpret_cast<LutMeta *>(raw + M);
     int *scratch = reinterpret_cast<int *>(meta + 1);
     int64_t *seg_c0 = reinterpret_cast<int64_t *>(scratch + 4 * M);                       // 16-byte aligned offset
-    int *seg_end = reinterpret_cast<int *>(seg_c0 + P);                                  // inclusive prefix of chunk counts
+    int64_t *seg_o = seg_c0 + P;                                                         // est offset of the segment
+    int *seg_end = reinterpret_cast<int *>(seg_o + P);                                   // inclusive prefix of chunk counts
     const int q = blockIdx.y, Ph = M >> 1;
     if (threadIdx.x == 0) {
         int run = 0;
         for (int s = 0; s < P; s++) {
             int l = probes[(size_t)q * P + s];
             int64_t c0 = 0, nc = 0;
-            if (l != PROBE_SKIP) {
+            const int64_t o = seg_off ? seg_off[(size_t)q * P + s] : ((int64_t)q * P + s) * slot_stride;
+            if (l != PROBE_SKIP && o >= 0) {
                 if (l < 0) l += n_lists;
                 c0 = list_chunk_off[l];
                 nc = list_chunk_off[l + 1] - c0;
+                if (list_size) { const int64_t real = ((int64_t)list_size[l] + 15) >> 4; if (real < nc) nc = real; }
             }
             seg_c0[s] = c0;
+            seg_o[s] = o;
             run += (int)nc;
             seg_end[s] = run;
         }
@@ -356,12 +383,13 @@ ivf_scan_fast_kernel(const uint4 *__restrict__ nat, const int64_t *__restrict__ 
         while (f >= seg_end[s]) s++;
         const int local = f - (s ? seg_end[s - 1] : 0);
         const int64_t c = seg_c0[s] + local;
-        const int64_t off = ((int64_t)q * P + s) * slot_stride + 16 * (int64_t)local;
+        const int64_t off = seg_o[s] + 16 * (int64_t)local;
         uint4 o;
         if (m.eligible) {
             bool flagged;
             o = scan_chunk_fast<SIGNED>(nat, c, Ph, rows, m, flagged);
-            if (flagged) patch.est_off[atomicAdd(patch.count, 1ULL)] = off;
+            if (flagged && !patch_push(patch, (uint32_t)(q * P + s), (uint32_t)local))
+                o = scan_chunk_exact_cold<ORDER, SIGNED>(nat, c, Ph, reinterpret_cast<const uint8_t *>(raw));
         } else {
             o = scan_chunk_exact<ORDER, SIGNED>(nat, c, Ph, reinterpret_cast<const uint8_t *>(raw));
         }
@@ -370,29 +398,31 @@ ivf_scan_fast_kernel(const uint4 *__restrict__ nat, const int64_t *__restrict__ 
 }
 
 // Patch pass: one half-warp per queued chunk recomputes its 16 estimates with the reference's fold.
-// mode 0: brute force (est_off -> q, chunk); mode 1: IVF (est_off -> q, slot, local chunk -> list).
+// mode 0: brute force (unit = q, chunk = local); mode 1: IVF (unit = q*P+s, chunk = list start + local).
 template <int ORDER, bool SIGNED>
 __global__ void __launch_bounds__(256)
 patch_kernel(const uint4 *__restrict__ nat, int M, const uint8_t *__restrict__ tables, uint8_t *__restrict__ est,
-             PatchList patch, int mode, int64_t est_stride /* or slot_stride */, const int64_t *__restrict__ list_chunk_off,
-             int n_lists, const int32_t *__restrict__ probes, int P)
+             PatchList patch, int mode, int64_t stride /* est_stride or slot_stride */, const int64_t *__restrict__ seg_off,
+             const int64_t *__restrict__ list_chunk_off, int n_lists, const int32_t *__restrict__ probes, int P)
 {
-    const unsigned long long count = *patch.count;
+    unsigned long long count = *patch.count;
+    if (count > patch.cap) count = patch.cap;
     const int Ph = M >> 1;
     const int hw = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, v = threadIdx.x & 15;
     const int n_hw = (gridDim.x * blockDim.x) >> 4;
     for (unsigned long long i = hw; i < count; i += n_hw) {
-        const int64_t off = patch.est_off[i];
-        int64_t q, c;
+        const uint2 en = patch.entry[i];
+        int64_t q, c, off;
         if (mode == 0) {
-            q = off / est_stride;
-            c = (off - q * est_stride) >> 4;
+            q = en.x;
+            c = en.y;
+            off = q * stride + 16 * c;
         } else {
-            const int64_t qs = off / est_stride;           // q * P + s
-            q = qs / P;
-            int l = probes[qs];
+            q = en.x / (uint32_t)P;
+            int l = probes[en.x];
             if (l < 0) l += n_lists;
-            c = list_chunk_off[l] + ((off - qs * est_stride) >> 4);
+            c = list_chunk_off[l] + en.y;
+            off = (seg_off ? seg_off[en.x] : (int64_t)en.x * stride) + 16 * (int64_t)en.y;
         }
         const int e = exact_vector<ORDER, SIGNED>(nat, c, Ph, v, tables + (size_t)q * M * 16);
         est[off + v] = (uint8_t)e;
@@ -404,7 +434,7 @@ patch_kernel(const uint4 *__restrict__ nat, int M, const uint8_t *__restrict__ t
 // ------------------------------------------------------------------------------------------------
 static size_t fast_smem_bytes(int M, int P)
 {
-    return (size_t)M * 32 + sizeof(LutMeta) + sizeof(int) * (4 * (size_t)M + 4) + (size_t)P * 12 + 16;
+    return (size_t)M * 32 + sizeof(LutMeta) + sizeof(int) * (4 * (size_t)M + 4) + (size_t)P * 20 + 16;
 }
 
 static int check_fast_args(int M, int order)
@@ -452,12 +482,14 @@ int launch_codes_from_native(const void *native, int64_t n_chunks, int M, uint64
     return TKB_OK;
 }
 
-static int split_workspace(void *workspace, int64_t workspace_bytes, int64_t units, PatchList &pl)
+// workspace = 16-byte header (flagged-chunk counter) + 8-byte entries; whatever does not fit is recomputed inline
+static int split_workspace(void *workspace, int64_t workspace_bytes, PatchList &pl)
 {
-    TKB_REQUIRE(workspace && workspace_bytes >= 16 + 8 * units, "scan workspace too small (need 16 + 8 bytes per chunk unit)");
+    TKB_REQUIRE(workspace && workspace_bytes >= 16 + 8, "scan workspace too small (need at least 24 bytes)");
     TKB_REQUIRE((uintptr_t)workspace % 16 == 0, "workspace must be 16-byte aligned");
     pl.count = reinterpret_cast<unsigned long long *>(workspace);
-    pl.est_off = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(workspace) + 16);
+    pl.entry = reinterpret_cast<uint2 *>(reinterpret_cast<char *>(workspace) + 16);
+    pl.cap = (unsigned long long)((workspace_bytes - 16) / 8);
     return TKB_OK;
 }
 
@@ -469,12 +501,12 @@ int launch_estimate_native(const void *native, int64_t n_chunks, int M, const ui
     TKB_REQUIRE(n_chunks >= 0 && Q >= 0, "negative extent");
     if (n_chunks == 0 || Q == 0) return TKB_OK;
     TKB_REQUIRE(native && tables && est, "null pointer");
+    TKB_REQUIRE(n_chunks <= 0xffffffffLL, "too many chunks for one launch");
     TKB_REQUIRE(est_stride >= 16 * n_chunks && est_stride % 16 == 0, "est_stride must be a multiple of 16 and >= 16*n_chunks");
     TKB_REQUIRE(((uintptr_t)native % 16 == 0) && ((uintptr_t)est % 16 == 0) && ((uintptr_t)tables % 16 == 0),
                 "device pointers must be 16-byte aligned");
     PatchList pl;
-    if (int rc = split_workspace(workspace, workspace_bytes, (int64_t)Q * n_chunks, pl)) return rc;
-    TKB_CUDA(cudaMemsetAsync(pl.count, 0, 16, st));
+    if (int rc = split_workspace(workspace, workspace_bytes, pl)) return rc;
     int64_t tiles = (n_chunks + FAST_THREADS - 1) / FAST_THREADS;
     if (tiles > 148 * 8 && Q > 1) tiles = 148 * 8;                 // grid-stride beyond that
     TKB_REQUIRE(tiles <= 0x7fffffff, "too many chunks for one launch");
@@ -483,34 +515,34 @@ int launch_estimate_native(const void *native, int64_t n_chunks, int M, const ui
     for (int q0 = 0; q0 < Q; q0 += 65535) {
         const int qn = (Q - q0 < 65535) ? (Q - q0) : 65535;
         dim3 grid((unsigned)tiles, (unsigned)qn);
-        // est offsets in the patch list are relative to the full buffer: pass full pointers, shift q via tables/est
+        TKB_CUDA(cudaMemsetAsync(pl.count, 0, 16, st));
+        // patch entries are relative to this launch's block of queries: both kernels get the shifted pointers
         TKB_DISPATCH_FAST(estimate_fast_kernel, grid, FAST_THREADS, smem, st, n4, n_chunks, M,
                           tables + (size_t)q0 * M * 16, est + (size_t)q0 * est_stride, est_stride, pl);
         TKB_LAUNCH_CHECK();
         TKB_DISPATCH_FAST(patch_kernel, 148 * 4, 256, 0, st, n4, M, tables + (size_t)q0 * M * 16,
-                          est + (size_t)q0 * est_stride, pl, 0, est_stride, nullptr, 0, nullptr, 1);
+                          est + (size_t)q0 * est_stride, pl, 0, est_stride, nullptr, nullptr, 0, nullptr, 1);
         TKB_LAUNCH_CHECK();
-        if (q0 + 65535 < Q) TKB_CUDA(cudaMemsetAsync(pl.count, 0, 16, st));
     }
     return TKB_OK;
 }
 
-int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, int n_lists, int M,
+int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                            const uint8_t *tables, const int32_t *probes, int Q, int P, uint8_t *est,
-                           int64_t slot_stride, int order, int signd, void *workspace, int64_t workspace_bytes,
-                           cudaStream_t st)
+                           int64_t slot_stride, const int64_t *seg_off, int64_t max_chunks_per_query, int order, int signd,
+                           void *workspace, int64_t workspace_bytes, cudaStream_t st)
 {
     if (int rc = check_fast_args(M, order)) return rc;
     TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists > 0, "bad extent");
-    if (Q == 0 || P == 0 || slot_stride == 0) return TKB_OK;
+    if (Q == 0 || P == 0 || (slot_stride == 0 && !seg_off)) return TKB_OK;
     TKB_REQUIRE(native && list_chunk_off && tables && probes && est, "null pointer");
     TKB_REQUIRE(slot_stride % 16 == 0, "slot_stride must be a multiple of 16");
     TKB_REQUIRE(P <= 4096, "too many probes");
+    TKB_REQUIRE((int64_t)Q * P <= 0xffffffffLL, "too many (query, probe) units for one launch");
     PatchList pl;
-    if (int rc = split_workspace(workspace, workspace_bytes, (int64_t)Q * P * (slot_stride / 16), pl)) return rc;
-    TKB_CUDA(cudaMemsetAsync(pl.count, 0, 16, st));
+    if (int rc = split_workspace(workspace, workspace_bytes, pl)) return rc;
     // enough CTAs to fill the machine when Q is small; otherwise one CTA per query walks all its lists
-    const int64_t max_chunks_per_query = (int64_t)P * (slot_stride / 16);
+    if (max_chunks_per_query <= 0) max_chunks_per_query = (int64_t)P * (slot_stride / 16);
     int64_t splits = (148 * 4 + Q - 1) / Q;
     const int64_t max_splits = (max_chunks_per_query + FAST_THREADS - 1) / FAST_THREADS;
     if (splits > max_splits) splits = max_splits;
@@ -520,15 +552,15 @@ int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, in
     for (int q0 = 0; q0 < Q; q0 += 65535) {
         const int qn = (Q - q0 < 65535) ? (Q - q0) : 65535;
         dim3 grid((unsigned)splits, (unsigned)qn);
-        TKB_DISPATCH_FAST(ivf_scan_fast_kernel, grid, FAST_THREADS, smem, st, n4, list_chunk_off, n_lists, M,
-                          tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P,
-                          est + (size_t)q0 * P * slot_stride, slot_stride, pl);
+        const int64_t *so = seg_off ? seg_off + (size_t)q0 * P : nullptr;          // offsets stay relative to `est`
+        uint8_t *eb = seg_off ? est : est + (size_t)q0 * P * slot_stride;
+        TKB_CUDA(cudaMemsetAsync(pl.count, 0, 16, st));
+        TKB_DISPATCH_FAST(ivf_scan_fast_kernel, grid, FAST_THREADS, smem, st, n4, list_chunk_off, list_size, n_lists, M,
+                          tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, pl);
         TKB_LAUNCH_CHECK();
-        TKB_DISPATCH_FAST(patch_kernel, 148 * 4, 256, 0, st, n4, M, tables + (size_t)q0 * M * 16,
-                          est + (size_t)q0 * P * slot_stride, pl, 1, slot_stride, list_chunk_off, n_lists,
-                          probes + (size_t)q0 * P, P);
+        TKB_DISPATCH_FAST(patch_kernel, 148 * 4, 256, 0, st, n4, M, tables + (size_t)q0 * M * 16, eb, pl, 1, slot_stride,
+                          so, list_chunk_off, n_lists, probes + (size_t)q0 * P, P);
         TKB_LAUNCH_CHECK();
-        if (q0 + 65535 < Q) TKB_CUDA(cudaMemsetAsync(pl.count, 0, 16, st));
     }
     return TKB_OK;
 }

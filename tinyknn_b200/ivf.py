@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _device as D
 from . import fast_pq as _fp
-from ._lib import lib, check, DTYPE_F32, DTYPE_F64, PROBE_SKIP
+from ._lib import lib, check, DTYPE_F32, DTYPE_F64, PROBE_SKIP, PLAN_SEND, PLAN_RECV  # noqa: F401
 from .fast_pq import FastPQ, TransformedData, query_pq  # noqa: F401  (ivf.py:5 re-export)
 from .utils import timer, knn_brute, group_data_by_indices, bottom_k
 
@@ -122,6 +122,7 @@ class IVF:
             data = np.ascontiguousarray(data, dtype=np.float64)
         dev = dict(
             C=C, M=M, n_lists=n_lists, max_chunks=int(np.max(np.diff(chunks))) if n_lists else 0,
+            max_real_chunks=int((int(sizes.max()) + 15) // 16) if n_lists else 0,
             codes=D.to_native(D.upload(codes), codes.shape[0], M), n_chunks_total=int(codes.shape[0]),
             list_chunk_off=D.upload(chunks), list_size=D.upload(sizes), ids=D.upload(ids),
             center_codes=D.to_native(D.upload(ctd.packed), ctd.packed.shape[0], M), center_chunks=int(ctd.packed.shape[0]),
@@ -189,14 +190,13 @@ class IVF:
         Rc = min(2 * P + 10, C)                                         # ref: fast_pq.py:293-295
         if pass_1 is None:
             pass_1 = (n_probes + 1) * k + 1                             # ref: ivf.py:135-136
-        slot_stride = 16 * max(dev["max_chunks"], 1)
-        qb = int(max(1, min(Q, _WORKSPACE_BYTES // max(1, P * slot_stride))))
+        qb = int(max(1, min(Q, _WORKSPACE_BYTES // max(1, P * 16 * max(dev["max_real_chunks"], 1)))))
         outs = []
         for lo in range(0, Q, qb):
             qs = queries[lo:min(Q, lo + qb)]
             if isinstance(qs, np.ndarray):
                 qs = D.upload(qs)
-            outs.append(self._query_block(dev, qs, k, P, Rc, pass_1, slot_stride, order))
+            outs.append(self._query_block(dev, qs, k, P, Rc, pass_1, order))
         if order == "device":
             ids, cnt, dst = (outs[0] if len(outs) == 1 else tuple(t.cat([o[i] for o in outs]) for i in range(3)))
             if to_host:
@@ -207,23 +207,18 @@ class IVF:
             return ids, cnt, dst
         return ids, cnt
 
-    def _query_block(self, dev, qs, k, P, Rc, pass_1, slot_stride, order):
-        t = D.torch()
+    # -- stages of one block of queries (shared with the list-sharded index, sharded.py) ----------------
+    def _coarse(self, dev, lut, Q, P, Rc, order):
+        """Probe selection (ref: ivf.py:131 -> fast_pq.py:284-312): scan of the PQ-encoded centroids, exact heap
+        replay of 2*n_probes+10 candidates, exact centroid distances, n_probes nearest. Returns int32 (Q, P)."""
         st = D.stream_ptr()
-        Q = qs.shape[0]
-        C, M, n_lists = dev["C"], dev["M"], dev["n_lists"]
+        C, M = dev["C"], dev["M"]
         sg = 1                                                           # IVF.query hard-codes signed=True (ivf.py:138,148)
-        # 1. LUTs (ref: ivf.py:125-128)
-        with self._stage("lut"):
-            lut = self.pq.distance_tables(qs, signed=True, normalize=(self.metric == "angular"))
         tables, qn = lut["tables"], lut["q"]
-        # 2. probe selection (ref: ivf.py:131 -> fast_pq.py:284-312)
-        cc = dev["center_codes"]
-        nck = dev["center_chunks"]
+        cc, nck = dev["center_codes"], dev["center_chunks"]
         est_c = D.empty((Q, 16 * nck), np.uint8)
-        fast = _fp.SCAN_IMPL == "fast"
         with self._stage("coarse_scan"):
-            if fast:
+            if _fp.SCAN_IMPL == "fast":
                 ws = D.scan_workspace(Q * nck)
                 check(lib.tkb_estimate_native_dev(D.ptr(cc), nck, M, D.ptr(tables), Q, D.ptr(est_c), 16 * nck,
                                                   _fp._order(), sg, D.ptr(ws), ws.numel(), st))
@@ -234,48 +229,63 @@ class IVF:
         with self._stage("coarse_replay"):
             check(lib.tkb_replay_fresh_dev(D.ptr(est_c), 16 * nck, nck, C, D.ptr(hci), D.ptr(hcv), Q, Rc, sg, st))
         probes = D.empty((Q, P), np.int32)
-        if Rc <= P:
-            check(lib.tkb_select_probes_dev(D.ptr(hci), None, DTYPE_F32, Q, Rc, P, D.ptr(probes), st))
-        else:
-            dc = D.empty((Q, Rc), np.float32)
-            check(lib.tkb_gather_dists_dev(D.ptr(dev["centers"]), DTYPE_F32, C, dev["d"], D.ptr(qn), D.ptr(hci),
-                                           Q, Rc, D.ptr(dc), st))
-            if order == "device":
-                check(lib.tkb_select_probes_dev(D.ptr(hci), D.ptr(dc), DTYPE_F32, Q, Rc, P, D.ptr(probes), st))
+        with self._stage("coarse_select"):
+            if Rc <= P:
+                check(lib.tkb_select_probes_dev(D.ptr(hci), None, DTYPE_F32, Q, Rc, P, D.ptr(probes), st))
             else:
-                hci_h, dc_h = hci.cpu().numpy(), dc.cpu().numpy()
-                best = np.argpartition(dc_h, P, axis=1)[:, :P]           # == per-row bottom_k (utils.py:22-25)
-                probes = D.upload(np.take_along_axis(hci_h, best, axis=1).astype(np.int32))
-        # 3. scan of the probed lists + ordered replay (ref: ivf.py:137-150)
-        est = D.empty((Q, P, slot_stride), np.uint8)
+                dc = D.empty((Q, Rc), np.float32)
+                check(lib.tkb_gather_dists_dev(D.ptr(dev["centers"]), DTYPE_F32, C, dev["d"], D.ptr(qn), D.ptr(hci),
+                                               Q, Rc, D.ptr(dc), st))
+                if order == "device":
+                    check(lib.tkb_select_probes_dev(D.ptr(hci), D.ptr(dc), DTYPE_F32, Q, Rc, P, D.ptr(probes), st))
+                else:
+                    hci_h, dc_h = hci.cpu().numpy(), dc.cpu().numpy()
+                    best = np.argpartition(dc_h, P, axis=1)[:, :P]       # == per-row bottom_k (utils.py:22-25)
+                    probes = D.upload(np.take_along_axis(hci_h, best, axis=1).astype(np.int32))
+        self._last = dict(center_heap=hci, tables=tables)
+        return probes
+
+    def _scan(self, dev, tables, probes, Q, P, est, seg_off, codes_key="codes", off_key="list_chunk_off"):
+        """Estimates of every (query, probed list) segment present in `seg_off` (ref: the scan half of
+        query_pq_*, ivf.py:142-150), written compactly into `est`."""
+        st = D.stream_ptr()
+        M, n_lists = dev["M"], dev["n_lists"]
+        max_q_chunks = P * max(dev["max_real_chunks"], 1)
         with self._stage("scan"):
-            if fast:
-                ws = D.scan_workspace(Q * P * (slot_stride // 16))
-                check(lib.tkb_ivf_scan_native_dev(D.ptr(dev["codes"]), D.ptr(dev["list_chunk_off"]), n_lists, M,
-                                                  D.ptr(tables), D.ptr(probes), Q, P, D.ptr(est), slot_stride,
-                                                  _fp._order(), sg, D.ptr(ws), ws.numel(), st))
+            if _fp.SCAN_IMPL == "fast":
+                ws = D.scan_workspace(min(Q * max_q_chunks, max(1 << 20, Q * max_q_chunks // 4)))
+                check(lib.tkb_ivf_scan_native_dev(D.ptr(dev[codes_key]), D.ptr(dev[off_key]), D.ptr(dev["list_size"]), n_lists, M,
+                                                  D.ptr(tables), D.ptr(probes), Q, P, D.ptr(est), 0, D.ptr(seg_off),
+                                                  max_q_chunks, _fp._order(), 1, D.ptr(ws), ws.numel(), st))
+                self._last["patch_ws"] = ws
             else:
-                check(lib.tkb_ivf_scan_dev(D.ptr(self._ref_codes(dev, "codes", dev["n_chunks_total"])),
-                                           D.ptr(dev["list_chunk_off"]), n_lists, M, D.ptr(tables),
-                                           D.ptr(probes), Q, P, D.ptr(est), slot_stride, _fp._order(), sg, st))
+                check(lib.tkb_ivf_scan_dev(D.ptr(self._ref_codes(dev, codes_key, dev["n_chunks_total"])), D.ptr(dev[off_key]),
+                                           D.ptr(dev["list_size"]), n_lists, M, D.ptr(tables), D.ptr(probes), Q, P,
+                                           D.ptr(est), 0, D.ptr(seg_off), max(dev["max_real_chunks"], 1), _fp._order(), 1, st))
+
+    def _replay_rescore(self, dev, qn, probes, Q, P, k, pass_1, est, seg_off, order):
+        """Ordered exact heap replay over the probed lists, then exact rescoring and the k nearest
+        (ref: ivf.py:137-163). `probes`/`seg_off` are the rows of these Q queries."""
+        st = D.stream_ptr()
+        n_lists = dev["n_lists"]
         hi_, hv_ = D.empty((Q, pass_1), np.int64), D.empty((Q, pass_1), np.int32)
         fb = D.empty((Q,), np.int32)
         with self._stage("replay"):
-            check(lib.tkb_ivf_replay_fresh_dev(D.ptr(est), slot_stride, D.ptr(dev["list_chunk_off"]),
+            check(lib.tkb_ivf_replay_fresh_dev(D.ptr(est), 0, D.ptr(seg_off), D.ptr(dev["list_chunk_off"]),
                                                D.ptr(dev["list_size"]), n_lists, D.ptr(dev["ids"]), D.ptr(probes), Q, P,
-                                               D.ptr(hi_), D.ptr(hv_), pass_1, sg, int(dev.get("unique_ids", False)),
+                                               D.ptr(hi_), D.ptr(hv_), pass_1, 1, int(dev.get("unique_ids", False)),
                                                D.ptr(fb), st))
-        # 4. exact rescoring (ref: ivf.py:154-163)
         ddt = np.float32 if dev["data_dtype"] == DTYPE_F32 else np.float64
         dd = D.empty((Q, pass_1), ddt)
         with self._stage("rescore"):
             check(lib.tkb_gather_dists_dev(D.ptr(dev["data"]), dev["data_dtype"], dev["data"].shape[0], dev["d"],
                                            D.ptr(qn), D.ptr(hi_), Q, pass_1, D.ptr(dd), st))
-        self._last = dict(probes=probes, heap_idx=hi_, heap_val=hv_, tables=tables, center_heap=hci)
+        self._last.update(probes=probes, heap_idx=hi_, heap_val=hv_)
         if order == "device":
             oi, od, oc = D.empty((Q, k), np.int64), D.empty((Q, k), ddt), D.empty((Q,), np.int32)
-            check(lib.tkb_select_topk_dev(D.ptr(hi_), D.ptr(dd), dev["data_dtype"], Q, pass_1, k,
-                                          D.ptr(oi), D.ptr(od), D.ptr(oc), st))
+            with self._stage("select"):
+                check(lib.tkb_select_topk_dev(D.ptr(hi_), D.ptr(dd), dev["data_dtype"], Q, pass_1, k,
+                                              D.ptr(oi), D.ptr(od), D.ptr(oc), st))
             return oi, oc, od
         hi_h, dd_h = hi_.cpu().numpy(), dd.cpu().numpy()
         ids = np.full((Q, k), -1, dtype=np.int64)
@@ -290,3 +300,28 @@ class IVF:
             cnt[i] = len(cand)
             ids[i, :len(cand)], dst[i, :len(cand)] = cand, cd
         return ids, cnt, dst
+
+    def _plan(self, dev, probes, Q, P, mode=PLAN_SEND, rank=0, n_ranks=1, q_per_rank=0, rows=None):
+        """Segment offsets of the compact estimate buffer (tkb_ivf_plan_dev). Returns (seg_off, group_bytes)."""
+        rows = Q if rows is None else rows
+        seg_off = D.empty((rows, P), np.int64)
+        gb = D.empty((2 * n_ranks + 1,), np.int64)
+        ws = D.empty((max(rows, 1) * n_ranks,), np.int64)
+        with self._stage("plan"):
+            check(lib.tkb_ivf_plan_dev(D.ptr(probes), Q, P, D.ptr(dev["list_size"]), D.ptr(dev.get("list_owner")), dev["n_lists"],
+                                       mode, rank, n_ranks, q_per_rank, D.ptr(seg_off), D.ptr(gb), D.ptr(ws), 8 * ws.numel(),
+                                       D.stream_ptr()))
+        return seg_off, gb
+
+    def _query_block(self, dev, qs, k, P, Rc, pass_1, order):
+        Q = qs.shape[0]
+        # 1. LUTs (ref: ivf.py:125-128)
+        with self._stage("lut"):
+            lut = self.pq.distance_tables(qs, signed=True, normalize=(self.metric == "angular"))
+        # 2. probe selection
+        probes = self._coarse(dev, lut, Q, P, Rc, order)
+        # 3. scan of the probed lists into a compact estimate buffer, ordered replay, rescoring
+        seg_off, _ = self._plan(dev, probes, Q, P)
+        est = D.empty((Q * P * 16 * max(dev["max_real_chunks"], 1),), np.uint8)      # upper bound; only the planned part is touched
+        self._scan(dev, lut["tables"], probes, Q, P, est, seg_off)
+        return self._replay_rescore(dev, lut["q"], probes, Q, P, k, pass_1, est, seg_off, order)

@@ -1,0 +1,216 @@
+"""List-sharded IVF over the GPUs of one box: one process per GPU, torch.distributed (NCCL over NVLink).
+
+The reference has no multi-device story at all (ref: tinyknn/ivf.py is single-process numpy). The scan of
+`IVF.query` is independent per (query, probed list) (ref: ivf.py:140-150), so the inverted lists are
+partitioned over the ranks; what is NOT independent is the heap that consumes the estimates: it is
+order-dependent and not a true top-R, so "local top-k per GPU + merge" would change the
+returned ids. The exact scheme used here moves the *estimates* (1 byte per scanned vector, 1/16..1/26 of the
+code bytes read) to the query's home rank, which replays the reference heap in probe order:
+
+  home rank (its Q/G queries)   LUT build -> centroid scan -> heap replay -> probe lists
+  all ranks                     all_gather(LUTs, probe lists)                        [NCCL, ~1 KB / query]
+  every rank, ALL G*Q/G queries scan of the probed lists it OWNS into a send buffer grouped by home rank
+  all ranks                     all_to_all_single(estimates), uneven splits          [NCCL, 1 B / scanned vector]
+  home rank                     ordered heap replay -> exact rescoring -> k nearest
+
+Both sides of a (scanning rank, home rank) pair order the segments by (query, probe slot), so offsets are
+computed locally from replicated metadata (tkb_ivf_plan_dev) and never travel. Replicated per rank:
+centroids + centroid codes, list sizes/owners, `ids`, the raw vectors for rescoring; sharded: the PQ codes.
+"""
+import numpy as np
+
+from . import _device as D
+from ._lib import PLAN_SEND, PLAN_RECV, PROBE_SKIP
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host-side logic (pure numpy / torch.distributed; exercised on CPU with gloo in tests/test_sharded_cpu.py)
+# ---------------------------------------------------------------------------------------------------------
+
+def assign_owners(list_sizes, n_ranks):
+    """Size-balanced list -> rank map: largest list first onto the least loaded rank (ties: lowest rank).
+    Deterministic, so every rank computes the same map. Returns int32 (n_lists,)."""
+    sizes = np.asarray(list_sizes, dtype=np.int64)
+    owner = np.zeros(len(sizes), dtype=np.int32)
+    load = np.zeros(n_ranks, dtype=np.int64)
+    for l in np.argsort(-sizes, kind="stable"):
+        r = int(np.argmin(load))
+        owner[l] = r
+        load[r] += sizes[l]
+    return owner
+
+
+def plan_host(probes, list_size, list_owner, mode, rank, n_ranks, q_per_rank):
+    """numpy restatement of tkb_ivf_plan_dev (csrc/tkb_plan.cu): (seg_off, group_bytes, group_base)."""
+    probes = np.asarray(probes)
+    Q, P = probes.shape
+    n_lists = len(list_size)
+    if mode == PLAN_RECV and n_ranks > 1:
+        q_lo, q_n = rank * q_per_rank, max(0, min(q_per_rank, Q - rank * q_per_rank))
+    else:
+        q_lo, q_n = 0, Q
+    seg_off = np.full((q_n, P), -1, dtype=np.int64)
+    nbytes = np.zeros((q_n, P), dtype=np.int64)
+    group = np.zeros((q_n, P), dtype=np.int64)
+    for i in range(q_n):
+        q = q_lo + i
+        for s in range(P):
+            l = int(probes[q, s])
+            if l == PROBE_SKIP:
+                continue
+            if l < 0:
+                l += n_lists
+            owner = 0 if list_owner is None else int(list_owner[l])
+            if mode == PLAN_SEND:
+                if list_owner is not None and owner != rank:
+                    continue
+                group[i, s] = q // q_per_rank if n_ranks > 1 else 0
+            else:
+                group[i, s] = owner
+            nbytes[i, s] = 16 * ((int(list_size[l]) + 15) // 16)
+    group_bytes = np.array([nbytes[group == g].sum() for g in range(n_ranks)], dtype=np.int64)
+    group_base = np.concatenate([[0], np.cumsum(group_bytes)[:-1]]).astype(np.int64)
+    run = group_base.copy()
+    for i in range(q_n):
+        for s in range(P):
+            if nbytes[i, s] > 0:
+                g = group[i, s]
+                seg_off[i, s] = run[g]
+                run[g] += nbytes[i, s]
+    return seg_off, group_bytes, group_base
+
+
+def all_to_all_bytes(send, send_splits, recv_splits, group=None):
+    """One uneven all-to-all of uint8 buffers (torch.distributed.all_to_all_single; NCCL on GPUs, gloo on CPU).
+    Falls back to pairwise send/recv on backends without all_to_all."""
+    import torch
+    import torch.distributed as dist
+    send_splits, recv_splits = [int(x) for x in send_splits], [int(x) for x in recv_splits]
+    recv = torch.empty(max(sum(recv_splits), 1), dtype=torch.uint8, device=send.device)[:sum(recv_splits)]
+    send = send[:sum(send_splits)]
+    try:
+        dist.all_to_all_single(recv, send, recv_splits, send_splits, group=group)
+    except RuntimeError:                                                     # e.g. gloo without all_to_all support
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        so = np.concatenate([[0], np.cumsum(send_splits)]).astype(np.int64)
+        ro = np.concatenate([[0], np.cumsum(recv_splits)]).astype(np.int64)
+        recv[ro[rank]:ro[rank + 1]] = send[so[rank]:so[rank + 1]]
+        reqs = []
+        for peer in range(world):
+            if peer == rank:
+                continue
+            if send_splits[peer]:
+                reqs.append(dist.isend(send[so[peer]:so[peer + 1]].contiguous(), peer, group=group))
+        for peer in range(world):
+            if peer != rank and recv_splits[peer]:
+                buf = torch.empty(recv_splits[peer], dtype=torch.uint8, device=send.device)
+                dist.recv(buf, peer, group=group)
+                recv[ro[peer]:ro[peer + 1]] = buf
+        for r in reqs:
+            r.wait()
+    return recv
+
+
+def all_gather_rows(x, group=None):
+    """Concatenation over ranks of equally shaped per-rank rows."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the sharded index (device side)
+# ---------------------------------------------------------------------------------------------------------
+
+class ShardedIVF:
+    """Wraps a built `IVF`: this rank keeps the PQ codes of the lists it owns and everything replicated.
+
+    `query_batch(queries, k, n_probes)` is collective: every rank passes ITS OWN block of queries (the same
+    number on every rank) and gets the results of that block."""
+
+    def __init__(self, ivf, rank=None, world=None, group=None, drop_full_codes=True):
+        import torch.distributed as dist
+        self.ivf = ivf
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        full = ivf.to_device()
+        t = D.torch()
+        sizes = np.asarray(full["host_sizes"], dtype=np.int64)
+        chunks = np.asarray(full["host_chunks"], dtype=np.int64)              # tile-padded CSR of the full index
+        self.owner = assign_owners(sizes, self.world)
+        mine = np.nonzero(self.owner == self.rank)[0]
+        M = full["M"]
+        tile_bytes = M * 8                                                    # bytes per chunk in the native layout
+        local_chunks = np.zeros(len(sizes) + 1, dtype=np.int64)
+        nc = np.diff(chunks)
+        local_chunks[1:] = np.cumsum(np.where(self.owner == self.rank, nc, 0))
+        # native codes are tile-major and every list starts on a tile: a list is one contiguous byte range
+        codes = full["codes"]
+        parts = [codes[int(chunks[l]) * tile_bytes:int(chunks[l + 1]) * tile_bytes] for l in mine if chunks[l + 1] > chunks[l]]
+        local_codes = t.cat(parts) if parts else D.empty((16,), np.uint8)
+        dev = dict(full)
+        dev.update(local_codes=local_codes, local_chunk_off=D.upload(local_chunks),
+                   list_owner=D.upload(self.owner), n_chunks_total=int(local_chunks[-1]))
+        if drop_full_codes and self.world > 1:
+            dev["codes"] = None                                               # the full copy is not needed any more
+        self.dev = dev
+
+    # The three local phases of a batch; query_batch strings them together with the two collectives (the
+    # single-GPU test drives them for every rank in turn and moves the buffers by hand).
+    def _home(self, queries, n_probes):
+        """LUTs and probe lists of this rank's own queries."""
+        ivf, dev = self.ivf, self.dev
+        if isinstance(queries, np.ndarray):
+            queries = D.upload(np.ascontiguousarray(queries, dtype=np.float32))
+        Qh, d = queries.shape
+        assert dev["d"] == d
+        P = min(n_probes, dev["C"])
+        Rc = min(2 * P + 10, dev["C"])
+        with ivf._stage("lut"):
+            lut = ivf.pq.distance_tables(queries, signed=True, normalize=(ivf.metric == "angular"))
+        probes_h = ivf._coarse(dev, lut, Qh, P, Rc, "device")
+        return dict(lut=lut, probes=probes_h, Qh=Qh, P=P)
+
+    def _scan_owned(self, tables, probes, Qh, P):
+        """Scan, for ALL G*Qh queries, of the probed lists this rank owns. Returns the send buffer, its split
+        sizes, and the receive-side plan of this rank's own queries (offsets + split sizes)."""
+        ivf, dev, G, r = self.ivf, self.dev, self.world, self.rank
+        Q = G * Qh
+        seg_s, gb_s = ivf._plan(dev, probes, Q, P, PLAN_SEND, r, G, Qh)
+        seg_r, gb_r = ivf._plan(dev, probes, Q, P, PLAN_RECV, r, G, Qh, rows=Qh)
+        splits = D.torch().stack([gb_s[:G + 1], gb_r[:G + 1]]).cpu().numpy()   # the one host sync of the batch
+        est_s = D.empty((max(int(splits[0, G]), 16),), np.uint8)
+        ivf._scan(dev, tables, probes, Q, P, est_s, seg_s, codes_key="local_codes", off_key="local_chunk_off")
+        return est_s, splits[0, :G], seg_r, splits[1, :G]
+
+    def _finish(self, home, est_r, seg_r, k, pass_1):
+        """Ordered heap replay over the received estimates, exact rescoring, k nearest (device tensors)."""
+        return self.ivf._replay_rescore(self.dev, home["lut"]["q"], home["probes"], home["Qh"], home["P"], k, pass_1,
+                                        est_r, seg_r, "device")
+
+    def query_batch(self, queries, k, n_probes=1, pass_1=None, return_distances=False, to_host=True):
+        """Collective. queries: this rank's f32 (Qh, d) block (same Qh on every rank). Selections use the
+        device order (ascending distance, ties by heap slot). Returns the results of this rank's block."""
+        ivf, G = self.ivf, self.world
+        if pass_1 is None:
+            pass_1 = (n_probes + 1) * k + 1                                     # ref: ivf.py:135-136
+        home = self._home(queries, n_probes)
+        tables, probes = home["lut"]["tables"], home["probes"]
+        if G > 1:
+            with ivf._stage("all_gather"):
+                tables = all_gather_rows(tables, self.group)
+                probes = all_gather_rows(probes, self.group)
+        est_s, send_splits, seg_r, recv_splits = self._scan_owned(tables, probes, home["Qh"], home["P"])
+        if G > 1:
+            with ivf._stage("all_to_all"):
+                est_r = all_to_all_bytes(est_s, send_splits, recv_splits, self.group)
+        else:
+            est_r = est_s
+        ids, cnt, dst = self._finish(home, est_r, seg_r, k, pass_1)
+        if to_host:
+            ids, cnt, dst = ids.cpu().numpy(), cnt.cpu().numpy(), dst.cpu().numpy()
+        return (ids, cnt, dst) if return_distances else (ids, cnt)

@@ -180,6 +180,7 @@ def build_ivf(X, metric, n_clusters, pq=None, kmeans_iters=6, fit_sample=200_000
         sizes_full = t.cat([sizes, t.zeros(n_clusters - C, dtype=sizes.dtype, device=X.device)]).to(t.int32)
         ivf.__dict__["_dev"] = dict(
             C=C, M=M, n_lists=n_clusters, max_chunks=int(chunks.max().item()),
+            max_real_chunks=int((int(sizes.max().item()) + 15) // 16),
             codes=D.to_native(packed, packed.shape[0], M), n_chunks_total=int(packed.shape[0]), list_chunk_off=off_full,
             list_size=sizes_full, ids=ids_padded,
             center_codes=D.to_native(D.upload(center_td.packed), center_td.packed.shape[0], M),
