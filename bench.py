@@ -35,7 +35,7 @@ WORKLOADS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="glove", choices=list(WORKLOADS))
@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
     ap.add_argument("--cpu-worker", nargs=4, metavar=("DIR", "OUT", "SPEC", "SLICE"), default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="lists", choices=["lists", "replicas"],
+                    help="N>1: 'lists' = inverted lists sharded over the ranks, estimates exchanged with one NCCL "
+                         "all-to-all (north star); 'replicas' = every rank holds the whole index and its own queries")
     return ap.parse_args()
 
 
@@ -220,7 +223,19 @@ def main():
     # ---------------- our arm ---------------------------------------------------------------------------
     dev_batches = [torch.from_numpy(b).cuda() for b in batches]
     pinned = [torch.from_numpy(b).pin_memory() for b in batches]
-    kw = dict(k=args.k, n_probes=args.n_probes, order="device")
+    kw = dict(k=args.k, n_probes=args.n_probes)
+    sharded = world > 1 and args.shard == "lists"
+    if sharded:
+        # every rank built the same index (same seed); rank r keeps the codes of its lists and answers its own
+        # block of queries: a different slice of the query pool per rank, the same number on every rank
+        from tinyknn_b200.sharded import ShardedIVF
+        engine = ShardedIVF(ivf)
+        roll = rank * 4 * Qn // world
+        dev_batches = [torch.roll(b, roll, 0) for b in dev_batches]
+        pinned = [torch.roll(b, roll, 0).pin_memory() for b in pinned]
+        run = lambda q, **o: engine.query_batch(q, **kw, **o)
+    else:
+        run = lambda q, **o: ivf.query_batch(q, order="device", **kw, **o)
 
     def sync_all():
         if dist is not None:
@@ -238,9 +253,18 @@ def main():
         bad = sum(set(ids[i][:cnt[i]]) != set(O.ivf_query(S, batches[0][i], args.k, n_probes=args.n_probes, kernels=K))
                   for i in range(ns))
         parity = dict(checked=ns, id_set_mismatch=int(bad), oracle="oracle/restate.py + pq_oracle.c")
+    if sharded:
+        # the sharded path must return exactly what the unsharded path returns for the same queries
+        a = run(dev_batches[0][:256].contiguous(), return_distances=True)
+        b = ivf.query_batch(dev_batches[0][:256].contiguous(), order="device", return_distances=True, **kw)
+        same = all(np.array_equal(x, y) for x, y in zip(a, b))
+        flag = torch.tensor([0 if same else 1], device="cuda")
+        dist.all_reduce(flag)
+        if rank == 0:
+            parity["sharded_vs_single_gpu_mismatching_ranks"] = int(flag.item())
 
     for i in range(args.warmup):
-        ivf.query_batch(dev_batches[i % 4], to_host=False, **kw)
+        run(dev_batches[i % 4], to_host=False)
     sync_all()
     # -- value: inputs resident in HBM
     ivf.profile(True)
@@ -251,24 +275,24 @@ def main():
     torch.cuda.profiler.start()                 # `ncu --profile-from-start off` captures exactly the timed steps
     e0.record()
     for i in range(args.steps):
-        ivf.query_batch(dev_batches[i % 4], to_host=False, **kw)
+        run(dev_batches[i % 4], to_host=False)
     e1.record()
     sync_all()
     torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler else None
     launches = _lib.launch_count() - calls0            # kernels launched by libtinyknn_b200.so in the timed region (counted in C)
     stages = ivf.stage_times()
     ivf.profile(False)
     # -- e2e: host (pinned) queries in, ids out, through the public API
     for i in range(min(2, args.warmup)):
-        ivf.query_batch(pinned[i % 4].numpy(), **kw)
+        run(pinned[i % 4].numpy())
     sync_all()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        ids_h, cnt_h = ivf.query_batch(pinned[i % 4].numpy(), **kw)
+        ids_h, cnt_h = run(pinned[i % 4].numpy())
     sync_all()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
 
     tms = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
     if dist is not None:
@@ -283,12 +307,19 @@ def main():
         M = dev["M"]
         # algorithmic bytes of the dominant kernel (inverted-list scan): M/2 B of codes per scanned
         # (query, vector) + 1 B estimate written; scanned vectors counted from the probe lists of the last step
-        probes = ivf._last["probes"].cpu().numpy().astype(np.int64)
+        # (on this rank: with sharded lists, the segments of the lists rank 0 owns, for the queries of all ranks)
+        probes = ivf._last["scan_probes"].cpu().numpy().astype(np.int64)
+        present = ivf._last["scan_seg_off"].cpu().numpy() >= 0
         probes = np.where(probes < 0, probes + dev["n_lists"], probes)
         real_chunks = (dev["host_sizes"].astype(np.int64) + 15) // 16      # the reference pads each list to 16 (not to our tiles)
-        scanned = int(16 * real_chunks[probes].sum())
+        scanned = int(16 * (real_chunks[np.where(present, probes, 0)] * present).sum())
         scan_ms = float(np.mean(stages["scan"]))
         alg_bytes = scanned * (M // 2 + 1)
+        traffic = None
+        try:                                # dram__bytes_read+write per launch of this kernel, from the committed ncu capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload, {}).get("ivf_scan_fast")
+        except (OSError, ValueError):
+            pass
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -297,7 +328,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
         roof = dict(bound="hbm", kernel="ivf_scan", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback", traffic=None,
+                    peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback", traffic=traffic,
                     algorithmic_bytes_per_launch=alg_bytes, scanned_vectors_per_launch=scanned,
                     kernel_ms=scan_ms, codes_per_s=scanned / (scan_ms * 1e-3),
                     stage_ms={k: float(np.mean(v)) for k, v in stages.items()})
@@ -306,8 +337,10 @@ def main():
             cb = run_cpu_arm(ivf, batches[0], args.n_probes, args.k, args.cpu_seconds, os.cpu_count() or 1)[0]
         line = dict(metric="IVF-PQ queries/s", value=value, unit="queries/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
-                    vs_baseline=None, dtype="i8", data="synthetic", config=dict(cfg, parallelism="query-sharded replicas x%d" % world,
-                    l2="each step streams a >1 GB estimate buffer (> 126 MB L2); query batches rotate between steps"),
+                    vs_baseline=None, dtype="i8", data="synthetic", config=dict(cfg, parallelism=("lists sharded over %d ranks, all-to-all of estimates" % world) if sharded
+                                             else ("query-sharded replicas x%d" % world),
+                    l2="estimate buffer rewritten every step and query batches rotate between steps; the codes of this "
+                                   "workload (31 MB) are L2-resident by nature, see DESIGN.md"),
                     clocks=clocks, e2e=dict(value=e2e_v, unit="queries/s", h2d_bytes_per_step=int(Qn * w["d"] * 4),
                                             d2h_bytes_per_step=int(Qn * args.k * 8 + Qn * 4)),
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=cb, parity=parity)

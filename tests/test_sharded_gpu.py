@@ -1,0 +1,53 @@
+"""Two ranks, two GPUs, NCCL: the list-sharded path must return what the single-GPU path returns.
+Skipped on boxes with fewer than two GPUs (the CPU gloo test and the single-GPU phase test cover the logic)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from tinyknn_b200 import synth
+        from tinyknn_b200.sharded import ShardedIVF
+        X = synth.clustered(60_000 + 1024, 64, 100, seed=3)
+        ivf = synth.build_ivf(X[:60_000], "euclidean", 96, seed=3)
+        qs = X[60_000:].contiguous()
+        Qh = 1024 // world
+        mine = qs[rank * Qh:(rank + 1) * Qh].contiguous()
+        ref = ivf.query_batch(mine, 10, n_probes=6, order="device", return_distances=True)
+        got = ShardedIVF(ivf).query_batch(mine, 10, n_probes=6, return_distances=True)
+        bad = sum(not np.array_equal(a, b) for a, b in zip(ref, got))
+        np.save(out, np.array([bad]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_nccl_two_gpus_equals_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    outs = [str(tmp_path / ("r%d.npy" % r)) for r in range(2)]
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, outs[r])) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    assert all(int(np.load(o)[0]) == 0 for o in outs)

@@ -251,6 +251,7 @@ class IVF:
         st = D.stream_ptr()
         M, n_lists = dev["M"], dev["n_lists"]
         max_q_chunks = P * max(dev["max_real_chunks"], 1)
+        self._last.update(scan_probes=probes, scan_seg_off=seg_off)
         with self._stage("scan"):
             if _fp.SCAN_IMPL == "fast":
                 ws = D.scan_workspace(min(Q * max_q_chunks, max(1 << 20, Q * max_q_chunks // 4)))
