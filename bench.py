@@ -267,7 +267,6 @@ def main():
         run(dev_batches[i % 4], to_host=False)
     sync_all()
     # -- value: inputs resident in HBM
-    ivf.profile(True)
     calls0 = _lib.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -281,6 +280,12 @@ def main():
     torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - calls0            # kernels launched by libtinyknn_b200.so in the timed region (counted in C)
+    # -- per-kernel times for the roofline: the same steps again, one stream, a CUDA-event pair around every stage
+    #    (in the timed loop above the sub-batches of a step overlap on side streams, which no event pair can untangle)
+    ivf.profile(True)
+    one = {} if sharded else dict(sub_batches=1)
+    for i in range(min(args.steps, 10)):
+        run(dev_batches[i % 4], to_host=False, **one)
     stages = ivf.stage_times()
     ivf.profile(False)
     # -- e2e: host (pinned) queries in, ids out, through the public API
@@ -314,6 +319,9 @@ def main():
         real_chunks = (dev["host_sizes"].astype(np.int64) + 15) // 16      # the reference pads each list to 16 (not to our tiles)
         scanned = int(16 * (real_chunks[np.where(present, probes, 0)] * present).sum())
         scan_ms = float(np.mean(stages["scan"]))
+        flagged = None
+        if "patch_ws" in ivf._last:                 # chunks whose certificate failed in the last scan (recomputed exactly)
+            flagged = int(ivf._last["patch_ws"][:8].cpu().numpy().view(np.int64)[0])
         alg_bytes = scanned * (M // 2 + 1)
         traffic = None
         try:                                # dram__bytes_read+write per launch of this kernel, from the committed ncu capture
@@ -330,7 +338,8 @@ def main():
         roof = dict(bound="hbm", kernel="ivf_scan", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                     peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback", traffic=traffic,
                     algorithmic_bytes_per_launch=alg_bytes, scanned_vectors_per_launch=scanned,
-                    kernel_ms=scan_ms, codes_per_s=scanned / (scan_ms * 1e-3),
+                    kernel_ms=scan_ms, codes_per_s=scanned / (scan_ms * 1e-3), flagged_chunks=flagged,
+                    kernel_timing="CUDA events around the launch, one stream, %d steps after the timed region" % min(args.steps, 10),
                     stage_ms={k: float(np.mean(v)) for k, v in stages.items()})
         cb = None
         if not args.no_cpu_baseline:

@@ -17,6 +17,7 @@ heap contents.
   order="device" : everything stays on the GPU; ties and order are resolved as "ascending distance,
                    then heap slot". One host sync per batch. This is the throughput mode.
 """
+import os
 from contextlib import contextmanager
 
 import numpy as np
@@ -28,6 +29,24 @@ from .fast_pq import FastPQ, TransformedData, query_pq  # noqa: F401  (ivf.py:5 
 from .utils import timer, knn_brute, group_data_by_indices, bottom_k
 
 _WORKSPACE_BYTES = 2 << 30          # cap of the per-batch estimate buffer (queries are sub-batched)
+_N_STREAMS = int(os.environ.get("TKB_STREAMS", "2"))
+_SUB_QUERIES = int(os.environ.get("TKB_SUB_QUERIES", "5000"))      # target queries per sub-batch
+_streams = {}
+
+
+def _side_streams(n):
+    """n side streams of the current device (created once)."""
+    t = D.torch()
+    pool = _streams.setdefault(t.cuda.current_device(), [])
+    while len(pool) < n:
+        pool.append(t.cuda.Stream())
+    return pool[:n]
+
+
+def _sub_batches(Q):
+    if _N_STREAMS <= 1 or Q < 2 * _SUB_QUERIES:
+        return 1
+    return max(2, Q // _SUB_QUERIES)
 
 
 class IVF:
@@ -173,10 +192,11 @@ class IVF:
         return ids[0][:counts[0]]
 
     def query_batch(self, queries, k, n_probes=1, pass_1=None, order="device", return_distances=False,
-                    to_host=True):
+                    to_host=True, sub_batches=None):
         """Batched IVF.query (new, additive API). queries: f32 (Q, d), host array or device tensor.
         Returns (ids, counts[, dists]): ids int64 (Q, k) padded with -1, counts int32 (Q,).
-        With to_host=False (order="device" only) the results stay on the GPU as torch tensors."""
+        With to_host=False (order="device" only) the results stay on the GPU as torch tensors.
+        sub_batches (order="device"): split the batch over side streams (None: automatic, 1: one stream)."""
         assert order in ("device", "numpy")
         assert to_host or order == "device"
         dev = self.to_device()
@@ -191,14 +211,42 @@ class IVF:
         if pass_1 is None:
             pass_1 = (n_probes + 1) * k + 1                             # ref: ivf.py:135-136
         qb = int(max(1, min(Q, _WORKSPACE_BYTES // max(1, P * 16 * max(dev["max_real_chunks"], 1)))))
+        # Sub-batches on alternating side streams: the latency-bound stages of one sub-batch (heap replay, row
+        # gathers) overlap the issue-bound scan of the next. Only in throughput mode; order="numpy" syncs per stage.
+        n_sub = 1 if order != "device" else (_sub_batches(Q) if sub_batches is None else max(1, int(sub_batches)))
+        if n_sub > 1:
+            qb = min(qb, -(-Q // n_sub))
         outs = []
-        for lo in range(0, Q, qb):
-            qs = queries[lo:min(Q, lo + qb)]
-            if isinstance(qs, np.ndarray):
-                qs = D.upload(qs)
-            outs.append(self._query_block(dev, qs, k, P, Rc, pass_1, order))
+        res = None
+        if order == "device":                                           # every block writes its rows of one result
+            ddt = np.float32 if dev["data_dtype"] == DTYPE_F32 else np.float64
+            res = (D.empty((Q, k), np.int64), D.empty((Q,), np.int32), D.empty((Q, k), ddt))
+        blk = lambda lo, hi: None if res is None else tuple(r[lo:hi] for r in res)
+        if n_sub > 1:
+            if isinstance(queries, np.ndarray):
+                queries = t.from_numpy(queries)
+                if not queries.is_pinned():
+                    queries = D.upload(queries.numpy())
+            cur = t.cuda.current_stream()
+            pool = _side_streams(min(n_sub, _N_STREAMS))
+            for s_ in pool:
+                s_.wait_stream(cur)
+            for i, lo in enumerate(range(0, Q, qb)):
+                with t.cuda.stream(pool[i % len(pool)]):
+                    qs = queries[lo:min(Q, lo + qb)]
+                    if not qs.is_cuda:
+                        qs = qs.to(D.device(), non_blocking=True)
+                    self._query_block(dev, qs, k, P, Rc, pass_1, order, blk(lo, min(Q, lo + qb)))
+            for s_ in pool:
+                cur.wait_stream(s_)
+        else:
+            for lo in range(0, Q, qb):
+                qs = queries[lo:min(Q, lo + qb)]
+                if isinstance(qs, np.ndarray):
+                    qs = D.upload(qs)
+                outs.append(self._query_block(dev, qs, k, P, Rc, pass_1, order, blk(lo, min(Q, lo + qb))))
         if order == "device":
-            ids, cnt, dst = (outs[0] if len(outs) == 1 else tuple(t.cat([o[i] for o in outs]) for i in range(3)))
+            ids, cnt, dst = res
             if to_host:
                 ids, cnt, dst = ids.cpu().numpy(), cnt.cpu().numpy(), dst.cpu().numpy()
         else:
@@ -264,7 +312,7 @@ class IVF:
                                            D.ptr(dev["list_size"]), n_lists, M, D.ptr(tables), D.ptr(probes), Q, P,
                                            D.ptr(est), 0, D.ptr(seg_off), max(dev["max_real_chunks"], 1), _fp._order(), 1, st))
 
-    def _replay_rescore(self, dev, qn, probes, Q, P, k, pass_1, est, seg_off, order):
+    def _replay_rescore(self, dev, qn, probes, Q, P, k, pass_1, est, seg_off, order, out=None):
         """Ordered exact heap replay over the probed lists, then exact rescoring and the k nearest
         (ref: ivf.py:137-163). `probes`/`seg_off` are the rows of these Q queries."""
         st = D.stream_ptr()
@@ -283,7 +331,7 @@ class IVF:
                                            D.ptr(qn), D.ptr(hi_), Q, pass_1, D.ptr(dd), st))
         self._last.update(probes=probes, heap_idx=hi_, heap_val=hv_)
         if order == "device":
-            oi, od, oc = D.empty((Q, k), np.int64), D.empty((Q, k), ddt), D.empty((Q,), np.int32)
+            oi, oc, od = out if out is not None else (D.empty((Q, k), np.int64), D.empty((Q,), np.int32), D.empty((Q, k), ddt))
             with self._stage("select"):
                 check(lib.tkb_select_topk_dev(D.ptr(hi_), D.ptr(dd), dev["data_dtype"], Q, pass_1, k,
                                               D.ptr(oi), D.ptr(od), D.ptr(oc), st))
@@ -314,7 +362,7 @@ class IVF:
                                        D.stream_ptr()))
         return seg_off, gb
 
-    def _query_block(self, dev, qs, k, P, Rc, pass_1, order):
+    def _query_block(self, dev, qs, k, P, Rc, pass_1, order, out=None):
         Q = qs.shape[0]
         # 1. LUTs (ref: ivf.py:125-128)
         with self._stage("lut"):
@@ -325,4 +373,4 @@ class IVF:
         seg_off, _ = self._plan(dev, probes, Q, P)
         est = D.empty((Q * P * 16 * max(dev["max_real_chunks"], 1),), np.uint8)      # upper bound; only the planned part is touched
         self._scan(dev, lut["tables"], probes, Q, P, est, seg_off)
-        return self._replay_rescore(dev, lut["q"], probes, Q, P, k, pass_1, est, seg_off, order)
+        return self._replay_rescore(dev, lut["q"], probes, Q, P, k, pass_1, est, seg_off, order, out)
