@@ -253,6 +253,14 @@ def main():
         bad = sum(set(ids[i][:cnt[i]]) != set(O.ivf_query(S, batches[0][i], args.k, n_probes=args.n_probes, kernels=K))
                   for i in range(ns))
         parity = dict(checked=ns, id_set_mismatch=int(bad), oracle="oracle/restate.py + pq_oracle.c")
+        # the timed (throughput) mode: fused kernel == stage-by-stage kernels, and its ids == the oracle run with the
+        # same selection rule (ascending distance, ties by heap slot)
+        fa = ivf.query_batch(batches[0][:256], order="device", return_distances=True, fused=True, **kw)
+        fb = ivf.query_batch(batches[0][:256], order="device", return_distances=True, fused=False, **kw)
+        parity["fused_vs_staged_mismatch"] = int(sum(not np.array_equal(x, y) for x, y in zip(fa, fb)))
+        parity["device_order_id_set_mismatch"] = int(sum(
+            set(fa[0][i][:fa[1][i]]) != set(O.ivf_query(S, batches[0][i], args.k, n_probes=args.n_probes, kernels=K,
+                                                        select=O.bottom_k_sorted)) for i in range(ns)))
     if sharded:
         # the sharded path must return exactly what the unsharded path returns for the same queries
         a = run(dev_batches[0][:256].contiguous(), return_distances=True)
@@ -287,6 +295,13 @@ def main():
     for i in range(min(args.steps, 10)):
         run(dev_batches[i % 4], to_host=False, **one)
     stages = ivf.stage_times()
+    last = dict(ivf._last)
+    staged = None
+    if "fused" in stages and not sharded:           # the stage-by-stage kernels of the same path, for the scan kernel's own roofline
+        ivf.profile(True)
+        for i in range(min(args.steps, 5)):
+            run(dev_batches[i % 4], to_host=False, sub_batches=1, fused=False)
+        staged = ivf.stage_times()
     ivf.profile(False)
     # -- e2e: host (pinned) queries in, ids out, through the public API
     for i in range(min(2, args.warmup)):
@@ -313,33 +328,54 @@ def main():
         # algorithmic bytes of the dominant kernel (inverted-list scan): M/2 B of codes per scanned
         # (query, vector) + 1 B estimate written; scanned vectors counted from the probe lists of the last step
         # (on this rank: with sharded lists, the segments of the lists rank 0 owns, for the queries of all ranks)
-        probes = ivf._last["scan_probes"].cpu().numpy().astype(np.int64)
-        present = ivf._last["scan_seg_off"].cpu().numpy() >= 0
+        probes = last["scan_probes"].cpu().numpy().astype(np.int64)
+        present = np.ones_like(probes, dtype=bool) if last.get("scan_seg_off") is None else last["scan_seg_off"].cpu().numpy() >= 0
+        present &= probes != -(2 ** 31)
         probes = np.where(probes < 0, probes + dev["n_lists"], probes)
         real_chunks = (dev["host_sizes"].astype(np.int64) + 15) // 16      # the reference pads each list to 16 (not to our tiles)
         scanned = int(16 * (real_chunks[np.where(present, probes, 0)] * present).sum())
-        scan_ms = float(np.mean(stages["scan"]))
-        flagged = None
-        if "patch_ws" in ivf._last:                 # chunks whose certificate failed in the last scan (recomputed exactly)
-            flagged = int(ivf._last["patch_ws"][:8].cpu().numpy().view(np.int64)[0])
-        alg_bytes = scanned * (M // 2 + 1)
-        traffic = None
-        try:                                # dram__bytes_read+write per launch of this kernel, from the committed ncu capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload, {}).get("ivf_scan_fast")
-        except (OSError, ValueError):
-            pass
+        Qk = probes.shape[0]
+        fused_run = "fused" in stages
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
-        roof = dict(bound="hbm", kernel="ivf_scan", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback", traffic=traffic,
-                    algorithmic_bytes_per_launch=alg_bytes, scanned_vectors_per_launch=scanned,
-                    kernel_ms=scan_ms, codes_per_s=scanned / (scan_ms * 1e-3), flagged_chunks=flagged,
-                    kernel_timing="CUDA events around the launch, one stream, %d steps after the timed region" % min(args.steps, 10),
+        try:                                # dram__bytes_read+write per launch, from the committed ncu captures
+            traffic_all = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload, {})
+        except (OSError, ValueError):
+            traffic_all = {}
+
+        def scan_roof(ms, flagged):
+            ab = scanned * (M // 2 + 1)
+            return dict(kernel="ivf_scan_fast", achieved=ab / (ms * 1e-3) / 1e9, peak=peak, unit="GB/s",
+                        frac=ab / (ms * 1e-3) / 1e9 / peak, traffic=traffic_all.get("ivf_scan_fast"),
+                        algorithmic_bytes_per_launch=ab, kernel_ms=ms, codes_per_s=scanned / (ms * 1e-3), flagged_chunks=flagged)
+
+        def counter(ws_key):
+            return int(last[ws_key][:16].cpu().numpy().view(np.int64)[0 if ws_key == "patch_ws" else 1]) if ws_key in last else None
+
+        if fused_run:
+            # one launch = LUT rows read (16*M B/query) + M/2 code bytes per scanned vector + the raw rows of the heap's
+            # candidates (R*d*itemsize per query; every heap is full on this workload); the estimates (1 B per scanned
+            # vector, written and read back) stay in the CTA's L2-resident scratch and are NOT counted
+            k_ms = float(np.mean(stages["fused"]))
+            R1 = (args.n_probes + 1) * args.k + 1
+            itemsize = 4 if dev["data_dtype"] == 0 else 8
+            alg_bytes = scanned * (M // 2) + Qk * 16 * M + Qk * R1 * dev["d"] * itemsize
+            roof = dict(bound="hbm", kernel="ivf_fused", achieved=alg_bytes / (k_ms * 1e-3) / 1e9, peak=peak, unit="GB/s",
+                        frac=alg_bytes / (k_ms * 1e-3) / 1e9 / peak, traffic=traffic_all.get("ivf_fused"),
+                        algorithmic_bytes_per_launch=alg_bytes, scanned_vectors_per_launch=scanned, kernel_ms=k_ms,
+                        codes_per_s=scanned / (k_ms * 1e-3), flagged_chunks=counter("fused_ws"))
+            if staged:
+                roof["scan_kernel_alone"] = scan_roof(float(np.mean(staged["scan"])), None)
+                roof["staged_stage_ms"] = {k: float(np.mean(v)) for k, v in staged.items()}
+        else:
+            roof = dict(bound="hbm", scanned_vectors_per_launch=scanned, **scan_roof(float(np.mean(stages["scan"])), counter("patch_ws")))
+        roof.update(peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                    kernel_timing="CUDA events around the launch on its stream, one stream, %d steps right after the timed region"
+                                  % min(args.steps, 10),
                     stage_ms={k: float(np.mean(v)) for k, v in stages.items()})
         cb = None
         if not args.no_cpu_baseline:

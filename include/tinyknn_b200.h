@@ -208,6 +208,32 @@ TKB_API int tkb_select_probes_dev(const int64_t *heap_idx, const void *dists, in
 TKB_API int tkb_select_topk_dev(const int64_t *heap_idx, const void *dists, int dists_dtype, int Q, int R,
                         int k, int64_t *out_ids, void *out_dists, int32_t *out_count, void *stream);
 
+/* The IVF.query body after probe selection as ONE kernel (ref: tinyknn/ivf.py:135-163): for each query, scan of
+ * the probed lists (query_pq_*'s scan half), exact replay of the reference heap of R slots in probe order
+ * (query_pq_*'s heap half with labels = ids), removal of the -1 padding, exact distances of the candidates
+ * (knn_brute1, ref: tinyknn/utils.py:89-92) and the k nearest (device order: ascending distance, ties by heap
+ * slot). Same results as tkb_ivf_scan_native_dev + tkb_ivf_replay_fresh_dev + tkb_gather_dists_dev +
+ * tkb_select_topk_dev, bit for bit; signed tables only (ref: tinyknn/ivf.py:138,148).
+ * Requires labels that are unique across the lists (one list per point; see tkb_ivf_replay_fresh_dev). Negative
+ * probe entries index from the end like a Python list and may visit a list twice: the reference's label dedupe
+ * is reproduced.
+ *   native/list_chunk_off/list_size/ids : the index, as for tkb_ivf_scan_native_dev / tkb_ivf_replay_dev
+ *   tables uint8[Q][M][16], probes int32[Q][P], queries f32[Q][d] (normalised for angular), rows [n_rows][d]
+ *   max_list_chunks : ceil(size/16) of the largest list
+ *   out_ids int64[Q][k] (-1 padded), out_dists f32/f64[Q][k] or NULL, out_count int32[Q]
+ *   heap_idx int64[Q][R] / heap_val int32[Q][R] : optional outputs, the reference's final heap arrays
+ *   workspace : 16-byte aligned device scratch of tkb_ivf_query_fused_workspace() bytes (a smaller one limits
+ *               the number of resident CTAs); its second 8-byte word returns the number of recomputed chunks */
+TKB_API int tkb_ivf_query_fused_workspace(int Q, int P, int R, int M, int order, int rows_dtype,
+                                  int64_t max_list_chunks, int64_t *bytes);
+TKB_API int tkb_ivf_query_fused_dev(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists,
+                            int M, const uint8_t *tables, const int32_t *probes, int Q, int P, const int64_t *ids,
+                            const void *rows, int rows_dtype, int64_t n_rows, int d, const float *queries,
+                            int R, int k, int order, int64_t max_list_chunks,
+                            int64_t *out_ids, void *out_dists, int32_t *out_count,
+                            int64_t *heap_idx, int32_t *heap_val,
+                            void *workspace, int64_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

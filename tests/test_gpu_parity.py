@@ -484,6 +484,28 @@ def test_replay_kernels_agree_with_oracle_fresh_heap():
             assert np.array_equal(a2[q], oi) and np.array_equal(b2[q], ov), (trial, q)
 
 
+@pytest.mark.parametrize("R,n", [(255, 9000), (256, 9000), (300, 20000), (1291, 60000), (4000, 30000), (70000, 90000)])
+def test_replay_deep_heaps(R, n):
+    """Heaps deeper than 8 levels: the pipelined queue replay runs 8 lanes per query (R <= 65535) or hands over to
+    the unpipelined kernel; heap arrays == oracle slot for slot, signed and unsigned."""
+    from tinyknn_b200._lib import lib, check
+    rng = np.random.default_rng(R)
+    nck = -(-n // 16)
+    for signd in (True, False):
+        Q = 5
+        est = rng.integers(0, 256, size=(Q, 16 * nck), dtype=np.uint8)
+        est[1] = (est[1] // 32 + 90).astype(np.uint8)                                         # few distinct values: ties everywhere
+        edev = D.upload(est)
+        hi, hv = D.empty((Q, R), np.int64), D.empty((Q, R), np.int32)
+        check(lib.tkb_replay_fresh_dev(D.ptr(edev), 16 * nck, nck, n, D.ptr(hi), D.ptr(hv), Q, R, int(signd), D.stream_ptr()))
+        a, b = hi.cpu().numpy(), hv.cpu().numpy()
+        for q in range(Q):
+            oi, ov = np.zeros(R, np.int64), np.zeros(R, np.int32)
+            O.init_heap(oi, ov, signd)
+            O.replay(est[q], n, oi, ov, signd)
+            assert np.array_equal(a[q], oi) and np.array_equal(b[q], ov), (signd, q)
+
+
 def test_ivf_duplicate_labels_use_dedupe_path():
     """build_probes=2 puts every point in two lists: labels repeat, the reference dedupes on insert."""
     np.random.seed(5)

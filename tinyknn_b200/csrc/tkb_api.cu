@@ -279,4 +279,23 @@ int tkb_select_topk_dev(const int64_t *heap_idx, const void *dists, int dists_dt
     return launch_select_topk(heap_idx, dists, dists_dtype, Q, R, k, out_ids, out_dists, out_count, (cudaStream_t)stream);
 }
 
+int tkb_ivf_query_fused_workspace(int Q, int P, int R, int M, int order, int rows_dtype,
+                                  int64_t max_list_chunks, int64_t *bytes)
+{
+    return fused_workspace_bytes(Q, P, R, M, order, rows_dtype, max_list_chunks, bytes);
+}
+
+int tkb_ivf_query_fused_dev(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists,
+                            int M, const uint8_t *tables, const int32_t *probes, int Q, int P, const int64_t *ids,
+                            const void *rows, int rows_dtype, int64_t n_rows, int d, const float *queries,
+                            int R, int k, int order, int64_t max_list_chunks,
+                            int64_t *out_ids, void *out_dists, int32_t *out_count,
+                            int64_t *heap_idx, int32_t *heap_val,
+                            void *workspace, int64_t workspace_bytes, void *stream)
+{
+    return launch_ivf_query_fused(native, list_chunk_off, list_size, n_lists, M, tables, probes, Q, P, ids, rows, rows_dtype,
+                                  n_rows, d, queries, R, k, order, max_list_chunks, out_ids, out_dists, out_count,
+                                  heap_idx, heap_val, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 }  // extern "C"

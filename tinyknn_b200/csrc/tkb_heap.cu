@@ -353,6 +353,224 @@ replay_rq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Queue replay, pipelined ("rq2"): same rounds as replay_rq_kernel, but
+//   * heap entries and queue records are ONE 32-bit word: value in the top byte (stored so that a signed compare of
+//     the words' top bytes orders them: int8 as is, uint8 ^ 0x80), stream position in the low 24 bits. A query's heap
+//     is a contiguous array (node i at word i+1, so that the two children of a node are one aligned 8-byte load),
+//     padded with sentinels (value -128: never "strictly greater" than anything), so leaves need no bounds test;
+//   * the sift-downs of CONSECUTIVE inserts of a query are pipelined over L lanes: an insert replaces the root and
+//     walks down one level per step; the next insert may start two steps later, because by then the previous one has
+//     finished writing levels 0 and 1, and from there on the two stay two levels apart (a step reads level s+1 and
+//     writes level s). The admission test of the next record only needs the root, which an insert fixes in its first
+//     step. So a query retires one insert every two steps instead of one every ~depth steps, and the result is the
+//     reference's array, slot for slot (ref: _fast_pq.pyx:274-307; the bound is still frozen per 16-vector chunk).
+// Preconditions on top of replay_rq_kernel's: stream positions < 2^24 - 1, depth of the heap <= 2L steps.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t RQ2_EMPTY = 0x00ffffffu;       // payload of a heap slot that was never filled
+constexpr uint32_t RQ2_SENTINEL = 0x80ffffffu;    // value -128
+
+template <bool SIGNED, int L>
+__global__ void __launch_bounds__(RQ_THREADS)
+replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, const int64_t *__restrict__ seg_off,
+                  int64_t n_chunks0, int n0, const int64_t *__restrict__ list_chunk_off,
+                  const int32_t *__restrict__ list_size, int n_lists, const int64_t *__restrict__ ids,
+                  const int32_t *__restrict__ probes, int Q, int P, int64_t *__restrict__ heap_idx,
+                  int32_t *__restrict__ heap_val, int R, int *__restrict__ fallback, int QPC, int QCAP)
+{
+    extern __shared__ __align__(16) unsigned char rq_sm[];
+    const int HS = 2 * R + 4;                                              // words per heap: slot i at word i+1, children of R-1 included
+    uint32_t *H = reinterpret_cast<uint32_t *>(rq_sm);                     // [QPC][HS]
+    uint32_t *QU = H + (size_t)QPC * HS;                                   // [QPC][QCAP+2]
+    int *cum = reinterpret_cast<int *>(QU + (size_t)QPC * (QCAP + 2));     // [QPC][P+1] real chunks before segment s
+    int *s_cursor = cum + (size_t)QPC * (P + 1);
+    int *s_seg = s_cursor + QPC, *s_bound = s_seg + QPC, *s_count = s_bound + QPC, *s_round = s_count + QPC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = RQ_THREADS / 32;
+    const int q0 = blockIdx.x * QPC;
+    const uint32_t flip = SIGNED ? 0u : 0x80u;                             // stored byte = value ^ flip
+    const int init = 127;                                                  // stored form of the reference's 127 / 255
+
+    for (int i = tid; i < QPC * HS; i += RQ_THREADS) {
+        const int j = i % HS;
+        H[i] = (j >= 1 && j <= R) ? (((uint32_t)init << 24) | RQ2_EMPTY) : RQ2_SENTINEL;
+    }
+    for (int t = tid; t < QPC; t += RQ_THREADS) {
+        const int q = q0 + t;
+        int *c = cum + (size_t)t * (P + 1);
+        bool ok = q < Q;
+        int run = 0;
+        c[0] = 0;
+        for (int s = 0; s < P; s++) {
+            int nc = 0;
+            if (ok) {
+                if (mode == 1) {
+                    const int l = probes[(size_t)q * P + s];
+                    if (l < 0 && l != PROBE_SKIP) ok = false;              // Python-wrapped index: lists may repeat
+                    else if (l != PROBE_SKIP) nc = (list_size[l] + 15) >> 4;
+                } else {
+                    int64_t r = ((int64_t)n0 + 15) >> 4;
+                    nc = (int)(r < n_chunks0 ? r : n_chunks0);
+                }
+            }
+            run += nc;
+            c[s + 1] = run;
+        }
+        if (run >= (1 << 20) - 1) ok = false;                              // positions must fit 24 bits
+        if (q < Q && fallback) fallback[q] = ok ? 0 : 1;
+        if (!ok) for (int s = 0; s <= P; s++) c[s] = 0;
+        s_cursor[t] = 0; s_seg[t] = 0; s_bound[t] = init; s_count[t] = 0; s_round[t] = 0;
+    }
+    __syncthreads();
+
+    for (;;) {
+        // ---- produce (as in replay_rq_kernel; records are packed words) -----------------------------
+        bool more = false;
+        for (int t = warp; t < QPC; t += n_warps) {
+            const int *c = cum + (size_t)t * (P + 1);
+            const int total = c[P];
+            const int cursor = s_cursor[t];
+            if (cursor >= total) { if (lane == 0) s_count[t] = 0; continue; }
+            const int q = q0 + t;
+            const int bound = s_bound[t];                                  // stored form
+            int W = s_round[t] == 0 ? ((R + 15) >> 4) + 1 : (cursor < 32 ? 32 : cursor);
+            if (W > (1 << 16)) W = 1 << 16;
+            int end = (total - cursor < W) ? total : cursor + W;
+            int count = 0, sg = s_seg[t];
+            uint32_t *qu = QU + (size_t)t * (QCAP + 2);
+            for (int base = cursor; base < end; base += 32) {
+                const int cc = base + lane;
+                const bool act = cc < end;
+                uint32_t m = 0;
+                uint4 e = make_uint4(0, 0, 0, 0);
+                int sl = sg;
+                if (act) {
+                    while (cc >= c[sl + 1]) sl++;
+                    const int local = cc - c[sl];
+                    int n;
+                    const uint8_t *ep;
+                    if (mode == 1) {
+                        n = list_size[probes[(size_t)q * P + sl]];
+                        ep = est + (seg_off ? seg_off[(size_t)q * P + sl] : ((int64_t)q * P + sl) * stride);
+                    } else {
+                        n = n0;
+                        ep = est + (int64_t)q * stride;
+                    }
+                    e = ldg_nc_u4(reinterpret_cast<const uint4 *>(ep) + local);
+                    if (!SIGNED) { e.x ^= 0x80808080u; e.y ^= 0x80808080u; e.z ^= 0x80808080u; e.w ^= 0x80808080u; }
+                    const int rem = n - 16 * local;
+                    m = cand_mask16<true>(e, bound) & (rem >= 16 ? 0xffffu : ((1u << rem) - 1u));
+                }
+                const int last = end - 1 - base;
+                sg = __shfl_sync(FULL, sl, last < 31 ? last : 31);
+                const int cnt = __popc(m);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                const int tot = __shfl_sync(FULL, incl, 31);
+                bool cut = false;
+                int keep_tot = tot;
+                if (count + tot > QCAP) {
+                    const unsigned over = __ballot_sync(FULL, count + incl > QCAP);
+                    const int cl = __ffs(over) - 1;
+                    keep_tot = __shfl_sync(FULL, incl - cnt, cl);
+                    sg = __shfl_sync(FULL, sl, cl);
+                    if (lane >= cl) m = 0;
+                    end = base + cl;
+                    cut = true;
+                }
+                int k = count + incl - cnt;
+                const uint32_t ws[4] = {e.x, e.y, e.z, e.w};
+                while (m) {
+                    const int v = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t byte = (ws[v >> 2] >> (8 * (v & 3))) & 0xffu;
+                    qu[k++] = (byte << 24) | (16u * (uint32_t)cc + v);
+                }
+                count += keep_tot;
+                if (cut) break;
+            }
+            if (lane == 0) { s_cursor[t] = end; s_seg[t] = sg; s_count[t] = count; s_round[t] = 1; qu[count] = RQ2_SENTINEL; qu[count + 1] = RQ2_SENTINEL; }
+            more = true;
+        }
+        if (!__syncthreads_or(more)) break;
+        // ---- consume: L lanes per query, 32/L queries per warp. The step is branch-free (the queries of a warp are in
+        //      different states; divergent code would be issued once per state and the loop is issue-bound) -----------
+        {
+            constexpr int QPW = 32 / L;
+            const int role = lane % L;
+            for (int tb = warp * QPW; tb < QPC; tb += n_warps * QPW) {
+                const int t = tb + lane / L;
+                const bool mine = t < QPC;
+                uint32_t *hw = H + (size_t)(mine ? t : 0) * HS;
+                const uint32_t *qu = QU + (size_t)(mine ? t : 0) * (QCAP + 2);
+                const int cnt = mine ? s_count[t] : 0;
+                int qi = 0, next_role = 0, cooldown = 0, frozen = 0;       // replicated over the query's L lanes
+                uint32_t cur_chunk = 0xffffffffu;
+                bool active = false;
+                uint32_t rw = 0, jo = 0;
+                int ev = 0;
+                while (__any_sync(FULL, active || qi < cnt)) {
+                    // admission: at most two records per step (the queue is padded with two sentinels)
+                    const uint32_t r0 = qu[qi], r1 = qu[qi + 1];
+                    const int rootv = (int)hw[1] >> 24;
+                    const bool ok0 = cooldown == 0 && qi < cnt;
+                    const uint32_t ch0 = (r0 & 0xffffffu) >> 4, ch1 = (r1 & 0xffffffu) >> 4;
+                    const int fr0 = (ok0 && ch0 != cur_chunk) ? rootv : frozen;          // first record of a chunk freezes the bound
+                    const bool acc0 = ok0 && ((int)r0 >> 24) < fr0;
+                    const bool ok1 = ok0 && !acc0 && qi + 1 < cnt;
+                    const int fr1 = (ok1 && ch1 != ch0) ? rootv : fr0;
+                    const bool acc1 = ok1 && ((int)r1 >> 24) < fr1;
+                    cur_chunk = ok1 ? ch1 : (ok0 ? ch0 : cur_chunk);
+                    frozen = fr1;
+                    qi += (ok0 ? 1 : 0) + (ok1 ? 1 : 0);
+                    const bool start = acc0 || acc1;
+                    if (start && role == next_role) { active = true; rw = acc0 ? r0 : r1; ev = (int)rw >> 24; jo = 0; }
+                    next_role = start ? (next_role + 1 == L ? 0 : next_role + 1) : next_role;
+                    cooldown = start ? 1 : (cooldown ? cooldown - 1 : 0);                 // next admission two steps from now
+                    // one level of the sift-down (ref: _fast_pq.pyx:290-307)
+                    const uint2 ch2 = *reinterpret_cast<const uint2 *>(hw + 2 * jo + 2);
+                    const int vl = (int)ch2.x >> 24, vr = (int)ch2.y >> 24;
+                    const bool pr = vr > vl;                               // the right child wins only when strictly greater
+                    const int vc = pr ? vr : vl;
+                    const bool stop = vc <= ev;                            // no child strictly greater: the record stays here
+                    if (active) hw[jo + 1] = stop ? rw : (pr ? ch2.y : ch2.x);
+                    jo = 2 * jo + 1 + (pr ? 1u : 0u);
+                    active = active && !stop;
+                    if (!active) jo = 0;
+                    __syncwarp();
+                }
+                if (mine && role == 0) s_bound[t] = (int)hw[1] >> 24;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- resolve labels and write the heap arrays --------------------------------------------------
+    for (int i = tid; i < R * QPC; i += RQ_THREADS) {
+        const int t = i / R, j = i - t * R;
+        const int q = q0 + t;
+        if (q >= Q) continue;
+        const uint32_t w = H[(size_t)t * HS + j + 1];
+        const uint32_t pay = w & 0xffffffu;
+        int64_t label = -1;
+        if (pay != RQ2_EMPTY) {
+            const int cc = (int)(pay >> 4), v = (int)(pay & 15u);
+            if (mode == 1) {
+                const int *c = cum + (size_t)t * (P + 1);
+                int lo = 0, hi = P;
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (c[mid] <= cc) lo = mid; else hi = mid; }
+                const int l = probes[(size_t)q * P + lo];
+                label = ids[16 * (list_chunk_off[l] + (cc - c[lo])) + v];
+            } else {
+                label = 16 * (int64_t)cc + v;
+            }
+        }
+        const uint32_t b = (w >> 24) ^ flip;
+        heap_idx[(size_t)q * R + j] = label;
+        heap_val[(size_t)q * R + j] = SIGNED ? (int)(int8_t)b : (int)b;
+    }
+}
+
 // warp-per-query IVF replay restricted to the queries flagged by the queue-replay kernel
 template <bool SIGNED>
 __global__ void __launch_bounds__(32 * REPLAY_WARPS)
@@ -429,16 +647,36 @@ int launch_ivf_replay(const uint8_t *est, int64_t slot_stride, const int64_t *se
 
 // Queue-replay launch geometry: QPC queries per CTA (a power of two <= 16), queue capacity QCAP records,
 // LPW lanes (queries) per consumer warp.
-struct RqGeom { int qpc, qcap, lpw; size_t smem; };
+struct RqGeom { int qpc, qcap, lpw; size_t smem; int v2, lanes; };
 
 static size_t rq_smem(int R, int P, int qpc, int qcap)
 {
     return (size_t)qpc * (8 * ((size_t)R + 1) + 8 * ((size_t)qcap + 1) + 4 * ((size_t)P + 1) + 20) + 16;
 }
 
-static bool rq_geometry(int Q, int R, int P, RqGeom &g)
+static size_t rq2_smem(int R, int P, int qpc, int qcap)
+{
+    return (size_t)qpc * (4 * (2 * (size_t)R + 4) + 4 * ((size_t)qcap + 2) + 4 * ((size_t)P + 1) + 20) + 16;
+}
+
+static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 0)
 {
     if (R <= 0 || P <= 0) return false;
+    static int v2_env = -1;
+    if (v2_env < 0) { const char *e = getenv("TKB_RQ2"); v2_env = e ? atoi(e) : 1; }
+    g.v2 = 0; g.lanes = 0;
+    if (v2_env && R <= 65535 && stream_chunks < (1 << 20) - 1) {                    // pipelined kernel: an insert takes <= floor(log2 R) + 1 steps <= 2 * lanes
+        g.v2 = 1;
+        g.lanes = R <= 255 ? 4 : 8;
+        g.qcap = 4 * R < 128 ? 128 : 4 * R;
+        int qpc = 16;
+        while (qpc > 1 && (Q + qpc - 1) / qpc < 2 * 148) qpc >>= 1;
+        while (qpc > 1 && rq2_smem(R, P, qpc, g.qcap) > 45 * 1024) qpc >>= 1;
+        g.qpc = qpc; g.lpw = 0;
+        g.smem = rq2_smem(R, P, qpc, g.qcap);
+        if (g.smem <= 200 * 1024) return true;
+        g.v2 = 0;
+    }
     g.qcap = 2 * R < 64 ? 64 : 2 * R;
     // enough CTAs to cover the machine about twice, as many queries per CTA as that allows, and at most
     // ~45 KB of shared memory so that several CTAs share an SM
@@ -461,8 +699,23 @@ static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t
                      const int32_t *probes, int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int *fallback,
                      const RqGeom &g, cudaStream_t st)
 {
-    TKB_CUDA(cudaFuncSetAttribute(replay_rq_kernel<SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const unsigned blocks = (unsigned)((Q + g.qpc - 1) / g.qpc);
+    if (g.v2) {
+        if (g.lanes == 4) {
+            TKB_CUDA(cudaFuncSetAttribute(replay_rq2_kernel<SIGNED, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+            replay_rq2_kernel<SIGNED, 4><<<blocks, RQ_THREADS, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off,
+                                                                            list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val,
+                                                                            R, fallback, g.qpc, g.qcap);
+        } else {
+            TKB_CUDA(cudaFuncSetAttribute(replay_rq2_kernel<SIGNED, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+            replay_rq2_kernel<SIGNED, 8><<<blocks, RQ_THREADS, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off,
+                                                                            list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val,
+                                                                            R, fallback, g.qpc, g.qcap);
+        }
+        TKB_LAUNCH_CHECK();
+        return TKB_OK;
+    }
+    TKB_CUDA(cudaFuncSetAttribute(replay_rq_kernel<SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     replay_rq_kernel<SIGNED><<<blocks, RQ_THREADS, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off,
                                                                  list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val,
                                                                  R, fallback, g.qpc, g.qcap, g.lpw);
@@ -478,7 +731,7 @@ int launch_replay_fresh(const uint8_t *est, int64_t est_stride, int64_t n_chunks
     if (Q == 0 || R == 0) return TKB_OK;
     TKB_REQUIRE(heap_idx && heap_val, "null pointer");
     RqGeom g;
-    if (n_chunks == 0 || n_chunks >= (1LL << 27) || !rq_geometry(Q, R, 1, g)) {
+    if (n_chunks == 0 || n_chunks >= (1LL << 27) || !rq_geometry(Q, R, 1, g, n_chunks)) {
         if (int rc = launch_heap_fill(heap_idx, heap_val, (int64_t)Q * R, signd, st)) return rc;
         return launch_replay(est, est_stride, n_chunks, n, heap_idx, heap_val, Q, R, signd, nullptr, st);
     }

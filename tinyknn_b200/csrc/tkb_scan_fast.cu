@@ -19,17 +19,9 @@
 //   S + N <= 127 (no prefix can exceed 127). Vectors failing the test are recomputed by the patch
 //   kernel with the reference's step-by-step saturating fold; queries whose LUT fails the per-query
 //   preconditions run the step-by-step fold for every vector.
-#include "tkb_common.cuh"
+#include "tkb_scan_core.cuh"
 
 namespace tkb {
-
-constexpr int FAST_THREADS = 256;
-constexpr int TILE = 8;                        // chunks per tile
-
-__device__ __forceinline__ size_t native_off(int64_t chunk, int p, int Ph)     // in uint4 units
-{
-    return ((size_t)(chunk >> 3) * Ph + p) * TILE + (chunk & 7);
-}
 
 // ------------------------------------------------------------------------------------------------
 // layout conversion (upload time)
@@ -87,222 +79,6 @@ __global__ void from_native_kernel(const uint4 *__restrict__ nat, int64_t n_chun
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-query LUT preparation (CTA prologue)
-// ------------------------------------------------------------------------------------------------
-struct LutMeta {
-    int eligible;          // fast path allowed for this query
-    int bias_tot;          // bias_0 + bias_1                         (signed fast path)
-    int k0, k1;            // certificate thresholds on the biased lane sums: S'_l <= k_l
-};
-
-// smem layout: uint4 rows[M] (biased when eligible, raw otherwise) | raw copy uint4 raw[M] | LutMeta | scratch
-template <bool SIGNED>
-__device__ void prepare_lut(const uint8_t *__restrict__ tq, int M, bool fast_allowed, uint4 *rows, uint4 *raw,
-                            LutMeta *meta, int *scratch /* 4*M ints */)
-{
-    const int tid = threadIdx.x;
-    for (int j = tid; j < M; j += blockDim.x) {
-        const uint4 r = reinterpret_cast<const uint4 *>(tq)[j];
-        raw[j] = r;
-        const uint32_t ws[4] = {r.x, r.y, r.z, r.w};
-        int mn = 1 << 30, mx = -(1 << 30);
-#pragma unroll
-        for (int c = 0; c < 16; c++) {
-            const uint32_t b = (ws[c >> 2] >> (8 * (c & 3))) & 0xffu;
-            const int t = SIGNED ? (int)(int8_t)b : (int)b;
-            mn = min(mn, t); mx = max(mx, t);
-        }
-        const int bias = SIGNED ? -mn : 0;                 // unsigned rows are used as they are
-        scratch[4 * j + 0] = bias;
-        scratch[4 * j + 1] = SIGNED ? max(0, -mn) : 0;     // contribution to N
-        scratch[4 * j + 2] = mx + bias;                    // largest biased entry
-        uint32_t o[4];
-#pragma unroll
-        for (int w = 0; w < 4; w++) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const uint32_t b = (ws[w] >> (8 * c)) & 0xffu;
-                const int t = SIGNED ? (int)(int8_t)b : (int)b;
-                v |= (uint32_t)((t + bias) & 0xff) << (8 * c);
-            }
-            o[w] = v;
-        }
-        rows[j] = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int bias[2] = {0, 0}, N[2] = {0, 0}, range = 0;
-        for (int j = 0; j < M; j++) {
-            const int l = (j >> 1) & 1;
-            bias[l] += scratch[4 * j + 0];
-            N[l] += scratch[4 * j + 1];
-            range = max(range, scratch[4 * j + 2]);
-        }
-        LutMeta m;
-        // 8 steps of one lane accumulate in a byte: 8 * range <= 255; PRMT zero trick needs entries < 128
-        m.eligible = fast_allowed && range <= 31 && (!SIGNED || (N[0] <= 128 && N[1] <= 128));
-        m.bias_tot = bias[0] + bias[1];
-        m.k0 = 127 - N[0] + bias[0];
-        m.k1 = 127 - N[1] + bias[1];
-        *meta = m;
-    }
-    __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------------
-// the fast chunk kernel: 16 vectors, M sub-quantizers, AVX lane split (pair p -> lane p & 1)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
-{
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
-    return d;
-}
-
-// one sub-quantizer (LUT row L = 16 biased bytes), two code words = 4 groups of 4 vectors
-__device__ __forceinline__ void lookup_step(const uint4 L, uint32_t wa, uint32_t wb, uint32_t (&acc)[4])
-{
-    const uint32_t xa = wa ^ 0x88888888u, xb = wb ^ 0x88888888u;
-    // entries 0..7 live in (L.x, L.y), entries 8..15 in (L.z, L.w). A selector nibble with bit 3 set
-    // makes PRMT return the replicated sign bit of the addressed byte, i.e. 0 for our entries < 128.
-    acc[0] += prmt(L.x, L.y, wa) + prmt(L.z, L.w, xa);
-    acc[1] += prmt(L.x, L.y, wa >> 16) + prmt(L.z, L.w, xa >> 16);
-    acc[2] += prmt(L.x, L.y, wb) + prmt(L.z, L.w, xb);
-    acc[3] += prmt(L.x, L.y, wb >> 16) + prmt(L.z, L.w, xb >> 16);
-}
-
-// Returns the 16 estimates (one byte per vector, vector order) and whether any vector failed the
-// certificate (then the caller queues the chunk for the patch kernel).
-template <bool SIGNED>
-__device__ __forceinline__ uint4 scan_chunk_fast(const uint4 *__restrict__ nat, int64_t chunk, int Ph,
-                                                 const uint4 *__restrict__ rows, const LutMeta &meta,
-                                                 bool &flagged)
-{
-    uint32_t wide[2][4][2];                    // [lane][group][even/odd] packed s16x2 biased sums
-#pragma unroll
-    for (int l = 0; l < 2; l++)
-#pragma unroll
-        for (int g = 0; g < 4; g++) { wide[l][g][0] = 0; wide[l][g][1] = 0; }
-
-    const uint4 *base = nat + native_off(chunk, 0, Ph);
-    for (int p0 = 0; p0 < Ph; p0 += 8) {
-        uint4 w[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            if (p0 + i < Ph) w[i] = ldg_nc_u4(base + (size_t)(p0 + i) * TILE);
-        uint32_t acc[2][4];
-#pragma unroll
-        for (int l = 0; l < 2; l++)
-#pragma unroll
-            for (int g = 0; g < 4; g++) acc[l][g] = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            if (p0 + i < Ph) {
-                const int j = 2 * (p0 + i);
-                lookup_step(rows[j], w[i].x, w[i].y, acc[i & 1]);          // sub-quantizer 2p
-                lookup_step(rows[j + 1], w[i].z, w[i].w, acc[i & 1]);      // sub-quantizer 2p+1
-            }
-        }
-#pragma unroll
-        for (int l = 0; l < 2; l++)
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                wide[l][g][0] += prmt(acc[l][g], 0u, 0x4240u);             // vectors 4g+0, 4g+2
-                wide[l][g][1] += prmt(acc[l][g], 0u, 0x4341u);             // vectors 4g+1, 4g+3
-            }
-    }
-
-    uint32_t outw[4];
-    uint32_t flag = 0x80008000u;               // running max of (S'_l - k_l), starts at the most negative s16x2
-    if (SIGNED) {
-        const uint32_t nbias = (uint32_t)((-meta.bias_tot) & 0xffff) * 0x00010001u;
-        const uint32_t nk0 = (uint32_t)((-meta.k0) & 0xffff) * 0x00010001u;
-        const uint32_t nk1 = (uint32_t)((-meta.k1) & 0xffff) * 0x00010001u;
-        const uint32_t lo128 = 0xff80ff80u, hi127 = 0x007f007fu;
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-            uint32_t e[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t s = __vadd2(wide[0][g][h], wide[1][g][h]);                  // no overflow: < 2^12
-                e[h] = __vimin3_s16x2(__viaddmax_s16x2(s, nbias, lo128), hi127, hi127);   // clamp(S0+S1, -128, 127)
-                const uint32_t d0 = __vadd2(wide[0][g][h], nk0);
-                flag = __vimax3_s16x2(flag, d0, __vadd2(wide[1][g][h], nk1));
-            }
-            outw[g] = prmt(e[0], e[1], 0x6240u);                                          // bytes v0 v1 v2 v3
-        }
-        flagged = ((int)(int16_t)(flag & 0xffffu) > 0) || ((int)(int16_t)(flag >> 16) > 0);
-    } else {
-        const uint32_t hi255 = 0x00ff00ffu;
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-            uint32_t e[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++)
-                e[h] = __vimin3_u16x2(__vadd2(wide[0][g][h], wide[1][g][h]), hi255, hi255);   // min(255, sum)
-            outw[g] = prmt(e[0], e[1], 0x6240u);
-        }
-        flagged = false;
-    }
-    return make_uint4(outw[0], outw[1], outw[2], outw[3]);
-}
-
-// step-by-step saturating fold on the native layout (ineligible LUTs, signed SSE order, patch kernel)
-template <int ORDER, bool SIGNED>
-__device__ __forceinline__ int exact_vector(const uint4 *__restrict__ nat, int64_t chunk, int Ph, int v,
-                                            const uint8_t *__restrict__ raw /* M*16 bytes */)
-{
-    const int g = v >> 2, sh = 4 * (v & 3) + 16 * (g & 1);
-    int a0 = 0, a1 = 0;
-    for (int p = 0; p < Ph; p++) {
-        const uint4 w = nat[native_off(chunk, p, Ph)];
-        const uint32_t c0 = (((g < 2) ? w.x : w.y) >> sh) & 15u;
-        const uint32_t c1 = (((g < 2) ? w.z : w.w) >> sh) & 15u;
-        int t0 = raw[32 * p + c0], t1 = raw[32 * p + 16 + c1];
-        if (SIGNED) { t0 = (int)(int8_t)t0; t1 = (int)(int8_t)t1; }
-        if (ORDER == TKB_ORDER_AVX && (p & 1)) a1 = sat_add8<SIGNED>(sat_add8<SIGNED>(a1, t0), t1);
-        else                                  a0 = sat_add8<SIGNED>(sat_add8<SIGNED>(a0, t0), t1);
-    }
-    return (ORDER == TKB_ORDER_AVX) ? sat_add8<SIGNED>(a0, a1) : a0;
-}
-
-template <int ORDER, bool SIGNED>
-__device__ __forceinline__ uint4 scan_chunk_exact(const uint4 *__restrict__ nat, int64_t chunk, int Ph,
-                                                  const uint8_t *__restrict__ raw)
-{
-    uint32_t o[4] = {0, 0, 0, 0};
-    for (int v = 0; v < 16; v++) {
-        const int e = exact_vector<ORDER, SIGNED>(nat, chunk, Ph, v, raw);
-        o[v >> 2] |= (uint32_t)(e & 0xff) << (8 * (v & 3));
-    }
-    return make_uint4(o[0], o[1], o[2], o[3]);
-}
-
-// cold path (patch list full): same fold, kept out of line so that it does not cost the hot loop registers
-template <int ORDER, bool SIGNED>
-__device__ __noinline__ uint4 scan_chunk_exact_cold(const uint4 *__restrict__ nat, int64_t chunk, int Ph,
-                                                    const uint8_t *__restrict__ raw)
-{
-    return scan_chunk_exact<ORDER, SIGNED>(nat, chunk, Ph, raw);
-}
-
-struct PatchList {
-    unsigned long long *count;     // number of flagged chunks (may exceed `cap`: the excess was recomputed inline)
-    uint2 *entry;                  // .x = unit (query, or query * P + probe slot), .y = chunk inside the unit's segment
-    unsigned long long cap;        // entries that fit
-};
-
-// queue a flagged chunk for the patch pass; false = list full, the caller recomputes the chunk itself
-__device__ __forceinline__ bool patch_push(const PatchList &pl, uint32_t unit, uint32_t local)
-{
-    const unsigned long long i = atomicAdd(pl.count, 1ULL);
-    if (i >= pl.cap) return false;
-    pl.entry[i] = make_uint2(unit, local);
-    return true;
-}
-
-// ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
 template <int ORDER, bool SIGNED>
@@ -319,8 +95,8 @@ estimate_fast_kernel(const uint4 *__restrict__ nat, int64_t n_chunks, int M, con
     const bool fast_allowed = !(SIGNED && ORDER == TKB_ORDER_SSE);
     prepare_lut<SIGNED>(tables + (size_t)q * M * 16, M, fast_allowed, rows, raw, meta, scratch);
     const LutMeta m = *meta;
-    for (int64_t c = (int64_t)blockIdx.x * FAST_THREADS + threadIdx.x; c < n_chunks;
-         c += (int64_t)gridDim.x * FAST_THREADS) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks;
+         c += (int64_t)gridDim.x * blockDim.x) {
         const int64_t off = (int64_t)q * est_stride + 16 * c;
         uint4 o;
         if (m.eligible) {
@@ -507,7 +283,9 @@ int launch_estimate_native(const void *native, int64_t n_chunks, int M, const ui
                 "device pointers must be 16-byte aligned");
     PatchList pl;
     if (int rc = split_workspace(workspace, workspace_bytes, pl)) return rc;
-    int64_t tiles = (n_chunks + FAST_THREADS - 1) / FAST_THREADS;
+    // short code arrays (the PQ-encoded centroids of an IVF index): a CTA only as wide as the array
+    const int threads = n_chunks >= FAST_THREADS ? FAST_THREADS : (int)((n_chunks + 31) / 32 * 32 < 64 ? 64 : (n_chunks + 31) / 32 * 32);
+    int64_t tiles = (n_chunks + threads - 1) / threads;
     if (tiles > 148 * 8 && Q > 1) tiles = 148 * 8;                 // grid-stride beyond that
     TKB_REQUIRE(tiles <= 0x7fffffff, "too many chunks for one launch");
     const size_t smem = fast_smem_bytes(M, 0);
@@ -517,7 +295,7 @@ int launch_estimate_native(const void *native, int64_t n_chunks, int M, const ui
         dim3 grid((unsigned)tiles, (unsigned)qn);
         TKB_CUDA(cudaMemsetAsync(pl.count, 0, 16, st));
         // patch entries are relative to this launch's block of queries: both kernels get the shifted pointers
-        TKB_DISPATCH_FAST(estimate_fast_kernel, grid, FAST_THREADS, smem, st, n4, n_chunks, M,
+        TKB_DISPATCH_FAST(estimate_fast_kernel, grid, threads, smem, st, n4, n_chunks, M,
                           tables + (size_t)q0 * M * 16, est + (size_t)q0 * est_stride, est_stride, pl);
         TKB_LAUNCH_CHECK();
         TKB_DISPATCH_FAST(patch_kernel, 148 * 4, 256, 0, st, n4, M, tables + (size_t)q0 * M * 16,

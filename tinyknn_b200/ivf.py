@@ -31,6 +31,9 @@ from .utils import timer, knn_brute, group_data_by_indices, bottom_k
 _WORKSPACE_BYTES = 2 << 30          # cap of the per-batch estimate buffer (queries are sub-batched)
 _N_STREAMS = int(os.environ.get("TKB_STREAMS", "2"))
 _SUB_QUERIES = int(os.environ.get("TKB_SUB_QUERIES", "5000"))      # target queries per sub-batch
+# One kernel after probe selection (tkb_ivf_query_fused_dev). Off by default: measured slower than the stage-by-stage
+# kernels at large batches (a CTA holds its scan registers while it sits in the latency-bound replay), DESIGN.md 4.6.
+FUSED = os.environ.get("TKB_FUSED", "0") != "0"
 _streams = {}
 
 
@@ -98,7 +101,7 @@ class IVF:
 
     # ------------------------------------------------------------------ device index ---------
     def __getstate__(self):
-        return {k: v for k, v in self.__dict__.items() if k not in ("_dev", "_last", "_prof")}
+        return {k: v for k, v in self.__dict__.items() if k not in ("_dev", "_last", "_prof", "_keep_heaps")}
 
     def invalidate(self):
         """Forget the device copy (call after replacing index arrays by hand)."""
@@ -192,11 +195,13 @@ class IVF:
         return ids[0][:counts[0]]
 
     def query_batch(self, queries, k, n_probes=1, pass_1=None, order="device", return_distances=False,
-                    to_host=True, sub_batches=None):
+                    to_host=True, sub_batches=None, fused=None):
         """Batched IVF.query (new, additive API). queries: f32 (Q, d), host array or device tensor.
         Returns (ids, counts[, dists]): ids int64 (Q, k) padded with -1, counts int32 (Q,).
         With to_host=False (order="device" only) the results stay on the GPU as torch tensors.
-        sub_batches (order="device"): split the batch over side streams (None: automatic, 1: one stream)."""
+        sub_batches (order="device"): split the batch over side streams (None: automatic, 1: one stream).
+        fused (order="device"): run everything after probe selection as one kernel (None: module default FUSED);
+        False keeps the stage-by-stage kernels (scan / replay / gather / select), same results."""
         assert order in ("device", "numpy")
         assert to_host or order == "device"
         dev = self.to_device()
@@ -216,6 +221,7 @@ class IVF:
         n_sub = 1 if order != "device" else (_sub_batches(Q) if sub_batches is None else max(1, int(sub_batches)))
         if n_sub > 1:
             qb = min(qb, -(-Q // n_sub))
+        fused = (FUSED if fused is None else bool(fused)) and order == "device" and bool(dev.get("unique_ids", False))
         outs = []
         res = None
         if order == "device":                                           # every block writes its rows of one result
@@ -236,7 +242,7 @@ class IVF:
                     qs = queries[lo:min(Q, lo + qb)]
                     if not qs.is_cuda:
                         qs = qs.to(D.device(), non_blocking=True)
-                    self._query_block(dev, qs, k, P, Rc, pass_1, order, blk(lo, min(Q, lo + qb)))
+                    self._query_block(dev, qs, k, P, Rc, pass_1, order, blk(lo, min(Q, lo + qb)), fused)
             for s_ in pool:
                 cur.wait_stream(s_)
         else:
@@ -244,7 +250,7 @@ class IVF:
                 qs = queries[lo:min(Q, lo + qb)]
                 if isinstance(qs, np.ndarray):
                     qs = D.upload(qs)
-                outs.append(self._query_block(dev, qs, k, P, Rc, pass_1, order, blk(lo, min(Q, lo + qb))))
+                outs.append(self._query_block(dev, qs, k, P, Rc, pass_1, order, blk(lo, min(Q, lo + qb)), fused))
         if order == "device":
             ids, cnt, dst = res
             if to_host:
@@ -362,13 +368,38 @@ class IVF:
                                        D.stream_ptr()))
         return seg_off, gb
 
-    def _query_block(self, dev, qs, k, P, Rc, pass_1, order, out=None):
+    def _fused_tail(self, dev, lut, probes, Q, P, k, pass_1, out=None, want_heap=False):
+        """Everything after probe selection in one kernel (ref: ivf.py:135-163): scan of the probed lists, exact heap
+        replay in probe order, exact rescoring, k nearest. Returns (ids, counts, dists) device tensors."""
+        import ctypes
+        st = D.stream_ptr()
+        M, mlc = dev["M"], max(dev["max_real_chunks"], 1)
+        need = ctypes.c_int64(0)
+        check(lib.tkb_ivf_query_fused_workspace(Q, P, pass_1, M, _fp._order(), dev["data_dtype"], mlc, ctypes.byref(need)))
+        ws = D.empty((need.value,), np.uint8)
+        ddt = np.float32 if dev["data_dtype"] == DTYPE_F32 else np.float64
+        oi, oc, od = out if out is not None else (D.empty((Q, k), np.int64), D.empty((Q,), np.int32), D.empty((Q, k), ddt))
+        hi_ = hv_ = None
+        if want_heap:
+            hi_, hv_ = D.empty((Q, pass_1), np.int64), D.empty((Q, pass_1), np.int32)
+        with self._stage("fused"):
+            check(lib.tkb_ivf_query_fused_dev(
+                D.ptr(dev["codes"]), D.ptr(dev["list_chunk_off"]), D.ptr(dev["list_size"]), dev["n_lists"], M,
+                D.ptr(lut["tables"]), D.ptr(probes), Q, P, D.ptr(dev["ids"]), D.ptr(dev["data"]), dev["data_dtype"],
+                dev["data"].shape[0], dev["d"], D.ptr(lut["q"]), pass_1, k, _fp._order(), mlc,
+                D.ptr(oi), D.ptr(od), D.ptr(oc), D.ptr(hi_), D.ptr(hv_), D.ptr(ws), ws.numel(), st))
+        self._last.update(probes=probes, scan_probes=probes, scan_seg_off=None, fused_ws=ws, heap_idx=hi_, heap_val=hv_)
+        return oi, oc, od
+
+    def _query_block(self, dev, qs, k, P, Rc, pass_1, order, out=None, fused=False):
         Q = qs.shape[0]
         # 1. LUTs (ref: ivf.py:125-128)
         with self._stage("lut"):
             lut = self.pq.distance_tables(qs, signed=True, normalize=(self.metric == "angular"))
         # 2. probe selection
         probes = self._coarse(dev, lut, Q, P, Rc, order)
+        if fused:
+            return self._fused_tail(dev, lut, probes, Q, P, k, pass_1, out, want_heap=bool(self.__dict__.get("_keep_heaps")))
         # 3. scan of the probed lists into a compact estimate buffer, ordered replay, rescoring
         seg_off, _ = self._plan(dev, probes, Q, P)
         est = D.empty((Q * P * 16 * max(dev["max_real_chunks"], 1),), np.uint8)      # upper bound; only the planned part is touched
