@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "tkb_scan_core.cuh"
+#include "tkb_rescore_core.cuh"
 
 namespace tkb {
 
@@ -97,28 +98,15 @@ __device__ __forceinline__ uint32_t fz_cand_mask16(const uint4 e, int bound)
     return pack(m0) | (pack(m1) << 4) | (pack(m2) << 8) | (pack(m3) << 12);
 }
 
-// exact distance of one row, the arithmetic of gather_dists_kernel (tkb_rescore.cu): lane i accumulates elements
-// i, i+32, ... with fma, then an xor-shuffle tree. U rows are in flight per warp to hide the gather latency.
+// exact distances of U rows at a time with the arithmetic of gather_dists_kernel (tkb_rescore_core.cuh): the partial
+// sums of all U rows are formed before the first shuffle, so U row reads are in flight per warp.
 template <typename T, int U>
 __device__ __forceinline__ void row_dists(const T *const (&y)[U], const float *__restrict__ x, int d, int lane, T (&out)[U])
 {
     T acc[U];
+    warp_rows_dispatch(y, x, d, lane, acc);
 #pragma unroll
-    for (int u = 0; u < U; u++) acc[u] = (T)0;
-    for (int i = lane; i < d; i += 32) {
-        const T xv = (T)x[i];
-        T yv[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) yv[u] = y[u] ? y[u][i] : (T)0;
-#pragma unroll
-        for (int u = 0; u < U; u++) { const T df = yv[u] - xv; acc[u] = fma(df, df, acc[u]); }
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-        T a = acc[u];
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(FULL, a, o);
-        out[u] = a;
-    }
+    for (int u = 0; u < U; u++) out[u] = warp_tree_sum<T>(acc[u]);
 }
 
 template <int ORDER, typename T>

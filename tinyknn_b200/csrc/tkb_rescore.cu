@@ -11,35 +11,42 @@
 // argpartition order is build/CPU specific; the host layer offers the numpy
 // order as a parity mode on top of gather_dists.
 #include "tkb_common.cuh"
+#include "tkb_rescore_core.cuh"
 
 namespace tkb {
 
 constexpr int GD_WARPS = 8;
+constexpr int GD_ROWS = 8;                            // candidate rows in flight per warp
 
+// A warp takes GD_ROWS candidate rows of one query (blockIdx.y: no index division on the hot path): the row indices are
+// read together, then all row reads are issued before any is consumed -- the gather is bound by memory-level parallelism.
 template <typename T>
 __global__ void __launch_bounds__(32 * GD_WARPS)
 gather_dists_kernel(const T *__restrict__ rows, int64_t n_rows, int d, const float *__restrict__ queries,
-                    const int64_t *__restrict__ idx, int64_t total, int R, T *__restrict__ dists)
+                    const int64_t *__restrict__ idx, int R, T *__restrict__ dists)
 {
-    const int64_t w = (int64_t)blockIdx.x * GD_WARPS + (threadIdx.x >> 5);
-    if (w >= total) return;
+    const int r0 = (blockIdx.x * GD_WARPS + (threadIdx.x >> 5)) * GD_ROWS;
+    if (r0 >= R) return;
     const int lane = threadIdx.x & 31;
-    const int64_t q = w / R;
-    int64_t row = idx[w];
-    if (row < 0) row += n_rows;                       // numpy negative indexing (heap padding -1 -> last row)
-    if (row < 0 || row >= n_rows) {                   // numpy would raise IndexError; flag with NaN
-        if (lane == 0) dists[w] = (T)NAN;
-        return;
+    const size_t w0 = (size_t)blockIdx.y * R + r0;
+    int64_t mine = 0;
+    if (lane < GD_ROWS && r0 + lane < R) mine = idx[w0 + lane];
+    const T *y[GD_ROWS];
+    bool live[GD_ROWS];
+#pragma unroll
+    for (int u = 0; u < GD_ROWS; u++) {
+        int64_t row = __shfl_sync(FULL, mine, u);
+        live[u] = r0 + u < R;
+        if (row < 0) row += n_rows;                   // numpy negative indexing (heap padding -1 -> last row)
+        y[u] = (live[u] && row >= 0 && row < n_rows) ? rows + row * d : nullptr;   // numpy would raise IndexError: NaN below
     }
-    const T *y = rows + row * d;
-    const float *x = queries + q * d;
-    T acc = (T)0;
-    for (int i = lane; i < d; i += 32) {
-        const T df = y[i] - (T)x[i];
-        acc = fma(df, df, acc);
+    T acc[GD_ROWS];
+    warp_rows_dispatch(y, queries + (size_t)blockIdx.y * d, d, lane, acc);
+#pragma unroll
+    for (int u = 0; u < GD_ROWS; u++) {
+        const T a = warp_tree_sum<T>(acc[u]);
+        if (lane == 0 && live[u]) dists[w0 + u] = y[u] ? a : (T)NAN;
     }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-    if (lane == 0) dists[w] = acc;
 }
 
 // One warp per query. Repeatedly extracts the smallest remaining (dist, slot) pair.
@@ -149,14 +156,17 @@ int launch_gather_dists(const void *rows, int rows_dtype, int64_t n_rows, int d,
     TKB_REQUIRE(rows && queries && idx && dists, "null pointer");
     TKB_REQUIRE(n_rows > 0 && d > 0, "empty rows");
     TKB_REQUIRE(rows_dtype == TKB_DTYPE_F32 || rows_dtype == TKB_DTYPE_F64, "rows dtype must be f32 or f64");
-    const int64_t total = (int64_t)Q * R;
-    const int64_t blocks = (total + GD_WARPS - 1) / GD_WARPS;
-    TKB_REQUIRE(blocks <= 0x7fffffff, "too many candidates for one launch");
-    if (rows_dtype == TKB_DTYPE_F32)
-        gather_dists_kernel<float><<<(unsigned)blocks, 32 * GD_WARPS, 0, st>>>((const float *)rows, n_rows, d, queries, idx, total, R, (float *)dists);
-    else
-        gather_dists_kernel<double><<<(unsigned)blocks, 32 * GD_WARPS, 0, st>>>((const double *)rows, n_rows, d, queries, idx, total, R, (double *)dists);
-    TKB_LAUNCH_CHECK();
+    const unsigned bx = (unsigned)((R + GD_WARPS * GD_ROWS - 1) / (GD_WARPS * GD_ROWS));
+    for (int q0 = 0; q0 < Q; q0 += 65535) {
+        const int qn = (Q - q0 < 65535) ? (Q - q0) : 65535;
+        const dim3 grid(bx, (unsigned)qn);
+        const size_t o = (size_t)q0 * R;
+        if (rows_dtype == TKB_DTYPE_F32)
+            gather_dists_kernel<float><<<grid, 32 * GD_WARPS, 0, st>>>((const float *)rows, n_rows, d, queries + (size_t)q0 * d, idx + o, R, (float *)dists + o);
+        else
+            gather_dists_kernel<double><<<grid, 32 * GD_WARPS, 0, st>>>((const double *)rows, n_rows, d, queries + (size_t)q0 * d, idx + o, R, (double *)dists + o);
+        TKB_LAUNCH_CHECK();
+    }
     return TKB_OK;
 }
 
