@@ -101,11 +101,15 @@ __device__ __forceinline__ void lookup_step(const uint4 L, uint32_t wa, uint32_t
 
 // Returns the 16 estimates (one byte per vector, vector order) and whether any vector failed the
 // certificate (then the caller queues the chunk for the patch kernel).
-template <bool SIGNED>
-__device__ __forceinline__ uint4 scan_chunk_fast(const uint4 *__restrict__ nat, int64_t chunk, int Ph,
+// PH > 0: the number of sub-quantizer pairs is a compile-time constant (26: GloVe-100 shape, 16: 128-d rotated to 64), the
+// pair loop unrolls completely and the tail predicates of the generic loop disappear (scan 0.65 -> 0.58 ms on the
+// GloVe-shape bench). Moving the selector shifts to the FMA pipe as IMAD.HI was measured too: no gain (tools/ubench.cu).
+template <bool SIGNED, int PH = 0>
+__device__ __forceinline__ uint4 scan_chunk_fast(const uint4 *__restrict__ nat, int64_t chunk, int Ph_rt,
                                                  const uint4 *__restrict__ rows, const LutMeta &meta,
                                                  bool &flagged)
 {
+    const int Ph = PH > 0 ? PH : Ph_rt;
     uint32_t wide[2][4][2];                    // [lane][group][even/odd] packed s16x2 biased sums
 #pragma unroll
     for (int l = 0; l < 2; l++)
@@ -113,7 +117,8 @@ __device__ __forceinline__ uint4 scan_chunk_fast(const uint4 *__restrict__ nat, 
         for (int g = 0; g < 4; g++) { wide[l][g][0] = 0; wide[l][g][1] = 0; }
 
     const uint4 *base = nat + native_off(chunk, 0, Ph);
-    for (int p0 = 0; p0 < Ph; p0 += 8) {
+#pragma unroll
+    for (int p0 = 0; p0 < (PH > 0 ? PH : Ph); p0 += 8) {
         uint4 w[8];
 #pragma unroll
         for (int i = 0; i < 8; i++)
@@ -127,8 +132,8 @@ __device__ __forceinline__ uint4 scan_chunk_fast(const uint4 *__restrict__ nat, 
         for (int i = 0; i < 8; i++) {
             if (p0 + i < Ph) {
                 const int j = 2 * (p0 + i);
-                lookup_step(rows[j], w[i].x, w[i].y, acc[i & 1]);          // sub-quantizer 2p
-                lookup_step(rows[j + 1], w[i].z, w[i].w, acc[i & 1]);      // sub-quantizer 2p+1
+                lookup_step(rows[j], w[i].x, w[i].y, acc[i & 1]);      // sub-quantizer 2p
+                lookup_step(rows[j + 1], w[i].z, w[i].w, acc[i & 1]);  // sub-quantizer 2p+1
             }
         }
 #pragma unroll

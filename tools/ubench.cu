@@ -9,9 +9,10 @@
 #define ITERS 4096
 #define CHAINS 8
 
-enum Op { PRMT, LOP3, IADD3, SHF, VIADDMIN32, VIADDMIN16X2, VIMAX16X2, IMAD, HFMA2SAT, HADD2, LDS8, LDS128, PRMT_VIADD, PRMT_HFMA, NOPS };
+enum Op { PRMT, LOP3, IADD3, SHF, VIADDMIN32, VIADDMIN16X2, VIMAX16X2, IMAD, HFMA2SAT, HADD2, LDS8, LDS128, PRMT_VIADD, PRMT_HFMA, IMADHI, PRMT_IMADHI, PRMT_IMAD, PRMT_SHF, NOPS };
 static const char *names[] = {"PRMT", "LOP3", "IADD3", "SHF", "VIADDMNMX.s32", "VIADDMNMX.s16x2", "VIADDMNMX.s16x2.RELU", "IMAD",
-                              "HFMA2.SAT", "HADD2", "LDS.U8 (row bcast)", "LDS.128 (bcast)", "PRMT+VIADDMNMX16x2 mix", "PRMT+HFMA2.SAT mix"};
+                              "HFMA2.SAT", "HADD2", "LDS.U8 (row bcast)", "LDS.128 (bcast)", "PRMT+VIADDMNMX16x2 mix", "PRMT+HFMA2.SAT mix",
+                              "IMAD.HI (mul.hi.u32 reg)", "PRMT+IMAD.HI mix", "PRMT+IMAD mix", "PRMT+SHF mix"};
 
 template <int OP>
 __global__ void __launch_bounds__(512) bench(uint32_t *out, uint32_t seed, long long *cycles)
@@ -40,6 +41,10 @@ __global__ void __launch_bounds__(512) bench(uint32_t *out, uint32_t seed, long 
             if (OP == LDS8) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(lut) + ((a[k] & 15) + 16 * k))); a[k] += v; }
             if (OP == LDS128) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(lut) + 16 * ((it + k) & 63))); a[k] ^= v.x ^ v.w; }
             if (OP == PRMT_VIADD) { uint32_t t; asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(b), "r"(c), "r"(a[k])); a[k] = __viaddmin_s16x2(a[k], t, c); }
+            if (OP == IMADHI) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a[k]) : "r"(b));
+            if (OP == PRMT_IMADHI) { uint32_t t; asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(b), "r"(c), "r"(a[k])); asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(a[k]) : "r"(t), "r"(b)); }
+            if (OP == PRMT_IMAD) { uint32_t t; asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(b), "r"(c), "r"(a[k])); asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a[k]) : "r"(t), "r"(b)); }
+            if (OP == PRMT_SHF) { uint32_t t; asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(b), "r"(c), "r"(a[k])); asm volatile("shf.r.wrap.b32 %0, %1, %2, 16;" : "=r"(a[k]) : "r"(t), "r"(b)); }
             if (OP == PRMT_HFMA) { uint32_t t; asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(b), "r"(c), "r"(a[k])); asm volatile("fma.rn.sat.f16x2 %0, %1, %2, %0;" : "+r"(a[k]) : "r"(t), "r"(c)); }
         }
     }
@@ -64,7 +69,7 @@ void run(int sms, uint32_t *out, long long *cyc)
     cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     long long h[8]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
-    const double ops_per_thread = (double)ITERS * CHAINS * ((OP == PRMT_VIADD || OP == PRMT_HFMA) ? 2 : 1);
+    const double ops_per_thread = (double)ITERS * CHAINS * ((OP == PRMT_VIADD || OP == PRMT_HFMA || OP == PRMT_IMADHI || OP == PRMT_IMAD || OP == PRMT_SHF) ? 2 : 1);
     const double per_sm_clk = ops_per_thread * 2048.0 / (double)h[0];
     const double total = ops_per_thread * blocks * threads;
     printf("%-28s %8.1f lane-ops/clk/SM   %8.2f Tlane-ops/s   (%.3f ms, %lld cycles)\n", names[OP], per_sm_clk,
@@ -82,6 +87,7 @@ int main()
     run<VIADDMIN32>(s, out, cyc); run<VIADDMIN16X2>(s, out, cyc); run<VIMAX16X2>(s, out, cyc); run<IMAD>(s, out, cyc);
     run<HFMA2SAT>(s, out, cyc); run<HADD2>(s, out, cyc); run<LDS8>(s, out, cyc); run<LDS128>(s, out, cyc);
     run<PRMT_VIADD>(s, out, cyc); run<PRMT_HFMA>(s, out, cyc);
+    run<IMADHI>(s, out, cyc); run<PRMT_IMADHI>(s, out, cyc); run<PRMT_IMAD>(s, out, cyc); run<PRMT_SHF>(s, out, cyc);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
