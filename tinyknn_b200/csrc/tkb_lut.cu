@@ -13,37 +13,95 @@
 //   * _mean: numpy's pairwise summation (8 accumulators, blocks of <=128, recursive halving on
 //     multiples of 8) over the flattened C-order (16, M) array, then dtype(f64(sum) / count);
 //   * np.round = round-half-to-even; astype(uint8) of a negative value wraps modulo 256.
-// One CTA per query; all staging in shared memory.
+// One CTA per query; all staging in shared memory. The mean is numpy's pairwise sum computed by the whole CTA.
 #include "tkb_common.cuh"
 
 namespace tkb {
 
 constexpr int LUT_THREADS = 128;
 
-// numpy pairwise sum (numpy/_core/src/umath/loops_utils.h.src, @TYPE@_pairwise_sum), executed by
-// one thread. The 8 partial sums per leaf block are independent, so the FP pipe stays busy.
-template <typename T>
-__device__ T np_pairwise_sum(const T *a, int n)
+// numpy pairwise sum (numpy/_core/src/umath/loops_utils.h.src, @TYPE@_pairwise_sum):
+//   n < 8      : res = 0; res += a[i] in order
+//   n <= 128   : r[k] = a[k] (k < 8); r[k] += a[i + k] for i = 8, 16, .. < n - n % 8;
+//                res = ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)); then res += a[i] for the n % 8 tail
+//   otherwise  : n2 = n / 2; n2 -= n2 % 8; pairwise(a, n2) + pairwise(a + n2, n - n2)
+// Computed by the whole CTA, bit for bit. numpy's recursion splits [0, n) into leaves of <= 128 elements
+// (n2 = n/2 rounded down to a multiple of 8); inside a leaf the 8 strided partial sums are independent chains and are
+// combined in a fixed tree, then the leaves are added pairwise in recursion order. Here thread 0 lists the leaves, 8
+// lanes per leaf form the partial sums, one lane per leaf combines them (plus the <8 tail elements), and thread 0 adds
+// the leaf sums in recursion order -- the operations and their order are exactly numpy's.
+struct PwScratch { int *off, *len; int n_leaves; };     // leaves are >= 60 elements long: at most n / 32 + 2 of them
+
+__device__ void pw_list_leaves(int off, int n, PwScratch *ps)
 {
-    if (n < 8) {
-        T res = (T)0;
-        for (int i = 0; i < n; i++) res += a[i];
-        return res;
-    }
-    if (n <= 128) {
-        T r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8) {
-            r0 += a[i + 0]; r1 += a[i + 1]; r2 += a[i + 2]; r3 += a[i + 3];
-            r4 += a[i + 4]; r5 += a[i + 5]; r6 += a[i + 6]; r7 += a[i + 7];
-        }
-        T res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
-        for (; i < n; i++) res += a[i];
-        return res;
-    }
+    if (n <= 128) { const int i = ps->n_leaves++; ps->off[i] = off; ps->len[i] = n; return; }
     int n2 = n / 2;
     n2 -= n2 % 8;
-    return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+    pw_list_leaves(off, n2, ps);
+    pw_list_leaves(off + n2, n - n2, ps);
+}
+
+template <typename T>
+__device__ T pw_combine(int n, const T *leaf_sum, int &next)
+{
+    if (n <= 128) return leaf_sum[next++];
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const T l = pw_combine<T>(n2, leaf_sum, next);
+    const T r = pw_combine<T>(n - n2, leaf_sum, next);
+    return l + r;
+}
+
+// a: n values in shared memory; part: 8 * PW_MAX_LEAVES scratch (T); returns the sum in every thread of the CTA.
+template <typename T>
+__device__ T cta_pairwise_sum(const T *a, int n, PwScratch *ps, T *part, T *leaf_sum, T *result)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) { ps->n_leaves = 0; pw_list_leaves(0, n, ps); }
+    __syncthreads();
+    const int nl = ps->n_leaves;
+    for (int i = tid; i < 8 * nl; i += nt) {                   // partial sum k of leaf l: a[k], a[8+k], ... (ascending)
+        const int l = i >> 3, k = i & 7, len = ps->len[l];
+        const T *p = a + ps->off[l];
+        if (len >= 8) {
+            T r = p[k];
+            for (int j = 8; j < len - (len % 8); j += 8) r += p[j + k];
+            part[i] = r;
+        }
+    }
+    __syncthreads();
+    for (int l = tid; l < nl; l += nt) {
+        const int len = ps->len[l];
+        const T *p = a + ps->off[l];
+        T res;
+        if (len < 8) {
+            res = (T)0;
+            for (int j = 0; j < len; j++) res += p[j];
+        } else {
+            const T *r = part + 8 * l;
+            res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+            for (int j = len - (len % 8); j < len; j++) res += p[j];
+        }
+        leaf_sum[l] = res;
+    }
+    __syncthreads();
+    if (tid == 0) { int next = 0; *result = pw_combine<T>(n, leaf_sum, next); }
+    __syncthreads();
+    return *result;
+}
+
+// CTA-wide min / max of one value per thread (warp shuffles, then one value per warp through shared memory)
+template <typename T, bool MAX>
+__device__ T cta_minmax(T v, T *red)
+{
+    for (int o = 16; o > 0; o >>= 1) { const T u = __shfl_xor_sync(FULL, v, o); v = MAX ? fmax(v, u) : fmin(v, u); }
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[warp] = v;
+    __syncthreads();
+    T r = red[0];
+    for (int w = 1; w < nw; w++) r = MAX ? fmax(r, red[w]) : fmin(r, red[w]);
+    return r;
 }
 
 __device__ __forceinline__ float  mul_rn(float a, float b)   { return __fmul_rn(a, b); }
@@ -52,14 +110,14 @@ __device__ __forceinline__ float  add_rn(float a, float b)   { return __fadd_rn(
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 
 // T = double when rotated (R != nullptr), float otherwise.
-// dynamic smem: T dists[16*M] | T qv[Dp] | float qpad[Dpad] | red[LUT_THREADS] (T)
+// dynamic smem: T dists[16*M] | T qv[Dp] | red[LUT_THREADS] (T) | float qpad[Dpad] | pairwise-sum scratch
 template <typename T>
 __global__ void __launch_bounds__(LUT_THREADS)
 lut_build_kernel(const float *__restrict__ queries, int d, int normalize, float *__restrict__ q_out,
                  const float *__restrict__ centers, int Dp, int dpb, const double *__restrict__ R,
                  int Dpad, double sqrt_n_blocks, double log_n_blocks, int signd,
                  uint8_t *__restrict__ tables, double *__restrict__ q_rot, double *__restrict__ shift_out,
-                 double *__restrict__ scale_out)
+                 double *__restrict__ scale_out, int pw_off)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int M = Dp / dpb;
@@ -67,7 +125,11 @@ lut_build_kernel(const float *__restrict__ queries, int d, int normalize, float 
     T *qv = dists + 16 * M;
     T *red = qv + Dp;
     float *qpad = reinterpret_cast<float *>(red + LUT_THREADS);
-    __shared__ T s_shift;
+    const int ML = 16 * M / 32 + 2;
+    T *pw_part = reinterpret_cast<T *>(smem_raw + pw_off);                 // [8 * ML] partial sums, [ML] leaf sums, then off/len
+    __shared__ PwScratch s_pw;
+    if (threadIdx.x == 0) { s_pw.off = reinterpret_cast<int *>(pw_part + 9 * ML); s_pw.len = s_pw.off + ML; }
+    __shared__ T s_sum;
     __shared__ float s_norm;
 
     const int q = blockIdx.x, tid = threadIdx.x;
@@ -110,43 +172,39 @@ lut_build_kernel(const float *__restrict__ queries, int d, int normalize, float 
     if (q_rot) for (int i = tid; i < Dp; i += LUT_THREADS) q_rot[(size_t)q * Dp + i] = (double)qv[i];
 
     // ---- dists[c][m] = sum_k (centers[c][m*dpb+k] - q[m*dpb+k])^2 ------------------------------
-    for (int e = tid; e < 16 * M; e += LUT_THREADS) {
-        const int c = e / M, m = e - c * M;
-        const float *cen = centers + (size_t)c * Dp + m * dpb;
-        const T *qq = qv + m * dpb;
-        T acc;
-        {
-            const T df = (T)cen[0] - qq[0];
-            acc = mul_rn(df, df);
+    {
+        int c = tid / M, m = tid - c * M;                                  // e = c * M + m advances by LUT_THREADS
+        const int dc = LUT_THREADS / M, dm = LUT_THREADS - dc * M;
+        for (int e = tid; e < 16 * M; e += LUT_THREADS) {
+            const float *cen = centers + (size_t)c * Dp + m * dpb;
+            const T *qq = qv + m * dpb;
+            T acc;
+            {
+                const T df = (T)cen[0] - qq[0];
+                acc = mul_rn(df, df);
+            }
+            for (int k = 1; k < dpb; k++) {
+                const T df = (T)cen[k] - qq[k];
+                acc = add_rn(acc, mul_rn(df, df));
+            }
+            dists[e] = acc;
+            c += dc; m += dm;
+            if (m >= M) { m -= M; c++; }
         }
-        for (int k = 1; k < dpb; k++) {
-            const T df = (T)cen[k] - qq[k];
-            acc = add_rn(acc, mul_rn(df, df));
-        }
-        dists[e] = acc;
     }
     __syncthreads();
 
     // ---- shift ---------------------------------------------------------------------------------
+    T shift;
     if (signd) {
-        if (tid == 0) {
-            const T sum = np_pairwise_sum<T>(dists, 16 * M);
-            const T mean = (T)((double)sum / (double)(16 * M));     // dtype(f64(sum)/intp(count))
-            s_shift = mul_rn(mean, (T)0.6931471806);                // python float is "weak": multiply in T
-        }
+        const T sum = cta_pairwise_sum<T>(dists, 16 * M, &s_pw, pw_part, pw_part + 8 * ML, &s_sum);
+        const T mean = (T)((double)sum / (double)(16 * M));         // dtype(f64(sum)/intp(count))
+        shift = mul_rn(mean, (T)0.6931471806);                      // python float is "weak": multiply in T
     } else {
         T mn = (T)INFINITY;
         for (int e = tid; e < 16 * M; e += LUT_THREADS) mn = fmin(mn, dists[e]);
-        red[tid] = mn;
-        __syncthreads();
-        for (int o = LUT_THREADS / 2; o > 0; o >>= 1) {
-            if (tid < o) red[tid] = fmin(red[tid], red[tid + o]);
-            __syncthreads();
-        }
-        if (tid == 0) s_shift = red[0];
+        shift = cta_minmax<T, false>(mn, red);
     }
-    __syncthreads();
-    const T shift = s_shift;
 
     // ---- dists -= shift ; max ------------------------------------------------------------------
     T mx = -(T)INFINITY;
@@ -155,13 +213,7 @@ lut_build_kernel(const float *__restrict__ queries, int d, int normalize, float 
         dists[e] = v;
         mx = fmax(mx, v);
     }
-    red[tid] = mx;
-    __syncthreads();
-    for (int o = LUT_THREADS / 2; o > 0; o >>= 1) {
-        if (tid < o) red[tid] = fmax(red[tid], red[tid + o]);
-        __syncthreads();
-    }
-    const double amax = (double)red[0];
+    const double amax = (double)cta_minmax<T, true>(mx, red);
 
     // ---- scale (f64 on both paths) -------------------------------------------------------------
     double scale;
@@ -194,16 +246,19 @@ int launch_lut_build(const float *queries, int Q, int d, int normalize, float *q
     TKB_REQUIRE(R != nullptr || Dp == Dpad, "without a rotation Dp must equal the padded dimension");
     const int M = Dp / dpb;
     const size_t tsz = R ? sizeof(double) : sizeof(float);
-    const size_t smem = tsz * (16 * (size_t)M + Dp + LUT_THREADS) + sizeof(float) * Dpad;
+    size_t pw_off = tsz * (16 * (size_t)M + Dp + LUT_THREADS) + sizeof(float) * Dpad;
+    pw_off = (pw_off + 15) / 16 * 16;
+    const size_t ML = 16 * (size_t)M / 32 + 2;
+    const size_t smem = pw_off + (tsz * 9 + 8) * ML;
     TKB_REQUIRE(smem <= 200 * 1024, "dimension too large for the LUT kernel");
     if (R) {
         TKB_CUDA(cudaFuncSetAttribute(lut_build_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lut_build_kernel<double><<<Q, LUT_THREADS, smem, st>>>(queries, d, normalize, q_out, centers, Dp, dpb, R, Dpad,
-                                                                sqrt_n_blocks, log_n_blocks, signd, tables, q_rot, shift, scale);
+                                                                sqrt_n_blocks, log_n_blocks, signd, tables, q_rot, shift, scale, (int)pw_off);
     } else {
         TKB_CUDA(cudaFuncSetAttribute(lut_build_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lut_build_kernel<float><<<Q, LUT_THREADS, smem, st>>>(queries, d, normalize, q_out, centers, Dp, dpb, R, Dpad,
-                                                               sqrt_n_blocks, log_n_blocks, signd, tables, q_rot, shift, scale);
+                                                               sqrt_n_blocks, log_n_blocks, signd, tables, q_rot, shift, scale, (int)pw_off);
     }
     TKB_LAUNCH_CHECK();
     return TKB_OK;
