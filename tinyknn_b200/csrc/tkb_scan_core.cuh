@@ -199,6 +199,44 @@ __device__ __forceinline__ int exact_vector(const uint4 *__restrict__ nat, int64
     return (ORDER == TKB_ORDER_AVX) ? sat_add8<SIGNED>(a0, a1) : a0;
 }
 
+// The same fold for the patch kernel, where nothing else hides latency: the code words and then the table bytes of 8
+// pairs are fetched before the (sequential) adds consume them, so a block costs two load round trips instead of sixteen.
+template <int ORDER, bool SIGNED>
+__device__ __forceinline__ int exact_vector_batched(const uint4 *__restrict__ nat, int64_t chunk, int Ph, int v,
+                                                    const uint8_t *__restrict__ raw /* M*16 bytes */)
+{
+    const int g = v >> 2, sh = 4 * (v & 3) + 16 * (g & 1);
+    int a0 = 0, a1 = 0;
+    for (int p0 = 0; p0 < Ph; p0 += 8) {
+        uint32_t c0[8], c1[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (p0 + i < Ph) {
+                const uint4 w = nat[native_off(chunk, p0 + i, Ph)];
+                c0[i] = (((g < 2) ? w.x : w.y) >> sh) & 15u;
+                c1[i] = (((g < 2) ? w.z : w.w) >> sh) & 15u;
+            }
+        }
+        int t0[8], t1[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (p0 + i < Ph) {
+                t0[i] = raw[32 * (p0 + i) + c0[i]];
+                t1[i] = raw[32 * (p0 + i) + 16 + c1[i]];
+                if (SIGNED) { t0[i] = (int)(int8_t)t0[i]; t1[i] = (int)(int8_t)t1[i]; }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (p0 + i < Ph) {                                    // (p0 + i) & 1 == i & 1
+                if (ORDER == TKB_ORDER_AVX && (i & 1)) a1 = sat_add8<SIGNED>(sat_add8<SIGNED>(a1, t0[i]), t1[i]);
+                else                                  a0 = sat_add8<SIGNED>(sat_add8<SIGNED>(a0, t0[i]), t1[i]);
+            }
+        }
+    }
+    return (ORDER == TKB_ORDER_AVX) ? sat_add8<SIGNED>(a0, a1) : a0;
+}
+
 template <int ORDER, bool SIGNED>
 __device__ __forceinline__ uint4 scan_chunk_exact(const uint4 *__restrict__ nat, int64_t chunk, int Ph,
                                                   const uint8_t *__restrict__ raw)

@@ -202,7 +202,7 @@ patch_kernel(const uint4 *__restrict__ nat, int M, const uint8_t *__restrict__ t
             c = list_chunk_off[l] + en.y;
             off = (seg_off ? seg_off[en.x] : (int64_t)en.x * stride) + 16 * (int64_t)en.y;
         }
-        const int e = exact_vector<ORDER, SIGNED>(nat, c, Ph, v, tables + (size_t)q * M * 16);
+        const int e = exact_vector_batched<ORDER, SIGNED>(nat, c, Ph, v, tables + (size_t)q * M * 16);
         est[off + v] = (uint8_t)e;
     }
 }
