@@ -20,6 +20,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+ORDER = "avx"
+
 WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the reference's published q/s are quoted on
     "glove": dict(n=1_183_514, d=100, metric="angular", n_clusters=1087, components=2000,
@@ -42,6 +44,8 @@ def parse():
     ap.add_argument("--queries", type=int, default=10_000)
     ap.add_argument("--n-probes", type=int, default=10)
     ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--order", default="avx", choices=["avx", "sse"],
+                    help="accumulation order of the 4-bit scan: the reference's default AVX2 build or its SSE build")
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
     ap.add_argument("--cpu-worker", nargs=4, metavar=("DIR", "OUT", "SPEC", "SLICE"), default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -62,7 +66,7 @@ def cpu_worker(dirname, out, spec, slc):
     z = {f[:-4]: np.load(os.path.join(dirname, f), mmap_mode="c") for f in os.listdir(dirname) if f.endswith(".npy")}
     S = O.ivf_state_from_arrays(z)
     kind = "ref" if ref_loader.have_ref_kernels() else "port"
-    K = O.Kernels(kind, "avx")
+    K = O.Kernels(kind, str(z["order"]) if "order" in z else "avx")
     lo, hi = (int(x) for x in slc.split(":"))
     qs = np.array(z["queries"])[lo:hi]
     n_probes, k = int(z["n_probes"]), int(z["k"])
@@ -99,7 +103,7 @@ def run_cpu_arm(ivf, queries, n_probes, k, seconds, cores, steps=3, warmup=1):
     shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
     with tempfile.TemporaryDirectory(dir=shm) as tmp:
         arrs = O.ivf_state_to_arrays(S)
-        arrs.update(queries=queries, n_probes=np.array(n_probes), k=np.array(k))
+        arrs.update(queries=queries, n_probes=np.array(n_probes), k=np.array(k), order=np.array(ORDER))
         for name, a in arrs.items():
             np.save(os.path.join(tmp, name + ".npy"), np.asarray(a))
         per = max(1, len(queries) // cores)
@@ -177,12 +181,15 @@ def main():
     args = parse()
     if args.cpu_worker:
         return cpu_worker(*args.cpu_worker)
+    global ORDER
+    ORDER = args.order
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     w = WORKLOADS[args.workload]
-    cfg = dict(workload="%s, %d queries/step, k=%d, n_probes=%d" % (w["name"], args.queries, args.k, args.n_probes),
-               n_probes=args.n_probes, k=args.k, queries_per_step=args.queries)
+    cfg = dict(workload="%s, %d queries/step, k=%d, n_probes=%d%s" % (w["name"], args.queries, args.k, args.n_probes,
+                                                                      "" if args.order == "avx" else ", sse accumulation order"),
+               n_probes=args.n_probes, k=args.k, queries_per_step=args.queries, order=args.order)
 
     if args.impl == "reference" and rank != 0:
         return 0
@@ -202,6 +209,7 @@ def main():
 
     import tinyknn_b200 as tinyknn                      # noqa: F401
     from tinyknn_b200 import _lib
+    tinyknn.fast_pq.set_order(args.order)
     ivf, qpool = build_index(args, torch)
     Qn = args.queries
     batches = [np.ascontiguousarray(qpool[i * Qn:(i + 1) * Qn]) for i in range(4)]
@@ -247,7 +255,7 @@ def main():
     if rank == 0:
         from oracle import restate as O
         S = O.IVFState.from_ivf(ivf)
-        K = O.Kernels("port", "avx")
+        K = O.Kernels("port", args.order)
         ns = 64
         ids, cnt = ivf.query_batch(batches[0][:ns], order="numpy", k=args.k, n_probes=args.n_probes)
         bad = sum(set(ids[i][:cnt[i]]) != set(O.ivf_query(S, batches[0][i], args.k, n_probes=args.n_probes, kernels=K))

@@ -11,6 +11,7 @@ query the very same index on the CPU. Nothing here is on the timed path.
 import numpy as np
 
 from . import _device as D
+from . import fast_pq as _fp
 from .fast_pq import FastPQ, TransformedData
 from .ivf import IVF
 
@@ -55,11 +56,12 @@ def kmeans(X, k, iters, seed):
     return C
 
 
-def fit_pq(X_sample, dims_per_block=2, rotate_dim=64, iters=8, seed=0, dpad=4):
+def fit_pq(X_sample, dims_per_block=2, rotate_dim=64, iters=8, seed=0, dpad=None):
     """FastPQ with torch-fitted codebooks: attributes as after FastPQ.fit (ref: fast_pq.py:50-104)."""
     t = D.torch()
     n, true_d = X_sample.shape
     dpb = dims_per_block
+    dpad = _fp.dpad if dpad is None else dpad                      # ref: fast_pq.py:21-27 (4 for the avx build, 2 for sse)
     Dpad = -(-true_d // (dpad * dpb)) * (dpad * dpb)
     Xp = t.zeros(n, Dpad, device=X_sample.device, dtype=t.float32)
     Xp[:, :true_d] = X_sample
@@ -89,11 +91,12 @@ def fit_pq(X_sample, dims_per_block=2, rotate_dim=64, iters=8, seed=0, dpad=4):
     return pq
 
 
-def encode(pq, X, dpad=4, chunk=1 << 17):
+def encode(pq, X, dpad=None, chunk=1 << 17):
     """Nearest-of-16 codes per block, uint8 (n, M), on the device (ref: fast_pq.py:147-184)."""
     t = D.torch()
     dpb = pq.dims_per_block
     n, true_d = X.shape
+    dpad = _fp.dpad if dpad is None else dpad
     Dpad = -(-true_d // (dpad * dpb)) * (dpad * dpb)
     d = pq.centers.shape[1]
     M = d // dpb
