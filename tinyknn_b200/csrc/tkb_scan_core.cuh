@@ -20,11 +20,14 @@ struct LutMeta {
     int eligible;          // fast path allowed for this query
     int bias_tot;          // bias_0 + bias_1                         (signed fast path)
     int k0, k1;            // certificate thresholds on the biased lane sums: S'_l <= k_l
+    int steps_ok;          // the byte-SIMD step-by-step fold (scan_chunk_steps) is usable: biased entries < 128
+    int pad_[3];
 };
 
-// smem layout: uint4 rows[M] (biased when eligible, raw otherwise) | raw copy uint4 raw[M] | LutMeta | scratch
-template <bool SIGNED>
-__device__ void prepare_lut(const uint8_t *__restrict__ tq, int M, bool fast_allowed, uint4 *rows, uint4 *raw,
+// smem: uint4 rows[M] (rows biased to >= 0) | raw copy uint4 raw[M] | uint2 sc[M] (clamp bounds of the step-by-step fold
+// after each row, in the biased domain) | LutMeta | scratch. ORDER decides which rows share an accumulator.
+template <int ORDER, bool SIGNED>
+__device__ void prepare_lut(const uint8_t *__restrict__ tq, int M, bool fast_allowed, uint4 *rows, uint4 *raw, uint2 *sc,
                             LutMeta *meta, int *scratch /* 4*M ints */)
 {
     const int tid = threadIdx.x;
@@ -72,6 +75,17 @@ __device__ void prepare_lut(const uint8_t *__restrict__ tq, int M, bool fast_all
         m.bias_tot = bias[0] + bias[1];
         m.k0 = 127 - N[0] + bias[0];
         m.k1 = 127 - N[1] + bias[1];
+        // step-by-step fold in the biased domain: A_j = a_j + B_j with B_j the bias accumulated so far in the row's
+        // accumulator, so that a_j = clamp(a_{j-1} + t_j) becomes A_j = clamp(A_{j-1} + t'_j, -128 + B_j, 127 + B_j)
+        int B[2] = {0, 0};
+        for (int j = 0; j < M; j++) {
+            const int l = ORDER == TKB_ORDER_AVX ? (j >> 1) & 1 : 0;
+            B[l] += scratch[4 * j + 0];
+            const int lo = SIGNED ? -128 + B[l] : 0, hi = SIGNED ? 127 + B[l] : 255;
+            sc[j] = make_uint2((uint32_t)(lo & 0xffff) * 0x00010001u, (uint32_t)(hi & 0xffff) * 0x00010001u);
+        }
+        m.steps_ok = range <= 127 && B[0] <= 30000 && B[1] <= 30000;
+        m.pad_[0] = m.pad_[1] = m.pad_[2] = 0;
         *meta = m;
     }
     __syncthreads();
@@ -180,6 +194,93 @@ __device__ __forceinline__ uint4 scan_chunk_fast(const uint4 *__restrict__ nat, 
     return make_uint4(outw[0], outw[1], outw[2], outw[3]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// The reference's fold step by step, 16 vectors per thread, byte-SIMD: every row is looked up with PRMT like in the
+// fast path, widened to s16x2 at once and added with the clamp of THAT step (VIADDMNMX + VIMNMX), so the result is the
+// reference's for any table whose biased entries stay below 128 -- no certificate needed. About twice the work of
+// scan_chunk_fast; used for the chunks whose certificate failed, for LUTs that are not eligible for the fast path and
+// for the signed SSE order (one accumulator: every prefix matters).
+// ------------------------------------------------------------------------------------------------
+template <bool SIGNED>
+__device__ __forceinline__ void steps_row(const uint4 L, const uint2 c, uint32_t wa, uint32_t wb, uint32_t (&A)[4][2])
+{
+    const uint32_t xa = wa ^ 0x88888888u, xb = wb ^ 0x88888888u;
+    uint32_t b[4];
+    b[0] = prmt(L.x, L.y, wa) + prmt(L.z, L.w, xa);
+    b[1] = prmt(L.x, L.y, wa >> 16) + prmt(L.z, L.w, xa >> 16);
+    b[2] = prmt(L.x, L.y, wb) + prmt(L.z, L.w, xb);
+    b[3] = prmt(L.x, L.y, wb >> 16) + prmt(L.z, L.w, xb >> 16);
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const uint32_t ev = prmt(b[g], 0u, 0x4240u), od = prmt(b[g], 0u, 0x4341u);      // vectors 4g+0,4g+2 / 4g+1,4g+3
+        if (SIGNED) {
+            A[g][0] = __vimin3_s16x2(__viaddmax_s16x2(A[g][0], ev, c.x), c.y, c.y);
+            A[g][1] = __vimin3_s16x2(__viaddmax_s16x2(A[g][1], od, c.x), c.y, c.y);
+        } else {
+            A[g][0] = __viaddmin_u16x2(A[g][0], ev, 0x00ff00ffu);
+            A[g][1] = __viaddmin_u16x2(A[g][1], od, 0x00ff00ffu);
+        }
+    }
+}
+
+template <int ORDER, bool SIGNED>
+__device__ __forceinline__ uint4 scan_chunk_steps(const uint4 *__restrict__ nat, int64_t chunk, int Ph,
+                                                  const uint4 *__restrict__ rows, const uint2 *__restrict__ sc,
+                                                  const LutMeta &meta)
+{
+    uint32_t A0[4][2], A1[4][2];               // accumulators of rows with j&2 == 0 / != 0 (avx); sse uses A0 only
+#pragma unroll
+    for (int g = 0; g < 4; g++) { A0[g][0] = A0[g][1] = A1[g][0] = A1[g][1] = 0; }
+    const uint4 *base = nat + native_off(chunk, 0, Ph);
+    for (int p = 0; p < Ph; p += 2) {
+        const uint4 w0 = ldg_nc_u4(base + (size_t)p * TILE);
+        uint4 w1 = make_uint4(0, 0, 0, 0);
+        const bool two = p + 1 < Ph;
+        if (two) w1 = ldg_nc_u4(base + (size_t)(p + 1) * TILE);
+        steps_row<SIGNED>(rows[2 * p], sc[2 * p], w0.x, w0.y, A0);
+        steps_row<SIGNED>(rows[2 * p + 1], sc[2 * p + 1], w0.z, w0.w, A0);
+        if (two) {
+            if (ORDER == TKB_ORDER_AVX) {
+                steps_row<SIGNED>(rows[2 * p + 2], sc[2 * p + 2], w1.x, w1.y, A1);
+                steps_row<SIGNED>(rows[2 * p + 3], sc[2 * p + 3], w1.z, w1.w, A1);
+            } else {
+                steps_row<SIGNED>(rows[2 * p + 2], sc[2 * p + 2], w1.x, w1.y, A0);
+                steps_row<SIGNED>(rows[2 * p + 3], sc[2 * p + 3], w1.z, w1.w, A0);
+            }
+        }
+    }
+    uint32_t outw[4];
+    if (SIGNED) {
+        const uint32_t nbias = (uint32_t)((-meta.bias_tot) & 0xffff) * 0x00010001u;
+        const uint32_t lo128 = 0xff80ff80u, hi127 = 0x007f007fu;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            uint32_t e[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++)        // sat(a0 + a1): the final add of the avx order; a no-op clamp for sse (A1 == 0)
+                e[h] = __vimin3_s16x2(__viaddmax_s16x2(__vadd2(A0[g][h], A1[g][h]), nbias, lo128), hi127, hi127);
+            outw[g] = prmt(e[0], e[1], 0x6240u);
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            uint32_t e[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) e[h] = __vimin3_u16x2(__vadd2(A0[g][h], A1[g][h]), 0x00ff00ffu, 0x00ff00ffu);
+            outw[g] = prmt(e[0], e[1], 0x6240u);
+        }
+    }
+    return make_uint4(outw[0], outw[1], outw[2], outw[3]);
+}
+
+template <int ORDER, bool SIGNED>
+__device__ __noinline__ uint4 scan_chunk_steps_cold(const uint4 *__restrict__ nat, int64_t chunk, int Ph,
+                                                    const uint4 *__restrict__ rows, const uint2 *__restrict__ sc,
+                                                    const LutMeta &meta)
+{
+    return scan_chunk_steps<ORDER, SIGNED>(nat, chunk, Ph, rows, sc, meta);
+}
+
 // step-by-step saturating fold on the native layout (ineligible LUTs, signed SSE order, patch kernel)
 template <int ORDER, bool SIGNED>
 __device__ __forceinline__ int exact_vector(const uint4 *__restrict__ nat, int64_t chunk, int Ph, int v,
@@ -255,21 +356,6 @@ __device__ __noinline__ uint4 scan_chunk_exact_cold(const uint4 *__restrict__ na
                                                     const uint8_t *__restrict__ raw)
 {
     return scan_chunk_exact<ORDER, SIGNED>(nat, chunk, Ph, raw);
-}
-
-struct PatchList {
-    unsigned long long *count;     // number of flagged chunks (may exceed `cap`: the excess was recomputed inline)
-    uint2 *entry;                  // .x = unit (query, or query * P + probe slot), .y = chunk inside the unit's segment
-    unsigned long long cap;        // entries that fit
-};
-
-// queue a flagged chunk for the patch pass; false = list full, the caller recomputes the chunk itself
-__device__ __forceinline__ bool patch_push(const PatchList &pl, uint32_t unit, uint32_t local)
-{
-    const unsigned long long i = atomicAdd(pl.count, 1ULL);
-    if (i >= pl.cap) return false;
-    pl.entry[i] = make_uint2(unit, local);
-    return true;
 }
 
 }  // namespace tkb

@@ -83,34 +83,95 @@ __global__ void from_native_kernel(const uint4 *__restrict__ nat, int64_t n_chun
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
+constexpr int PEND_CAP = 1024;                 // deferred chunks per CTA; more than that are recomputed on the spot
+
+// Shared-memory carve-up of the scan kernels (P = 0 for the brute-force kernel).
+struct ScanSmem {
+    uint4 *rows, *raw;
+    uint2 *sc;
+    LutMeta *meta;
+    int *scratch;
+    int64_t *pend_off;                         // est byte offset of a deferred chunk
+    uint32_t *pend_chunk;                      // its chunk in the code array
+    int *n_pend;
+    int64_t *seg_c0, *seg_o;
+    int *seg_end;
+};
+
+__host__ __device__ inline size_t scan_smem_carve(unsigned char *base, int M, int P, ScanSmem *out)
+{
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 15) / 16 * 16; return at; };
+    const size_t rows = take((size_t)M * 16), raw = take((size_t)M * 16), sc = take((size_t)M * 8);
+    const size_t meta = take(sizeof(LutMeta)), scratch = take((size_t)M * 16);
+    const size_t po = take((size_t)PEND_CAP * 8), pc = take((size_t)PEND_CAP * 4), np = take(16);
+    const size_t c0 = take((size_t)P * 8), so = take((size_t)P * 8), se = take((size_t)P * 4);
+    if (out) {
+        out->rows = reinterpret_cast<uint4 *>(base + rows); out->raw = reinterpret_cast<uint4 *>(base + raw);
+        out->sc = reinterpret_cast<uint2 *>(base + sc); out->meta = reinterpret_cast<LutMeta *>(base + meta);
+        out->scratch = reinterpret_cast<int *>(base + scratch);
+        out->pend_off = reinterpret_cast<int64_t *>(base + po); out->pend_chunk = reinterpret_cast<uint32_t *>(base + pc);
+        out->n_pend = reinterpret_cast<int *>(base + np);
+        out->seg_c0 = reinterpret_cast<int64_t *>(base + c0); out->seg_o = reinterpret_cast<int64_t *>(base + so);
+        out->seg_end = reinterpret_cast<int *>(base + se);
+    }
+    return o;
+}
+
+// One chunk of one query. The fast path's certificate decides; a chunk that fails it is NOT recomputed by the thread
+// that found it (its warp would wait) but queued in shared memory and recomputed by the whole CTA after the main loop
+// (scan_deferred) with the step-by-step byte-SIMD fold -- the LUT of the query is still in shared memory then.
+template <int ORDER, bool SIGNED, int PH>
+__device__ __forceinline__ void scan_one(const uint4 *__restrict__ nat, int64_t c, int Ph, const ScanSmem &sm, const LutMeta &m,
+                                         uint8_t *__restrict__ est, int64_t off)
+{
+    uint4 o;
+    if (m.eligible) {
+        bool flagged;
+        o = scan_chunk_fast<SIGNED, PH>(nat, c, Ph, sm.rows, m, flagged);
+        if (flagged) {
+            const int i = atomicAdd(sm.n_pend, 1);
+            if (i < PEND_CAP) { sm.pend_off[i] = off; sm.pend_chunk[i] = (uint32_t)c; return; }
+            o = scan_chunk_steps_cold<ORDER, SIGNED>(nat, c, Ph, sm.rows, sm.sc, m);
+        }
+    } else if (m.steps_ok) {
+        o = scan_chunk_steps<ORDER, SIGNED>(nat, c, Ph, sm.rows, sm.sc, m);
+    } else {
+        o = scan_chunk_exact_cold<ORDER, SIGNED>(nat, c, Ph, reinterpret_cast<const uint8_t *>(sm.raw));
+    }
+    *reinterpret_cast<uint4 *>(est + off) = o;
+}
+
+template <int ORDER, bool SIGNED>
+__device__ __forceinline__ void scan_deferred(const uint4 *__restrict__ nat, int Ph, const ScanSmem &sm, const LutMeta &m,
+                                              uint8_t *__restrict__ est, unsigned long long *stat)
+{
+    __syncthreads();
+    const int total = *sm.n_pend, n = total < PEND_CAP ? total : PEND_CAP;
+    if (threadIdx.x == 0 && total && stat) atomicAdd(stat, (unsigned long long)total);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        *reinterpret_cast<uint4 *>(est + sm.pend_off[i]) =
+            scan_chunk_steps<ORDER, SIGNED>(nat, (int64_t)sm.pend_chunk[i], Ph, sm.rows, sm.sc, m);
+}
+
 template <int ORDER, bool SIGNED, int PH = 0>
 __global__ void __launch_bounds__(FAST_THREADS, 3)
 estimate_fast_kernel(const uint4 *__restrict__ nat, int64_t n_chunks, int M, const uint8_t *__restrict__ tables,
-                     uint8_t *__restrict__ est, int64_t est_stride, PatchList patch)
+                     uint8_t *__restrict__ est, int64_t est_stride, unsigned long long *stat, int Qn)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    uint4 *rows = reinterpret_cast<uint4 *>(smem);
-    uint4 *raw = rows + M;
-    LutMeta *meta = reinterpret_cast<LutMeta *>(raw + M);
-    int *scratch = reinterpret_cast<int *>(meta + 1);
-    const int q = blockIdx.y, Ph = M >> 1;
+    ScanSmem sm;
+    scan_smem_carve(smem, M, 0, &sm);
+    // blockIdx.x = stripe * Qn + query: the CTAs that run together read the same stripe of codes for different queries,
+    // so a code array larger than L2 is still fetched from HBM about once per batch, not once per query
+    const int q = blockIdx.x % Qn, stripe = blockIdx.x / Qn, n_stripes = gridDim.x / Qn, Ph = M >> 1;
+    if (threadIdx.x == 0) *sm.n_pend = 0;
     const bool fast_allowed = !(SIGNED && ORDER == TKB_ORDER_SSE);
-    prepare_lut<SIGNED>(tables + (size_t)q * M * 16, M, fast_allowed, rows, raw, meta, scratch);
-    const LutMeta m = *meta;
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks;
-         c += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t off = (int64_t)q * est_stride + 16 * c;
-        uint4 o;
-        if (m.eligible) {
-            bool flagged;
-            o = scan_chunk_fast<SIGNED, PH>(nat, c, Ph, rows, m, flagged);
-            if (flagged && !patch_push(patch, (uint32_t)q, (uint32_t)c))
-                o = scan_chunk_exact_cold<ORDER, SIGNED>(nat, c, Ph, reinterpret_cast<const uint8_t *>(raw));
-        } else {
-            o = scan_chunk_exact<ORDER, SIGNED>(nat, c, Ph, reinterpret_cast<const uint8_t *>(raw));
-        }
-        *reinterpret_cast<uint4 *>(est + off) = o;
-    }
+    prepare_lut<ORDER, SIGNED>(tables + (size_t)q * M * 16, M, fast_allowed, sm.rows, sm.raw, sm.sc, sm.meta, sm.scratch);
+    const LutMeta m = *sm.meta;
+    for (int64_t c = (int64_t)stripe * blockDim.x + threadIdx.x; c < n_chunks; c += (int64_t)n_stripes * blockDim.x)
+        scan_one<ORDER, SIGNED, PH>(nat, c, Ph, sm, m, est, (int64_t)q * est_stride + 16 * c);
+    scan_deferred<ORDER, SIGNED>(nat, Ph, sm, m, est, stat);
 }
 
 // One CTA column per query: the P probed lists are walked as one flat range of chunks, so the LUT is
@@ -123,18 +184,15 @@ __global__ void __launch_bounds__(FAST_THREADS, 3)
 ivf_scan_fast_kernel(const uint4 *__restrict__ nat, const int64_t *__restrict__ list_chunk_off,
                      const int32_t *__restrict__ list_size, int n_lists, int M,
                      const uint8_t *__restrict__ tables, const int32_t *__restrict__ probes, int P,
-                     uint8_t *__restrict__ est, int64_t slot_stride, const int64_t *__restrict__ seg_off, PatchList patch)
+                     uint8_t *__restrict__ est, int64_t slot_stride, const int64_t *__restrict__ seg_off,
+                     unsigned long long *stat)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    uint4 *rows = reinterpret_cast<uint4 *>(smem);
-    uint4 *raw = rows + M;
-    LutMeta *meta = reinterpret_cast<LutMeta *>(raw + M);
-    int *scratch = reinterpret_cast<int *>(meta + 1);
-    int64_t *seg_c0 = reinterpret_cast<int64_t *>(scratch + 4 * M);                       // 16-byte aligned offset
-    int64_t *seg_o = seg_c0 + P;                                                         // est offset of the segment
-    int *seg_end = reinterpret_cast<int *>(seg_o + P);                                   // inclusive prefix of chunk counts
+    ScanSmem sm;
+    scan_smem_carve(smem, M, P, &sm);
     const int q = blockIdx.y, Ph = M >> 1;
     if (threadIdx.x == 0) {
+        *sm.n_pend = 0;
         int run = 0;
         for (int s = 0; s < P; s++) {
             int l = probes[(size_t)q * P + s];
@@ -146,65 +204,23 @@ ivf_scan_fast_kernel(const uint4 *__restrict__ nat, const int64_t *__restrict__ 
                 nc = list_chunk_off[l + 1] - c0;
                 if (list_size) { const int64_t real = ((int64_t)list_size[l] + 15) >> 4; if (real < nc) nc = real; }
             }
-            seg_c0[s] = c0;
-            seg_o[s] = o;
+            sm.seg_c0[s] = c0;
+            sm.seg_o[s] = o;
             run += (int)nc;
-            seg_end[s] = run;
+            sm.seg_end[s] = run;
         }
     }
     const bool fast_allowed = !(SIGNED && ORDER == TKB_ORDER_SSE);
-    prepare_lut<SIGNED>(tables + (size_t)q * M * 16, M, fast_allowed, rows, raw, meta, scratch);   // syncs
-    const LutMeta m = *meta;
-    const int total = seg_end[P - 1];
+    prepare_lut<ORDER, SIGNED>(tables + (size_t)q * M * 16, M, fast_allowed, sm.rows, sm.raw, sm.sc, sm.meta, sm.scratch);   // syncs
+    const LutMeta m = *sm.meta;
+    const int total = sm.seg_end[P - 1];
     int s = 0;                                       // f only grows: the slot search resumes where it stopped
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
-        while (f >= seg_end[s]) s++;
-        const int local = f - (s ? seg_end[s - 1] : 0);
-        const int64_t c = seg_c0[s] + local;
-        const int64_t off = seg_o[s] + 16 * (int64_t)local;
-        uint4 o;
-        if (m.eligible) {
-            bool flagged;
-            o = scan_chunk_fast<SIGNED, PH>(nat, c, Ph, rows, m, flagged);
-            if (flagged && !patch_push(patch, (uint32_t)(q * P + s), (uint32_t)local))
-                o = scan_chunk_exact_cold<ORDER, SIGNED>(nat, c, Ph, reinterpret_cast<const uint8_t *>(raw));
-        } else {
-            o = scan_chunk_exact<ORDER, SIGNED>(nat, c, Ph, reinterpret_cast<const uint8_t *>(raw));
-        }
-        *reinterpret_cast<uint4 *>(est + off) = o;
+        while (f >= sm.seg_end[s]) s++;
+        const int local = f - (s ? sm.seg_end[s - 1] : 0);
+        scan_one<ORDER, SIGNED, PH>(nat, sm.seg_c0[s] + local, Ph, sm, m, est, sm.seg_o[s] + 16 * (int64_t)local);
     }
-}
-
-// Patch pass: one half-warp per queued chunk recomputes its 16 estimates with the reference's fold.
-// mode 0: brute force (unit = q, chunk = local); mode 1: IVF (unit = q*P+s, chunk = list start + local).
-template <int ORDER, bool SIGNED>
-__global__ void __launch_bounds__(256)
-patch_kernel(const uint4 *__restrict__ nat, int M, const uint8_t *__restrict__ tables, uint8_t *__restrict__ est,
-             PatchList patch, int mode, int64_t stride /* est_stride or slot_stride */, const int64_t *__restrict__ seg_off,
-             const int64_t *__restrict__ list_chunk_off, int n_lists, const int32_t *__restrict__ probes, int P)
-{
-    unsigned long long count = *patch.count;
-    if (count > patch.cap) count = patch.cap;
-    const int Ph = M >> 1;
-    const int hw = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, v = threadIdx.x & 15;
-    const int n_hw = (gridDim.x * blockDim.x) >> 4;
-    for (unsigned long long i = hw; i < count; i += n_hw) {
-        const uint2 en = patch.entry[i];
-        int64_t q, c, off;
-        if (mode == 0) {
-            q = en.x;
-            c = en.y;
-            off = q * stride + 16 * c;
-        } else {
-            q = en.x / (uint32_t)P;
-            int l = probes[en.x];
-            if (l < 0) l += n_lists;
-            c = list_chunk_off[l] + en.y;
-            off = (seg_off ? seg_off[en.x] : (int64_t)en.x * stride) + 16 * (int64_t)en.y;
-        }
-        const int e = exact_vector_batched<ORDER, SIGNED>(nat, c, Ph, v, tables + (size_t)q * M * 16);
-        est[off + v] = (uint8_t)e;
-    }
+    scan_deferred<ORDER, SIGNED>(nat, Ph, sm, m, est, stat);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -212,7 +228,7 @@ patch_kernel(const uint4 *__restrict__ nat, int M, const uint8_t *__restrict__ t
 // ------------------------------------------------------------------------------------------------
 static size_t fast_smem_bytes(int M, int P)
 {
-    return (size_t)M * 32 + sizeof(LutMeta) + sizeof(int) * (4 * (size_t)M + 4) + (size_t)P * 20 + 16;
+    return scan_smem_carve(nullptr, M, P, nullptr);
 }
 
 static int check_fast_args(int M, int order)
@@ -277,14 +293,15 @@ int launch_codes_from_native(const void *native, int64_t n_chunks, int M, uint64
     return TKB_OK;
 }
 
-// workspace = 16-byte header (flagged-chunk counter) + 8-byte entries; whatever does not fit is recomputed inline
-static int split_workspace(void *workspace, int64_t workspace_bytes, PatchList &pl)
+// The workspace only carries a statistic now: its first 8 bytes count the chunks whose certificate failed (they are
+// recomputed inside the scan kernel). NULL is allowed.
+static int stat_counter(void *workspace, int64_t workspace_bytes, unsigned long long **stat, cudaStream_t st)
 {
-    TKB_REQUIRE(workspace && workspace_bytes >= 16 + 8, "scan workspace too small (need at least 24 bytes)");
+    *stat = nullptr;
+    if (!workspace || workspace_bytes < 16) return TKB_OK;
     TKB_REQUIRE((uintptr_t)workspace % 16 == 0, "workspace must be 16-byte aligned");
-    pl.count = reinterpret_cast<unsigned long long *>(workspace);
-    pl.entry = reinterpret_cast<uint2 *>(reinterpret_cast<char *>(workspace) + 16);
-    pl.cap = (unsigned long long)((workspace_bytes - 16) / 8);
+    *stat = reinterpret_cast<unsigned long long *>(workspace);
+    TKB_CUDA(cudaMemsetAsync(workspace, 0, 16, st));
     return TKB_OK;
 }
 
@@ -300,29 +317,24 @@ int launch_estimate_native(const void *native, int64_t n_chunks, int M, const ui
     TKB_REQUIRE(est_stride >= 16 * n_chunks && est_stride % 16 == 0, "est_stride must be a multiple of 16 and >= 16*n_chunks");
     TKB_REQUIRE(((uintptr_t)native % 16 == 0) && ((uintptr_t)est % 16 == 0) && ((uintptr_t)tables % 16 == 0),
                 "device pointers must be 16-byte aligned");
-    PatchList pl;
-    if (int rc = split_workspace(workspace, workspace_bytes, pl)) return rc;
+    unsigned long long *stat;
+    if (int rc = stat_counter(workspace, workspace_bytes, &stat, st)) return rc;
     // short code arrays (the PQ-encoded centroids of an IVF index): a CTA only as wide as the array
     const int threads = n_chunks >= FAST_THREADS ? FAST_THREADS : (int)((n_chunks + 31) / 32 * 32 < 64 ? 64 : (n_chunks + 31) / 32 * 32);
     int64_t tiles = (n_chunks + threads - 1) / threads;
-    if (tiles > 148 * 8 && Q > 1) tiles = 148 * 8;                 // grid-stride beyond that
-    TKB_REQUIRE(tiles <= 0x7fffffff, "too many chunks for one launch");
+    if (tiles > 148 * 6) tiles = 148 * 6;                          // grid-stride beyond that: the LUT prologue is paid per CTA
+    if (tiles > 32768) tiles = 32768;                              // tiles * queries stays below 2^31
     const size_t smem = fast_smem_bytes(M, 0);
     const uint4 *n4 = reinterpret_cast<const uint4 *>(native);
     for (int q0 = 0; q0 < Q; q0 += 65535) {
         const int qn = (Q - q0 < 65535) ? (Q - q0) : 65535;
-        dim3 grid((unsigned)tiles, (unsigned)qn);
-        TKB_CUDA(cudaMemsetAsync(pl.count, 0, 16, st));
-        // patch entries are relative to this launch's block of queries: both kernels get the shifted pointers
+        const unsigned grid = (unsigned)(tiles * qn);
         if (order == TKB_ORDER_AVX && signd)
             TKB_DISPATCH_FAST_AVXS(estimate_fast_kernel, grid, threads, smem, st, n4, n_chunks, M,
-                                   tables + (size_t)q0 * M * 16, est + (size_t)q0 * est_stride, est_stride, pl);
+                                   tables + (size_t)q0 * M * 16, est + (size_t)q0 * est_stride, est_stride, stat, qn);
         else
             TKB_DISPATCH_FAST(estimate_fast_kernel, grid, threads, smem, st, n4, n_chunks, M,
-                              tables + (size_t)q0 * M * 16, est + (size_t)q0 * est_stride, est_stride, pl);
-        TKB_LAUNCH_CHECK();
-        TKB_DISPATCH_FAST(patch_kernel, 148 * 4, 256, 0, st, n4, M, tables + (size_t)q0 * M * 16,
-                          est + (size_t)q0 * est_stride, pl, 0, est_stride, nullptr, nullptr, 0, nullptr, 1);
+                              tables + (size_t)q0 * M * 16, est + (size_t)q0 * est_stride, est_stride, stat, qn);
         TKB_LAUNCH_CHECK();
     }
     return TKB_OK;
@@ -340,8 +352,8 @@ int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, co
     TKB_REQUIRE(slot_stride % 16 == 0, "slot_stride must be a multiple of 16");
     TKB_REQUIRE(P <= 4096, "too many probes");
     TKB_REQUIRE((int64_t)Q * P <= 0xffffffffLL, "too many (query, probe) units for one launch");
-    PatchList pl;
-    if (int rc = split_workspace(workspace, workspace_bytes, pl)) return rc;
+    unsigned long long *stat;
+    if (int rc = stat_counter(workspace, workspace_bytes, &stat, st)) return rc;
     // enough CTAs to fill the machine when Q is small; otherwise one CTA per query walks all its lists
     if (max_chunks_per_query <= 0) max_chunks_per_query = (int64_t)P * (slot_stride / 16);
     // 128-thread CTAs: a query's ~700 chunks quantise better over 128 threads than over 256 (0.58 -> 0.545 ms measured)
@@ -358,16 +370,12 @@ int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, co
         dim3 grid((unsigned)splits, (unsigned)qn);
         const int64_t *so = seg_off ? seg_off + (size_t)q0 * P : nullptr;          // offsets stay relative to `est`
         uint8_t *eb = seg_off ? est : est + (size_t)q0 * P * slot_stride;
-        TKB_CUDA(cudaMemsetAsync(pl.count, 0, 16, st));
         if (order == TKB_ORDER_AVX && signd)
             TKB_DISPATCH_FAST_AVXS(ivf_scan_fast_kernel, grid, scan_threads, smem, st, n4, list_chunk_off, list_size, n_lists, M,
-                                   tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, pl);
+                                   tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat);
         else
             TKB_DISPATCH_FAST(ivf_scan_fast_kernel, grid, scan_threads, smem, st, n4, list_chunk_off, list_size, n_lists, M,
-                              tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, pl);
-        TKB_LAUNCH_CHECK();
-        TKB_DISPATCH_FAST(patch_kernel, 148 * 4, 256, 0, st, n4, M, tables + (size_t)q0 * M * 16, eb, pl, 1, slot_stride,
-                          so, list_chunk_off, n_lists, probes + (size_t)q0 * P, P);
+                              tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat);
         TKB_LAUNCH_CHECK();
     }
     return TKB_OK;
