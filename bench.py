@@ -29,6 +29,11 @@ WORKLOADS = {
     # BASELINE.json configs[2]
     "sift": dict(n=1_000_000, d=128, metric="euclidean", n_clusters=1024, components=2000,
                  name="IVF euclidean, SIFT-1M shape synthetic 1000000x128, 1024 lists"),
+    # BASELINE.json configs[4] (one GPU holds the whole index; `--gpus N` shards its lists) and a 10M stand-in
+    "ivf100m": dict(n=100_000_000, d=128, metric="euclidean", n_clusters=16384, components=50_000,
+                    name="IVF euclidean 100M x 128 synthetic, 16384 lists"),
+    "ivf10m": dict(n=10_000_000, d=128, metric="euclidean", n_clusters=4096, components=20_000,
+                   name="IVF euclidean 10M x 128 synthetic, 4096 lists"),
     "tiny": dict(n=60_000, d=100, metric="angular", n_clusters=128, components=200,
                  name="IVF angular tiny (CI)"),
 }
@@ -173,7 +178,8 @@ def build_index(args, torch, seed=10):
     w = WORKLOADS[args.workload]
     X = synth.clustered(w["n"] + 4 * args.queries, w["d"], w["components"], seed, normalize=False)
     data, qpool = X[:w["n"]], X[w["n"]:]
-    ivf = synth.build_ivf(data, w["metric"], w["n_clusters"], seed=seed)
+    big = w["n"] * w["d"] * 4 > (8 << 30)                          # raw vectors stay on the GPU only (rows fetched on demand)
+    ivf = synth.build_ivf(data, w["metric"], w["n_clusters"], seed=seed, host_data=not big)
     return ivf, qpool.cpu().numpy()
 
 
@@ -215,6 +221,10 @@ def main():
     batches = [np.ascontiguousarray(qpool[i * Qn:(i + 1) * Qn]) for i in range(4)]
 
     # ---------------- reference arm: the reference's CPU path on this box's host cores ----------------
+    if args.impl == "reference" and not isinstance(ivf.data, np.ndarray):
+        print(json.dumps(dict(impl="reference", unavailable="the raw vectors of this workload (%.0f GB) are kept on the GPU "
+                              "only; the reference arm runs on the default workload" % (w["n"] * w["d"] * 4 / 2 ** 30))))
+        return 0
     if args.impl == "reference":
         cores = os.cpu_count() or 1
         cb, step_s, per_step = run_cpu_arm(ivf, batches[0], args.n_probes, args.k, max(4.0, args.cpu_seconds * 2), cores,
@@ -304,6 +314,10 @@ def main():
         run(dev_batches[i % 4], to_host=False, **one)
     stages = ivf.stage_times()
     last = dict(ivf._last)
+    n_prof = min(args.steps, 10)
+    scan_log = list(ivf.__dict__.get("_scan_log") or [])
+    blocks_per_step = max(1, len(scan_log) // n_prof)                # a batch larger than the estimate workspace runs in blocks
+    scan_log = scan_log[-blocks_per_step:]
     staged = None
     if "fused" in stages and not sharded:           # the stage-by-stage kernels of the same path, for the scan kernel's own roofline
         ivf.profile(True)
@@ -336,13 +350,16 @@ def main():
         # algorithmic bytes of the dominant kernel (inverted-list scan): M/2 B of codes per scanned
         # (query, vector) + 1 B estimate written; scanned vectors counted from the probe lists of the last step
         # (on this rank: with sharded lists, the segments of the lists rank 0 owns, for the queries of all ranks)
-        probes = last["scan_probes"].cpu().numpy().astype(np.int64)
-        present = np.ones_like(probes, dtype=bool) if last.get("scan_seg_off") is None else last["scan_seg_off"].cpu().numpy() >= 0
-        present &= probes != -(2 ** 31)
-        probes = np.where(probes < 0, probes + dev["n_lists"], probes)
         real_chunks = (dev["host_sizes"].astype(np.int64) + 15) // 16      # the reference pads each list to 16 (not to our tiles)
-        scanned = int(16 * (real_chunks[np.where(present, probes, 0)] * present).sum())
-        Qk = probes.shape[0]
+        scanned, Qk = 0, 0
+        for pr_, so_ in (scan_log or [(last["scan_probes"], last.get("scan_seg_off"))]):   # the blocks of ONE step
+            probes = pr_.cpu().numpy().astype(np.int64)
+            present = np.ones_like(probes, dtype=bool) if so_ is None else so_.cpu().numpy() >= 0
+            present &= probes != -(2 ** 31)
+            probes = np.where(probes < 0, probes + dev["n_lists"], probes)
+            scanned += int(16 * (real_chunks[np.where(present, probes, 0)] * present).sum())
+            Qk += probes.shape[0]
+        per_step = lambda v: float(np.sum(v)) / max(1, len(v) // blocks_per_step)      # ms per step of a stage
         fused_run = "fused" in stages
         peaks = {}
         try:
@@ -368,7 +385,7 @@ def main():
             # one launch = LUT rows read (16*M B/query) + M/2 code bytes per scanned vector + the raw rows of the heap's
             # candidates (R*d*itemsize per query; every heap is full on this workload); the estimates (1 B per scanned
             # vector, written and read back) stay in the CTA's L2-resident scratch and are NOT counted
-            k_ms = float(np.mean(stages["fused"]))
+            k_ms = per_step(stages["fused"])
             R1 = (args.n_probes + 1) * args.k + 1
             itemsize = 4 if dev["data_dtype"] == 0 else 8
             alg_bytes = scanned * (M // 2) + Qk * 16 * M + Qk * R1 * dev["d"] * itemsize
@@ -377,16 +394,17 @@ def main():
                         algorithmic_bytes_per_launch=alg_bytes, scanned_vectors_per_launch=scanned, kernel_ms=k_ms,
                         codes_per_s=scanned / (k_ms * 1e-3), flagged_chunks=counter("fused_ws"))
             if staged:
-                roof["scan_kernel_alone"] = scan_roof(float(np.mean(staged["scan"])), None)
-                roof["staged_stage_ms"] = {k: float(np.mean(v)) for k, v in staged.items()}
+                roof["scan_kernel_alone"] = scan_roof(per_step(staged["scan"]), None)
+                roof["staged_stage_ms"] = {k: per_step(v) for k, v in staged.items()}
         else:
-            roof = dict(bound="hbm", scanned_vectors_per_launch=scanned, **scan_roof(float(np.mean(stages["scan"])), counter("patch_ws")))
+            roof = dict(bound="hbm", scanned_vectors_per_launch=scanned, launches_per_step=blocks_per_step,
+                        **scan_roof(per_step(stages["scan"]), counter("patch_ws")))
         roof.update(peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                     kernel_timing="CUDA events around the launch on its stream, one stream, %d steps right after the timed region"
                                   % min(args.steps, 10),
-                    stage_ms={k: float(np.mean(v)) for k, v in stages.items()})
+                    stage_ms={k: per_step(v) for k, v in stages.items()})
         cb = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and isinstance(ivf.data, np.ndarray):
             cb = run_cpu_arm(ivf, batches[0], args.n_probes, args.k, args.cpu_seconds, os.cpu_count() or 1)[0]
         line = dict(metric="IVF-PQ queries/s", value=value, unit="queries/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",

@@ -371,7 +371,7 @@ constexpr uint32_t RQ2_EMPTY = 0x00ffffffu;       // payload of a heap slot that
 constexpr uint32_t RQ2_SENTINEL = 0x80ffffffu;    // value -128
 
 template <bool SIGNED, int L>
-__global__ void __launch_bounds__(RQ_THREADS)
+__global__ void __launch_bounds__(RQ_THREADS, 5)            // 5 CTAs/SM: 10 000 queries at 16 per CTA are one wave
 replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, const int64_t *__restrict__ seg_off,
                   int64_t n_chunks0, int n0, const int64_t *__restrict__ list_chunk_off,
                   const int32_t *__restrict__ list_size, int n_lists, const int64_t *__restrict__ ids,
@@ -437,56 +437,80 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
             int end = (total - cursor < W) ? total : cursor + W;
             int count = 0, sg = s_seg[t];
             uint32_t *qu = QU + (size_t)t * (QCAP + 2);
-            for (int base = cursor; base < end; base += 32) {
-                const int cc = base + lane;
-                const bool act = cc < end;
-                uint32_t m = 0;
-                uint4 e = make_uint4(0, 0, 0, 0);
-                int sl = sg;
-                if (act) {
-                    while (cc >= c[sl + 1]) sl++;
-                    const int local = cc - c[sl];
-                    int n;
-                    const uint8_t *ep;
-                    if (mode == 1) {
-                        n = list_size[probes[(size_t)q * P + sl]];
-                        ep = est + (seg_off ? seg_off[(size_t)q * P + sl] : ((int64_t)q * P + sl) * stride);
-                    } else {
-                        n = n0;
-                        ep = est + (int64_t)q * stride;
-                    }
-                    e = ldg_nc_u4(reinterpret_cast<const uint4 *>(ep) + local);
-                    if (!SIGNED) { e.x ^= 0x80808080u; e.y ^= 0x80808080u; e.z ^= 0x80808080u; e.w ^= 0x80808080u; }
-                    const int rem = n - 16 * local;
-                    m = cand_mask16<true>(e, bound) & (rem >= 16 ? 0xffffu : ((1u << rem) - 1u));
-                }
-                const int last = end - 1 - base;
-                sg = __shfl_sync(FULL, sl, last < 31 ? last : 31);
-                const int cnt = __popc(m);
-                int incl = cnt;
+            // PF steps of 32 chunks are fetched before the first is examined: a window is thousands of chunks long once the
+            // bound has settled and almost nothing survives the filter, so the walk is a chain of load latencies otherwise
+            constexpr int PF = 4;
+            for (int base0 = cursor; base0 < end; base0 += 32 * PF) {
+                uint4 ev[PF];
+                int slv[PF], remv[PF];
+                {
+                    int sl = sg;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-                const int tot = __shfl_sync(FULL, incl, 31);
+                    for (int u = 0; u < PF; u++) {
+                        const int cc = base0 + 32 * u + lane;
+                        ev[u] = make_uint4(0, 0, 0, 0); remv[u] = 0;
+                        if (cc < end) {
+                            while (cc >= c[sl + 1]) sl++;
+                            const int local = cc - c[sl];
+                            int n;
+                            const uint8_t *ep;
+                            if (mode == 1) {
+                                n = list_size[probes[(size_t)q * P + sl]];
+                                ep = est + (seg_off ? seg_off[(size_t)q * P + sl] : ((int64_t)q * P + sl) * stride);
+                            } else {
+                                n = n0;
+                                ep = est + (int64_t)q * stride;
+                            }
+                            ev[u] = ldg_nc_u4(reinterpret_cast<const uint4 *>(ep) + local);
+                            remv[u] = n - 16 * local;
+                        }
+                        slv[u] = sl;
+                    }
+                }
                 bool cut = false;
-                int keep_tot = tot;
-                if (count + tot > QCAP) {
-                    const unsigned over = __ballot_sync(FULL, count + incl > QCAP);
-                    const int cl = __ffs(over) - 1;
-                    keep_tot = __shfl_sync(FULL, incl - cnt, cl);
-                    sg = __shfl_sync(FULL, sl, cl);
-                    if (lane >= cl) m = 0;
-                    end = base + cl;
-                    cut = true;
+#pragma unroll
+                for (int u = 0; u < PF; u++) {
+                    const int base = base0 + 32 * u;
+                    if (base >= end) break;
+                    const int cc = base + lane;
+                    const bool act = cc < end;
+                    uint32_t m = 0;
+                    uint4 e = ev[u];
+                    const int sl = slv[u];
+                    if (act) {
+                        if (!SIGNED) { e.x ^= 0x80808080u; e.y ^= 0x80808080u; e.z ^= 0x80808080u; e.w ^= 0x80808080u; }
+                        const int rem = remv[u];
+                        m = cand_mask16<true>(e, bound) & (rem >= 16 ? 0xffffu : ((1u << rem) - 1u));
+                    }
+                    const int last = end - 1 - base;
+                    sg = __shfl_sync(FULL, sl, last < 31 ? last : 31);
+                    if (__ballot_sync(FULL, m != 0) == 0) continue;          // nothing survives in these 32 chunks: the common case
+                    const int cnt = __popc(m);
+                    int incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                    const int tot = __shfl_sync(FULL, incl, 31);
+                    int keep_tot = tot;
+                    if (count + tot > QCAP) {
+                        const unsigned over = __ballot_sync(FULL, count + incl > QCAP);
+                        const int cl = __ffs(over) - 1;
+                        keep_tot = __shfl_sync(FULL, incl - cnt, cl);
+                        sg = __shfl_sync(FULL, sl, cl);
+                        if (lane >= cl) m = 0;
+                        end = base + cl;
+                        cut = true;
+                    }
+                    int k = count + incl - cnt;
+                    const uint32_t ws[4] = {e.x, e.y, e.z, e.w};
+                    while (m) {
+                        const int v = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t byte = (ws[v >> 2] >> (8 * (v & 3))) & 0xffu;
+                        qu[k++] = (byte << 24) | (16u * (uint32_t)cc + v);
+                    }
+                    count += keep_tot;
+                    if (cut) break;
                 }
-                int k = count + incl - cnt;
-                const uint32_t ws[4] = {e.x, e.y, e.z, e.w};
-                while (m) {
-                    const int v = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint32_t byte = (ws[v >> 2] >> (8 * (v & 3))) & 0xffu;
-                    qu[k++] = (byte << 24) | (16u * (uint32_t)cc + v);
-                }
-                count += keep_tot;
                 if (cut) break;
             }
             if (lane == 0) { s_cursor[t] = end; s_seg[t] = sg; s_count[t] = count; s_round[t] = 1; qu[count] = RQ2_SENTINEL; qu[count + 1] = RQ2_SENTINEL; }

@@ -361,7 +361,12 @@ int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, co
     if (!scan_threads) { const char *e = getenv("TKB_SCAN_THREADS"); scan_threads = e ? atoi(e) : 128; if (scan_threads != 64 && scan_threads != 256) scan_threads = 128; }
     int64_t splits = (148 * 4 + Q - 1) / Q;
     const int64_t max_splits = (max_chunks_per_query + scan_threads - 1) / scan_threads;
+    // long probe lists (100M-vector indexes: tens of thousands of chunks per query): several CTAs per query, so that the
+    // grid is many waves of similar CTAs instead of a few waves whose length is the longest query
+    const int64_t long_splits = max_chunks_per_query / (32 * scan_threads);
+    if (splits < long_splits) splits = long_splits;
     if (splits > max_splits) splits = max_splits;
+    if (splits > 1024) splits = 1024;
     if (splits < 1) splits = 1;
     const size_t smem = fast_smem_bytes(M, P);
     const uint4 *n4 = reinterpret_cast<const uint4 *>(native);

@@ -28,13 +28,14 @@ from ._lib import lib, check, DTYPE_F32, DTYPE_F64, PROBE_SKIP, PLAN_SEND, PLAN_
 from .fast_pq import FastPQ, TransformedData, query_pq  # noqa: F401  (ivf.py:5 re-export)
 from .utils import timer, knn_brute, group_data_by_indices, bottom_k
 
-_WORKSPACE_BYTES = 2 << 30          # cap of the per-batch estimate buffer (queries are sub-batched)
+_WORKSPACE_BYTES = 2 << 30          # cap of the per-batch estimate buffer (queries are sub-batched); see _workspace_cap
 _N_STREAMS = int(os.environ.get("TKB_STREAMS", "2"))
 _SUB_QUERIES = int(os.environ.get("TKB_SUB_QUERIES", "5000"))      # target queries per sub-batch
 # One kernel after probe selection (tkb_ivf_query_fused_dev). Off by default: measured slower than the stage-by-stage
 # kernels at large batches (a CTA holds its scan registers while it sits in the latency-bound replay), DESIGN.md 4.6.
 FUSED = os.environ.get("TKB_FUSED", "0") != "0"
 _streams = {}
+_ws_cap = {}
 
 
 def _side_streams(n):
@@ -44,6 +45,17 @@ def _side_streams(n):
     while len(pool) < n:
         pool.append(t.cuda.Stream())
     return pool[:n]
+
+
+def _workspace_cap():
+    """Bytes the estimate buffer of one block of queries may reserve: it is sized for the largest list in every probe slot
+    (only the planned part is touched), so a skewed 100M-vector index needs room or its batches fall apart into blocks too
+    small to fill the GPU. A quarter of the free memory, at least 2 GB, at most 32 GB."""
+    dev_ = D.torch().cuda.current_device()
+    if dev_ not in _ws_cap:                                         # asked once per device: cudaMemGetInfo synchronises
+        free, _ = D.torch().cuda.mem_get_info()
+        _ws_cap[dev_] = int(min(32 << 30, max(_WORKSPACE_BYTES, free // 4)))
+    return _ws_cap[dev_]
 
 
 def _sub_batches(Q):
@@ -101,7 +113,7 @@ class IVF:
 
     # ------------------------------------------------------------------ device index ---------
     def __getstate__(self):
-        return {k: v for k, v in self.__dict__.items() if k not in ("_dev", "_last", "_prof", "_keep_heaps")}
+        return {k: v for k, v in self.__dict__.items() if k not in ("_dev", "_last", "_prof", "_keep_heaps", "_scan_log")}
 
     def invalidate(self):
         """Forget the device copy (call after replacing index arrays by hand)."""
@@ -167,6 +179,7 @@ class IVF:
         """Record a CUDA-event pair around every stage of the following query_batch calls
         (on the launching stream). Read them back with `stage_times()`."""
         self.__dict__["_prof"] = {} if enabled else None
+        self.__dict__["_scan_log"] = []
 
     @contextmanager
     def _stage(self, name):
@@ -215,7 +228,7 @@ class IVF:
         Rc = min(2 * P + 10, C)                                         # ref: fast_pq.py:293-295
         if pass_1 is None:
             pass_1 = (n_probes + 1) * k + 1                             # ref: ivf.py:135-136
-        qb = int(max(1, min(Q, _WORKSPACE_BYTES // max(1, P * 16 * max(dev["max_real_chunks"], 1)))))
+        qb = int(max(1, min(Q, _workspace_cap() // max(1, P * 16 * max(dev["max_real_chunks"], 1)))))
         # Sub-batches on alternating side streams: the latency-bound stages of one sub-batch (heap replay, row
         # gathers) overlap the issue-bound scan of the next. Only in throughput mode; order="numpy" syncs per stage.
         n_sub = 1 if order != "device" else (_sub_batches(Q) if sub_batches is None else max(1, int(sub_batches)))
@@ -306,6 +319,8 @@ class IVF:
         M, n_lists = dev["M"], dev["n_lists"]
         max_q_chunks = P * max(dev["max_real_chunks"], 1)
         self._last.update(scan_probes=probes, scan_seg_off=seg_off)
+        if self.__dict__.get("_prof") is not None:                      # every block of a profiled batch (bench.py sums them)
+            self.__dict__.setdefault("_scan_log", []).append((probes, seg_off))
         with self._stage("scan"):
             if _fp.SCAN_IMPL == "fast":
                 ws = D.scan_workspace(min(Q * max_q_chunks, max(1 << 20, Q * max_q_chunks // 4)))

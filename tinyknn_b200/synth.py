@@ -22,16 +22,44 @@ def clustered(n, d, n_components, seed, normalize=False, sigma=1.0, device=None,
     device = device or D.device()
     g = t.Generator(device=device).manual_seed(seed)
     means = t.randn(n_components, d, generator=g, device=device) * 2
-    comp = t.randint(n_components, (n,), generator=g, device=device)
-    X = means[comp]
-    X += t.randn(n, d, generator=g, device=device) * sigma
-    if normalize:
-        X /= X.norm(dim=1, keepdim=True)
+    X = t.empty(n, d, device=device, dtype=t.float32)
+    step = 1 << 22                                                 # blocks: 100M x 128 must not need a second 51 GB array
+    for lo in range(0, n, step):
+        m = min(step, n - lo)
+        comp = t.randint(n_components, (m,), generator=g, device=device)
+        blk = t.randn(m, d, generator=g, device=device)
+        if sigma != 1.0:
+            blk *= sigma
+        blk += means[comp]
+        if normalize:
+            blk /= blk.norm(dim=1, keepdim=True)
+        X[lo:lo + m] = blk
     return X
 
 
-def _nearest(X, C, chunk=1 << 18):
+class DeviceRows:
+    """Row access to a device matrix with numpy semantics, for indexes whose raw vectors are too large to mirror on the
+    host (100M x 128 f32 = 51 GB): `rows[ids]` fetches just those rows. Enough for the oracle's rescoring."""
+
+    def __init__(self, X):
+        self.X = X
+        self.shape = tuple(X.shape)
+        self.dtype = np.dtype(np.float32)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, idx):
+        t = D.torch()
+        idx = t.as_tensor(np.asarray(idx, dtype=np.int64), device=self.X.device)
+        idx = t.where(idx < 0, idx + self.shape[0], idx)
+        return self.X[idx].cpu().numpy()
+
+
+def _nearest(X, C, chunk=None):
     t = D.torch()
+    if chunk is None:                                              # the (chunk x centres) distance block stays around 1 GB
+        chunk = max(1024, min(1 << 18, (1 << 28) // max(1, C.shape[0])))
     out = t.empty(X.shape[0], dtype=t.int64, device=X.device)
     cn = (C * C).sum(1)
     for lo in range(0, X.shape[0], chunk):
@@ -124,7 +152,7 @@ def pack_codes(codes):
     return byte.permute(0, 2, 1).contiguous().reshape(n // 16, M * 8).view(t.int64)
 
 
-def build_ivf(X, metric, n_clusters, pq=None, kmeans_iters=6, fit_sample=200_000, seed=0, keep_device=True):
+def build_ivf(X, metric, n_clusters, pq=None, kmeans_iters=6, fit_sample=200_000, seed=0, keep_device=True, host_data=True):
     """IVF index over device data X (f32, (n, d)); one list per point (build_probes = 1).
     Returns an `IVF` whose host attributes mirror the reference's and whose device copy is in place."""
     t = D.require_cuda()
@@ -175,7 +203,7 @@ def build_ivf(X, metric, n_clusters, pq=None, kmeans_iters=6, fit_sample=200_000
     ivf.pq_transformed_points = [TransformedData(int(sizes_h[l]), packed_h[off_h[l]:off_h[l] + (int(sizes_h[l]) + 15) // 16])
                                  for l in range(C)] + [None] * (n_clusters - C)
     ivf.ids = [order_h[start_h[l]:start_h[l + 1]] for l in range(C)] + [None] * (n_clusters - C)
-    ivf.data = X.cpu().numpy()
+    ivf.data = X.cpu().numpy() if host_data else DeviceRows(X)       # host_data=False: rows are fetched on demand
     if keep_device:
         from ._lib import DTYPE_F32
         M = packed.shape[1]
