@@ -21,9 +21,10 @@ struct PlanArgs {
     const int32_t *list_size;     // [n_lists]
     const int32_t *list_owner;    // [n_lists] or null: every list is local
     int Q, P, n_lists, mode, rank, n_ranks, q_per_rank;
+    const int64_t *home_base;     // TKB_PLAN_PUSH: [n_ranks] address of each home rank's receive buffer, as mapped here
 };
 
-__device__ __forceinline__ int64_t plan_seg(const PlanArgs &a, int q, int s, int &group)
+__device__ __forceinline__ int64_t plan_seg(const PlanArgs &a, int q, int s, int &group, bool *mine = nullptr)
 {
     // returns the segment's bytes (0 when absent from this rank's buffer) and its group
     group = 0;
@@ -31,7 +32,12 @@ __device__ __forceinline__ int64_t plan_seg(const PlanArgs &a, int q, int s, int
     if (l == PROBE_SKIP) return 0;
     if (l < 0) l += a.n_lists;
     const int owner = a.list_owner ? a.list_owner[l] : 0;
-    if (a.mode == TKB_PLAN_SEND) {
+    if (a.mode == TKB_PLAN_PUSH) {
+        // the home rank's buffer holds EVERY segment of its queries in (query, slot) order, whoever scans it;
+        // this rank writes only the segments of the lists it owns
+        group = a.n_ranks > 1 ? q / a.q_per_rank : 0;
+        if (mine) *mine = !a.list_owner || owner == a.rank;
+    } else if (a.mode == TKB_PLAN_SEND) {
         if (a.list_owner && owner != a.rank) return 0;
         group = a.n_ranks > 1 ? q / a.q_per_rank : 0;
     } else {
@@ -117,33 +123,37 @@ __global__ void plan_write_kernel(PlanArgs a, const int64_t *__restrict__ qbase,
     plan_range(a, q_lo, q_n);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q_n) return;
+    const bool push = a.mode == TKB_PLAN_PUSH;
     int64_t run[PLAN_MAX_RANKS];
 #pragma unroll
-    for (int g = 0; g < PLAN_MAX_RANKS; g++)
-        run[g] = g < a.n_ranks ? group_bytes[a.n_ranks + 1 + g] + qbase[(size_t)i * a.n_ranks + g] : 0;
+    for (int g = 0; g < PLAN_MAX_RANKS; g++)                      // push: absolute addresses inside the home rank's buffer
+        run[g] = g < a.n_ranks ? (push ? a.home_base[g] : group_bytes[a.n_ranks + 1 + g]) + qbase[(size_t)i * a.n_ranks + g] : 0;
     for (int s = 0; s < a.P; s++) {
         int g;
-        const int64_t b = plan_seg(a, q_lo + i, s, g);
+        bool mine = true;
+        const int64_t b = plan_seg(a, q_lo + i, s, g, &mine);
         int64_t off = -1;
         if (b > 0) {
 #pragma unroll
             for (int k = 0; k < PLAN_MAX_RANKS; k++) if (k == g) { off = run[k]; run[k] += b; }
+            if (!mine) off = -1;
         }
         seg_off[(size_t)i * a.P + s] = off;
     }
 }
 
 int launch_ivf_plan(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner, int n_lists,
-                    int mode, int rank, int n_ranks, int q_per_rank, int64_t *seg_off, int64_t *group_bytes,
-                    void *workspace, int64_t workspace_bytes, cudaStream_t st)
+                    int mode, int rank, int n_ranks, int q_per_rank, const int64_t *home_base, int64_t *seg_off,
+                    int64_t *group_bytes, void *workspace, int64_t workspace_bytes, cudaStream_t st)
 {
     TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists > 0, "bad extent");
-    TKB_REQUIRE(mode == TKB_PLAN_SEND || mode == TKB_PLAN_RECV, "mode must be TKB_PLAN_SEND or TKB_PLAN_RECV");
+    TKB_REQUIRE(mode == TKB_PLAN_SEND || mode == TKB_PLAN_RECV || mode == TKB_PLAN_PUSH, "mode must be TKB_PLAN_SEND, _RECV or _PUSH");
+    TKB_REQUIRE(mode != TKB_PLAN_PUSH || home_base, "TKB_PLAN_PUSH needs the receive-buffer addresses (home_base)");
     TKB_REQUIRE(n_ranks >= 1 && n_ranks <= PLAN_MAX_RANKS && rank >= 0 && rank < n_ranks, "bad rank / n_ranks");
     TKB_REQUIRE(n_ranks == 1 || (q_per_rank > 0 && (int64_t)q_per_rank * n_ranks >= Q), "q_per_rank * n_ranks must cover Q");
     TKB_REQUIRE(n_ranks == 1 || list_owner, "list_owner is required when lists are sharded");
     TKB_REQUIRE(group_bytes, "null pointer");
-    PlanArgs a{probes, list_size, list_owner, Q, P, n_lists, mode, rank, n_ranks, q_per_rank};
+    PlanArgs a{probes, list_size, list_owner, Q, P, n_lists, mode, rank, n_ranks, q_per_rank, home_base};
     int q_n = Q;
     if (mode == TKB_PLAN_RECV && n_ranks > 1) { q_n = Q - rank * q_per_rank; if (q_n > q_per_rank) q_n = q_per_rank; if (q_n < 0) q_n = 0; }
     if (q_n == 0 || P == 0) {
