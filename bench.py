@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
     ap.add_argument("--cpu-worker", nargs=4, metavar=("DIR", "OUT", "SPEC", "SLICE"), default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
+                    help="--shard lists: 'push' = the scan kernel stores estimates into the home rank's HBM over NVLink peer "
+                         "memory (falls back to nccl when peer buffers cannot be mapped), 'nccl' = send buffer + all-to-all")
     ap.add_argument("--shard", default="lists", choices=["lists", "replicas"],
                     help="N>1: 'lists' = inverted lists sharded over the ranks, estimates exchanged with one NCCL "
                          "all-to-all (north star); 'replicas' = every rank holds the whole index and its own queries")
@@ -251,7 +254,7 @@ def main():
         roll = rank * 4 * Qn // world
         dev_batches = [torch.roll(b, roll, 0) for b in dev_batches]
         pinned = [torch.roll(b, roll, 0).pin_memory() for b in pinned]
-        run = lambda q, **o: engine.query_batch(q, **kw, **o)
+        run = lambda q, **o: engine.query_batch(q, exchange=args.exchange, **kw, **o)
     else:
         run = lambda q, **o: ivf.query_batch(q, order="device", **kw, **o)
 
@@ -408,7 +411,7 @@ def main():
             cb = run_cpu_arm(ivf, batches[0], args.n_probes, args.k, args.cpu_seconds, os.cpu_count() or 1)[0]
         line = dict(metric="IVF-PQ queries/s", value=value, unit="queries/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
-                    vs_baseline=None, dtype="i8", data="synthetic", config=dict(cfg, parallelism=("lists sharded over %d ranks, all-to-all of estimates" % world) if sharded
+                    vs_baseline=None, dtype="i8", data="synthetic", config=dict(cfg, parallelism=("lists sharded over %d ranks, %s" % (world, "estimates stored into the home rank's HBM by the scan kernel (NVLink peer memory)" if engine.last_exchange == "push" else "NCCL all-to-all of estimates")) if sharded
                                              else ("query-sharded replicas x%d" % world),
                     l2="estimate buffer rewritten every step and query batches rotate between steps; the codes of this "
                                    "workload (31 MB) are L2-resident by nature, see DESIGN.md"),

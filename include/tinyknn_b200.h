@@ -135,9 +135,33 @@ TKB_API int tkb_ivf_scan_dev(const uint64_t *codes, const int64_t *list_chunk_of
  *   workspace: 8 * queries * n_ranks bytes */
 #define TKB_PLAN_SEND 0
 #define TKB_PLAN_RECV 1
+#define TKB_PLAN_PUSH 2   /* tkb_ivf_plan_push_dev only */
 TKB_API int tkb_ivf_plan_dev(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner,
                      int n_lists, int mode, int rank, int n_ranks, int q_per_rank,
                      int64_t *seg_off, int64_t *group_bytes, void *workspace, int64_t workspace_bytes, void *stream);
+
+/* Push plan (fused scan + exchange over NVLink peer memory, DESIGN.md "multi-GPU"): the home rank of a query keeps the
+ * estimates of ALL its segments packed in (query, probe slot) order -- exactly the single-GPU layout
+ * (tkb_ivf_plan_dev, n_ranks == 1, over its own block of queries) -- and every scanning rank writes the segments of the
+ * lists it owns straight into that buffer through a peer mapping. For all Q queries:
+ *   seg_addr int64[Q][P] = home_base[q / q_per_rank] + offset of (q, s) inside the home buffer when this rank owns the
+ *                          list, else -1. home_base int64[n_ranks] (device): the address of every rank's receive buffer
+ *                          as mapped in THIS process (tkb_peer_open; the local pointer for rank == own).
+ *   group_bytes[g] = bytes of home rank g's buffer (all segments), [n_ranks] = their sum.
+ * Pass seg_addr as `seg_off` with est == NULL to tkb_ivf_scan_native_dev: the offsets are then absolute addresses. */
+TKB_API int tkb_ivf_plan_push_dev(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner,
+                          int n_lists, int rank, int n_ranks, int q_per_rank, const int64_t *home_base,
+                          int64_t *seg_addr, int64_t *group_bytes, void *workspace, int64_t workspace_bytes, void *stream);
+
+/* Peer-visible device buffers for the push exchange: one process per GPU, so the buffers are shared as CUDA IPC handles
+ * (64 bytes) that the caller moves between the processes of a box itself (torch.distributed all_gather in the host layer).
+ * tkb_peer_alloc: cudaMalloc on the current device + its handle. tkb_peer_open: map another process's buffer into this one
+ * (peer access over NVLink is enabled lazily); not valid in the allocating process. close / free undo them. */
+#define TKB_PEER_HANDLE_BYTES 64
+TKB_API int tkb_peer_alloc(int64_t bytes, void **dev_ptr, unsigned char *handle);
+TKB_API int tkb_peer_open(const unsigned char *handle, void **dev_ptr);
+TKB_API int tkb_peer_close(void *dev_ptr);
+TKB_API int tkb_peer_free(void *dev_ptr);
 
 /* Device-native code layout for the fast scan (chosen at upload, round-trips to the reference layout).
  * tile = 8 chunks; the 16 bytes of (tile t, pair p, chunk slot s) sit at ((t*M/2 + p)*8 + s)*16 and hold
@@ -152,7 +176,9 @@ TKB_API int tkb_codes_from_native_dev(const void *native, int64_t n_chunks, int 
  * certificate decides which chunks the exact patch pass recomputes.
  * workspace: 16-byte aligned device scratch, 16 + 8 bytes per chunk that may fail the certificate; chunks that
  * do not fit are recomputed inside the scan kernel (slower, still exact), so any size >= 24 is valid.
- * max_chunks_per_query (ivf): upper bound used to size the grid (0: P * slot_stride / 16). */
+ * max_chunks_per_query (ivf): upper bound used to size the grid (0: P * slot_stride / 16).
+ * tkb_ivf_scan_native_dev with est == NULL and seg_off != NULL: seg_off holds absolute device addresses (possibly
+ * peer-mapped memory of another GPU), negative = skip (tkb_ivf_plan_push_dev). */
 TKB_API int tkb_estimate_native_dev(const void *native, int64_t n_chunks, int M, const uint8_t *tables, int Q,
                             uint8_t *est, int64_t est_stride, int order, int signd,
                             void *workspace, int64_t workspace_bytes, void *stream);

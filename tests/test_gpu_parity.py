@@ -669,3 +669,66 @@ def test_sharded_phases_equal_single_gpu(golden, G):
         assert np.array_equal(ivf._last["heap_idx"].cpu().numpy(), ref_heap[sl])
         assert np.array_equal(ids.cpu().numpy(), ref_ids[sl]) and np.array_equal(cnt.cpu().numpy(), ref_cnt[sl])
         assert np.array_equal(dst.cpu().numpy(), ref_d[sl])
+
+
+@pytest.mark.parametrize("G", [1, 2, 4])
+def test_push_plan_device_matches_host_restatement(G):
+    """tkb_ivf_plan_push_dev: absolute addresses = home_base[home rank] + the host restatement's offsets."""
+    from tinyknn_b200._lib import lib, check, PROBE_SKIP, PLAN_PUSH
+    from tinyknn_b200 import sharded as SH
+    rng = np.random.default_rng(50 + G)
+    n_lists, Qh, P = 53, 29, 6
+    sizes = rng.integers(0, 900, size=n_lists).astype(np.int32)
+    owner = SH.assign_owners(sizes, G)
+    Q = G * Qh
+    probes = np.stack([rng.permutation(n_lists)[:P] for _ in range(Q)]).astype(np.int32)
+    probes[5 % Q, 1] = PROBE_SKIP
+    probes[7 % Q, 0] = -1
+    base = (rng.integers(1, 1 << 30, size=G).astype(np.int64) << 8)
+    d_probes, d_sizes, d_owner, d_base = D.upload(probes), D.upload(sizes), D.upload(owner), D.upload(base)
+    for r in range(G):
+        seg, gb, _ = SH.plan_host(probes, sizes, owner if G > 1 else None, PLAN_PUSH, r, G, Qh)
+        exp = np.where(seg >= 0, seg + base[np.arange(Q) // Qh][:, None], -1)
+        d_seg, d_gb, d_ws = D.empty((Q, P), np.int64), D.empty((2 * G + 1,), np.int64), D.empty((Q * G,), np.int64)
+        check(lib.tkb_ivf_plan_push_dev(D.ptr(d_probes), Q, P, D.ptr(d_sizes), D.ptr(d_owner) if G > 1 else None, n_lists,
+                                        r, G, Qh, D.ptr(d_base), D.ptr(d_seg), D.ptr(d_gb), D.ptr(d_ws), 8 * Q * G, D.stream_ptr()))
+        assert np.array_equal(d_seg.cpu().numpy(), exp), (G, r)
+        assert np.array_equal(d_gb.cpu().numpy()[:G], gb)
+
+
+@pytest.mark.parametrize("G", [2, 3])
+def test_sharded_push_phases_equal_single_gpu(golden, G):
+    """The push exchange driven rank by rank on ONE GPU: every "rank" stores its estimates straight into the home
+    ranks' receive buffers (tkb_peer_alloc memory, local addresses); heaps, ids, distances == the unsharded path."""
+    from tinyknn_b200.sharded import ShardedIVF, PeerBuffers
+    import torch
+    z = golden["ivf"]
+    S = O.ivf_state_from_arrays(z, "euc128_")
+    ivf = _ivf_from_state(S)
+    qs = np.ascontiguousarray(z["euc128_q"][:48 // G * G])
+    Qh = len(qs) // G
+    k, n_probes = 10, 8
+    ref_ids, ref_cnt, ref_d = ivf.query_batch(qs, k, n_probes=n_probes, order="device", return_distances=True)
+    ref_heap = ivf._last["heap_idx"].cpu().numpy()
+    shards = [ShardedIVF(ivf, rank=r, world=G, drop_full_codes=False) for r in range(G)]
+    homes = [sh._home(qs[r * Qh:(r + 1) * Qh], n_probes) for r, sh in enumerate(shards)]
+    P = homes[0]["P"]
+    tables = torch.cat([h["lut"]["tables"] for h in homes])
+    probes = torch.cat([h["probes"] for h in homes])
+    cap = shards[0].push_capacity(Qh, P)
+    bufs = [PeerBuffers(cap, rank=0, world=1, n_buf=1) for _ in range(G)]       # one receive buffer per "rank", all local
+    try:
+        home_base = D.upload(np.array([b.local[0].address for b in bufs], dtype=np.int64))
+        totals = [sh._scan_push(tables, probes, Qh, P, home_base).cpu().numpy() for sh in shards]
+        for b, sh in enumerate(shards):
+            seg_r, gb = ivf._plan(sh.dev, homes[b]["probes"], Qh, P)
+            need = int(gb.cpu().numpy()[1])
+            assert need <= cap and all(int(t[b]) == need for t in totals)
+            ids, cnt, dst = sh._finish(homes[b], bufs[b].local[0], seg_r, k, (n_probes + 1) * k + 1)
+            sl = slice(b * Qh, (b + 1) * Qh)
+            assert np.array_equal(ivf._last["heap_idx"].cpu().numpy(), ref_heap[sl])
+            assert np.array_equal(ids.cpu().numpy(), ref_ids[sl]) and np.array_equal(cnt.cpu().numpy(), ref_cnt[sl])
+            assert np.array_equal(dst.cpu().numpy(), ref_d[sl])
+    finally:
+        for b in bufs:
+            b.close()

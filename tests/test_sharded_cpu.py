@@ -155,3 +155,30 @@ def test_plan_host_layout_properties():
                     if l == PROBE_SKIP or owner[l] != a or sizes[l] == 0:
                         continue
                     assert send[a][0][q, s] - send[a][2][b] == recv[b][0][i, s] - recv[b][2][a]
+
+
+def test_plan_host_push_layout_is_the_home_ranks_single_gpu_layout():
+    """TKB_PLAN_PUSH: what rank a writes for home b's queries lands exactly where b's own single-GPU plan of its block
+    expects it; every segment is written by exactly one rank; the per-home buffer sizes agree."""
+    from tinyknn_b200.sharded import plan_host, assign_owners
+    from tinyknn_b200._lib import PLAN_SEND, PLAN_PUSH, PROBE_SKIP
+    rng = np.random.default_rng(2)
+    n_lists, G, Qh, P = 41, 3, 11, 5
+    sizes = rng.integers(0, 300, size=n_lists).astype(np.int32)
+    sizes[4] = 0
+    owner = assign_owners(sizes, G)
+    probes = np.stack([rng.permutation(n_lists)[:P] for _ in range(G * Qh)]).astype(np.int32)
+    probes[3, 2] = PROBE_SKIP
+    probes[17, 0] = -2
+    push = [plan_host(probes, sizes, owner, PLAN_PUSH, r, G, Qh) for r in range(G)]
+    for b in range(G):
+        blk = probes[b * Qh:(b + 1) * Qh]
+        home, hb, _ = plan_host(blk, sizes, None, PLAN_SEND, 0, 1, 0)
+        writers = np.zeros(home.shape, dtype=np.int64)
+        for a in range(G):
+            assert push[a][1][b] == hb.sum()
+            seg = push[a][0][b * Qh:(b + 1) * Qh]
+            hit = seg >= 0
+            assert np.array_equal(seg[hit], home[hit])
+            writers += hit
+        assert np.array_equal(writers, (home >= 0).astype(np.int64))

@@ -27,8 +27,13 @@ def _worker(rank, world, port, out):
         Qh = 1024 // world
         mine = qs[rank * Qh:(rank + 1) * Qh].contiguous()
         ref = ivf.query_batch(mine, 10, n_probes=6, order="device", return_distances=True)
-        got = ShardedIVF(ivf).query_batch(mine, 10, n_probes=6, return_distances=True)
-        bad = sum(not np.array_equal(a, b) for a, b in zip(ref, got))
+        sh = ShardedIVF(ivf)
+        bad, used = 0, []
+        for exchange in ("nccl", "push", "push", "push"):            # repeated pushes alternate the receive buffers
+            got = sh.query_batch(mine, 10, n_probes=6, return_distances=True, exchange=exchange)
+            bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
+            used.append(sh.last_exchange)
+        bad += used != ["nccl", "push", "push", "push"]               # peer memory must really have been used
         np.save(out, np.array([bad]))
     finally:
         dist.destroy_process_group()

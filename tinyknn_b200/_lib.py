@@ -32,6 +32,11 @@ SIGNATURES = {
     "tkb_launch_count": [],
     "tkb_ivf_scan_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _i64, _vp, _i64, _i, _i, _vp],
     "tkb_ivf_plan_dev": [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _vp],
+    "tkb_ivf_plan_push_dev": [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp],
+    "tkb_peer_alloc": [_i64, _c.POINTER(_vp), _vp],
+    "tkb_peer_open": [_vp, _c.POINTER(_vp)],
+    "tkb_peer_close": [_vp],
+    "tkb_peer_free": [_vp],
     "tkb_codes_to_native_dev": [_vp, _i64, _i, _vp, _vp],
     "tkb_codes_from_native_dev": [_vp, _i64, _i, _vp, _vp],
     "tkb_estimate_native_dev": [_vp, _i64, _i, _vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp],
@@ -82,7 +87,7 @@ def last_error():
 
 
 n_calls = 0          # C-ABI calls that returned OK
-PLAN_SEND, PLAN_RECV = 0, 1
+PLAN_SEND, PLAN_RECV, PLAN_PUSH = 0, 1, 2
 
 
 def launch_count():

@@ -1,5 +1,6 @@
 // tkb_api.cu -- extern "C" boundary of libtinyknn_b200.so (see include/tinyknn_b200.h).
 #include <stdarg.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -192,8 +193,66 @@ int tkb_ivf_plan_dev(const int32_t *probes, int Q, int P, const int32_t *list_si
                      int n_lists, int mode, int rank, int n_ranks, int q_per_rank,
                      int64_t *seg_off, int64_t *group_bytes, void *workspace, int64_t workspace_bytes, void *stream)
 {
-    return launch_ivf_plan(probes, Q, P, list_size, list_owner, n_lists, mode, rank, n_ranks, q_per_rank, seg_off,
+    TKB_REQUIRE(mode != TKB_PLAN_PUSH, "use tkb_ivf_plan_push_dev for TKB_PLAN_PUSH");
+    return launch_ivf_plan(probes, Q, P, list_size, list_owner, n_lists, mode, rank, n_ranks, q_per_rank, nullptr, seg_off,
                            group_bytes, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int tkb_ivf_plan_push_dev(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner,
+                          int n_lists, int rank, int n_ranks, int q_per_rank, const int64_t *home_base,
+                          int64_t *seg_addr, int64_t *group_bytes, void *workspace, int64_t workspace_bytes, void *stream)
+{
+    return launch_ivf_plan(probes, Q, P, list_size, list_owner, n_lists, TKB_PLAN_PUSH, rank, n_ranks, q_per_rank, home_base,
+                           seg_addr, group_bytes, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// peer memory (one process per GPU; CUDA IPC handles travel through the caller's own channel)
+// ---------------------------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == TKB_PEER_HANDLE_BYTES, "handle size");
+
+int tkb_peer_alloc(int64_t bytes, void **dev_ptr, unsigned char *handle)
+{
+    TKB_REQUIRE(bytes > 0 && dev_ptr && handle, "bad argument");
+    if (int rc = require_device()) return rc;
+    void *p = nullptr;
+    TKB_CUDA(cudaMalloc(&p, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        cudaGetLastError();
+        return set_err(TKB_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, sizeof(h));
+    *dev_ptr = p;
+    return TKB_OK;
+}
+
+int tkb_peer_open(const unsigned char *handle, void **dev_ptr)
+{
+    TKB_REQUIRE(handle && dev_ptr, "null pointer");
+    if (int rc = require_device()) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    TKB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr = p;
+    return TKB_OK;
+}
+
+int tkb_peer_close(void *dev_ptr)
+{
+    if (!dev_ptr) return TKB_OK;
+    TKB_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return TKB_OK;
+}
+
+int tkb_peer_free(void *dev_ptr)
+{
+    if (!dev_ptr) return TKB_OK;
+    TKB_CUDA(cudaFree(dev_ptr));
+    return TKB_OK;
 }
 
 int tkb_codes_to_native_dev(const uint64_t *codes, int64_t n_chunks, int M, void *native, void *stream)

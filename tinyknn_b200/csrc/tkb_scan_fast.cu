@@ -348,7 +348,9 @@ int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, co
     if (int rc = check_fast_args(M, order)) return rc;
     TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists > 0, "bad extent");
     if (Q == 0 || P == 0 || (slot_stride == 0 && !seg_off)) return TKB_OK;
-    TKB_REQUIRE(native && list_chunk_off && tables && probes && est, "null pointer");
+    // est == NULL with a plan: the plan holds absolute addresses (TKB_PLAN_PUSH: segments land in the receive buffers of
+    // the queries' home ranks, peer-mapped over NVLink)
+    TKB_REQUIRE(native && list_chunk_off && tables && probes && (est || seg_off), "null pointer");
     TKB_REQUIRE(slot_stride % 16 == 0, "slot_stride must be a multiple of 16");
     TKB_REQUIRE(P <= 4096, "too many probes");
     TKB_REQUIRE((int64_t)Q * P <= 0xffffffffLL, "too many (query, probe) units for one launch");

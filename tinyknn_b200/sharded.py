@@ -13,19 +13,32 @@ code bytes read) to the query's home rank, which replays the reference heap in p
   all ranks                     all_to_all_single(estimates), uneven splits          [NCCL, 1 B / scanned vector]
   home rank                     ordered heap replay -> exact rescoring -> k nearest
 
+exchange="push" (the default when peer memory is available) fuses the scan with the exchange: the home rank's receive
+buffer holds the segments of its queries in the single-GPU (query, probe slot) layout, every rank maps every receive
+buffer (CUDA IPC, NVLink peer access) and the scan kernel of the owning rank stores each estimate chunk straight into
+the home rank's HBM (tkb_ivf_plan_push_dev gives it absolute addresses). No send buffer, no all-to-all, no host sync
+for split sizes: the only collective after the all-gather is a one-element all-reduce that orders "every scan has
+finished" before the replays. exchange="nccl" keeps the all-to-all path.
+
 Both sides of a (scanning rank, home rank) pair order the segments by (query, probe slot), so offsets are
 computed locally from replicated metadata (tkb_ivf_plan_dev) and never travel. Replicated per rank:
 centroids + centroid codes, list sizes/owners, `ids`, the raw vectors for rescoring; sharded: the PQ codes.
 """
+import os
+
 import numpy as np
 
 from . import _device as D
-from ._lib import PLAN_SEND, PLAN_RECV, PROBE_SKIP
+from ._lib import PLAN_SEND, PLAN_RECV, PLAN_PUSH, PROBE_SKIP
 
 
 # ---------------------------------------------------------------------------------------------------------
 # host-side logic (pure numpy / torch.distributed; exercised on CPU with gloo in tests/test_sharded_cpu.py)
 # ---------------------------------------------------------------------------------------------------------
+
+# default exchange of ShardedIVF.query_batch: "push" (NVLink peer stores from the scan kernel) or "nccl" (all-to-all)
+EXCHANGE = os.environ.get("TKB_EXCHANGE", "push")
+
 
 def assign_owners(list_sizes, n_ranks):
     """Size-balanced list -> rank map: largest list first onto the least loaded rank (ties: lowest rank).
@@ -41,7 +54,7 @@ def assign_owners(list_sizes, n_ranks):
 
 
 def plan_host(probes, list_size, list_owner, mode, rank, n_ranks, q_per_rank):
-    """numpy restatement of tkb_ivf_plan_dev (csrc/tkb_plan.cu): (seg_off, group_bytes, group_base)."""
+    """numpy restatement of tkb_ivf_plan_dev / tkb_ivf_plan_push_dev (csrc/tkb_plan.cu): (seg_off, group_bytes, group_base)."""
     probes = np.asarray(probes)
     Q, P = probes.shape
     n_lists = len(list_size)
@@ -52,6 +65,7 @@ def plan_host(probes, list_size, list_owner, mode, rank, n_ranks, q_per_rank):
     seg_off = np.full((q_n, P), -1, dtype=np.int64)
     nbytes = np.zeros((q_n, P), dtype=np.int64)
     group = np.zeros((q_n, P), dtype=np.int64)
+    mine = np.ones((q_n, P), dtype=bool)
     for i in range(q_n):
         q = q_lo + i
         for s in range(P):
@@ -61,7 +75,10 @@ def plan_host(probes, list_size, list_owner, mode, rank, n_ranks, q_per_rank):
             if l < 0:
                 l += n_lists
             owner = 0 if list_owner is None else int(list_owner[l])
-            if mode == PLAN_SEND:
+            if mode == PLAN_PUSH:
+                group[i, s] = q // q_per_rank if n_ranks > 1 else 0
+                mine[i, s] = list_owner is None or owner == rank
+            elif mode == PLAN_SEND:
                 if list_owner is not None and owner != rank:
                     continue
                 group[i, s] = q // q_per_rank if n_ranks > 1 else 0
@@ -70,12 +87,14 @@ def plan_host(probes, list_size, list_owner, mode, rank, n_ranks, q_per_rank):
             nbytes[i, s] = 16 * ((int(list_size[l]) + 15) // 16)
     group_bytes = np.array([nbytes[group == g].sum() for g in range(n_ranks)], dtype=np.int64)
     group_base = np.concatenate([[0], np.cumsum(group_bytes)[:-1]]).astype(np.int64)
-    run = group_base.copy()
+    # PLAN_PUSH: offsets are relative to the start of the home rank's own buffer (the device plan adds its address)
+    run = np.zeros(n_ranks, dtype=np.int64) if mode == PLAN_PUSH else group_base.copy()
     for i in range(q_n):
         for s in range(P):
             if nbytes[i, s] > 0:
                 g = group[i, s]
-                seg_off[i, s] = run[g]
+                if mine[i, s]:
+                    seg_off[i, s] = run[g]
                 run[g] += nbytes[i, s]
     return seg_off, group_bytes, group_base
 
@@ -119,6 +138,71 @@ def all_gather_rows(x, group=None):
     out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     dist.all_gather_into_tensor(out, x.contiguous(), group=group)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# peer-mapped receive buffers of the push exchange
+# ---------------------------------------------------------------------------------------------------------
+
+class _Raw:
+    """A device buffer that torch does not own (cudaMalloc'ed by tkb_peer_alloc)."""
+
+    def __init__(self, address, nbytes):
+        self.address, self.nbytes = int(address), int(nbytes)
+
+    def data_ptr(self):
+        return self.address
+
+    def numel(self):
+        return self.nbytes
+
+
+class PeerBuffers:
+    """`n_buf` receive buffers of `nbytes` on every rank, each mapped into every other rank's process.
+
+    Collective over `group`: the 64-byte CUDA IPC handles (tkb_peer_alloc) travel in one all-gather and are opened with
+    tkb_peer_open. `bases[b]` is a device int64[world]: the address of rank g's buffer b as seen from this process.
+    Consecutive batches alternate between the buffers, so a fast rank can push batch i+1 while a slow home rank is
+    still replaying batch i (batch i+2 cannot start before the home rank has passed the barrier of batch i+1)."""
+
+    def __init__(self, nbytes, group=None, rank=0, world=1, n_buf=2):
+        import ctypes
+        from ._lib import lib, check
+        t = D.require_cuda()
+        self.nbytes, self.rank, self.world, self.n_buf = int(nbytes), rank, world, n_buf
+        self.local, self._opened = [], []
+        handles = np.zeros((n_buf, 64), dtype=np.uint8)
+        for b in range(n_buf):
+            p = ctypes.c_void_p()
+            h = (ctypes.c_ubyte * 64)()
+            check(lib.tkb_peer_alloc(self.nbytes, ctypes.byref(p), h))
+            self.local.append(_Raw(p.value, self.nbytes))
+            handles[b] = np.frombuffer(h, dtype=np.uint8)
+        addr = np.zeros((n_buf, world), dtype=np.int64)
+        addr[:, rank] = [x.address for x in self.local]
+        if world > 1:
+            every = all_gather_rows(D.upload(handles)[None], group).cpu().numpy()          # (world, n_buf, 64)
+            for g in range(world):
+                if g == rank:
+                    continue
+                for b in range(n_buf):
+                    p = ctypes.c_void_p()
+                    hb = (ctypes.c_ubyte * 64).from_buffer_copy(every[g, b].tobytes())
+                    check(lib.tkb_peer_open(hb, ctypes.byref(p)))
+                    self._opened.append(p.value)
+                    addr[b, g] = p.value
+        self.bases = [D.upload(addr[b]) for b in range(n_buf)]
+        self.flag = t.zeros(1, dtype=t.int32, device=D.device())
+        self.turn = 0
+
+    def close(self):
+        from ._lib import lib
+        D.torch().cuda.synchronize()
+        for p in self._opened:
+            lib.tkb_peer_close(p)
+        for x in self.local:
+            lib.tkb_peer_free(x.address)
+        self._opened, self.local = [], []
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -187,29 +271,89 @@ class ShardedIVF:
         ivf._scan(dev, tables, probes, Q, P, est_s, seg_s, codes_key="local_codes", off_key="local_chunk_off")
         return est_s, splits[0, :G], seg_r, splits[1, :G]
 
+    def _scan_push(self, tables, probes, Qh, P, home_base):
+        """Fused scan + exchange: scan, for ALL G*Qh queries, of the probed lists this rank owns, every estimate chunk
+        stored directly at its place in the home rank's receive buffer (`home_base`: device int64[G] of addresses
+        valid in this process). Returns the per-home buffer sizes (device int64[G])."""
+        ivf, dev, G, r = self.ivf, self.dev, self.world, self.rank
+        Q = G * Qh
+        seg = D.empty((Q, P), np.int64)
+        gb = D.empty((2 * G + 1,), np.int64)
+        ws = D.empty((max(Q, 1) * G,), np.int64)
+        from ._lib import lib, check
+        with ivf._stage("plan"):
+            check(lib.tkb_ivf_plan_push_dev(D.ptr(probes), Q, P, D.ptr(dev["list_size"]), D.ptr(dev["list_owner"]), dev["n_lists"],
+                                            r, G, Qh, D.ptr(home_base), D.ptr(seg), D.ptr(gb), D.ptr(ws), 8 * ws.numel(),
+                                            D.stream_ptr()))
+        ivf._scan(dev, tables, probes, Q, P, None, seg, codes_key="local_codes", off_key="local_chunk_off")
+        return gb[:G]
+
+    def push_capacity(self, Qh, P):
+        """Upper bound of a home rank's receive buffer, from replicated metadata only (every rank computes the same
+        number): Qh queries x the P largest lists, padded to chunks."""
+        sizes = np.sort(16 * ((np.asarray(self.dev["host_sizes"], dtype=np.int64) + 15) // 16))[::-1]
+        return int(max(Qh, 1) * max(int(sizes[:P].sum()), 16))
+
+    def _peers(self, Qh, P):
+        """The peer-mapped receive buffers for batches of this shape (collective when they have to be (re)allocated);
+        None when they would not fit comfortably (then the all-to-all path is used)."""
+        need = self.push_capacity(Qh, P)
+        pb = self.__dict__.get("_pb")
+        if pb is not None and pb.nbytes >= need:
+            return pb
+        t = D.torch()
+        free, _ = t.cuda.mem_get_info()
+        fits = t.tensor([int(2 * need <= free // 3)], dtype=t.int32, device=D.device())
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(fits, op=dist.ReduceOp.MIN, group=self.group)
+        if not int(fits.item()):
+            return None
+        if pb is not None:
+            pb.close()
+        self.__dict__["_pb"] = pb = PeerBuffers(need, self.group, self.rank, self.world)
+        return pb
+
     def _finish(self, home, est_r, seg_r, k, pass_1):
         """Ordered heap replay over the received estimates, exact rescoring, k nearest (device tensors)."""
         return self.ivf._replay_rescore(self.dev, home["lut"]["q"], home["probes"], home["Qh"], home["P"], k, pass_1,
                                         est_r, seg_r, "device")
 
-    def query_batch(self, queries, k, n_probes=1, pass_1=None, return_distances=False, to_host=True):
+    def query_batch(self, queries, k, n_probes=1, pass_1=None, return_distances=False, to_host=True, exchange=None):
         """Collective. queries: this rank's f32 (Qh, d) block (same Qh on every rank). Selections use the
-        device order (ascending distance, ties by heap slot). Returns the results of this rank's block."""
+        device order (ascending distance, ties by heap slot). Returns the results of this rank's block.
+        exchange: "push" (scan stores into the home rank's HBM over NVLink peer memory), "nccl" (send buffer +
+        all-to-all) or None = the module default EXCHANGE; every rank must pass the same value."""
         ivf, G = self.ivf, self.world
+        exchange = EXCHANGE if exchange is None else exchange
+        assert exchange in ("push", "nccl")
         if pass_1 is None:
             pass_1 = (n_probes + 1) * k + 1                                     # ref: ivf.py:135-136
         home = self._home(queries, n_probes)
         tables, probes = home["lut"]["tables"], home["probes"]
+        Qh, P = home["Qh"], home["P"]
+        pb = self._peers(Qh, P) if (exchange == "push" and G > 1) else None
+        self.last_exchange = "push" if pb is not None else ("nccl" if G > 1 else "local")
         if G > 1:
             with ivf._stage("all_gather"):
                 tables = all_gather_rows(tables, self.group)
                 probes = all_gather_rows(probes, self.group)
-        est_s, send_splits, seg_r, recv_splits = self._scan_owned(tables, probes, home["Qh"], home["P"])
-        if G > 1:
-            with ivf._stage("all_to_all"):
-                est_r = all_to_all_bytes(est_s, send_splits, recv_splits, self.group)
+        if pb is not None:
+            import torch.distributed as dist
+            b = pb.turn
+            pb.turn = (b + 1) % pb.n_buf
+            seg_r, _ = ivf._plan(self.dev, home["probes"], Qh, P)                # the single-GPU layout of my own queries
+            self._scan_push(tables, probes, Qh, P, pb.bases[b])
+            with ivf._stage("barrier"):                                         # every rank's scan kernel has completed
+                dist.all_reduce(pb.flag, group=self.group)
+            est_r = pb.local[b]
         else:
-            est_r = est_s
+            est_s, send_splits, seg_r, recv_splits = self._scan_owned(tables, probes, Qh, P)
+            if G > 1:
+                with ivf._stage("all_to_all"):
+                    est_r = all_to_all_bytes(est_s, send_splits, recv_splits, self.group)
+            else:
+                est_r = est_s
         ids, cnt, dst = self._finish(home, est_r, seg_r, k, pass_1)
         if to_host:
             ids, cnt, dst = ids.cpu().numpy(), cnt.cpu().numpy(), dst.cpu().numpy()
