@@ -163,6 +163,22 @@ TKB_API int tkb_peer_open(const unsigned char *handle, void **dev_ptr);
 TKB_API int tkb_peer_close(void *dev_ptr);
 TKB_API int tkb_peer_free(void *dev_ptr);
 
+/* Batched PQ encoder (build time): replaces FastPQ.transform (ref: tinyknn/fast_pq.py:147-184) with
+ * pad2 (ref: tinyknn/utils.py:14-19), the rotation `data @ R.T`, the per-block nearest-of-16 search of knn_brute
+ * (ref: tinyknn/utils.py:66-86) and the nibble packing of transform_data (ref: tinyknn/_transform.py:4-77).
+ * The arithmetic mirrors numpy operation by operation (csrc/tkb_encode.cu), so codes equal the reference's wherever
+ * the nearest codeword is unique.
+ *   rows      f32/f64 [n_rows][d]      vectors (already normalised for angular indexes, ref: tinyknn/ivf.py:80-82)
+ *   row_index int64[n_out] or NULL     output position i encodes rows[row_index[i]]; an index outside [0, n_rows) is
+ *                                      the zero vector (the reference's padding rows). NULL: position i = row i.
+ *   n_out     multiple of 16           positions to encode (chunks of 16, lists padded by the caller)
+ *   centers   f32[16][Dp], cnorm f32[Dp/dpb][16] = per block |c|^2 in f32 (np.einsum on the f32 codebook)
+ *   R         f64[Dp][Dpad] or NULL    Dpad = d rounded up to dpad * dpb (ref: fast_pq.py:161-169); Dp <= 128 when R
+ *   codes     uint64[n_out/16][Dp/dpb] out, reference layout (feed tkb_codes_to_native_dev for the scan layout) */
+TKB_API int tkb_encode_dev(const void *rows, int rows_dtype, int64_t n_rows, int d, const int64_t *row_index, int64_t n_out,
+                   const float *centers, const float *cnorm, int Dp, int dpb, const double *R, int Dpad,
+                   uint64_t *codes, void *stream);
+
 /* Device-native code layout for the fast scan (chosen at upload, round-trips to the reference layout).
  * tile = 8 chunks; the 16 bytes of (tile t, pair p, chunk slot s) sit at ((t*M/2 + p)*8 + s)*16 and hold
  * 8 halfwords: halfword g = codes of sub-quantizer 2p for vectors 4g..4g+3 (nibble i = vector 4g+i),

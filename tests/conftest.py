@@ -32,7 +32,7 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def golden():
-    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("scan", "lut", "ivf")}
+    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("scan", "lut", "ivf", "encode")}
 
 
 @pytest.fixture(scope="session", autouse=True)

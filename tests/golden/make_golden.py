@@ -116,10 +116,32 @@ def ivf_cases(t):
     return out
 
 
+def encode_cases(t):
+    """FastPQ.transform of the reference (fast_pq.py:147-184): inputs, fitted quantizer, packed codes."""
+    out, names = {}, []
+    np.random.seed(10)
+    for name, (n, d, dtype, kmeans) in {"rot128": (530, 128, np.float32, True), "plain100": (500, 100, np.float32, True),
+                                        "rot20": (333, 20, np.float32, True), "rot128_f64": (200, 128, np.float64, True),
+                                        "plain100_f64": (150, 100, np.float64, True), "rot200": (180, 200, np.float32, True)}.items():
+        means = np.random.randn(12, d) * 2
+        X = (means[np.random.randint(12, size=n)] + np.random.randn(n, d)).astype(dtype)
+        pq = t.FastPQ(2, use_kmeans=kmeans).fit(X)
+        td = pq.transform(X)
+        assert td.size == n
+        out[name + "_X"], out[name + "_centers"], out[name + "_packed"] = X, pq.centers, td.packed
+        out[name + "_R"] = np.zeros((0, 0)) if pq.R is None else pq.R
+        names.append(name)
+    out["names"] = np.array(names)
+    return out
+
+
 def main():
     assert build_ref.build(), "needs /root/reference"
     t = ref_loader.load_ref_package()
-    for fname, fn in (("scan.npz", scan_cases), ("lut.npz", lut_cases), ("ivf.npz", ivf_cases)):
+    only = sys.argv[1:]
+    for fname, fn in (("scan.npz", scan_cases), ("lut.npz", lut_cases), ("ivf.npz", ivf_cases), ("encode.npz", encode_cases)):
+        if only and fname not in only:
+            continue
         arrays = fn(t)
         np.savez_compressed(os.path.join(HERE, fname), **arrays)
         print(fname, os.path.getsize(os.path.join(HERE, fname)) // 1024, "KiB")

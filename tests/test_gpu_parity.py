@@ -732,3 +732,80 @@ def test_sharded_push_phases_equal_single_gpu(golden, G):
     finally:
         for b in bufs:
             b.close()
+
+
+# ---- PQ encoder (FastPQ.transform on the GPU) ------------------------------------------------------
+
+def _enc_pq(z, name):
+    pq = tinyknn.FastPQ(2)
+    R = z[name + "_R"]
+    pq.centers, pq.R = np.ascontiguousarray(z[name + "_centers"]), (None if R.size == 0 else np.ascontiguousarray(R))
+    pq.sqrt_n_blocks = np.sqrt(pq.centers.shape[1] // 2)
+    return pq
+
+
+def _assert_codes_equal_up_to_ties(pq, X, got_packed, exp_packed):
+    """Codes must equal the reference's; a difference is only tolerated where the two codewords are EXACTLY tied in the
+    reference's own `part` matrix (np.argpartition may return either)."""
+    if np.array_equal(got_packed, exp_packed):
+        return 0
+    got, exp = O.unpack(got_packed).astype(np.int64), O.unpack(exp_packed).astype(np.int64)
+    parts = O.pq_encode_parts(O.PQState(2, pq.centers, pq.R), X)
+    rows, cols = np.nonzero(got != exp)
+    for r, m in zip(rows, cols):
+        assert parts[m][r, got[r, m]] == parts[m][r, exp[r, m]], (r, m)
+    return len(rows)
+
+
+def test_encode_device_equals_reference_golden(golden):
+    """tkb_encode_dev on the reference's own inputs: packed codes identical to FastPQ.transform of the reference
+    (rotated f64 path, unrotated f32 path, f64 rows, padding of n to 16 and of d to dpad*dpb, 200-d rows)."""
+    z = golden["encode"]
+    for name in z["names"]:
+        pq, X = _enc_pq(z, name), z[name + "_X"]
+        td = pq.transform(X, device=True)
+        assert td.size == len(X) and td.packed.dtype == np.uint64 and td.packed.shape == z[name + "_packed"].shape
+        ties = _assert_codes_equal_up_to_ties(pq, X, td.packed, z[name + "_packed"])
+        assert ties <= 2, (name, ties)
+
+
+def test_encode_device_row_index_and_padding(golden):
+    """Gathered encoding (what IVF.build uses): position i = rows[row_index[i]], out-of-range = zero vector."""
+    z = golden["encode"]
+    rng = np.random.default_rng(3)
+    for name in ("rot128", "plain100"):
+        pq, X = _enc_pq(z, name), z[name + "_X"]
+        idx = rng.integers(-1, len(X), size=16 * 37).astype(np.int64)
+        idx[5] = len(X) + 3                                            # out of range -> zero vector
+        got = pq.encode_device(D.upload(X), row_index=D.upload(idx)).cpu().numpy().view(np.uint64)
+        rows = np.where(((idx >= 0) & (idx < len(X)))[:, None], X[np.clip(idx, 0, len(X) - 1)], 0).astype(X.dtype)
+        n, exp = O.pq_transform(O.PQState(2, pq.centers, pq.R), rows)
+        assert _assert_codes_equal_up_to_ties(pq, rows, got, exp) <= 2
+
+
+def test_encode_device_large_matches_oracle_and_scan_roundtrip():
+    """200k x 128 rows: equal to the numpy restatement; the codes feed the scan (native layout round trip)."""
+    rng = np.random.default_rng(11)
+    X = rng.standard_normal((200_000, 128)).astype(np.float32)
+    pq = tinyknn.FastPQ(2, use_kmeans=False).fit(X[:5000])
+    td = pq.transform(X, device=True)
+    n, exp = O.pq_transform(O.PQState.from_pq(pq), X)
+    assert n == td.size and _assert_codes_equal_up_to_ties(pq, X, td.packed, exp) <= 4
+    nat = D.to_native(D.upload(td.packed), td.packed.shape[0], td.packed.shape[1])
+    assert np.array_equal(D.from_native(nat, td.packed.shape[0], td.packed.shape[1]).cpu().numpy().view(np.uint64), td.packed)
+
+
+def test_ivf_build_device_encoding_equals_host_build():
+    """IVF.build with the one-launch GPU encoding == the list-by-list host encoding (same ids, same packed codes)."""
+    np.random.seed(4)
+    X = np.random.randn(3000, 32).astype(np.float32)
+    a = tinyknn.IVF("angular", 20, tinyknn.FastPQ(2)).fit(X)
+    import copy
+    b = copy.deepcopy(a)
+    a.build(X, n_probes=2, device=True)
+    b.build(X, n_probes=2, device=False)
+    assert a.pq_transformed_centers.size == b.pq_transformed_centers.size
+    for ta, tb, ia, ib in zip(a.pq_transformed_points, b.pq_transformed_points, a.ids, b.ids):
+        assert np.array_equal(ia, ib)
+        if isinstance(tb, tuple):
+            assert ta.size == tb.size and np.array_equal(ta.packed, tb.packed)

@@ -225,3 +225,28 @@ def test_restatement_matches_reference_package():
                 for npr in (1, 4):
                     assert np.array_equal(ivf.query(q.copy(), 10, n_probes=npr),
                                           O.ivf_query(S, q, 10, n_probes=npr, kernels=K))
+
+
+def _enc_pq(z, name):
+    R = z[name + "_R"]
+    return O.PQState(2, z[name + "_centers"], None if R.size == 0 else R)
+
+
+def test_golden_encode(golden):
+    """oracle.pq_transform == the reference's FastPQ.transform output (tests/golden/encode.npz), bit for bit."""
+    z = golden["encode"]
+    for name in z["names"]:
+        n, packed = O.pq_transform(_enc_pq(z, name), z[name + "_X"])
+        assert n == len(z[name + "_X"]) and np.array_equal(packed, z[name + "_packed"]), name
+
+
+@pytest.mark.skipif(not ref_loader.have_ref_package(), reason="/root/reference not present")
+def test_encode_restatement_matches_reference_package():
+    t = ref_loader.load_ref_package()
+    rng = np.random.default_rng(5)
+    for d in (24, 100, 128):
+        X = rng.standard_normal((300, d)).astype(np.float32)
+        pq = t.FastPQ(2, use_kmeans=True).fit(X)
+        td = pq.transform(X[:77])
+        n, packed = O.pq_transform(O.PQState.from_pq(pq), X[:77])
+        assert n == td.size and np.array_equal(packed, td.packed)

@@ -37,6 +37,7 @@ SIGNATURES = {
     "tkb_peer_open": [_vp, _c.POINTER(_vp)],
     "tkb_peer_close": [_vp],
     "tkb_peer_free": [_vp],
+    "tkb_encode_dev": [_vp, _i, _i64, _i, _vp, _i64, _vp, _vp, _i, _i, _vp, _i, _vp, _vp],
     "tkb_codes_to_native_dev": [_vp, _i64, _i, _vp, _vp],
     "tkb_codes_from_native_dev": [_vp, _i64, _i, _vp, _vp],
     "tkb_estimate_native_dev": [_vp, _i64, _i, _vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp],

@@ -255,6 +255,14 @@ int tkb_peer_free(void *dev_ptr)
     return TKB_OK;
 }
 
+int tkb_encode_dev(const void *rows, int rows_dtype, int64_t n_rows, int d, const int64_t *row_index, int64_t n_out,
+                   const float *centers, const float *cnorm, int Dp, int dpb, const double *R, int Dpad,
+                   uint64_t *codes, void *stream)
+{
+    return launch_encode(rows, rows_dtype, n_rows, d, row_index, n_out, centers, cnorm, Dp, dpb, R, Dpad, codes,
+                         (cudaStream_t)stream);
+}
+
 int tkb_codes_to_native_dev(const uint64_t *codes, int64_t n_chunks, int M, void *native, void *stream)
 {
     return launch_codes_to_native(codes, n_chunks, M, native, (cudaStream_t)stream);

@@ -105,6 +105,9 @@ int launch_ivf_scan(const uint64_t *codes, const int64_t *list_chunk_off, const 
 int launch_ivf_plan(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner, int n_lists,
                     int mode, int rank, int n_ranks, int q_per_rank, const int64_t *home_base, int64_t *seg_off,
                     int64_t *group_bytes, void *workspace, int64_t workspace_bytes, cudaStream_t st);
+int launch_encode(const void *rows, int rows_dtype, int64_t n_rows, int d, const int64_t *row_index, int64_t n_out,
+                  const float *centers, const float *cnorm, int Dp, int dpb, const double *R, int Dpad, uint64_t *codes,
+                  cudaStream_t st);
 int launch_codes_to_native(const uint64_t *ref, int64_t n_chunks, int M, void *native, cudaStream_t st);
 int launch_codes_from_native(const void *native, int64_t n_chunks, int M, uint64_t *ref, cudaStream_t st);
 int launch_estimate_native(const void *native, int64_t n_chunks, int M, const uint8_t *tables, int Q, uint8_t *est,

@@ -96,6 +96,7 @@ struct ScanSmem {
     int *n_pend;
     int64_t *seg_c0, *seg_o;
     int *seg_end;
+    int keep;                                  // flagged chunks are pinned in L2 (evict_last) until the deferred pass
 };
 
 __host__ __device__ inline size_t scan_smem_carve(unsigned char *base, int M, int P, ScanSmem *out)
@@ -114,8 +115,19 @@ __host__ __device__ inline size_t scan_smem_carve(unsigned char *base, int M, in
         out->n_pend = reinterpret_cast<int *>(base + np);
         out->seg_c0 = reinterpret_cast<int64_t *>(base + c0); out->seg_o = reinterpret_cast<int64_t *>(base + so);
         out->seg_end = reinterpret_cast<int *>(base + se);
+        out->keep = 0;
     }
     return o;
+}
+
+// The 16-byte groups of a chunk that failed the certificate will be read again by scan_deferred, a few hundred KB of
+// streamed codes later: by then they have left L2 (the main loads are evict-first) and each 16-byte group costs a 32-byte
+// DRAM sector a second time. Re-touching them with an evict_last prefetch while they are still in L2 keeps them there.
+__device__ __forceinline__ void keep_chunk_in_l2(const uint4 *__restrict__ nat, int64_t c, int Ph)
+{
+    const uint4 *base = nat + native_off(c, 0, Ph);
+    for (int p = 0; p < Ph; p++)
+        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (size_t)p * TILE));
 }
 
 // One chunk of one query. The fast path's certificate decides; a chunk that fails it is NOT recomputed by the thread
@@ -131,7 +143,11 @@ __device__ __forceinline__ void scan_one(const uint4 *__restrict__ nat, int64_t 
         o = scan_chunk_fast<SIGNED, PH>(nat, c, Ph, sm.rows, m, flagged);
         if (flagged) {
             const int i = atomicAdd(sm.n_pend, 1);
-            if (i < PEND_CAP) { sm.pend_off[i] = off; sm.pend_chunk[i] = (uint32_t)c; return; }
+            if (i < PEND_CAP) {
+                sm.pend_off[i] = off; sm.pend_chunk[i] = (uint32_t)c;
+                if (sm.keep) keep_chunk_in_l2(nat, c, Ph);
+                return;
+            }
             o = scan_chunk_steps_cold<ORDER, SIGNED>(nat, c, Ph, sm.rows, sm.sc, m);
         }
     } else if (m.steps_ok) {
@@ -185,11 +201,12 @@ ivf_scan_fast_kernel(const uint4 *__restrict__ nat, const int64_t *__restrict__ 
                      const int32_t *__restrict__ list_size, int n_lists, int M,
                      const uint8_t *__restrict__ tables, const int32_t *__restrict__ probes, int P,
                      uint8_t *__restrict__ est, int64_t slot_stride, const int64_t *__restrict__ seg_off,
-                     unsigned long long *stat)
+                     unsigned long long *stat, int keep)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     ScanSmem sm;
     scan_smem_carve(smem, M, P, &sm);
+    sm.keep = keep;
     const int q = blockIdx.y, Ph = M >> 1;
     if (threadIdx.x == 0) {
         *sm.n_pend = 0;
@@ -372,6 +389,11 @@ int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, co
     if (splits < 1) splits = 1;
     const size_t smem = fast_smem_bytes(M, P);
     const uint4 *n4 = reinterpret_cast<const uint4 *>(native);
+    // TKB_SCAN_KEEP=1 pins flagged chunks in L2 until the deferred pass. Measured on the 100M x 128 index (ncu, r1d): DRAM reads
+    // 96.6 -> 87.7 GB per launch (= the algorithmic bytes), kernel 16.98 -> 16.43 ms in isolation, but no gain inside a step
+    // (the evict_last lines pile up in L2 across launches): off by default.
+    static int keep = -1;
+    if (keep < 0) { const char *e = getenv("TKB_SCAN_KEEP"); keep = (e && atoi(e) == 1) ? 1 : 0; }
     for (int q0 = 0; q0 < Q; q0 += 65535) {
         const int qn = (Q - q0 < 65535) ? (Q - q0) : 65535;
         dim3 grid((unsigned)splits, (unsigned)qn);
@@ -379,10 +401,10 @@ int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, co
         uint8_t *eb = seg_off ? est : est + (size_t)q0 * P * slot_stride;
         if (order == TKB_ORDER_AVX && signd)
             TKB_DISPATCH_FAST_AVXS(ivf_scan_fast_kernel, grid, scan_threads, smem, st, n4, list_chunk_off, list_size, n_lists, M,
-                                   tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat);
+                                   tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep);
         else
             TKB_DISPATCH_FAST(ivf_scan_fast_kernel, grid, scan_threads, smem, st, n4, list_chunk_off, list_size, n_lists, M,
-                              tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat);
+                              tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep);
         TKB_LAUNCH_CHECK();
     }
     return TKB_OK;

@@ -113,10 +113,21 @@ class FastPQ:
             books.append(km.cluster_centers_.copy())
         return books
 
-    def transform(self, data, verbose=False):
+    def transform(self, data, verbose=False, device=None):
+        """ref: fast_pq.py:147-184. Build-time, not on the query path. device=None: encode on the GPU
+        (`tkb_encode_dev`) when one is present, else with numpy on the host; True / False force one of them."""
         assert self.centers is not None, "PQ has not been fitted"
         if data.size == 0:
             return data
+        if device is None:
+            device = D.torch().cuda.is_available()
+        if device:
+            true_n = data.shape[0]
+            packed = self.encode_device(D.upload(np.ascontiguousarray(data)) if isinstance(data, np.ndarray) else data)
+            return TransformedData(true_n, packed.cpu().numpy().view(np.uint64))
+        return self._transform_host(data)
+
+    def _transform_host(self, data):
         true_n = data.shape[0]
         dpb = self.dims_per_block
         data = pad2(data, 16, dpad * dpb)
@@ -134,6 +145,31 @@ class FastPQ:
                 part = np.einsum("ij,ij->i", xm, xm)[:, None] + np.einsum("ij,ij->i", cm, cm)[None] - 2 * xm @ cm.T
                 codes[lo:lo + xm.shape[0], m] = np.argmin(part, axis=1)
         return TransformedData(true_n, transform_data(codes))
+
+    def encode_device(self, rows, row_index=None, n_out=None):
+        """Batched encoder on the GPU (new, additive API; `tkb_encode_dev`): rows f32/f64 (n, d) device tensor ->
+        packed codes, int64 bit patterns (n_out/16, M) in the reference layout. Output position i encodes
+        rows[row_index[i]] (an index outside [0, n) = the zero vector = the reference's padding rows); without
+        row_index position i is row i and n_out defaults to n rounded up to 16."""
+        t = D.require_cuda()
+        assert self.centers is not None, "PQ has not been fitted"
+        n, d = rows.shape
+        rows = rows.contiguous()
+        assert rows.dtype in (t.float32, t.float64)
+        Dpad, Dp, M = self._lut_dims(d)
+        if n_out is None:
+            n_out = (len(row_index) if row_index is not None else n)
+            n_out = -(-n_out // 16) * 16
+        assert n_out % 16 == 0 and (row_index is None or len(row_index) == n_out)
+        cen, R = self._dev_state()
+        dpb = self.dims_per_block
+        books = np.ascontiguousarray(self.centers, dtype=np.float32).reshape(16, M, dpb).transpose(1, 0, 2)
+        cnorm = np.stack([np.einsum("ij,ij->i", b, b) for b in books]).astype(np.float32)   # utils.py:78 (Ynorm2, f32)
+        out = D.empty((n_out // 16, M), np.int64)
+        check(lib.tkb_encode_dev(D.ptr(rows), DTYPE_F64 if rows.dtype == t.float64 else DTYPE_F32, n, d,
+                                 D.ptr(row_index), n_out, D.ptr(cen), D.ptr(D.upload(cnorm)), Dp, dpb, D.ptr(R), Dpad,
+                                 D.ptr(out), D.stream_ptr()))
+        return out
 
     # ------------------------------------------------------------------ query time (device) --
     def _dev_state(self):

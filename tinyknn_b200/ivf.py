@@ -91,8 +91,10 @@ class IVF:
             self.pq.fit(X, verbose=verbose)
         return self
 
-    def build(self, X, n_probes=2, verbose=False):
-        """Put every point into the lists of its n_probes nearest centroids (ref: ivf.py:53-104)."""
+    def build(self, X, n_probes=2, verbose=False, device=None):
+        """Put every point into the lists of its n_probes nearest centroids (ref: ivf.py:53-104).
+        device=None: the PQ encoding of all lists runs as ONE `tkb_encode_dev` launch when a GPU is present (rows gathered
+        list by list, every list padded to 16 with zero vectors like FastPQ.transform does), else list by list on the host."""
         assert n_probes <= self.n_clusters, \
             f"Can't assign points to {n_probes} clusters, as index only has {self.n_clusters}"
         self.data = data = X.copy()
@@ -106,10 +108,31 @@ class IVF:
         with timer(verbose, "Transforming points..."):
             n_active = self.active_centers.shape[0]
             groups, self.ids = group_data_by_indices(data, nearest, n_active)
-            for i, g in enumerate(groups):
-                self.pq_transformed_points[i] = self.pq.transform(g)
+            if device is None:
+                device = D.torch().cuda.is_available()
+            if device and data.dtype in (np.float32, np.float64):
+                self._encode_lists_device(data, groups)
+            else:
+                for i, g in enumerate(groups):
+                    self.pq_transformed_points[i] = self.pq.transform(g, device=False)
         self.__dict__.pop("_dev", None)
         return self
+
+    def _encode_lists_device(self, data, groups):
+        """pq.transform of every list in one launch: position i of the output encodes data[row_index[i]], -1 = padding."""
+        sizes = np.array([len(i) for i in self.ids], dtype=np.int64)
+        n16 = -(-sizes // 16) * 16
+        off = np.concatenate(([0], np.cumsum(n16)))
+        row_index = np.full(int(off[-1]), -1, dtype=np.int64)
+        for l, ids_l in enumerate(self.ids):
+            row_index[off[l]:off[l] + sizes[l]] = np.asarray(ids_l, dtype=np.int64)
+        if off[-1]:
+            packed = self.pq.encode_device(D.upload(data), row_index=D.upload(row_index)).cpu().numpy().view(np.uint64)
+        for l in range(len(self.ids)):
+            if sizes[l] == 0:
+                self.pq_transformed_points[l] = groups[l]            # FastPQ.transform returns empty input as is (fast_pq.py:160)
+            else:
+                self.pq_transformed_points[l] = TransformedData(int(sizes[l]), packed[off[l] // 16:off[l + 1] // 16])
 
     # ------------------------------------------------------------------ device index ---------
     def __getstate__(self):
@@ -372,13 +395,15 @@ class IVF:
         return ids, cnt, dst
 
     def _plan(self, dev, probes, Q, P, mode=PLAN_SEND, rank=0, n_ranks=1, q_per_rank=0, rows=None):
-        """Segment offsets of the compact estimate buffer (tkb_ivf_plan_dev). Returns (seg_off, group_bytes)."""
+        """Segment offsets of the compact estimate buffer (tkb_ivf_plan_dev). Returns (seg_off, group_bytes).
+        n_ranks == 1 plans every segment (list ownership only matters to the sharded modes)."""
         rows = Q if rows is None else rows
         seg_off = D.empty((rows, P), np.int64)
         gb = D.empty((2 * n_ranks + 1,), np.int64)
         ws = D.empty((max(rows, 1) * n_ranks,), np.int64)
         with self._stage("plan"):
-            check(lib.tkb_ivf_plan_dev(D.ptr(probes), Q, P, D.ptr(dev["list_size"]), D.ptr(dev.get("list_owner")), dev["n_lists"],
+            check(lib.tkb_ivf_plan_dev(D.ptr(probes), Q, P, D.ptr(dev["list_size"]),
+                                       D.ptr(dev.get("list_owner")) if n_ranks > 1 else None, dev["n_lists"],
                                        mode, rank, n_ranks, q_per_rank, D.ptr(seg_off), D.ptr(gb), D.ptr(ws), 8 * ws.numel(),
                                        D.stream_ptr()))
         return seg_off, gb
