@@ -188,10 +188,11 @@ TKB_API int tkb_codes_to_native_dev(const uint64_t *codes, int64_t n_chunks, int
 TKB_API int tkb_codes_from_native_dev(const void *native, int64_t n_chunks, int M, uint64_t *codes, void *stream);
 
 /* Fast scan on the native layout: same results as tkb_estimate_dev / tkb_ivf_scan_dev, bit for bit.
- * LUT rows are looked up with PRMT; sums are accumulated without per-step clamps and a per-vector
- * certificate decides which chunks the exact patch pass recomputes.
- * workspace: 16-byte aligned device scratch, 16 + 8 bytes per chunk that may fail the certificate; chunks that
- * do not fit are recomputed inside the scan kernel (slower, still exact), so any size >= 24 is valid.
+ * LUT rows are looked up with PRMT; sums are accumulated without per-step clamps and a per-vector certificate decides
+ * which chunks are recomputed with the reference's step-by-step fold -- inside the same kernel, by the CTA that found
+ * them.
+ * workspace: optional 16-byte aligned device scratch of >= 16 bytes; its first 8 bytes return the number of chunks whose
+ * certificate failed (a statistic, reset by every call). NULL is allowed.
  * max_chunks_per_query (ivf): upper bound used to size the grid (0: P * slot_stride / 16).
  * tkb_ivf_scan_native_dev with est == NULL and seg_off != NULL: seg_off holds absolute device addresses (possibly
  * peer-mapped memory of another GPU), negative = skip (tkb_ivf_plan_push_dev). */
@@ -231,6 +232,22 @@ TKB_API int tkb_ivf_replay_fresh_dev(const uint8_t *est, int64_t slot_stride, co
                              const int32_t *probes, int Q, int P,
                              int64_t *heap_idx, int32_t *heap_val, int R, int signd,
                              int unique_labels, int32_t *fallback, void *stream);
+
+/* Chunk minima for long probe lists. The scan additionally stores, for every 16-vector chunk, the smallest
+ * of its estimates: cmin[o / 16] for the chunk whose estimates sit at est + o (cmin: est bytes / 16 + 16 bytes, 16-byte
+ * aligned, same signedness as est). The replay of a query whose segments lie back to back in `est` (the compact plan of
+ * tkb_ivf_plan_dev with n_ranks == 1) then tests 16 chunks per 16-byte load and fetches a chunk's estimates only when its
+ * minimum is below the (stale, hence conservative) bound of the round; other queries take the ordinary path. Results are
+ * identical to tkb_ivf_scan_native_dev + tkb_ivf_replay_fresh_dev, bit for bit (the heap arrays included). */
+TKB_API int tkb_ivf_scan_native_cm_dev(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
+                               const uint8_t *tables, const int32_t *probes, int Q, int P,
+                               uint8_t *est, const int64_t *seg_off, uint8_t *cmin, int64_t max_chunks_per_query,
+                               int order, int signd, void *workspace, int64_t workspace_bytes, void *stream);
+TKB_API int tkb_ivf_replay_fresh_cm_dev(const uint8_t *est, const int64_t *seg_off, const uint8_t *cmin, const int64_t *list_chunk_off,
+                                const int32_t *list_size, int n_lists, const int64_t *ids,
+                                const int32_t *probes, int Q, int P,
+                                int64_t *heap_idx, int32_t *heap_val, int R, int signd,
+                                int unique_labels, int32_t *fallback, void *stream);
 
 /* Exact rescoring distances: replaces the arithmetic of knn_brute1 (ref: tinyknn/utils.py:89-92).
  *   dists[q][r] = sum_i (rows[idx[q][r]][i] - queries[q][i])^2, computed in the rows' dtype

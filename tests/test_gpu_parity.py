@@ -809,3 +809,90 @@ def test_ivf_build_device_encoding_equals_host_build():
         assert np.array_equal(ia, ib)
         if isinstance(tb, tuple):
             assert ta.size == tb.size and np.array_equal(ta.packed, tb.packed)
+
+
+# ---- chunk minima: the replay of long probe lists (tkb_ivf_scan_native_cm_dev / tkb_ivf_replay_fresh_cm_dev) ---------
+
+def _host_cmin(packed_est, signd):
+    v = packed_est.reshape(-1, 16)
+    return (v.view(np.int8) if signd else v).min(axis=1).astype(np.int8 if signd else np.uint8).view(np.uint8)
+
+
+@pytest.mark.parametrize("signd", [True, False])
+def test_replay_cm_long_streams_equal_plain_replay_and_oracle(signd):
+    """Streams of several thousand chunks (so that rounds past RQ_CM_MIN use the chunk minima), value distributions with
+    many ties and with rare candidates, a skipped slot, an empty list, sizes that are not multiples of 16, heaps small
+    enough to cut rounds: heap arrays of the cm replay == plain replay == oracle."""
+    from tinyknn_b200._lib import lib, check, PROBE_SKIP, PLAN_SEND
+    from tinyknn_b200 import sharded as SH
+    rng = np.random.default_rng(77 + int(signd))
+    for trial in range(4):
+        n_lists = 12
+        sizes = rng.integers(3000, 30000, size=n_lists).astype(np.int32)
+        sizes[3], sizes[7] = 0, 17
+        nc8 = (-(-sizes.astype(np.int64) // 128)) * 8
+        off = np.zeros(n_lists + 1, np.int64)
+        off[1:] = np.cumsum(nc8)
+        ids = rng.permutation(16 * int(off[-1])).astype(np.int64) + 10 ** 10
+        Q, P, R = 9, 6, [331, 40, 111, 7][trial]
+        probes = np.stack([rng.permutation(n_lists)[:P] for _ in range(Q)]).astype(np.int32)
+        probes[2, 1] = PROBE_SKIP
+        seg, gb, _ = SH.plan_host(probes, sizes, None, PLAN_SEND, 0, 1, 0)
+        total = int(gb.sum())
+        if trial % 2 == 0:                                           # smooth: candidates get rare as the bound settles
+            est = np.clip(rng.normal(60, 25, size=total), 0, 126).astype(np.uint8)
+        else:                                                        # few distinct values: ties everywhere, long queues
+            est = (rng.integers(0, 6, size=total) * 9 + 40).astype(np.uint8)
+        if signd:
+            est = (est.astype(np.int16) - 64).astype(np.int8).view(np.uint8)
+        cm = np.concatenate([_host_cmin(est, signd), np.zeros(16, np.uint8)])
+        d_est, d_cm, d_seg = D.upload(np.concatenate([est, np.zeros(16, np.uint8)])), D.upload(cm), D.upload(seg)
+        d_off, d_sizes, d_ids, d_probes = (D.upload(x) for x in (off, sizes, ids, probes))
+        fb = D.empty((Q,), np.int32)
+        h = [(D.empty((Q, R), np.int64), D.empty((Q, R), np.int32)) for _ in range(2)]
+        check(lib.tkb_ivf_replay_fresh_dev(D.ptr(d_est), 0, D.ptr(d_seg), D.ptr(d_off), D.ptr(d_sizes), n_lists, D.ptr(d_ids),
+                                           D.ptr(d_probes), Q, P, D.ptr(h[0][0]), D.ptr(h[0][1]), R, int(signd), 1, D.ptr(fb), D.stream_ptr()))
+        check(lib.tkb_ivf_replay_fresh_cm_dev(D.ptr(d_est), D.ptr(d_seg), D.ptr(d_cm), D.ptr(d_off), D.ptr(d_sizes), n_lists, D.ptr(d_ids),
+                                              D.ptr(d_probes), Q, P, D.ptr(h[1][0]), D.ptr(h[1][1]), R, int(signd), 1, D.ptr(fb), D.stream_ptr()))
+        a, b = h[0][0].cpu().numpy(), h[0][1].cpu().numpy()
+        assert np.array_equal(h[1][0].cpu().numpy(), a) and np.array_equal(h[1][1].cpu().numpy(), b), trial
+        for q in range(0, Q, 4):
+            oi, ov = np.zeros(R, np.int64), np.zeros(R, np.int32)
+            O.init_heap(oi, ov, signd)
+            for s_ in range(P):
+                l = int(probes[q, s_])
+                if l == PROBE_SKIP or sizes[l] == 0:
+                    continue
+                ncr = -(-int(sizes[l]) // 16)
+                O.replay(est[seg[q, s_]:seg[q, s_] + 16 * ncr], int(sizes[l]), oi, ov, signd,
+                         np.ascontiguousarray(ids[16 * off[l]:16 * off[l] + 16 * ncr]))
+            assert np.array_equal(a[q], oi) and np.array_equal(b[q], ov), (trial, q)
+
+
+def test_query_batch_with_chunk_minima_equals_plain(monkeypatch):
+    """End to end on an index with long lists: the cm scan writes the same estimates plus correct minima, and query_batch
+    returns the same ids, distances and heap arrays with and without the chunk-minimum path."""
+    from tinyknn_b200 import synth, ivf as ivf_mod
+    X = synth.clustered(400_000 + 64, 64, 50, seed=5)
+    ivf = synth.build_ivf(X[:400_000], "euclidean", 12, seed=5)
+    qs = X[400_000:].contiguous()
+    monkeypatch.setattr(ivf_mod, "CMIN_CHUNKS", 0)
+    ref = ivf.query_batch(qs, 10, n_probes=6, order="device", return_distances=True, sub_batches=1)
+    ref_heap = (ivf._last["heap_idx"].cpu().numpy(), ivf._last["heap_val"].cpu().numpy())
+    monkeypatch.setattr(ivf_mod, "CMIN_CHUNKS", 1)
+    got = ivf.query_batch(qs, 10, n_probes=6, order="device", return_distances=True, sub_batches=1)
+    assert all(np.array_equal(x, y) for x, y in zip(ref, got))
+    assert np.array_equal(ivf._last["heap_idx"].cpu().numpy(), ref_heap[0])
+    assert np.array_equal(ivf._last["heap_val"].cpu().numpy(), ref_heap[1])
+    # the minima the scan wrote: recompute from its estimates
+    dev = ivf.to_device()
+    lut = ivf.pq.distance_tables(qs, signed=True)
+    Q, P = qs.shape[0], 6
+    probes = ivf._coarse(dev, lut, Q, P, min(2 * P + 10, dev["C"]), "device")
+    seg_off, gb = ivf._plan(dev, probes, Q, P)
+    total = int(gb.cpu().numpy()[1])
+    est, cmin = D.empty((total + 16,), np.uint8), D.empty((total // 16 + 16,), np.uint8)
+    ivf._scan(dev, lut["tables"], probes, Q, P, est, seg_off, cmin=cmin)
+    e, c = est.cpu().numpy()[:total], cmin.cpu().numpy()[:total // 16]
+    assert np.array_equal(c, _host_cmin(e, True))
+    assert total // 16 > 20_000                                     # long streams: the cm rounds really ran

@@ -134,9 +134,10 @@ def mirror_native(packed):
     return nat
 
 
-def scan_workspace(units):
-    """Scratch for the fast scan's patch list: 16 + 8 bytes per (query, chunk) unit."""
-    return empty((16 + 8 * max(int(units), 1),), np.uint8)
+def scan_workspace(units=0):
+    """Scratch of the fast scan: its first 8 bytes count the chunks whose certificate failed (they are recomputed inside
+    the scan kernel, so no per-chunk patch list is needed any more; `units` is ignored)."""
+    return empty((64,), np.uint8)
 
 
 def drop_mirrors():

@@ -327,6 +327,27 @@ int tkb_ivf_replay_fresh_dev(const uint8_t *est, int64_t slot_stride, const int6
                                    heap_val, R, signd, unique_labels, fallback, (cudaStream_t)stream);
 }
 
+int tkb_ivf_scan_native_cm_dev(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
+                               const uint8_t *tables, const int32_t *probes, int Q, int P,
+                               uint8_t *est, const int64_t *seg_off, uint8_t *cmin, int64_t max_chunks_per_query,
+                               int order, int signd, void *workspace, int64_t workspace_bytes, void *stream)
+{
+    TKB_REQUIRE(cmin && (uintptr_t)cmin % 16 == 0, "cmin must be a 16-byte aligned device buffer");
+    return launch_ivf_scan_native(native, list_chunk_off, list_size, n_lists, M, tables, probes, Q, P, est, 0, seg_off,
+                                  max_chunks_per_query, order, signd, workspace, workspace_bytes, (cudaStream_t)stream, cmin);
+}
+
+int tkb_ivf_replay_fresh_cm_dev(const uint8_t *est, const int64_t *seg_off, const uint8_t *cmin, const int64_t *list_chunk_off,
+                                const int32_t *list_size, int n_lists, const int64_t *ids,
+                                const int32_t *probes, int Q, int P,
+                                int64_t *heap_idx, int32_t *heap_val, int R, int signd,
+                                int unique_labels, int32_t *fallback, void *stream)
+{
+    TKB_REQUIRE(cmin, "null pointer");
+    return launch_ivf_replay_fresh(est, 0, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
+                                   heap_val, R, signd, unique_labels, fallback, (cudaStream_t)stream, cmin);
+}
+
 int tkb_gather_dists_dev(const void *rows, int rows_dtype, int64_t n_rows, int d,
                          const float *queries, const int64_t *idx, int Q, int R,
                          void *dists, void *stream)

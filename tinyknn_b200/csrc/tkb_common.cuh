@@ -116,7 +116,7 @@ int launch_estimate_native(const void *native, int64_t n_chunks, int M, const ui
 int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                            const uint8_t *tables, const int32_t *probes, int Q, int P, uint8_t *est,
                            int64_t slot_stride, const int64_t *seg_off, int64_t max_chunks_per_query, int order, int signd,
-                           void *workspace, int64_t workspace_bytes, cudaStream_t st);
+                           void *workspace, int64_t workspace_bytes, cudaStream_t st, uint8_t *cmin = nullptr);
 int launch_heap_fill(int64_t *heap_idx, int32_t *heap_val, int64_t count, int signd, cudaStream_t st);
 int launch_replay(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n, int64_t *heap_idx,
                   int32_t *heap_val, int Q, int R, int signd, const int64_t *labels, cudaStream_t st);
@@ -129,7 +129,7 @@ int launch_replay_fresh(const uint8_t *est, int64_t est_stride, int64_t n_chunks
 int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                             const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
                             int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int signd,
-                            int unique_labels, int *fallback, cudaStream_t st);
+                            int unique_labels, int *fallback, cudaStream_t st, const uint8_t *cmin = nullptr);
 int launch_lut_build(const float *queries, int Q, int d, int normalize, float *q_out,
                      const float *centers, int Dp, int dpb, const double *R, int Dpad,
                      double sqrt_n_blocks, double log_n_blocks, int signd, uint8_t *tables,

@@ -367,16 +367,19 @@ replay_rq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, cons
 //     reference's array, slot for slot (ref: _fast_pq.pyx:274-307; the bound is still frozen per 16-vector chunk).
 // Preconditions on top of replay_rq_kernel's: stream positions < 2^24 - 1, depth of the heap <= 2L steps.
 // ------------------------------------------------------------------------------------------------
+constexpr int RQ_CM_BLOCK = 512;                  // chunks a warp tests per step of the chunk-minimum path (16 per lane)
+constexpr int RQ_CM_MIN = 1024;                   // stream position (chunks) from which a round uses the chunk minima
 constexpr uint32_t RQ2_EMPTY = 0x00ffffffu;       // payload of a heap slot that was never filled
 constexpr uint32_t RQ2_SENTINEL = 0x80ffffffu;    // value -128
 
-template <bool SIGNED, int L>
-__global__ void __launch_bounds__(RQ_THREADS, 5)            // 5 CTAs/SM: 10 000 queries at 16 per CTA are one wave
+template <bool SIGNED, int L, bool CM = false>
+__global__ void __launch_bounds__(RQ_THREADS, CM ? 4 : 5)   // 5 CTAs/SM: 10 000 queries at 16 per CTA are one wave
 replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, const int64_t *__restrict__ seg_off,
                   int64_t n_chunks0, int n0, const int64_t *__restrict__ list_chunk_off,
                   const int32_t *__restrict__ list_size, int n_lists, const int64_t *__restrict__ ids,
                   const int32_t *__restrict__ probes, int Q, int P, int64_t *__restrict__ heap_idx,
-                  int32_t *__restrict__ heap_val, int R, int *__restrict__ fallback, int QPC, int QCAP)
+                  int32_t *__restrict__ heap_val, int R, int *__restrict__ fallback, int QPC, int QCAP,
+                  const uint8_t *__restrict__ cmin)
 {
     extern __shared__ __align__(16) unsigned char rq_sm[];
     const int HS = 2 * R + 4;                                              // words per heap: slot i at word i+1, children of R-1 included
@@ -385,6 +388,10 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
     int *cum = reinterpret_cast<int *>(QU + (size_t)QPC * (QCAP + 2));     // [QPC][P+1] real chunks before segment s
     int *s_cursor = cum + (size_t)QPC * (P + 1);
     int *s_seg = s_cursor + QPC, *s_bound = s_seg + QPC, *s_count = s_bound + QPC, *s_round = s_count + QPC;
+    // chunk-minimum path (cmin != null): est offset of the query's first chunk, or -1 when its segments are not back to back;
+    // one list of flagged chunks per warp
+    long long *s_qoff = reinterpret_cast<long long *>(rq_sm + (((size_t)((unsigned char *)(s_round + QPC) - rq_sm) + 15) & ~(size_t)15));
+    uint32_t *LST = reinterpret_cast<uint32_t *>(s_qoff + QPC);            // [n_warps][RQ_CM_BLOCK]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = RQ_THREADS / 32;
     const int q0 = blockIdx.x * QPC;
     const uint32_t flip = SIGNED ? 0u : 0x80u;                             // stored byte = value ^ flip
@@ -419,6 +426,19 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
         if (q < Q && fallback) fallback[q] = ok ? 0 : 1;
         if (!ok) for (int s = 0; s <= P; s++) c[s] = 0;
         s_cursor[t] = 0; s_seg[t] = 0; s_bound[t] = init; s_count[t] = 0; s_round[t] = 0;
+        if (CM && cmin) {
+            // the query's stream is one contiguous byte range of `est` when its segments lie back to back (the compact
+            // single-GPU plan): chunk cc of the stream is est[qoff + 16 cc ..] and its minimum is cmin[qoff / 16 + cc]
+            long long qoff = -1;
+            bool contig = ok && mode == 1 && seg_off != nullptr;
+            for (int s = 0; contig && s < P; s++) {
+                if (c[s + 1] == c[s]) continue;
+                const long long o = seg_off[(size_t)q * P + s];
+                if (qoff < 0) qoff = o - 16LL * c[s];
+                if (o < 0 || o != qoff + 16LL * c[s]) contig = false;
+            }
+            s_qoff[t] = (contig && qoff >= 0) ? qoff : -1;
+        }
     }
     __syncthreads();
 
@@ -440,6 +460,89 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
             // PF steps of 32 chunks are fetched before the first is examined: a window is thousands of chunks long once the
             // bound has settled and almost nothing survives the filter, so the walk is a chain of load latencies otherwise
             constexpr int PF = 4;
+            const bool use_cm = CM && cmin != nullptr && cursor >= RQ_CM_MIN && s_qoff[t] >= 0;
+            if (use_cm) {
+                // Long streams: once the bound has settled almost no chunk holds a candidate. The scan left one byte per
+                // chunk (its smallest estimate); a lane tests 16 chunks with one 16-byte load of those, the chunks that may
+                // hold a candidate are listed in stream order and only they are fetched and examined as above.
+                const long long qoff = s_qoff[t];
+                const uint8_t *cmq = cmin + (qoff >> 4);
+                const uint8_t *eq = est + qoff;
+                uint32_t *lst = LST + (size_t)warp * RQ_CM_BLOCK;
+                const int skew = (int)((uintptr_t)(cmq + cursor) & 15);
+                bool cut = false;
+                auto load_cm = [&](int lc) {
+                    uint4 e = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);      // stored form of "no candidate"
+                    if (lc < end && lc + 16 > cursor) {
+                        e = ldg_nc_u4(reinterpret_cast<const uint4 *>(cmq + lc));
+                        if (!SIGNED) { e.x ^= 0x80808080u; e.y ^= 0x80808080u; e.z ^= 0x80808080u; e.w ^= 0x80808080u; }
+                    }
+                    return e;
+                };
+                uint4 nxt = load_cm(cursor - skew + 16 * lane);
+                for (int b0 = cursor - skew; b0 < end && !cut; b0 += RQ_CM_BLOCK) {
+                    const int lc = b0 + 16 * lane;                           // this lane's 16 chunks: lc .. lc+15
+                    const uint4 e = nxt;
+                    nxt = load_cm(lc + RQ_CM_BLOCK);                         // the next block is in flight while this one is examined
+                    uint32_t m = 0;
+                    if (lc < end && lc + 16 > cursor) {
+                        m = cand_mask16<true>(e, bound);
+                        if (lc < cursor) m &= ~((1u << (cursor - lc)) - 1u);
+                        if (lc + 16 > end) m &= (1u << (end - lc)) - 1u;
+                    }
+                    if (__ballot_sync(FULL, m != 0) == 0) continue;
+                    const int fc = __popc(m);
+                    int fi = fc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, fi, o); if (lane >= o) fi += v; }
+                    const int F = __shfl_sync(FULL, fi, 31);
+                    {
+                        int k = fi - fc;
+                        while (m) { const int v = __ffs(m) - 1; m &= m - 1; lst[k++] = (uint32_t)(lc + v); }
+                    }
+                    __syncwarp();
+                    for (int j0 = 0; j0 < F; j0 += 32) {
+                        const bool act = j0 + lane < F;
+                        const int cc = act ? (int)lst[j0 + lane] : 0;
+                        uint32_t mm = 0;
+                        uint4 ee = make_uint4(0, 0, 0, 0);
+                        if (act) {
+                            int lo = 0, hi = P;                              // segment with c[lo] <= cc < c[lo+1]
+                            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (c[mid] <= cc) lo = mid; else hi = mid; }
+                            const int rem = list_size[probes[(size_t)q * P + lo]] - 16 * (cc - c[lo]);
+                            ee = ldg_nc_u4(reinterpret_cast<const uint4 *>(eq + 16LL * cc));
+                            if (!SIGNED) { ee.x ^= 0x80808080u; ee.y ^= 0x80808080u; ee.z ^= 0x80808080u; ee.w ^= 0x80808080u; }
+                            mm = cand_mask16<true>(ee, bound) & (rem >= 16 ? 0xffffu : ((1u << rem) - 1u));
+                        }
+                        if (__ballot_sync(FULL, mm != 0) == 0) continue;
+                        const int cnt = __popc(mm);
+                        int incl = cnt;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                        const int tot = __shfl_sync(FULL, incl, 31);
+                        int keep_tot = tot;
+                        if (count + tot > QCAP) {                            // queue full: the next round resumes at the first chunk that does not fit
+                            const unsigned over = __ballot_sync(FULL, count + incl > QCAP);
+                            const int cl = __ffs(over) - 1;
+                            keep_tot = __shfl_sync(FULL, incl - cnt, cl);
+                            end = __shfl_sync(FULL, cc, cl);
+                            if (lane >= cl) mm = 0;
+                            cut = true;
+                        }
+                        int k = count + incl - cnt;
+                        const uint32_t ws[4] = {ee.x, ee.y, ee.z, ee.w};
+                        while (mm) {
+                            const int v = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const uint32_t byte = (ws[v >> 2] >> (8 * (v & 3))) & 0xffu;
+                            qu[k++] = (byte << 24) | (16u * (uint32_t)cc + v);
+                        }
+                        count += keep_tot;
+                        if (cut) break;
+                    }
+                    __syncwarp();
+                }
+            } else
             for (int base0 = cursor; base0 < end; base0 += 32 * PF) {
                 uint4 ev[PF];
                 int slv[PF], remv[PF];
@@ -678,12 +781,14 @@ static size_t rq_smem(int R, int P, int qpc, int qcap)
     return (size_t)qpc * (8 * ((size_t)R + 1) + 8 * ((size_t)qcap + 1) + 4 * ((size_t)P + 1) + 20) + 16;
 }
 
-static size_t rq2_smem(int R, int P, int qpc, int qcap)
+static size_t rq2_smem(int R, int P, int qpc, int qcap, bool cm = false)
 {
-    return (size_t)qpc * (4 * (2 * (size_t)R + 4) + 4 * ((size_t)qcap + 2) + 4 * ((size_t)P + 1) + 20) + 16;
+    const size_t base = (size_t)qpc * (4 * (2 * (size_t)R + 4) + 4 * ((size_t)qcap + 2) + 4 * ((size_t)P + 1) + 20) + 16;
+    // chunk-minimum path: s_qoff[qpc] + one list of RQ_CM_BLOCK chunk numbers per warp
+    return cm ? base + 16 + 8 * (size_t)qpc + 4 * (size_t)(RQ_THREADS / 32) * RQ_CM_BLOCK : base;
 }
 
-static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 0)
+static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 0, bool cm = false)
 {
     if (R <= 0 || P <= 0) return false;
     static int v2_env = -1;
@@ -697,7 +802,7 @@ static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 
         while (qpc > 1 && (Q + qpc - 1) / qpc < 2 * 148) qpc >>= 1;
         while (qpc > 1 && rq2_smem(R, P, qpc, g.qcap) > 45 * 1024) qpc >>= 1;
         g.qpc = qpc; g.lpw = 0;
-        g.smem = rq2_smem(R, P, qpc, g.qcap);
+        g.smem = rq2_smem(R, P, qpc, g.qcap, cm);
         if (g.smem <= 200 * 1024) return true;
         g.v2 = 0;
     }
@@ -721,21 +826,20 @@ template <bool SIGNED>
 static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t *seg_off, int64_t n_chunks0, int n0,
                      const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, const int64_t *ids,
                      const int32_t *probes, int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int *fallback,
-                     const RqGeom &g, cudaStream_t st)
+                     const RqGeom &g, cudaStream_t st, const uint8_t *cmin = nullptr)
 {
     const unsigned blocks = (unsigned)((Q + g.qpc - 1) / g.qpc);
     if (g.v2) {
-        if (g.lanes == 4) {
-            TKB_CUDA(cudaFuncSetAttribute(replay_rq2_kernel<SIGNED, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-            replay_rq2_kernel<SIGNED, 4><<<blocks, RQ_THREADS, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off,
-                                                                            list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val,
-                                                                            R, fallback, g.qpc, g.qcap);
-        } else {
-            TKB_CUDA(cudaFuncSetAttribute(replay_rq2_kernel<SIGNED, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-            replay_rq2_kernel<SIGNED, 8><<<blocks, RQ_THREADS, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off,
-                                                                            list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val,
-                                                                            R, fallback, g.qpc, g.qcap);
-        }
+#define TKB_RQ2_LAUNCH(LANES, CMV)                                                                                                   \
+        do {                                                                                                                         \
+            TKB_CUDA(cudaFuncSetAttribute(replay_rq2_kernel<SIGNED, LANES, CMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
+            replay_rq2_kernel<SIGNED, LANES, CMV><<<blocks, RQ_THREADS, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off, \
+                                                                                     list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val,  \
+                                                                                     R, fallback, g.qpc, g.qcap, cmin);                          \
+        } while (0)
+        if (cmin) { if (g.lanes == 4) TKB_RQ2_LAUNCH(4, true); else TKB_RQ2_LAUNCH(8, true); }
+        else      { if (g.lanes == 4) TKB_RQ2_LAUNCH(4, false); else TKB_RQ2_LAUNCH(8, false); }
+#undef TKB_RQ2_LAUNCH
         TKB_LAUNCH_CHECK();
         return TKB_OK;
     }
@@ -768,10 +872,10 @@ template <bool SIGNED>
 static int ivf_replay_fresh_t(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                               const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
                               int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int *fallback,
-                              const RqGeom &g, cudaStream_t st)
+                              const RqGeom &g, cudaStream_t st, const uint8_t *cmin)
 {
     if (int rc = launch_rq<SIGNED>(1, est, slot_stride, seg_off, 0, 0, list_chunk_off, list_size, n_lists, ids, probes,
-                                   Q, P, heap_idx, heap_val, R, fallback, g, st)) return rc;
+                                   Q, P, heap_idx, heap_val, R, fallback, g, st, cmin)) return rc;
     // queries whose probe list holds Python-wrapped (negative) entries: warp-per-query kernel with label dedupe
     ivf_replay_fallback_kernel<SIGNED><<<(unsigned)((Q + REPLAY_WARPS - 1) / REPLAY_WARPS), 32 * REPLAY_WARPS, 0, st>>>(
         est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
@@ -782,23 +886,25 @@ static int ivf_replay_fresh_t(const uint8_t *est, int64_t slot_stride, const int
 int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                             const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
                             int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int signd,
-                            int unique_labels, int *fallback, cudaStream_t st)
+                            int unique_labels, int *fallback, cudaStream_t st, const uint8_t *cmin)
 {
     TKB_REQUIRE(Q >= 0 && R >= 0 && P >= 0 && n_lists > 0, "bad extent");
     if (Q == 0 || R == 0) return TKB_OK;
     TKB_REQUIRE(heap_idx && heap_val, "null pointer");
+    TKB_REQUIRE(!cmin || ((uintptr_t)cmin % 16 == 0 && seg_off), "cmin must be 16-byte aligned and needs a segment plan");
     RqGeom g;
-    if (!unique_labels || P == 0 || P >= 0xffff || !fallback || !rq_geometry(Q, R, P, g)) {
+    if (!unique_labels || P == 0 || P >= 0xffff || !fallback || !rq_geometry(Q, R, P, g, 0, cmin != nullptr)) {
         if (int rc = launch_heap_fill(heap_idx, heap_val, (int64_t)Q * R, signd, st)) return rc;
         return launch_ivf_replay(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
                                  heap_val, R, signd, st);
     }
     TKB_REQUIRE(est && list_chunk_off && list_size && ids && probes, "null pointer");
     TKB_REQUIRE(slot_stride % 16 == 0 && (uintptr_t)est % 16 == 0, "est must be 16-byte aligned/strided");
+    if (!g.v2) cmin = nullptr;                                             // only the pipelined kernel reads the chunk minima
     if (signd) return ivf_replay_fresh_t<true>(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P,
-                                               heap_idx, heap_val, R, fallback, g, st);
+                                               heap_idx, heap_val, R, fallback, g, st, cmin);
     return ivf_replay_fresh_t<false>(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P,
-                                     heap_idx, heap_val, R, fallback, g, st);
+                                     heap_idx, heap_val, R, fallback, g, st, cmin);
 }
 
 }  // namespace tkb

@@ -97,6 +97,7 @@ struct ScanSmem {
     int64_t *seg_c0, *seg_o;
     int *seg_end;
     int keep;                                  // flagged chunks are pinned in L2 (evict_last) until the deferred pass
+    uint8_t *cmin;                             // optional: smallest estimate of every chunk, at cmin[est offset / 16]
 };
 
 __host__ __device__ inline size_t scan_smem_carve(unsigned char *base, int M, int P, ScanSmem *out)
@@ -116,6 +117,7 @@ __host__ __device__ inline size_t scan_smem_carve(unsigned char *base, int M, in
         out->seg_c0 = reinterpret_cast<int64_t *>(base + c0); out->seg_o = reinterpret_cast<int64_t *>(base + so);
         out->seg_end = reinterpret_cast<int *>(base + se);
         out->keep = 0;
+        out->cmin = nullptr;
     }
     return o;
 }
@@ -128,6 +130,24 @@ __device__ __forceinline__ void keep_chunk_in_l2(const uint4 *__restrict__ nat, 
     const uint4 *base = nat + native_off(c, 0, Ph);
     for (int p = 0; p < Ph; p++)
         asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (size_t)p * TILE));
+}
+
+// Smallest of a chunk's 16 estimates (signed or unsigned like the estimates themselves): the heap replay of a long
+// probe list tests this byte first and fetches the 16 estimates only when one of them can be a candidate.
+template <bool SIGNED>
+__device__ __forceinline__ uint8_t chunk_min(const uint4 o)
+{
+    uint32_t m;
+    if (SIGNED) {
+        m = __vmins4(__vmins4(o.x, o.y), __vmins4(o.z, o.w));
+        m = __vmins4(m, m >> 16);
+        m = __vmins4(m, m >> 8);
+    } else {
+        m = __vminu4(__vminu4(o.x, o.y), __vminu4(o.z, o.w));
+        m = __vminu4(m, m >> 16);
+        m = __vminu4(m, m >> 8);
+    }
+    return (uint8_t)(m & 0xffu);
 }
 
 // One chunk of one query. The fast path's certificate decides; a chunk that fails it is NOT recomputed by the thread
@@ -156,6 +176,7 @@ __device__ __forceinline__ void scan_one(const uint4 *__restrict__ nat, int64_t 
         o = scan_chunk_exact_cold<ORDER, SIGNED>(nat, c, Ph, reinterpret_cast<const uint8_t *>(sm.raw));
     }
     *reinterpret_cast<uint4 *>(est + off) = o;
+    if (sm.cmin) sm.cmin[off >> 4] = chunk_min<SIGNED>(o);
 }
 
 template <int ORDER, bool SIGNED>
@@ -165,9 +186,11 @@ __device__ __forceinline__ void scan_deferred(const uint4 *__restrict__ nat, int
     __syncthreads();
     const int total = *sm.n_pend, n = total < PEND_CAP ? total : PEND_CAP;
     if (threadIdx.x == 0 && total && stat) atomicAdd(stat, (unsigned long long)total);
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        *reinterpret_cast<uint4 *>(est + sm.pend_off[i]) =
-            scan_chunk_steps<ORDER, SIGNED>(nat, (int64_t)sm.pend_chunk[i], Ph, sm.rows, sm.sc, m);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint4 o = scan_chunk_steps<ORDER, SIGNED>(nat, (int64_t)sm.pend_chunk[i], Ph, sm.rows, sm.sc, m);
+        *reinterpret_cast<uint4 *>(est + sm.pend_off[i]) = o;
+        if (sm.cmin) sm.cmin[sm.pend_off[i] >> 4] = chunk_min<SIGNED>(o);
+    }
 }
 
 template <int ORDER, bool SIGNED, int PH = 0>
@@ -201,12 +224,13 @@ ivf_scan_fast_kernel(const uint4 *__restrict__ nat, const int64_t *__restrict__ 
                      const int32_t *__restrict__ list_size, int n_lists, int M,
                      const uint8_t *__restrict__ tables, const int32_t *__restrict__ probes, int P,
                      uint8_t *__restrict__ est, int64_t slot_stride, const int64_t *__restrict__ seg_off,
-                     unsigned long long *stat, int keep)
+                     unsigned long long *stat, int keep, uint8_t *__restrict__ cmin)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     ScanSmem sm;
     scan_smem_carve(smem, M, P, &sm);
     sm.keep = keep;
+    sm.cmin = cmin;
     const int q = blockIdx.y, Ph = M >> 1;
     if (threadIdx.x == 0) {
         *sm.n_pend = 0;
@@ -360,10 +384,11 @@ int launch_estimate_native(const void *native, int64_t n_chunks, int M, const ui
 int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                            const uint8_t *tables, const int32_t *probes, int Q, int P, uint8_t *est,
                            int64_t slot_stride, const int64_t *seg_off, int64_t max_chunks_per_query, int order, int signd,
-                           void *workspace, int64_t workspace_bytes, cudaStream_t st)
+                           void *workspace, int64_t workspace_bytes, cudaStream_t st, uint8_t *cmin)
 {
     if (int rc = check_fast_args(M, order)) return rc;
     TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists > 0, "bad extent");
+    TKB_REQUIRE(!cmin || (est && seg_off), "chunk minima need a compact plan relative to est");
     if (Q == 0 || P == 0 || (slot_stride == 0 && !seg_off)) return TKB_OK;
     // est == NULL with a plan: the plan holds absolute addresses (TKB_PLAN_PUSH: segments land in the receive buffers of
     // the queries' home ranks, peer-mapped over NVLink)
@@ -401,10 +426,10 @@ int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, co
         uint8_t *eb = seg_off ? est : est + (size_t)q0 * P * slot_stride;
         if (order == TKB_ORDER_AVX && signd)
             TKB_DISPATCH_FAST_AVXS(ivf_scan_fast_kernel, grid, scan_threads, smem, st, n4, list_chunk_off, list_size, n_lists, M,
-                                   tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep);
+                                   tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep, cmin);
         else
             TKB_DISPATCH_FAST(ivf_scan_fast_kernel, grid, scan_threads, smem, st, n4, list_chunk_off, list_size, n_lists, M,
-                              tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep);
+                              tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep, cmin);
         TKB_LAUNCH_CHECK();
     }
     return TKB_OK;

@@ -34,6 +34,9 @@ _SUB_QUERIES = int(os.environ.get("TKB_SUB_QUERIES", "5000"))      # target quer
 # One kernel after probe selection (tkb_ivf_query_fused_dev). Off by default: measured slower than the stage-by-stage
 # kernels at large batches (a CTA holds its scan registers while it sits in the latency-bound replay), DESIGN.md 4.6.
 FUSED = os.environ.get("TKB_FUSED", "0") != "0"
+# Chunk minima (tkb_ivf_scan_native_cm_dev / tkb_ivf_replay_fresh_cm_dev) when a query may scan at least this many chunks:
+# the replay of long probe lists then reads 1 byte per chunk instead of 16. 0 disables.
+CMIN_CHUNKS = int(os.environ.get("TKB_CMIN_CHUNKS", "8192"))
 _streams = {}
 _ws_cap = {}
 
@@ -335,7 +338,7 @@ class IVF:
         self._last = dict(center_heap=hci, tables=tables)
         return probes
 
-    def _scan(self, dev, tables, probes, Q, P, est, seg_off, codes_key="codes", off_key="list_chunk_off"):
+    def _scan(self, dev, tables, probes, Q, P, est, seg_off, codes_key="codes", off_key="list_chunk_off", cmin=None):
         """Estimates of every (query, probed list) segment present in `seg_off` (ref: the scan half of
         query_pq_*, ivf.py:142-150), written compactly into `est`."""
         st = D.stream_ptr()
@@ -347,16 +350,21 @@ class IVF:
         with self._stage("scan"):
             if _fp.SCAN_IMPL == "fast":
                 ws = D.scan_workspace(min(Q * max_q_chunks, max(1 << 20, Q * max_q_chunks // 4)))
-                check(lib.tkb_ivf_scan_native_dev(D.ptr(dev[codes_key]), D.ptr(dev[off_key]), D.ptr(dev["list_size"]), n_lists, M,
-                                                  D.ptr(tables), D.ptr(probes), Q, P, D.ptr(est), 0, D.ptr(seg_off),
-                                                  max_q_chunks, _fp._order(), 1, D.ptr(ws), ws.numel(), st))
+                if cmin is not None:
+                    check(lib.tkb_ivf_scan_native_cm_dev(D.ptr(dev[codes_key]), D.ptr(dev[off_key]), D.ptr(dev["list_size"]), n_lists, M,
+                                                         D.ptr(tables), D.ptr(probes), Q, P, D.ptr(est), D.ptr(seg_off), D.ptr(cmin),
+                                                         max_q_chunks, _fp._order(), 1, D.ptr(ws), ws.numel(), st))
+                else:
+                    check(lib.tkb_ivf_scan_native_dev(D.ptr(dev[codes_key]), D.ptr(dev[off_key]), D.ptr(dev["list_size"]), n_lists, M,
+                                                      D.ptr(tables), D.ptr(probes), Q, P, D.ptr(est), 0, D.ptr(seg_off),
+                                                      max_q_chunks, _fp._order(), 1, D.ptr(ws), ws.numel(), st))
                 self._last["patch_ws"] = ws
             else:
                 check(lib.tkb_ivf_scan_dev(D.ptr(self._ref_codes(dev, codes_key, dev["n_chunks_total"])), D.ptr(dev[off_key]),
                                            D.ptr(dev["list_size"]), n_lists, M, D.ptr(tables), D.ptr(probes), Q, P,
                                            D.ptr(est), 0, D.ptr(seg_off), max(dev["max_real_chunks"], 1), _fp._order(), 1, st))
 
-    def _replay_rescore(self, dev, qn, probes, Q, P, k, pass_1, est, seg_off, order, out=None):
+    def _replay_rescore(self, dev, qn, probes, Q, P, k, pass_1, est, seg_off, order, out=None, cmin=None):
         """Ordered exact heap replay over the probed lists, then exact rescoring and the k nearest
         (ref: ivf.py:137-163). `probes`/`seg_off` are the rows of these Q queries."""
         st = D.stream_ptr()
@@ -364,10 +372,16 @@ class IVF:
         hi_, hv_ = D.empty((Q, pass_1), np.int64), D.empty((Q, pass_1), np.int32)
         fb = D.empty((Q,), np.int32)
         with self._stage("replay"):
-            check(lib.tkb_ivf_replay_fresh_dev(D.ptr(est), 0, D.ptr(seg_off), D.ptr(dev["list_chunk_off"]),
-                                               D.ptr(dev["list_size"]), n_lists, D.ptr(dev["ids"]), D.ptr(probes), Q, P,
-                                               D.ptr(hi_), D.ptr(hv_), pass_1, 1, int(dev.get("unique_ids", False)),
-                                               D.ptr(fb), st))
+            if cmin is not None:
+                check(lib.tkb_ivf_replay_fresh_cm_dev(D.ptr(est), D.ptr(seg_off), D.ptr(cmin), D.ptr(dev["list_chunk_off"]),
+                                                      D.ptr(dev["list_size"]), n_lists, D.ptr(dev["ids"]), D.ptr(probes), Q, P,
+                                                      D.ptr(hi_), D.ptr(hv_), pass_1, 1, int(dev.get("unique_ids", False)),
+                                                      D.ptr(fb), st))
+            else:
+                check(lib.tkb_ivf_replay_fresh_dev(D.ptr(est), 0, D.ptr(seg_off), D.ptr(dev["list_chunk_off"]),
+                                                   D.ptr(dev["list_size"]), n_lists, D.ptr(dev["ids"]), D.ptr(probes), Q, P,
+                                                   D.ptr(hi_), D.ptr(hv_), pass_1, 1, int(dev.get("unique_ids", False)),
+                                                   D.ptr(fb), st))
         ddt = np.float32 if dev["data_dtype"] == DTYPE_F32 else np.float64
         dd = D.empty((Q, pass_1), ddt)
         with self._stage("rescore"):
@@ -443,5 +457,8 @@ class IVF:
         # 3. scan of the probed lists into a compact estimate buffer, ordered replay, rescoring
         seg_off, _ = self._plan(dev, probes, Q, P)
         est = D.empty((Q * P * 16 * max(dev["max_real_chunks"], 1),), np.uint8)      # upper bound; only the planned part is touched
-        self._scan(dev, lut["tables"], probes, Q, P, est, seg_off)
-        return self._replay_rescore(dev, lut["q"], probes, Q, P, k, pass_1, est, seg_off, order, out)
+        cmin = None
+        if CMIN_CHUNKS > 0 and _fp.SCAN_IMPL == "fast" and P * max(dev["max_real_chunks"], 1) >= CMIN_CHUNKS:
+            cmin = D.empty((est.numel() // 16 + 16,), np.uint8)
+        self._scan(dev, lut["tables"], probes, Q, P, est, seg_off, cmin=cmin)
+        return self._replay_rescore(dev, lut["q"], probes, Q, P, k, pass_1, est, seg_off, order, out, cmin=cmin)
