@@ -57,9 +57,12 @@ def parse():
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
                     help="--shard lists: 'push' = the scan kernel stores estimates into the home rank's HBM over NVLink peer "
                          "memory (falls back to nccl when peer buffers cannot be mapped), 'nccl' = send buffer + all-to-all")
-    ap.add_argument("--shard", default="lists", choices=["lists", "replicas"],
-                    help="N>1: 'lists' = inverted lists sharded over the ranks, estimates exchanged with one NCCL "
-                         "all-to-all (north star); 'replicas' = every rank holds the whole index and its own queries")
+    ap.add_argument("--shard", default="auto", choices=["auto", "lists", "replicas"],
+                    help="N>1: 'lists' = inverted lists sharded over the ranks, estimates stored into the query's home rank "
+                         "(north star; what a 100M-vector index needs for aggregate bandwidth); 'replicas' = every rank holds "
+                         "the whole index and answers its own queries, no data-path collective; 'auto' = lists when the PQ "
+                         "codes of the workload are >= 1 GB, else replicas (a 31 MB index gains nothing from being split: "
+                         "measured 8 GPUs, GloVe shape: lists 24.4M q/s, DESIGN.md 6)")
     return ap.parse_args()
 
 
@@ -245,6 +248,9 @@ def main():
     dev_batches = [torch.from_numpy(b).cuda() for b in batches]
     pinned = [torch.from_numpy(b).pin_memory() for b in batches]
     kw = dict(k=args.k, n_probes=args.n_probes)
+    if args.shard == "auto":
+        code_bytes = w["n"] * (-(-w["d"] // 8) * 8 // 2 if w["d"] == 100 else 32) // 2      # M/2 bytes per vector (M = 52 / 32)
+        args.shard = "lists" if code_bytes >= (1 << 30) else "replicas"
     sharded = world > 1 and args.shard == "lists"
     if sharded:
         # every rank built the same index (same seed); rank r keeps the codes of its lists and answers its own
@@ -413,8 +419,10 @@ def main():
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="i8", data="synthetic", config=dict(cfg, parallelism=("lists sharded over %d ranks, %s" % (world, "estimates stored into the home rank's HBM by the scan kernel (NVLink peer memory)" if engine.last_exchange == "push" else "NCCL all-to-all of estimates")) if sharded
                                              else ("query-sharded replicas x%d" % world),
-                    l2="estimate buffer rewritten every step and query batches rotate between steps; the codes of this "
-                                   "workload (31 MB) are L2-resident by nature, see DESIGN.md"),
+                    l2=("estimate buffer rewritten every step and query batches rotate between steps; the codes of this "
+                        "workload (%d MB) %s" % (dev["n_chunks_total"] * M * 8 >> 20,
+                                                 "are L2-resident by nature, see DESIGN.md" if dev["n_chunks_total"] * M * 8 < (100 << 20)
+                                                 else "are larger than the 126 MB L2: every step streams them from HBM"))),
                     clocks=clocks, e2e=dict(value=e2e_v, unit="queries/s", h2d_bytes_per_step=int(Qn * w["d"] * 4),
                                             d2h_bytes_per_step=int(Qn * args.k * 8 + Qn * 4)),
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=cb, parity=parity)

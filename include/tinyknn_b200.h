@@ -179,6 +179,17 @@ TKB_API int tkb_encode_dev(const void *rows, int rows_dtype, int64_t n_rows, int
                    const float *centers, const float *cnorm, int Dp, int dpb, const double *R, int Dpad,
                    uint64_t *codes, void *stream);
 
+/* Coarse assignment (build time): replaces the arithmetic of knn_brute(data, all_centers, k) in
+ * IVF.build (ref: tinyknn/ivf.py:84-86, tinyknn/utils.py:66-86): part = (|x|^2 + |c|^2) - (2x).c with the dot product as
+ * the FMA chain over the dimension that the reference's sgemm/dgemm computes (bit-identical for d <= 384), the k in
+ * {1, 2} smallest per row in ascending (part, index) order. rows/centers/xnorm/cnorm share one dtype (f32 or f64).
+ *   xnorm [n], cnorm [C] : |x|^2 / |c|^2 as the caller's numpy computed them (np.einsum; pass them for bit parity), or
+ *                          NULL: computed here left to right into scratch ((n + C) elements)
+ *   nearest int32[n][k]  : out. k = 1 reproduces the reference's assignment wherever the minimum is unique; for k = 2 the
+ *                          SET per row is the reference's, the order inside a row is not (np.argpartition's is unspecified) */
+TKB_API int tkb_assign_dev(const void *rows, int dtype, int64_t n, int d, const void *centers, int C, const void *xnorm,
+                   const void *cnorm, int k, int32_t *nearest, void *scratch, int64_t scratch_bytes, void *stream);
+
 /* Device-native code layout for the fast scan (chosen at upload, round-trips to the reference layout).
  * tile = 8 chunks; the 16 bytes of (tile t, pair p, chunk slot s) sit at ((t*M/2 + p)*8 + s)*16 and hold
  * 8 halfwords: halfword g = codes of sub-quantizer 2p for vectors 4g..4g+3 (nibble i = vector 4g+i),
@@ -243,6 +254,14 @@ TKB_API int tkb_ivf_scan_native_cm_dev(const void *native, const int64_t *list_c
                                const uint8_t *tables, const int32_t *probes, int Q, int P,
                                uint8_t *est, const int64_t *seg_off, uint8_t *cmin, int64_t max_chunks_per_query,
                                int order, int signd, void *workspace, int64_t workspace_bytes, void *stream);
+/* The same scan inside the push exchange (est == NULL, seg_addr = absolute addresses from tkb_ivf_plan_push_dev): the
+ * minima of a segment go to the home rank's minima region. cm_home int64[n_ranks] (device): for home rank h,
+ * (address of its minima region) - (address of its estimate buffer >> 4), both as mapped in THIS process; the home rank of
+ * query q is q / q_per_rank. */
+TKB_API int tkb_ivf_scan_native_push_cm_dev(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
+                                    const uint8_t *tables, const int32_t *probes, int Q, int P,
+                                    const int64_t *seg_addr, const int64_t *cm_home, int q_per_rank, int64_t max_chunks_per_query,
+                                    int order, int signd, void *workspace, int64_t workspace_bytes, void *stream);
 TKB_API int tkb_ivf_replay_fresh_cm_dev(const uint8_t *est, const int64_t *seg_off, const uint8_t *cmin, const int64_t *list_chunk_off,
                                 const int32_t *list_size, int n_lists, const int64_t *ids,
                                 const int32_t *probes, int Q, int P,

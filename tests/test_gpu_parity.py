@@ -802,7 +802,7 @@ def test_ivf_build_device_encoding_equals_host_build():
     a = tinyknn.IVF("angular", 20, tinyknn.FastPQ(2)).fit(X)
     import copy
     b = copy.deepcopy(a)
-    a.build(X, n_probes=2, device=True)
+    a.build(X, n_probes=2, device=True, assign_device=False)
     b.build(X, n_probes=2, device=False)
     assert a.pq_transformed_centers.size == b.pq_transformed_centers.size
     for ta, tb, ia, ib in zip(a.pq_transformed_points, b.pq_transformed_points, a.ids, b.ids):

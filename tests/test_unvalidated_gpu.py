@@ -1,0 +1,109 @@
+"""GPU tests of code written AFTER round 1's GPU budget was spent: none of this has run on hardware yet, so the file is
+skipped unless TKB_RUN_UNVALIDATED=1 (first thing to run next round: `TKB_RUN_UNVALIDATED=1 pytest tests/test_unvalidated_gpu.py`).
+Covers tkb_assign_dev (IVF.build's coarse assignment) and the chunk minima inside the push exchange."""
+import os
+
+import numpy as np
+import pytest
+
+import tinyknn_b200 as tinyknn
+from oracle import restate as O
+from tinyknn_b200 import _device as D
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("TKB_RUN_UNVALIDATED") != "1", reason="not yet validated on a GPU (TKB_RUN_UNVALIDATED=1 runs it)")]
+
+
+@pytest.mark.parametrize("metric,build_probes", [("angular", 1), ("euclidean", 1), ("angular", 2)])
+def test_ivf_build_device_equals_host_build(metric, build_probes):
+    """IVF.build with the GPU assignment (tkb_assign_dev) and the one-launch GPU encoding (tkb_encode_dev) == the host
+    build: same lists, ids in the same order and identical packed codes for build_probes = 1; for 2 lists per point the
+    same id SETS per list (np.argpartition's column order is unspecified) with the same code per id."""
+    import copy
+    np.random.seed(4)
+    X = np.random.randn(3000, 32).astype(np.float32)
+    a = tinyknn.IVF(metric, 20, tinyknn.FastPQ(2)).fit(X)
+    b = copy.deepcopy(a)
+    a.build(X, n_probes=build_probes, device=True, assign_device=True)
+    b.build(X, n_probes=build_probes, device=False)
+    assert np.array_equal(a.active_centers, b.active_centers)
+    assert a.pq_transformed_centers.size == b.pq_transformed_centers.size
+    assert np.array_equal(a.pq_transformed_centers.packed, b.pq_transformed_centers.packed)
+    for ta, tb, ia, ib in zip(a.pq_transformed_points, b.pq_transformed_points, a.ids, b.ids):
+        if not isinstance(tb, tuple):
+            continue
+        assert ta.size == tb.size
+        if build_probes == 1:
+            assert np.array_equal(ia, ib) and np.array_equal(ta.packed, tb.packed)
+        else:
+            oa, ob = np.argsort(ia, kind="stable"), np.argsort(ib, kind="stable")
+            assert np.array_equal(np.asarray(ia)[oa], np.asarray(ib)[ob])
+            ca, cb = O.unpack(ta.packed)[:ta.size], O.unpack(tb.packed)[:tb.size]
+            assert np.array_equal(ca[oa], cb[ob])
+
+
+@pytest.mark.parametrize("n,d,C,dtype,metric", [(5000, 100, 1087, np.float32, "angular"), (3000, 128, 300, np.float32, "euclidean"),
+                                                (1000, 20, 37, np.float64, "euclidean"), (2000, 384, 64, np.float32, "euclidean"),
+                                                (130, 7, 3, np.float32, "euclidean")])
+def test_assign_device_equals_knn_brute(n, d, C, dtype, metric):
+    """tkb_assign_dev vs the reference's knn_brute arithmetic (oracle restatement): identical nearest centroid for every
+    row (a difference is only tolerated on an exact tie of the reference's own `part` values); k = 2: same pairs."""
+    from tinyknn_b200.utils import knn_brute_device
+    rng = np.random.default_rng(n + d)
+    means = rng.standard_normal((C, d)) * 2
+    X = (means[rng.integers(C, size=n)] + rng.standard_normal((n, d))).astype(dtype)
+    Y = (means + 0.1 * rng.standard_normal((C, d))).astype(dtype)
+    Xr, Yr = (X, Y) if metric == "euclidean" else (X / np.linalg.norm(X, axis=1, keepdims=True), Y / np.linalg.norm(Y, axis=1, keepdims=True))
+    part = np.einsum("ij,ij->i", Xr, Xr)[:, None] + np.einsum("ij,ij->i", Yr, Yr)[None] - 2 * Xr @ Yr.T      # utils.py:80-83
+    exp1 = O.knn_brute(Xr, Yr, 1)[:, 0]
+    got1 = knn_brute_device(X, Y, 1, metric=metric)[:, 0]
+    bad = np.nonzero(got1 != exp1)[0]
+    assert all(part[r, got1[r]] == part[r, exp1[r]] for r in bad) and len(bad) <= 2
+    if C >= 2:
+        exp2 = np.sort(O.knn_brute(Xr, Yr, 2), axis=1)
+        got2 = knn_brute_device(X, Y, 2, metric=metric)
+        assert np.all(part[np.arange(n), got2[:, 0]] <= part[np.arange(n), got2[:, 1]])           # ascending order
+        bad = np.nonzero(np.any(np.sort(got2, axis=1) != exp2, axis=1))[0]
+        assert len(bad) <= 2
+
+
+
+
+def test_push_exchange_with_chunk_minima_single_gpu(monkeypatch):
+    """The push exchange with the minima region, driven rank by rank on one GPU over an index with long lists: every
+    "rank" stores estimates AND chunk minima into the home buffers; the cm replay on the home rank == the unsharded path."""
+    import torch
+    from tinyknn_b200 import synth, ivf as ivf_mod, sharded as SH
+    X = synth.clustered(300_000 + 48, 64, 40, seed=9)
+    ivf = synth.build_ivf(X[:300_000], "euclidean", 12, seed=9)
+    qs = X[300_000:].contiguous()
+    G, k, n_probes = 2, 10, 6
+    Qh = qs.shape[0] // G
+    monkeypatch.setattr(ivf_mod, "CMIN_CHUNKS", 0)
+    ref = ivf.query_batch(qs, k, n_probes=n_probes, order="device", return_distances=True, sub_batches=1)
+    ref_heap = ivf._last["heap_idx"].cpu().numpy()
+    monkeypatch.setattr(ivf_mod, "CMIN_CHUNKS", 1)
+    shards = [SH.ShardedIVF(ivf, rank=r, world=G, drop_full_codes=False) for r in range(G)]
+    homes = [sh._home(qs[r * Qh:(r + 1) * Qh].contiguous(), n_probes) for r, sh in enumerate(shards)]
+    P = homes[0]["P"]
+    tables = torch.cat([h["lut"]["tables"] for h in homes])
+    probes = torch.cat([h["probes"] for h in homes])
+    cap = shards[0].push_capacity(Qh, P)
+    bufs = [SH.PeerBuffers(cap, rank=0, world=1, n_buf=1) for _ in range(G)]
+    try:
+        addr = np.array([b.local[0].address for b in bufs], dtype=np.int64)
+        home_base = D.upload(addr)
+        cm_table = D.upload(addr + bufs[0].nbytes - (addr >> 4))
+        for sh in shards:
+            sh._scan_push(tables, probes, Qh, P, home_base, cm_table)
+        for b, sh in enumerate(shards):
+            seg_r, gb = ivf._plan(sh.dev, homes[b]["probes"], Qh, P)
+            total = int(gb.cpu().numpy()[1])
+            ids, cnt, dst = sh._finish(homes[b], bufs[b].local[0], seg_r, k, (n_probes + 1) * k + 1, bufs[b].local_cmin[0])
+            sl = slice(b * Qh, (b + 1) * Qh)
+            assert np.array_equal(ivf._last["heap_idx"].cpu().numpy(), ref_heap[sl])
+            assert np.array_equal(ids.cpu().numpy(), ref[0][sl]) and np.array_equal(dst.cpu().numpy(), ref[2][sl])
+            assert total // 16 > 1024 * Qh                              # streams long enough for the cm rounds
+    finally:
+        for b in bufs:
+            b.close()

@@ -38,6 +38,7 @@ SIGNATURES = {
     "tkb_peer_close": [_vp],
     "tkb_peer_free": [_vp],
     "tkb_encode_dev": [_vp, _i, _i64, _i, _vp, _i64, _vp, _vp, _i, _i, _vp, _i, _vp, _vp],
+    "tkb_assign_dev": [_vp, _i, _i64, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp],
     "tkb_codes_to_native_dev": [_vp, _i64, _i, _vp, _vp],
     "tkb_codes_from_native_dev": [_vp, _i64, _i, _vp, _vp],
     "tkb_estimate_native_dev": [_vp, _i64, _i, _vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp],
@@ -48,6 +49,7 @@ SIGNATURES = {
     "tkb_replay_fresh_dev": [_vp, _i64, _i64, _i, _vp, _vp, _i, _i, _i, _vp],
     "tkb_ivf_replay_fresh_dev": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
     "tkb_ivf_scan_native_cm_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp],
+    "tkb_ivf_scan_native_push_cm_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i64, _i, _i, _vp, _i64, _vp],
     "tkb_ivf_replay_fresh_cm_dev": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
     "tkb_gather_dists_dev": [_vp, _i, _i64, _i, _vp, _vp, _i, _i, _vp, _vp],
     "tkb_select_probes_dev": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],

@@ -263,6 +263,12 @@ int tkb_encode_dev(const void *rows, int rows_dtype, int64_t n_rows, int d, cons
                          (cudaStream_t)stream);
 }
 
+int tkb_assign_dev(const void *rows, int dtype, int64_t n, int d, const void *centers, int C, const void *xnorm,
+                   const void *cnorm, int k, int32_t *nearest, void *scratch, int64_t scratch_bytes, void *stream)
+{
+    return launch_assign(rows, dtype, n, d, centers, C, xnorm, cnorm, k, nearest, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
 int tkb_codes_to_native_dev(const uint64_t *codes, int64_t n_chunks, int M, void *native, void *stream)
 {
     return launch_codes_to_native(codes, n_chunks, M, native, (cudaStream_t)stream);
@@ -335,6 +341,17 @@ int tkb_ivf_scan_native_cm_dev(const void *native, const int64_t *list_chunk_off
     TKB_REQUIRE(cmin && (uintptr_t)cmin % 16 == 0, "cmin must be a 16-byte aligned device buffer");
     return launch_ivf_scan_native(native, list_chunk_off, list_size, n_lists, M, tables, probes, Q, P, est, 0, seg_off,
                                   max_chunks_per_query, order, signd, workspace, workspace_bytes, (cudaStream_t)stream, cmin);
+}
+
+int tkb_ivf_scan_native_push_cm_dev(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
+                                    const uint8_t *tables, const int32_t *probes, int Q, int P,
+                                    const int64_t *seg_addr, const int64_t *cm_home, int q_per_rank, int64_t max_chunks_per_query,
+                                    int order, int signd, void *workspace, int64_t workspace_bytes, void *stream)
+{
+    TKB_REQUIRE(seg_addr && cm_home, "null pointer");
+    return launch_ivf_scan_native(native, list_chunk_off, list_size, n_lists, M, tables, probes, Q, P, nullptr, 0, seg_addr,
+                                  max_chunks_per_query, order, signd, workspace, workspace_bytes, (cudaStream_t)stream, nullptr,
+                                  cm_home, q_per_rank);
 }
 
 int tkb_ivf_replay_fresh_cm_dev(const uint8_t *est, const int64_t *seg_off, const uint8_t *cmin, const int64_t *list_chunk_off,

@@ -108,6 +108,8 @@ int launch_ivf_plan(const int32_t *probes, int Q, int P, const int32_t *list_siz
 int launch_encode(const void *rows, int rows_dtype, int64_t n_rows, int d, const int64_t *row_index, int64_t n_out,
                   const float *centers, const float *cnorm, int Dp, int dpb, const double *R, int Dpad, uint64_t *codes,
                   cudaStream_t st);
+int launch_assign(const void *rows, int dtype, int64_t n, int d, const void *centers, int C, const void *xnorm,
+                  const void *cnorm, int k, int32_t *nearest, void *scratch, int64_t scratch_bytes, cudaStream_t st);
 int launch_codes_to_native(const uint64_t *ref, int64_t n_chunks, int M, void *native, cudaStream_t st);
 int launch_codes_from_native(const void *native, int64_t n_chunks, int M, uint64_t *ref, cudaStream_t st);
 int launch_estimate_native(const void *native, int64_t n_chunks, int M, const uint8_t *tables, int Q, uint8_t *est,
@@ -116,7 +118,8 @@ int launch_estimate_native(const void *native, int64_t n_chunks, int M, const ui
 int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                            const uint8_t *tables, const int32_t *probes, int Q, int P, uint8_t *est,
                            int64_t slot_stride, const int64_t *seg_off, int64_t max_chunks_per_query, int order, int signd,
-                           void *workspace, int64_t workspace_bytes, cudaStream_t st, uint8_t *cmin = nullptr);
+                           void *workspace, int64_t workspace_bytes, cudaStream_t st, uint8_t *cmin = nullptr,
+                           const int64_t *cm_home = nullptr, int q_per_rank = 0);
 int launch_heap_fill(int64_t *heap_idx, int32_t *heap_val, int64_t count, int signd, cudaStream_t st);
 int launch_replay(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n, int64_t *heap_idx,
                   int32_t *heap_val, int Q, int R, int signd, const int64_t *labels, cudaStream_t st);

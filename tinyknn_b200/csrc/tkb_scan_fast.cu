@@ -224,13 +224,16 @@ ivf_scan_fast_kernel(const uint4 *__restrict__ nat, const int64_t *__restrict__ 
                      const int32_t *__restrict__ list_size, int n_lists, int M,
                      const uint8_t *__restrict__ tables, const int32_t *__restrict__ probes, int P,
                      uint8_t *__restrict__ est, int64_t slot_stride, const int64_t *__restrict__ seg_off,
-                     unsigned long long *stat, int keep, uint8_t *__restrict__ cmin)
+                     unsigned long long *stat, int keep, uint8_t *__restrict__ cmin,
+                     const int64_t *__restrict__ cm_home, int q_per_rank, int q_base)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     ScanSmem sm;
     scan_smem_carve(smem, M, P, &sm);
     sm.keep = keep;
-    sm.cmin = cmin;
+    // push exchange: est offsets are absolute addresses inside the home rank's buffer; its minima region is addressed as
+    // cm_home[home rank] + (address >> 4) (the table holds minima base - (est base >> 4), per home rank)
+    sm.cmin = cm_home ? reinterpret_cast<uint8_t *>(cm_home[(q_base + (int)blockIdx.y) / q_per_rank]) : cmin;
     const int q = blockIdx.y, Ph = M >> 1;
     if (threadIdx.x == 0) {
         *sm.n_pend = 0;
@@ -384,11 +387,13 @@ int launch_estimate_native(const void *native, int64_t n_chunks, int M, const ui
 int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                            const uint8_t *tables, const int32_t *probes, int Q, int P, uint8_t *est,
                            int64_t slot_stride, const int64_t *seg_off, int64_t max_chunks_per_query, int order, int signd,
-                           void *workspace, int64_t workspace_bytes, cudaStream_t st, uint8_t *cmin)
+                           void *workspace, int64_t workspace_bytes, cudaStream_t st, uint8_t *cmin,
+                           const int64_t *cm_home, int q_per_rank)
 {
     if (int rc = check_fast_args(M, order)) return rc;
     TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists > 0, "bad extent");
     TKB_REQUIRE(!cmin || (est && seg_off), "chunk minima need a compact plan relative to est");
+    TKB_REQUIRE(!cm_home || (!est && seg_off && q_per_rank > 0 && !cmin), "per-home minima tables belong to the push exchange (est == NULL)");
     if (Q == 0 || P == 0 || (slot_stride == 0 && !seg_off)) return TKB_OK;
     // est == NULL with a plan: the plan holds absolute addresses (TKB_PLAN_PUSH: segments land in the receive buffers of
     // the queries' home ranks, peer-mapped over NVLink)
@@ -426,10 +431,10 @@ int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, co
         uint8_t *eb = seg_off ? est : est + (size_t)q0 * P * slot_stride;
         if (order == TKB_ORDER_AVX && signd)
             TKB_DISPATCH_FAST_AVXS(ivf_scan_fast_kernel, grid, scan_threads, smem, st, n4, list_chunk_off, list_size, n_lists, M,
-                                   tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep, cmin);
+                                   tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep, cmin, cm_home, q_per_rank, q0);
         else
             TKB_DISPATCH_FAST(ivf_scan_fast_kernel, grid, scan_threads, smem, st, n4, list_chunk_off, list_size, n_lists, M,
-                              tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep, cmin);
+                              tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep, cmin, cm_home, q_per_rank, q0);
         TKB_LAUNCH_CHECK();
     }
     return TKB_OK;

@@ -26,7 +26,7 @@ from . import _device as D
 from . import fast_pq as _fp
 from ._lib import lib, check, DTYPE_F32, DTYPE_F64, PROBE_SKIP, PLAN_SEND, PLAN_RECV  # noqa: F401
 from .fast_pq import FastPQ, TransformedData, query_pq  # noqa: F401  (ivf.py:5 re-export)
-from .utils import timer, knn_brute, group_data_by_indices, bottom_k
+from .utils import timer, knn_brute, knn_brute_device, group_data_by_indices, bottom_k
 
 _WORKSPACE_BYTES = 2 << 30          # cap of the per-batch estimate buffer (queries are sub-batched); see _workspace_cap
 _N_STREAMS = int(os.environ.get("TKB_STREAMS", "2"))
@@ -37,6 +37,8 @@ FUSED = os.environ.get("TKB_FUSED", "0") != "0"
 # Chunk minima (tkb_ivf_scan_native_cm_dev / tkb_ivf_replay_fresh_cm_dev) when a query may scan at least this many chunks:
 # the replay of long probe lists then reads 1 byte per chunk instead of 16. 0 disables.
 CMIN_CHUNKS = int(os.environ.get("TKB_CMIN_CHUNKS", "8192"))
+# IVF.build: coarse assignment on the GPU (tkb_assign_dev). Opt-in until it has been validated on hardware.
+ASSIGN_DEVICE = os.environ.get("TKB_ASSIGN_DEVICE", "0") != "0"
 _streams = {}
 _ws_cap = {}
 
@@ -94,7 +96,7 @@ class IVF:
             self.pq.fit(X, verbose=verbose)
         return self
 
-    def build(self, X, n_probes=2, verbose=False, device=None):
+    def build(self, X, n_probes=2, verbose=False, device=None, assign_device=None):
         """Put every point into the lists of its n_probes nearest centroids (ref: ivf.py:53-104).
         device=None: the PQ encoding of all lists runs as ONE `tkb_encode_dev` launch when a GPU is present (rows gathered
         list by list, every list padded to 16 with zero vectors like FastPQ.transform does), else list by list on the host."""
@@ -103,16 +105,21 @@ class IVF:
         self.data = data = X.copy()
         if self.metric == "angular":
             data /= np.linalg.norm(data, axis=1, keepdims=True)
+        if device is None:
+            device = D.torch().cuda.is_available()
         with timer(verbose, "Computing nearest clusters..."):
-            nearest = knn_brute(data, self.all_centers, k=n_probes, metric=self.metric)
+            if assign_device is None:
+                assign_device = ASSIGN_DEVICE
+            if device and assign_device and n_probes <= 2 and data.dtype in (np.float32, np.float64):
+                nearest = knn_brute_device(data, self.all_centers, k=n_probes, metric=self.metric)      # tkb_assign_dev
+            else:
+                nearest = knn_brute(data, self.all_centers, k=n_probes, metric=self.metric)
         with timer(verbose, "PQ Transforming active centers..."):
             self.active_centers = np.ascontiguousarray(self.all_centers[np.unique(nearest)], dtype=np.float32)
             self.pq_transformed_centers = self.pq.transform(self.active_centers)
         with timer(verbose, "Transforming points..."):
             n_active = self.active_centers.shape[0]
             groups, self.ids = group_data_by_indices(data, nearest, n_active)
-            if device is None:
-                device = D.torch().cuda.is_available()
             if device and data.dtype in (np.float32, np.float64):
                 self._encode_lists_device(data, groups)
             else:
@@ -338,7 +345,8 @@ class IVF:
         self._last = dict(center_heap=hci, tables=tables)
         return probes
 
-    def _scan(self, dev, tables, probes, Q, P, est, seg_off, codes_key="codes", off_key="list_chunk_off", cmin=None):
+    def _scan(self, dev, tables, probes, Q, P, est, seg_off, codes_key="codes", off_key="list_chunk_off", cmin=None,
+              push_cm=None):
         """Estimates of every (query, probed list) segment present in `seg_off` (ref: the scan half of
         query_pq_*, ivf.py:142-150), written compactly into `est`."""
         st = D.stream_ptr()
@@ -350,7 +358,11 @@ class IVF:
         with self._stage("scan"):
             if _fp.SCAN_IMPL == "fast":
                 ws = D.scan_workspace(min(Q * max_q_chunks, max(1 << 20, Q * max_q_chunks // 4)))
-                if cmin is not None:
+                if push_cm is not None:                                  # (per-home minima table, queries per rank)
+                    check(lib.tkb_ivf_scan_native_push_cm_dev(D.ptr(dev[codes_key]), D.ptr(dev[off_key]), D.ptr(dev["list_size"]), n_lists, M,
+                                                              D.ptr(tables), D.ptr(probes), Q, P, D.ptr(seg_off), D.ptr(push_cm[0]), push_cm[1],
+                                                              max_q_chunks, _fp._order(), 1, D.ptr(ws), ws.numel(), st))
+                elif cmin is not None:
                     check(lib.tkb_ivf_scan_native_cm_dev(D.ptr(dev[codes_key]), D.ptr(dev[off_key]), D.ptr(dev["list_size"]), n_lists, M,
                                                          D.ptr(tables), D.ptr(probes), Q, P, D.ptr(est), D.ptr(seg_off), D.ptr(cmin),
                                                          max_q_chunks, _fp._order(), 1, D.ptr(ws), ws.numel(), st))

@@ -38,6 +38,9 @@ from ._lib import PLAN_SEND, PLAN_RECV, PLAN_PUSH, PROBE_SKIP
 
 # default exchange of ShardedIVF.query_batch: "push" (NVLink peer stores from the scan kernel) or "nccl" (all-to-all)
 EXCHANGE = os.environ.get("TKB_EXCHANGE", "push")
+# chunk minima inside the push exchange (the home buffer carries a minima region). Opt-in: written after round 1's GPU
+# budget was spent, not yet run on hardware (tests/test_unvalidated_gpu.py).
+PUSH_CMIN = os.environ.get("TKB_PUSH_CMIN", "0") != "0"
 
 
 def assign_owners(list_sizes, n_ranks):
@@ -169,14 +172,17 @@ class PeerBuffers:
         import ctypes
         from ._lib import lib, check
         t = D.require_cuda()
-        self.nbytes, self.rank, self.world, self.n_buf = int(nbytes), rank, world, n_buf
-        self.local, self._opened = [], []
+        nbytes = -(-int(nbytes) // 256) * 256
+        self.nbytes, self.rank, self.world, self.n_buf = nbytes, rank, world, n_buf
+        self.local, self.local_cmin, self._opened = [], [], []
         handles = np.zeros((n_buf, 64), dtype=np.uint8)
         for b in range(n_buf):
             p = ctypes.c_void_p()
             h = (ctypes.c_ubyte * 64)()
-            check(lib.tkb_peer_alloc(self.nbytes, ctypes.byref(p), h))
+            # one allocation = [estimates: nbytes][chunk minima: nbytes / 16 + 16]
+            check(lib.tkb_peer_alloc(self.nbytes + self.nbytes // 16 + 16, ctypes.byref(p), h))
             self.local.append(_Raw(p.value, self.nbytes))
+            self.local_cmin.append(_Raw(p.value + self.nbytes, self.nbytes // 16 + 16))
             handles[b] = np.frombuffer(h, dtype=np.uint8)
         addr = np.zeros((n_buf, world), dtype=np.int64)
         addr[:, rank] = [x.address for x in self.local]
@@ -192,6 +198,8 @@ class PeerBuffers:
                     self._opened.append(p.value)
                     addr[b, g] = p.value
         self.bases = [D.upload(addr[b]) for b in range(n_buf)]
+        # minima region of home rank g, addressed by the scan as table[g] + (absolute estimate address >> 4)
+        self.cm_tables = [D.upload(addr[b] + self.nbytes - (addr[b] >> 4)) for b in range(n_buf)]
         self.flag = t.zeros(1, dtype=t.int32, device=D.device())
         self.turn = 0
 
@@ -271,7 +279,7 @@ class ShardedIVF:
         ivf._scan(dev, tables, probes, Q, P, est_s, seg_s, codes_key="local_codes", off_key="local_chunk_off")
         return est_s, splits[0, :G], seg_r, splits[1, :G]
 
-    def _scan_push(self, tables, probes, Qh, P, home_base):
+    def _scan_push(self, tables, probes, Qh, P, home_base, cm_table=None):
         """Fused scan + exchange: scan, for ALL G*Qh queries, of the probed lists this rank owns, every estimate chunk
         stored directly at its place in the home rank's receive buffer (`home_base`: device int64[G] of addresses
         valid in this process). Returns the per-home buffer sizes (device int64[G])."""
@@ -285,7 +293,8 @@ class ShardedIVF:
             check(lib.tkb_ivf_plan_push_dev(D.ptr(probes), Q, P, D.ptr(dev["list_size"]), D.ptr(dev["list_owner"]), dev["n_lists"],
                                             r, G, Qh, D.ptr(home_base), D.ptr(seg), D.ptr(gb), D.ptr(ws), 8 * ws.numel(),
                                             D.stream_ptr()))
-        ivf._scan(dev, tables, probes, Q, P, None, seg, codes_key="local_codes", off_key="local_chunk_off")
+        ivf._scan(dev, tables, probes, Q, P, None, seg, codes_key="local_codes", off_key="local_chunk_off",
+                  push_cm=None if cm_table is None else (cm_table, Qh))
         return gb[:G]
 
     def push_capacity(self, Qh, P):
@@ -314,10 +323,10 @@ class ShardedIVF:
         self.__dict__["_pb"] = pb = PeerBuffers(need, self.group, self.rank, self.world)
         return pb
 
-    def _finish(self, home, est_r, seg_r, k, pass_1):
+    def _finish(self, home, est_r, seg_r, k, pass_1, cmin_r=None):
         """Ordered heap replay over the received estimates, exact rescoring, k nearest (device tensors)."""
         return self.ivf._replay_rescore(self.dev, home["lut"]["q"], home["probes"], home["Qh"], home["P"], k, pass_1,
-                                        est_r, seg_r, "device")
+                                        est_r, seg_r, "device", cmin=cmin_r)
 
     def query_batch(self, queries, k, n_probes=1, pass_1=None, return_distances=False, to_host=True, exchange=None):
         """Collective. queries: this rank's f32 (Qh, d) block (same Qh on every rank). Selections use the
@@ -343,10 +352,14 @@ class ShardedIVF:
             b = pb.turn
             pb.turn = (b + 1) % pb.n_buf
             seg_r, _ = ivf._plan(self.dev, home["probes"], Qh, P)                # the single-GPU layout of my own queries
-            self._scan_push(tables, probes, Qh, P, pb.bases[b])
+            from . import ivf as _ivf_mod
+            use_cm = (PUSH_CMIN and _ivf_mod.CMIN_CHUNKS > 0
+                      and P * max(self.dev["max_real_chunks"], 1) >= _ivf_mod.CMIN_CHUNKS)
+            self._scan_push(tables, probes, Qh, P, pb.bases[b], pb.cm_tables[b] if use_cm else None)
             with ivf._stage("barrier"):                                         # every rank's scan kernel has completed
                 dist.all_reduce(pb.flag, group=self.group)
             est_r = pb.local[b]
+            cmin_r = pb.local_cmin[b] if use_cm else None
         else:
             est_s, send_splits, seg_r, recv_splits = self._scan_owned(tables, probes, Qh, P)
             if G > 1:
@@ -354,7 +367,8 @@ class ShardedIVF:
                     est_r = all_to_all_bytes(est_s, send_splits, recv_splits, self.group)
             else:
                 est_r = est_s
-        ids, cnt, dst = self._finish(home, est_r, seg_r, k, pass_1)
+            cmin_r = None
+        ids, cnt, dst = self._finish(home, est_r, seg_r, k, pass_1, cmin_r)
         if to_host:
             ids, cnt, dst = ids.cpu().numpy(), cnt.cpu().numpy(), dst.cpu().numpy()
         return (ids, cnt, dst) if return_distances else (ids, cnt)

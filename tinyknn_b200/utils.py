@@ -113,3 +113,27 @@ def group_data_by_indices(X, indices, k):
             part.append(np.empty((0, X.shape[1])))
             id_list.append(np.empty(0))
     return [np.vstack(p) for p in parts], [np.hstack(i) for i in ids]
+
+
+def knn_brute_device(X, Y, k, metric="euclidean"):
+    """knn_brute (ref: utils.py:66-86) for k in {1, 2} with the rows x centroids contraction on the GPU (`tkb_assign_dev`).
+    The norms are numpy's own (np.einsum, as in the reference), the dot products are the FMA chain the reference's BLAS
+    computes, so for k = 1 the result equals knn_brute's wherever the minimum is unique; for k = 2 each row holds the
+    same two indices in ascending-distance order (np.argpartition's order is unspecified). Returns int (n, k)."""
+    from . import _device as D
+    from ._lib import lib, check, DTYPE_F32, DTYPE_F64
+    assert 1 <= k <= 2 and k <= Y.shape[0], f"Can't find knn with {k=} and {Y.shape[0]} targets."
+    if metric == "angular":
+        X = X / np.linalg.norm(X, axis=1, keepdims=True)
+        Y = Y / np.linalg.norm(Y, axis=1, keepdims=True)
+    elif metric != "euclidean":
+        raise ValueError(f"Metric not supported: {metric}")
+    T = np.result_type(X.dtype, Y.dtype)
+    T = np.float32 if T == np.float32 else np.float64
+    xn = _sqnorms(X).astype(T)                       # Xnorm2 / Ynorm2 in their own dtypes, promoted like numpy would
+    yn = _sqnorms(Y).astype(T)
+    Xd, Yd = D.upload(np.ascontiguousarray(X, dtype=T)), D.upload(np.ascontiguousarray(Y, dtype=T))
+    out = D.empty((X.shape[0], k), np.int32)
+    check(lib.tkb_assign_dev(D.ptr(Xd), DTYPE_F32 if T == np.float32 else DTYPE_F64, X.shape[0], X.shape[1], D.ptr(Yd),
+                             Y.shape[0], D.ptr(D.upload(xn)), D.ptr(D.upload(yn)), k, D.ptr(out), None, 0, D.stream_ptr()))
+    return out.cpu().numpy().astype(int)
