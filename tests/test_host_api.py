@@ -186,3 +186,73 @@ def test_fit_transform_host_side_and_pickle():
         tinyknn.FastPQ(2).fit(np.zeros((0, 4), np.float32))
     with pytest.raises(AssertionError):
         tinyknn.IVF("manhattan", 3)
+
+
+def test_index_save_load_round_trip(tmp_path):
+    """Stable on-disk format (tinyknn_b200/io.py): every attribute the query path and the oracle read survives a
+    save/load, memory-mapped or not; lists are views into one codes / ids file; empty and never-filled lists keep
+    their reference representation; a half-written directory (no meta.json) and a foreign dpad are refused."""
+    from tinyknn_b200 import fast_pq as fp
+    np.random.seed(3)
+    X = np.random.randn(700, 20).astype(np.float32)
+    ivf = tinyknn.IVF("angular", 9, tinyknn.FastPQ(2))
+    ivf.fit(X).build(X, n_probes=2, device=False)
+    ivf.pq_transformed_points.append(None)                         # a slot the build never filled
+    ivf.ids.append(None)
+    ivf.n_clusters += 1
+    path = str(tmp_path / "idx")
+    tinyknn.save_index(ivf, path)
+    for mmap in (True, False):
+        got = tinyknn.load_index(path, mmap=mmap)
+        assert got.metric == ivf.metric and got.n_clusters == ivf.n_clusters
+        assert got.pq.dims_per_block == 2 and got.pq.rotate_dim == ivf.pq.rotate_dim and got.pq.use_kmeans == ivf.pq.use_kmeans
+        assert got.pq.sqrt_n_blocks == ivf.pq.sqrt_n_blocks
+        for name in ("centers", "R"):
+            assert np.array_equal(getattr(got.pq, name), getattr(ivf.pq, name))
+        assert np.array_equal(got.all_centers, ivf.all_centers) and np.array_equal(got.active_centers, ivf.active_centers)
+        assert got.active_centers.dtype == np.float32 and got.active_centers.flags.c_contiguous
+        assert got.pq_transformed_centers.size == ivf.pq_transformed_centers.size
+        assert np.array_equal(got.pq_transformed_centers.packed, ivf.pq_transformed_centers.packed)
+        assert np.array_equal(got.data, ivf.data)
+        assert len(got.pq_transformed_points) == len(ivf.pq_transformed_points)
+        for a, b, ia, ib in zip(got.pq_transformed_points, ivf.pq_transformed_points, got.ids, ivf.ids):
+            if b is None:
+                assert a is None and ia is None
+            elif not isinstance(b, tuple):
+                assert not isinstance(a, tuple) and a.size == 0
+            else:
+                assert a.size == b.size and a.packed.dtype == np.uint64 and np.array_equal(a.packed, b.packed)
+                assert np.array_equal(ia, ib) and ia.dtype == np.int64
+        pickle.loads(pickle.dumps(got))                            # a loaded index still pickles like the reference's
+    no_data = str(tmp_path / "idx_nodata")
+    tinyknn.save_index(ivf, no_data, include_data=False)
+    assert not os.path.exists(os.path.join(no_data, "data.npy"))
+    assert np.array_equal(tinyknn.load_index(no_data, data=ivf.data).data, ivf.data)
+    os.remove(os.path.join(no_data, "meta.json"))
+    with pytest.raises(FileNotFoundError):
+        tinyknn.load_index(no_data)
+    fp.set_order("sse")
+    try:
+        with pytest.raises(ValueError):
+            tinyknn.load_index(path)
+    finally:
+        fp.set_order("avx")
+
+
+def test_loaded_index_is_queried_identically_by_the_oracle(tmp_path):
+    """The on-disk format keeps the reference's attribute types: the CPU oracle answers from a memory-mapped index
+    exactly as from the original."""
+    from oracle import restate as O
+    np.random.seed(5)
+    X = np.random.randn(900, 24).astype(np.float32)
+    ivf = tinyknn.IVF("euclidean", 8, tinyknn.FastPQ(2))
+    ivf.fit(X).build(X, n_probes=1, device=False)
+    path = tinyknn.save_index(ivf, str(tmp_path / "idx"))
+    got = tinyknn.load_index(path)
+    K = O.Kernels("port", "avx")
+    Sa, Sb = O.IVFState.from_ivf(ivf), O.IVFState.from_ivf(got)
+    for q in np.random.randn(12, 24).astype(np.float32):
+        ta, tb = {}, {}
+        a = O.ivf_query(Sa, q, 5, n_probes=3, kernels=K, trace=ta)
+        b = O.ivf_query(Sb, q, 5, n_probes=3, kernels=K, trace=tb)
+        assert np.array_equal(a, b) and np.array_equal(ta["heap_indices"], tb["heap_indices"])

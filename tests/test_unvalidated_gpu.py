@@ -107,3 +107,15 @@ def test_push_exchange_with_chunk_minima_single_gpu(monkeypatch):
     finally:
         for b in bufs:
             b.close()
+
+
+def test_saved_index_answers_identically(tmp_path):
+    """save_index / load_index (memory-mapped) -> to_device -> query_batch == the original index."""
+    np.random.seed(6)
+    X = np.random.randn(4000, 32).astype(np.float32)
+    qs = np.random.randn(64, 32).astype(np.float32)
+    ivf = tinyknn.IVF("euclidean", 16, tinyknn.FastPQ(2)).fit(X[:2000]).build(X, n_probes=1)
+    got = tinyknn.load_index(tinyknn.save_index(ivf, str(tmp_path / "idx")))
+    a = ivf.query_batch(qs, 10, n_probes=4, order="device", return_distances=True)
+    b = got.query_batch(qs, 10, n_probes=4, order="device", return_distances=True)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))

@@ -10,6 +10,7 @@ from .fast_pq import FastPQ, avx
 from .ivf import IVF
 from . import utils
 from .utils import bottom_k, bottom_k_2d, cdist, knn_brute, group_data_by_indices
+from .io import save_index, load_index          # additive: stable on-disk index format (not part of the reference's exports)
 
 __all__ = ["FastPQ", "IVF", "avx", "utils", "bottom_k", "bottom_k_2d", "cdist", "knn_brute",
            "group_data_by_indices", "_transform", "_fast_pq", "_fast_pq_avx"]
