@@ -179,6 +179,15 @@ class ClockSampler:
         return out
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """Phase timestamps on stderr (TKB_BENCH_LOG=1): where a long run spends its wall-clock, per rank."""
+    if os.environ.get("TKB_BENCH_LOG", "0") != "0":
+        print("[bench rank %s +%.1fs] %s" % (os.environ.get("RANK", "0"), time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
+
+
 def build_index(args, torch, seed=10):
     from tinyknn_b200 import synth
     w = WORKLOADS[args.workload]
@@ -222,7 +231,9 @@ def main():
     import tinyknn_b200 as tinyknn                      # noqa: F401
     from tinyknn_b200 import _lib
     tinyknn.fast_pq.set_order(args.order)
+    log("building the synthetic index")
     ivf, qpool = build_index(args, torch)
+    log("index built")
     Qn = args.queries
     batches = [np.ascontiguousarray(qpool[i * Qn:(i + 1) * Qn]) for i in range(4)]
 
@@ -257,6 +268,7 @@ def main():
         # block of queries: a different slice of the query pool per rank, the same number on every rank
         from tinyknn_b200.sharded import ShardedIVF
         engine = ShardedIVF(ivf)
+        log("lists sharded")
         roll = rank * 4 * Qn // world
         dev_batches = [torch.roll(b, roll, 0) for b in dev_batches]
         pinned = [torch.roll(b, roll, 0).pin_memory() for b in pinned]
@@ -298,9 +310,11 @@ def main():
         if rank == 0:
             parity["sharded_vs_single_gpu_mismatching_ranks"] = int(flag.item())
 
+    log("parity gate done")
     for i in range(args.warmup):
         run(dev_batches[i % 4], to_host=False)
     sync_all()
+    log("warm-up done")
     # -- value: inputs resident in HBM
     calls0 = _lib.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None

@@ -203,14 +203,20 @@ class PeerBuffers:
         self.flag = t.zeros(1, dtype=t.int32, device=D.device())
         self.turn = 0
 
-    def close(self):
+    def close(self, group=None):
+        """Collective when world > 1: every rank unmaps its peers' buffers, THEN (after a barrier) frees its own -- an
+        exporter must not free memory that another process still has mapped."""
         from ._lib import lib
         D.torch().cuda.synchronize()
         for p in self._opened:
             lib.tkb_peer_close(p)
+        self._opened = []
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=group)
         for x in self.local:
             lib.tkb_peer_free(x.address)
-        self._opened, self.local = [], []
+        self.local, self.local_cmin = [], []
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -319,7 +325,7 @@ class ShardedIVF:
         if not int(fits.item()):
             return None
         if pb is not None:
-            pb.close()
+            pb.close(self.group)
         self.__dict__["_pb"] = pb = PeerBuffers(need, self.group, self.rank, self.world)
         return pb
 
