@@ -1,0 +1,8 @@
+#!/bin/bash
+# FIRST GPU call of the next round (one GPU): the tests that were written after round 1's GPU budget was spent, then the
+# regular suite, smoke, and the default bench. Usage (from the repo root, under gpurun): bash tools/gpu_next.sh <tag>
+tag=${1:-next}; out=gpurun_out/$tag; mkdir -p $out
+TKB_RUN_UNVALIDATED=1 timeout 900 python -m pytest tests/test_unvalidated_gpu.py -q > $out/pytest_unvalidated.log 2>&1; tail -25 $out/pytest_unvalidated.log
+timeout 1200 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; tail -5 $out/pytest_gpu.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1; tail -2 $out/smoke.log
+timeout 900 python bench.py --steps 20 --warmup 3 > $out/bench.json 2> $out/bench.err; tail -c 2500 $out/bench.json; tail -3 $out/bench.err
