@@ -427,7 +427,7 @@ def main():
                                   % min(args.steps, 10),
                     stage_ms={k: per_step(v) for k, v in stages.items()})
         cb = None
-        if not args.no_cpu_baseline and isinstance(ivf.data, np.ndarray):
+        if not args.no_cpu_baseline and world == 1 and isinstance(ivf.data, np.ndarray):      # rank 0 at N=1 only
             cb = run_cpu_arm(ivf, batches[0], args.n_probes, args.k, args.cpu_seconds, os.cpu_count() or 1)[0]
         line = dict(metric="IVF-PQ queries/s", value=value, unit="queries/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
