@@ -119,3 +119,35 @@ def test_saved_index_answers_identically(tmp_path):
     a = ivf.query_batch(qs, 10, n_probes=4, order="device", return_distances=True)
     b = got.query_batch(qs, 10, n_probes=4, order="device", return_distances=True)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_glove_shape_full_size_properties():
+    """BASELINE.json configs[1] at full size (1 183 514 x 100, 1087 lists): size-independent properties of the path --
+    idempotence, sub-batching and the fused kernel give the same answers, ids == oracle (reference selection order) on a
+    sample, and every estimate of a whole-database brute-force scan == the C oracle (61 M lookups per query)."""
+    from tinyknn_b200 import synth
+    n, nq = 1_183_514, 2048
+    X = synth.clustered(n + nq, 100, 2000, seed=10)
+    ivf = synth.build_ivf(X[:n], "angular", 1087, seed=10)
+    qs = X[n:].contiguous()
+    kw = dict(k=10, n_probes=10, order="device", return_distances=True)
+    a = ivf.query_batch(qs, **kw)
+    for other in (ivf.query_batch(qs, **kw), ivf.query_batch(qs, sub_batches=1, **kw), ivf.query_batch(qs, sub_batches=1, fused=True, **kw)):
+        assert all(np.array_equal(x, y) for x, y in zip(a, other))
+    assert (a[1] == 10).all() and (np.diff(a[2], axis=1) >= 0).all()          # k results each, ascending distances
+    S = O.IVFState.from_ivf(ivf)
+    K = O.Kernels("port", "avx")
+    qh = qs.cpu().numpy()
+    ids, cnt = ivf.query_batch(qh[:32], 10, n_probes=10, order="numpy")
+    for i in range(32):
+        assert set(ids[i][:cnt[i]]) == set(O.ivf_query(S, qh[i], 10, n_probes=10, kernels=K))
+    # whole database, one list after the other, through FastPQ's own brute-force entry point
+    packed = np.concatenate([td.packed for td in ivf.pq_transformed_points if isinstance(td, tuple)])
+    td_all = tinyknn.fast_pq.TransformedData(16 * len(packed), packed)
+    for i in range(2):
+        q = qh[i] / np.linalg.norm(qh[i])
+        dt = ivf.pq.distance_table(q)
+        est = dt.estimate_distances(td_all)
+        exp = np.zeros(2 * len(packed), np.uint64)
+        O.estimate_pq(packed, np.ascontiguousarray(dt.tables), exp, True, "avx")
+        assert np.array_equal(est.view(np.uint8), exp.view(np.uint8)[:len(est)])
