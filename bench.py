@@ -200,6 +200,9 @@ def build_index(args, torch, seed=10):
 
 def main():
     args = parse()
+    if os.environ.get("TKB_BENCH_WATCHDOG"):            # seconds: dump every thread's Python stack periodically (where is a rank stuck?)
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["TKB_BENCH_WATCHDOG"]), repeat=True, file=sys.stderr)
     if args.cpu_worker:
         return cpu_worker(*args.cpu_worker)
     global ORDER
