@@ -250,3 +250,70 @@ def test_encode_restatement_matches_reference_package():
         td = pq.transform(X[:77])
         n, packed = O.pq_transform(O.PQState.from_pq(pq), X[:77])
         assert n == td.size and np.array_equal(packed, td.packed)
+
+
+# ---- the arithmetic the build-time CUDA kernels implement, stated in scalar C and pinned against numpy itself -------
+
+def _chain_lib():
+    import ctypes
+    from oracle import build_oracle
+    L = ctypes.CDLL(build_oracle.build_chain())
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    L.tko_dchain.argtypes = L.tko_schain.argtypes = [vp, vp, vp, i64, i32, i32]
+    L.tko_encode_f64.argtypes = L.tko_encode_f32.argtypes = [vp, i64, i32, i32, vp, vp, vp]
+    L.tko_assign_f32.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data
+
+
+def test_numpy_matmul_is_a_sequential_fma_chain():
+    """The assumption tkb_encode.cu / tkb_assign.cu rest on: numpy's `@` (OpenBLAS gemm) computes every output as an FMA
+    chain over the inner dimension in ascending order starting from 0 (one K block: K <= 384 for f32)."""
+    L = _chain_lib()
+    rng = np.random.default_rng(0)
+    for dt, fn, shapes in ((np.float64, L.tko_dchain, [(700, 64, 128), (100, 16, 2), (333, 24, 24)]),
+                           (np.float32, L.tko_schain, [(100, 16, 2), (100, 1087, 100), (100, 300, 128), (100, 64, 384)])):
+        for n, m, K in shapes:
+            a, b = rng.standard_normal((n, K)).astype(dt), rng.standard_normal((m, K)).astype(dt)
+            out = np.empty((n, m), dt)
+            fn(_p(a), _p(b), _p(out), n, m, K)
+            assert np.array_equal(out, a @ b.T), (dt.__name__, n, m, K)
+
+
+def test_scalar_encoder_arithmetic_equals_reference_codes(golden):
+    """tko_encode_* (the arithmetic of tkb_encode.cu, one element at a time) reproduces the reference's packed codes."""
+    L = _chain_lib()
+    z = golden["encode"]
+    for name in z["names"]:
+        X, centers, R = z[name + "_X"], np.ascontiguousarray(z[name + "_centers"]), z[name + "_R"]
+        data = O.pad2(X, 16, 8)
+        if R.size:
+            a = np.ascontiguousarray(data, dtype=np.float64)
+            rot = np.empty((len(a), R.shape[0]), np.float64)
+            L.tko_dchain(_p(a), _p(np.ascontiguousarray(R)), _p(rot), len(a), R.shape[0], R.shape[1])
+            assert np.array_equal(rot, data @ R.T)
+            data = rot
+        Dp = centers.shape[1]
+        M = Dp // 2
+        cn = np.ascontiguousarray(np.stack([np.einsum("ij,ij->i", b, b) for b in centers.reshape(16, M, 2).transpose(1, 0, 2)]), dtype=np.float32)
+        codes = np.empty((len(data), M), np.uint8)
+        data = np.ascontiguousarray(data)
+        (L.tko_encode_f64 if data.dtype == np.float64 else L.tko_encode_f32)(_p(data), len(data), Dp, 2, _p(centers), _p(cn), _p(codes))
+        assert np.array_equal(O.transform_data(codes), z[name + "_packed"]), name
+
+
+def test_scalar_assignment_arithmetic_equals_knn_brute():
+    """tko_assign_f32 (the arithmetic of tkb_assign.cu) == the reference's knn_brute(X, Y, 1) given numpy's own norms."""
+    L = _chain_lib()
+    rng = np.random.default_rng(3)
+    for n, d, C in ((400, 100, 1087), (300, 128, 200), (200, 20, 37)):
+        means = rng.standard_normal((C, d)) * 2
+        X = (means[rng.integers(C, size=n)] + rng.standard_normal((n, d))).astype(np.float32)
+        Y = np.ascontiguousarray(means + 0.1 * rng.standard_normal((C, d)), dtype=np.float32)
+        xn, yn = np.einsum("ij,ij->i", X, X), np.einsum("ij,ij->i", Y, Y)
+        out = np.empty(n, np.int32)
+        L.tko_assign_f32(_p(X), n, d, _p(Y), C, _p(xn), _p(yn), _p(out))
+        assert np.array_equal(out, O.knn_brute(X, Y, 1)[:, 0])
