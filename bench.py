@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
                     help="--shard lists: 'push' = the scan kernel stores estimates into the home rank's HBM over NVLink peer "
                          "memory (falls back to nccl when peer buffers cannot be mapped), 'nccl' = send buffer + all-to-all")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay one captured CUDA graph per step (IVF.graphed) instead of launching the kernels one by one; "
+                         "single GPU / replicas only. Opt-in: not yet validated on hardware")
     ap.add_argument("--shard", default="auto", choices=["auto", "lists", "replicas"],
                     help="N>1: 'lists' = inverted lists sharded over the ranks, estimates stored into the query's home rank "
                          "(north star; what a 100M-vector index needs for aggregate bandwidth); 'replicas' = every rank holds "
@@ -278,6 +281,11 @@ def main():
         run = lambda q, **o: engine.query_batch(q, exchange=args.exchange, **kw, **o)
     else:
         run = lambda q, **o: ivf.query_batch(q, order="device", **kw, **o)
+    eager_run, graphed = run, None
+    if args.graph and not sharded:
+        graphed = ivf.graphed(Qn, args.k, n_probes=args.n_probes)
+        cfg["cuda_graph"] = True
+        run = lambda q, **o: (graphed(q, to_host=o.get("to_host", True)) if not (set(o) - {"to_host"}) else eager_run(q, **o))
 
     def sync_all():
         if dist is not None:
@@ -332,6 +340,8 @@ def main():
     torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - calls0            # kernels launched by libtinyknn_b200.so in the timed region (counted in C)
+    if graphed is not None:                            # replays do not pass through the C launch counter
+        launches = graphed.launches_per_replay * args.steps
     # -- per-kernel times for the roofline: the same steps again, one stream, a CUDA-event pair around every stage
     #    (in the timed loop above the sub-batches of a step overlap on side streams, which no event pair can untangle)
     ivf.profile(True)

@@ -151,3 +151,21 @@ def test_glove_shape_full_size_properties():
         exp = np.zeros(2 * len(packed), np.uint64)
         O.estimate_pq(packed, np.ascontiguousarray(dt.tables), exp, True, "avx")
         assert np.array_equal(est.view(np.uint8), exp.view(np.uint8)[:len(est)])
+
+
+def test_graphed_batch_equals_eager(golden):
+    """IVF.graphed: the captured batch replays to the same ids / counts / distances as the eager query_batch, for
+    several different query sets through the same graph, with and without sub-batches."""
+    from tinyknn_b200 import synth
+    X = synth.clustered(120_000 + 3 * 4096, 64, 80, seed=2)
+    ivf = synth.build_ivf(X[:120_000], "euclidean", 128, seed=2)
+    for sub in (1, 2):
+        g = ivf.graphed(4096, 10, n_probes=8, sub_batches=sub)
+        assert g.launches_per_replay > 5
+        for i in range(3):
+            qs = X[120_000 + i * 4096:120_000 + (i + 1) * 4096].contiguous()
+            ref = ivf.query_batch(qs, 10, n_probes=8, order="device", return_distances=True, sub_batches=1)
+            got = g(qs, return_distances=True)
+            assert all(np.array_equal(a, b) for a, b in zip(ref, got)), (sub, i)
+            got_h = g(qs.cpu().numpy(), return_distances=True)           # host queries in
+            assert all(np.array_equal(a, b) for a, b in zip(ref, got_h))

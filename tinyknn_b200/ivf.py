@@ -307,6 +307,14 @@ class IVF:
             return ids, cnt, dst
         return ids, cnt
 
+    def graphed(self, n_queries, k, n_probes=1, pass_1=None, sub_batches=None):
+        """CUDA-graph version of `query_batch(order="device")` for a fixed batch shape (new, additive API): the whole
+        sequence of launches of one batch is captured once and replayed per call, which removes the host-side launch
+        cost that a synchronous caller pays in front of every batch (about 26 launches). Returns a `GraphedBatch`;
+        `graphed(...)(queries)` gives the same results as `query_batch(queries, k, n_probes, order="device")`.
+        NOT YET RUN ON A GPU (written after round 1's GPU budget was spent): tests/test_unvalidated_gpu.py."""
+        return GraphedBatch(self, int(n_queries), int(k), int(n_probes), pass_1, sub_batches)
+
     # -- stages of one block of queries (shared with the list-sharded index, sharded.py) ----------------
     def _coarse(self, dev, lut, Q, P, Rc, order):
         """Probe selection (ref: ivf.py:131 -> fast_pq.py:284-312): scan of the PQ-encoded centroids, exact heap
@@ -474,3 +482,47 @@ class IVF:
             cmin = D.empty((est.numel() // 16 + 16,), np.uint8)
         self._scan(dev, lut["tables"], probes, Q, P, est, seg_off, cmin=cmin)
         return self._replay_rescore(dev, lut["q"], probes, Q, P, k, pass_1, est, seg_off, order, out, cmin=cmin)
+
+
+class GraphedBatch:
+    """One captured `IVF.query_batch` of a fixed shape (see `IVF.graphed`). Static device buffers: the queries are copied
+    into `q_in`, the graph is replayed, the results are read from `out` (device tensors ids (Q, k) int64, counts (Q,)
+    int32, dists (Q, k)); consecutive calls therefore serialise on the stream they are issued on."""
+
+    def __init__(self, ivf, Q, k, n_probes, pass_1=None, sub_batches=None):
+        t = D.require_cuda()
+        dev = ivf.to_device()
+        self.ivf, self.Q, self.k = ivf, Q, k
+        self.q_in = D.empty((Q, dev["d"]), np.float32)
+        self.q_in.zero_()
+        kw = dict(k=k, n_probes=n_probes, pass_1=pass_1, order="device", return_distances=True, to_host=False,
+                  sub_batches=sub_batches, fused=False)
+        from ._lib import launch_count
+        warm = t.cuda.Stream()                                  # capture needs a warmed-up allocator and cached device state
+        warm.wait_stream(t.cuda.current_stream())
+        with t.cuda.stream(warm):
+            for _ in range(2):
+                ivf.query_batch(self.q_in, **kw)
+        t.cuda.current_stream().wait_stream(warm)
+        t.cuda.synchronize()
+        self.graph = t.cuda.CUDAGraph()
+        n0 = launch_count()
+        with t.cuda.graph(self.graph):
+            self.out = ivf.query_batch(self.q_in, **kw)
+        self.launches_per_replay = launch_count() - n0          # kernels inside the graph (tkb_launch_count counts the capture once)
+
+    def __call__(self, queries, return_distances=False, to_host=True):
+        t = D.torch()
+        if isinstance(queries, np.ndarray):
+            queries = t.from_numpy(np.ascontiguousarray(queries, dtype=np.float32))
+        assert tuple(queries.shape) == tuple(self.q_in.shape), "a GraphedBatch answers batches of exactly the captured shape"
+        self.q_in.copy_(queries, non_blocking=True)
+        self.graph.replay()
+        ids, cnt, dst = self.out
+        if to_host:
+            host = [t.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in (ids, cnt, dst)]
+            for h, x in zip(host, (ids, cnt, dst)):
+                h.copy_(x, non_blocking=True)
+            t.cuda.current_stream().synchronize()
+            ids, cnt, dst = (h.numpy() for h in host)
+        return (ids, cnt, dst) if return_distances else (ids, cnt)
