@@ -798,8 +798,12 @@ static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 
         g.v2 = 1;
         g.lanes = R <= 255 ? 4 : 8;
         g.qcap = 4 * R < 128 ? 128 : 4 * R;
+        // CTAs wanted before queries are packed 16 to a CTA (TKB_RQ_MIN_CTAS, default 2 x 148). The launch list of round 1
+        // shows a 5 000-query launch (313 CTAs) taking almost as long as a 10 000-query one: worth an A/B at 4 x 148.
+        static int min_ctas = 0;
+        if (!min_ctas) { const char *e = getenv("TKB_RQ_MIN_CTAS"); min_ctas = e ? atoi(e) : 0; if (min_ctas <= 0) min_ctas = 2 * 148; }
         int qpc = 16;
-        while (qpc > 1 && (Q + qpc - 1) / qpc < 2 * 148) qpc >>= 1;
+        while (qpc > 1 && (Q + qpc - 1) / qpc < min_ctas) qpc >>= 1;
         while (qpc > 1 && rq2_smem(R, P, qpc, g.qcap) > 45 * 1024) qpc >>= 1;
         g.qpc = qpc; g.lpw = 0;
         g.smem = rq2_smem(R, P, qpc, g.qcap, cm);
