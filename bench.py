@@ -454,6 +454,8 @@ def main():
                                             d2h_bytes_per_step=int(Qn * args.k * 8 + Qn * 4)),
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=cb, parity=parity)
         print(json.dumps(line))
+    if sharded:
+        engine.close()                                  # unmap / free the peer buffers (collective)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

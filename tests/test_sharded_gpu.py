@@ -34,6 +34,7 @@ def _worker(rank, world, port, out):
             bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
             used.append(sh.last_exchange)
         bad += used != ["nccl", "push", "push", "push"]               # peer memory must really have been used
+        sh.close()
         np.save(out, np.array([bad]))
     finally:
         dist.destroy_process_group()

@@ -329,6 +329,13 @@ class ShardedIVF:
         self.__dict__["_pb"] = pb = PeerBuffers(need, self.group, self.rank, self.world)
         return pb
 
+    def close(self):
+        """Release the peer-mapped receive buffers (collective when world > 1). The index itself stays usable: the next
+        push batch maps fresh buffers."""
+        pb = self.__dict__.pop("_pb", None)
+        if pb is not None:
+            pb.close(self.group)
+
     def _finish(self, home, est_r, seg_r, k, pass_1, cmin_r=None):
         """Ordered heap replay over the received estimates, exact rescoring, k nearest (device tensors)."""
         return self.ivf._replay_rescore(self.dev, home["lut"]["q"], home["probes"], home["Qh"], home["P"], k, pass_1,
