@@ -191,13 +191,22 @@ def log(msg):
         print("[bench rank %s +%.1fs] %s" % (os.environ.get("RANK", "0"), time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
 
 
-def build_index(args, torch, seed=10):
+def resolve_shard(args):
+    """--shard auto: lists when the PQ codes of the workload are >= 1 GB, else replicas."""
+    if args.shard == "auto":
+        w = WORKLOADS[args.workload]
+        code_bytes = w["n"] * (-(-w["d"] // 8) * 8 // 2 if w["d"] == 100 else 32) // 2      # M/2 bytes per vector (M = 52 / 32)
+        args.shard = "lists" if code_bytes >= (1 << 30) else "replicas"
+    return args.shard
+
+
+def build_index(args, torch, seed=10, deterministic=False):
     from tinyknn_b200 import synth
     w = WORKLOADS[args.workload]
     X = synth.clustered(w["n"] + 4 * args.queries, w["d"], w["components"], seed, normalize=False)
     data, qpool = X[:w["n"]], X[w["n"]:]
     big = w["n"] * w["d"] * 4 > (8 << 30)                          # raw vectors stay on the GPU only (rows fetched on demand)
-    ivf = synth.build_ivf(data, w["metric"], w["n_clusters"], seed=seed, host_data=not big)
+    ivf = synth.build_ivf(data, w["metric"], w["n_clusters"], seed=seed, host_data=not big, deterministic=deterministic)
     return ivf, qpool.cpu().numpy()
 
 
@@ -238,8 +247,18 @@ def main():
     from tinyknn_b200 import _lib
     tinyknn.fast_pq.set_order(args.order)
     log("building the synthetic index")
-    ivf, qpool = build_index(args, torch)
+    # ranks of a list-sharded job build the index independently from the same seed: it has to come out bit-identical
+    lists_mode = world > 1 and args.impl == "ours" and resolve_shard(args) == "lists"
+    ivf, qpool = build_index(args, torch, deterministic=lists_mode)
     log("index built")
+    if lists_mode:
+        from tinyknn_b200 import synth
+        same = synth.index_consistent(ivf, dist)
+        log("index identical on all ranks: %s" % same)
+        if not same:                                    # one index for the whole job: rank 0's
+            synth.sync_index_from_rank0(ivf, dist)
+            log("device index broadcast from rank 0; identical now: %s" % synth.index_consistent(ivf, dist))
+        cfg["index"] = "built by every rank from the same seed, " + ("bit-identical" if same else "differed: rank 0's broadcast to all")
     Qn = args.queries
     batches = [np.ascontiguousarray(qpool[i * Qn:(i + 1) * Qn]) for i in range(4)]
 
@@ -265,10 +284,7 @@ def main():
     dev_batches = [torch.from_numpy(b).cuda() for b in batches]
     pinned = [torch.from_numpy(b).pin_memory() for b in batches]
     kw = dict(k=args.k, n_probes=args.n_probes)
-    if args.shard == "auto":
-        code_bytes = w["n"] * (-(-w["d"] // 8) * 8 // 2 if w["d"] == 100 else 32) // 2      # M/2 bytes per vector (M = 52 / 32)
-        args.shard = "lists" if code_bytes >= (1 << 30) else "replicas"
-    sharded = world > 1 and args.shard == "lists"
+    sharded = world > 1 and resolve_shard(args) == "lists"
     if sharded:
         # every rank built the same index (same seed); rank r keeps the codes of its lists and answers its own
         # block of queries: a different slice of the query pool per rank, the same number on every rank

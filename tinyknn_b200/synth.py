@@ -68,15 +68,25 @@ def _nearest(X, C, chunk=None):
     return out
 
 
-def kmeans(X, k, iters, seed):
-    """A few Lloyd iterations (empty clusters are re-seeded from random points)."""
+def kmeans(X, k, iters, seed, deterministic=False):
+    """A few Lloyd iterations (empty clusters are re-seeded from random points). deterministic=True sums the members of a
+    cluster in a fixed order (index_add_ uses atomics otherwise): every rank of a multi-GPU job that builds the index from
+    the same seed must end up with the very same centroids, hence the same lists."""
     t = D.torch()
     g = t.Generator(device=X.device).manual_seed(seed)
     C = X[t.randperm(X.shape[0], generator=g, device=X.device)[:k]].clone()
     for _ in range(iters):
         a = _nearest(X, C)
         cnt = t.bincount(a, minlength=k)
-        S = t.zeros_like(C).index_add_(0, a, X)
+        if deterministic:
+            prev = t.are_deterministic_algorithms_enabled()
+            t.use_deterministic_algorithms(True)
+            try:
+                S = t.zeros_like(C).index_add_(0, a, X)
+            finally:
+                t.use_deterministic_algorithms(prev)
+        else:
+            S = t.zeros_like(C).index_add_(0, a, X)
         C = t.where(cnt[:, None] > 0, S / cnt.clamp(min=1)[:, None], C)
         empty = (cnt == 0).nonzero().flatten()
         if len(empty):
@@ -152,7 +162,8 @@ def pack_codes(codes):
     return byte.permute(0, 2, 1).contiguous().reshape(n // 16, M * 8).view(t.int64)
 
 
-def build_ivf(X, metric, n_clusters, pq=None, kmeans_iters=6, fit_sample=200_000, seed=0, keep_device=True, host_data=True):
+def build_ivf(X, metric, n_clusters, pq=None, kmeans_iters=6, fit_sample=200_000, seed=0, keep_device=True, host_data=True,
+              deterministic=False):
     """IVF index over device data X (f32, (n, d)); one list per point (build_probes = 1).
     Returns an `IVF` whose host attributes mirror the reference's and whose device copy is in place."""
     t = D.require_cuda()
@@ -161,7 +172,7 @@ def build_ivf(X, metric, n_clusters, pq=None, kmeans_iters=6, fit_sample=200_000
         X = X / X.norm(dim=1, keepdim=True)
     g = t.Generator(device=X.device).manual_seed(seed)
     sample = X[t.randperm(n, generator=g, device=X.device)[:min(n, fit_sample)]]
-    centers = kmeans(sample, n_clusters, kmeans_iters, seed)
+    centers = kmeans(sample, n_clusters, kmeans_iters, seed, deterministic=deterministic)
     if metric == "angular":
         centers = centers / centers.norm(dim=1, keepdim=True)
     if pq is None:
@@ -229,3 +240,55 @@ def pq_transform_small(pq, rows):
     padded = t.zeros(n16, rows.shape[1], device=rows.device, dtype=rows.dtype)
     padded[:n] = rows
     return TransformedData(n, pack_codes(encode(pq, padded)).cpu().numpy().view(np.uint64))
+
+
+def index_fingerprint(ivf):
+    """Integer checksums (device int64[6], wrap-around sums of the bit patterns) of everything a rank of a list-sharded job
+    must agree on with the others: list sizes, codes, ids, centroids, centroid codes, the PQ codebook."""
+    t = D.torch()
+    dev = ivf.to_device()
+    bits = lambda x: x.contiguous().view(t.int32).to(t.int64).sum() if x.dtype == t.float32 else x.contiguous().view(-1).to(t.int64).sum()
+    sizes = dev["list_size"].to(t.int64)
+    codes = dev["codes"]
+    n8 = codes.numel() // 8 * 8
+    pqc = D.upload(np.ascontiguousarray(ivf.pq.centers, dtype=np.float32))
+    return t.stack([(sizes * t.arange(1, len(sizes) + 1, device=sizes.device)).sum(), codes[:n8].view(t.int64).sum(),
+                    dev["ids"].sum(), bits(dev["centers"]), dev["center_codes"][:dev["center_codes"].numel() // 8 * 8].view(t.int64).sum(),
+                    bits(pqc)])
+
+
+def index_consistent(ivf, dist, group=None):
+    """True when every rank holds the same index (collective)."""
+    fp = index_fingerprint(ivf)
+    lo, hi = fp.clone(), fp.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    return bool((lo == hi).all().item())
+
+
+def sync_index_from_rank0(ivf, dist, group=None):
+    """Make every rank's DEVICE copy of the index equal to rank 0's (collective; NCCL broadcasts). Used when the ranks'
+    independently built indexes differ: a list-sharded job needs one index. Host-side attributes (the per-list views the
+    oracle reads) are left alone: only rank 0 checks against the oracle, and rank 0 is the source."""
+    t = D.torch()
+    dev = ivf.to_device()
+    rank = dist.get_rank(group)
+    scalars = ("C", "M", "n_lists", "max_chunks", "max_real_chunks", "n_chunks_total", "center_chunks")
+    names = ("codes", "list_chunk_off", "list_size", "ids", "center_codes", "centers")
+    hdr = t.tensor([int(dev[k]) for k in scalars] + [int(dev[n].numel()) for n in names], dtype=t.int64, device=D.device())
+    dist.broadcast(hdr, 0, group=group)
+    h = [int(v) for v in hdr.cpu().tolist()]
+    for key, v in zip(scalars, h):
+        dev[key] = v
+    for n, numel in zip(names, h[len(scalars):]):
+        x = dev[n].contiguous().view(-1)
+        if x.numel() != numel:
+            x = t.empty(numel, dtype=x.dtype, device=x.device)
+        dist.broadcast(x, 0, group=group)
+        dev[n] = x.view(-1, dev["d"]) if n == "centers" else x
+    dev["host_sizes"] = dev["list_size"].cpu().numpy()
+    dev["host_chunks"] = dev["list_chunk_off"].cpu().numpy()
+    pqc = D.upload(np.ascontiguousarray(ivf.pq.centers, dtype=np.float32))
+    dist.broadcast(pqc, 0, group=group)
+    ivf.pq.centers = pqc.cpu().numpy()
+    ivf.pq.__dict__.pop("_dev", None)
