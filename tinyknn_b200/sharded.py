@@ -317,6 +317,7 @@ class ShardedIVF:
         if pb is not None and pb.nbytes >= need:
             return pb
         t = D.torch()
+        t.cuda.empty_cache()                                  # the buffers come from cudaMalloc, not from torch's cache
         free, _ = t.cuda.mem_get_info()
         fits = t.tensor([int(2 * need <= free // 3)], dtype=t.int32, device=D.device())
         if self.world > 1:
