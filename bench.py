@@ -57,6 +57,10 @@ def parse():
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
                     help="--shard lists: 'push' = the scan kernel stores estimates into the home rank's HBM over NVLink peer "
                          "memory (falls back to nccl when peer buffers cannot be mapped), 'nccl' = send buffer + all-to-all")
+    ap.add_argument("--e2e-pipeline", action="store_true",
+                    help="also report e2e_pipelined: the same host-buffer loop with two batches in flight "
+                         "(query_batch(to_host='async')): batch i+1 is submitted before batch i is collected. Opt-in: not yet "
+                         "validated on hardware")
     ap.add_argument("--graph", action="store_true",
                     help="replay one captured CUDA graph per step (IVF.graphed) instead of launching the kernels one by one; "
                          "single GPU / replicas only. Opt-in: not yet validated on hardware")
@@ -386,6 +390,19 @@ def main():
         ids_h, cnt_h = run(pinned[i % 4].numpy())
     sync_all()
     e2e_s = time.perf_counter() - t0
+    e2e_pipe_s = None
+    if args.e2e_pipeline and not sharded and graphed is None:
+        pending = None
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            nxt = eager_run(pinned[i % 4].numpy(), to_host="async")
+            if pending is not None:
+                pending.result()
+            pending = nxt
+        pending.result()
+        sync_all()
+        e2e_pipe_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
 
     tms = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
@@ -469,6 +486,9 @@ def main():
                     clocks=clocks, e2e=dict(value=e2e_v, unit="queries/s", h2d_bytes_per_step=int(Qn * w["d"] * 4),
                                             d2h_bytes_per_step=int(Qn * args.k * 8 + Qn * 4)),
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=cb, parity=parity)
+        if e2e_pipe_s is not None:                       # rank 0's own loop (replicas run the same loop on every rank)
+            line["e2e_pipelined"] = dict(value=Qn * args.steps * world / e2e_pipe_s, unit="queries/s", in_flight=2,
+                                         note="same host buffers and copies as e2e, batch i+1 submitted before batch i is collected")
         print(json.dumps(line))
     if sharded:
         engine.close()                                  # unmap / free the peer buffers (collective)

@@ -169,3 +169,19 @@ def test_graphed_batch_equals_eager(golden):
             assert all(np.array_equal(a, b) for a, b in zip(ref, got)), (sub, i)
             got_h = g(qs.cpu().numpy(), return_distances=True)           # host queries in
             assert all(np.array_equal(a, b) for a, b in zip(ref, got_h))
+
+
+def test_async_results_equal_sync(golden):
+    """query_batch(to_host="async"): two batches in flight, collected out of band, equal the synchronous results."""
+    from tinyknn_b200 import synth
+    X = synth.clustered(100_000 + 2 * 6000, 64, 60, seed=4)
+    ivf = synth.build_ivf(X[:100_000], "euclidean", 100, seed=4)
+    import torch
+    qa = X[100_000:106_000].cpu().pin_memory()
+    qb = X[106_000:112_000].cpu().pin_memory()
+    ref_a = ivf.query_batch(qa.numpy(), 10, n_probes=6, order="device", return_distances=True)
+    ref_b = ivf.query_batch(qb.numpy(), 10, n_probes=6, order="device", return_distances=True)
+    pa = ivf.query_batch(qa.numpy(), 10, n_probes=6, order="device", return_distances=True, to_host="async")
+    pb = ivf.query_batch(qb.numpy(), 10, n_probes=6, order="device", return_distances=True, to_host="async")
+    assert all(np.array_equal(x, y) for x, y in zip(ref_b, pb.result()))
+    assert all(np.array_equal(x, y) for x, y in zip(ref_a, pa.result()))

@@ -244,7 +244,9 @@ class IVF:
                     to_host=True, sub_batches=None, fused=None):
         """Batched IVF.query (new, additive API). queries: f32 (Q, d), host array or device tensor.
         Returns (ids, counts[, dists]): ids int64 (Q, k) padded with -1, counts int32 (Q,).
-        With to_host=False (order="device" only) the results stay on the GPU as torch tensors.
+        With to_host=False (order="device" only) the results stay on the GPU as torch tensors; to_host="async" returns a
+        `PendingBatch` at once (device-to-host copies into pinned memory are queued behind the kernels; `.result()` waits),
+        so that a caller can submit the next batch before it collects the previous one -- NOT YET RUN ON A GPU.
         sub_batches (order="device"): split the batch over side streams (None: automatic, 1: one stream).
         fused (order="device"): run everything after probe selection as one kernel (None: module default FUSED);
         False keeps the stage-by-stage kernels (scan / replay / gather / select), same results."""
@@ -299,6 +301,9 @@ class IVF:
                 outs.append(self._query_block(dev, qs, k, P, Rc, pass_1, order, blk(lo, min(Q, lo + qb)), fused))
         if order == "device":
             ids, cnt, dst = res
+            if isinstance(to_host, str):                                # "async": copies queued, nothing waited for
+                assert to_host == "async"
+                return PendingBatch(ids, cnt, dst, return_distances)
             if to_host:
                 ids, cnt, dst = ids.cpu().numpy(), cnt.cpu().numpy(), dst.cpu().numpy()
         else:
@@ -482,6 +487,27 @@ class IVF:
             cmin = D.empty((est.numel() // 16 + 16,), np.uint8)
         self._scan(dev, lut["tables"], probes, Q, P, est, seg_off, cmin=cmin)
         return self._replay_rescore(dev, lut["q"], probes, Q, P, k, pass_1, est, seg_off, order, out, cmin=cmin)
+
+
+class PendingBatch:
+    """Result of `query_batch(..., to_host="async")`: the copies to pinned host memory are queued on the launching stream
+    behind the batch's kernels; `result()` waits for them and returns the numpy arrays."""
+
+    def __init__(self, ids, cnt, dst, return_distances):
+        t = D.torch()
+        self._dev = (ids, cnt, dst)                                     # keep the device results alive until the copies ran
+        self._host = [t.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in self._dev]
+        for h, x in zip(self._host, self._dev):
+            h.copy_(x, non_blocking=True)
+        self._done = t.cuda.Event()
+        self._done.record()
+        self._return_distances = return_distances
+
+    def result(self):
+        self._done.synchronize()
+        ids, cnt, dst = (h.numpy() for h in self._host)
+        self._dev = None
+        return (ids, cnt, dst) if self._return_distances else (ids, cnt)
 
 
 class GraphedBatch:

@@ -7,3 +7,4 @@ timeout 1200 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; tai
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1; tail -2 $out/smoke.log
 timeout 900 python bench.py --steps 20 --warmup 3 > $out/bench.json 2> $out/bench.err; tail -c 2500 $out/bench.json; tail -3 $out/bench.err
 timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --graph > $out/bench_graph.json 2> $out/bench_graph.err; tail -c 1200 $out/bench_graph.json; tail -3 $out/bench_graph.err
+timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-pipeline > $out/bench_pipe.json 2> $out/bench_pipe.err; tail -c 600 $out/bench_pipe.json; tail -3 $out/bench_pipe.err
