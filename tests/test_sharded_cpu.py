@@ -182,3 +182,110 @@ def test_plan_host_push_layout_is_the_home_ranks_single_gpu_layout():
             assert np.array_equal(seg[hit], home[hit])
             writers += hit
         assert np.array_equal(writers, (home >= 0).astype(np.int64))
+
+
+def _push_worker(rank, world, port, prefix, n_probes, k, shm_names, cap, out):
+    """The push exchange on CPU: the "peer-mapped receive buffers" are POSIX shared-memory blocks, the scan is the oracle;
+    every rank stores the segments of the lists it owns straight into the home rank's block at the offsets of
+    plan_host(PLAN_PUSH), a barrier orders the stores before the replays."""
+    sys.path.insert(0, ROOT)
+    from multiprocessing import shared_memory
+    import torch
+    import torch.distributed as dist
+    from oracle import restate as O
+    from tinyknn_b200 import sharded as SH
+    from tinyknn_b200._lib import PLAN_SEND, PLAN_PUSH
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    blocks = [shared_memory.SharedMemory(name=n) for n in shm_names]
+    try:
+        z = np.load(GOLDEN)
+        S = O.ivf_state_from_arrays(z, prefix)
+        K = O.Kernels("port", "avx")
+        qs = np.asarray(z[prefix + "q"], dtype=np.float32)
+        Qh = len(qs) // world
+        home = qs[rank * Qh:(rank + 1) * Qh]
+        sizes = np.array([t[0] for t in S.pq_transformed_points], dtype=np.int32)
+        owner = SH.assign_owners(sizes, world)
+        P = min(n_probes, S.pq_transformed_centers[0])
+        M = S.pq_transformed_centers[1].shape[1]
+        tabs = np.zeros((Qh, 2 * M), dtype=np.uint64)
+        probes_h = np.zeros((Qh, P), dtype=np.int32)
+        qn = []
+        for i, q in enumerate(home):
+            q = np.array(q, dtype=np.float32)
+            if S.metric == "angular":
+                q /= np.linalg.norm(q)
+            dt = O.make_dtable(S.pq, q, K)
+            tabs[i] = dt.tables[:2 * M]
+            probes_h[i] = dt.top(S.pq_transformed_centers, S.active_centers, k=n_probes)
+            qn.append(q)
+        tables = SH.all_gather_rows(torch.from_numpy(tabs.view(np.int64)), None).numpy().view(np.uint64)
+        probes = SH.all_gather_rows(torch.from_numpy(probes_h), None).numpy()
+        Q = world * Qh
+        seg, gb, _ = SH.plan_host(probes, sizes, owner, PLAN_PUSH, rank, world, Qh)
+        assert gb.max() <= cap
+        homes = [np.ndarray((cap,), dtype=np.uint8, buffer=b.buf) for b in blocks]
+        written = 0
+        for q in range(Q):
+            for s in range(P):
+                if seg[q, s] < 0:
+                    continue
+                l = int(probes[q, s])
+                n, packed = S.pq_transformed_points[l]
+                est = np.zeros(2 * len(packed), dtype=np.uint64)
+                K.estimate_pq(packed, np.ascontiguousarray(tables[q]), est, True)
+                homes[q // Qh][seg[q, s]:seg[q, s] + 16 * len(packed)] = est.view(np.uint8)     # the "peer store"
+                written += 16 * len(packed)
+        dist.barrier()                                                   # every rank's scan has finished
+        seg_r, gb_r, _ = SH.plan_host(probes_h, sizes, None, PLAN_SEND, 0, 1, 0)                  # my own single-rank layout
+        mine = homes[rank]
+        bad = 0
+        for i in range(Qh):
+            R = (n_probes + 1) * k + 1
+            hi, hv = np.zeros(R, np.int64), np.zeros(R, np.int32)
+            O.init_heap(hi, hv, True)
+            for s in range(P):
+                l = int(probes_h[i, s])
+                n = int(sizes[l])
+                if n == 0:
+                    continue
+                nb = 16 * ((n + 15) // 16)
+                O.replay(np.array(mine[seg_r[i, s]:seg_r[i, s] + nb]), n, hi, hv, True, np.ascontiguousarray(S.ids[l], dtype=np.int64))
+            tr = {}
+            exp = O.ivf_query(S, home[i], k, n_probes=n_probes, kernels=K, trace=tr)
+            if not (np.array_equal(hi, tr["heap_indices"]) and np.array_equal(hv, tr["heap_values"])):
+                bad += 1
+        np.save(out, np.array([bad, written, int(gb_r.sum())]))
+        dist.barrier()
+    finally:
+        del homes, mine
+        for b in blocks:
+            b.close()
+        dist.destroy_process_group()
+
+
+def test_push_exchange_host_logic_gloo_world2(tmp_path):
+    from multiprocessing import shared_memory
+    import torch.multiprocessing as mp
+    world, port, cap = 2, _free_port(), 4 << 20
+    blocks = [shared_memory.SharedMemory(create=True, size=cap) for _ in range(world)]
+    try:
+        outs = [str(tmp_path / ("p%d.npy" % r)) for r in range(world)]
+        ctx = mp.get_context("spawn")
+        procs = [ctx.Process(target=_push_worker, args=(r, world, port, "euc128_", 8, 10, [b.name for b in blocks], cap, outs[r]))
+                 for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(300)
+            assert p.exitcode == 0
+        res = [np.load(o) for o in outs]
+        assert all(r[0] == 0 for r in res), res                              # heaps == the single-process oracle on every rank
+        assert sum(r[1] for r in res) == sum(r[2] for r in res)             # bytes stored == bytes the home layouts hold
+        assert all(r[1] > 0 for r in res)
+    finally:
+        for b in blocks:
+            b.close()
+            b.unlink()
