@@ -797,6 +797,11 @@ static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 
     if (v2_env && R <= 65535 && stream_chunks < (1 << 20) - 1) {                    // pipelined kernel: an insert takes <= floor(log2 R) + 1 steps <= 2 * lanes
         g.v2 = 1;
         g.lanes = R <= 255 ? 4 : 8;
+        // TKB_RQ_LANES=8 forces 8 lanes per query for small heaps too: half as many queries per consumer warp, twice as many
+        // consumer warps to hide the shared-memory latency of the sift chain (an A/B for round 2; results are identical)
+        static int lanes_env = -1;
+        if (lanes_env < 0) { const char *e = getenv("TKB_RQ_LANES"); lanes_env = e ? atoi(e) : 0; }
+        if (lanes_env == 8) g.lanes = 8;
         g.qcap = 4 * R < 128 ? 128 : 4 * R;
         // CTAs wanted before queries are packed 16 to a CTA (TKB_RQ_MIN_CTAS, default 2 x 148). The launch list of round 1
         // shows a 5 000-query launch (313 CTAs) taking almost as long as a 10 000-query one: worth an A/B at 4 x 148.
