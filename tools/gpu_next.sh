@@ -8,3 +8,5 @@ timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 
 timeout 900 python bench.py --steps 20 --warmup 3 > $out/bench.json 2> $out/bench.err; tail -c 2500 $out/bench.json; tail -3 $out/bench.err
 timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --graph > $out/bench_graph.json 2> $out/bench_graph.err; tail -c 1200 $out/bench_graph.json; tail -3 $out/bench_graph.err
 timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-pipeline > $out/bench_pipe.json 2> $out/bench_pipe.err; tail -c 600 $out/bench_pipe.json; tail -3 $out/bench_pipe.err
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:replay_rq2 -c 4 \
+    -o $out/replay_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/ncu_replay.log 2>&1; tail -2 $out/ncu_replay.log
