@@ -379,7 +379,7 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                   const int32_t *__restrict__ list_size, int n_lists, const int64_t *__restrict__ ids,
                   const int32_t *__restrict__ probes, int Q, int P, int64_t *__restrict__ heap_idx,
                   int32_t *__restrict__ heap_val, int R, int *__restrict__ fallback, int QPC, int QCAP,
-                  const uint8_t *__restrict__ cmin)
+                  const uint8_t *__restrict__ cmin, int qpw)
 {
     extern __shared__ __align__(16) unsigned char rq_sm[];
     const int HS = 2 * R + 4;                                              // words per heap: slot i at word i+1, children of R-1 included
@@ -623,11 +623,13 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
         // ---- consume: L lanes per query, 32/L queries per warp. The step is branch-free (the queries of a warp are in
         //      different states; divergent code would be issued once per state and the loop is issue-bound) -----------
         {
-            constexpr int QPW = 32 / L;
+            // qpw queries per consumer warp (default 32 / L; fewer = less lock-step waste, more warps busy: the replay model
+            // of tools/replay_model.py puts 8 lock-stepped queries at +26 % steps over one query per warp)
+            const int QPW = (qpw > 0 && qpw <= 32 / L) ? qpw : 32 / L;
             const int role = lane % L;
             for (int tb = warp * QPW; tb < QPC; tb += n_warps * QPW) {
                 const int t = tb + lane / L;
-                const bool mine = t < QPC;
+                const bool mine = lane / L < QPW && t < QPC;
                 uint32_t *hw = H + (size_t)(mine ? t : 0) * HS;
                 const uint32_t *qu = QU + (size_t)(mine ? t : 0) * (QCAP + 2);
                 const int cnt = mine ? s_count[t] : 0;
@@ -831,6 +833,14 @@ static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 
     return g.smem <= 200 * 1024;
 }
 
+// TKB_RQ_QPW: queries per consumer warp of the pipelined replay (1, 2, 4, 8; default 32 / lanes). An A/B switch for round 2.
+static int rq_qpw()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("TKB_RQ_QPW"); v = e ? atoi(e) : 0; if (v != 1 && v != 2 && v != 4 && v != 8) v = 0; }
+    return v;
+}
+
 template <bool SIGNED>
 static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t *seg_off, int64_t n_chunks0, int n0,
                      const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, const int64_t *ids,
@@ -844,7 +854,7 @@ static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t
             TKB_CUDA(cudaFuncSetAttribute(replay_rq2_kernel<SIGNED, LANES, CMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
             replay_rq2_kernel<SIGNED, LANES, CMV><<<blocks, RQ_THREADS, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off, \
                                                                                      list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val,  \
-                                                                                     R, fallback, g.qpc, g.qcap, cmin);                          \
+                                                                                     R, fallback, g.qpc, g.qcap, cmin, rq_qpw());               \
         } while (0)
         if (cmin) { if (g.lanes == 4) TKB_RQ2_LAUNCH(4, true); else TKB_RQ2_LAUNCH(8, true); }
         else      { if (g.lanes == 4) TKB_RQ2_LAUNCH(4, false); else TKB_RQ2_LAUNCH(8, false); }
