@@ -11,8 +11,17 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+EMU = os.environ.get("TKB_EMU", "0") == "1"
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if EMU:
+        # TKB_EMU=1: the gpu-marked tests run on the CPU emulator (tests/emulate): the package's host layer on CPU tensors, the
+        # library's CUDA sources compiled against cuda_emu.h. Test infrastructure only; see tests/emulate/emu_torch.py.
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emulate"))
+        import emu_torch
+        emu_torch.install()
 
 
 def pytest_collection_modifyitems(config, items):
@@ -22,7 +31,7 @@ def pytest_collection_modifyitems(config, items):
         has_gpu = torch.cuda.is_available()
     except Exception:
         has_gpu = False
-    if has_gpu:
+    if has_gpu or EMU:
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

@@ -1,0 +1,272 @@
+// cuda_emu.cpp -- fiber scheduler and runtime shim behind cuda_emu.h (TEST INFRASTRUCTURE ONLY).
+#include "cuda_emu.h"
+
+#include <sys/mman.h>
+#include <ucontext.h>
+
+#include <deque>
+#include <string>
+#include <vector>
+
+uint3 threadIdx, blockIdx;
+dim3 blockDim, gridDim;
+
+namespace emu {
+namespace {
+
+constexpr size_t STACK_BYTES = 256 * 1024;
+constexpr uint64_t CANARY = 0xC0DEC0DEDEADBEEFull;
+
+struct Fiber {
+    ucontext_t ctx;
+    uint3 tid;
+    unsigned linear = 0;
+    bool done = false;
+};
+
+struct Warp {
+    int live = 0, arrived = 0;
+    unsigned gen = 0;
+    unsigned live_mask = 0;
+    uint64_t pad[32] = {0};
+    uint64_t res[2][32] = {{0}};
+    std::vector<int> waiters;
+};
+
+struct Block {
+    std::vector<Fiber> fibers;
+    std::vector<Warp> warps;
+    std::deque<int> ready;
+    int live = 0, bar_arrived = 0, bar_pred = 0;
+    unsigned bar_gen = 0;
+    int bar_res[2] = {0, 0};
+    std::vector<int> bar_waiters;
+    unsigned char *smem = nullptr;
+    size_t smem_bytes = 0;
+};
+
+ucontext_t g_sched;
+Block *g_blk = nullptr;
+int g_cur = -1;
+const std::function<void()> *g_body = nullptr;
+unsigned char *g_stacks = nullptr;
+size_t g_stack_count = 0;
+std::string g_error;
+cudaError_t g_last = cudaSuccess;
+Stats g_stats = {};
+
+void park()
+{
+    g_stats.switches++;
+    swapcontext(&g_blk->fibers[g_cur].ctx, &g_sched);
+}
+
+void wake(std::vector<int> &list)
+{
+    for (int f : list) g_blk->ready.push_back(f);
+    list.clear();
+}
+
+void finish_collective(Warp &w)
+{
+    std::memcpy(w.res[w.gen & 1], w.pad, sizeof(w.pad));
+    w.arrived = 0;
+    w.gen++;
+    wake(w.waiters);
+}
+
+void finish_barrier(Block &b)
+{
+    b.bar_res[b.bar_gen & 1] = b.bar_pred;
+    b.bar_pred = 0;
+    b.bar_arrived = 0;
+    b.bar_gen++;
+    wake(b.bar_waiters);
+}
+
+void fiber_main()
+{
+    (*g_body)();
+    Block &b = *g_blk;
+    Fiber &f = b.fibers[g_cur];
+    f.done = true;
+    b.live--;
+    Warp &w = b.warps[f.linear >> 5];
+    const unsigned lane = f.linear & 31;
+    w.live--;
+    w.live_mask &= ~(1u << lane);
+    w.pad[lane] = 0;
+    if (w.arrived > 0 && w.arrived == w.live) { g_stats.collectives_with_exited_lanes++; finish_collective(w); }
+    if (b.bar_arrived > 0 && b.bar_arrived == b.live) finish_barrier(b);
+    swapcontext(&f.ctx, &g_sched);            // never resumed
+}
+
+void ensure_stacks(size_t n)
+{
+    if (n <= g_stack_count) return;
+    if (g_stacks) munmap(g_stacks, g_stack_count * STACK_BYTES);
+    g_stacks = (unsigned char *)mmap(nullptr, n * STACK_BYTES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (g_stacks == MAP_FAILED) { perror("emu: mmap of fiber stacks"); abort(); }
+    g_stack_count = n;
+}
+
+}  // namespace
+
+Stats &stats() { return g_stats; }
+
+unsigned lane_id() { return g_blk->fibers[g_cur].linear & 31; }
+
+unsigned live_lane_mask() { return g_blk->warps[g_blk->fibers[g_cur].linear >> 5].live_mask; }
+
+unsigned char *dyn_smem() { return g_blk->smem; }
+
+int block_barrier(int pred)
+{
+    Block &b = *g_blk;
+    g_stats.barriers++;
+    const unsigned gen = b.bar_gen;
+    b.bar_pred |= pred ? 1 : 0;
+    b.bar_arrived++;
+    if (b.bar_arrived == b.live) finish_barrier(b);
+    else { b.bar_waiters.push_back(g_cur); park(); }
+    return b.bar_res[gen & 1];
+}
+
+const uint64_t *warp_gather(uint64_t v)
+{
+    Block &b = *g_blk;
+    const unsigned linear = b.fibers[g_cur].linear;
+    Warp &w = b.warps[linear >> 5];
+    g_stats.collectives++;
+    const unsigned gen = w.gen;
+    w.pad[linear & 31] = v;
+    w.arrived++;
+    if (w.arrived == w.live) finish_collective(w);
+    else { w.waiters.push_back(g_cur); park(); }
+    return w.res[gen & 1];
+}
+
+void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body)
+{
+    g_stats.launches++;
+    const unsigned nthreads = block.x * block.y * block.z;
+    if (nthreads == 0 || nthreads > 1024 || grid.x == 0 || grid.y == 0 || grid.z == 0 || smem_bytes > 227 * 1024) {
+        g_error = "emu: invalid launch configuration";
+        g_last = cudaErrorInvalidValue;
+        return;
+    }
+    ensure_stacks(nthreads);
+    std::vector<unsigned char> smem_store(smem_bytes + 64 + sizeof(uint64_t) * 4);
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_store.data() + 15) & ~(uintptr_t)15);
+    gridDim = grid;
+    blockDim = block;
+    g_body = &body;
+    for (unsigned bz = 0; bz < grid.z; bz++)
+    for (unsigned by = 0; by < grid.y; by++)
+    for (unsigned bx = 0; bx < grid.x; bx++) {
+        g_stats.blocks++;
+        Block blk;
+        blk.fibers.resize(nthreads);
+        blk.warps.resize((nthreads + 31) / 32);
+        blk.live = (int)nthreads;
+        blk.smem = smem;
+        blk.smem_bytes = smem_bytes;
+        std::memset(smem, 0xA5, smem_bytes);                        // shared memory starts uninitialised, not zeroed
+        for (int i = 0; i < 4; i++) std::memcpy(smem + smem_bytes + 8 * i, &CANARY, 8);
+        g_blk = &blk;
+        blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+        for (unsigned t = 0; t < nthreads; t++) {
+            Fiber &f = blk.fibers[t];
+            f.linear = t;
+            f.tid.x = t % block.x; f.tid.y = (t / block.x) % block.y; f.tid.z = t / (block.x * block.y);
+            Warp &w = blk.warps[t >> 5];
+            w.live++;
+            w.live_mask |= 1u << (t & 31);
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = g_stacks + (size_t)t * STACK_BYTES;
+            f.ctx.uc_stack.ss_size = STACK_BYTES;
+            f.ctx.uc_link = &g_sched;
+            makecontext(&f.ctx, fiber_main, 0);
+            blk.ready.push_back((int)t);
+            g_stats.fibers++;
+        }
+        while (!blk.ready.empty()) {
+            g_cur = blk.ready.front();
+            blk.ready.pop_front();
+            threadIdx = blk.fibers[g_cur].tid;
+            g_stats.switches++;
+            swapcontext(&g_sched, &blk.fibers[g_cur].ctx);
+        }
+        g_cur = -1;
+        if (blk.live != 0) {                                        // parked fibers nobody will wake: a divergent barrier / collective
+            char msg[256];
+            int at_bar = (int)blk.bar_waiters.size(), at_warp = 0;
+            for (auto &w : blk.warps) at_warp += (int)w.waiters.size();
+            snprintf(msg, sizeof msg, "emu: deadlock in block (%u,%u,%u): %d threads alive, %d parked at __syncthreads, %d at a warp collective",
+                     bx, by, bz, blk.live, at_bar, at_warp);
+            g_error = msg;
+            g_last = cudaErrorLaunchFailure;
+            g_blk = nullptr;
+            return;
+        }
+        for (int i = 0; i < 4; i++) {
+            uint64_t c;
+            std::memcpy(&c, smem + smem_bytes + 8 * i, 8);
+            if (c != CANARY) {
+                g_error = "emu: write beyond the end of dynamic shared memory";
+                g_last = cudaErrorLaunchFailure;
+                g_blk = nullptr;
+                return;
+            }
+        }
+        g_blk = nullptr;
+    }
+}
+
+}  // namespace emu
+
+extern "C" {
+const char *emu_last_error(void) { return emu::g_error.c_str(); }
+void emu_stats(long long *o)
+{
+    const emu::Stats &s = emu::g_stats;
+    o[0] = s.launches; o[1] = s.blocks; o[2] = s.fibers; o[3] = s.switches; o[4] = s.collectives; o[5] = s.barriers;
+    o[6] = s.collectives_with_exited_lanes;
+}
+void emu_reset_stats(void) { emu::g_stats = emu::Stats{}; emu::g_error.clear(); }
+}
+
+// ---- runtime API shim ------------------------------------------------------------------------------------------------
+cudaError_t cudaGetLastError(void)
+{
+    const cudaError_t e = emu::g_last;
+    emu::g_last = cudaSuccess;
+    return e;
+}
+const char *cudaGetErrorString(cudaError_t e)
+{
+    if (e == cudaSuccess) return "no error";
+    return emu::g_error.empty() ? "emulated CUDA error" : emu::g_error.c_str();
+}
+cudaError_t cudaMalloc(void **p, size_t bytes)
+{
+    *p = aligned_alloc(256, (bytes + 255) / 256 * 256 + 256);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t) { std::memmove(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind) { std::memmove(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *dst, int value, size_t bytes, cudaStream_t) { std::memset(dst, value, bytes); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaGetDevice(int *dev) { *dev = 0; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int *value, cudaDeviceAttr attr, int)
+{
+    *value = attr == cudaDevAttrMultiProcessorCount ? 148 : 0;
+    return cudaSuccess;
+}
+// "IPC" inside one process: the handle carries the pointer
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { std::memset(h, 0, sizeof *h); std::memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }

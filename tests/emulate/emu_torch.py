@@ -1,0 +1,140 @@
+"""Runs the WHOLE Python package on the CPU emulator (TEST INFRASTRUCTURE ONLY; installed by tests/conftest.py when
+TKB_EMU=1, never by the package): every module's `lib` (the ctypes handle of libtinyknn_b200.so) is replaced by
+libtkb_emu.so -- the same CUDA sources compiled against cuda_emu.h -- and `_device`'s torch handle by a proxy whose tensors
+live on the CPU ("device" memory = host memory) and whose torch.cuda is a stand-in (one stream, no-op synchronisation).
+With that the GPU parity tests (-m gpu) execute the product's host layer and the product's kernel sources, and compare them
+with the oracle, on a machine without a GPU. Nothing here is reachable from the package itself."""
+import contextlib
+import sys
+import time
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def wait_stream(self, other):
+        pass
+
+    def wait_event(self, ev):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def record_event(self, ev=None):
+        ev = ev or _Event()
+        ev.record()
+        return ev
+
+
+class _Event:
+    def __init__(self, enable_timing=False, **kw):
+        self.t = None
+
+    def record(self, stream=None):
+        self.t = time.perf_counter()
+
+    def synchronize(self):
+        pass
+
+    def query(self):
+        return True
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+
+class _Cuda:
+    Event = _Event
+    _cur = _Stream()
+
+    @staticmethod
+    def is_available():
+        return True
+
+    @staticmethod
+    def current_device():
+        return 0
+
+    @staticmethod
+    def device_count():
+        return 1
+
+    @staticmethod
+    def set_device(dev):
+        pass
+
+    @classmethod
+    def current_stream(cls, device=None):
+        return cls._cur
+
+    @staticmethod
+    def Stream(*a, **kw):
+        return _Stream()
+
+    @staticmethod
+    def stream(s):
+        return contextlib.nullcontext()
+
+    @staticmethod
+    def synchronize(device=None):
+        pass
+
+    @staticmethod
+    def mem_get_info(device=None):
+        return (8 << 30, 16 << 30)
+
+    @staticmethod
+    def empty_cache():
+        pass
+
+
+class _Torch:
+    """torch with every device being the CPU."""
+
+    def __init__(self, real):
+        self._real = real
+        self.cuda = _Cuda()
+
+    def device(self, *a, **kw):
+        return self._real.device("cpu")
+
+    def empty(self, *a, **kw):
+        kw.pop("pin_memory", None)
+        return self._real.empty(*a, **kw)
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+
+_installed = False
+
+
+def install():
+    global _installed
+    if _installed:
+        return
+    import torch
+    import tinyknn_b200                                          # noqa: F401  (the real library loads fine without a GPU)
+    from tinyknn_b200 import _lib, _device as D
+    sys.path.insert(0, __file__.rsplit("/", 1)[0])
+    import emu_lib
+    emu = emu_lib.load()
+    real = _lib.lib
+    for name, mod in list(sys.modules.items()):
+        if mod is not None and (name == "tinyknn_b200" or name.startswith("tinyknn_b200.")):
+            for attr, val in list(vars(mod).items()):
+                if val is real:
+                    setattr(mod, attr, emu)
+    D._torch = _Torch(torch)
+    upload = D.upload
+
+    def upload_copy(arr, non_blocking=False):
+        # on the CPU `from_numpy(...).to(device)` aliases the host array; a device copy never does
+        return upload(arr, non_blocking).clone()
+
+    D.upload = upload_copy
+    for name, mod in list(sys.modules.items()):                  # modules that bound `upload` by name
+        if mod is not None and name.startswith("tinyknn_b200.") and getattr(mod, "upload", None) is upload:
+            mod.upload = upload_copy
+    _installed = True

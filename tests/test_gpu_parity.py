@@ -387,7 +387,8 @@ def _dev_estimates(packed, tables_u8, order, signd, impl):
                                           int(signd), D.ptr(ws), ws.numel(), D.stream_ptr()))
         npatched = int(ws[:8].cpu().numpy().view(np.uint64)[0])
     else:
-        check(lib.tkb_estimate_dev(D.ptr(D.upload(packed)), n_chunks, M, D.ptr(tdev), Q, D.ptr(est), 16 * n_chunks, o,
+        pdev = D.upload(packed)
+        check(lib.tkb_estimate_dev(D.ptr(pdev), n_chunks, M, D.ptr(tdev), Q, D.ptr(est), 16 * n_chunks, o,
                                    int(signd), D.stream_ptr()))
         npatched = 0
     return est.cpu().numpy(), npatched

@@ -12,11 +12,7 @@
 // CTA tile: 128 rows x 64 centroids, 256 threads, 8 x 4 accumulators per thread, k-tiles of 16 staged k-major in shared
 // memory. Each thread keeps the best KSEL (1 or 2) candidates of its rows among its centroid columns; the 16 threads that
 // share a row merge with shuffles at the end. Order of the output: ascending (part, centroid index).
-#ifdef TKB_EMULATE                     // tests/emulate: the kernels of this file compiled for the CPU (no launchers)
-#include "cuda_emu.h"
-#else
 #include "tkb_common.cuh"
-#endif
 
 namespace tkb {
 
@@ -163,7 +159,6 @@ assign_kernel(const T *__restrict__ rows, int64_t n, int d, const T *__restrict_
     }
 }
 
-#ifndef TKB_EMULATE
 template <typename T>
 int assign_t(const T *rows, int64_t n, int d, const T *centers, int C, const T *xnorm, const T *cnorm, int k,
              int32_t *nearest, T *scratch, cudaStream_t st)
@@ -185,11 +180,9 @@ int assign_t(const T *rows, int64_t n, int d, const T *centers, int C, const T *
     return TKB_OK;
 }
 
-#endif  // TKB_EMULATE
 
 }  // namespace
 
-#ifndef TKB_EMULATE
 int launch_assign(const void *rows, int dtype, int64_t n, int d, const void *centers, int C, const void *xnorm,
                   const void *cnorm, int k, int32_t *nearest, void *scratch, int64_t scratch_bytes, cudaStream_t st)
 {
@@ -208,6 +201,5 @@ int launch_assign(const void *rows, int dtype, int64_t n, int d, const void *cen
     return assign_t<float>((const float *)rows, n, d, (const float *)centers, C, (const float *)xnorm, (const float *)cnorm,
                            k, nearest, (float *)scratch, st);
 }
-#endif  // TKB_EMULATE
 
 }  // namespace tkb

@@ -90,10 +90,14 @@ __device__ __forceinline__ int sat_add8(int acc, int t)
 
 __device__ __forceinline__ uint4 ldg_nc_u4(const uint4 *p)
 {
+#ifdef TKB_EMULATE                       // tests/emulate: the source compiled for the CPU, no PTX
+    return *p;
+#else
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
+#endif
 }
 
 // kernels' host-side launchers (one per .cu file), used by tkb_api.cu

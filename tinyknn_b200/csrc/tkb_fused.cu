@@ -81,10 +81,14 @@ __host__ __device__ inline FusedSmem fused_layout(int G, int R, int P, int M, in
 
 __device__ __forceinline__ uint4 ldg_cg_u4(const uint4 *p)
 {
+#ifdef TKB_EMULATE                       // tests/emulate: the source compiled for the CPU, no PTX
+    return *p;
+#else
     uint4 r;
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
+#endif
 }
 
 __device__ __forceinline__ uint32_t fz_cmp_lt4s(uint32_t est4, uint32_t bound4) { return __vcmplts4(est4, bound4); }

@@ -638,10 +638,13 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                 bool active = false;
                 uint32_t rw = 0, jo = 0;
                 int ev = 0;
+                // The root is read AFTER the barrier that ends a step and carried into the next one: the lane that starts an
+                // insert rewrites hw[1] in its first step, and the L lanes of the query must all see the value from before
+                // that write (they replicate the admission state) without relying on lock-step execution inside a step.
+                int rootv = (int)hw[1] >> 24;
                 while (__any_sync(FULL, active || qi < cnt)) {
                     // admission: at most two records per step (the queue is padded with two sentinels)
                     const uint32_t r0 = qu[qi], r1 = qu[qi + 1];
-                    const int rootv = (int)hw[1] >> 24;
                     const bool ok0 = cooldown == 0 && qi < cnt;
                     const uint32_t ch0 = (r0 & 0xffffffu) >> 4, ch1 = (r1 & 0xffffffu) >> 4;
                     const int fr0 = (ok0 && ch0 != cur_chunk) ? rootv : frozen;          // first record of a chunk freezes the bound
@@ -667,8 +670,9 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                     active = active && !stop;
                     if (!active) jo = 0;
                     __syncwarp();
+                    rootv = (int)hw[1] >> 24;
                 }
-                if (mine && role == 0) s_bound[t] = (int)hw[1] >> 24;
+                if (mine && role == 0) s_bound[t] = rootv;
             }
         }
         __syncthreads();

@@ -96,9 +96,13 @@ __device__ void prepare_lut(const uint8_t *__restrict__ tq, int M, bool fast_all
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 {
+#ifdef TKB_EMULATE                       // tests/emulate: the source compiled for the CPU, no PTX
+    return emu::prmt(a, b, s);
+#else
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
     return d;
+#endif
 }
 
 // one sub-quantizer (LUT row L = 16 biased bytes), two code words = 4 groups of 4 vectors

@@ -128,8 +128,12 @@ __host__ __device__ inline size_t scan_smem_carve(unsigned char *base, int M, in
 __device__ __forceinline__ void keep_chunk_in_l2(const uint4 *__restrict__ nat, int64_t c, int Ph)
 {
     const uint4 *base = nat + native_off(c, 0, Ph);
+#ifndef TKB_EMULATE                      // a cache hint: nothing to emulate on the CPU (tests/emulate)
     for (int p = 0; p < Ph; p++)
         asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (size_t)p * TILE));
+#else
+    (void)base;
+#endif
 }
 
 // Smallest of a chunk's 16 estimates (signed or unsigned like the estimates themselves): the heap replay of a long

@@ -166,8 +166,9 @@ class FastPQ:
         books = np.ascontiguousarray(self.centers, dtype=np.float32).reshape(16, M, dpb).transpose(1, 0, 2)
         cnorm = np.stack([np.einsum("ij,ij->i", b, b) for b in books]).astype(np.float32)   # utils.py:78 (Ynorm2, f32)
         out = D.empty((n_out // 16, M), np.int64)
+        cnorm_dev = D.upload(cnorm)                                   # named: the tensor must outlive the launch
         check(lib.tkb_encode_dev(D.ptr(rows), DTYPE_F64 if rows.dtype == t.float64 else DTYPE_F32, n, d,
-                                 D.ptr(row_index), n_out, D.ptr(cen), D.ptr(D.upload(cnorm)), Dp, dpb, D.ptr(R), Dpad,
+                                 D.ptr(row_index), n_out, D.ptr(cen), D.ptr(cnorm_dev), Dp, dpb, D.ptr(R), Dpad,
                                  D.ptr(out), D.stream_ptr()))
         return out
 

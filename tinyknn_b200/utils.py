@@ -133,7 +133,8 @@ def knn_brute_device(X, Y, k, metric="euclidean"):
     xn = _sqnorms(X).astype(T)                       # Xnorm2 / Ynorm2 in their own dtypes, promoted like numpy would
     yn = _sqnorms(Y).astype(T)
     Xd, Yd = D.upload(np.ascontiguousarray(X, dtype=T)), D.upload(np.ascontiguousarray(Y, dtype=T))
+    xnd, ynd = D.upload(xn), D.upload(yn)            # named: the tensors must outlive the launch
     out = D.empty((X.shape[0], k), np.int32)
     check(lib.tkb_assign_dev(D.ptr(Xd), DTYPE_F32 if T == np.float32 else DTYPE_F64, X.shape[0], X.shape[1], D.ptr(Yd),
-                             Y.shape[0], D.ptr(D.upload(xn)), D.ptr(D.upload(yn)), k, D.ptr(out), None, 0, D.stream_ptr()))
+                             Y.shape[0], D.ptr(xnd), D.ptr(ynd), k, D.ptr(out), None, 0, D.stream_ptr()))
     return out.cpu().numpy().astype(int)
