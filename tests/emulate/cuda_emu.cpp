@@ -2,7 +2,9 @@
 #include "cuda_emu.h"
 
 #include <sys/mman.h>
+#if !defined(__x86_64__)
 #include <ucontext.h>
+#endif
 
 #include <deque>
 #include <string>
@@ -17,8 +19,57 @@ namespace {
 constexpr size_t STACK_BYTES = 256 * 1024;
 constexpr uint64_t CANARY = 0xC0DEC0DEDEADBEEFull;
 
+// Context switch. x86-64: a hand-written switch of the callee-saved registers and the stack pointer (ucontext's swapcontext
+// makes a signal-mask system call per switch, and a sync-heavy kernel switches millions of times); elsewhere ucontext.
+#if defined(__x86_64__)
+struct Context { void *sp = nullptr; };
+extern "C" void emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+    .text
+    .globl emu_switch
+    .type emu_switch, @function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size emu_switch, .-emu_switch
+)");
+inline void ctx_switch(Context &from, Context &to) { emu_switch(&from.sp, to.sp); }
+inline void ctx_make(Context &c, unsigned char *stack, size_t bytes, void (*entry)())
+{
+    void **top = reinterpret_cast<void **>(stack + bytes);           // 16-byte aligned
+    top[-1] = nullptr;                                               // where a return address would be: entry never returns
+    top[-2] = reinterpret_cast<void *>(entry);                       // `ret` of the first switch jumps here
+    for (int i = 3; i <= 8; i++) top[-i] = nullptr;                  // rbp rbx r12 r13 r14 r15
+    c.sp = top - 8;
+}
+#else
+struct Context { ucontext_t uc; };
+inline void ctx_switch(Context &from, Context &to) { swapcontext(&from.uc, &to.uc); }
+inline void ctx_make(Context &c, unsigned char *stack, size_t bytes, void (*entry)())
+{
+    getcontext(&c.uc);
+    c.uc.uc_stack.ss_sp = stack;
+    c.uc.uc_stack.ss_size = bytes;
+    c.uc.uc_link = nullptr;
+    makecontext(&c.uc, entry, 0);
+}
+#endif
+
 struct Fiber {
-    ucontext_t ctx;
+    Context ctx;
     uint3 tid;
     unsigned linear = 0;
     bool done = false;
@@ -45,7 +96,7 @@ struct Block {
     size_t smem_bytes = 0;
 };
 
-ucontext_t g_sched;
+Context g_sched;
 Block *g_blk = nullptr;
 int g_cur = -1;
 const std::function<void()> *g_body = nullptr;
@@ -58,7 +109,7 @@ Stats g_stats = {};
 void park()
 {
     g_stats.switches++;
-    swapcontext(&g_blk->fibers[g_cur].ctx, &g_sched);
+    ctx_switch(g_blk->fibers[g_cur].ctx, g_sched);
 }
 
 void wake(std::vector<int> &list)
@@ -98,7 +149,8 @@ void fiber_main()
     w.pad[lane] = 0;
     if (w.arrived > 0 && w.arrived == w.live) { g_stats.collectives_with_exited_lanes++; finish_collective(w); }
     if (b.bar_arrived > 0 && b.bar_arrived == b.live) finish_barrier(b);
-    swapcontext(&f.ctx, &g_sched);            // never resumed
+    ctx_switch(f.ctx, g_sched);               // never resumed
+    abort();
 }
 
 void ensure_stacks(size_t n)
@@ -165,10 +217,14 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
     for (unsigned by = 0; by < grid.y; by++)
     for (unsigned bx = 0; bx < grid.x; bx++) {
         g_stats.blocks++;
-        Block blk;
-        blk.fibers.resize(nthreads);
-        blk.warps.resize((nthreads + 31) / 32);
+        static Block blk;                                           // reused: a fresh 1024-fiber block per CTA costs more than small kernels
+        if (blk.fibers.size() < nthreads) blk.fibers.resize(nthreads);
+        blk.warps.assign((nthreads + 31) / 32, Warp());
+        blk.ready.clear();
+        blk.bar_waiters.clear();
         blk.live = (int)nthreads;
+        blk.bar_arrived = blk.bar_pred = 0;
+        blk.bar_gen = 0;
         blk.smem = smem;
         blk.smem_bytes = smem_bytes;
         std::memset(smem, 0xA5, smem_bytes);                        // shared memory starts uninitialised, not zeroed
@@ -182,11 +238,8 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
             Warp &w = blk.warps[t >> 5];
             w.live++;
             w.live_mask |= 1u << (t & 31);
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = g_stacks + (size_t)t * STACK_BYTES;
-            f.ctx.uc_stack.ss_size = STACK_BYTES;
-            f.ctx.uc_link = &g_sched;
-            makecontext(&f.ctx, fiber_main, 0);
+            f.done = false;
+            ctx_make(f.ctx, g_stacks + (size_t)t * STACK_BYTES, STACK_BYTES, fiber_main);
             blk.ready.push_back((int)t);
             g_stats.fibers++;
         }
@@ -195,7 +248,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
             blk.ready.pop_front();
             threadIdx = blk.fibers[g_cur].tid;
             g_stats.switches++;
-            swapcontext(&g_sched, &blk.fibers[g_cur].ctx);
+            ctx_switch(g_sched, blk.fibers[g_cur].ctx);
         }
         g_cur = -1;
         if (blk.live != 0) {                                        // parked fibers nobody will wake: a divergent barrier / collective

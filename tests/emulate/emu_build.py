@@ -92,7 +92,7 @@ def sources():
 def source_hash():
     h = hashlib.sha256(" ".join(CXXFLAGS).encode())
     cu, hdr = sources()
-    for p in cu + hdr + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "emu_build.py", "shim/cuda_runtime.h")]:
+    for p in cu + hdr + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "emu_build.py", "shim/cuda_runtime.h", "selftest.cu")]:
         with open(p, "rb") as f:
             h.update(f.read())
     return h.hexdigest()
@@ -112,7 +112,7 @@ def build(force=False, verbose=False):
             with open(os.path.join(OUT, "src", os.path.basename(path)), "w") as f:
                 f.write('#line 1 "%s"\n' % path)
                 f.write(translate(open(path).read())[0])
-    for path in cu:
+    for path in cu + [os.path.join(HERE, "selftest.cu")]:
         text, n_launch, n_sm = translate(open(path).read())
         total_launch += n_launch
         if verbose:

@@ -1,9 +1,17 @@
-"""The SOURCE of tkb_assign.cu's kernels executed on the CPU (tests/emulate/cuda_emu.h: one OS thread per CUDA thread, real
-barriers, emulated warp shuffles) and checked against the oracle. The kernel was written after round 1's GPU budget was
-spent; this is what stands in for a GPU run of its logic (tiling, barrier placement, top-k merge, edge tiles) until then."""
-import ctypes
+"""The library's CUDA SOURCES executed on the CPU (tests/emulate: launch syntax translated, every CUDA thread a fiber, real
+__syncthreads / warp-collective semantics, "device" memory = host memory) and checked against the oracle -- what stands in for
+a GPU in the container that builds this repo, and the first validation of code written after a round's GPU budget was spent.
+
+Three layers:
+  * the emulator checks itself (collectives, barriers, SIMD-in-a-word intrinsics against scalar definitions, and the
+    conditions it must REPORT: a divergent barrier, a write past the end of dynamic shared memory);
+  * the C ABI called directly with numpy buffers (scan, heap replay, probe planning) against the oracle;
+  * the gpu-marked test files run unchanged with TKB_EMU=1 (tests/conftest.py installs tests/emulate/emu_torch.py: the package's
+    host layer on CPU tensors + the emulated library), in a subprocess, minus the cases that are too slow without a GPU.
+This is test infrastructure: the package itself never loads the emulated library and has no CPU path."""
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -11,53 +19,181 @@ import pytest
 from oracle import restate as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EMU = os.path.join(ROOT, "tests", "emulate")
+sys.path.insert(0, os.path.join(ROOT, "tests", "emulate"))
 
 
 @pytest.fixture(scope="module")
 def emu():
-    out = os.path.join(EMU, "_build", "libassign_emu.so")
-    src = [os.path.join(EMU, "assign_emu.cpp"), os.path.join(EMU, "cuda_emu.h"), os.path.join(ROOT, "tinyknn_b200", "csrc", "tkb_assign.cu")]
-    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in src):
-        os.makedirs(os.path.dirname(out), exist_ok=True)
-        cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-ffp-contract=off", "-mfma", "-DTKB_EMULATE", "-I", EMU, "-shared", "-fPIC",
-               src[0], "-o", out]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            pytest.skip("cannot compile the emulation harness: " + r.stderr[-300:])
-    L = ctypes.CDLL(out)
-    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
-    L.emu_assign_f32.argtypes = L.emu_assign_f64.argtypes = [vp, i64, i32, vp, i32, vp, vp, i32, vp]
-    L.emu_row_sqnorm_f32.argtypes = [vp, i64, i32, vp]
-    return L
+    import emu_lib
+    try:
+        emu_lib.load()
+    except Exception as e:                                           # noqa: BLE001
+        pytest.skip("cannot build the emulated library: %s" % str(e)[-400:])
+    return emu_lib
 
 
-@pytest.mark.parametrize("n,d,C,dtype", [(300, 100, 150, np.float32), (129, 20, 37, np.float32), (128, 16, 64, np.float32),
-                                         (70, 7, 3, np.float32), (200, 128, 65, np.float64)])
-def test_assign_kernel_source_on_cpu(emu, n, d, C, dtype):
-    rng = np.random.default_rng(n + d + C)
-    means = rng.standard_normal((C, d)) * 2
-    X = np.ascontiguousarray(means[rng.integers(C, size=n)] + rng.standard_normal((n, d)), dtype=dtype)
-    Y = np.ascontiguousarray(means + 0.1 * rng.standard_normal((C, d)), dtype=dtype)
-    xn, yn = np.einsum("ij,ij->i", X, X), np.einsum("ij,ij->i", Y, Y)
-    part = xn[:, None] + yn[None] - 2 * X @ Y.T                                   # utils.py:80-83
-    fn = emu.emu_assign_f32 if dtype == np.float32 else emu.emu_assign_f64
-    for k in (1, 2):
-        if k > C:
+# ---- the emulator itself -----------------------------------------------------------------------------------------------------
+
+def test_emulator_warp_collectives(emu):
+    L = emu.load()
+    T = 96
+    out = np.zeros((T, 8), np.uint32)
+    assert L.emu_selftest_collectives(out.ctypes.data, T) == 0
+    lane, warp = np.arange(T) % 32, np.arange(T) // 32
+    ballot = sum(1 << i for i in range(32) if i % 3 == 0)
+    assert np.all(out[:, 0] == ballot)
+    assert np.array_equal(out[:, 1], 100 * warp + 5)
+    assert np.array_equal(out[:, 2], lane ^ 16)
+    assert np.array_equal(out[:, 3], np.where(lane >= 3, lane - 3, lane))
+    assert np.array_equal(out[:, 4], np.where(lane + 30 < 32, lane + 30, lane))
+    assert np.array_equal(out[:, 5], (warp == 1).astype(np.uint32))            # __any_sync is per warp
+    assert np.all(out[:, 6] == 1)
+    assert np.array_equal(out[:, 7], lane * (lane + 1) // 2)
+
+
+def test_emulator_barriers_and_shared_memory(emu):
+    L = emu.load()
+    blocks, T, rounds = 3, 128, 3
+    out = np.zeros((blocks, 2), np.int32)
+    assert L.emu_selftest_barrier(out.ctypes.data, blocks, T, rounds) == 0
+    assert np.all(out[:, 0] == sum(0 + r for r in range(rounds)))              # thread T-1 reads thread 0's slot after the barrier
+    assert np.all(out[:, 1] == 1)                                              # __syncthreads_or: one thread's predicate reaches all
+    out = np.zeros((blocks, 2), np.int32)
+    assert L.emu_selftest_barrier(out.ctypes.data, blocks, T, 2) == 0
+    assert np.all(out[:, 1] == 0)
+    res = np.zeros(256, np.int32)
+    assert L.emu_selftest_early_exit(res.ctypes.data, 256, 100) == 0           # 156 threads return before the barrier
+    assert np.all(res[:100] == 100) and np.all(res[100:] == 0)
+
+
+def test_emulator_reports_divergent_barrier_and_smem_overrun(emu):
+    L = emu.load()
+    out = np.zeros(4, np.int32)
+    assert L.emu_selftest_divergent(out.ctypes.data) != 0
+    assert b"deadlock" in L.emu_last_error()
+    assert L.emu_selftest_overrun(256) != 0
+    assert b"shared memory" in L.emu_last_error()
+    assert L.emu_selftest_barrier(np.zeros((1, 2), np.int32).ctypes.data, 1, 64, 1) == 0     # and it recovers
+
+
+def test_emulator_simd_intrinsics_match_scalar_definitions(emu):
+    L = emu.load()
+    rng = np.random.default_rng(0)
+    n = 4000
+    a, b, c = (rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32) for _ in range(3))
+    edge = np.array([0, 0x7fff7fff, 0x80008000, 0xffffffff, 0x007f007f, 0xff80ff80, 0x7f7f7f7f, 0x80808080], np.uint32)
+    a[:8], b[8:16], c[16:24] = edge, edge, edge
+    out = np.zeros((n, 12), np.uint32)
+    assert L.emu_selftest_simd(a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data, n) == 0
+
+    def halves(x, signed):
+        h = np.stack([x & 0xffff, x >> 16], 1).astype(np.int64)
+        return np.where(h >= 0x8000, h - 0x10000, h) if signed else h
+
+    def pack2(h):
+        h = h.astype(np.int64) & 0xffff
+        return (h[:, 0] | (h[:, 1] << 16)).astype(np.uint32)
+
+    def bytes_(x, signed):
+        v = np.stack([(x >> (8 * i)) & 0xff for i in range(4)], 1).astype(np.int64)
+        return np.where(v >= 0x80, v - 0x100, v) if signed else v
+
+    def pack4(v):
+        v = v.astype(np.int64) & 0xff
+        return (v[:, 0] | (v[:, 1] << 8) | (v[:, 2] << 16) | (v[:, 3] << 24)).astype(np.uint32)
+
+    wrap16 = lambda h: ((h + 0x8000) % 0x10000) - 0x8000                                    # noqa: E731
+    assert np.array_equal(out[:, 0], pack2(halves(a, False) + halves(b, False)))
+    assert np.array_equal(out[:, 1], pack2(np.minimum(np.minimum(halves(a, True), halves(b, True)), halves(c, True))))
+    assert np.array_equal(out[:, 2], pack2(np.maximum(np.maximum(halves(a, True), halves(b, True)), halves(c, True))))
+    assert np.array_equal(out[:, 3], pack2(np.minimum(np.minimum(halves(a, False), halves(b, False)), halves(c, False))))
+    assert np.array_equal(out[:, 4], pack2(np.maximum(wrap16(halves(a, True) + halves(b, True)), halves(c, True))))
+    assert np.array_equal(out[:, 5], pack2(np.minimum((halves(a, False) + halves(b, False)) % 0x10000, halves(c, False))))
+    assert np.array_equal(out[:, 6], pack4(np.minimum(bytes_(a, True), bytes_(b, True))))
+    assert np.array_equal(out[:, 7], pack4(np.minimum(bytes_(a, False), bytes_(b, False))))
+    assert np.array_equal(out[:, 8], pack4(np.where(bytes_(a, True) < bytes_(b, True), 0xff, 0)))
+    assert np.array_equal(out[:, 9], pack4(np.where(bytes_(a, False) < bytes_(b, False), 0xff, 0)))
+    s32 = lambda x: x.astype(np.int64) - ((x.astype(np.int64) >> 31) << 32)                 # noqa: E731
+    wrap32 = lambda v: ((v + 2 ** 31) % 2 ** 32) - 2 ** 31                                  # noqa: E731
+    assert np.array_equal(out[:, 10], (np.minimum(wrap32(s32(a) + s32(b)), s32(c)) % 2 ** 32).astype(np.uint32))
+    # prmt.b32, default mode (PTX ISA): selector nibble i picks byte (n & 7) of {a, b}; bit 3 replicates that byte's sign bit
+    src = np.concatenate([bytes_(a, False), bytes_(b, False)], 1)
+    sel = np.stack([(c >> (4 * i)) & 0xf for i in range(4)], 1).astype(np.int64)
+    picked = np.take_along_axis(src, sel & 7, 1)
+    picked = np.where(sel & 8, np.where(picked & 0x80, 0xff, 0), picked)
+    assert np.array_equal(out[:, 11], pack4(picked))
+
+
+# ---- the C ABI on numpy buffers ------------------------------------------------------------------------------------------------
+
+def _tables(rng, M, signd, kind):
+    if kind == "full":
+        return rng.integers(0, 256, size=(M, 16)).astype(np.uint8)
+    if kind == "hot":                                                # small range, large values: many saturations
+        t = rng.integers(8, 30, size=(M, 16)).astype(np.int16)
+        return (t - (20 if signd else 0)).astype(np.int8).view(np.uint8)
+    t = np.round(rng.exponential(6.0, size=(M, 16)) - 4).clip(-4, 128 / M ** 0.5).astype(np.int8)
+    return t.view(np.uint8) if signd else (t + 4).astype(np.uint8)
+
+
+@pytest.mark.parametrize("M", [52, 32, 8, 20])
+def test_fast_scan_source_bit_exact(emu, M):
+    """tkb_codes_to_native_dev + tkb_estimate_native_dev (PRMT lookups, deferred clamps, certificate, deferred exact pass) for
+    the compile-time pair counts of BASELINE.json's shapes (M = 52, 32) and the generic loop, both orders, signed/unsigned."""
+    L = emu.load()
+    rng = np.random.default_rng(M)
+    for order, signd, kind in [("avx", 1, "lut"), ("avx", 1, "hot"), ("avx", 1, "full"), ("avx", 0, "lut"), ("sse", 1, "lut"),
+                               ("sse", 0, "hot")]:
+        if order == "avx" and M % 4:
             continue
-        out = np.full((n, k), -7, np.int32)
-        fn(X.ctypes.data, n, d, Y.ctypes.data, C, xn.ctypes.data, yn.ctypes.data, k, out.ctypes.data)
-        if k == 1:
-            assert np.array_equal(out[:, 0], O.knn_brute(X, Y, 1)[:, 0])
-        else:
-            assert np.array_equal(np.sort(out, axis=1), np.sort(O.knn_brute(X, Y, 2), axis=1))
-            assert np.all(part[np.arange(n), out[:, 0]] <= part[np.arange(n), out[:, 1]])
-            assert np.array_equal(out[:, 0], O.knn_brute(X, Y, 1)[:, 0])
+        n = int(rng.integers(1, 3000))
+        codes = rng.integers(0, 16, size=(-(-n // 16) * 16, M), dtype=np.uint8)
+        packed = np.ascontiguousarray(O.transform_data(codes))
+        nch = len(packed)
+        Q = 3
+        tabs = emu.aligned((Q, M, 16), np.uint8)
+        tabs[:] = np.stack([_tables(rng, M, signd, kind) for _ in range(Q)])
+        nat = emu.aligned((-(-nch // 8) * 8 * M * 8,), np.uint8)
+        emu.check(L.tkb_codes_to_native_dev(emu.ptr(packed), nch, M, emu.ptr(nat), None))
+        back = np.zeros_like(packed)
+        emu.check(L.tkb_codes_from_native_dev(emu.ptr(nat), nch, M, emu.ptr(back), None))
+        assert np.array_equal(back, packed)
+        est, ws = emu.aligned((Q, 16 * nch), np.uint8), emu.aligned((64,), np.uint8)
+        emu.check(L.tkb_estimate_native_dev(emu.ptr(nat), nch, M, emu.ptr(tabs), Q, emu.ptr(est), 16 * nch,
+                                            1 if order == "avx" else 0, signd, emu.ptr(ws), 64, None))
+        for q in range(Q):
+            exp = np.zeros(2 * nch, np.uint64)
+            O.estimate_pq(packed, O.transform_tables(tabs[q]), exp, bool(signd), order)
+            assert np.array_equal(est[q], exp.view(np.uint8)), (M, order, signd, kind, q)
 
 
-def test_row_sqnorm_kernel_source_on_cpu(emu):
-    rng = np.random.default_rng(1)
-    X = rng.standard_normal((300, 2)).astype(np.float32)                          # dpb-sized rows: einsum == mul-add
-    out = np.empty(300, np.float32)
-    emu.emu_row_sqnorm_f32(X.ctypes.data, 300, 2, out.ctypes.data)
-    assert np.array_equal(out, np.einsum("ij,ij->i", X, X))
+def test_emulated_abi_reports_errors_like_the_real_one(emu):
+    L = emu.load()
+    assert L.tkb_estimate_native_dev(None, 4, 6, None, 1, None, 64, 1, 1, None, 0, None) == 1          # avx order needs M % 4 == 0
+    assert b"M % 4" in L.tkb_last_error()
+
+
+# ---- the gpu-marked test files on the emulator -------------------------------------------------------------------------------
+
+# too slow without a GPU (minutes each) or not emulable (CUDA graphs, pinned host memory)
+_SKIP_ON_EMULATOR = ("test_replay_deep_heaps and 70000", "test_glove_shape_full_size_properties", "test_graphed_batch_equals_eager",
+                     "test_async_results_equal_sync", "test_estimate_large_bit_exact", "test_fast_scan_large_and_patch_rate",
+                     "test_query_batch_with_chunk_minima_equals_plain", "test_encode_device_large_matches_oracle_and_scan_roundtrip")
+
+
+def test_gpu_test_files_pass_on_the_emulator(emu):
+    """tests/test_gpu_parity.py, test_fused_gpu.py and the quarantined test_unvalidated_gpu.py (code that has not run on
+    hardware yet: coarse assignment kernel, chunk minima inside the push exchange, saved-index queries), executed with
+    TKB_EMU=1: the product's host layer and kernel sources against the oracle and the golden fixtures."""
+    emu.load()                                                       # build once, before the child starts
+    env = dict(os.environ, TKB_EMU="1", TKB_RUN_UNVALIDATED="1", OMP_NUM_THREADS="2")
+    k = " and ".join("not (%s)" % s for s in _SKIP_ON_EMULATOR)
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider", "-k", k,
+           os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_fused_gpu.py"),
+           os.path.join(ROOT, "tests", "test_unvalidated_gpu.py")]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    tail = r.stdout[-3000:] + r.stderr[-1500:]
+    assert r.returncode == 0, tail
+    last = r.stdout.strip().splitlines()[-1]
+    assert " passed" in last and "failed" not in last, tail
+    assert int(last.split(" passed")[0].split()[-1]) >= 140, last
