@@ -286,6 +286,19 @@ TKB_API int tkb_select_probes_dev(const int64_t *heap_idx, const void *dists, in
 TKB_API int tkb_select_topk_dev(const int64_t *heap_idx, const void *dists, int dists_dtype, int Q, int R,
                         int k, int64_t *out_ids, void *out_dists, int32_t *out_count, void *stream);
 
+/* Probe selection as ONE kernel: replaces `dtable.top(pq_transformed_centers, active_centers, k=n_probes)` of IVF.query
+ * (ref: tinyknn/ivf.py:131 -> tinyknn/fast_pq.py:284-312) for Q queries: the scan of the PQ-encoded centroids, the exact
+ * replay of the reference heap of R = min(2 * n_probes + 10, C) slots (signed tables, label = centroid position), the exact
+ * distances of the candidates to the raw centroids (knn_brute1) and the P nearest in device order. Same results as
+ * tkb_estimate_native_dev + tkb_replay_fresh_dev + tkb_gather_dists_dev + tkb_select_probes_dev, bit for bit (R <= P: the
+ * raw heap, INT32_MIN in the missing slots). R <= 1024.
+ *   native_centers : encoded centroids in the native layout (n_chunks chunks, C real vectors); centers f32[C][d]
+ *   tables uint8[Q][M][16]; queries f32[Q][d] (normalised for angular); probes int32[Q][P] out
+ *   heap_idx int64[Q][R], heap_val int32[Q][R], dists f32[Q][R] : optional outputs (NULL to skip) */
+TKB_API int tkb_coarse_probes_dev(const void *native_centers, int64_t n_chunks, int C, int M, const uint8_t *tables, int Q,
+                          const float *centers, int d, const float *queries, int R, int P, int order, int32_t *probes,
+                          int64_t *heap_idx, int32_t *heap_val, float *dists, void *stream);
+
 /* The IVF.query body after probe selection as ONE kernel (ref: tinyknn/ivf.py:135-163): for each query, scan of
  * the probed lists (query_pq_*'s scan half), exact replay of the reference heap of R slots in probe order
  * (query_pq_*'s heap half with labels = ids), removal of the -1 padding, exact distances of the candidates

@@ -53,6 +53,7 @@ SIGNATURES = {
     "tkb_ivf_replay_fresh_cm_dev": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
     "tkb_gather_dists_dev": [_vp, _i, _i64, _i, _vp, _vp, _i, _i, _vp, _vp],
     "tkb_select_probes_dev": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "tkb_coarse_probes_dev": [_vp, _i64, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "tkb_select_topk_dev": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "tkb_ivf_query_fused_workspace": [_i, _i, _i, _i, _i, _i, _i64, _c.POINTER(_c.c_int64)],
     "tkb_ivf_query_fused_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i64, _i, _vp, _i, _i, _i, _i64,

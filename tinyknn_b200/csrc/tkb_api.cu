@@ -378,6 +378,14 @@ int tkb_select_probes_dev(const int64_t *heap_idx, const void *dists, int dists_
     return launch_select_probes(heap_idx, dists, dists_dtype, Q, R, P, probes, (cudaStream_t)stream);
 }
 
+int tkb_coarse_probes_dev(const void *native_centers, int64_t n_chunks, int C, int M, const uint8_t *tables, int Q,
+                          const float *centers, int d, const float *queries, int R, int P, int order, int32_t *probes,
+                          int64_t *heap_idx, int32_t *heap_val, float *dists, void *stream)
+{
+    return launch_coarse_probes(native_centers, n_chunks, C, M, tables, Q, centers, d, queries, R, P, order, probes, heap_idx,
+                                heap_val, dists, (cudaStream_t)stream);
+}
+
 int tkb_select_topk_dev(const int64_t *heap_idx, const void *dists, int dists_dtype, int Q, int R,
                         int k, int64_t *out_ids, void *out_dists, int32_t *out_count, void *stream)
 {

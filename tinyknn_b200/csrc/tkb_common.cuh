@@ -147,6 +147,9 @@ int launch_select_probes(const int64_t *heap_idx, const void *dists, int dtype, 
                          int32_t *probes, cudaStream_t st);
 int launch_select_topk(const int64_t *heap_idx, const void *dists, int dtype, int Q, int R, int k,
                        int64_t *out_ids, void *out_dists, int32_t *out_count, cudaStream_t st);
+int launch_coarse_probes(const void *native_centers, int64_t n_chunks, int C, int M, const uint8_t *tables, int Q,
+                         const float *centers, int d, const float *queries, int R, int P, int order, int32_t *probes,
+                         int64_t *heap_idx, int32_t *heap_val, float *dists, cudaStream_t st);
 int fused_workspace_bytes(int Q, int P, int R, int M, int order, int rows_dtype, int64_t max_list_chunks, int64_t *bytes);
 int launch_ivf_query_fused(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                            const uint8_t *tables, const int32_t *probes, int Q, int P, const int64_t *ids,

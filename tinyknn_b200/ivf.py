@@ -37,6 +37,9 @@ FUSED = os.environ.get("TKB_FUSED", "0") != "0"
 # Chunk minima (tkb_ivf_scan_native_cm_dev / tkb_ivf_replay_fresh_cm_dev) when a query may scan at least this many chunks:
 # the replay of long probe lists then reads 1 byte per chunk instead of 16. 0 disables.
 CMIN_CHUNKS = int(os.environ.get("TKB_CMIN_CHUNKS", "8192"))
+# Probe selection as one kernel (tkb_coarse_probes_dev) instead of scan / replay / gather / select. Opt-in until it has been
+# timed on hardware; results are identical (tests/test_fused_gpu.py).
+COARSE_FUSED = os.environ.get("TKB_COARSE_FUSED", "0") != "0"
 # IVF.build: coarse assignment on the GPU (tkb_assign_dev). Opt-in until it has been validated on hardware.
 ASSIGN_DEVICE = os.environ.get("TKB_ASSIGN_DEVICE", "0") != "0"
 _streams = {}
@@ -329,6 +332,14 @@ class IVF:
         sg = 1                                                           # IVF.query hard-codes signed=True (ivf.py:138,148)
         tables, qn = lut["tables"], lut["q"]
         cc, nck = dev["center_codes"], dev["center_chunks"]
+        if COARSE_FUSED and order == "device" and _fp.SCAN_IMPL == "fast" and Rc <= 1024 and nck <= 4096:
+            hci, hcv = D.empty((Q, Rc), np.int64), D.empty((Q, Rc), np.int32)
+            probes = D.empty((Q, P), np.int32)
+            with self._stage("coarse_fused"):
+                check(lib.tkb_coarse_probes_dev(D.ptr(cc), nck, C, M, D.ptr(tables), Q, D.ptr(dev["centers"]), dev["d"], D.ptr(qn),
+                                                Rc, P, _fp._order(), D.ptr(probes), D.ptr(hci), D.ptr(hcv), None, st))
+            self._last = dict(center_heap=hci, tables=tables)
+            return probes
         est_c = D.empty((Q, 16 * nck), np.uint8)
         with self._stage("coarse_scan"):
             if _fp.SCAN_IMPL == "fast":
