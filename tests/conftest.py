@@ -24,6 +24,12 @@ def pytest_configure(config):
         emu_torch.install()
 
 
+def pytest_terminal_summary(terminalreporter):
+    if EMU:
+        import emu_lib
+        terminalreporter.write_line("emulator: %s" % emu_lib.stats())
+
+
 def pytest_collection_modifyitems(config, items):
     # GPU tests skip themselves cleanly when collected on a machine without a device.
     try:

@@ -76,7 +76,7 @@ struct Fiber {
 };
 
 struct Warp {
-    int live = 0, arrived = 0;
+    int live = 0, arrived = 0, created = 0;
     unsigned gen = 0;
     unsigned live_mask = 0;
     uint64_t pad[32] = {0};
@@ -190,6 +190,7 @@ const uint64_t *warp_gather(uint64_t v)
     const unsigned linear = b.fibers[g_cur].linear;
     Warp &w = b.warps[linear >> 5];
     g_stats.collectives++;
+    if (w.live != w.created && w.arrived == 0) g_stats.collectives_with_exited_lanes++;     // legal only with a partial mask
     const unsigned gen = w.gen;
     w.pad[linear & 31] = v;
     w.arrived++;
@@ -237,6 +238,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
             f.tid.x = t % block.x; f.tid.y = (t / block.x) % block.y; f.tid.z = t / (block.x * block.y);
             Warp &w = blk.warps[t >> 5];
             w.live++;
+            w.created++;
             w.live_mask |= 1u << (t & 31);
             f.done = false;
             ctx_make(f.ctx, g_stacks + (size_t)t * STACK_BYTES, STACK_BYTES, fiber_main);

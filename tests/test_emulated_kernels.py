@@ -194,6 +194,10 @@ def test_gpu_test_files_pass_on_the_emulator(emu):
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = r.stdout[-3000:] + r.stderr[-1500:]
     assert r.returncode == 0, tail
-    last = r.stdout.strip().splitlines()[-1]
+    lines = r.stdout.strip().splitlines()
+    last = lines[-1]
     assert " passed" in last and "failed" not in last, tail
     assert int(last.split(" passed")[0].split()[-1]) >= 140, last
+    # no kernel ever ran a full-mask warp collective after some of the warp's lanes had returned
+    stats = [ln for ln in lines if ln.startswith("emulator:")]
+    assert stats and "'collectives_with_exited_lanes': 0" in stats[-1], stats
