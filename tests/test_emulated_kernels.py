@@ -201,3 +201,26 @@ def test_gpu_test_files_pass_on_the_emulator(emu):
     # no kernel ever ran a full-mask warp collective after some of the warp's lanes had returned
     stats = [ln for ln in lines if ln.startswith("emulator:")]
     assert stats and "'collectives_with_exited_lanes': 0" in stats[-1], stats
+
+
+REFERENCE_TESTS = "/root/reference/tests"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_TESTS), reason="the reference checkout is only present in the build container")
+def test_reference_own_test_files_pass_unmodified_on_the_emulator(emu):
+    """Drop-in check: the reference's own test files (tests/test_pq.py, test_ivf.py, test_multiprobe.py, test_heap.py,
+    test_transform.py, test_utils.py), collected from the read-only checkout and run UNMODIFIED with `tinyknn` aliased to this
+    package on the emulator (tests/emulate/ref_alias_plugin.py): every kernel call goes through the C ABI into the CUDA sources."""
+    emu.load()
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", OMP_NUM_THREADS="2",
+               PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests", "emulate"), ROOT, os.environ.get("PYTHONPATH", "")]))
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        cmd = [sys.executable, "-m", "pytest", "-q", "-p", "ref_alias_plugin", "-p", "no:cacheprovider", "--rootdir", tmp,
+               "-c", os.devnull, "-W", "ignore", REFERENCE_TESTS]
+        r = subprocess.run(cmd, cwd=tmp, env=env, capture_output=True, text=True, timeout=900)
+    tail = r.stdout[-3000:] + r.stderr[-1500:]
+    assert r.returncode == 0, tail
+    last = r.stdout.strip().splitlines()[-1]
+    assert " passed" in last and "failed" not in last and "error" not in last, tail
+    assert int(last.split(" passed")[0].split()[-1]) >= 120, last
