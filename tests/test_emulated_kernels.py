@@ -224,3 +224,25 @@ def test_reference_own_test_files_pass_unmodified_on_the_emulator(emu):
     last = r.stdout.strip().splitlines()[-1]
     assert " passed" in last and "failed" not in last and "error" not in last, tail
     assert int(last.split(" passed")[0].split()[-1]) >= 120, last
+
+
+def test_bench_dry_run_on_the_emulator_prints_the_contract_line(emu):
+    """bench.py's main() end to end (index build, parity gate, timed loop, stage timing, e2e loop, CPU arm, JSON line) with
+    the library and torch.cuda emulated (tests/emulate/emu_bench.py, `tiny` workload): the numbers mean nothing, the keys and
+    the parity gate do -- a Python-level mistake in bench.py must not wait for the GPU box to show up."""
+    import json
+    emu.load()
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emulate", "emu_bench.py"), "--workload", "tiny", "--queries", "128",
+           "--steps", "2", "--warmup", "3", "--cpu-seconds", "1"]
+    r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, OMP_NUM_THREADS="2"), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["steps"] == 2 and line["warmup"] == 3 and line["n_gpus"] == 1 and line["gpu_launches"] > 0
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and line["e2e"]["h2d_bytes_per_step"] == 128 * 100 * 4
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and line["roofline"]["bound"] == "hbm"
+    assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert line["parity"]["id_set_mismatch"] == 0 and line["parity"]["device_order_id_set_mismatch"] == 0
