@@ -1,12 +1,15 @@
 // cuda_emu.cpp -- fiber scheduler and runtime shim behind cuda_emu.h (TEST INFRASTRUCTURE ONLY).
 #include "cuda_emu.h"
 
+#include <fcntl.h>
 #include <sys/mman.h>
+#include <unistd.h>
 #if !defined(__x86_64__)
 #include <ucontext.h>
 #endif
 
 #include <deque>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -303,12 +306,48 @@ const char *cudaGetErrorString(cudaError_t e)
     if (e == cudaSuccess) return "no error";
     return emu::g_error.empty() ? "emulated CUDA error" : emu::g_error.c_str();
 }
+// cudaMalloc'ed memory is backed by a POSIX shared-memory object, so that the CUDA IPC calls (the push exchange's peer-mapped
+// receive buffers, one process per "GPU") work between emulated processes: the handle carries the object's name, opening it
+// maps the same pages at another address -- like a real peer mapping.
+namespace {
+struct Alloc { std::string name; size_t bytes; bool owner; };
+std::map<void *, Alloc> g_allocs;
+int g_alloc_seq = 0;
+struct UnlinkAtExit {                                               // scratch buffers the library never frees
+    ~UnlinkAtExit() { for (auto &kv : g_allocs) if (kv.second.owner) shm_unlink(kv.second.name.c_str()); }
+} g_unlink_at_exit;
+
+void *map_shm(const std::string &name, size_t bytes, bool create)
+{
+    const int fd = shm_open(name.c_str(), create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0) return nullptr;
+    if (create && ftruncate(fd, (off_t)bytes) != 0) { close(fd); shm_unlink(name.c_str()); return nullptr; }
+    void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    return p == MAP_FAILED ? nullptr : p;
+}
+}  // namespace
+
 cudaError_t cudaMalloc(void **p, size_t bytes)
 {
-    *p = aligned_alloc(256, (bytes + 255) / 256 * 256 + 256);
-    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+    const size_t padded = (bytes + 4095) / 4096 * 4096 + 4096;
+    char name[64];
+    snprintf(name, sizeof name, "/tkbemu_%d_%d", (int)getpid(), g_alloc_seq++);
+    *p = map_shm(name, padded, true);
+    if (!*p) return cudaErrorMemoryAllocation;
+    g_allocs[*p] = Alloc{name, padded, true};
+    return cudaSuccess;
 }
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaFree(void *p)
+{
+    if (!p) return cudaSuccess;
+    auto it = g_allocs.find(p);
+    if (it == g_allocs.end() || !it->second.owner) return cudaErrorInvalidValue;
+    munmap(p, it->second.bytes);
+    shm_unlink(it->second.name.c_str());
+    g_allocs.erase(it);
+    return cudaSuccess;
+}
 cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t) { std::memmove(dst, src, bytes); return cudaSuccess; }
 cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind) { std::memmove(dst, src, bytes); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void *dst, int value, size_t bytes, cudaStream_t) { std::memset(dst, value, bytes); return cudaSuccess; }
@@ -321,7 +360,33 @@ cudaError_t cudaDeviceGetAttribute(int *value, cudaDeviceAttr attr, int)
     *value = attr == cudaDevAttrMultiProcessorCount ? 148 : 0;
     return cudaSuccess;
 }
-// "IPC" inside one process: the handle carries the pointer
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { std::memset(h, 0, sizeof *h); std::memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
-cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
-cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p)
+{
+    auto it = g_allocs.find(p);
+    if (it == g_allocs.end()) return cudaErrorInvalidValue;
+    std::memset(h, 0, sizeof *h);
+    snprintf(h->reserved, 48, "%s", it->second.name.c_str());
+    const uint64_t bytes = it->second.bytes;
+    std::memcpy(h->reserved + 48, &bytes, 8);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned)
+{
+    h.reserved[47] = 0;
+    uint64_t bytes = 0;
+    std::memcpy(&bytes, h.reserved + 48, 8);
+    for (auto &kv : g_allocs)                                       // CUDA refuses to open a handle in the exporting process
+        if (kv.second.owner && kv.second.name == h.reserved) return cudaErrorInvalidValue;
+    *p = map_shm(h.reserved, bytes, false);
+    if (!*p) return cudaErrorInvalidValue;
+    g_allocs[*p] = Alloc{h.reserved, bytes, false};
+    return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void *p)
+{
+    auto it = g_allocs.find(p);
+    if (it == g_allocs.end() || it->second.owner) return cudaErrorInvalidValue;
+    munmap(p, it->second.bytes);
+    g_allocs.erase(it);
+    return cudaSuccess;
+}

@@ -41,6 +41,18 @@ torch.Tensor.pin_memory = lambda self, *a, **k: self
 _tensor = torch.tensor
 torch.tensor = lambda *a, **k: _tensor(*a, **{x: y for x, y in k.items() if x != "device"})
 
+import torch.distributed as _dist                                   # noqa: E402
+
+_init = _dist.init_process_group
+
+
+def _init_gloo(backend=None, **kw):                                 # N > 1 dry runs: gloo stands in for NCCL
+    kw.pop("device_id", None)
+    return _init("gloo", **kw)
+
+
+_dist.init_process_group = _init_gloo
+
 import __graft_entry__                                             # noqa: E402
 
 __graft_entry__.build = lambda: None                               # the real build ran already; nothing to compile here

@@ -289,3 +289,78 @@ def test_push_exchange_host_logic_gloo_world2(tmp_path):
         for b in blocks:
             b.close()
             b.unlink()
+
+
+# ---- the REAL list-sharded path (ShardedIVF + the kernels' sources) on the CPU emulator, two processes over gloo -----------------
+
+def _emu_worker(rank, world, port, out):
+    """tests/test_sharded_gpu.py's worker with gloo for NCCL and the emulated library for the GPU (tests/emulate): both
+    exchanges -- the all-to-all and the push exchange, where the scan kernel of one process stores into the other's receive
+    buffer (emulated CUDA IPC = POSIX shared memory) --, chunk minima inside the push exchange, and the broadcast that gives
+    every rank rank 0's index."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emulate"))
+    import torch.distributed as dist
+    import emu_torch
+    emu_torch.install()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tinyknn_b200 import synth, sharded as SH, ivf as ivf_mod
+        from tinyknn_b200.sharded import ShardedIVF
+        X = synth.clustered(12_000 + 256, 32, 40, seed=3)
+        ivf = synth.build_ivf(X[:12_000], "euclidean", 24, seed=3, deterministic=True)
+        qs = X[12_000:].contiguous()
+        Qh = 256 // world
+        mine = qs[rank * Qh:(rank + 1) * Qh].contiguous()
+        bad = 0
+        bad += not synth.index_consistent(ivf, dist)                   # same seed, deterministic build: identical indexes
+        ref = ivf.query_batch(mine, 10, n_probes=5, order="device", return_distances=True)
+        sh = ShardedIVF(ivf)
+        used = []
+        for exchange in ("nccl", "push", "push", "push"):              # repeated pushes alternate the receive buffers
+            got = sh.query_batch(mine, 10, n_probes=5, return_distances=True, exchange=exchange)
+            bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
+            used.append(sh.last_exchange)
+        bad += used != ["nccl", "push", "push", "push"]
+        SH.PUSH_CMIN, ivf_mod.CMIN_CHUNKS = True, 1                    # chunk minima travel with the pushed estimates
+        for _ in range(2):
+            got = sh.query_batch(mine, 10, n_probes=5, return_distances=True, exchange="push")
+            bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
+        sh.close()
+        # one index for the whole job: rank 1 loses its copy, the fingerprints differ, rank 0's index is broadcast
+        dev = ivf.to_device()
+        if rank == 1:
+            dev["codes"].zero_()
+            dev["centers"].mul_(0.5)
+            dev["ids"].add_(7)
+        bad += synth.index_consistent(ivf, dist)
+        synth.sync_index_from_rank0(ivf, dist)
+        bad += not synth.index_consistent(ivf, dist)
+        sh = ShardedIVF(ivf)
+        got = sh.query_batch(mine, 10, n_probes=5, return_distances=True, exchange="nccl")
+        bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
+        sh.close()
+        np.save(out, np.array([bad]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_index_on_the_emulator_gloo_world2(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emulate"))
+    import emu_lib
+    try:
+        emu_lib.load()                                              # build once, before the workers start
+    except Exception as e:                                           # noqa: BLE001
+        pytest.skip("cannot build the emulated library: %s" % str(e)[-300:])
+    import torch.multiprocessing as mp
+    port = _free_port()
+    outs = [str(tmp_path / ("e%d.npy" % r)) for r in range(2)]
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_emu_worker, args=(r, 2, port, outs[r])) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(900)
+        assert p.exitcode == 0
+    assert all(int(np.load(o)[0]) == 0 for o in outs)
