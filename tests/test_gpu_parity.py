@@ -485,6 +485,55 @@ def test_replay_kernels_agree_with_oracle_fresh_heap():
             assert np.array_equal(a2[q], oi) and np.array_equal(b2[q], ov), (trial, q)
 
 
+def test_replay_full_ctas_sixteen_queries_each():
+    """Enough queries (>= 16 x 296) for the queue replay to pack 16 queries into every CTA, 8 per consumer warp -- the geometry
+    of the benchmark batches, which the small-batch tests above never reach: heap arrays == oracle for every query, both
+    replay modes (one segment per query; IVF segments through a compact plan)."""
+    from tinyknn_b200._lib import lib, check, PLAN_SEND
+    rng = np.random.default_rng(44)
+    Q, R, n = 4800, 21, 300
+    nck = -(-n // 16)
+    est = rng.integers(0, 256, size=(Q, 16 * nck), dtype=np.uint8)
+    est[::3] = (est[::3] // 16 + 100).astype(np.uint8)                       # every third query: few distinct values, ties
+    edev = D.upload(est)
+    hi, hv = D.empty((Q, R), np.int64), D.empty((Q, R), np.int32)
+    check(lib.tkb_replay_fresh_dev(D.ptr(edev), 16 * nck, nck, n, D.ptr(hi), D.ptr(hv), Q, R, 1, D.stream_ptr()))
+    a, b = hi.cpu().numpy(), hv.cpu().numpy()
+    for q in range(Q):
+        oi, ov = np.zeros(R, np.int64), np.zeros(R, np.int32)
+        O.init_heap(oi, ov, True)
+        O.replay(est[q], n, oi, ov, True)
+        assert np.array_equal(a[q], oi) and np.array_equal(b[q], ov), q
+    # IVF mode: 3 probed lists per query out of 40, compact plan
+    n_lists, P = 40, 3
+    sizes = rng.integers(1, 200, size=n_lists).astype(np.int32)
+    nc8 = (-(-sizes.astype(np.int64) // 128)) * 8
+    off = np.zeros(n_lists + 1, np.int64)
+    off[1:] = np.cumsum(nc8)
+    ids = rng.permutation(16 * int(off[-1])).astype(np.int64) + 10 ** 9
+    probes = np.stack([rng.permutation(n_lists)[:P] for _ in range(Q)]).astype(np.int32)
+    d_off, d_sizes, d_ids, d_probes = (D.upload(x) for x in (off, sizes, ids, probes))
+    d_seg, d_gb, d_ws = D.empty((Q, P), np.int64), D.empty((3,), np.int64), D.empty((Q,), np.int64)
+    check(lib.tkb_ivf_plan_dev(D.ptr(d_probes), Q, P, D.ptr(d_sizes), None, n_lists, PLAN_SEND, 0, 1, 0,
+                               D.ptr(d_seg), D.ptr(d_gb), D.ptr(d_ws), 8 * Q, D.stream_ptr()))
+    seg, total = d_seg.cpu().numpy(), int(d_gb.cpu().numpy()[1])
+    pe = rng.integers(0, 256, size=max(total, 16), dtype=np.uint8)
+    d_pe = D.upload(pe)
+    hi, hv, fb = D.empty((Q, R), np.int64), D.empty((Q, R), np.int32), D.empty((Q,), np.int32)
+    check(lib.tkb_ivf_replay_fresh_dev(D.ptr(d_pe), 0, D.ptr(d_seg), D.ptr(d_off), D.ptr(d_sizes), n_lists, D.ptr(d_ids),
+                                       D.ptr(d_probes), Q, P, D.ptr(hi), D.ptr(hv), R, 1, 1, D.ptr(fb), D.stream_ptr()))
+    a, b = hi.cpu().numpy(), hv.cpu().numpy()
+    for q in range(0, Q, 7):
+        oi, ov = np.zeros(R, np.int64), np.zeros(R, np.int32)
+        O.init_heap(oi, ov, True)
+        for s in range(P):
+            l = int(probes[q, s])
+            ncr = -(-int(sizes[l]) // 16)
+            O.replay(pe[seg[q, s]:seg[q, s] + 16 * ncr], int(sizes[l]), oi, ov, True,
+                     np.ascontiguousarray(ids[16 * off[l]:16 * off[l] + 16 * ncr]))
+        assert np.array_equal(a[q], oi) and np.array_equal(b[q], ov), q
+
+
 @pytest.mark.parametrize("R,n", [(255, 9000), (256, 9000), (300, 20000), (1291, 60000), (4000, 30000), (70000, 90000)])
 def test_replay_deep_heaps(R, n):
     """Heaps deeper than 8 levels: the pipelined queue replay runs 8 lanes per query (R <= 65535) or hands over to
