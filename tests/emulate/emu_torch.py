@@ -127,6 +127,9 @@ def install():
                 if val is real:
                     setattr(mod, attr, emu)
     D._torch = _Torch(torch)
+    # a device-to-host copy is a COPY: on the CPU `.cpu()` would alias the "device" buffer, and a later launch that reuses the
+    # buffer would silently change what a test had read back
+    torch.Tensor.cpu = lambda self, *a, **k: self.clone()
     upload = D.upload
 
     def upload_copy(arr, non_blocking=False):

@@ -196,10 +196,11 @@ class FastPQ:
             assert Dp == Dpad, "query dimension does not match the fitted quantizer"
         return Dpad, Dp, Dp // dpb
 
-    def distance_tables(self, queries, signed=True, normalize=False):
+    def distance_tables(self, queries, signed=True, normalize=False, buf=None):
         """Batched LUT build (new, additive API). queries: f32 (Q, d) host array or device tensor.
         Returns a dict of device tensors: tables u8 (Q, M, 16), q f32 (Q, d) (normalised when
-        `normalize`), q_rot f64 (Q, Dp), shift f64 (Q,), scale f64 (Q,)."""
+        `normalize`), q_rot f64 (Q, Dp), shift f64 (Q,), scale f64 (Q,). buf: optional allocator
+        `buf(name, shape, np_dtype)` (IVF.query_batch reuses its per-stream workspace; default: fresh tensors)."""
         t = D.require_cuda()
         assert self.centers is not None, "PQ has not been fitted"
         if isinstance(queries, np.ndarray):
@@ -207,9 +208,11 @@ class FastPQ:
         Q, d = queries.shape
         Dpad, Dp, M = self._lut_dims(d)
         cen, R = self._dev_state()
-        out = dict(tables=D.empty((Q, M, 16), np.uint8), q=D.empty((Q, d), np.float32),
-                   q_rot=D.empty((Q, Dp), np.float64), shift=D.empty((Q,), np.float64),
-                   scale=D.empty((Q,), np.float64))
+        if buf is None:
+            buf = lambda name, shape, dt: D.empty(shape, dt)                 # noqa: E731
+        out = dict(tables=buf("lut_tables", (Q, M, 16), np.uint8), q=buf("lut_q", (Q, d), np.float32),
+                   q_rot=buf("lut_q_rot", (Q, Dp), np.float64), shift=buf("lut_shift", (Q,), np.float64),
+                   scale=buf("lut_scale", (Q,), np.float64))
         check(lib.tkb_lut_build_dev(
             D.ptr(queries), Q, d, int(bool(normalize)), D.ptr(out["q"]), D.ptr(cen), Dp, self.dims_per_block,
             D.ptr(R), Dpad, float(self.sqrt_n_blocks), float(np.log(M)), int(bool(signed)),

@@ -37,6 +37,8 @@ FUSED = os.environ.get("TKB_FUSED", "0") != "0"
 # Chunk minima (tkb_ivf_scan_native_cm_dev / tkb_ivf_replay_fresh_cm_dev) when a query may scan at least this many chunks:
 # the replay of long probe lists then reads 1 byte per chunk instead of 16. 0 disables.
 CMIN_CHUNKS = int(os.environ.get("TKB_CMIN_CHUNKS", "8192"))
+# Reuse the temporaries of a block shape across batches (per stream) instead of allocating 23 tensors per block.
+WORKSPACE_REUSE = os.environ.get("TKB_WORKSPACE_REUSE", "1") != "0"
 # Probe selection as one kernel (tkb_coarse_probes_dev) instead of scan / replay / gather / select. Opt-in until it has been
 # timed on hardware; results are identical (tests/test_fused_gpu.py).
 COARSE_FUSED = os.environ.get("TKB_COARSE_FUSED", "0") != "0"
@@ -64,6 +66,26 @@ def _workspace_cap():
         free, _ = D.torch().cuda.mem_get_info()
         _ws_cap[dev_] = int(min(32 << 30, max(_WORKSPACE_BYTES, free // 4)))
     return _ws_cap[dev_]
+
+
+class _Workspace:
+    """The temporaries of one block shape on one stream, allocated once and reused by the following batches (reuse on one
+    stream is stream-ordered, hence safe): a block of `query_batch` needs 23 device buffers, and asking torch for them costs
+    the host more than launching the 13 kernels -- time a synchronous caller pays in front of every batch."""
+    __slots__ = ("bufs",)
+
+    def __init__(self):
+        self.bufs = {}
+
+    def __call__(self, name, shape, np_dtype):
+        x = self.bufs.get(name)
+        if x is None or tuple(x.shape) != tuple(shape):
+            x = self.bufs[name] = D.empty(shape, np_dtype)
+        return x
+
+
+def _fresh(name, shape, np_dtype):
+    return D.empty(shape, np_dtype)
 
 
 def _sub_batches(Q):
@@ -149,7 +171,7 @@ class IVF:
 
     # ------------------------------------------------------------------ device index ---------
     def __getstate__(self):
-        return {k: v for k, v in self.__dict__.items() if k not in ("_dev", "_last", "_prof", "_keep_heaps", "_scan_log")}
+        return {k: v for k, v in self.__dict__.items() if k not in ("_dev", "_last", "_prof", "_keep_heaps", "_scan_log", "_ws")}
 
     def invalidate(self):
         """Forget the device copy (call after replacing index arrays by hand)."""
@@ -324,7 +346,7 @@ class IVF:
         return GraphedBatch(self, int(n_queries), int(k), int(n_probes), pass_1, sub_batches)
 
     # -- stages of one block of queries (shared with the list-sharded index, sharded.py) ----------------
-    def _coarse(self, dev, lut, Q, P, Rc, order):
+    def _coarse(self, dev, lut, Q, P, Rc, order, buf=_fresh):
         """Probe selection (ref: ivf.py:131 -> fast_pq.py:284-312): scan of the PQ-encoded centroids, exact heap
         replay of 2*n_probes+10 candidates, exact centroid distances, n_probes nearest. Returns int32 (Q, P)."""
         st = D.stream_ptr()
@@ -333,31 +355,31 @@ class IVF:
         tables, qn = lut["tables"], lut["q"]
         cc, nck = dev["center_codes"], dev["center_chunks"]
         if COARSE_FUSED and order == "device" and _fp.SCAN_IMPL == "fast" and Rc <= 1024 and nck <= 4096:
-            hci, hcv = D.empty((Q, Rc), np.int64), D.empty((Q, Rc), np.int32)
-            probes = D.empty((Q, P), np.int32)
+            hci, hcv = buf("hci", (Q, Rc), np.int64), buf("hcv", (Q, Rc), np.int32)
+            probes = buf("probes", (Q, P), np.int32)
             with self._stage("coarse_fused"):
                 check(lib.tkb_coarse_probes_dev(D.ptr(cc), nck, C, M, D.ptr(tables), Q, D.ptr(dev["centers"]), dev["d"], D.ptr(qn),
                                                 Rc, P, _fp._order(), D.ptr(probes), D.ptr(hci), D.ptr(hcv), None, st))
             self._last = dict(center_heap=hci, tables=tables)
             return probes
-        est_c = D.empty((Q, 16 * nck), np.uint8)
+        est_c = buf("est_c", (Q, 16 * nck), np.uint8)
         with self._stage("coarse_scan"):
             if _fp.SCAN_IMPL == "fast":
-                ws = D.scan_workspace(Q * nck)
+                ws = buf("coarse_ws", (64,), np.uint8)
                 check(lib.tkb_estimate_native_dev(D.ptr(cc), nck, M, D.ptr(tables), Q, D.ptr(est_c), 16 * nck,
                                                   _fp._order(), sg, D.ptr(ws), ws.numel(), st))
             else:
                 check(lib.tkb_estimate_dev(D.ptr(self._ref_codes(dev, "center_codes", nck)), nck, M, D.ptr(tables), Q,
                                            D.ptr(est_c), 16 * nck, _fp._order(), sg, st))
-        hci, hcv = D.empty((Q, Rc), np.int64), D.empty((Q, Rc), np.int32)
+        hci, hcv = buf("hci", (Q, Rc), np.int64), buf("hcv", (Q, Rc), np.int32)
         with self._stage("coarse_replay"):
             check(lib.tkb_replay_fresh_dev(D.ptr(est_c), 16 * nck, nck, C, D.ptr(hci), D.ptr(hcv), Q, Rc, sg, st))
-        probes = D.empty((Q, P), np.int32)
+        probes = buf("probes", (Q, P), np.int32)
         with self._stage("coarse_select"):
             if Rc <= P:
                 check(lib.tkb_select_probes_dev(D.ptr(hci), None, DTYPE_F32, Q, Rc, P, D.ptr(probes), st))
             else:
-                dc = D.empty((Q, Rc), np.float32)
+                dc = buf("dc", (Q, Rc), np.float32)
                 check(lib.tkb_gather_dists_dev(D.ptr(dev["centers"]), DTYPE_F32, C, dev["d"], D.ptr(qn), D.ptr(hci),
                                                Q, Rc, D.ptr(dc), st))
                 if order == "device":
@@ -370,7 +392,7 @@ class IVF:
         return probes
 
     def _scan(self, dev, tables, probes, Q, P, est, seg_off, codes_key="codes", off_key="list_chunk_off", cmin=None,
-              push_cm=None):
+              push_cm=None, buf=_fresh):
         """Estimates of every (query, probed list) segment present in `seg_off` (ref: the scan half of
         query_pq_*, ivf.py:142-150), written compactly into `est`."""
         st = D.stream_ptr()
@@ -381,7 +403,7 @@ class IVF:
             self.__dict__.setdefault("_scan_log", []).append((probes, seg_off))
         with self._stage("scan"):
             if _fp.SCAN_IMPL == "fast":
-                ws = D.scan_workspace(min(Q * max_q_chunks, max(1 << 20, Q * max_q_chunks // 4)))
+                ws = buf("scan_ws", (64,), np.uint8)                     # its first 8 bytes count the recomputed chunks
                 if push_cm is not None:                                  # (per-home minima table, queries per rank)
                     check(lib.tkb_ivf_scan_native_push_cm_dev(D.ptr(dev[codes_key]), D.ptr(dev[off_key]), D.ptr(dev["list_size"]), n_lists, M,
                                                               D.ptr(tables), D.ptr(probes), Q, P, D.ptr(seg_off), D.ptr(push_cm[0]), push_cm[1],
@@ -400,13 +422,13 @@ class IVF:
                                            D.ptr(dev["list_size"]), n_lists, M, D.ptr(tables), D.ptr(probes), Q, P,
                                            D.ptr(est), 0, D.ptr(seg_off), max(dev["max_real_chunks"], 1), _fp._order(), 1, st))
 
-    def _replay_rescore(self, dev, qn, probes, Q, P, k, pass_1, est, seg_off, order, out=None, cmin=None):
+    def _replay_rescore(self, dev, qn, probes, Q, P, k, pass_1, est, seg_off, order, out=None, cmin=None, buf=_fresh):
         """Ordered exact heap replay over the probed lists, then exact rescoring and the k nearest
         (ref: ivf.py:137-163). `probes`/`seg_off` are the rows of these Q queries."""
         st = D.stream_ptr()
         n_lists = dev["n_lists"]
-        hi_, hv_ = D.empty((Q, pass_1), np.int64), D.empty((Q, pass_1), np.int32)
-        fb = D.empty((Q,), np.int32)
+        hi_, hv_ = buf("heap_idx", (Q, pass_1), np.int64), buf("heap_val", (Q, pass_1), np.int32)
+        fb = buf("fallback", (Q,), np.int32)
         with self._stage("replay"):
             if cmin is not None:
                 check(lib.tkb_ivf_replay_fresh_cm_dev(D.ptr(est), D.ptr(seg_off), D.ptr(cmin), D.ptr(dev["list_chunk_off"]),
@@ -419,7 +441,7 @@ class IVF:
                                                    D.ptr(hi_), D.ptr(hv_), pass_1, 1, int(dev.get("unique_ids", False)),
                                                    D.ptr(fb), st))
         ddt = np.float32 if dev["data_dtype"] == DTYPE_F32 else np.float64
-        dd = D.empty((Q, pass_1), ddt)
+        dd = buf("dd", (Q, pass_1), ddt)
         with self._stage("rescore"):
             check(lib.tkb_gather_dists_dev(D.ptr(dev["data"]), dev["data_dtype"], dev["data"].shape[0], dev["d"],
                                            D.ptr(qn), D.ptr(hi_), Q, pass_1, D.ptr(dd), st))
@@ -444,13 +466,13 @@ class IVF:
             ids[i, :len(cand)], dst[i, :len(cand)] = cand, cd
         return ids, cnt, dst
 
-    def _plan(self, dev, probes, Q, P, mode=PLAN_SEND, rank=0, n_ranks=1, q_per_rank=0, rows=None):
+    def _plan(self, dev, probes, Q, P, mode=PLAN_SEND, rank=0, n_ranks=1, q_per_rank=0, rows=None, buf=_fresh):
         """Segment offsets of the compact estimate buffer (tkb_ivf_plan_dev). Returns (seg_off, group_bytes).
         n_ranks == 1 plans every segment (list ownership only matters to the sharded modes)."""
         rows = Q if rows is None else rows
-        seg_off = D.empty((rows, P), np.int64)
-        gb = D.empty((2 * n_ranks + 1,), np.int64)
-        ws = D.empty((max(rows, 1) * n_ranks,), np.int64)
+        seg_off = buf("seg_off", (rows, P), np.int64)
+        gb = buf("plan_gb", (2 * n_ranks + 1,), np.int64)
+        ws = buf("plan_ws", (max(rows, 1) * n_ranks,), np.int64)
         with self._stage("plan"):
             check(lib.tkb_ivf_plan_dev(D.ptr(probes), Q, P, D.ptr(dev["list_size"]),
                                        D.ptr(dev.get("list_owner")) if n_ranks > 1 else None, dev["n_lists"],
@@ -483,21 +505,32 @@ class IVF:
 
     def _query_block(self, dev, qs, k, P, Rc, pass_1, order, out=None, fused=False):
         Q = qs.shape[0]
+        # Temporaries: reused per (stream, block shape) in throughput mode. Not while profiling (bench.py reads the probe
+        # lists of every block of a step afterwards) and not in the parity mode, whose callers look at `_last`.
+        buf = _fresh
+        if order == "device" and WORKSPACE_REUSE and self.__dict__.get("_prof") is None:
+            cache = self.__dict__.setdefault("_ws", {})
+            key = (D.stream_ptr(), Q, P, Rc, k, pass_1)
+            buf = cache.get(key)
+            if buf is None:
+                if len(cache) >= 16:
+                    cache.clear()
+                buf = cache[key] = _Workspace()
         # 1. LUTs (ref: ivf.py:125-128)
         with self._stage("lut"):
-            lut = self.pq.distance_tables(qs, signed=True, normalize=(self.metric == "angular"))
+            lut = self.pq.distance_tables(qs, signed=True, normalize=(self.metric == "angular"), buf=buf)
         # 2. probe selection
-        probes = self._coarse(dev, lut, Q, P, Rc, order)
+        probes = self._coarse(dev, lut, Q, P, Rc, order, buf=buf)
         if fused:
             return self._fused_tail(dev, lut, probes, Q, P, k, pass_1, out, want_heap=bool(self.__dict__.get("_keep_heaps")))
         # 3. scan of the probed lists into a compact estimate buffer, ordered replay, rescoring
-        seg_off, _ = self._plan(dev, probes, Q, P)
-        est = D.empty((Q * P * 16 * max(dev["max_real_chunks"], 1),), np.uint8)      # upper bound; only the planned part is touched
+        seg_off, _ = self._plan(dev, probes, Q, P, buf=buf)
+        est = buf("est", (Q * P * 16 * max(dev["max_real_chunks"], 1),), np.uint8)   # upper bound; only the planned part is touched
         cmin = None
         if CMIN_CHUNKS > 0 and _fp.SCAN_IMPL == "fast" and P * max(dev["max_real_chunks"], 1) >= CMIN_CHUNKS:
-            cmin = D.empty((est.numel() // 16 + 16,), np.uint8)
-        self._scan(dev, lut["tables"], probes, Q, P, est, seg_off, cmin=cmin)
-        return self._replay_rescore(dev, lut["q"], probes, Q, P, k, pass_1, est, seg_off, order, out, cmin=cmin)
+            cmin = buf("cmin", (est.numel() // 16 + 16,), np.uint8)
+        self._scan(dev, lut["tables"], probes, Q, P, est, seg_off, cmin=cmin, buf=buf)
+        return self._replay_rescore(dev, lut["q"], probes, Q, P, k, pass_1, est, seg_off, order, out, cmin=cmin, buf=buf)
 
 
 class PendingBatch:
