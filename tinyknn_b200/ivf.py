@@ -330,7 +330,9 @@ class IVF:
                 assert to_host == "async"
                 return PendingBatch(ids, cnt, dst, return_distances)
             if to_host:
-                ids, cnt, dst = ids.cpu().numpy(), cnt.cpu().numpy(), dst.cpu().numpy()
+                ids, cnt = ids.cpu().numpy(), cnt.cpu().numpy()
+                if return_distances:                                     # not copied unless asked for
+                    dst = dst.cpu().numpy()
         else:
             ids, cnt, dst = (np.concatenate([o[i] for o in outs]) for i in range(3))
         if return_distances:
