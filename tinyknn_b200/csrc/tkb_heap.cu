@@ -633,46 +633,51 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                 uint32_t *hw = H + (size_t)(mine ? t : 0) * HS;
                 const uint32_t *qu = QU + (size_t)(mine ? t : 0) * (QCAP + 2);
                 const int cnt = mine ? s_count[t] : 0;
-                int qi = 0, next_role = 0, cooldown = 0, frozen = 0;       // replicated over the query's L lanes
-                uint32_t cur_chunk = 0xffffffffu;
+                // State replicated over the query's L lanes: queue cursor, bound frozen for the current chunk, last record seen.
+                // Values stay in the top byte of their 32-bit words and are compared there: for words a, b with the value in
+                // bits 24..31 (signed) and a 24-bit payload below, value(a) < value(b)  <=>  (int)a < (int)(b & 0xff000000),
+                // so no per-step byte extraction; "same chunk" is a masked xor of two records. Cursors are pointers, not
+                // indices; the heap node an insert looks at is a 32-bit word index nw (slot j = word j + 1, children = words 2 nw, 2 nw + 1).
+                const uint32_t *qp = qu, *const qend = qu + cnt;
+                int next_role = 0, cooldown = 0;
+                uint32_t frm = 0, cur = 0xffffffffu;                       // chunk 0xfffff never occurs (positions < 2^24 - 16)
                 bool active = false;
-                uint32_t rw = 0, jo = 0;
-                int ev = 0;
+                uint32_t rw = 0;
+                uint32_t nw = 1;
                 // The root is read AFTER the barrier that ends a step and carried into the next one: the lane that starts an
                 // insert rewrites hw[1] in its first step, and the L lanes of the query must all see the value from before
                 // that write (they replicate the admission state) without relying on lock-step execution inside a step.
-                int rootv = (int)hw[1] >> 24;
-                while (__any_sync(FULL, active || qi < cnt)) {
+                uint32_t rootm = hw[1] & 0xff000000u;
+                while (__any_sync(FULL, active || qp < qend)) {
                     // admission: at most two records per step (the queue is padded with two sentinels)
-                    const uint32_t r0 = qu[qi], r1 = qu[qi + 1];
-                    const bool ok0 = cooldown == 0 && qi < cnt;
-                    const uint32_t ch0 = (r0 & 0xffffffu) >> 4, ch1 = (r1 & 0xffffffu) >> 4;
-                    const int fr0 = (ok0 && ch0 != cur_chunk) ? rootv : frozen;          // first record of a chunk freezes the bound
-                    const bool acc0 = ok0 && ((int)r0 >> 24) < fr0;
-                    const bool ok1 = ok0 && !acc0 && qi + 1 < cnt;
-                    const int fr1 = (ok1 && ch1 != ch0) ? rootv : fr0;
-                    const bool acc1 = ok1 && ((int)r1 >> 24) < fr1;
-                    cur_chunk = ok1 ? ch1 : (ok0 ? ch0 : cur_chunk);
-                    frozen = fr1;
-                    qi += (ok0 ? 1 : 0) + (ok1 ? 1 : 0);
+                    const uint32_t r0 = qp[0], r1 = qp[1];
+                    const bool ok0 = cooldown == 0 && qp < qend;
+                    const uint32_t fr0 = (ok0 && ((r0 ^ cur) & 0x00fffff0u) != 0) ? rootm : frm;   // first record of a chunk freezes the bound
+                    const bool acc0 = ok0 && (int)r0 < (int)fr0;
+                    const bool ok1 = ok0 && !acc0 && qp + 1 < qend;
+                    const uint32_t fr1 = (ok1 && ((r1 ^ r0) & 0x00fffff0u) != 0) ? rootm : fr0;
+                    const bool acc1 = ok1 && (int)r1 < (int)fr1;
+                    cur = ok1 ? r1 : (ok0 ? r0 : cur);
+                    frm = fr1;
+                    qp += (ok0 ? 1 : 0) + (ok1 ? 1 : 0);
                     const bool start = acc0 || acc1;
-                    if (start && role == next_role) { active = true; rw = acc0 ? r0 : r1; ev = (int)rw >> 24; jo = 0; }
+                    if (start && role == next_role) { active = true; rw = acc0 ? r0 : r1; nw = 1; }
                     next_role = start ? (next_role + 1 == L ? 0 : next_role + 1) : next_role;
                     cooldown = start ? 1 : (cooldown ? cooldown - 1 : 0);                 // next admission two steps from now
                     // one level of the sift-down (ref: _fast_pq.pyx:290-307)
-                    const uint2 ch2 = *reinterpret_cast<const uint2 *>(hw + 2 * jo + 2);
-                    const int vl = (int)ch2.x >> 24, vr = (int)ch2.y >> 24;
-                    const bool pr = vr > vl;                               // the right child wins only when strictly greater
-                    const int vc = pr ? vr : vl;
-                    const bool stop = vc <= ev;                            // no child strictly greater: the record stays here
-                    if (active) hw[jo + 1] = stop ? rw : (pr ? ch2.y : ch2.x);
-                    jo = 2 * jo + 1 + (pr ? 1u : 0u);
+                    const uint32_t kw = 2 * nw;
+                    const uint2 ch2 = *reinterpret_cast<const uint2 *>(hw + kw);
+                    const bool pr = (int)ch2.x < (int)(ch2.y & 0xff000000u);              // the right child wins only when strictly greater
+                    const uint32_t cw = pr ? ch2.y : ch2.x;
+                    const bool stop = !((int)rw < (int)(cw & 0xff000000u));               // no child strictly greater: the record stays here
+                    if (active) hw[nw] = stop ? rw : cw;
+                    nw = kw + (pr ? 1u : 0u);
                     active = active && !stop;
-                    if (!active) jo = 0;
+                    if (!active) nw = 1;
                     __syncwarp();
-                    rootv = (int)hw[1] >> 24;
+                    rootm = hw[1] & 0xff000000u;
                 }
-                if (mine && role == 0) s_bound[t] = rootv;
+                if (mine && role == 0) s_bound[t] = (int)rootm >> 24;
             }
         }
         __syncthreads();
