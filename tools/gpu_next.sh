@@ -13,7 +13,7 @@ timeout 900 ncu --profile-from-start off --set full --clock-control none --impor
 # A/Bs prepared in round 1 (all results must stay identical: the bench's parity gate runs every time)
 #   replay geometry (tools/replay_model.py), scan CTA width (694 chunks per query leave 9.6 % of the lanes idle at 128 threads,
 #   1.4 % at 64), sub-batch size for the synchronous e2e loop
-for cfg in "TKB_COARSE_FUSED=1" "TKB_RQ_MIN_CTAS=1184 TKB_RQ_QPW=1" "TKB_RQ_MIN_CTAS=592 TKB_RQ_QPW=2" "TKB_RQ_LANES=8" "TKB_SCAN_THREADS=64" "TKB_SUB_QUERIES=2500" "TKB_SUB_QUERIES=2500 TKB_STREAMS=3"; do
+for cfg in "TKB_WORKSPACE_REUSE=0" "TKB_COARSE_FUSED=1" "TKB_COARSE_FUSED=1 TKB_SUB_QUERIES=2500 TKB_STREAMS=3" "TKB_RQ_MIN_CTAS=1184 TKB_RQ_QPW=1" "TKB_RQ_MIN_CTAS=592 TKB_RQ_QPW=2" "TKB_RQ_LANES=8" "TKB_SCAN_THREADS=64" "TKB_SUB_QUERIES=2500" "TKB_SUB_QUERIES=2500 TKB_STREAMS=3"; do
   env $cfg timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $out/bench_rq.json 2> $out/bench_rq.err
   python - "$out/bench_rq.json" "$cfg" <<'PY'
 import json,sys
