@@ -108,6 +108,8 @@ size_t g_stack_count = 0;
 std::string g_error;
 cudaError_t g_last = cudaSuccess;
 Stats g_stats = {};
+int g_order = -1;                    // 0 fifo, 1 lifo, 2 random
+uint64_t g_rng = 0x9E3779B97F4A7C15ull;
 
 void park()
 {
@@ -205,6 +207,11 @@ const uint64_t *warp_gather(uint64_t v)
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body)
 {
     g_stats.launches++;
+    if (g_order < 0) {
+        const char *e = getenv("TKB_EMU_ORDER");
+        g_order = !e ? 0 : (!strncmp(e, "lifo", 4) ? 1 : (!strncmp(e, "random", 6) ? 2 : 0));
+        if (e && !strncmp(e, "random:", 7)) g_rng ^= strtoull(e + 7, nullptr, 10) * 0x2545F4914F6CDD1Dull;
+    }
     const unsigned nthreads = block.x * block.y * block.z;
     if (nthreads == 0 || nthreads > 1024 || grid.x == 0 || grid.y == 0 || grid.z == 0 || smem_bytes > 227 * 1024) {
         g_error = "emu: invalid launch configuration";
@@ -249,8 +256,22 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
             g_stats.fibers++;
         }
         while (!blk.ready.empty()) {
-            g_cur = blk.ready.front();
-            blk.ready.pop_front();
+            // Which runnable fiber goes next is unspecified in CUDA (between two synchronisation points the threads of a block
+            // run in any order): TKB_EMU_ORDER=fifo (default: ascending thread order), lifo, or random[:seed] -- a kernel whose
+            // result depends on the choice has a race.
+            if (g_order == 1) {
+                g_cur = blk.ready.back();
+                blk.ready.pop_back();
+            } else if (g_order == 2) {
+                g_rng = g_rng * 6364136223846793005ull + 1442695040888963407ull;
+                const size_t pick = (size_t)((g_rng >> 33) % blk.ready.size());
+                g_cur = blk.ready[pick];
+                blk.ready[pick] = blk.ready.back();
+                blk.ready.pop_back();
+            } else {
+                g_cur = blk.ready.front();
+                blk.ready.pop_front();
+            }
             threadIdx = blk.fibers[g_cur].tid;
             g_stats.switches++;
             ctx_switch(g_sched, blk.fibers[g_cur].ctx);

@@ -83,9 +83,22 @@ __global__ void simd_kernel(const uint32_t *a, const uint32_t *b, const uint32_t
     o[11] = emu::prmt(a[i], b[i], c[i]);
 }
 
+// a deliberate race: every thread reads its neighbour's slot without a barrier after the writes
+__global__ void racy_kernel(int *out)
+{
+    __shared__ int s[64];
+    s[threadIdx.x] = (int)threadIdx.x + 1;
+    out[threadIdx.x] = s[(threadIdx.x + 1) % 64];
+}
+
 }  // namespace
 
 extern "C" {
+int emu_selftest_racy(int *out)
+{
+    racy_kernel<<<1, 64, 0, 0>>>(out);
+    return cudaGetLastError();
+}
 int emu_selftest_collectives(uint32_t *out, int threads)
 {
     collectives_kernel<<<1, threads, 0, 0>>>(out);

@@ -76,6 +76,20 @@ def test_emulator_reports_divergent_barrier_and_smem_overrun(emu):
     assert L.emu_selftest_barrier(np.zeros((1, 2), np.int32).ctypes.data, 1, 64, 1) == 0     # and it recovers
 
 
+def test_emulator_scheduling_orders_expose_a_race(emu):
+    """TKB_EMU_ORDER picks which runnable thread goes next (fifo / lifo / random): a kernel with a race gives different results
+    under different orders, a correct one does not -- the gpu-marked files pass under all three (run by hand, ~80 s each)."""
+    emu.load()
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import emu_lib; L = emu_lib.load(); o = np.zeros(64, np.int32); "
+            "assert L.emu_selftest_racy(o.ctypes.data) == 0; print(','.join(map(str, o)))" % os.path.join(ROOT, "tests", "emulate"))
+    outs = {}
+    for order in ("fifo", "lifo", "random:7"):
+        r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, TKB_EMU_ORDER=order), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs[order] = r.stdout.strip()
+    assert len(set(outs.values())) == 3, outs
+
+
 def test_emulator_simd_intrinsics_match_scalar_definitions(emu):
     L = emu.load()
     rng = np.random.default_rng(0)
