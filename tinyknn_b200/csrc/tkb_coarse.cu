@@ -142,12 +142,12 @@ coarse_probes_kernel(CoarseArgs a)
                 const int src = __ffs(ball) - 1;
                 if (lane == src) {                                                                      // the chunk's owner inserts
                     const int frozen = bound;
-                    const uint32_t ws[4] = {e.x, e.y, e.z, e.w};
                     uint32_t mm = coarse_mask16(e, frozen) & valid;
                     while (mm) {
                         const int v = __ffs(mm) - 1;
                         mm &= mm - 1;
-                        const int ev = (int)(int8_t)((ws[v >> 2] >> (8 * (v & 3))) & 0xffu);
+                        const uint32_t w = v < 8 ? (v < 4 ? e.x : e.y) : (v < 12 ? e.z : e.w);      // selects, not a local array
+                        const int ev = (int)(int8_t)((w >> (8 * (v & 3))) & 0xffu);
                         coarse_sift(sm.hval, sm.hpos, R, 16 * c + v, ev);
                     }
                 }
