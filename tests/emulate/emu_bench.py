@@ -37,7 +37,6 @@ class _Profiler:
 
 torch.cuda.profiler = _Profiler
 torch.Tensor.cuda = lambda self, *a, **k: self.clone()
-torch.Tensor.pin_memory = lambda self, *a, **k: self
 _tensor = torch.tensor
 torch.tensor = lambda *a, **k: _tensor(*a, **{x: y for x, y in k.items() if x != "device"})
 

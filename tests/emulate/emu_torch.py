@@ -130,6 +130,7 @@ def install():
     # a device-to-host copy is a COPY: on the CPU `.cpu()` would alias the "device" buffer, and a later launch that reuses the
     # buffer would silently change what a test had read back
     torch.Tensor.cpu = lambda self, *a, **k: self.clone()
+    torch.Tensor.pin_memory = lambda self, *a, **k: self            # no driver: pageable memory stands in for pinned memory
     upload = D.upload
 
     def upload_copy(arr, non_blocking=False):
