@@ -527,10 +527,12 @@ class IVF:
             return self._fused_tail(dev, lut, probes, Q, P, k, pass_1, out, want_heap=bool(self.__dict__.get("_keep_heaps")))
         # 3. scan of the probed lists into a compact estimate buffer, ordered replay, rescoring
         seg_off, _ = self._plan(dev, probes, Q, P, buf=buf)
-        est = buf("est", (Q * P * 16 * max(dev["max_real_chunks"], 1),), np.uint8)   # upper bound; only the planned part is touched
+        est_bytes = Q * P * 16 * max(dev["max_real_chunks"], 1)                     # upper bound; only the planned part is touched
+        big = buf if est_bytes <= (1 << 30) else _fresh     # GBs of estimates (100M-vector indexes) go back to the allocator after every block
+        est = big("est", (est_bytes,), np.uint8)
         cmin = None
         if CMIN_CHUNKS > 0 and _fp.SCAN_IMPL == "fast" and P * max(dev["max_real_chunks"], 1) >= CMIN_CHUNKS:
-            cmin = buf("cmin", (est.numel() // 16 + 16,), np.uint8)
+            cmin = big("cmin", (est.numel() // 16 + 16,), np.uint8)
         self._scan(dev, lut["tables"], probes, Q, P, est, seg_off, cmin=cmin, buf=buf)
         return self._replay_rescore(dev, lut["q"], probes, Q, P, k, pass_1, est, seg_off, order, out, cmin=cmin, buf=buf)
 
