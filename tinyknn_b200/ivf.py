@@ -572,18 +572,23 @@ class GraphedBatch:
         kw = dict(k=k, n_probes=n_probes, pass_1=pass_1, order="device", return_distances=True, to_host=False,
                   sub_batches=sub_batches, fused=False)
         from ._lib import launch_count
-        warm = t.cuda.Stream()                                  # capture needs a warmed-up allocator and cached device state
-        warm.wait_stream(t.cuda.current_stream())
-        with t.cuda.stream(warm):
-            for _ in range(2):
-                ivf.query_batch(self.q_in, **kw)
-        t.cuda.current_stream().wait_stream(warm)
-        t.cuda.synchronize()
-        self.graph = t.cuda.CUDAGraph()
-        n0 = launch_count()
-        with t.cuda.graph(self.graph):
-            self.out = ivf.query_batch(self.q_in, **kw)
-        self.launches_per_replay = launch_count() - n0          # kernels inside the graph (tkb_launch_count counts the capture once)
+        global WORKSPACE_REUSE
+        reuse, WORKSPACE_REUSE = WORKSPACE_REUSE, False         # the graph's temporaries must come from ITS memory pool, which lives as
+        try:                                                    # long as the graph does (the per-stream workspaces can be dropped)
+            warm = t.cuda.Stream()                              # capture needs a warmed-up allocator and cached device state
+            warm.wait_stream(t.cuda.current_stream())
+            with t.cuda.stream(warm):
+                for _ in range(2):
+                    ivf.query_batch(self.q_in, **kw)
+            t.cuda.current_stream().wait_stream(warm)
+            t.cuda.synchronize()
+            self.graph = t.cuda.CUDAGraph()
+            n0 = launch_count()
+            with t.cuda.graph(self.graph):
+                self.out = ivf.query_batch(self.q_in, **kw)
+            self.launches_per_replay = launch_count() - n0      # kernels inside the graph (tkb_launch_count counts the capture once)
+        finally:
+            WORKSPACE_REUSE = reuse
 
     def __call__(self, queries, return_distances=False, to_host=True):
         t = D.torch()
