@@ -1,6 +1,7 @@
 """GPU tests of code written AFTER round 1's GPU budget was spent: none of this has run on hardware yet, so the file is
 skipped unless TKB_RUN_UNVALIDATED=1 (first thing to run next round: `TKB_RUN_UNVALIDATED=1 pytest tests/test_unvalidated_gpu.py`).
-Covers tkb_assign_dev (IVF.build's coarse assignment) and the chunk minima inside the push exchange."""
+Covers tkb_assign_dev (IVF.build's coarse assignment), the chunk minima inside the push exchange and the one-kernel probe
+selection (tkb_coarse_probes_dev). All of it passes on the CPU emulator (TKB_EMU=1, tests/emulate), which the CPU suite runs."""
 import os
 
 import numpy as np
@@ -185,3 +186,108 @@ def test_async_results_equal_sync(golden):
     pb = ivf.query_batch(qb.numpy(), 10, n_probes=6, order="device", return_distances=True, to_host="async")
     assert all(np.array_equal(x, y) for x, y in zip(ref_b, pb.result()))
     assert all(np.array_equal(x, y) for x, y in zip(ref_a, pa.result()))
+
+
+from tinyknn_b200._lib import lib, check, DTYPE_F32, ORDER_AVX, ORDER_SSE           # noqa: E402
+from tinyknn_b200._transform import transform_data                                  # noqa: E402
+from test_gpu_parity import _ivf_from_state                                         # noqa: E402
+
+
+# ---- probe selection as one kernel (tkb_coarse_probes_dev) -------------------------------------------------------------------
+
+def _coarse_staged(cc, nck, C, M, tables, Q, centers, d, qn, Rc, P, order):
+    st = D.stream_ptr()
+    est = D.empty((Q, 16 * nck), np.uint8)
+    ws = D.scan_workspace(Q * nck)
+    check(lib.tkb_estimate_native_dev(D.ptr(cc), nck, M, D.ptr(tables), Q, D.ptr(est), 16 * nck, order, 1, D.ptr(ws), ws.numel(), st))
+    hi, hv = D.empty((Q, Rc), np.int64), D.empty((Q, Rc), np.int32)
+    check(lib.tkb_replay_fresh_dev(D.ptr(est), 16 * nck, nck, C, D.ptr(hi), D.ptr(hv), Q, Rc, 1, st))
+    probes, dc = D.empty((Q, P), np.int32), D.empty((Q, Rc), np.float32)
+    if Rc <= P:
+        check(lib.tkb_select_probes_dev(D.ptr(hi), None, DTYPE_F32, Q, Rc, P, D.ptr(probes), st))
+    else:
+        check(lib.tkb_gather_dists_dev(D.ptr(centers), DTYPE_F32, C, d, D.ptr(qn), D.ptr(hi), Q, Rc, D.ptr(dc), st))
+        check(lib.tkb_select_probes_dev(D.ptr(hi), D.ptr(dc), DTYPE_F32, Q, Rc, P, D.ptr(probes), st))
+    return [x.cpu().numpy() for x in (probes, hi, hv, dc)] + [est.cpu().numpy()]
+
+
+@pytest.mark.parametrize("M,order", [(52, "avx"), (32, "avx"), (8, "avx"), (6, "sse"), (52, "sse")])
+def test_coarse_probes_one_kernel_equals_staged_and_oracle(M, order):
+    """tkb_coarse_probes_dev == estimate + fresh replay + gather + select_probes, bit for bit (probes, heap arrays, distances),
+    and its heap == the oracle's replay of the same estimates: random LUT-like, saturating ("hot": -1 slots survive) and
+    full-range tables; centroid counts that end inside a chunk, fewer centroids than candidates, R <= P."""
+    rng = np.random.default_rng(M + len(order))
+    o = ORDER_AVX if order == "avx" else ORDER_SSE
+    for trial, (C, P) in enumerate([(1087, 10), (1024, 10), (17, 3), (9, 2), (300, 40), (40, 30), (1, 1), (129, 1)]):
+        d = (100, 16, 7)[trial % 3]
+        Rc = min(2 * P + 10, C)
+        Q = 6
+        kind = ("lut", "hot", "full", "narrow")[trial % 4]
+        codes = rng.integers(0, 16, size=(-(-C // 16) * 16, M), dtype=np.uint8)
+        codes[C:] = 0                                               # padding rows are encoded zero vectors, whatever their code
+        packed = transform_data(codes)
+        nck = len(packed)
+        tabs = []
+        for _ in range(Q):
+            if kind == "full":
+                t = rng.integers(0, 256, size=(M, 16)).astype(np.uint8)
+            elif kind == "hot":
+                t = (rng.integers(8, 30, size=(M, 16)) - 20).astype(np.int8).view(np.uint8)
+            elif kind == "narrow":
+                t = (rng.integers(0, 28, size=(M, 16)) - 4).astype(np.int8).view(np.uint8)
+            else:
+                t = np.round(rng.exponential(6.0, size=(M, 16)) - 4).clip(-4, 128 / M ** 0.5).astype(np.int8).view(np.uint8)
+            tabs.append(t)
+        tables = D.upload(np.stack(tabs))
+        cc = D.to_native(D.upload(packed), nck, M)
+        cen = rng.standard_normal((C, d)).astype(np.float32)
+        if C > 3:
+            cen[2] = cen[1]                                         # tied distances: the slot decides
+        qs = rng.standard_normal((Q, d)).astype(np.float32)
+        centers, qn = D.upload(cen), D.upload(qs)
+        exp = _coarse_staged(cc, nck, C, M, tables, Q, centers, d, qn, Rc, P, o)
+        probes, hi, hv, dc = D.empty((Q, P), np.int32), D.empty((Q, Rc), np.int64), D.empty((Q, Rc), np.int32), D.empty((Q, Rc), np.float32)
+        check(lib.tkb_coarse_probes_dev(D.ptr(cc), nck, C, M, D.ptr(tables), Q, D.ptr(centers), d, D.ptr(qn), Rc, P, o,
+                                        D.ptr(probes), D.ptr(hi), D.ptr(hv), D.ptr(dc), D.stream_ptr()))
+        got = [x.cpu().numpy() for x in (probes, hi, hv, dc)]
+        assert np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2]), (trial, C, P, kind)
+        assert np.array_equal(got[0], exp[0]), (trial, C, P, kind)
+        if Rc > P:
+            assert np.array_equal(got[3], exp[3]), (trial, C, P, kind)
+        for q in range(Q):                                          # and the oracle, from the staged path's estimates
+            oi, ov = np.zeros(Rc, np.int64), np.zeros(Rc, np.int32)
+            O.init_heap(oi, ov, True)
+            O.replay(exp[4][q], C, oi, ov, True)
+            assert np.array_equal(got[1][q], oi) and np.array_equal(got[2][q], ov), (trial, q)
+        # outputs are optional
+        p2 = D.empty((Q, P), np.int32)
+        check(lib.tkb_coarse_probes_dev(D.ptr(cc), nck, C, M, D.ptr(tables), Q, D.ptr(centers), d, D.ptr(qn), Rc, P, o,
+                                        D.ptr(p2), None, None, None, D.stream_ptr()))
+        assert np.array_equal(p2.cpu().numpy(), exp[0])
+
+
+def test_query_batch_with_one_kernel_probe_selection(golden, monkeypatch):
+    """IVF.query_batch(order="device") with TKB_COARSE_FUSED: same ids, counts, distances, probe heaps and final heaps."""
+    from tinyknn_b200 import ivf as ivf_mod
+    z = golden["ivf"]
+    for name in z["names"]:
+        ivf = _ivf_from_state(O.ivf_state_from_arrays(z, name + "_"))
+        ivf._keep_heaps = True
+        qs = z[name + "_q"]
+        for npr in (1, 3, 8):
+            monkeypatch.setattr(ivf_mod, "COARSE_FUSED", False)
+            a = ivf.query_batch(qs, 10, n_probes=npr, order="device", return_distances=True, sub_batches=1)
+            ha = ivf._last["center_heap"].cpu().numpy(), ivf._last["heap_idx"].cpu().numpy()
+            monkeypatch.setattr(ivf_mod, "COARSE_FUSED", True)
+            b = ivf.query_batch(qs, 10, n_probes=npr, order="device", return_distances=True, sub_batches=1)
+            hb = ivf._last["center_heap"].cpu().numpy(), ivf._last["heap_idx"].cpu().numpy()
+            assert all(np.array_equal(x, y) for x, y in zip(a, b)), (name, npr)
+            assert np.array_equal(ha[0], hb[0]) and np.array_equal(ha[1], hb[1]), (name, npr)
+
+
+def test_coarse_probes_rejects_bad_arguments():
+    with pytest.raises(ValueError):
+        check(lib.tkb_coarse_probes_dev(None, 4, 60, 6, None, 1, None, 8, None, 30, 10, ORDER_AVX, None, None, None, None, None))
+    with pytest.raises(ValueError):
+        check(lib.tkb_coarse_probes_dev(None, 4, 20, 8, None, 1, None, 8, None, 30, 10, ORDER_AVX, None, None, None, None, None))   # R > C
+    check(lib.tkb_coarse_probes_dev(None, 4, 60, 8, None, 0, None, 8, None, 30, 10, ORDER_AVX, None, None, None, None, None))      # Q = 0

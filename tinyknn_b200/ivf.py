@@ -40,7 +40,7 @@ CMIN_CHUNKS = int(os.environ.get("TKB_CMIN_CHUNKS", "8192"))
 # Reuse the temporaries of a block shape across batches (per stream) instead of allocating 23 tensors per block.
 WORKSPACE_REUSE = os.environ.get("TKB_WORKSPACE_REUSE", "1") != "0"
 # Probe selection as one kernel (tkb_coarse_probes_dev) instead of scan / replay / gather / select. Opt-in until it has been
-# timed on hardware; results are identical (tests/test_fused_gpu.py).
+# timed on hardware; results are identical (tests/test_unvalidated_gpu.py, run on the emulator).
 COARSE_FUSED = os.environ.get("TKB_COARSE_FUSED", "0") != "0"
 # IVF.build: coarse assignment on the GPU (tkb_assign_dev). Opt-in until it has been validated on hardware.
 ASSIGN_DEVICE = os.environ.get("TKB_ASSIGN_DEVICE", "0") != "0"
