@@ -108,6 +108,12 @@ size_t g_stack_count = 0;
 std::string g_error;
 cudaError_t g_last = cudaSuccess;
 Stats g_stats = {};
+// "CUDA graphs": while a capture is open, launches / memsets / copies are recorded (and executed: harmless, the real capture
+// only records); a replay runs the recorded nodes again with the argument values they were recorded with.
+struct GraphNode { int kind; dim3 grid, block; size_t smem; std::function<void()> body; void *dst; const void *src; int value; size_t bytes; };
+std::vector<std::vector<GraphNode>> g_graphs;
+int g_capture = -1;
+bool g_replaying = false;
 int g_order = -1;                    // 0 fifo, 1 lifo, 2 random
 uint64_t g_rng = 0x9E3779B97F4A7C15ull;
 
@@ -207,6 +213,7 @@ const uint64_t *warp_gather(uint64_t v)
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body)
 {
     g_stats.launches++;
+    if (g_capture >= 0 && !g_replaying) g_graphs[g_capture].push_back(GraphNode{0, grid, block, smem_bytes, body, nullptr, nullptr, 0, 0});
     if (g_order < 0) {
         const char *e = getenv("TKB_EMU_ORDER");
         g_order = !e ? 0 : (!strncmp(e, "lifo", 4) ? 1 : (!strncmp(e, "random", 6) ? 2 : 0));
@@ -313,6 +320,30 @@ void emu_stats(long long *o)
     o[6] = s.collectives_with_exited_lanes;
 }
 void emu_reset_stats(void) { emu::g_stats = emu::Stats{}; emu::g_error.clear(); }
+int emu_graph_begin(void)
+{
+    emu::g_graphs.emplace_back();
+    emu::g_capture = (int)emu::g_graphs.size() - 1;
+    return emu::g_capture;
+}
+int emu_graph_end(void)
+{
+    const int id = emu::g_capture;
+    emu::g_capture = -1;
+    return id < 0 ? -1 : (int)emu::g_graphs[id].size();
+}
+int emu_graph_replay(int id)
+{
+    if (id < 0 || id >= (int)emu::g_graphs.size() || emu::g_capture >= 0) return -1;
+    emu::g_replaying = true;
+    for (const emu::GraphNode &n : emu::g_graphs[id]) {
+        if (n.kind == 0) emu::launch(n.grid, n.block, n.smem, n.body);
+        else if (n.kind == 1) std::memset(n.dst, n.value, n.bytes);
+        else std::memmove(n.dst, n.src, n.bytes);
+    }
+    emu::g_replaying = false;
+    return emu::g_last == cudaSuccess ? 0 : 1;
+}
 }
 
 // ---- runtime API shim ------------------------------------------------------------------------------------------------
@@ -369,9 +400,21 @@ cudaError_t cudaFree(void *p)
     g_allocs.erase(it);
     return cudaSuccess;
 }
-cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t) { std::memmove(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t)
+{
+    if (emu::g_capture >= 0 && !emu::g_replaying)
+        emu::g_graphs[emu::g_capture].push_back(emu::GraphNode{2, dim3(), dim3(), 0, nullptr, dst, src, 0, bytes});
+    std::memmove(dst, src, bytes);
+    return cudaSuccess;
+}
 cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind) { std::memmove(dst, src, bytes); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void *dst, int value, size_t bytes, cudaStream_t) { std::memset(dst, value, bytes); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *dst, int value, size_t bytes, cudaStream_t)
+{
+    if (emu::g_capture >= 0 && !emu::g_replaying)
+        emu::g_graphs[emu::g_capture].push_back(emu::GraphNode{1, dim3(), dim3(), 0, nullptr, dst, nullptr, value, bytes});
+    std::memset(dst, value, bytes);
+    return cudaSuccess;
+}
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
 cudaError_t cudaGetDevice(int *dev) { *dev = 0; return cudaSuccess; }

@@ -3,7 +3,8 @@ C++ and compiled against cuda_emu.h, so that the C ABI of include/tinyknn_b200.h
 are host pointers. TEST INFRASTRUCTURE ONLY -- the package never loads this library.
 
 The translation is textual and small:
-  * `kernel<targs><<<grid, block, smem, stream>>>(args)`  ->  `::emu::launch(dim3(grid), dim3(block), smem, [&]() { kernel<targs>(args); })`
+  * `kernel<targs><<<grid, block, smem, stream>>>(args)`  ->  `::emu::launch(dim3(grid), dim3(block), smem, [=]() { kernel<targs>(args); })`
+    (the closure owns copies of the arguments, like a kernel node of a CUDA graph: cuda_emu.cpp can record and replay it)
   * `extern __shared__ [__align__(n)] T name[];`         ->  `T *name = reinterpret_cast<T *>(::emu::dyn_smem());`
   * `__noinline__`                                       ->  `__attribute__((noinline))`
 everything else (qualifiers, intrinsics, the runtime API) is supplied by cuda_emu.h / shim/cuda_runtime.h; the four inline-PTX
@@ -74,7 +75,7 @@ def translate(src):
             a0 += 1
         a1 = _balanced(src, a0)
         out.append(src[pos:m.start(1)])
-        out.append("::emu::launch(dim3(%s), dim3(%s), (size_t)(%s), [&]() { %s%s; })" % (grid, block, smem, m.group(1), src[a0:a1]))
+        out.append("::emu::launch(dim3(%s), dim3(%s), (size_t)(%s), [=]() { %s%s; })" % (grid, block, smem, m.group(1), src[a0:a1]))
         pos = a1
         n_launch += 1
     text = "".join(out)

@@ -44,9 +44,52 @@ class _Event:
         return (other.t - self.t) * 1e3
 
 
+class _Graph:
+    """torch.cuda.CUDAGraph on the emulator: the library records the launches (with copies of their arguments), memsets and
+    copies issued while the capture is open, `replay()` runs them again."""
+    capturing = False
+    current = None
+
+    def __init__(self):
+        self.id = -1
+        self.nodes = 0
+        self.pool = []                 # tensors allocated during the capture: the graph's private memory pool keeps them alive
+
+    def replay(self):
+        import emu_lib
+        if emu_lib.load().emu_graph_replay(self.id) != 0:
+            raise RuntimeError("emulated graph replay failed: %s" % emu_lib.load().emu_last_error().decode())
+
+
+class _Capture:
+    def __init__(self, graph):
+        self.graph = graph
+
+    def __enter__(self):
+        import emu_lib
+        self.graph.id = emu_lib.load().emu_graph_begin()
+        _Graph.capturing, _Graph.current = True, self.graph
+
+    def __exit__(self, *exc):
+        import emu_lib
+        _Graph.capturing, _Graph.current = False, None
+        self.graph.nodes = emu_lib.load().emu_graph_end()
+        return False
+
+
+def _no_sync_in_capture(what):
+    if _Graph.capturing:
+        raise RuntimeError("%s while a CUDA graph is being captured (a synchronising call: illegal on hardware)" % what)
+
+
 class _Cuda:
     Event = _Event
+    CUDAGraph = _Graph
     _cur = _Stream()
+
+    @staticmethod
+    def graph(g, *a, **kw):
+        return _Capture(g)
 
     @staticmethod
     def is_available():
@@ -78,7 +121,7 @@ class _Cuda:
 
     @staticmethod
     def synchronize(device=None):
-        pass
+        _no_sync_in_capture("torch.cuda.synchronize()")
 
     @staticmethod
     def mem_get_info(device=None):
@@ -101,7 +144,10 @@ class _Torch:
 
     def empty(self, *a, **kw):
         kw.pop("pin_memory", None)
-        return self._real.empty(*a, **kw)
+        x = self._real.empty(*a, **kw)
+        if _Graph.capturing:
+            _Graph.current.pool.append(x)
+        return x
 
     def __getattr__(self, name):
         return getattr(self._real, name)
@@ -129,7 +175,18 @@ def install():
     D._torch = _Torch(torch)
     # a device-to-host copy is a COPY: on the CPU `.cpu()` would alias the "device" buffer, and a later launch that reuses the
     # buffer would silently change what a test had read back
-    torch.Tensor.cpu = lambda self, *a, **k: self.clone()
+    def _cpu(self, *a, **k):
+        _no_sync_in_capture("Tensor.cpu()")
+        return self.clone()
+
+    item = torch.Tensor.item
+
+    def _item(self):
+        _no_sync_in_capture("Tensor.item()")
+        return item(self)
+
+    torch.Tensor.cpu = _cpu
+    torch.Tensor.item = _item
     torch.Tensor.pin_memory = lambda self, *a, **k: self            # no driver: pageable memory stands in for pinned memory
     upload = D.upload
 
