@@ -21,7 +21,7 @@ import emu_torch                                                   # noqa: E402
 emu_torch.install()
 fake = emu_torch._Cuda()
 for name in ("is_available", "current_device", "device_count", "set_device", "current_stream", "Stream", "stream", "synchronize",
-             "mem_get_info", "empty_cache", "Event"):
+             "mem_get_info", "empty_cache", "Event", "CUDAGraph", "graph"):
     setattr(torch.cuda, name, getattr(fake, name))
 
 
