@@ -353,8 +353,10 @@ def main():
     sync_all()
     torch.cuda.profiler.start()                 # `ncu --profile-from-start off` captures exactly the timed steps
     e0.record()
+    t_issue = time.perf_counter()
     for i in range(args.steps):
         run(dev_batches[i % 4], to_host=False)
+    t_issue = time.perf_counter() - t_issue            # wall-clock the host needed to ISSUE the steps (nothing waited for)
     e1.record()
     sync_all()
     torch.cuda.profiler.stop()
@@ -485,7 +487,10 @@ def main():
                                                  else "are larger than the 126 MB L2: every step streams them from HBM"))),
                     clocks=clocks, e2e=dict(value=e2e_v, unit="queries/s", h2d_bytes_per_step=int(Qn * w["d"] * 4),
                                             d2h_bytes_per_step=int(Qn * args.k * 8 + Qn * 4)),
-                    gpu_launches=int(launches), roofline=roof, cpu_baseline=cb, parity=parity)
+                    gpu_launches=int(launches), roofline=roof, cpu_baseline=cb, parity=parity,
+                    # host-side issue time of one step on rank 0: close to ms_per_step = the loop is bound by Python/launch cost,
+                    # far below = the GPU is the bottleneck
+                    host_issue_ms_per_step=t_issue * 1e3 / args.steps)
         if e2e_pipe_s is not None:                       # rank 0's own loop (replicas run the same loop on every rank)
             line["e2e_pipelined"] = dict(value=Qn * args.steps * world / e2e_pipe_s, unit="queries/s", in_flight=2,
                                          note="same host buffers and copies as e2e, batch i+1 submitted before batch i is collected")
