@@ -24,6 +24,13 @@ LIB = os.path.join(OUT, "libtkb_emu.so")
 CXXFLAGS = ["-std=c++17", "-O1", "-g", "-ffp-contract=off", "-mfma", "-fPIC", "-DTKB_EMULATE", "-w",
             "-I", os.path.join(HERE, "shim"), "-I", HERE, "-I", CSRC]
 
+# TKB_EMU_UBSAN=1: misaligned accesses through the vector types (uint4, uint2, float4, double2: what the GPU reports as
+# "misaligned address") and out-of-bounds indexing of fixed-size arrays abort with a message instead of passing silently on x86
+if os.environ.get("TKB_EMU_UBSAN", "0") == "1":
+    CXXFLAGS = CXXFLAGS + ["-fsanitize=alignment,bounds", "-fno-sanitize-recover=all"]
+    OUT = OUT + "_ubsan"
+    LIB = os.path.join(OUT, "libtkb_emu.so")
+
 _KERNEL_EXPR = re.compile(r"([A-Za-z_]\w*(?:\s*<[^<>;(){}]*>)?)\s*$")
 _EXTERN_SHARED = re.compile(r"extern\s+__shared__\s+(?:__align__\(\s*\d+\s*\)\s+)?([A-Za-z_][\w ]*?)\s+(\w+)\s*\[\s*\]\s*;")
 
@@ -134,7 +141,7 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             raise RuntimeError("g++ failed on %s:\n%s" % (path, outp[-6000:]))
     tmp = LIB + ".tmp%d" % os.getpid()
-    subprocess.check_call(["g++", "-shared", "-o", tmp] + objs)
+    subprocess.check_call(["g++", "-shared", "-o", tmp] + objs + (["-fsanitize=alignment,bounds"] if "-fno-sanitize-recover=all" in CXXFLAGS else []))
     os.replace(tmp, LIB)
     with open(stamp, "w") as f:
         f.write(digest)

@@ -91,9 +91,21 @@ __global__ void racy_kernel(int *out)
     out[threadIdx.x] = s[(threadIdx.x + 1) % 64];
 }
 
+// a 16-byte vector load from an address the caller chooses (TKB_EMU_UBSAN=1 builds abort when it is misaligned)
+__global__ void vector_load_kernel(const unsigned char *p, uint32_t *out)
+{
+    const uint4 v = *reinterpret_cast<const uint4 *>(p);
+    out[0] = v.x + v.y + v.z + v.w;
+}
+
 }  // namespace
 
 extern "C" {
+int emu_selftest_vector_load(const unsigned char *p, uint32_t *out)
+{
+    vector_load_kernel<<<1, 1, 0, 0>>>(p, out);
+    return cudaGetLastError();
+}
 int emu_selftest_racy(int *out)
 {
     racy_kernel<<<1, 64, 0, 0>>>(out);

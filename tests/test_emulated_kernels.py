@@ -90,6 +90,15 @@ def test_emulator_scheduling_orders_expose_a_race(emu):
     assert len(set(outs.values())) == 3, outs
 
 
+def test_emulator_ubsan_build_aborts_on_a_misaligned_vector_load(emu):
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import emu_lib; L = emu_lib.load(); b = emu_lib.aligned((64,), np.uint8); "
+            "o = np.zeros(1, np.uint32); assert L.emu_selftest_vector_load(b.ctypes.data, o.ctypes.data) == 0; print('aligned ok', flush=True); "
+            "L.emu_selftest_vector_load(b.ctypes.data + 4, o.ctypes.data); print('misaligned passed')" % os.path.join(ROOT, "tests", "emulate"))
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, TKB_EMU_UBSAN="1"), capture_output=True, text=True, timeout=900)
+    assert "aligned ok" in r.stdout and "misaligned passed" not in r.stdout and r.returncode != 0, r.stdout + r.stderr[-800:]
+    assert "misaligned address" in r.stderr or "alignment" in r.stderr, r.stderr[-800:]
+
+
 def test_emulator_simd_intrinsics_match_scalar_definitions(emu):
     L = emu.load()
     rng = np.random.default_rng(0)
@@ -201,7 +210,9 @@ def test_gpu_test_files_pass_on_the_emulator(emu):
     hardware yet: coarse assignment kernel, chunk minima inside the push exchange, saved-index queries), executed with
     TKB_EMU=1: the product's host layer and kernel sources against the oracle and the golden fixtures."""
     emu.load()                                                       # build once, before the child starts
-    env = dict(os.environ, TKB_EMU="1", TKB_RUN_UNVALIDATED="1", OMP_NUM_THREADS="2")
+    # the child uses the UBSan build of the emulated library: a misaligned access through a vector type (uint4, float4, ...: a
+    # "misaligned address" fault on the GPU) or an out-of-bounds index into a fixed-size array aborts the run
+    env = dict(os.environ, TKB_EMU="1", TKB_EMU_UBSAN="1", TKB_RUN_UNVALIDATED="1", OMP_NUM_THREADS="2")
     k = " and ".join("not (%s)" % s for s in _SKIP_ON_EMULATOR)
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider", "-k", k,
            os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_fused_gpu.py"),
