@@ -366,14 +366,19 @@ struct Alloc { std::string name; size_t bytes; bool owner; };
 std::map<void *, Alloc> g_allocs;
 int g_alloc_seq = 0;
 struct UnlinkAtExit {                                               // scratch buffers the library never frees
-    ~UnlinkAtExit() { for (auto &kv : g_allocs) if (kv.second.owner) shm_unlink(kv.second.name.c_str()); }
+    ~UnlinkAtExit() { for (auto &kv : g_allocs) if (kv.second.owner && !kv.second.name.empty()) shm_unlink(kv.second.name.c_str()); }
 } g_unlink_at_exit;
 
 void *map_shm(const std::string &name, size_t bytes, bool create)
 {
     const int fd = shm_open(name.c_str(), create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
     if (fd < 0) return nullptr;
-    if (create && ftruncate(fd, (off_t)bytes) != 0) { close(fd); shm_unlink(name.c_str()); return nullptr; }
+    // posix_fallocate reserves the pages now: a full /dev/shm fails here instead of raising SIGBUS at the first touch
+    if (create && (ftruncate(fd, (off_t)bytes) != 0 || posix_fallocate(fd, 0, (off_t)bytes) != 0)) {
+        close(fd);
+        shm_unlink(name.c_str());
+        return nullptr;
+    }
     void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
     close(fd);
     return p == MAP_FAILED ? nullptr : p;
@@ -386,7 +391,12 @@ cudaError_t cudaMalloc(void **p, size_t bytes)
     char name[64];
     snprintf(name, sizeof name, "/tkbemu_%d_%d", (int)getpid(), g_alloc_seq++);
     *p = map_shm(name, padded, true);
-    if (!*p) return cudaErrorMemoryAllocation;
+    if (!*p) {                                                      // no room in /dev/shm: private memory (no IPC handle for it)
+        *p = mmap(nullptr, padded, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (*p == MAP_FAILED) { *p = nullptr; return cudaErrorMemoryAllocation; }
+        g_allocs[*p] = Alloc{"", padded, true};
+        return cudaSuccess;
+    }
     g_allocs[*p] = Alloc{name, padded, true};
     return cudaSuccess;
 }
@@ -396,7 +406,7 @@ cudaError_t cudaFree(void *p)
     auto it = g_allocs.find(p);
     if (it == g_allocs.end() || !it->second.owner) return cudaErrorInvalidValue;
     munmap(p, it->second.bytes);
-    shm_unlink(it->second.name.c_str());
+    if (!it->second.name.empty()) shm_unlink(it->second.name.c_str());
     g_allocs.erase(it);
     return cudaSuccess;
 }
@@ -427,7 +437,7 @@ cudaError_t cudaDeviceGetAttribute(int *value, cudaDeviceAttr attr, int)
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p)
 {
     auto it = g_allocs.find(p);
-    if (it == g_allocs.end()) return cudaErrorInvalidValue;
+    if (it == g_allocs.end() || it->second.name.empty()) return cudaErrorInvalidValue;
     std::memset(h, 0, sizeof *h);
     snprintf(h->reserved, 48, "%s", it->second.name.c_str());
     const uint64_t bytes = it->second.bytes;
