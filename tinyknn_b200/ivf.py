@@ -18,7 +18,7 @@ heap contents.
                    then heap slot". One host sync per batch. This is the throughput mode.
 """
 import os
-from contextlib import contextmanager
+from contextlib import contextmanager, nullcontext
 
 import numpy as np
 
@@ -66,6 +66,9 @@ def _workspace_cap():
         free, _ = D.torch().cuda.mem_get_info()
         _ws_cap[dev_] = int(min(32 << 30, max(_WORKSPACE_BYTES, free // 4)))
     return _ws_cap[dev_]
+
+
+_NO_STAGE = nullcontext()
 
 
 class _Workspace:
@@ -239,12 +242,13 @@ class IVF:
         self.__dict__["_prof"] = {} if enabled else None
         self.__dict__["_scan_log"] = []
 
-    @contextmanager
     def _stage(self, name):
-        prof = self.__dict__.get("_prof")
-        if prof is None:
-            yield
-            return
+        """Context of one stage: nothing unless profile(True) asked for a CUDA-event pair around every stage."""
+        return _NO_STAGE if self.__dict__.get("_prof") is None else self._timed_stage(name)
+
+    @contextmanager
+    def _timed_stage(self, name):
+        prof = self.__dict__["_prof"]
         t = D.torch()
         e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
         e0.record()
