@@ -341,6 +341,42 @@ def _emu_worker(rank, world, port, out):
         got = sh.query_batch(mine, 10, n_probes=5, return_distances=True, exchange="nccl")
         bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
         sh.close()
+        # an index built ONCE: rank 0 passes its index, rank 1 passes nothing and receives the device copy (bench.py's N > 1 path)
+        ivf2 = synth.replicate_index(ivf if rank == 0 else None, dist)
+        bad += not synth.index_consistent(ivf2, dist)
+        bad += (rank == 1 and ivf2 is ivf)
+        ref2 = ivf2.query_batch(mine, 10, n_probes=5, order="device", return_distances=True)
+        bad += sum(not np.array_equal(a, b) for a, b in zip(ref, ref2))
+        sh = ShardedIVF(ivf2)
+        got = sh.query_batch(mine, 10, n_probes=5, return_distances=True, exchange="push")
+        bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
+        # dropping the unsharded copy really drops it: the wrapped index cannot answer on its own any more, the shard can
+        sh.drop_full_codes()
+        bad += ivf2.to_device()["codes"] is not None or sh.dev["codes"] is not None
+        try:
+            ivf2.query_batch(mine, 10, n_probes=5, order="device")
+            bad += 1
+        except Exception:                                              # noqa: BLE001  (TinyKnnError: null pointer)
+            pass
+        got = sh.query_batch(mine, 10, n_probes=5, return_distances=True, exchange="nccl")
+        bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
+        sh.close()
+        # a host-built index is sharded from its host arrays: a rank uploads the codes of its own lists only
+        if rank == 0:
+            ivf.__dict__.pop("_dev", None)
+            full_bytes = int(ivf._build_device()["codes"].numel())
+        box = [ivf if rank == 0 else None]
+        dist.broadcast_object_list(box, 0)                             # pickled host-side index (device copy excluded)
+        ivf3 = box[0]
+        ivf3.data = np.ascontiguousarray(X[:12_000].cpu().numpy())
+        ivf3.__dict__.pop("_dev", None)
+        sh = ShardedIVF(ivf3)
+        bad += "_dev" in ivf3.__dict__ or sh.dev["codes"] is not None
+        if rank == 0:
+            bad += not (0 < int(sh.dev["local_codes"].numel()) < full_bytes)
+        got = sh.query_batch(mine, 10, n_probes=5, return_distances=True, exchange="nccl")
+        bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
+        sh.close()
         np.save(out, np.array([bad]))
     finally:
         dist.destroy_process_group()

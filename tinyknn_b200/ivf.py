@@ -186,6 +186,13 @@ class IVF:
         dev = self.__dict__.get("_dev")
         if dev is not None:
             return dev
+        dev = self.__dict__["_dev"] = self._build_device()
+        return dev
+
+    def _build_device(self, owned=None):
+        """The device copy of the index. owned: optional bool mask over the lists -- only the codes of those lists are
+        uploaded (`local_codes` / `local_chunk_off`, `codes` stays None): what a rank of a list-sharded job holds
+        (sharded.ShardedIVF), so that an index whose codes do not fit one GPU can still be sharded."""
         D.require_cuda()
         ctd = self.pq_transformed_centers
         C = int(ctd.size)
@@ -193,21 +200,25 @@ class IVF:
         n_lists = len(self.pq_transformed_points)
         sizes = np.zeros(n_lists, dtype=np.int32)
         chunks = np.zeros(n_lists + 1, dtype=np.int64)
+        local = np.zeros(n_lists + 1, dtype=np.int64)
         parts, id_parts = [], []
         for l, td in enumerate(self.pq_transformed_points):
             n_l, packed = (0, None) if td is None or not isinstance(td, tuple) else td
             nc = 0 if packed is None else packed.shape[0]
             nc8 = -(-nc // 8) * 8                       # every list starts on a tile (8-chunk) boundary
+            mine = owned is None or bool(owned[l])
             if nc:
                 assert packed.shape[1] == M and packed.dtype == np.uint64
-                parts.append(packed)
-                if nc8 > nc:
-                    parts.append(np.zeros((nc8 - nc, M), dtype=np.uint64))
+                if mine:
+                    parts.append(packed)
+                    if nc8 > nc:
+                        parts.append(np.zeros((nc8 - nc, M), dtype=np.uint64))
                 ids_l = np.full(16 * nc8, -1, dtype=np.int64)
                 ids_l[:n_l] = np.asarray(self.ids[l], dtype=np.int64)[:n_l]
                 id_parts.append(ids_l)
             sizes[l] = n_l
             chunks[l + 1] = chunks[l] + nc8
+            local[l + 1] = local[l] + (nc8 if mine else 0)
         codes = np.concatenate(parts) if parts else np.zeros((1, M), dtype=np.uint64)
         ids = np.concatenate(id_parts) if id_parts else np.zeros(16, dtype=np.int64)
         real = ids[ids >= 0]
@@ -215,16 +226,18 @@ class IVF:
         data = self.data
         if not isinstance(data, np.ndarray) or data.dtype not in (np.float32, np.float64):
             data = np.ascontiguousarray(data, dtype=np.float64)
+        native = D.to_native(D.upload(codes), codes.shape[0], M)
         dev = dict(
             C=C, M=M, n_lists=n_lists, max_chunks=int(np.max(np.diff(chunks))) if n_lists else 0,
             max_real_chunks=int((int(sizes.max()) + 15) // 16) if n_lists else 0,
-            codes=D.to_native(D.upload(codes), codes.shape[0], M), n_chunks_total=int(codes.shape[0]),
+            codes=native, n_chunks_total=int(codes.shape[0]),
             list_chunk_off=D.upload(chunks), list_size=D.upload(sizes), ids=D.upload(ids),
             center_codes=D.to_native(D.upload(ctd.packed), ctd.packed.shape[0], M), center_chunks=int(ctd.packed.shape[0]),
             centers=D.upload(np.ascontiguousarray(self.active_centers, dtype=np.float32)),
             data=D.upload(data), data_dtype=DTYPE_F32 if data.dtype == np.float32 else DTYPE_F64,
             d=int(data.shape[1]), host_sizes=sizes, host_chunks=chunks, unique_ids=unique_ids)
-        self.__dict__["_dev"] = dev
+        if owned is not None:
+            dev.update(codes=None, local_codes=native, local_chunk_off=D.upload(local), n_chunks_total=int(local[-1]))
         return dev
 
     @staticmethod

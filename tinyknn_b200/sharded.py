@@ -229,14 +229,24 @@ class ShardedIVF:
     `query_batch(queries, k, n_probes)` is collective: every rank passes ITS OWN block of queries (the same
     number on every rank) and gets the results of that block."""
 
-    def __init__(self, ivf, rank=None, world=None, group=None, drop_full_codes=True):
+    def __init__(self, ivf, rank=None, world=None, group=None, drop_full_codes=False):
+        """drop_full_codes: give up the unsharded copy of the PQ codes (see `drop_full_codes()`). An index that has no
+        device copy yet is sharded from its HOST arrays: only the codes of this rank's lists are uploaded."""
         import torch.distributed as dist
         self.ivf = ivf
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
-        full = ivf.to_device()
         t = D.torch()
+        full = ivf.__dict__.get("_dev")
+        if full is None:                                                      # host-built index: upload my lists only
+            sizes = np.array([0 if (td is None or not isinstance(td, tuple)) else td[0] for td in ivf.pq_transformed_points],
+                             dtype=np.int64)
+            self.owner = assign_owners(sizes, self.world)
+            dev = ivf._build_device(owned=(self.owner == self.rank))
+            dev["list_owner"] = D.upload(self.owner)
+            self.dev = dev
+            return
         sizes = np.asarray(full["host_sizes"], dtype=np.int64)
         chunks = np.asarray(full["host_chunks"], dtype=np.int64)              # tile-padded CSR of the full index
         self.owner = assign_owners(sizes, self.world)
@@ -253,9 +263,18 @@ class ShardedIVF:
         dev = dict(full)
         dev.update(local_codes=local_codes, local_chunk_off=D.upload(local_chunks),
                    list_owner=D.upload(self.owner), n_chunks_total=int(local_chunks[-1]))
-        if drop_full_codes and self.world > 1:
-            dev["codes"] = None                                               # the full copy is not needed any more
         self.dev = dev
+        if drop_full_codes:
+            self.drop_full_codes()
+
+    def drop_full_codes(self):
+        """Free the unsharded copy of the PQ codes: from here on this rank holds only the codes of its own lists (capacity
+        scales with the number of ranks) and the wrapped IVF's own `query_batch` fails loudly (null code pointer)."""
+        self.dev["codes"] = None
+        full = self.ivf.__dict__.get("_dev")
+        if full is not None:
+            full["codes"] = None
+            full.pop("codes_ref", None)
 
     # The three local phases of a batch; query_batch strings them together with the two collectives (the
     # single-GPU test drives them for every rank in turn and moves the buffers by hand).

@@ -266,6 +266,72 @@ def index_consistent(ivf, dist, group=None):
     return bool((lo == hi).all().item())
 
 
+_REPL_SCALARS = ("C", "M", "n_lists", "max_chunks", "max_real_chunks", "n_chunks_total", "center_chunks", "d", "data_dtype")
+_REPL_ARRAYS = ("codes", "list_chunk_off", "list_size", "ids", "center_codes", "centers", "data")
+
+
+def _bcast_tensor(x, dist, src, group, like=None):
+    """Broadcast one device tensor from `src` (the receivers pass x=None): header (dtype code, ndim, shape), then the payload
+    in slices of at most 4 GiB (a 51 GB raw-vector matrix travels over NVLink in a fraction of a second per slice)."""
+    t = D.torch()
+    codes = [t.uint8, t.int8, t.int32, t.int64, t.float32, t.float64]
+    hdr = t.zeros(8, dtype=t.int64, device=D.device())
+    if x is not None:
+        x = x.contiguous()
+        hdr[0], hdr[1] = codes.index(x.dtype), x.dim()
+        for i, n in enumerate(x.shape):
+            hdr[2 + i] = n
+    dist.broadcast(hdr, src, group=group)
+    h = [int(v) for v in hdr.cpu().tolist()]
+    shape = tuple(h[2:2 + h[1]])
+    if x is None:
+        x = t.empty(shape, dtype=codes[h[0]], device=D.device())
+    flat = x.view(-1)
+    step = (4 << 30) // max(1, flat.element_size())
+    for lo in range(0, flat.numel(), step):
+        dist.broadcast(flat[lo:lo + step], src, group=group)
+    return x
+
+
+def replicate_index(ivf, dist, group=None, src=0):
+    """ONE index for a multi-GPU job (collective): rank `src` passes its built `IVF`, every other rank passes None and gets
+    an `IVF` whose DEVICE copy (codes, CSR offsets, sizes, ids, centroid codes, centroids, raw vectors) and quantizer are
+    rank `src`'s, bit for bit, received over NCCL -- nothing is rebuilt per rank, so the ranks of a list-sharded job cannot
+    disagree about an offset. The receivers hold no host-side list views (pq_transformed_points / ids stay empty): the
+    oracle checks run on the source rank, the query path only reads the device copy."""
+    t = D.torch()
+    rank = dist.get_rank(group)
+    if rank == src:
+        dev = ivf.to_device()
+        meta = dict(metric=ivf.metric, n_clusters=ivf.n_clusters, dpb=ivf.pq.dims_per_block, rotate_dim=ivf.pq.rotate_dim,
+                    has_R=ivf.pq.R is not None, unique_ids=bool(dev.get("unique_ids", False)),
+                    scalars=[int(dev[k]) for k in _REPL_SCALARS])
+        box = [meta]
+    else:
+        box = [None]
+    dist.broadcast_object_list(box, src, group=group)
+    meta = box[0]
+    if rank != src:
+        ivf = IVF(meta["metric"], meta["n_clusters"], FastPQ(meta["dpb"], rotate_dim=meta["rotate_dim"]))
+        dev = dict(zip(_REPL_SCALARS, meta["scalars"]), unique_ids=meta["unique_ids"])
+        ivf.__dict__["_dev"] = dev
+    pqc = _bcast_tensor(D.upload(np.ascontiguousarray(ivf.pq.centers, dtype=np.float32)) if rank == src else None, dist, src, group)
+    pqR = None
+    if meta["has_R"]:
+        pqR = _bcast_tensor(D.upload(np.ascontiguousarray(ivf.pq.R, dtype=np.float64)) if rank == src else None, dist, src, group)
+    for name in _REPL_ARRAYS:
+        dev[name] = _bcast_tensor(dev[name] if rank == src else None, dist, src, group)
+    if rank != src:
+        ivf.pq.centers = pqc.cpu().numpy()
+        ivf.pq.R = None if pqR is None else pqR.cpu().numpy()
+        ivf.pq.sqrt_n_blocks = np.sqrt(ivf.pq.centers.shape[1] // ivf.pq.dims_per_block)
+        dev["host_sizes"] = dev["list_size"].cpu().numpy()
+        dev["host_chunks"] = dev["list_chunk_off"].cpu().numpy()
+        ivf.all_centers = ivf.active_centers = None
+        ivf.data = DeviceRows(dev["data"])
+    return ivf
+
+
 def sync_index_from_rank0(ivf, dist, group=None):
     """Make every rank's DEVICE copy of the index equal to rank 0's (collective; NCCL broadcasts). Used when the ranks'
     independently built indexes differ: a list-sharded job needs one index. Host-side attributes (the per-list views the
