@@ -93,3 +93,15 @@ void tko_assign_f32(const float *x, int64_t n, int d, const float *c, int C, con
         out[i] = best;
     }
 }
+
+/* numpy's VECTOR @ MATRIX.T for float64 (`q @ R.T` in FastPQ.distance_table, ref: tinyknn/fast_pq.py:203-204) is OpenBLAS's
+ * dgemv, not gemm: four accumulators (k mod 4), each a sequential FMA chain, combined as (a0 + a2) + (a1 + a3).
+ * out[j] = that over k of a[k] * b[j][k]; K % 4 == 0 (every padded dimension of the avx build). tkb_lut.cu mirrors it. */
+void tko_dgemv4(const double *a, const double *b, double *out, int m, int K)
+{
+    for (int j = 0; j < m; j++) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k < K; k++) acc[k & 3] = fma(a[k], b[(int64_t)j * K + k], acc[k & 3]);
+        out[j] = (acc[0] + acc[2]) + (acc[1] + acc[3]);
+    }
+}

@@ -283,6 +283,35 @@ def test_numpy_matmul_is_a_sequential_fma_chain():
             assert np.array_equal(out, a @ b.T), (dt.__name__, n, m, K)
 
 
+def test_numpy_vector_times_matrix_is_a_four_lane_fma_chain(golden):
+    """The assumption the LUT kernel's rotation rests on (tkb_lut.cu; ref: fast_pq.py:203-204 `q @ R.T`): for a float64 VECTOR
+    numpy calls OpenBLAS's dgemv, which sums in four lanes (k mod 4), FMA, combined (a0 + a2) + (a1 + a3) -- pinned against
+    numpy itself for random inputs and against the reference's own rotated queries in the golden LUT fixture."""
+    import ctypes
+    L = _chain_lib()
+    L.tko_dgemv4.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    rng = np.random.default_rng(3)
+    for K, m in ((16, 16), (24, 24), (64, 64), (104, 64), (128, 64), (200, 64), (256, 64), (1024, 64)):
+        R = np.ascontiguousarray(rng.standard_normal((m, K)))
+        for _ in range(20):
+            q = rng.standard_normal(K).astype(np.float32)
+            out, q64 = np.empty(m, np.float64), q.astype(np.float64)
+            L.tko_dgemv4(_p(q64), _p(R), _p(out), m, K)
+            assert np.array_equal(out, q @ R.T), (K, m)
+    z = golden["lut"]
+    for name in z["names"]:
+        R = z[name + "_R"]
+        if R.size == 0 or R.shape[1] % 4:
+            continue
+        R = np.ascontiguousarray(R)
+        for q, want in zip(z[name + "_q"], z[name + "_qrot"]):
+            qp = np.zeros(R.shape[1], np.float64)
+            qp[:len(q)] = q
+            out = np.empty(R.shape[0], np.float64)
+            L.tko_dgemv4(_p(qp), _p(R), _p(out), R.shape[0], R.shape[1])
+            assert np.array_equal(out, want), name
+
+
 def test_scalar_encoder_arithmetic_equals_reference_codes(golden):
     """tko_encode_* (the arithmetic of tkb_encode.cu, one element at a time) reproduces the reference's packed codes."""
     L = _chain_lib()

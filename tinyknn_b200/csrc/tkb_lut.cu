@@ -157,13 +157,31 @@ lut_build_kernel(const float *__restrict__ queries, int d, int normalize, float 
 
     // ---- rotation q @ R.T (f64) or identity ----------------------------------------------------
     if (R) {
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int i = warp; i < Dp; i += LUT_THREADS / 32) {
-            const double *Ri = R + (size_t)i * Dpad;
+        // numpy's `q @ R.T` (f32 vector promoted to f64, times the f64 matrix) is OpenBLAS's dgemv: four accumulators
+        // (k mod 4), each a sequential FMA chain over k, combined as (a0 + a2) + (a1 + a3) -- established against numpy itself
+        // (numpy 2.3.5 / OpenBLAS 0.3.30, every Dpad % 4 == 0 from 16 to 1024: tests/test_oracle_pinned.py). The same
+        // operations in the same order here, four lanes per output, so q_rot equals numpy's bit for bit; a tail of Dpad % 4
+        // elements (sse build with odd block counts only) is summed separately and added last.
+        const int K4 = Dpad & ~3;
+        for (int u0 = 0; u0 < 4 * Dp; u0 += LUT_THREADS) {
+            const int u = u0 + tid, i = u >> 2, l = u & 3;
+            const bool valid = u < 4 * Dp;
             double acc = 0.0;
-            for (int k = lane; k < Dpad; k += 32) acc = fma((double)qpad[k], Ri[k], acc);
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-            if (lane == 0) qv[i] = (T)acc;
+            if (valid) {
+                const double *Ri = R + (size_t)i * Dpad;
+                for (int k = l; k < K4; k += 4) acc = fma((double)qpad[k], Ri[k], acc);
+            }
+            const double s = add_rn(acc, __shfl_xor_sync(FULL, acc, 2));        // lanes 0,2: a0 + a2; lanes 1,3: a1 + a3
+            double r = add_rn(s, __shfl_xor_sync(FULL, s, 1));                  // lane 0: (a0 + a2) + (a1 + a3)
+            if (valid && l == 0) {
+                if (K4 < Dpad) {
+                    const double *Ri = R + (size_t)i * Dpad;
+                    double t = 0.0;
+                    for (int k = K4; k < Dpad; k++) t = add_rn(t, mul_rn((double)qpad[k], Ri[k]));
+                    r = add_rn(r, t);
+                }
+                qv[i] = (T)r;
+            }
         }
     } else {
         for (int i = tid; i < Dp; i += LUT_THREADS) qv[i] = (T)qpad[i];
