@@ -206,7 +206,7 @@ _SKIP_ON_EMULATOR = ("test_replay_deep_heaps and 70000", "test_glove_shape_full_
 
 
 def test_gpu_test_files_pass_on_the_emulator(emu):
-    """tests/test_gpu_parity.py, test_fused_gpu.py and the quarantined test_unvalidated_gpu.py (code that has not run on
+    """tests/test_gpu_parity.py, test_fused_gpu.py and test_gpu_build_and_batch.py (code that first ran on
     hardware yet: coarse assignment kernel, chunk minima inside the push exchange, saved-index queries), executed with
     TKB_EMU=1: the product's host layer and kernel sources against the oracle and the golden fixtures."""
     emu.load()                                                       # build once, before the child starts
@@ -216,7 +216,7 @@ def test_gpu_test_files_pass_on_the_emulator(emu):
     k = " and ".join("not (%s)" % s for s in _SKIP_ON_EMULATOR)
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider", "-k", k,
            os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_fused_gpu.py"),
-           os.path.join(ROOT, "tests", "test_unvalidated_gpu.py")]
+           os.path.join(ROOT, "tests", "test_gpu_build_and_batch.py")]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = r.stdout[-3000:] + r.stderr[-1500:]
     assert r.returncode == 0, tail

@@ -1,7 +1,7 @@
-"""GPU tests of code written AFTER round 1's GPU budget was spent: none of this has run on hardware yet, so the file is
-skipped unless TKB_RUN_UNVALIDATED=1 (first thing to run next round: `TKB_RUN_UNVALIDATED=1 pytest tests/test_unvalidated_gpu.py`).
-Covers tkb_assign_dev (IVF.build's coarse assignment), the chunk minima inside the push exchange and the one-kernel probe
-selection (tkb_coarse_probes_dev). All of it passes on the CPU emulator (TKB_EMU=1, tests/emulate), which the CPU suite runs."""
+"""GPU tests of the build-time kernel tkb_assign_dev (IVF.build's coarse assignment), the chunk minima inside the push
+exchange, the one-kernel probe selection (tkb_coarse_probes_dev), the saved-index query, CUDA-graph and asynchronous batches.
+Written at the end of round 1 (first run on the CPU emulator, tests/emulate), validated on a B200 at the start of round 2:
+20 passed (profiles/r2_gputest_first_call.txt)."""
 import os
 
 import numpy as np
@@ -11,8 +11,7 @@ import tinyknn_b200 as tinyknn
 from oracle import restate as O
 from tinyknn_b200 import _device as D
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("TKB_RUN_UNVALIDATED") != "1", reason="not yet validated on a GPU (TKB_RUN_UNVALIDATED=1 runs it)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("metric,build_probes", [("angular", 1), ("euclidean", 1), ("angular", 2)])

@@ -48,6 +48,8 @@ SIGNATURES = {
     "tkb_ivf_replay_dev": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp],
     "tkb_replay_fresh_dev": [_vp, _i64, _i64, _i, _vp, _vp, _i, _i, _i, _vp],
     "tkb_ivf_replay_fresh_dev": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "tkb_ivf_scan_tc_workspace": [_i, _i, _i, _c.POINTER(_c.c_int64)],
+    "tkb_ivf_scan_tc_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp],
     "tkb_ivf_scan_native_cm_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp],
     "tkb_ivf_scan_native_push_cm_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i64, _i, _i, _vp, _i64, _vp],
     "tkb_ivf_replay_fresh_cm_dev": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],

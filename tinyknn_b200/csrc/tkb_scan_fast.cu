@@ -229,8 +229,9 @@ ivf_scan_fast_kernel(const uint4 *__restrict__ nat, const int64_t *__restrict__ 
                      const uint8_t *__restrict__ tables, const int32_t *__restrict__ probes, int P,
                      uint8_t *__restrict__ est, int64_t slot_stride, const int64_t *__restrict__ seg_off,
                      unsigned long long *stat, int keep, uint8_t *__restrict__ cmin,
-                     const int64_t *__restrict__ cm_home, int q_per_rank, int q_base)
+                     const int64_t *__restrict__ cm_home, int q_per_rank, int q_base, const uint8_t *__restrict__ skip_q)
 {
+    if (skip_q && skip_q[blockIdx.y]) return;        // the query's segments are scanned by another kernel (tkb_scan_tc.cu)
     extern __shared__ __align__(16) unsigned char smem[];
     ScanSmem sm;
     scan_smem_carve(smem, M, P, &sm);
@@ -392,7 +393,7 @@ int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, co
                            const uint8_t *tables, const int32_t *probes, int Q, int P, uint8_t *est,
                            int64_t slot_stride, const int64_t *seg_off, int64_t max_chunks_per_query, int order, int signd,
                            void *workspace, int64_t workspace_bytes, cudaStream_t st, uint8_t *cmin,
-                           const int64_t *cm_home, int q_per_rank)
+                           const int64_t *cm_home, int q_per_rank, const uint8_t *skip_q)
 {
     if (int rc = check_fast_args(M, order)) return rc;
     TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists > 0, "bad extent");
@@ -435,10 +436,12 @@ int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, co
         uint8_t *eb = seg_off ? est : est + (size_t)q0 * P * slot_stride;
         if (order == TKB_ORDER_AVX && signd)
             TKB_DISPATCH_FAST_AVXS(ivf_scan_fast_kernel, grid, scan_threads, smem, st, n4, list_chunk_off, list_size, n_lists, M,
-                                   tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep, cmin, cm_home, q_per_rank, q0);
+                                   tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep, cmin, cm_home, q_per_rank, q0,
+                                   skip_q ? skip_q + q0 : nullptr);
         else
             TKB_DISPATCH_FAST(ivf_scan_fast_kernel, grid, scan_threads, smem, st, n4, list_chunk_off, list_size, n_lists, M,
-                              tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep, cmin, cm_home, q_per_rank, q0);
+                              tables + (size_t)q0 * M * 16, probes + (size_t)q0 * P, P, eb, slot_stride, so, stat, keep, cmin, cm_home, q_per_rank, q0,
+                                   skip_q ? skip_q + q0 : nullptr);
         TKB_LAUNCH_CHECK();
     }
     return TKB_OK;

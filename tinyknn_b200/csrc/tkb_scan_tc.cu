@@ -1,0 +1,490 @@
+// tkb_scan_tc.cu -- the LIST-MAJOR PQ scan on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+// Replaces, for batches in which several queries probe the same inverted list, the same reference functions as
+// tkb_scan_fast.cu (compute_block_dists_avx + the scan half of query_pq_avx; ref: tinyknn/_fast_pq_256.pyx:65-156,
+// tinyknn/ivf.py:140-150), and produces the same bytes: one estimate per (query, scanned vector) in the compact segment
+// layout of tkb_ivf_plan_dev, plus the optional chunk minima.
+//
+// Why a GEMM is exact here. Per accumulation lane l (sub-quantizers with (j >> 1) & 1 == l) the
+// reference folds M/2 LUT entries with a saturating add after every step. The UNSATURATED lane sums are a linear map
+//     S_l[vector, query] = sum_j  onehot(code[vector][j])[0..16) . T_query[j][0..16)          (j in lane l)
+// i.e. (one-hot codes, 128 x 16*M/2, int8) x (LUT slab, 16*M/2 x queries, int8) -> int32, exactly what
+// `tcgen05.mma.kind::i8` computes. With N_l = sum_j max(0, -min_c T[j][c]) per (query, lane): N_l <= 128 means no
+// prefix of the fold can go below -128, S_l + N_l <= 127 means none can exceed 127, and then the reference's lane value
+// IS S_l and its estimate is clamp(S_0 + S_1). The certificate is checked per (vector, query); a pair that fails it is
+// refolded step by step (the reference's own recurrence) from the LUT slab in shared memory before the tile is written;
+// a query with N_l > 128 is left to the CUDA-core kernel (tkb_scan_fast.cu) altogether.
+//
+// Why list-major. The CUDA-core scan reads a list's codes once per (query, list) and spends ~1.7 ALU instructions per
+// lookup: on the 100M x 128 index it is bound by HBM *and* by the integer pipe at the same time. Here a 128-vector tile
+// of a list is expanded to one-hot form ONCE (by the CUDA cores, straight into tensor memory as the A operand) and
+// multiplied with the LUTs of ALL the queries of the batch that probe this list (B operand, shared memory): the code bytes
+// are read once per list and batch, and the per-(vector, query) work left on the CUDA cores is the epilogue.
+//
+// Work decomposition: a counting sort of the batch's (query, probe slot) pairs by list (tc_count / tc_offsets / tc_fill),
+// then a persistent kernel, one CTA per SM, pulls items = (list, group of <= NT queries, range of tiles).
+//
+//   A (TMEM, K-major)  : lane r = vector r of the tile, 32-bit column 4j + w = bytes 4w..4w+3 of onehot(code[r][j])
+//   B (SMEM, K-major, no swizzle): unit (j, i) = the 16 LUT bytes T_i[j][0..16) at (j * NT + (i / 8) * 8 + i % 8) * 16:
+//                        8-query core matrices of 128 B, stride-byte-offset 128 B, leading-byte-offset NT * 16 B
+//   D (TMEM)           : two accumulators (lane 0 / lane 1), column n = query n of the group, int32
+//   one MMA per sub-quantizer pair p (K = 32 bytes = 2 units), accumulating into D[p & 1].
+#include <stdlib.h>
+
+#include "tkb_scan_core.cuh"
+
+namespace tkb {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_NT = 64;                       // queries per group (UMMA N <= 64: 2 x 2 x 64 accumulator columns + 256 of A)
+constexpr int TC_TILES_PER_ITEM = 64;           // tiles (of 128 vectors) per work item: long lists are split
+constexpr int TC_OUT_STRIDE = TC_NT / 4 + 1;    // words per row of the transposed output tile (padded: conflict-free)
+constexpr int TC_PATCH_CAP = 1024;
+
+struct TcQueryMeta { int16_t elig, k0, k1, pad; };
+
+// ---- work list -------------------------------------------------------------------------------------------------------
+// ws (int32 words): [0] total items, [1] next item (persistent kernel's counter), [2] refolded pairs (statistic), [3] pad;
+// then cnt[n_lists], cursor[n_lists], bucket_off[n_lists + 1], item_off[n_lists + 1], bucket[Q * P].
+struct TcWork {
+    int *hdr, *cnt, *cursor, *bucket_off, *item_off, *bucket;
+    TcQueryMeta *qmeta;
+    int64_t *seg_rest;
+    uint8_t *skip_q;
+};
+
+__host__ __device__ inline size_t tc_carve(void *base, int Q, int P, int n_lists, TcWork *w)
+{
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 15) / 16 * 16; return at; };
+    const size_t hdr = take(16), cnt = take(4 * (size_t)n_lists), cur = take(4 * (size_t)n_lists);
+    const size_t bo = take(4 * ((size_t)n_lists + 1)), io = take(4 * ((size_t)n_lists + 1));
+    const size_t bk = take(4 * (size_t)Q * P), qm = take(sizeof(TcQueryMeta) * (size_t)Q), sr = take(8 * (size_t)Q * P);
+    const size_t sk = take((size_t)Q);
+    if (w) {
+        unsigned char *b = reinterpret_cast<unsigned char *>(base);
+        w->hdr = reinterpret_cast<int *>(b + hdr); w->cnt = reinterpret_cast<int *>(b + cnt);
+        w->cursor = reinterpret_cast<int *>(b + cur); w->bucket_off = reinterpret_cast<int *>(b + bo);
+        w->item_off = reinterpret_cast<int *>(b + io); w->bucket = reinterpret_cast<int *>(b + bk);
+        w->qmeta = reinterpret_cast<TcQueryMeta *>(b + qm); w->seg_rest = reinterpret_cast<int64_t *>(b + sr);
+        w->skip_q = b + sk;
+    }
+    return o;
+}
+
+// one warp per query: N_l = sum over the lane's rows of max(0, -min_c T[j][c]); eligible iff both <= 128
+__global__ void tc_query_meta_kernel(const uint8_t *__restrict__ tables, int Q, int M, TcQueryMeta *__restrict__ qmeta,
+                                     uint8_t *__restrict__ skip_q)
+{
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    int n0 = 0, n1 = 0;
+    for (int j = lane; j < M; j += 32) {
+        const uint4 r = reinterpret_cast<const uint4 *>(tables + (size_t)q * M * 16)[j];
+        const uint32_t m4 = __vmins4(__vmins4(r.x, r.y), __vmins4(r.z, r.w));
+        const uint32_t m2 = __vmins4(m4, m4 >> 16);
+        const int mn = (int)(int8_t)(__vmins4(m2, m2 >> 8) & 0xffu);
+        const int c = mn < 0 ? -mn : 0;
+        if ((j >> 1) & 1) n1 += c; else n0 += c;
+    }
+    for (int o = 16; o > 0; o >>= 1) { n0 += __shfl_xor_sync(FULL, n0, o); n1 += __shfl_xor_sync(FULL, n1, o); }
+    if (lane == 0) {
+        TcQueryMeta m;
+        m.elig = (n0 <= 128 && n1 <= 128) ? 1 : 0;
+        m.k0 = (int16_t)(127 - n0); m.k1 = (int16_t)(127 - n1); m.pad = 0;
+        qmeta[q] = m;
+        skip_q[q] = (uint8_t)m.elig;             // the CUDA-core kernel skips the queries this kernel handles
+    }
+}
+
+__global__ void tc_count_kernel(const int32_t *__restrict__ probes, const int64_t *__restrict__ seg_off, int64_t QP, int P,
+                                int n_lists, const TcQueryMeta *__restrict__ qmeta, int *__restrict__ cnt,
+                                int64_t *__restrict__ seg_rest)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= QP) return;
+    int l = probes[e];
+    const int64_t so = seg_off[e];
+    const bool valid = l != PROBE_SKIP && so >= 0;
+    if (valid && l < 0) l += n_lists;                 // Python-wrapped list index (ref: ivf.py:141 indexes a list)
+    const bool tc = valid && l >= 0 && l < n_lists && qmeta[e / P].elig;
+    if (tc) atomicAdd(cnt + l, 1);
+    seg_rest[e] = tc ? -2 : so;                      // -2: taken by the tensor-core path (any negative = absent for the CUDA-core kernel)
+}
+
+// one CTA: exclusive prefix sums over the lists of (pairs) and (work items)
+__global__ void __launch_bounds__(1024)
+tc_offsets_kernel(const int *__restrict__ cnt, const int32_t *__restrict__ list_size, int n_lists, int *__restrict__ bucket_off,
+                  int *__restrict__ item_off, int *__restrict__ hdr)
+{
+    __shared__ int s_a[1024], s_b[1024];
+    const int tid = threadIdx.x, per = (n_lists + 1023) / 1024;
+    const int lo = tid * per, hi = min(n_lists, lo + per);
+    int a = 0, b = 0;
+    for (int l = lo; l < hi; l++) {
+        const int c = cnt[l];
+        const int tiles = (((list_size[l] + 15) >> 4) + 7) >> 3;
+        a += c;
+        b += ((c + TC_NT - 1) / TC_NT) * ((tiles + TC_TILES_PER_ITEM - 1) / TC_TILES_PER_ITEM);
+    }
+    s_a[tid] = a; s_b[tid] = b;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int va = tid >= o ? s_a[tid - o] : 0, vb = tid >= o ? s_b[tid - o] : 0;
+        __syncthreads();
+        s_a[tid] += va; s_b[tid] += vb;
+        __syncthreads();
+    }
+    int ra = s_a[tid] - a, rb = s_b[tid] - b;
+    for (int l = lo; l < hi; l++) {
+        const int c = cnt[l];
+        const int tiles = (((list_size[l] + 15) >> 4) + 7) >> 3;
+        bucket_off[l] = ra; item_off[l] = rb;
+        ra += c;
+        rb += ((c + TC_NT - 1) / TC_NT) * ((tiles + TC_TILES_PER_ITEM - 1) / TC_TILES_PER_ITEM);
+    }
+    if (tid == 1023) { bucket_off[n_lists] = s_a[1023]; item_off[n_lists] = s_b[1023]; hdr[0] = s_b[1023]; }
+}
+
+__global__ void tc_fill_kernel(const int32_t *__restrict__ probes, const int64_t *__restrict__ seg_rest, int64_t QP, int n_lists,
+                               const int *__restrict__ bucket_off, int *__restrict__ cursor, int *__restrict__ bucket)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= QP || seg_rest[e] != -2) return;
+    int l = probes[e];
+    if (l < 0) l += n_lists;
+    bucket[bucket_off[l] + atomicAdd(cursor + l, 1)] = (int)e;
+}
+
+#ifndef TKB_EMULATE                      // tensor memory and tcgen05 have no CPU stand-in (tests/emulate): the entry point reports that
+// ---- tcgen05 / mbarrier wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem_d] (+)= A[tmem_a] (128 x 32 int8, TMEM) * B[desc_b] (N x 32 int8, SMEM, K-major)
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+}
+
+// K-major, no swizzle: start address, leading-byte-offset (between the two 16-byte K chunks of one MMA), stride-byte-offset
+// (between 8-row core matrices), descriptor version 1 (Blackwell)
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)((lbo_bytes & 0x3ffffu) >> 4) << 16) |
+           ((uint64_t)((sbo_bytes & 0x3ffffu) >> 4) << 32) | (1ull << 46);
+}
+
+// kind::i8 instruction descriptor: D = s32, A = B = signed 8 bit, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_i8(int n)
+{
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// the 16-byte one-hot unit of a 4-bit code: word c >> 2 holds 1 << 8 * (c & 3)
+__device__ __forceinline__ void onehot_unit(uint32_t c, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3)
+{
+    const uint32_t x = 1u << ((c & 3u) << 3), h = c >> 2;
+    w0 = h == 0 ? x : 0u; w1 = h == 1 ? x : 0u; w2 = h == 2 ? x : 0u; w3 = h == 3 ? x : 0u;
+}
+
+struct TcSmem {
+    uint64_t mbar;
+    uint32_t tmem_base;
+    int item, n_patch;
+    int q_of[TC_NT];                            // query of group member i (-1: padding column)
+    int2 kq[TC_NT];                             // certificate thresholds of its two lanes
+    long long dst[TC_NT];                       // est offset of its segment
+    uint32_t outT[128 * TC_OUT_STRIDE];         // estimates of the tile: row = vector, byte n = query n of the group
+    uint32_t patch[TC_PATCH_CAP];               // (row << 16) | query column of the pairs whose certificate failed
+};
+
+template <int PH>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict__ list_chunk_off,
+                   const int32_t *__restrict__ list_size, int n_lists, const uint8_t *__restrict__ tables, int P,
+                   uint8_t *__restrict__ est, const int64_t *__restrict__ seg_off, uint8_t *__restrict__ cmin, TcWork W)
+{
+    constexpr int M = 2 * PH;
+    constexpr int A_COLS = 8 * PH;                                   // 32-bit columns of one one-hot tile
+    constexpr int D_COL0 = 256;                                      // accumulators: lane l at D_COL0 + l * TC_NT
+    static_assert(A_COLS <= 256, "one-hot tile does not fit beside the accumulators");
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    TcSmem &S = *reinterpret_cast<TcSmem *>(tc_smem);
+    uint8_t *B = tc_smem + ((sizeof(TcSmem) + 127) / 128) * 128;     // LUT slab: M * TC_NT units of 16 bytes
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
+    const int row = 32 * (warp & 3) + lane;                          // TMEM lane = vector of the tile this thread owns
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        mbar_init(&S.mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+    uint32_t phase = 0;
+
+    for (;;) {
+        if (tid == 0) S.item = atomicAdd(W.hdr + 1, 1);
+        __syncthreads();
+        const int item = S.item;
+        if (item >= W.hdr[0]) break;
+        // ---- decode the item: list, query group, tile range ---------------------------------------------------------
+        int lo = 0, hi = n_lists;                                    // largest l with item_off[l] <= item
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (W.item_off[mid] <= item) lo = mid; else hi = mid; }
+        const int l = lo;
+        const int cnt = W.cnt[l], n_real = (list_size[l] + 15) >> 4, tiles = (n_real + 7) >> 3;
+        const int splits = (tiles + TC_TILES_PER_ITEM - 1) / TC_TILES_PER_ITEM;
+        const int local = item - W.item_off[l], g = local / splits, sp = local - g * splits;
+        const int per = (tiles + splits - 1) / splits, t0 = sp * per, t1 = min(tiles, t0 + per);
+        const int nq = min(TC_NT, cnt - g * TC_NT);
+        const int N = max(16, (nq + 15) & ~15);
+        const int64_t c0 = list_chunk_off[l];                        // first chunk of the list (a multiple of 8: tile aligned)
+        // ---- group members, LUT slab -----------------------------------------------------------------------------------
+        if (tid < TC_NT) {
+            int q = -1;
+            long long d = 0;
+            int2 k = make_int2(0, 0);
+            if (tid < nq) {
+                const int e = W.bucket[W.bucket_off[l] + g * TC_NT + tid];
+                q = e / P;
+                d = seg_off[e];
+                const TcQueryMeta m = W.qmeta[q];
+                k = make_int2(m.k0, m.k1);
+            }
+            S.q_of[tid] = q; S.dst[tid] = d; S.kq[tid] = k;
+        }
+        if (tid == 0) S.n_patch = 0;
+        __syncthreads();
+        for (int u = tid; u < M * N; u += TC_THREADS) {              // unit (j, i): the LUT row j of group member i
+            const int i = u % N, j = u / N;
+            const int q = S.q_of[i];
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (q >= 0) v = reinterpret_cast<const uint4 *>(tables + ((size_t)q * M + j) * 16)[0];
+            *reinterpret_cast<uint4 *>(B + ((size_t)j * TC_NT + i) * 16) = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        __syncthreads();
+        const uint32_t idesc = umma_idesc_i8(N);
+        const int nh = N >> 1;                                        // query columns per warpgroup in the epilogue
+
+        for (int t = t0; t < t1; t++) {
+            // ---- expand: this thread's vector, the warpgroup's half of the sub-quantizer pairs --------------------------
+            {
+                const int s = row >> 4, v = row & 15, gq = v >> 2, sh = 16 * (gq & 1) + 4 * (v & 3);
+                const uint32_t *tb = nat32 + (((size_t)(c0 >> 3) + t) * PH * 8 + s) * 4 + (gq >> 1);
+#pragma unroll
+                for (int pi = 0; pi < PH / 2; pi++) {
+                    const int p = wg * (PH / 2) + pi;
+                    const uint32_t wa = __ldg(tb + (size_t)p * 32), wb = __ldg(tb + (size_t)p * 32 + 2);
+                    uint32_t r[8];
+                    onehot_unit((wa >> sh) & 15u, r[0], r[1], r[2], r[3]);
+                    onehot_unit((wb >> sh) & 15u, r[4], r[5], r[6], r[7]);
+                    tmem_st8(tmem + lane_base + 8 * p, r);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+            tc_fence_before();
+            __syncthreads();
+            // ---- multiply: one MMA per sub-quantizer pair, lanes alternate --------------------------------------------------
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t b0 = smem_u32(B);
+#pragma unroll
+                for (int p = 0; p < PH; p++)
+                    umma_i8_ts(tmem + D_COL0 + (p & 1) * TC_NT, tmem + 8 * p,
+                               umma_desc_kmajor(b0 + (uint32_t)(2 * p) * TC_NT * 16, TC_NT * 16, 128), idesc, p >= 2 ? 1u : 0u);
+                umma_commit(&S.mbar);
+            }
+            mbar_wait(&S.mbar, phase);
+            phase ^= 1;
+            tc_fence_after();
+            // ---- epilogue: certificate, clamp, transposed tile in shared memory --------------------------------------------
+            for (int c8 = 0; c8 < nh; c8 += 8) {
+                const int n0 = wg * nh + c8;
+                uint32_t a[8], b[8];
+                tmem_ld8(tmem + lane_base + D_COL0 + n0, a);
+                tmem_ld8(tmem + lane_base + D_COL0 + TC_NT + n0, b);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t o[2] = {0, 0};
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int2 k = S.kq[n0 + u];
+                    const int s0 = (int)a[u], s1 = (int)b[u];
+                    const int e = min(max(s0 + s1, -128), 127);
+                    o[u >> 2] |= (uint32_t)(e & 0xff) << (8 * (u & 3));
+                    if ((s0 > k.x || s1 > k.y) && n0 + u < nq) {
+                        const int i = atomicAdd(&S.n_patch, 1);
+                        if (i < TC_PATCH_CAP) S.patch[i] = ((uint32_t)row << 16) | (uint32_t)(n0 + u);   // overflow: the whole tile is refolded
+                    }
+                }
+                S.outT[row * TC_OUT_STRIDE + (n0 >> 2)] = o[0];
+                S.outT[row * TC_OUT_STRIDE + (n0 >> 2) + 1] = o[1];
+            }
+            tc_fence_before();
+            __syncthreads();
+            // ---- refold the pairs whose certificate failed: the reference's recurrence, from the slab ----------------------
+            {
+                const int np = S.n_patch;
+                const bool all = np > TC_PATCH_CAP;                  // queue overflow: every (row, query) of the tile
+                const int total = all ? 128 * nq : np;
+                for (int i = tid; i < total; i += TC_THREADS) {
+                    const int r = all ? i % 128 : (int)(S.patch[i] >> 16), n = all ? i / 128 : (int)(S.patch[i] & 0xffffu);
+                    const int s = r >> 4, v = r & 15, gq = v >> 2, sh = 16 * (gq & 1) + 4 * (v & 3);
+                    const uint32_t *tb = nat32 + (((size_t)(c0 >> 3) + t) * PH * 8 + s) * 4 + (gq >> 1);
+                    const uint8_t *Bq = B + (size_t)n * 16;
+                    int a0 = 0, a1 = 0;
+                    for (int p = 0; p < PH; p++) {
+                        const uint32_t ca = (__ldg(tb + (size_t)p * 32) >> sh) & 15u, cb = (__ldg(tb + (size_t)p * 32 + 2) >> sh) & 15u;
+                        const int ta = (int)(int8_t)Bq[(size_t)(2 * p) * TC_NT * 16 + ca];
+                        const int tb2 = (int)(int8_t)Bq[(size_t)(2 * p + 1) * TC_NT * 16 + cb];
+                        if (p & 1) a1 = sat_add8<true>(sat_add8<true>(a1, ta), tb2);
+                        else       a0 = sat_add8<true>(sat_add8<true>(a0, ta), tb2);
+                    }
+                    reinterpret_cast<uint8_t *>(S.outT)[(r * TC_OUT_STRIDE + (n >> 2)) * 4 + (n & 3)] = (uint8_t)sat_add8<true>(a0, a1);
+                }
+                if (tid == 0 && np) { atomicAdd(W.hdr + 2, np); S.n_patch = 0; }
+            }
+            __syncthreads();
+            // ---- write the tile: 16 estimates (one chunk) of one query per task, coalesced 16-byte stores -------------------
+            for (int task = tid; task < nq * 8; task += TC_THREADS) {
+                const int n = task >> 3, sc = task & 7;
+                const int chunk = t * 8 + sc;
+                if (chunk >= n_real) continue;
+                uint32_t o[4];
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    uint32_t x = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const uint32_t word = S.outT[(16 * sc + 4 * w + b) * TC_OUT_STRIDE + (n >> 2)];
+                        x |= ((word >> (8 * (n & 3))) & 0xffu) << (8 * b);
+                    }
+                    o[w] = x;
+                }
+                const long long off = S.dst[n] + 16LL * chunk;
+                *reinterpret_cast<uint4 *>(est + off) = make_uint4(o[0], o[1], o[2], o[3]);
+                if (cmin) {
+                    uint32_t m = __vmins4(__vmins4(o[0], o[1]), __vmins4(o[2], o[3]));
+                    m = __vmins4(m, m >> 16);
+                    m = __vmins4(m, m >> 8);
+                    cmin[off >> 4] = (uint8_t)(m & 0xffu);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+#endif  // TKB_EMULATE
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+int tc_workspace_bytes(int Q, int P, int n_lists, int64_t *bytes)
+{
+    TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists >= 0 && bytes, "bad extent");
+    *bytes = (int64_t)tc_carve(nullptr, Q, P, n_lists, nullptr) + 256;
+    return TKB_OK;
+}
+
+int launch_ivf_scan_tc(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
+                       const uint8_t *tables, const int32_t *probes, int Q, int P, uint8_t *est, const int64_t *seg_off,
+                       uint8_t *cmin, int64_t max_chunks_per_query, void *workspace, int64_t workspace_bytes, cudaStream_t st)
+{
+#ifdef TKB_EMULATE
+    return set_err(TKB_ERR_INVALID, "the tensor-core scan needs an sm_100a device (not available on the CPU emulator)");
+#else
+    TKB_REQUIRE(M == 32, "the tensor-core scan is built for M = 32 sub-quantizers (d = 128 rotated to 64)");
+    TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists > 0, "bad extent");
+    if (Q == 0 || P == 0) return TKB_OK;
+    TKB_REQUIRE(native && list_chunk_off && list_size && tables && probes && est && seg_off && workspace, "null pointer");
+    TKB_REQUIRE((int64_t)Q * P <= 0x7fffffffLL, "too many (query, probe) units for one launch");
+    TKB_REQUIRE((uintptr_t)workspace % 16 == 0 && (uintptr_t)est % 16 == 0 && (uintptr_t)tables % 16 == 0, "pointers must be 16-byte aligned");
+    int64_t need = 0;
+    tc_workspace_bytes(Q, P, n_lists, &need);
+    TKB_REQUIRE(workspace_bytes >= need, "workspace too small (tkb_ivf_scan_tc_workspace)");
+    TcWork W;
+    tc_carve(workspace, Q, P, n_lists, &W);
+    const int64_t QP = (int64_t)Q * P;
+    // hdr, cnt, cursor are contiguous at the start of the workspace
+    TKB_CUDA(cudaMemsetAsync(workspace, 0, (size_t)((unsigned char *)W.bucket_off - (unsigned char *)workspace), st));
+    tc_query_meta_kernel<<<(Q + 7) / 8, 256, 0, st>>>(tables, Q, M, W.qmeta, W.skip_q);
+    TKB_LAUNCH_CHECK();
+    tc_count_kernel<<<(unsigned)((QP + 255) / 256), 256, 0, st>>>(probes, seg_off, QP, P, n_lists, W.qmeta, W.cnt, W.seg_rest);
+    TKB_LAUNCH_CHECK();
+    tc_offsets_kernel<<<1, 1024, 0, st>>>(W.cnt, list_size, n_lists, W.bucket_off, W.item_off, W.hdr);
+    TKB_LAUNCH_CHECK();
+    tc_fill_kernel<<<(unsigned)((QP + 255) / 256), 256, 0, st>>>(probes, W.seg_rest, QP, n_lists, W.bucket_off, W.cursor, W.bucket);
+    TKB_LAUNCH_CHECK();
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        TKB_CUDA(cudaGetDevice(&dev));
+        TKB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // one CTA per SM (the kernel owns all 512 TMEM columns): the slab + the rest of the shared memory is padded past half an SM's
+    const size_t smem = ((sizeof(TcSmem) + 127) / 128) * 128 + (size_t)M * TC_NT * 16 + 128;
+    const size_t smem_req = smem > 120 * 1024 ? smem : 120 * 1024;
+    TKB_CUDA(cudaFuncSetAttribute(ivf_scan_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
+    ivf_scan_tc_kernel<16><<<n_sm, TC_THREADS, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native), list_chunk_off, list_size,
+                                                                n_lists, tables, P, est, seg_off, cmin, W);
+    TKB_LAUNCH_CHECK();
+    // the (query, list) pairs the tensor-core path does not take (queries whose LUT fails the per-query precondition):
+    // the CUDA-core kernel, which skips every query marked in skip_q
+    return launch_ivf_scan_native(native, list_chunk_off, list_size, n_lists, M, tables, probes, Q, P, est, 0, W.seg_rest,
+                                  max_chunks_per_query, TKB_ORDER_AVX, 1, nullptr, 0, st, cmin, nullptr, 0, W.skip_q);
+#endif
+}
+
+}  // namespace tkb

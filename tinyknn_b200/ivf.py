@@ -11,9 +11,10 @@ whole index resident in HBM and runs, per batch of queries:
 Selection order (`order=`): the reference picks probe lists and the final k with np.argpartition,
 whose output ORDER is numpy-build/CPU specific while the visiting order of the lists changes the
 heap contents.
-  order="numpy"  : the two tiny selections (<= 2*n_probes+10 and <= pass_1 floats per query) are done
-                   by numpy's own argpartition on the host, exactly like the reference -- bit-exact
-                   ids on the machine that runs it. `IVF.query` uses this.
+  order="numpy"  : the two tiny selections (<= 2*n_probes+10 and <= pass_1 floats per query) are done on the
+                   host exactly like the reference: numpy's own arithmetic for the exact distances of those few
+                   candidates and numpy's own argpartition -- the reference's ids on the machine that runs it.
+                   `IVF.query` uses this.
   order="device" : everything stays on the GPU; ties and order are resolved as "ascending distance,
                    then heap slot". One host sync per batch. This is the throughput mode.
 """
@@ -40,10 +41,14 @@ CMIN_CHUNKS = int(os.environ.get("TKB_CMIN_CHUNKS", "8192"))
 # Reuse the temporaries of a block shape across batches (per stream) instead of allocating 23 tensors per block.
 WORKSPACE_REUSE = os.environ.get("TKB_WORKSPACE_REUSE", "1") != "0"
 # Probe selection as one kernel (tkb_coarse_probes_dev) instead of scan / replay / gather / select. Opt-in until it has been
-# timed on hardware; results are identical (tests/test_unvalidated_gpu.py, run on the emulator).
+# timed on hardware; results are identical (tests/test_gpu_build_and_batch.py, run on the emulator).
 COARSE_FUSED = os.environ.get("TKB_COARSE_FUSED", "0") != "0"
 # IVF.build: coarse assignment on the GPU (tkb_assign_dev). Opt-in until it has been validated on hardware.
 ASSIGN_DEVICE = os.environ.get("TKB_ASSIGN_DEVICE", "0") != "0"
+# List-major scan on the tensor cores (tkb_ivf_scan_tc_dev; csrc/tkb_scan_tc.cu): "0" never, "1" whenever the kernel applies
+# (M = 32, avx order), "auto" = when the batch puts at least TC_MIN_SHARE queries on an average list.
+TC_SCAN = os.environ.get("TKB_TC_SCAN", "0")
+TC_MIN_SHARE = float(os.environ.get("TKB_TC_MIN_SHARE", "6"))
 _streams = {}
 _ws_cap = {}
 
@@ -300,6 +305,10 @@ class IVF:
             queries = np.ascontiguousarray(queries, dtype=np.float32)
         Q, d = queries.shape
         assert dev["d"] == d                                            # ref: ivf.py:161
+        if Q == 0:
+            ddt0 = np.float32 if dev["data_dtype"] == DTYPE_F32 else np.float64
+            out0 = (np.zeros((0, k), np.int64), np.zeros((0,), np.int32), np.zeros((0, k), ddt0))
+            return out0 if return_distances else out0[:2]
         C = dev["C"]
         P = min(n_probes, C)                                            # ref: fast_pq.py:291
         Rc = min(2 * P + 10, C)                                         # ref: fast_pq.py:293-295
@@ -361,7 +370,7 @@ class IVF:
         sequence of launches of one batch is captured once and replayed per call, which removes the host-side launch
         cost that a synchronous caller pays in front of every batch (about 26 launches). Returns a `GraphedBatch`;
         `graphed(...)(queries)` gives the same results as `query_batch(queries, k, n_probes, order="device")`.
-        NOT YET RUN ON A GPU (written after round 1's GPU budget was spent): tests/test_unvalidated_gpu.py."""
+        NOT YET RUN ON A GPU (written after round 1's GPU budget was spent): tests/test_gpu_build_and_batch.py."""
         return GraphedBatch(self, int(n_queries), int(k), int(n_probes), pass_1, sub_batches)
 
     # -- stages of one block of queries (shared with the list-sharded index, sharded.py) ----------------
@@ -404,9 +413,16 @@ class IVF:
                 if order == "device":
                     check(lib.tkb_select_probes_dev(D.ptr(hci), D.ptr(dc), DTYPE_F32, Q, Rc, P, D.ptr(probes), st))
                 else:
-                    hci_h, dc_h = hci.cpu().numpy(), dc.cpu().numpy()
-                    best = np.argpartition(dc_h, P, axis=1)[:, :P]       # == per-row bottom_k (utils.py:22-25)
-                    probes = D.upload(np.take_along_axis(hci_h, best, axis=1).astype(np.int32))
+                    # parity mode: the <= 2 n_probes + 10 exact distances per query with numpy's own arithmetic on the host
+                    # (knn_brute1, utils.py:89-92), not the GPU's differently ordered sums: a near-tie must break as it does in
+                    # the reference, because the visiting order of the lists decides the heap
+                    hci_h, q_h = hci.cpu().numpy(), qn.cpu().numpy()
+                    cen = np.asarray(self.active_centers)
+                    top = np.empty((Q, P), dtype=np.int32)
+                    for i in range(Q):
+                        diff = cen[hci_h[i]] - q_h[i]                    # a -1 slot indexes the last centroid, like the reference
+                        top[i] = hci_h[i][bottom_k(np.einsum("ij,ij->i", diff, diff), P)]
+                    probes = D.upload(top)
         self._last = dict(center_heap=hci, tables=tables)
         return probes
 
@@ -423,7 +439,19 @@ class IVF:
         with self._stage("scan"):
             if _fp.SCAN_IMPL == "fast":
                 ws = buf("scan_ws", (64,), np.uint8)                     # its first 8 bytes count the recomputed chunks
-                if push_cm is not None:                                  # (per-home minima table, queries per rank)
+                use_tc = (TC_SCAN != "0" and push_cm is None and est is not None and seg_off is not None and M == 32
+                          and _fp._order() == 1 and codes_key == "codes"
+                          and (TC_SCAN == "1" or Q * P >= TC_MIN_SHARE * max(1, dev["C"])))
+                if use_tc:
+                    import ctypes
+                    need = ctypes.c_int64(0)
+                    check(lib.tkb_ivf_scan_tc_workspace(Q, P, n_lists, ctypes.byref(need)))
+                    tws = buf("tc_ws", (need.value,), np.uint8)
+                    check(lib.tkb_ivf_scan_tc_dev(D.ptr(dev[codes_key]), D.ptr(dev[off_key]), D.ptr(dev["list_size"]), n_lists, M,
+                                                  D.ptr(tables), D.ptr(probes), Q, P, D.ptr(est), D.ptr(seg_off), D.ptr(cmin),
+                                                  max_q_chunks, D.ptr(tws), tws.numel(), st))
+                    self._last["tc_ws"] = tws
+                elif push_cm is not None:                                # (per-home minima table, queries per rank)
                     check(lib.tkb_ivf_scan_native_push_cm_dev(D.ptr(dev[codes_key]), D.ptr(dev[off_key]), D.ptr(dev["list_size"]), n_lists, M,
                                                               D.ptr(tables), D.ptr(probes), Q, P, D.ptr(seg_off), D.ptr(push_cm[0]), push_cm[1],
                                                               max_q_chunks, _fp._order(), 1, D.ptr(ws), ws.numel(), st))
@@ -471,7 +499,9 @@ class IVF:
                 check(lib.tkb_select_topk_dev(D.ptr(hi_), D.ptr(dd), dev["data_dtype"], Q, pass_1, k,
                                               D.ptr(oi), D.ptr(od), D.ptr(oc), st))
             return oi, oc, od
-        hi_h, dd_h = hi_.cpu().numpy(), dd.cpu().numpy()
+        # parity mode: the exact rescoring distances with numpy's own arithmetic on the host (ref: ivf.py:161-163,
+        # utils.py:89-92), so that near-ties among the <= pass_1 candidates break exactly as in the reference
+        hi_h, dd_h, q_h = hi_.cpu().numpy(), dd.cpu().numpy(), qn.cpu().numpy()
         ids = np.full((Q, k), -1, dtype=np.int64)
         dst = np.full((Q, k), np.inf, dtype=ddt)
         cnt = np.zeros(Q, dtype=np.int32)
@@ -479,6 +509,8 @@ class IVF:
             keep = hi_h[i] != -1                                         # ref: ivf.py:154-155
             cand, cd = hi_h[i][keep], dd_h[i][keep]
             if len(cand) > k:                                            # ref: ivf.py:158-163
+                diff = self.data[cand] - q_h[i]
+                cd = np.einsum("ij,ij->i", diff, diff)
                 best = bottom_k(cd, k)
                 cand, cd = cand[best], cd[best]
             cnt[i] = len(cand)

@@ -39,7 +39,7 @@ from ._lib import PLAN_SEND, PLAN_RECV, PLAN_PUSH, PROBE_SKIP
 # default exchange of ShardedIVF.query_batch: "push" (NVLink peer stores from the scan kernel) or "nccl" (all-to-all)
 EXCHANGE = os.environ.get("TKB_EXCHANGE", "push")
 # chunk minima inside the push exchange (the home buffer carries a minima region). Opt-in: written after round 1's GPU
-# budget was spent, not yet run on hardware (tests/test_unvalidated_gpu.py).
+# budget was spent, not yet run on hardware (tests/test_gpu_build_and_batch.py).
 PUSH_CMIN = os.environ.get("TKB_PUSH_CMIN", "0") != "0"
 
 
