@@ -595,6 +595,8 @@ def main():
                         algorithmic_bytes_per_launch=ab, kernel_ms=ms, codes_per_s=scanned / (ms * 1e-3), flagged_chunks=flagged)
 
         def counter(ws_key):
+            if ws_key == "patch_ws" and "tc_ws" in last:              # tensor-core scan: refolded (vector, query) pairs
+                return None
             return int(last[ws_key][:16].cpu().numpy().view(np.int64)[0 if ws_key == "patch_ws" else 1]) if ws_key in last else None
 
         if fused_run:
@@ -615,6 +617,11 @@ def main():
         else:
             roof = dict(bound="hbm", scanned_vectors_per_launch=scanned, launches_per_step=blocks_per_step,
                         **scan_roof(per_step(stages["scan"]), counter("patch_ws")))
+        if "tc_ws" in last:
+            hdr = last["tc_ws"][:16].cpu().numpy().view(np.int32)
+            roof.update(kernel="ivf_scan_tc", tc_work_items=int(hdr[0]), tc_refolded_pairs=int(hdr[2]),
+                        note="list-major tensor-core scan (tcgen05.mma kind::i8): the code bytes are read once per list and batch, "
+                             "so `achieved` (algorithmic bytes / time) is not bounded by the HBM peak; see `traffic`")
         code_bytes = dev["n_chunks_total"] * M * 8 if not sharded else extra.get("code_bytes_per_rank", 0)
         roof.update(peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                     kernel_timing="CUDA events around the launch on its stream, one stream, %d steps right after the timed region"

@@ -392,16 +392,16 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
     // one list of flagged chunks per warp
     long long *s_qoff = reinterpret_cast<long long *>(rq_sm + (((size_t)((unsigned char *)(s_round + QPC) - rq_sm) + 15) & ~(size_t)15));
     uint32_t *LST = reinterpret_cast<uint32_t *>(s_qoff + QPC);            // [n_warps][RQ_CM_BLOCK]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = RQ_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NTH = blockDim.x, n_warps = NTH / 32;   // 64, 128 or 256 threads
     const int q0 = blockIdx.x * QPC;
     const uint32_t flip = SIGNED ? 0u : 0x80u;                             // stored byte = value ^ flip
     const int init = 127;                                                  // stored form of the reference's 127 / 255
 
-    for (int i = tid; i < QPC * HS; i += RQ_THREADS) {
+    for (int i = tid; i < QPC * HS; i += NTH) {
         const int j = i % HS;
         H[i] = (j >= 1 && j <= R) ? (((uint32_t)init << 24) | RQ2_EMPTY) : RQ2_SENTINEL;
     }
-    for (int t = tid; t < QPC; t += RQ_THREADS) {
+    for (int t = tid; t < QPC; t += NTH) {
         const int q = q0 + t;
         int *c = cum + (size_t)t * (P + 1);
         bool ok = q < Q;
@@ -684,7 +684,7 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
     }
 
     // ---- resolve labels and write the heap arrays --------------------------------------------------
-    for (int i = tid; i < R * QPC; i += RQ_THREADS) {
+    for (int i = tid; i < R * QPC; i += NTH) {
         const int t = i / R, j = i - t * R;
         const int q = q0 + t;
         if (q >= Q) continue;
@@ -785,18 +785,28 @@ int launch_ivf_replay(const uint8_t *est, int64_t slot_stride, const int64_t *se
 
 // Queue-replay launch geometry: QPC queries per CTA (a power of two <= 16), queue capacity QCAP records,
 // LPW lanes (queries) per consumer warp.
-struct RqGeom { int qpc, qcap, lpw; size_t smem; int v2, lanes; };
+struct RqGeom { int qpc, qcap, lpw; size_t smem; int v2, lanes, threads; };
 
 static size_t rq_smem(int R, int P, int qpc, int qcap)
 {
     return (size_t)qpc * (8 * ((size_t)R + 1) + 8 * ((size_t)qcap + 1) + 4 * ((size_t)P + 1) + 20) + 16;
 }
 
-static size_t rq2_smem(int R, int P, int qpc, int qcap, bool cm = false)
+static size_t rq2_smem(int R, int P, int qpc, int qcap, bool cm = false, int threads = RQ_THREADS)
 {
     const size_t base = (size_t)qpc * (4 * (2 * (size_t)R + 4) + 4 * ((size_t)qcap + 2) + 4 * ((size_t)P + 1) + 20) + 16;
     // chunk-minimum path: s_qoff[qpc] + one list of RQ_CM_BLOCK chunk numbers per warp
-    return cm ? base + 16 + 8 * (size_t)qpc + 4 * (size_t)(RQ_THREADS / 32) * RQ_CM_BLOCK : base;
+    return cm ? base + 16 + 8 * (size_t)qpc + 4 * (size_t)(threads / 32) * RQ_CM_BLOCK : base;
+}
+
+// Launch geometry knobs of the pipelined replay (A/B switches; results do not depend on them): threads per CTA (TKB_RQ_THREADS:
+// 64 / 128 / 256), queue capacity in multiples of R (TKB_RQ_QCAP: 1..8, default 4), shared memory per CTA that decides how many
+// queries share one (TKB_RQ_SMEM_KB, default 45)
+static int rq_env(const char *name, int dflt, int lo, int hi)
+{
+    const char *e = getenv(name);
+    const int v = e ? atoi(e) : dflt;
+    return (v < lo || v > hi) ? dflt : v;
 }
 
 static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 0, bool cm = false)
@@ -804,7 +814,7 @@ static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 
     if (R <= 0 || P <= 0) return false;
     static int v2_env = -1;
     if (v2_env < 0) { const char *e = getenv("TKB_RQ2"); v2_env = e ? atoi(e) : 1; }
-    g.v2 = 0; g.lanes = 0;
+    g.v2 = 0; g.lanes = 0; g.threads = RQ_THREADS;
     if (v2_env && R <= 65535 && stream_chunks < (1 << 20) - 1) {                    // pipelined kernel: an insert takes <= floor(log2 R) + 1 steps <= 2 * lanes
         g.v2 = 1;
         g.lanes = R <= 255 ? 4 : 8;
@@ -813,16 +823,23 @@ static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 
         static int lanes_env = -1;
         if (lanes_env < 0) { const char *e = getenv("TKB_RQ_LANES"); lanes_env = e ? atoi(e) : 0; }
         if (lanes_env == 8) g.lanes = 8;
-        g.qcap = 4 * R < 128 ? 128 : 4 * R;
+        static int qcap_mult = 0, smem_kb = 0, threads = 0;
+        if (!qcap_mult) {
+            qcap_mult = rq_env("TKB_RQ_QCAP", 4, 1, 8); smem_kb = rq_env("TKB_RQ_SMEM_KB", 45, 8, 200);
+            threads = rq_env("TKB_RQ_THREADS", 256, 64, 256);
+            if (threads != 64 && threads != 128) threads = 256;
+        }
+        g.threads = threads;
+        g.qcap = qcap_mult * R < 128 ? 128 : qcap_mult * R;
         // CTAs wanted before queries are packed 16 to a CTA (TKB_RQ_MIN_CTAS, default 2 x 148). The launch list of round 1
         // shows a 5 000-query launch (313 CTAs) taking almost as long as a 10 000-query one: worth an A/B at 4 x 148.
         static int min_ctas = 0;
         if (!min_ctas) { const char *e = getenv("TKB_RQ_MIN_CTAS"); min_ctas = e ? atoi(e) : 0; if (min_ctas <= 0) min_ctas = 2 * 148; }
         int qpc = 16;
         while (qpc > 1 && (Q + qpc - 1) / qpc < min_ctas) qpc >>= 1;
-        while (qpc > 1 && rq2_smem(R, P, qpc, g.qcap) > 45 * 1024) qpc >>= 1;
+        while (qpc > 1 && rq2_smem(R, P, qpc, g.qcap) > (size_t)smem_kb * 1024) qpc >>= 1;
         g.qpc = qpc; g.lpw = 0;
-        g.smem = rq2_smem(R, P, qpc, g.qcap, cm);
+        g.smem = rq2_smem(R, P, qpc, g.qcap, cm, g.threads);
         if (g.smem <= 200 * 1024) return true;
         g.v2 = 0;
     }
@@ -861,7 +878,7 @@ static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t
 #define TKB_RQ2_LAUNCH(LANES, CMV)                                                                                                   \
         do {                                                                                                                         \
             TKB_CUDA(cudaFuncSetAttribute(replay_rq2_kernel<SIGNED, LANES, CMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
-            replay_rq2_kernel<SIGNED, LANES, CMV><<<blocks, RQ_THREADS, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off, \
+            replay_rq2_kernel<SIGNED, LANES, CMV><<<blocks, g.threads, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off, \
                                                                                      list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val,  \
                                                                                      R, fallback, g.qpc, g.qcap, cmin, rq_qpw());               \
         } while (0)

@@ -224,203 +224,346 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int n)
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-// the 16-byte one-hot unit of a 4-bit code: word c >> 2 holds 1 << 8 * (c & 3)
+// The 16-byte one-hot unit of a 4-bit code c: byte k = (k == c). One PRMT per 32-bit word: the selector nibble of byte b of
+// word w is c ^ (4w + b); it is 0 (-> source byte 0 = 0x01) exactly when c == 4w + b, any other nibble value selects a zero byte
+// (or, with bit 3 set, the replicated sign bit of a byte that is 0x00 or 0x01, i.e. zero).
 __device__ __forceinline__ void onehot_unit(uint32_t c, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3)
 {
-    const uint32_t x = 1u << ((c & 3u) << 3), h = c >> 2;
-    w0 = h == 0 ? x : 0u; w1 = h == 1 ? x : 0u; w2 = h == 2 ? x : 0u; w3 = h == 3 ? x : 0u;
+    const uint32_t cr = c * 0x1111u;
+    w0 = prmt(1u, 0u, cr ^ 0x3210u); w1 = prmt(1u, 0u, cr ^ 0x7654u);
+    w2 = prmt(1u, 0u, cr ^ 0xba98u); w3 = prmt(1u, 0u, cr ^ 0xfedcu);
 }
 
-struct TcSmem {
-    uint64_t mbar;
-    uint32_t tmem_base;
-    int item, n_patch;
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- roles of the persistent kernel -------------------------------------------------------------------------------------
+//   warps 0..7   expansion : thread = one vector (TMEM lane) of the tile, warps 0-3 the first half of the sub-quantizer pairs,
+//                            warps 4-7 the second half; one-hot units straight into tensor memory (tcgen05.st)
+//   warps 8..15  epilogue  : thread = one vector, warps 8-11 the first half of the group's queries, 12-15 the second half;
+//                            tcgen05.ld, certificate, clamp, transposed tile in shared memory, coalesced 16-byte stores
+//   warp 16      multiplies: one thread issues the tile's PH tcgen05.mma and commits them to the mbarriers
+//   warp 17      loads     : fetches the next work item, stages its LUT slab (double-buffered)
+// A and D are double-buffered in tensor memory, so the expansion of tile t+1, the MMAs of tile t and the epilogue of tile t-1
+// run at the same time; nothing but mbarriers (and one named barrier inside the epilogue group) synchronises the roles.
+constexpr int TC_E_WARPS = 8, TC_P_WARPS = 8;
+constexpr int TC_WARPS = TC_E_WARPS + TC_P_WARPS + 2;
+constexpr int TC_THREADS2 = 32 * TC_WARPS;
+constexpr int TC_QUEUE = 2048;                  // refold queue of one work item
+
+struct TcItem {
+    int valid, list, nq, N, t0, t1, n_real, pad;
+    long long tile0;                            // first tile of the list in the code array
     int q_of[TC_NT];                            // query of group member i (-1: padding column)
     int2 kq[TC_NT];                             // certificate thresholds of its two lanes
     long long dst[TC_NT];                       // est offset of its segment
-    uint32_t outT[128 * TC_OUT_STRIDE];         // estimates of the tile: row = vector, byte n = query n of the group
-    uint32_t patch[TC_PATCH_CAP];               // (row << 16) | query column of the pairs whose certificate failed
 };
 
+struct TcShared {
+    uint64_t item_full[2], item_empty[2], a_full[2], a_empty[2], d_full[2], d_empty[2];
+    uint32_t tmem_base;
+    int n_queue;
+    TcItem item[2];
+    uint32_t outT[128 * TC_OUT_STRIDE];         // estimates of the tile: row = vector, byte n = query n of the group
+    uint32_t queue[TC_QUEUE];                   // (tile << 16) | (row << 8) | query column of the pairs whose certificate failed
+};
+
+// the reference's fold of one (vector, query): codes from the code array, LUT rows from the slab
 template <int PH>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__device__ __forceinline__ int tc_refold(const uint32_t *__restrict__ nat32, long long tile, int r, const uint8_t *Bq)
+{
+    const int s = r >> 4, v = r & 15, gq = v >> 2, sh = 16 * (gq & 1) + 4 * (v & 3);
+    const uint32_t *tb = nat32 + ((size_t)tile * PH * 8 + s) * 4 + (gq >> 1);
+    int a0 = 0, a1 = 0;
+#pragma unroll 4
+    for (int p = 0; p < PH; p++) {
+        const uint32_t ca = (__ldg(tb + (size_t)p * 32) >> sh) & 15u, cb = (__ldg(tb + (size_t)p * 32 + 2) >> sh) & 15u;
+        const int ta = (int)(int8_t)Bq[(size_t)(2 * p) * TC_NT * 16 + ca];
+        const int tb2 = (int)(int8_t)Bq[(size_t)(2 * p + 1) * TC_NT * 16 + cb];
+        if (p & 1) a1 = sat_add8<true>(sat_add8<true>(a1, ta), tb2);
+        else       a0 = sat_add8<true>(sat_add8<true>(a0, ta), tb2);
+    }
+    return sat_add8<true>(a0, a1);
+}
+
+// signed minimum into one byte of global memory (chunk minima after a refold: the value can only go down)
+__device__ __forceinline__ void atomic_min_s8(uint8_t *addr, int v)
+{
+    unsigned int *word = reinterpret_cast<unsigned int *>(reinterpret_cast<uintptr_t>(addr) & ~(uintptr_t)3);
+    const int sh = 8 * (int)(reinterpret_cast<uintptr_t>(addr) & 3);
+    unsigned int old = *reinterpret_cast<volatile unsigned int *>(word);
+    for (;;) {
+        if ((int)(int8_t)((old >> sh) & 0xffu) <= v) return;
+        const unsigned int want = (old & ~(0xffu << sh)) | ((unsigned int)(v & 0xff) << sh);
+        const unsigned int seen = atomicCAS(word, old, want);
+        if (seen == old) return;
+        old = seen;
+    }
+}
+
+template <int PH>
+__global__ void __launch_bounds__(TC_THREADS2, 1)
 ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict__ list_chunk_off,
                    const int32_t *__restrict__ list_size, int n_lists, const uint8_t *__restrict__ tables, int P,
                    uint8_t *__restrict__ est, const int64_t *__restrict__ seg_off, uint8_t *__restrict__ cmin, TcWork W)
 {
     constexpr int M = 2 * PH;
     constexpr int A_COLS = 8 * PH;                                   // 32-bit columns of one one-hot tile
-    constexpr int D_COL0 = 256;                                      // accumulators: lane l at D_COL0 + l * TC_NT
-    static_assert(A_COLS <= 256, "one-hot tile does not fit beside the accumulators");
+    constexpr int D_COL0 = 2 * A_COLS;                               // accumulator (buffer b, lane l) at D_COL0 + (2 b + l) * TC_NT
+    static_assert(2 * A_COLS + 4 * TC_NT <= 512, "tensor memory: two one-hot tiles + two pairs of accumulators");
     extern __shared__ __align__(128) unsigned char tc_smem[];
-    TcSmem &S = *reinterpret_cast<TcSmem *>(tc_smem);
-    uint8_t *B = tc_smem + ((sizeof(TcSmem) + 127) / 128) * 128;     // LUT slab: M * TC_NT units of 16 bytes
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
-    const int row = 32 * (warp & 3) + lane;                          // TMEM lane = vector of the tile this thread owns
-    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    TcShared &S = *reinterpret_cast<TcShared *>(tc_smem);
+    uint8_t *Bslab = tc_smem + ((sizeof(TcShared) + 127) / 128) * 128;   // two LUT slabs of M * TC_NT units of 16 bytes
+    constexpr size_t SLAB = (size_t)M * TC_NT * 16;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    if (tid == 0) {
-        mbar_init(&S.mbar, 1);
+    if (tid == 32) {
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&S.item_full[b], 32);
+            mbar_init(&S.item_empty[b], TC_E_WARPS + TC_P_WARPS + 1);
+            mbar_init(&S.a_full[b], TC_E_WARPS);
+            mbar_init(&S.a_empty[b], 1);
+            mbar_init(&S.d_full[b], 1);
+            mbar_init(&S.d_empty[b], TC_P_WARPS);
+        }
+        S.n_queue = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
-    uint32_t phase = 0;
 
-    for (;;) {
-        if (tid == 0) S.item = atomicAdd(W.hdr + 1, 1);
-        __syncthreads();
-        const int item = S.item;
-        if (item >= W.hdr[0]) break;
-        // ---- decode the item: list, query group, tile range ---------------------------------------------------------
-        int lo = 0, hi = n_lists;                                    // largest l with item_off[l] <= item
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (W.item_off[mid] <= item) lo = mid; else hi = mid; }
-        const int l = lo;
-        const int cnt = W.cnt[l], n_real = (list_size[l] + 15) >> 4, tiles = (n_real + 7) >> 3;
-        const int splits = (tiles + TC_TILES_PER_ITEM - 1) / TC_TILES_PER_ITEM;
-        const int local = item - W.item_off[l], g = local / splits, sp = local - g * splits;
-        const int per = (tiles + splits - 1) / splits, t0 = sp * per, t1 = min(tiles, t0 + per);
-        const int nq = min(TC_NT, cnt - g * TC_NT);
-        const int N = max(16, (nq + 15) & ~15);
-        const int64_t c0 = list_chunk_off[l];                        // first chunk of the list (a multiple of 8: tile aligned)
-        // ---- group members, LUT slab -----------------------------------------------------------------------------------
-        if (tid < TC_NT) {
-            int q = -1;
-            long long d = 0;
-            int2 k = make_int2(0, 0);
-            if (tid < nq) {
-                const int e = W.bucket[W.bucket_off[l] + g * TC_NT + tid];
-                q = e / P;
-                d = seg_off[e];
-                const TcQueryMeta m = W.qmeta[q];
-                k = make_int2(m.k0, m.k1);
+    if (warp == TC_WARPS - 1) {
+        // ================================ loader =====================================================================
+        for (uint32_t it = 0;; it++) {
+            const int par = it & 1;
+            mbar_wait(&S.item_empty[par], ((it >> 1) & 1) ^ 1);
+            TcItem &I = S.item[par];
+            int item = 0;
+            if (lane == 0) item = atomicAdd(W.hdr + 1, 1);
+            item = __shfl_sync(FULL, item, 0);
+            if (item >= W.hdr[0]) {
+                if (lane == 0) I.valid = 0;
+                __syncwarp();
+                mbar_arrive(&S.item_full[par]);
+                break;
             }
-            S.q_of[tid] = q; S.dst[tid] = d; S.kq[tid] = k;
+            int lo = 0, hi = n_lists;                                // largest l with item_off[l] <= item
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (W.item_off[mid] <= item) lo = mid; else hi = mid; }
+            const int l = lo;
+            const int cnt = W.cnt[l], n_real = (list_size[l] + 15) >> 4, tiles = (n_real + 7) >> 3;
+            const int splits = (tiles + TC_TILES_PER_ITEM - 1) / TC_TILES_PER_ITEM;
+            const int local = item - W.item_off[l], g = local / splits, sp = local - g * splits;
+            const int per = (tiles + splits - 1) / splits, t0 = sp * per, t1 = min(tiles, t0 + per);
+            const int nq = min(TC_NT, cnt - g * TC_NT);
+            const int N = max(16, (nq + 15) & ~15);
+            if (lane == 0) {
+                I.valid = 1; I.list = l; I.nq = nq; I.N = N; I.t0 = t0; I.t1 = t1; I.n_real = n_real;
+                I.tile0 = list_chunk_off[l] >> 3;                    // lists start on a tile
+            }
+            for (int i = lane; i < TC_NT; i += 32) {
+                int q = -1;
+                long long d = 0;
+                int2 k = make_int2(0, 0);
+                if (i < nq) {
+                    const int e = W.bucket[W.bucket_off[l] + g * TC_NT + i];
+                    q = e / P;
+                    d = seg_off[e];
+                    const TcQueryMeta m = W.qmeta[q];
+                    k = make_int2(m.k0, m.k1);
+                }
+                I.q_of[i] = q; I.dst[i] = d; I.kq[i] = k;
+            }
+            __syncwarp();
+            uint8_t *B = Bslab + (size_t)par * SLAB;
+            for (int u0 = 0; u0 < M * N; u0 += 32 * 8) {             // unit (j, i): LUT row j of group member i; 8 loads in flight
+                uint4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int u = u0 + 32 * k + lane;
+                    v[k] = make_uint4(0, 0, 0, 0);
+                    if (u < M * N) {
+                        const int q = I.q_of[u % N];
+                        if (q >= 0) v[k] = __ldg(reinterpret_cast<const uint4 *>(tables + ((size_t)q * M + u / N) * 16));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int u = u0 + 32 * k + lane;
+                    if (u < M * N) *reinterpret_cast<uint4 *>(B + ((size_t)(u / N) * TC_NT + u % N) * 16) = v[k];
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(&S.item_full[par]);
         }
-        if (tid == 0) S.n_patch = 0;
-        __syncthreads();
-        for (int u = tid; u < M * N; u += TC_THREADS) {              // unit (j, i): the LUT row j of group member i
-            const int i = u % N, j = u / N;
-            const int q = S.q_of[i];
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (q >= 0) v = reinterpret_cast<const uint4 *>(tables + ((size_t)q * M + j) * 16)[0];
-            *reinterpret_cast<uint4 *>(B + ((size_t)j * TC_NT + i) * 16) = v;
+    } else if (warp == TC_WARPS - 2) {
+        // ================================ MMA issuer =================================================================
+        uint32_t g = 0;                                              // tiles issued so far (buffer = g & 1)
+        for (uint32_t it = 0;; it++) {
+            const int par = it & 1;
+            mbar_wait(&S.item_full[par], (it >> 1) & 1);
+            const TcItem &I = S.item[par];
+            if (!I.valid) break;
+            if (lane == 0) {
+                const uint32_t idesc = umma_idesc_i8(I.N);
+                const uint32_t b0 = smem_u32(Bslab + (size_t)par * SLAB);
+                for (int t = I.t0; t < I.t1; t++, g++) {
+                    const uint32_t b = g & 1, ph = (g >> 1) & 1;
+                    mbar_wait(&S.a_full[b], ph);
+                    mbar_wait(&S.d_empty[b], ph ^ 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int p = 0; p < PH; p++)
+                        umma_i8_ts(tmem + D_COL0 + (2 * b + (p & 1)) * TC_NT, tmem + b * A_COLS + 8 * p,
+                                   umma_desc_kmajor(b0 + (uint32_t)(2 * p) * TC_NT * 16, TC_NT * 16, 128), idesc, p >= 2 ? 1u : 0u);
+                    umma_commit(&S.a_empty[b]);
+                    umma_commit(&S.d_full[b]);
+                }
+            }
+            g = __shfl_sync(FULL, g, 0);
+            if (lane == 0) mbar_arrive(&S.item_empty[par]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-        __syncthreads();
-        const uint32_t idesc = umma_idesc_i8(N);
-        const int nh = N >> 1;                                        // query columns per warpgroup in the epilogue
-
-        for (int t = t0; t < t1; t++) {
-            // ---- expand: this thread's vector, the warpgroup's half of the sub-quantizer pairs --------------------------
-            {
-                const int s = row >> 4, v = row & 15, gq = v >> 2, sh = 16 * (gq & 1) + 4 * (v & 3);
-                const uint32_t *tb = nat32 + (((size_t)(c0 >> 3) + t) * PH * 8 + s) * 4 + (gq >> 1);
+    } else if (warp < TC_E_WARPS) {
+        // ================================ expansion ==================================================================
+        const int row = 32 * (warp & 3) + lane, eg = warp >> 2;
+        const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+        const int s = row >> 4, v = row & 15, gq = v >> 2, sh = 16 * (gq & 1) + 4 * (v & 3);
+        uint32_t g = 0;
+        for (uint32_t it = 0;; it++) {
+            const int par = it & 1;
+            mbar_wait(&S.item_full[par], (it >> 1) & 1);
+            const TcItem &I = S.item[par];
+            if (!I.valid) break;
+            const int t0 = I.t0, t1 = I.t1;
+            const uint32_t *tb = nat32 + ((size_t)(I.tile0 + t0) * PH * 8 + s) * 4 + (gq >> 1) + (size_t)eg * (PH / 2) * 32;
+            uint32_t cur[PH];                                         // this thread's code words of the tile: PH/2 pairs x 2
+#pragma unroll
+            for (int pi = 0; pi < PH / 2; pi++) { cur[2 * pi] = __ldg(tb + pi * 32); cur[2 * pi + 1] = __ldg(tb + pi * 32 + 2); }
+            for (int t = t0; t < t1; t++, g++) {
+                const uint32_t b = g & 1, ph = (g >> 1) & 1;
+                uint32_t nxt[PH];
+                if (t + 1 < t1) {                                     // the next tile's words are in flight while this one is expanded
+                    const uint32_t *tn = tb + (size_t)(t + 1 - t0) * PH * 32;
+#pragma unroll
+                    for (int pi = 0; pi < PH / 2; pi++) { nxt[2 * pi] = __ldg(tn + pi * 32); nxt[2 * pi + 1] = __ldg(tn + pi * 32 + 2); }
+                }
+                mbar_wait(&S.a_empty[b], ph ^ 1);
+                tc_fence_after();
 #pragma unroll
                 for (int pi = 0; pi < PH / 2; pi++) {
-                    const int p = wg * (PH / 2) + pi;
-                    const uint32_t wa = __ldg(tb + (size_t)p * 32), wb = __ldg(tb + (size_t)p * 32 + 2);
                     uint32_t r[8];
-                    onehot_unit((wa >> sh) & 15u, r[0], r[1], r[2], r[3]);
-                    onehot_unit((wb >> sh) & 15u, r[4], r[5], r[6], r[7]);
-                    tmem_st8(tmem + lane_base + 8 * p, r);
+                    onehot_unit((cur[2 * pi] >> sh) & 15u, r[0], r[1], r[2], r[3]);
+                    onehot_unit((cur[2 * pi + 1] >> sh) & 15u, r[4], r[5], r[6], r[7]);
+                    tmem_st8(tmem + lane_base + b * A_COLS + 8 * (eg * (PH / 2) + pi), r);
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.a_full[b]);
+                if (t + 1 < t1) {
+#pragma unroll
+                    for (int i = 0; i < PH; i++) cur[i] = nxt[i];
+                }
             }
-            tc_fence_before();
-            __syncthreads();
-            // ---- multiply: one MMA per sub-quantizer pair, lanes alternate --------------------------------------------------
-            if (tid == 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.item_empty[par]);
+        }
+    } else {
+        // ================================ epilogue ===================================================================
+        const int pw = warp - TC_E_WARPS, pg = pw >> 2, ptid = tid - 32 * TC_E_WARPS;
+        const int row = 32 * (warp & 3) + lane;
+        const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+        uint32_t g = 0;
+        for (uint32_t it = 0;; it++) {
+            const int par = it & 1;
+            mbar_wait(&S.item_full[par], (it >> 1) & 1);
+            const TcItem &I = S.item[par];
+            if (!I.valid) break;
+            const int t0 = I.t0, t1 = I.t1, N = I.N, nq = I.nq, n_real = I.n_real, nh = N >> 1;
+            const long long tile0 = I.tile0;
+            const uint8_t *B = Bslab + (size_t)par * SLAB;
+            for (int t = t0; t < t1; t++, g++) {
+                const uint32_t b = g & 1, ph = (g >> 1) & 1;
+                mbar_wait(&S.d_full[b], ph);
                 tc_fence_after();
-                const uint32_t b0 = smem_u32(B);
+                for (int c8 = 0; c8 < nh; c8 += 8) {
+                    const int n0 = pg * nh + c8;
+                    uint32_t a[8], c[8];
+                    tmem_ld8(tmem + lane_base + D_COL0 + (2 * b) * TC_NT + n0, a);
+                    tmem_ld8(tmem + lane_base + D_COL0 + (2 * b + 1) * TC_NT + n0, c);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    uint32_t o[2] = {0, 0};
 #pragma unroll
-                for (int p = 0; p < PH; p++)
-                    umma_i8_ts(tmem + D_COL0 + (p & 1) * TC_NT, tmem + 8 * p,
-                               umma_desc_kmajor(b0 + (uint32_t)(2 * p) * TC_NT * 16, TC_NT * 16, 128), idesc, p >= 2 ? 1u : 0u);
-                umma_commit(&S.mbar);
-            }
-            mbar_wait(&S.mbar, phase);
-            phase ^= 1;
-            tc_fence_after();
-            // ---- epilogue: certificate, clamp, transposed tile in shared memory --------------------------------------------
-            for (int c8 = 0; c8 < nh; c8 += 8) {
-                const int n0 = wg * nh + c8;
-                uint32_t a[8], b[8];
-                tmem_ld8(tmem + lane_base + D_COL0 + n0, a);
-                tmem_ld8(tmem + lane_base + D_COL0 + TC_NT + n0, b);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                uint32_t o[2] = {0, 0};
+                    for (int u = 0; u < 8; u++) {
+                        const int2 k = I.kq[n0 + u];
+                        const int s0 = (int)a[u], s1 = (int)c[u];
+                        int e = min(max(s0 + s1, -128), 127);
+                        if ((s0 > k.x || s1 > k.y) && n0 + u < nq) {   // certificate failed: the fold has to be done step by step
+                            const int qi = atomicAdd(&S.n_queue, 1);
+                            if (qi < TC_QUEUE) S.queue[qi] = ((uint32_t)(t - t0) << 16) | ((uint32_t)row << 8) | (uint32_t)(n0 + u);
+                            else e = tc_refold<PH>(nat32, tile0 + t, row, B + (size_t)(n0 + u) * 16);   // queue full: on the spot
+                        }
+                        o[u >> 2] |= (uint32_t)(e & 0xff) << (8 * (u & 3));
+                    }
+                    S.outT[row * TC_OUT_STRIDE + (n0 >> 2)] = o[0];
+                    S.outT[row * TC_OUT_STRIDE + (n0 >> 2) + 1] = o[1];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.d_empty[b]);
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
+                // the tile: 16 estimates (one chunk) of one query per task, coalesced 16-byte stores
+                for (int task = ptid; task < nq * 8; task += 32 * TC_P_WARPS) {
+                    const int n = task >> 3, sc = task & 7;
+                    const int chunk = t * 8 + sc;
+                    if (chunk >= n_real) continue;
+                    uint32_t o[4];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int2 k = S.kq[n0 + u];
-                    const int s0 = (int)a[u], s1 = (int)b[u];
-                    const int e = min(max(s0 + s1, -128), 127);
-                    o[u >> 2] |= (uint32_t)(e & 0xff) << (8 * (u & 3));
-                    if ((s0 > k.x || s1 > k.y) && n0 + u < nq) {
-                        const int i = atomicAdd(&S.n_patch, 1);
-                        if (i < TC_PATCH_CAP) S.patch[i] = ((uint32_t)row << 16) | (uint32_t)(n0 + u);   // overflow: the whole tile is refolded
+                    for (int w = 0; w < 4; w++) {
+                        uint32_t x = 0;
+#pragma unroll
+                        for (int bb = 0; bb < 4; bb++) {
+                            const uint32_t word = S.outT[(16 * sc + 4 * w + bb) * TC_OUT_STRIDE + (n >> 2)];
+                            x |= ((word >> (8 * (n & 3))) & 0xffu) << (8 * bb);
+                        }
+                        o[w] = x;
+                    }
+                    const long long off = I.dst[n] + 16LL * chunk;
+                    *reinterpret_cast<uint4 *>(est + off) = make_uint4(o[0], o[1], o[2], o[3]);
+                    if (cmin) {
+                        uint32_t m = __vmins4(__vmins4(o[0], o[1]), __vmins4(o[2], o[3]));
+                        m = __vmins4(m, m >> 16);
+                        m = __vmins4(m, m >> 8);
+                        cmin[off >> 4] = (uint8_t)(m & 0xffu);
                     }
                 }
-                S.outT[row * TC_OUT_STRIDE + (n0 >> 2)] = o[0];
-                S.outT[row * TC_OUT_STRIDE + (n0 >> 2) + 1] = o[1];
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
             }
-            tc_fence_before();
-            __syncthreads();
-            // ---- refold the pairs whose certificate failed: the reference's recurrence, from the slab ----------------------
+            // the item's refold queue: the reference's recurrence for the pairs whose certificate failed, bytes patched in place
+            // (the refolded value is never above the provisional one, so a chunk minimum can only go down)
             {
-                const int np = S.n_patch;
-                const bool all = np > TC_PATCH_CAP;                  // queue overflow: every (row, query) of the tile
-                const int total = all ? 128 * nq : np;
-                for (int i = tid; i < total; i += TC_THREADS) {
-                    const int r = all ? i % 128 : (int)(S.patch[i] >> 16), n = all ? i / 128 : (int)(S.patch[i] & 0xffffu);
-                    const int s = r >> 4, v = r & 15, gq = v >> 2, sh = 16 * (gq & 1) + 4 * (v & 3);
-                    const uint32_t *tb = nat32 + (((size_t)(c0 >> 3) + t) * PH * 8 + s) * 4 + (gq >> 1);
-                    const uint8_t *Bq = B + (size_t)n * 16;
-                    int a0 = 0, a1 = 0;
-                    for (int p = 0; p < PH; p++) {
-                        const uint32_t ca = (__ldg(tb + (size_t)p * 32) >> sh) & 15u, cb = (__ldg(tb + (size_t)p * 32 + 2) >> sh) & 15u;
-                        const int ta = (int)(int8_t)Bq[(size_t)(2 * p) * TC_NT * 16 + ca];
-                        const int tb2 = (int)(int8_t)Bq[(size_t)(2 * p + 1) * TC_NT * 16 + cb];
-                        if (p & 1) a1 = sat_add8<true>(sat_add8<true>(a1, ta), tb2);
-                        else       a0 = sat_add8<true>(sat_add8<true>(a0, ta), tb2);
-                    }
-                    reinterpret_cast<uint8_t *>(S.outT)[(r * TC_OUT_STRIDE + (n >> 2)) * 4 + (n & 3)] = (uint8_t)sat_add8<true>(a0, a1);
+                const int nqd = min(S.n_queue, TC_QUEUE);
+                for (int i = ptid; i < nqd; i += 32 * TC_P_WARPS) {
+                    const uint32_t en = S.queue[i];
+                    const int tt = t0 + (int)(en >> 16), r = (int)((en >> 8) & 0xffu), n = (int)(en & 0xffu);
+                    if (tt * 8 + (r >> 4) >= n_real) continue;       // a padding vector of the last tile: never written
+                    const int e = tc_refold<PH>(nat32, tile0 + tt, r, B + (size_t)n * 16);
+                    const long long off = I.dst[n] + 128LL * tt + r;
+                    est[off] = (uint8_t)e;
+                    if (cmin) atomic_min_s8(cmin + (off >> 4), e);
                 }
-                if (tid == 0 && np) { atomicAdd(W.hdr + 2, np); S.n_patch = 0; }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
+                if (ptid == 0) { if (S.n_queue) atomicAdd(W.hdr + 2, S.n_queue); S.n_queue = 0; }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
             }
-            __syncthreads();
-            // ---- write the tile: 16 estimates (one chunk) of one query per task, coalesced 16-byte stores -------------------
-            for (int task = tid; task < nq * 8; task += TC_THREADS) {
-                const int n = task >> 3, sc = task & 7;
-                const int chunk = t * 8 + sc;
-                if (chunk >= n_real) continue;
-                uint32_t o[4];
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    uint32_t x = 0;
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const uint32_t word = S.outT[(16 * sc + 4 * w + b) * TC_OUT_STRIDE + (n >> 2)];
-                        x |= ((word >> (8 * (n & 3))) & 0xffu) << (8 * b);
-                    }
-                    o[w] = x;
-                }
-                const long long off = S.dst[n] + 16LL * chunk;
-                *reinterpret_cast<uint4 *>(est + off) = make_uint4(o[0], o[1], o[2], o[3]);
-                if (cmin) {
-                    uint32_t m = __vmins4(__vmins4(o[0], o[1]), __vmins4(o[2], o[3]));
-                    m = __vmins4(m, m >> 16);
-                    m = __vmins4(m, m >> 8);
-                    cmin[off >> 4] = (uint8_t)(m & 0xffu);
-                }
-            }
-            __syncthreads();
+            if (lane == 0) mbar_arrive(&S.item_empty[par]);
         }
     }
     tc_fence_before();
@@ -474,10 +617,10 @@ int launch_ivf_scan_tc(const void *native, const int64_t *list_chunk_off, const 
         TKB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
     // one CTA per SM (the kernel owns all 512 TMEM columns): the slab + the rest of the shared memory is padded past half an SM's
-    const size_t smem = ((sizeof(TcSmem) + 127) / 128) * 128 + (size_t)M * TC_NT * 16 + 128;
+    const size_t smem = ((sizeof(TcShared) + 127) / 128) * 128 + 2 * (size_t)M * TC_NT * 16 + 128;
     const size_t smem_req = smem > 120 * 1024 ? smem : 120 * 1024;
     TKB_CUDA(cudaFuncSetAttribute(ivf_scan_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
-    ivf_scan_tc_kernel<16><<<n_sm, TC_THREADS, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native), list_chunk_off, list_size,
+    ivf_scan_tc_kernel<16><<<n_sm, TC_THREADS2, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native), list_chunk_off, list_size,
                                                                 n_lists, tables, P, est, seg_off, cmin, W);
     TKB_LAUNCH_CHECK();
     // the (query, list) pairs the tensor-core path does not take (queries whose LUT fails the per-query precondition):

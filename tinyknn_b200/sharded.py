@@ -38,9 +38,10 @@ from ._lib import PLAN_SEND, PLAN_RECV, PLAN_PUSH, PROBE_SKIP
 
 # default exchange of ShardedIVF.query_batch: "push" (NVLink peer stores from the scan kernel) or "nccl" (all-to-all)
 EXCHANGE = os.environ.get("TKB_EXCHANGE", "push")
-# chunk minima inside the push exchange (the home buffer carries a minima region). Opt-in: written after round 1's GPU
-# budget was spent, not yet run on hardware (tests/test_gpu_build_and_batch.py).
-PUSH_CMIN = os.environ.get("TKB_PUSH_CMIN", "0") != "0"
+# chunk minima inside the push exchange (the home buffer carries a minima region): the home rank's replay of long probe
+# lists reads 1 byte per chunk instead of 16 (100M x 128, 2 GPUs: replay 9.9 -> ~4.5 ms per step). Validated on hardware in
+# round 2 (tests/test_gpu_build_and_batch.py, tests/test_sharded_gpu.py).
+PUSH_CMIN = os.environ.get("TKB_PUSH_CMIN", "1") != "0"
 
 
 def assign_owners(list_sizes, n_ranks):
