@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--parity-queries", type=int, default=2000,
                     help="queries of the first batch checked against the oracle before anything is timed (LUT bytes, probe "
                          "lists, heap arrays, id sets; reference selection order and the device order)")
+    ap.add_argument("--recall-queries", type=int, default=500,
+                    help="recall@k of the timed mode against exact brute force, on this many queries of the first batch (0: skip)")
     ap.add_argument("--cpu-queries", type=int, default=2048,
                     help="workloads whose raw vectors stay on the GPU (10M/100M): the CPU arm cycles through this many queries of "
                          "the batch; the rows their rescoring reads are recorded in an untimed pass of the oracle and kept on the host")
@@ -354,6 +356,29 @@ def parity_gate(ivf, queries, args, kw):
                      "(np.argpartition visiting order) -- the parity delta of the throughput mode")
 
 
+def recall_at_k(ivf, queries, ids, cnt, k, torch):
+    """recall@k of the returned ids against exact nearest neighbours (brute force over the raw vectors on the GPU, torch
+    matmuls: ground truth only, like the reference's benchmark computes it with knn_brute, ref: examples/bench.py:76-86)."""
+    dev = ivf.to_device()
+    X = dev["data"]
+    q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(X.device)
+    if ivf.metric == "angular":
+        q = q / q.norm(dim=1, keepdim=True)
+    best_d = torch.full((len(q), k), float("inf"), device=X.device)
+    best_i = torch.full((len(q), k), -1, dtype=torch.int64, device=X.device)
+    step = 1 << 20
+    for lo in range(0, X.shape[0], step):
+        x = X[lo:lo + step].float()
+        d2 = (x * x).sum(1)[None, :] - 2.0 * (q @ x.T)               # |x|^2 - 2 q.x  (+ |q|^2, constant per query)
+        dd, ii = torch.topk(d2, min(k, d2.shape[1]), dim=1, largest=False)
+        cat_d, cat_i = torch.cat([best_d, dd], 1), torch.cat([best_i, ii + lo], 1)
+        sel = torch.topk(cat_d, k, dim=1, largest=False).indices
+        best_d, best_i = torch.gather(cat_d, 1, sel), torch.gather(cat_i, 1, sel)
+    truth = best_i.cpu().numpy()
+    hit = sum(len(set(ids[i][:cnt[i]].tolist()) & set(truth[i].tolist())) for i in range(len(q)))
+    return hit / float(len(q) * k)
+
+
 def main():
     args = parse()
     if os.environ.get("TKB_BENCH_WATCHDOG"):            # seconds: dump every thread's Python stack periodically (where is a rank stuck?)
@@ -462,11 +487,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    parity = None
+    parity, recall = None, None
     if rank == 0:
         log("parity gate")
         parity = parity_gate(ivf, batches[0], args, kw)
         log("parity gate: %s" % {k_: v for k_, v in parity.items() if k_.endswith("mismatch")})
+        if args.recall_queries > 0:
+            nr = min(args.recall_queries, Qn)
+            r_ids, r_cnt = ivf.query_batch(batches[0][:nr], order="device", **kw)
+            recall = dict(k=args.k, queries=nr, value=recall_at_k(ivf, batches[0][:nr], r_ids, r_cnt, args.k, torch),
+                          truth="exact brute force over the raw vectors (torch, GPU)")
+            log("recall@%d = %.4f" % (args.k, recall["value"]))
     if sharded:
         # the sharded path must return exactly what the unsharded path returns for the same queries
         a = run(dev_batches[0][:256].contiguous(), return_distances=True)
@@ -618,8 +649,13 @@ def main():
             roof = dict(bound="hbm", scanned_vectors_per_launch=scanned, launches_per_step=blocks_per_step,
                         **scan_roof(per_step(stages["scan"]), counter("patch_ws")))
         if "tc_ws" in last:
-            hdr = last["tc_ws"][:16].cpu().numpy().view(np.int32)
-            roof.update(kernel="ivf_scan_tc", tc_work_items=int(hdr[0]), tc_refolded_pairs=int(hdr[2]),
+            hdr = last["tc_ws"][:32].cpu().numpy().view(np.int32)
+            roof.update(kernel="ivf_scan_tc", tc_work_items=int(hdr[0]), tc_refolded_pairs=int(hdr[2]), tc_tiles=int(hdr[3]),
+                        tc_mean_group_columns=16.0 * int(hdr[4]) / max(1, int(hdr[3])),
+                        tc_role_cycles_per_tile={k_: round(float(v_) / max(1, int(hdr[3])) , 1) for k_, v_ in zip(
+                            ("expand_wait", "expand_work", "mma_wait_a", "mma_wait_d", "mma_issue", "epi_wait", "epi_work", "epi_barrier",
+                             "epi_copy", "epi_flush", "load_wait", "load_stage", "total"),
+                            last["tc_ws"][32:32 + 8 * 13].cpu().numpy().view(np.int64))},
                         note="list-major tensor-core scan (tcgen05.mma kind::i8): the code bytes are read once per list and batch, "
                              "so `achieved` (algorithmic bytes / time) is not bounded by the HBM peak; see `traffic`")
         code_bytes = dev["n_chunks_total"] * M * 8 if not sharded else extra.get("code_bytes_per_rank", 0)
@@ -650,7 +686,7 @@ def main():
                     vs_baseline=None, dtype="i8", data="synthetic", config=cfg, parallelism=parallelism, l2=l2, index=index_note,
                     clocks=clocks, e2e=dict(value=e2e_v, unit="queries/s", h2d_bytes_per_step=int(Qn * w["d"] * 4),
                                             d2h_bytes_per_step=int(Qn * args.k * 8 + Qn * 4)),
-                    gpu_launches=int(launches), roofline=roof, cpu_baseline=cb, parity=parity,
+                    gpu_launches=int(launches), roofline=roof, cpu_baseline=cb, parity=parity, recall=recall,
                     # host-side issue time of one step on rank 0: close to ms_per_step = the loop is bound by Python/launch cost,
                     # far below = the GPU is the bottleneck
                     host_issue_ms_per_step=t_issue * 1e3 / args.steps, **extra)

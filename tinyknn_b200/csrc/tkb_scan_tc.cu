@@ -37,17 +37,28 @@ namespace tkb {
 
 constexpr int TC_THREADS = 256;
 constexpr int TC_NT = 64;                       // queries per group (UMMA N <= 64: 2 x 2 x 64 accumulator columns + 256 of A)
-constexpr int TC_TILES_PER_ITEM = 64;           // tiles (of 128 vectors) per work item: long lists are split
-constexpr int TC_OUT_STRIDE = TC_NT / 4 + 1;    // words per row of the transposed output tile (padded: conflict-free)
+constexpr int TC_TILES_PER_ITEM = 128;          // tiles (of 128 vectors) per work item: long lists are split
+constexpr int TC_OUT_STRIDE = TC_NT / 4 + 1;    // words per row of the transposed output tile (see tc_out_addr)
 constexpr int TC_PATCH_CAP = 1024;
 
 struct TcQueryMeta { int16_t elig, k0, k1, pad; };
 
+// Word (row = vector of the tile, c = four queries) of the transposed output tile. Row stride 17 keeps the epilogue's stores (32
+// consecutive rows, one column) on 32 banks; rotating the column by 4 per 32 rows does the same for the loads of the copy-out
+// (rows 16 apart, four consecutive columns).
+__host__ __device__ constexpr int tc_out_addr(int row, int c) { return row * TC_OUT_STRIDE + ((c + 4 * (row >> 5)) & 15); }
+// cycle counters of one representative warp per role (lane 0), summed over all CTAs
+enum TcClock { CK_E_WAIT = 0, CK_E_WORK, CK_M_WAIT_A, CK_M_WAIT_D, CK_M_ISSUE, CK_P_WAIT, CK_P_EPI, CK_P_BAR, CK_P_COPY, CK_P_FLUSH,
+               CK_L_WAIT, CK_L_STAGE, CK_TOTAL, CK_COUNT };
+
 // ---- work list -------------------------------------------------------------------------------------------------------
-// ws (int32 words): [0] total items, [1] next item (persistent kernel's counter), [2] refolded pairs (statistic), [3] pad;
+// ws (int32 words): [0] total items, [1] next item (persistent kernel's counter), [2] refolded pairs, [3] tiles multiplied,
+// [4] sum over those tiles of the group's N / 16 (statistics), [5..7] pad; then 16 int64 cycle counters (where the roles of
+// the kernel spend their time, summed over the CTAs: see TcClock)
 // then cnt[n_lists], cursor[n_lists], bucket_off[n_lists + 1], item_off[n_lists + 1], bucket[Q * P].
 struct TcWork {
     int *hdr, *cnt, *cursor, *bucket_off, *item_off, *bucket;
+    unsigned long long *clk;
     TcQueryMeta *qmeta;
     int64_t *seg_rest;
     uint8_t *skip_q;
@@ -57,13 +68,14 @@ __host__ __device__ inline size_t tc_carve(void *base, int Q, int P, int n_lists
 {
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 15) / 16 * 16; return at; };
-    const size_t hdr = take(16), cnt = take(4 * (size_t)n_lists), cur = take(4 * (size_t)n_lists);
+    const size_t hdr = take(32 + 8 * 16), cnt = take(4 * (size_t)n_lists), cur = take(4 * (size_t)n_lists);
     const size_t bo = take(4 * ((size_t)n_lists + 1)), io = take(4 * ((size_t)n_lists + 1));
     const size_t bk = take(4 * (size_t)Q * P), qm = take(sizeof(TcQueryMeta) * (size_t)Q), sr = take(8 * (size_t)Q * P);
     const size_t sk = take((size_t)Q);
     if (w) {
         unsigned char *b = reinterpret_cast<unsigned char *>(base);
         w->hdr = reinterpret_cast<int *>(b + hdr); w->cnt = reinterpret_cast<int *>(b + cnt);
+        w->clk = reinterpret_cast<unsigned long long *>(b + hdr + 32);
         w->cursor = reinterpret_cast<int *>(b + cur); w->bucket_off = reinterpret_cast<int *>(b + bo);
         w->item_off = reinterpret_cast<int *>(b + io); w->bucket = reinterpret_cast<int *>(b + bk);
         w->qmeta = reinterpret_cast<TcQueryMeta *>(b + qm); w->seg_rest = reinterpret_cast<int64_t *>(b + sr);
@@ -169,13 +181,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     const uint32_t addr = smem_u32(bar);
     uint32_t done;
-    do {
+    do {                                        // try_wait suspends the thread (up to the time hint) instead of spinning
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity), "r"(1000000u) : "memory");
     } while (!done);
 }
 
@@ -201,13 +213,13 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
-                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
 }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
 }
 
 // K-major, no swizzle: start address, leading-byte-offset (between the two 16-byte K chunks of one MMA), stride-byte-offset
@@ -240,24 +252,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 
 // ---- roles of the persistent kernel -------------------------------------------------------------------------------------
-//   warps 0..7   expansion : thread = one vector (TMEM lane) of the tile, warps 0-3 the first half of the sub-quantizer pairs,
-//                            warps 4-7 the second half; one-hot units straight into tensor memory (tcgen05.st)
-//   warps 8..15  epilogue  : thread = one vector, warps 8-11 the first half of the group's queries, 12-15 the second half;
-//                            tcgen05.ld, certificate, clamp, transposed tile in shared memory, coalesced 16-byte stores
+//   warps 0..7   expansion : thread = one vector (TMEM lane) of a tile, all its sub-quantizers; warps 0-3 take the even tiles
+//                            (buffer 0), warps 4-7 the odd ones (buffer 1); one-hot units straight into tensor memory
+//   warps 8..15  epilogue  : thread = one vector, all the queries of the group; warps 8-11 the even tiles, 12-15 the odd ones:
+//                            tcgen05.ld, certificate, clamp (s16x2 SIMD), transposed tile in shared memory, 16-byte stores
 //   warp 16      multiplies: one thread issues the tile's PH tcgen05.mma and commits them to the mbarriers
 //   warp 17      loads     : fetches the next work item, stages its LUT slab (double-buffered)
 // A and D are double-buffered in tensor memory, so the expansion of tile t+1, the MMAs of tile t and the epilogue of tile t-1
-// run at the same time; nothing but mbarriers (and one named barrier inside the epilogue group) synchronises the roles.
+// run at the same time; the two halves of a role work on alternate tiles and never wait for each other. Nothing but mbarriers
+// (and a 128-thread named barrier inside each epilogue half) synchronises the roles.
 constexpr int TC_E_WARPS = 8, TC_P_WARPS = 8;
 constexpr int TC_WARPS = TC_E_WARPS + TC_P_WARPS + 2;
 constexpr int TC_THREADS2 = 32 * TC_WARPS;
-constexpr int TC_QUEUE = 2048;                  // refold queue of one work item
+constexpr int TC_QUEUE = 4096;                  // refold queue of one work item
 
 struct TcItem {
     int valid, list, nq, N, t0, t1, n_real, pad;
     long long tile0;                            // first tile of the list in the code array
     int q_of[TC_NT];                            // query of group member i (-1: padding column)
-    int2 kq[TC_NT];                             // certificate thresholds of its two lanes
+    uint2 kq2[TC_NT / 2];                       // certificate thresholds of query pairs: .x = (k0[2i], k0[2i+1]), .y = (k1[..]) as s16x2
     long long dst[TC_NT];                       // est offset of its segment
 };
 
@@ -266,13 +279,13 @@ struct TcShared {
     uint32_t tmem_base;
     int n_queue;
     TcItem item[2];
-    uint32_t outT[128 * TC_OUT_STRIDE];         // estimates of the tile: row = vector, byte n = query n of the group
+    uint32_t outT[2][2][128 * TC_OUT_STRIDE];   // [epilogue half][tile parity]: row = vector, byte n = query n of the group
     uint32_t queue[TC_QUEUE];                   // (tile << 16) | (row << 8) | query column of the pairs whose certificate failed
 };
 
 // the reference's fold of one (vector, query): codes from the code array, LUT rows from the slab
 template <int PH>
-__device__ __forceinline__ int tc_refold(const uint32_t *__restrict__ nat32, long long tile, int r, const uint8_t *Bq)
+__device__ __noinline__ int tc_refold(const uint32_t *__restrict__ nat32, long long tile, int r, const uint8_t *Bq)
 {
     const int s = r >> 4, v = r & 15, gq = v >> 2, sh = 16 * (gq & 1) + 4 * (v & 3);
     const uint32_t *tb = nat32 + ((size_t)tile * PH * 8 + s) * 4 + (gq >> 1);
@@ -303,6 +316,50 @@ __device__ __forceinline__ void atomic_min_s8(uint8_t *addr, int v)
     }
 }
 
+// Slow path of the epilogue (kept out of line: the four roles of the kernel run different code at the same time and share one
+// instruction cache): among these 8 queries of the warp's 32 vectors some certificate failed. Every lane builds the bit mask of its
+// failing queries, one warp scan and ONE shared-memory atomic reserve the queue slots, the lanes write their (tile, vector, query)
+// records; when the queue is full the pairs are refolded on the spot and the corrected byte replaces the provisional one in
+// (o0, o1). Called by whole warps.
+template <int PH>
+__device__ __noinline__ void tc_flagged8(TcShared &S, const uint2 *kq2, uint4 pa, uint4 pc, int n0, int nq, int t_rel, int row,
+                                         uint32_t &o0, uint32_t &o1, const uint32_t *__restrict__ nat32, long long tile,
+                                         const uint8_t *B)
+{
+    const uint32_t pas[4] = {pa.x, pa.y, pa.z, pa.w}, pcs[4] = {pc.x, pc.y, pc.z, pc.w};
+    const int lane = threadIdx.x & 31;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const uint2 k = kq2[(n0 >> 1) + u];
+        const uint32_t d = __vmaxs2(__vsub2(pas[u], k.x), __vsub2(pcs[u], k.y));        // > 0 in a half: that query's certificate failed
+        if ((int)(int16_t)(d & 0xffffu) > 0) mask |= 1u << (2 * u);
+        if ((int)(int16_t)(d >> 16) > 0) mask |= 2u << (2 * u);
+    }
+    const int valid = nq - n0;                                                          // padding columns of the group never count
+    if (valid < 8) mask &= (1u << (valid < 0 ? 0 : valid)) - 1u;
+    const int cnt = __popc(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(&S.n_queue, total);
+    base = __shfl_sync(FULL, base, 31) + incl - cnt;
+    while (mask) {
+        const int u = __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (base < TC_QUEUE) S.queue[base] = ((uint32_t)t_rel << 16) | ((uint32_t)row << 8) | (uint32_t)(n0 + u);
+        else {
+            const int e = tc_refold<PH>(nat32, tile, row, B + (size_t)(n0 + u) * 16);
+            uint32_t &o = u < 4 ? o0 : o1;
+            o = (o & ~(0xffu << (8 * (u & 3)))) | ((uint32_t)(e & 0xff) << (8 * (u & 3)));
+        }
+        base++;
+    }
+}
+
 template <int PH>
 __global__ void __launch_bounds__(TC_THREADS2, 1)
 ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict__ list_chunk_off,
@@ -327,10 +384,10 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
         for (int b = 0; b < 2; b++) {
             mbar_init(&S.item_full[b], 32);
             mbar_init(&S.item_empty[b], TC_E_WARPS + TC_P_WARPS + 1);
-            mbar_init(&S.a_full[b], TC_E_WARPS);
+            mbar_init(&S.a_full[b], TC_E_WARPS / 2);
             mbar_init(&S.a_empty[b], 1);
             mbar_init(&S.d_full[b], 1);
-            mbar_init(&S.d_empty[b], TC_P_WARPS);
+            mbar_init(&S.d_empty[b], TC_P_WARPS / 2);
         }
         S.n_queue = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -342,9 +399,13 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
 
     if (warp == TC_WARPS - 1) {
         // ================================ loader =====================================================================
+        long long lk[2] = {0, 0};
         for (uint32_t it = 0;; it++) {
             const int par = it & 1;
+            const long long c0_ = clock64();
             mbar_wait(&S.item_empty[par], ((it >> 1) & 1) ^ 1);
+            const long long c1_ = clock64();
+            lk[0] += c1_ - c0_;
             TcItem &I = S.item[par];
             int item = 0;
             if (lane == 0) item = atomicAdd(W.hdr + 1, 1);
@@ -371,15 +432,17 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             for (int i = lane; i < TC_NT; i += 32) {
                 int q = -1;
                 long long d = 0;
-                int2 k = make_int2(0, 0);
+                int k0 = 0, k1 = 0;
                 if (i < nq) {
                     const int e = W.bucket[W.bucket_off[l] + g * TC_NT + i];
                     q = e / P;
                     d = seg_off[e];
                     const TcQueryMeta m = W.qmeta[q];
-                    k = make_int2(m.k0, m.k1);
+                    k0 = m.k0; k1 = m.k1;
                 }
-                I.q_of[i] = q; I.dst[i] = d; I.kq[i] = k;
+                I.q_of[i] = q; I.dst[i] = d;
+                reinterpret_cast<uint16_t *>(I.kq2)[4 * (i >> 1) + (i & 1)] = (uint16_t)(int16_t)k0;
+                reinterpret_cast<uint16_t *>(I.kq2)[4 * (i >> 1) + 2 + (i & 1)] = (uint16_t)(int16_t)k1;
             }
             __syncwarp();
             uint8_t *B = Bslab + (size_t)par * SLAB;
@@ -402,10 +465,14 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
             mbar_arrive(&S.item_full[par]);
+            lk[1] += clock64() - c1_;
         }
+        if (lane == 0) { atomicAdd(W.clk + CK_L_WAIT, (unsigned long long)lk[0]); atomicAdd(W.clk + CK_L_STAGE, (unsigned long long)lk[1]); }
     } else if (warp == TC_WARPS - 2) {
         // ================================ MMA issuer =================================================================
         uint32_t g = 0;                                              // tiles issued so far (buffer = g & 1)
+        long long mk[3] = {0, 0, 0};
+        const long long k0_ = clock64();
         for (uint32_t it = 0;; it++) {
             const int par = it & 1;
             mbar_wait(&S.item_full[par], (it >> 1) & 1);
@@ -416,138 +483,183 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                 const uint32_t b0 = smem_u32(Bslab + (size_t)par * SLAB);
                 for (int t = I.t0; t < I.t1; t++, g++) {
                     const uint32_t b = g & 1, ph = (g >> 1) & 1;
+                    const long long c0_ = clock64();
                     mbar_wait(&S.a_full[b], ph);
+                    const long long c1_ = clock64();
                     mbar_wait(&S.d_empty[b], ph ^ 1);
                     tc_fence_after();
+                    const long long c2_ = clock64();
 #pragma unroll
                     for (int p = 0; p < PH; p++)
                         umma_i8_ts(tmem + D_COL0 + (2 * b + (p & 1)) * TC_NT, tmem + b * A_COLS + 8 * p,
                                    umma_desc_kmajor(b0 + (uint32_t)(2 * p) * TC_NT * 16, TC_NT * 16, 128), idesc, p >= 2 ? 1u : 0u);
                     umma_commit(&S.a_empty[b]);
                     umma_commit(&S.d_full[b]);
+                    mk[0] += c1_ - c0_; mk[1] += c2_ - c1_; mk[2] += clock64() - c2_;
                 }
             }
             g = __shfl_sync(FULL, g, 0);
-            if (lane == 0) mbar_arrive(&S.item_empty[par]);
+            if (lane == 0) {
+                atomicAdd(W.hdr + 3, I.t1 - I.t0);
+                atomicAdd(W.hdr + 4, (I.t1 - I.t0) * (I.N >> 4));
+                mbar_arrive(&S.item_empty[par]);
+            }
+        }
+        if (lane == 0) {
+            atomicAdd(W.clk + CK_M_WAIT_A, (unsigned long long)mk[0]); atomicAdd(W.clk + CK_M_WAIT_D, (unsigned long long)mk[1]);
+            atomicAdd(W.clk + CK_M_ISSUE, (unsigned long long)mk[2]); atomicAdd(W.clk + CK_TOTAL, (unsigned long long)(clock64() - k0_));
         }
     } else if (warp < TC_E_WARPS) {
         // ================================ expansion ==================================================================
-        const int row = 32 * (warp & 3) + lane, eg = warp >> 2;
+        const int row = 32 * (warp & 3) + lane, eb = warp >> 2;      // eb: the buffer (tile parity) this half works on
         const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
         const int s = row >> 4, v = row & 15, gq = v >> 2, sh = 16 * (gq & 1) + 4 * (v & 3);
         uint32_t g = 0;
+        long long ck[2] = {0, 0};
         for (uint32_t it = 0;; it++) {
             const int par = it & 1;
             mbar_wait(&S.item_full[par], (it >> 1) & 1);
             const TcItem &I = S.item[par];
             if (!I.valid) break;
             const int t0 = I.t0, t1 = I.t1;
-            const uint32_t *tb = nat32 + ((size_t)(I.tile0 + t0) * PH * 8 + s) * 4 + (gq >> 1) + (size_t)eg * (PH / 2) * 32;
-            uint32_t cur[PH];                                         // this thread's code words of the tile: PH/2 pairs x 2
-#pragma unroll
-            for (int pi = 0; pi < PH / 2; pi++) { cur[2 * pi] = __ldg(tb + pi * 32); cur[2 * pi + 1] = __ldg(tb + pi * 32 + 2); }
-            for (int t = t0; t < t1; t++, g++) {
-                const uint32_t b = g & 1, ph = (g >> 1) & 1;
-                uint32_t nxt[PH];
-                if (t + 1 < t1) {                                     // the next tile's words are in flight while this one is expanded
-                    const uint32_t *tn = tb + (size_t)(t + 1 - t0) * PH * 32;
-#pragma unroll
-                    for (int pi = 0; pi < PH / 2; pi++) { nxt[2 * pi] = __ldg(tn + pi * 32); nxt[2 * pi + 1] = __ldg(tn + pi * 32 + 2); }
-                }
-                mbar_wait(&S.a_empty[b], ph ^ 1);
+            const int first = t0 + (int)((eb - g) & 1);              // this half's first tile of the item: (g + first - t0) & 1 == eb
+            const uint32_t *tb = nat32 + ((size_t)I.tile0 * PH * 8 + s) * 4 + (gq >> 1);
+            // the code words of a tile are fetched where they are used; the tile this half expands next is prefetched into L1 a tile
+            // ahead (one 128-byte line per sub-quantizer pair and half-warp), so those loads hit. The loop is kept small: the four
+            // roles of the kernel share one instruction cache.
+            if (first < t1 && (lane & 15) == 0)
+                for (int p = 0; p < PH; p++)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(tb + ((size_t)first * PH + p) * 32));
+            for (int t = first; t < t1; t += 2) {
+                const uint32_t gg = g + (uint32_t)(t - t0), ph = (gg >> 1) & 1;
+                if (t + 2 < t1 && (lane & 15) == 0)
+                    for (int p = 0; p < PH; p++)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(tb + ((size_t)(t + 2) * PH + p) * 32));
+                const long long c0_ = clock64();
+                mbar_wait(&S.a_empty[eb], ph ^ 1);
                 tc_fence_after();
-#pragma unroll
-                for (int pi = 0; pi < PH / 2; pi++) {
+                const long long c1_ = clock64();
+                const uint32_t *tt = tb + (size_t)t * PH * 32;
+#pragma unroll 4
+                for (int p = 0; p < PH; p++) {
+                    const uint32_t ca = (__ldg(tt + p * 32) >> sh) & 15u, cb = (__ldg(tt + p * 32 + 2) >> sh) & 15u;
                     uint32_t r[8];
-                    onehot_unit((cur[2 * pi] >> sh) & 15u, r[0], r[1], r[2], r[3]);
-                    onehot_unit((cur[2 * pi + 1] >> sh) & 15u, r[4], r[5], r[6], r[7]);
-                    tmem_st8(tmem + lane_base + b * A_COLS + 8 * (eg * (PH / 2) + pi), r);
+                    onehot_unit(ca, r[0], r[1], r[2], r[3]);
+                    onehot_unit(cb, r[4], r[5], r[6], r[7]);
+                    tmem_st8(tmem + lane_base + eb * A_COLS + 8 * p, r);
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&S.a_full[b]);
-                if (t + 1 < t1) {
-#pragma unroll
-                    for (int i = 0; i < PH; i++) cur[i] = nxt[i];
-                }
+                if (lane == 0) mbar_arrive(&S.a_full[eb]);
+                ck[0] += c1_ - c0_; ck[1] += clock64() - c1_;
             }
+            g += (uint32_t)(t1 - t0);
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.item_empty[par]);
         }
+        if (warp == 0 && lane == 0) { atomicAdd(W.clk + CK_E_WAIT, (unsigned long long)ck[0]); atomicAdd(W.clk + CK_E_WORK, (unsigned long long)ck[1]); }
     } else {
         // ================================ epilogue ===================================================================
-        const int pw = warp - TC_E_WARPS, pg = pw >> 2, ptid = tid - 32 * TC_E_WARPS;
+        const int pb = (warp - TC_E_WARPS) >> 2;                     // the buffer (tile parity) this half works on
+        const int htid = tid - 32 * (TC_E_WARPS + 4 * pb);           // 0..127 inside the half
+        const int ptid = tid - 32 * TC_E_WARPS;                      // 0..255 inside the role
         const int row = 32 * (warp & 3) + lane;
         const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-        uint32_t g = 0;
+        uint32_t g = 0, k_tile = 0;                                  // k_tile: tiles this half has written (outT parity)
+        long long pk[5] = {0, 0, 0, 0, 0};
         for (uint32_t it = 0;; it++) {
             const int par = it & 1;
             mbar_wait(&S.item_full[par], (it >> 1) & 1);
             const TcItem &I = S.item[par];
             if (!I.valid) break;
-            const int t0 = I.t0, t1 = I.t1, N = I.N, nq = I.nq, n_real = I.n_real, nh = N >> 1;
+            const int t0 = I.t0, t1 = I.t1, N = I.N, nq = I.nq, n_real = I.n_real;
             const long long tile0 = I.tile0;
             const uint8_t *B = Bslab + (size_t)par * SLAB;
-            for (int t = t0; t < t1; t++, g++) {
-                const uint32_t b = g & 1, ph = (g >> 1) & 1;
-                mbar_wait(&S.d_full[b], ph);
+            const int first = t0 + (int)((pb - g) & 1);
+            for (int t = first; t < t1; t += 2, k_tile++) {
+                const uint32_t gg = g + (uint32_t)(t - t0), ph = (gg >> 1) & 1;
+                uint32_t *outT = S.outT[pb][k_tile & 1];
+                const long long c0_ = clock64();
+                mbar_wait(&S.d_full[pb], ph);
                 tc_fence_after();
-                for (int c8 = 0; c8 < nh; c8 += 8) {
-                    const int n0 = pg * nh + c8;
+                const long long c1_ = clock64();
+                // 8 query columns per step; the loads of the next step are issued before this step's arithmetic, and the accumulators go
+                // back to the MMA issuer as soon as the last load has landed (not after the whole epilogue). Small loop body on purpose.
+                {
                     uint32_t a[8], c[8];
-                    tmem_ld8(tmem + lane_base + D_COL0 + (2 * b) * TC_NT + n0, a);
-                    tmem_ld8(tmem + lane_base + D_COL0 + (2 * b + 1) * TC_NT + n0, c);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    uint32_t o[2] = {0, 0};
+                    tmem_ld8(tmem + lane_base + D_COL0 + (2 * pb) * TC_NT, a);
+                    tmem_ld8(tmem + lane_base + D_COL0 + (2 * pb + 1) * TC_NT, c);
+#pragma unroll 2
+                    for (int n0 = 0; n0 < N; n0 += 8) {
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        uint32_t pa[4], pc[4];                        // lane sums of two queries per register (s16x2: |S| <= 16 * 128)
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const int2 k = I.kq[n0 + u];
-                        const int s0 = (int)a[u], s1 = (int)c[u];
-                        int e = min(max(s0 + s1, -128), 127);
-                        if ((s0 > k.x || s1 > k.y) && n0 + u < nq) {   // certificate failed: the fold has to be done step by step
-                            const int qi = atomicAdd(&S.n_queue, 1);
-                            if (qi < TC_QUEUE) S.queue[qi] = ((uint32_t)(t - t0) << 16) | ((uint32_t)row << 8) | (uint32_t)(n0 + u);
-                            else e = tc_refold<PH>(nat32, tile0 + t, row, B + (size_t)(n0 + u) * 16);   // queue full: on the spot
+                        for (int u = 0; u < 4; u++) { pa[u] = prmt(a[2 * u], a[2 * u + 1], 0x5410u); pc[u] = prmt(c[2 * u], c[2 * u + 1], 0x5410u); }
+                        if (n0 + 8 < N) {
+                            tmem_ld8(tmem + lane_base + D_COL0 + (2 * pb) * TC_NT + n0 + 8, a);
+                            tmem_ld8(tmem + lane_base + D_COL0 + (2 * pb + 1) * TC_NT + n0 + 8, c);
+                        } else {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&S.d_empty[pb]);
                         }
-                        o[u >> 2] |= (uint32_t)(e & 0xff) << (8 * (u & 3));
+                        uint32_t e2[4], fl = 0x80008000u;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {                 // two queries per step, s16x2
+                            const uint2 k = I.kq2[(n0 >> 1) + u];
+                            e2[u] = __vimin3_s16x2(__viaddmax_s16x2(pa[u], pc[u], 0xff80ff80u), 0x007f007fu, 0x007f007fu);
+                            fl = __vimax3_s16x2(fl, __vsub2(pa[u], k.x), __vsub2(pc[u], k.y));
+                        }
+                        uint32_t o0 = prmt(e2[0], e2[1], 0x6420u), o1 = prmt(e2[2], e2[3], 0x6420u);
+                        if (__any_sync(FULL, (int)(int16_t)(fl & 0xffffu) > 0 || (int)(int16_t)(fl >> 16) > 0))
+                            tc_flagged8<PH>(S, I.kq2, make_uint4(pa[0], pa[1], pa[2], pa[3]), make_uint4(pc[0], pc[1], pc[2], pc[3]), n0, nq,
+                                            t - t0, row, o0, o1, nat32, tile0 + t, B);
+                        outT[tc_out_addr(row, n0 >> 2)] = o0;
+                        outT[tc_out_addr(row, (n0 >> 2) + 1)] = o1;
                     }
-                    S.outT[row * TC_OUT_STRIDE + (n0 >> 2)] = o[0];
-                    S.outT[row * TC_OUT_STRIDE + (n0 >> 2) + 1] = o[1];
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.d_empty[b]);
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
-                // the tile: 16 estimates (one chunk) of one query per task, coalesced 16-byte stores
-                for (int task = ptid; task < nq * 8; task += 32 * TC_P_WARPS) {
-                    const int n = task >> 3, sc = task & 7;
+                // one barrier per tile inside the half: outT is double-buffered, so this barrier also separates the stores of
+                // tile k + 2 from the reads of tile k
+                const long long c2_ = clock64();
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + pb) : "memory");
+                const long long c3_ = clock64();
+                // the tile: a task = 4 queries x one chunk: 16 words in (rows of the chunk), 4 x 16 bytes out
+                for (int task = htid; task < ((nq + 3) >> 2) * 8; task += 128) {
+                    const int n4 = task >> 3, sc = task & 7;
                     const int chunk = t * 8 + sc;
                     if (chunk >= n_real) continue;
-                    uint32_t o[4];
+                    uint32_t w[16];
 #pragma unroll
-                    for (int w = 0; w < 4; w++) {
-                        uint32_t x = 0;
+                    for (int k = 0; k < 16; k++) w[k] = outT[tc_out_addr(16 * sc + k, n4)];
 #pragma unroll
-                        for (int bb = 0; bb < 4; bb++) {
-                            const uint32_t word = S.outT[(16 * sc + 4 * w + bb) * TC_OUT_STRIDE + (n >> 2)];
-                            x |= ((word >> (8 * (n & 3))) & 0xffu) << (8 * bb);
+                    for (int j = 0; j < 4; j++) {
+                        const int n = 4 * n4 + j;
+                        if (n >= nq) break;
+                        uint32_t o[4];
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; q4++) {              // byte j of four consecutive rows
+                            const uint32_t sel = 0x0040u + 0x0011u * j;                      // (w0.byte j, w1.byte j)
+                            const uint32_t lo = prmt(w[4 * q4], w[4 * q4 + 1], sel), hi = prmt(w[4 * q4 + 2], w[4 * q4 + 3], sel);
+                            o[q4] = prmt(lo, hi, 0x5410u);
                         }
-                        o[w] = x;
-                    }
-                    const long long off = I.dst[n] + 16LL * chunk;
-                    *reinterpret_cast<uint4 *>(est + off) = make_uint4(o[0], o[1], o[2], o[3]);
-                    if (cmin) {
-                        uint32_t m = __vmins4(__vmins4(o[0], o[1]), __vmins4(o[2], o[3]));
-                        m = __vmins4(m, m >> 16);
-                        m = __vmins4(m, m >> 8);
-                        cmin[off >> 4] = (uint8_t)(m & 0xffu);
+                        const long long off = I.dst[n] + 16LL * chunk;
+                        *reinterpret_cast<uint4 *>(est + off) = make_uint4(o[0], o[1], o[2], o[3]);
+                        if (cmin) {
+                            uint32_t m = __vmins4(__vmins4(o[0], o[1]), __vmins4(o[2], o[3]));
+                            m = __vmins4(m, m >> 16);
+                            m = __vmins4(m, m >> 8);
+                            cmin[off >> 4] = (uint8_t)(m & 0xffu);
+                        }
                     }
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
+                pk[0] += c1_ - c0_; pk[1] += c2_ - c1_; pk[2] += c3_ - c2_; pk[3] += clock64() - c3_;
             }
-            // the item's refold queue: the reference's recurrence for the pairs whose certificate failed, bytes patched in place
-            // (the refolded value is never above the provisional one, so a chunk minimum can only go down)
+            g += (uint32_t)(t1 - t0);
+            const long long f0_ = clock64();
+            // the item's refold queue (both halves together): the reference's recurrence for the pairs whose certificate failed,
+            // bytes patched in place (the refolded value is never above the provisional one: a chunk minimum can only go down)
+            asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
             {
                 const int nqd = min(S.n_queue, TC_QUEUE);
                 for (int i = ptid; i < nqd; i += 32 * TC_P_WARPS) {
@@ -559,12 +671,15 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     est[off] = (uint8_t)e;
                     if (cmin) atomic_min_s8(cmin + (off >> 4), e);
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
+                asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
                 if (ptid == 0) { if (S.n_queue) atomicAdd(W.hdr + 2, S.n_queue); S.n_queue = 0; }
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
+                asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
             }
+            pk[4] += clock64() - f0_;
             if (lane == 0) mbar_arrive(&S.item_empty[par]);
         }
+        if (warp == TC_E_WARPS && lane == 0)
+            for (int i = 0; i < 5; i++) atomicAdd(W.clk + CK_P_WAIT + i, (unsigned long long)pk[i]);
     }
     tc_fence_before();
     __syncthreads();

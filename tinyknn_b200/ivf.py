@@ -96,6 +96,14 @@ def _fresh(name, shape, np_dtype):
     return D.empty(shape, np_dtype)
 
 
+def _tc_applies(dev, Q, P):
+    """The tensor-core scan is built for M = 32 in the avx accumulation order and pays off when several queries of the
+    batch probe the same list."""
+    if TC_SCAN == "0" or dev["M"] != 32 or _fp._order() != 1 or _fp.SCAN_IMPL != "fast":
+        return False
+    return TC_SCAN == "1" or Q * P >= TC_MIN_SHARE * max(1, dev["C"])
+
+
 def _sub_batches(Q):
     if _N_STREAMS <= 1 or Q < 2 * _SUB_QUERIES:
         return 1
@@ -318,6 +326,8 @@ class IVF:
         # Sub-batches on alternating side streams: the latency-bound stages of one sub-batch (heap replay, row
         # gathers) overlap the issue-bound scan of the next. Only in throughput mode; order="numpy" syncs per stage.
         n_sub = 1 if order != "device" else (_sub_batches(Q) if sub_batches is None else max(1, int(sub_batches)))
+        if sub_batches is None and _tc_applies(dev, Q, P):              # the list-major scan shares a list's tile among ALL the
+            n_sub = 1                                                   # queries of a launch: splitting the batch doubles its work
         if n_sub > 1:
             qb = min(qb, -(-Q // n_sub))
         fused = (FUSED if fused is None else bool(fused)) and order == "device" and bool(dev.get("unique_ids", False))
@@ -439,9 +449,8 @@ class IVF:
         with self._stage("scan"):
             if _fp.SCAN_IMPL == "fast":
                 ws = buf("scan_ws", (64,), np.uint8)                     # its first 8 bytes count the recomputed chunks
-                use_tc = (TC_SCAN != "0" and push_cm is None and est is not None and seg_off is not None and M == 32
-                          and _fp._order() == 1 and codes_key == "codes"
-                          and (TC_SCAN == "1" or Q * P >= TC_MIN_SHARE * max(1, dev["C"])))
+                use_tc = (push_cm is None and est is not None and seg_off is not None and codes_key == "codes"
+                          and _tc_applies(dev, Q, P))
                 if use_tc:
                     import ctypes
                     need = ctypes.c_int64(0)
