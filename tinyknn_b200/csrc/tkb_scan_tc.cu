@@ -177,18 +177,36 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+// backoff_ns > 0: a role that usually waits long sleeps between polls instead of taking issue slots from the working warps
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsigned backoff_ns = 0)
 {
     const uint32_t addr = smem_u32(bar);
     uint32_t done;
-    do {                                        // try_wait suspends the thread (up to the time hint) instead of spinning
+    for (;;) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}\n" : "=r"(done) : "r"(addr), "r"(parity), "r"(1000000u) : "memory");
-    } while (!done);
+        if (done) break;
+        if (backoff_ns) __nanosleep(backoff_ns);
+    }
+}
+
+// one lane of a converged warp (the tcgen05 instructions take their operands from uniform registers: issued from divergent
+// code -- `if (lane == 0)` -- the compiler has to wrap every one of them in a broadcast loop)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "@px mov.s32 %0, 1;\n\t"
+        "}\n" : "+r"(pred) : "r"(0xffffffffu));
+    return pred != 0;
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -220,6 +238,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr));
 }
 
 // K-major, no swizzle: start address, leading-byte-offset (between the two 16-byte K chunks of one MMA), stride-byte-offset
@@ -276,6 +301,7 @@ struct TcItem {
 
 struct TcShared {
     uint64_t item_full[2], item_empty[2], a_full[2], a_empty[2], d_full[2], d_empty[2];
+    uint64_t o_full[2][2], o_empty[2][2];       // transposed tile [half][parity]: epilogue half -> expansion half (which writes it out) and back
     uint32_t tmem_base;
     int n_queue;
     TcItem item[2];
@@ -388,6 +414,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             mbar_init(&S.a_empty[b], 1);
             mbar_init(&S.d_full[b], 1);
             mbar_init(&S.d_empty[b], TC_P_WARPS / 2);
+            for (int k = 0; k < 2; k++) { mbar_init(&S.o_full[b][k], TC_P_WARPS / 2); mbar_init(&S.o_empty[b][k], TC_E_WARPS / 2); }
         }
         S.n_queue = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -403,7 +430,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
         for (uint32_t it = 0;; it++) {
             const int par = it & 1;
             const long long c0_ = clock64();
-            mbar_wait(&S.item_empty[par], ((it >> 1) & 1) ^ 1);
+            mbar_wait(&S.item_empty[par], ((it >> 1) & 1) ^ 1, 1000);
             const long long c1_ = clock64();
             lk[0] += c1_ - c0_;
             TcItem &I = S.item[par];
@@ -478,7 +505,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             mbar_wait(&S.item_full[par], (it >> 1) & 1);
             const TcItem &I = S.item[par];
             if (!I.valid) break;
-            if (lane == 0) {
+            {                                                         // the whole warp runs the loop, one elected lane issues
                 const uint32_t idesc = umma_idesc_i8(I.N);
                 const uint32_t b0 = smem_u32(Bslab + (size_t)par * SLAB);
                 for (int t = I.t0; t < I.t1; t++, g++) {
@@ -489,16 +516,18 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     mbar_wait(&S.d_empty[b], ph ^ 1);
                     tc_fence_after();
                     const long long c2_ = clock64();
+                    if (elect_one()) {
 #pragma unroll
-                    for (int p = 0; p < PH; p++)
-                        umma_i8_ts(tmem + D_COL0 + (2 * b + (p & 1)) * TC_NT, tmem + b * A_COLS + 8 * p,
-                                   umma_desc_kmajor(b0 + (uint32_t)(2 * p) * TC_NT * 16, TC_NT * 16, 128), idesc, p >= 2 ? 1u : 0u);
-                    umma_commit(&S.a_empty[b]);
-                    umma_commit(&S.d_full[b]);
+                        for (int p = 0; p < PH; p++)
+                            umma_i8_ts(tmem + D_COL0 + (2 * b + (p & 1)) * TC_NT, tmem + b * A_COLS + 8 * p,
+                                       umma_desc_kmajor(b0 + (uint32_t)(2 * p) * TC_NT * 16, TC_NT * 16, 128), idesc, p >= 2 ? 1u : 0u);
+                        umma_commit(&S.a_empty[b]);
+                        umma_commit(&S.d_full[b]);
+                    }
+                    __syncwarp();
                     mk[0] += c1_ - c0_; mk[1] += c2_ - c1_; mk[2] += clock64() - c2_;
                 }
             }
-            g = __shfl_sync(FULL, g, 0);
             if (lane == 0) {
                 atomicAdd(W.hdr + 3, I.t1 - I.t0);
                 atomicAdd(W.hdr + 4, (I.t1 - I.t0) * (I.N >> 4));
@@ -510,128 +539,34 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             atomicAdd(W.clk + CK_M_ISSUE, (unsigned long long)mk[2]); atomicAdd(W.clk + CK_TOTAL, (unsigned long long)(clock64() - k0_));
         }
     } else if (warp < TC_E_WARPS) {
-        // ================================ expansion ==================================================================
+        // ================================ expansion (+ copy-out) =====================================================
         const int row = 32 * (warp & 3) + lane, eb = warp >> 2;      // eb: the buffer (tile parity) this half works on
+        const int htid = tid - 128 * eb;                             // 0..127 inside the half
         const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
         const int s = row >> 4, v = row & 15, gq = v >> 2, sh = 16 * (gq & 1) + 4 * (v & 3);
-        uint32_t g = 0;
-        long long ck[2] = {0, 0};
+        uint32_t g = 0, k_tile = 0;                                  // k_tile: tiles this half has expanded (= the epilogue half's count)
+        long long ck[3] = {0, 0, 0};
         for (uint32_t it = 0;; it++) {
             const int par = it & 1;
-            mbar_wait(&S.item_full[par], (it >> 1) & 1);
+            mbar_wait(&S.item_full[par], (it >> 1) & 1, 200);
             const TcItem &I = S.item[par];
             if (!I.valid) break;
-            const int t0 = I.t0, t1 = I.t1;
+            const int t0 = I.t0, t1 = I.t1, nq = I.nq, n_real = I.n_real;
             const int first = t0 + (int)((eb - g) & 1);              // this half's first tile of the item: (g + first - t0) & 1 == eb
             const uint32_t *tb = nat32 + ((size_t)I.tile0 * PH * 8 + s) * 4 + (gq >> 1);
-            // the code words of a tile are fetched where they are used; the tile this half expands next is prefetched into L1 a tile
-            // ahead (one 128-byte line per sub-quantizer pair and half-warp), so those loads hit. The loop is kept small: the four
-            // roles of the kernel share one instruction cache.
-            if (first < t1 && (lane & 15) == 0)
-                for (int p = 0; p < PH; p++)
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(tb + ((size_t)first * PH + p) * 32));
-            for (int t = first; t < t1; t += 2) {
-                const uint32_t gg = g + (uint32_t)(t - t0), ph = (gg >> 1) & 1;
-                if (t + 2 < t1 && (lane & 15) == 0)
-                    for (int p = 0; p < PH; p++)
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(tb + ((size_t)(t + 2) * PH + p) * 32));
-                const long long c0_ = clock64();
-                mbar_wait(&S.a_empty[eb], ph ^ 1);
-                tc_fence_after();
-                const long long c1_ = clock64();
-                const uint32_t *tt = tb + (size_t)t * PH * 32;
-#pragma unroll 4
-                for (int p = 0; p < PH; p++) {
-                    const uint32_t ca = (__ldg(tt + p * 32) >> sh) & 15u, cb = (__ldg(tt + p * 32 + 2) >> sh) & 15u;
-                    uint32_t r[8];
-                    onehot_unit(ca, r[0], r[1], r[2], r[3]);
-                    onehot_unit(cb, r[4], r[5], r[6], r[7]);
-                    tmem_st8(tmem + lane_base + eb * A_COLS + 8 * p, r);
-                }
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.a_full[eb]);
-                ck[0] += c1_ - c0_; ck[1] += clock64() - c1_;
-            }
-            g += (uint32_t)(t1 - t0);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.item_empty[par]);
-        }
-        if (warp == 0 && lane == 0) { atomicAdd(W.clk + CK_E_WAIT, (unsigned long long)ck[0]); atomicAdd(W.clk + CK_E_WORK, (unsigned long long)ck[1]); }
-    } else {
-        // ================================ epilogue ===================================================================
-        const int pb = (warp - TC_E_WARPS) >> 2;                     // the buffer (tile parity) this half works on
-        const int htid = tid - 32 * (TC_E_WARPS + 4 * pb);           // 0..127 inside the half
-        const int ptid = tid - 32 * TC_E_WARPS;                      // 0..255 inside the role
-        const int row = 32 * (warp & 3) + lane;
-        const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-        uint32_t g = 0, k_tile = 0;                                  // k_tile: tiles this half has written (outT parity)
-        long long pk[5] = {0, 0, 0, 0, 0};
-        for (uint32_t it = 0;; it++) {
-            const int par = it & 1;
-            mbar_wait(&S.item_full[par], (it >> 1) & 1);
-            const TcItem &I = S.item[par];
-            if (!I.valid) break;
-            const int t0 = I.t0, t1 = I.t1, N = I.N, nq = I.nq, n_real = I.n_real;
-            const long long tile0 = I.tile0;
-            const uint8_t *B = Bslab + (size_t)par * SLAB;
-            const int first = t0 + (int)((pb - g) & 1);
-            for (int t = first; t < t1; t += 2, k_tile++) {
-                const uint32_t gg = g + (uint32_t)(t - t0), ph = (gg >> 1) & 1;
-                uint32_t *outT = S.outT[pb][k_tile & 1];
-                const long long c0_ = clock64();
-                mbar_wait(&S.d_full[pb], ph);
-                tc_fence_after();
-                const long long c1_ = clock64();
-                // 8 query columns per step; the loads of the next step are issued before this step's arithmetic, and the accumulators go
-                // back to the MMA issuer as soon as the last load has landed (not after the whole epilogue). Small loop body on purpose.
-                {
-                    uint32_t a[8], c[8];
-                    tmem_ld8(tmem + lane_base + D_COL0 + (2 * pb) * TC_NT, a);
-                    tmem_ld8(tmem + lane_base + D_COL0 + (2 * pb + 1) * TC_NT, c);
-#pragma unroll 2
-                    for (int n0 = 0; n0 < N; n0 += 8) {
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        uint32_t pa[4], pc[4];                        // lane sums of two queries per register (s16x2: |S| <= 16 * 128)
-#pragma unroll
-                        for (int u = 0; u < 4; u++) { pa[u] = prmt(a[2 * u], a[2 * u + 1], 0x5410u); pc[u] = prmt(c[2 * u], c[2 * u + 1], 0x5410u); }
-                        if (n0 + 8 < N) {
-                            tmem_ld8(tmem + lane_base + D_COL0 + (2 * pb) * TC_NT + n0 + 8, a);
-                            tmem_ld8(tmem + lane_base + D_COL0 + (2 * pb + 1) * TC_NT + n0 + 8, c);
-                        } else {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&S.d_empty[pb]);
-                        }
-                        uint32_t e2[4], fl = 0x80008000u;
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {                 // two queries per step, s16x2
-                            const uint2 k = I.kq2[(n0 >> 1) + u];
-                            e2[u] = __vimin3_s16x2(__viaddmax_s16x2(pa[u], pc[u], 0xff80ff80u), 0x007f007fu, 0x007f007fu);
-                            fl = __vimax3_s16x2(fl, __vsub2(pa[u], k.x), __vsub2(pc[u], k.y));
-                        }
-                        uint32_t o0 = prmt(e2[0], e2[1], 0x6420u), o1 = prmt(e2[2], e2[3], 0x6420u);
-                        if (__any_sync(FULL, (int)(int16_t)(fl & 0xffffu) > 0 || (int)(int16_t)(fl >> 16) > 0))
-                            tc_flagged8<PH>(S, I.kq2, make_uint4(pa[0], pa[1], pa[2], pa[3]), make_uint4(pc[0], pc[1], pc[2], pc[3]), n0, nq,
-                                            t - t0, row, o0, o1, nat32, tile0 + t, B);
-                        outT[tc_out_addr(row, n0 >> 2)] = o0;
-                        outT[tc_out_addr(row, (n0 >> 2) + 1)] = o1;
-                    }
-                }
-                // one barrier per tile inside the half: outT is double-buffered, so this barrier also separates the stores of
-                // tile k + 2 from the reads of tile k
-                const long long c2_ = clock64();
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + pb) : "memory");
-                const long long c3_ = clock64();
-                // the tile: a task = 4 queries x one chunk: 16 words in (rows of the chunk), 4 x 16 bytes out
+            // The epilogue half leaves the tile transposed in shared memory (row = vector, byte = query); this half, which would
+            // otherwise wait for the tensor core, writes it out: a task = 4 queries x one chunk: 16 words in, 4 x 16 bytes out.
+            auto copy_out = [&](int t, uint32_t k) {
+                const long long w0_ = clock64();
+                mbar_wait(&S.o_full[eb][k & 1], (k >> 1) & 1, 100);
+                const uint32_t *outT = S.outT[eb][k & 1];
                 for (int task = htid; task < ((nq + 3) >> 2) * 8; task += 128) {
                     const int n4 = task >> 3, sc = task & 7;
                     const int chunk = t * 8 + sc;
                     if (chunk >= n_real) continue;
                     uint32_t w[16];
 #pragma unroll
-                    for (int k = 0; k < 16; k++) w[k] = outT[tc_out_addr(16 * sc + k, n4)];
+                    for (int kk = 0; kk < 16; kk++) w[kk] = outT[tc_out_addr(16 * sc + kk, n4)];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const int n = 4 * n4 + j;
@@ -653,10 +588,126 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                         }
                     }
                 }
-                pk[0] += c1_ - c0_; pk[1] += c2_ - c1_; pk[2] += c3_ - c2_; pk[3] += clock64() - c3_;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.o_empty[eb][k & 1]);
+                ck[2] += clock64() - w0_;
+            };
+            for (int t = first; t < t1; t += 2, k_tile++) {
+                const uint32_t gg = g + (uint32_t)(t - t0), ph = (gg >> 1) & 1;
+                // the tile's code words: all loads in flight before the wait for the buffer, which hides their latency
+                uint32_t cur[2 * PH];
+#pragma unroll
+                for (int p = 0; p < PH; p++) {
+                    cur[2 * p] = __ldg(tb + ((size_t)t * PH + p) * 32);
+                    cur[2 * p + 1] = __ldg(tb + ((size_t)t * PH + p) * 32 + 2);
+                }
+                const long long c0_ = clock64();
+                mbar_wait(&S.a_empty[eb], ph ^ 1, 100);
+                tc_fence_after();
+                const long long c1_ = clock64();
+#pragma unroll
+                for (int p = 0; p < PH; p++) {
+                    uint32_t r[8];
+                    onehot_unit((cur[2 * p] >> sh) & 15u, r[0], r[1], r[2], r[3]);
+                    onehot_unit((cur[2 * p + 1] >> sh) & 15u, r[4], r[5], r[6], r[7]);
+                    tmem_st8(tmem + lane_base + eb * A_COLS + 8 * p, r);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.a_full[eb]);
+                ck[0] += c1_ - c0_; ck[1] += clock64() - c1_;
+                if (t != first) copy_out(t - 2, k_tile - 1);         // the previous tile of this half: its epilogue has had a whole MMA's time
+            }
+            if (first < t1) copy_out(first + 2 * ((t1 - 1 - first) >> 1), k_tile - 1);   // the half's last tile of the item
+            g += (uint32_t)(t1 - t0);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.item_empty[par]);
+        }
+        if (warp == 0 && lane == 0) {
+            atomicAdd(W.clk + CK_E_WAIT, (unsigned long long)ck[0]); atomicAdd(W.clk + CK_E_WORK, (unsigned long long)ck[1]);
+            atomicAdd(W.clk + CK_P_COPY, (unsigned long long)ck[2]);
+        }
+    } else {
+        // ================================ epilogue ===================================================================
+        const int pb = (warp - TC_E_WARPS) >> 2;                     // the buffer (tile parity) this half works on
+        const int htid = tid - 32 * (TC_E_WARPS + 4 * pb);           // 0..127 inside the half
+        const int ptid = tid - 32 * TC_E_WARPS;                      // 0..255 inside the role
+        const int row = 32 * (warp & 3) + lane;
+        const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+        uint32_t g = 0, k_tile = 0;                                  // k_tile: tiles this half has written (outT parity)
+        long long pk[5] = {0, 0, 0, 0, 0};
+        for (uint32_t it = 0;; it++) {
+            const int par = it & 1;
+            mbar_wait(&S.item_full[par], (it >> 1) & 1);
+            const TcItem &I = S.item[par];
+            if (!I.valid) break;
+            const int t0 = I.t0, t1 = I.t1, N = I.N, nq = I.nq, n_real = I.n_real;
+            const long long tile0 = I.tile0;
+            const uint8_t *B = Bslab + (size_t)par * SLAB;
+            const int first = t0 + (int)((pb - g) & 1);
+            for (int t = first; t < t1; t += 2, k_tile++) {
+                const uint32_t gg = g + (uint32_t)(t - t0), ph = (gg >> 1) & 1;
+                uint32_t *outT = S.outT[pb][k_tile & 1];
+                const long long b0_ = clock64();
+                mbar_wait(&S.o_empty[pb][k_tile & 1], ((k_tile >> 1) & 1) ^ 1);   // written out two own tiles ago
+                const long long c0_ = clock64();
+                pk[2] += c0_ - b0_;
+                mbar_wait(&S.d_full[pb], ph);
+                tc_fence_after();
+                const long long c1_ = clock64();
+                // 16 query columns per step (a group has a multiple of 16); the loads of the next step are issued before this step's
+                // arithmetic, and the accumulators go back to the MMA issuer as soon as the last load has landed, not after the whole
+                // epilogue. Small loop body on purpose.
+                {
+                    uint32_t a[16], c[16];
+                    tmem_ld16(tmem + lane_base + D_COL0 + (2 * pb) * TC_NT, a);
+                    tmem_ld16(tmem + lane_base + D_COL0 + (2 * pb + 1) * TC_NT, c);
+#pragma unroll 1
+                    for (int n0 = 0; n0 < N; n0 += 16) {
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        uint32_t pa[8], pc[8];                        // lane sums of two queries per register (s16x2: |S| <= 16 * 128)
+#pragma unroll
+                        for (int u = 0; u < 8; u++) { pa[u] = prmt(a[2 * u], a[2 * u + 1], 0x5410u); pc[u] = prmt(c[2 * u], c[2 * u + 1], 0x5410u); }
+                        if (n0 + 16 < N) {
+                            tmem_ld16(tmem + lane_base + D_COL0 + (2 * pb) * TC_NT + n0 + 16, a);
+                            tmem_ld16(tmem + lane_base + D_COL0 + (2 * pb + 1) * TC_NT + n0 + 16, c);
+                        } else {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&S.d_empty[pb]);
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {                 // 8 queries each
+                            const int n8 = n0 + 8 * h;
+                            uint32_t e2[4], fl = 0x80008000u;
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {             // two queries per step, s16x2
+                                const uint2 k = I.kq2[(n8 >> 1) + u];
+                                e2[u] = __vimin3_s16x2(__viaddmax_s16x2(pa[4 * h + u], pc[4 * h + u], 0xff80ff80u), 0x007f007fu, 0x007f007fu);
+                                fl = __vimax3_s16x2(fl, __vsub2(pa[4 * h + u], k.x), __vsub2(pc[4 * h + u], k.y));
+                            }
+                            uint32_t o0 = prmt(e2[0], e2[1], 0x6420u), o1 = prmt(e2[2], e2[3], 0x6420u);
+                            if (__any_sync(FULL, (int)(int16_t)(fl & 0xffffu) > 0 || (int)(int16_t)(fl >> 16) > 0))
+                                tc_flagged8<PH>(S, I.kq2, make_uint4(pa[4 * h], pa[4 * h + 1], pa[4 * h + 2], pa[4 * h + 3]),
+                                                make_uint4(pc[4 * h], pc[4 * h + 1], pc[4 * h + 2], pc[4 * h + 3]), n8, nq, t - t0, row, o0, o1,
+                                                nat32, tile0 + t, B);
+                            outT[tc_out_addr(row, n8 >> 2)] = o0;
+                            outT[tc_out_addr(row, (n8 >> 2) + 1)] = o1;
+                        }
+                    }
+                }
+                const long long c2_ = clock64();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.o_full[pb][k_tile & 1]);   // the expansion half writes the tile out
+                pk[0] += c1_ - c0_; pk[1] += c2_ - c1_;
             }
             g += (uint32_t)(t1 - t0);
             const long long f0_ = clock64();
+            for (uint32_t back = 1; back <= 2 && back <= k_tile; back++) {   // (waiting again for an older phase returns at once)
+                const uint32_t k = k_tile - back;
+                mbar_wait(&S.o_empty[pb][k & 1], (k >> 1) & 1);
+            }
             // the item's refold queue (both halves together): the reference's recurrence for the pairs whose certificate failed,
             // bytes patched in place (the refolded value is never above the provisional one: a chunk minimum can only go down)
             asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
