@@ -35,11 +35,9 @@
 
 namespace tkb {
 
-constexpr int TC_THREADS = 256;
 constexpr int TC_NT = 64;                       // queries per group (UMMA N <= 64: 2 x 2 x 64 accumulator columns + 256 of A)
 constexpr int TC_TILES_PER_ITEM = 128;          // tiles (of 128 vectors) per work item: long lists are split
 constexpr int TC_OUT_STRIDE = TC_NT / 4 + 1;    // words per row of the transposed output tile (see tc_out_addr)
-constexpr int TC_PATCH_CAP = 1024;
 
 struct TcQueryMeta { int16_t elig, k0, k1, pad; };
 
@@ -240,6 +238,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
 }
 
+// 8 accumulator columns, the low 16 bits of each, two per register (.pack::16b): exactly the s16x2 operands of the epilogue
+__device__ __forceinline__ void tmem_ld8_pack16(uint32_t taddr, uint32_t (&v)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.pack::16b.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -261,14 +266,17 @@ __device__ __forceinline__ uint32_t umma_idesc_i8(int n)
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-// The 16-byte one-hot unit of a 4-bit code c: byte k = (k == c). One PRMT per 32-bit word: the selector nibble of byte b of
-// word w is c ^ (4w + b); it is 0 (-> source byte 0 = 0x01) exactly when c == 4w + b, any other nibble value selects a zero byte
-// (or, with bit 3 set, the replicated sign bit of a byte that is 0x00 or 0x01, i.e. zero).
+// The 16-byte one-hot unit of a 4-bit code c: byte k = (k == c). One PRMT per 32-bit word: the selector nibble of byte b of word
+// w is 0 (-> source byte 0 = 0x01) exactly when c == 4w + b; any other nibble value selects a zero byte (or, with bit 3 set, the
+// replicated sign bit of a byte that is 0x00 or 0x01, i.e. zero). For words 0..2 the selector is c * 0x1111 - (nibbles 4w..4w+3):
+// ONE multiply-add on the FMA pipe (a borrow between nibbles can never fake a zero nibble there -- checked exhaustively); for
+// word 3 the borrow chain of c = 0 would, so its selector is the XOR form. The integer pipe, which binds this kernel, is left
+// with the four PRMTs, one XOR and the two instructions that extract the code.
 __device__ __forceinline__ void onehot_unit(uint32_t c, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3)
 {
     const uint32_t cr = c * 0x1111u;
-    w0 = prmt(1u, 0u, cr ^ 0x3210u); w1 = prmt(1u, 0u, cr ^ 0x7654u);
-    w2 = prmt(1u, 0u, cr ^ 0xba98u); w3 = prmt(1u, 0u, cr ^ 0xfedcu);
+    w0 = prmt(1u, 0u, c * 0x1111u - 0x3210u); w1 = prmt(1u, 0u, c * 0x1111u - 0x7654u);
+    w2 = prmt(1u, 0u, c * 0x1111u - 0xba98u); w3 = prmt(1u, 0u, cr ^ 0xfedcu);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -277,17 +285,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 
 // ---- roles of the persistent kernel -------------------------------------------------------------------------------------
-//   warps 0..7   expansion : thread = one vector (TMEM lane) of a tile, all its sub-quantizers; warps 0-3 take the even tiles
-//                            (buffer 0), warps 4-7 the odd ones (buffer 1); one-hot units straight into tensor memory
-//   warps 8..15  epilogue  : thread = one vector, all the queries of the group; warps 8-11 the even tiles, 12-15 the odd ones:
-//                            tcgen05.ld, certificate, clamp (s16x2 SIMD), transposed tile in shared memory, 16-byte stores
-//   warp 16      multiplies: one thread issues the tile's PH tcgen05.mma and commits them to the mbarriers
+//   warps 0..15  workers   : two halves of 8 warps; half h owns the tiles of parity h and the buffers A[h], D[h] in tensor memory.
+//                            A thread is one vector (TMEM lane 32 * (warp % 4) + lane) of the tile; the two warps that share a lane
+//                            quadrant split the sub-quantizer pairs (expansion) and the group's queries (epilogue) between them.
+//                            Per tile: one-hot units into A[h] (tcgen05.st) -> [the MMA warp multiplies; meanwhile the warp writes
+//                            out its part of the half's previous tile] -> tcgen05.ld of D[h], certificate + clamp (s16x2 SIMD),
+//                            transposed tile in shared memory. While a half waits for its MMA or for tensor memory the other half
+//                            works: every scheduler holds four busy warps.
+//   warp 16      multiplies: one elected lane issues the tile's PH tcgen05.mma and commits them to the half's mbarrier
 //   warp 17      loads     : fetches the next work item, stages its LUT slab (double-buffered)
-// A and D are double-buffered in tensor memory, so the expansion of tile t+1, the MMAs of tile t and the epilogue of tile t-1
-// run at the same time; the two halves of a role work on alternate tiles and never wait for each other. Nothing but mbarriers
-// (and a 128-thread named barrier inside each epilogue half) synchronises the roles.
-constexpr int TC_E_WARPS = 8, TC_P_WARPS = 8;
-constexpr int TC_WARPS = TC_E_WARPS + TC_P_WARPS + 2;
+// A half reads D[h] and rewrites A[h] in program order, so the MMA warp needs no "empty" barriers: a_full[h] implies both.
+constexpr int TC_WORKERS = 16;
+constexpr int TC_WARPS = TC_WORKERS + 2;
 constexpr int TC_THREADS2 = 32 * TC_WARPS;
 constexpr int TC_QUEUE = 4096;                  // refold queue of one work item
 
@@ -295,17 +304,16 @@ struct TcItem {
     int valid, list, nq, N, t0, t1, n_real, pad;
     long long tile0;                            // first tile of the list in the code array
     int q_of[TC_NT];                            // query of group member i (-1: padding column)
-    uint2 kq2[TC_NT / 2];                       // certificate thresholds of query pairs: .x = (k0[2i], k0[2i+1]), .y = (k1[..]) as s16x2
+    uint2 kq2[TC_NT / 2];                       // NEGATED certificate thresholds of query pairs: .x = (-k0[2i], -k0[2i+1]), .y = (-k1[..]), s16x2
     long long dst[TC_NT];                       // est offset of its segment
 };
 
 struct TcShared {
-    uint64_t item_full[2], item_empty[2], a_full[2], a_empty[2], d_full[2], d_empty[2];
-    uint64_t o_full[2][2], o_empty[2][2];       // transposed tile [half][parity]: epilogue half -> expansion half (which writes it out) and back
+    uint64_t item_full[2], item_empty[2], a_full[2], d_full[2];
     uint32_t tmem_base;
     int n_queue;
     TcItem item[2];
-    uint32_t outT[2][2][128 * TC_OUT_STRIDE];   // [epilogue half][tile parity]: row = vector, byte n = query n of the group
+    uint32_t outT[2][128 * TC_OUT_STRIDE];      // [half]: row = vector, byte n = query n of the group (a warp reads back only what it wrote)
     uint32_t queue[TC_QUEUE];                   // (tile << 16) | (row << 8) | query column of the pairs whose certificate failed
 };
 
@@ -358,7 +366,7 @@ __device__ __noinline__ void tc_flagged8(TcShared &S, const uint2 *kq2, uint4 pa
 #pragma unroll
     for (int u = 0; u < 4; u++) {
         const uint2 k = kq2[(n0 >> 1) + u];
-        const uint32_t d = __vmaxs2(__vsub2(pas[u], k.x), __vsub2(pcs[u], k.y));        // > 0 in a half: that query's certificate failed
+        const uint32_t d = __vmaxs2(__vadd2(pas[u], k.x), __vadd2(pcs[u], k.y));        // > 0 in a half: that query's certificate failed (k negated)
         if ((int)(int16_t)(d & 0xffffu) > 0) mask |= 1u << (2 * u);
         if ((int)(int16_t)(d >> 16) > 0) mask |= 2u << (2 * u);
     }
@@ -409,12 +417,9 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
     if (tid == 32) {
         for (int b = 0; b < 2; b++) {
             mbar_init(&S.item_full[b], 32);
-            mbar_init(&S.item_empty[b], TC_E_WARPS + TC_P_WARPS + 1);
-            mbar_init(&S.a_full[b], TC_E_WARPS / 2);
-            mbar_init(&S.a_empty[b], 1);
+            mbar_init(&S.item_empty[b], TC_WORKERS + 1);
+            mbar_init(&S.a_full[b], TC_WORKERS / 2);
             mbar_init(&S.d_full[b], 1);
-            mbar_init(&S.d_empty[b], TC_P_WARPS / 2);
-            for (int k = 0; k < 2; k++) { mbar_init(&S.o_full[b][k], TC_P_WARPS / 2); mbar_init(&S.o_empty[b][k], TC_E_WARPS / 2); }
         }
         S.n_queue = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -468,8 +473,8 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     k0 = m.k0; k1 = m.k1;
                 }
                 I.q_of[i] = q; I.dst[i] = d;
-                reinterpret_cast<uint16_t *>(I.kq2)[4 * (i >> 1) + (i & 1)] = (uint16_t)(int16_t)k0;
-                reinterpret_cast<uint16_t *>(I.kq2)[4 * (i >> 1) + 2 + (i & 1)] = (uint16_t)(int16_t)k1;
+                reinterpret_cast<uint16_t *>(I.kq2)[4 * (i >> 1) + (i & 1)] = (uint16_t)(int16_t)(-k0);          // negated: the epilogue adds
+                reinterpret_cast<uint16_t *>(I.kq2)[4 * (i >> 1) + 2 + (i & 1)] = (uint16_t)(int16_t)(-k1);
             }
             __syncwarp();
             uint8_t *B = Bslab + (size_t)par * SLAB;
@@ -511,17 +516,14 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                 for (int t = I.t0; t < I.t1; t++, g++) {
                     const uint32_t b = g & 1, ph = (g >> 1) & 1;
                     const long long c0_ = clock64();
-                    mbar_wait(&S.a_full[b], ph);
-                    const long long c1_ = clock64();
-                    mbar_wait(&S.d_empty[b], ph ^ 1);
+                    mbar_wait(&S.a_full[b], ph);          // A[b] written AND D[b] read by the half (program order of its warps)
                     tc_fence_after();
-                    const long long c2_ = clock64();
+                    const long long c1_ = clock64(), c2_ = c1_;
                     if (elect_one()) {
 #pragma unroll
                         for (int p = 0; p < PH; p++)
                             umma_i8_ts(tmem + D_COL0 + (2 * b + (p & 1)) * TC_NT, tmem + b * A_COLS + 8 * p,
                                        umma_desc_kmajor(b0 + (uint32_t)(2 * p) * TC_NT * 16, TC_NT * 16, 128), idesc, p >= 2 ? 1u : 0u);
-                        umma_commit(&S.a_empty[b]);
                         umma_commit(&S.d_full[b]);
                     }
                     __syncwarp();
@@ -538,182 +540,135 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             atomicAdd(W.clk + CK_M_WAIT_A, (unsigned long long)mk[0]); atomicAdd(W.clk + CK_M_WAIT_D, (unsigned long long)mk[1]);
             atomicAdd(W.clk + CK_M_ISSUE, (unsigned long long)mk[2]); atomicAdd(W.clk + CK_TOTAL, (unsigned long long)(clock64() - k0_));
         }
-    } else if (warp < TC_E_WARPS) {
-        // ================================ expansion (+ copy-out) =====================================================
-        const int row = 32 * (warp & 3) + lane, eb = warp >> 2;      // eb: the buffer (tile parity) this half works on
-        const int htid = tid - 128 * eb;                             // 0..127 inside the half
-        const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-        const int s = row >> 4, v = row & 15, gq = v >> 2, sh = 16 * (gq & 1) + 4 * (v & 3);
-        uint32_t g = 0, k_tile = 0;                                  // k_tile: tiles this half has expanded (= the epilogue half's count)
-        long long ck[3] = {0, 0, 0};
-        for (uint32_t it = 0;; it++) {
-            const int par = it & 1;
-            mbar_wait(&S.item_full[par], (it >> 1) & 1, 200);
-            const TcItem &I = S.item[par];
-            if (!I.valid) break;
-            const int t0 = I.t0, t1 = I.t1, nq = I.nq, n_real = I.n_real;
-            const int first = t0 + (int)((eb - g) & 1);              // this half's first tile of the item: (g + first - t0) & 1 == eb
-            const uint32_t *tb = nat32 + ((size_t)I.tile0 * PH * 8 + s) * 4 + (gq >> 1);
-            // The epilogue half leaves the tile transposed in shared memory (row = vector, byte = query); this half, which would
-            // otherwise wait for the tensor core, writes it out: a task = 4 queries x one chunk: 16 words in, 4 x 16 bytes out.
-            auto copy_out = [&](int t, uint32_t k) {
-                const long long w0_ = clock64();
-                mbar_wait(&S.o_full[eb][k & 1], (k >> 1) & 1, 100);
-                const uint32_t *outT = S.outT[eb][k & 1];
-                for (int task = htid; task < ((nq + 3) >> 2) * 8; task += 128) {
-                    const int n4 = task >> 3, sc = task & 7;
-                    const int chunk = t * 8 + sc;
-                    if (chunk >= n_real) continue;
-                    uint32_t w[16];
-#pragma unroll
-                    for (int kk = 0; kk < 16; kk++) w[kk] = outT[tc_out_addr(16 * sc + kk, n4)];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int n = 4 * n4 + j;
-                        if (n >= nq) break;
-                        uint32_t o[4];
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; q4++) {              // byte j of four consecutive rows
-                            const uint32_t sel = 0x0040u + 0x0011u * j;                      // (w0.byte j, w1.byte j)
-                            const uint32_t lo = prmt(w[4 * q4], w[4 * q4 + 1], sel), hi = prmt(w[4 * q4 + 2], w[4 * q4 + 3], sel);
-                            o[q4] = prmt(lo, hi, 0x5410u);
-                        }
-                        const long long off = I.dst[n] + 16LL * chunk;
-                        *reinterpret_cast<uint4 *>(est + off) = make_uint4(o[0], o[1], o[2], o[3]);
-                        if (cmin) {
-                            uint32_t m = __vmins4(__vmins4(o[0], o[1]), __vmins4(o[2], o[3]));
-                            m = __vmins4(m, m >> 16);
-                            m = __vmins4(m, m >> 8);
-                            cmin[off >> 4] = (uint8_t)(m & 0xffu);
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.o_empty[eb][k & 1]);
-                ck[2] += clock64() - w0_;
-            };
-            for (int t = first; t < t1; t += 2, k_tile++) {
-                const uint32_t gg = g + (uint32_t)(t - t0), ph = (gg >> 1) & 1;
-                // the tile's code words: all loads in flight before the wait for the buffer, which hides their latency
-                uint32_t cur[2 * PH];
-#pragma unroll
-                for (int p = 0; p < PH; p++) {
-                    cur[2 * p] = __ldg(tb + ((size_t)t * PH + p) * 32);
-                    cur[2 * p + 1] = __ldg(tb + ((size_t)t * PH + p) * 32 + 2);
-                }
-                const long long c0_ = clock64();
-                mbar_wait(&S.a_empty[eb], ph ^ 1, 100);
-                tc_fence_after();
-                const long long c1_ = clock64();
-#pragma unroll
-                for (int p = 0; p < PH; p++) {
-                    uint32_t r[8];
-                    onehot_unit((cur[2 * p] >> sh) & 15u, r[0], r[1], r[2], r[3]);
-                    onehot_unit((cur[2 * p + 1] >> sh) & 15u, r[4], r[5], r[6], r[7]);
-                    tmem_st8(tmem + lane_base + eb * A_COLS + 8 * p, r);
-                }
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.a_full[eb]);
-                ck[0] += c1_ - c0_; ck[1] += clock64() - c1_;
-                if (t != first) copy_out(t - 2, k_tile - 1);         // the previous tile of this half: its epilogue has had a whole MMA's time
-            }
-            if (first < t1) copy_out(first + 2 * ((t1 - 1 - first) >> 1), k_tile - 1);   // the half's last tile of the item
-            g += (uint32_t)(t1 - t0);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.item_empty[par]);
-        }
-        if (warp == 0 && lane == 0) {
-            atomicAdd(W.clk + CK_E_WAIT, (unsigned long long)ck[0]); atomicAdd(W.clk + CK_E_WORK, (unsigned long long)ck[1]);
-            atomicAdd(W.clk + CK_P_COPY, (unsigned long long)ck[2]);
-        }
     } else {
-        // ================================ epilogue ===================================================================
-        const int pb = (warp - TC_E_WARPS) >> 2;                     // the buffer (tile parity) this half works on
-        const int htid = tid - 32 * (TC_E_WARPS + 4 * pb);           // 0..127 inside the half
-        const int ptid = tid - 32 * TC_E_WARPS;                      // 0..255 inside the role
+        // ================================ workers ====================================================================
+        const int h = warp >> 3, sub = (warp >> 2) & 1;              // half (tile parity, buffers), which of the two warps of a lane quadrant
         const int row = 32 * (warp & 3) + lane;
         const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-        uint32_t g = 0, k_tile = 0;                                  // k_tile: tiles this half has written (outT parity)
-        long long pk[5] = {0, 0, 0, 0, 0};
+        const int s = row >> 4, v = row & 15, gq = v >> 2, sh = 16 * (gq & 1) + 4 * (v & 3);
+        constexpr int PW = PH / 2;                                   // sub-quantizer pairs per warp
+        uint32_t g = 0, k_tile = 0;                                  // tiles seen by the kernel / tiles of this half
+        long long ck[5] = {0, 0, 0, 0, 0};
         for (uint32_t it = 0;; it++) {
             const int par = it & 1;
-            mbar_wait(&S.item_full[par], (it >> 1) & 1);
+            mbar_wait(&S.item_full[par], (it >> 1) & 1, 100);
             const TcItem &I = S.item[par];
             if (!I.valid) break;
-            const int t0 = I.t0, t1 = I.t1, N = I.N, nq = I.nq, n_real = I.n_real;
+            const int t0 = I.t0, t1 = I.t1, N = I.N, nq = I.nq, n_real = I.n_real, nh = N >> 1;
             const long long tile0 = I.tile0;
             const uint8_t *B = Bslab + (size_t)par * SLAB;
-            const int first = t0 + (int)((pb - g) & 1);
-            for (int t = first; t < t1; t += 2, k_tile++) {
-                const uint32_t gg = g + (uint32_t)(t - t0), ph = (gg >> 1) & 1;
-                uint32_t *outT = S.outT[pb][k_tile & 1];
-                const long long b0_ = clock64();
-                mbar_wait(&S.o_empty[pb][k_tile & 1], ((k_tile >> 1) & 1) ^ 1);   // written out two own tiles ago
-                const long long c0_ = clock64();
-                pk[2] += c0_ - b0_;
-                mbar_wait(&S.d_full[pb], ph);
-                tc_fence_after();
-                const long long c1_ = clock64();
-                // 16 query columns per step (a group has a multiple of 16); the loads of the next step are issued before this step's
-                // arithmetic, and the accumulators go back to the MMA issuer as soon as the last load has landed, not after the whole
-                // epilogue. Small loop body on purpose.
-                {
-                    uint32_t a[16], c[16];
-                    tmem_ld16(tmem + lane_base + D_COL0 + (2 * pb) * TC_NT, a);
-                    tmem_ld16(tmem + lane_base + D_COL0 + (2 * pb + 1) * TC_NT, c);
-#pragma unroll 1
-                    for (int n0 = 0; n0 < N; n0 += 16) {
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        uint32_t pa[8], pc[8];                        // lane sums of two queries per register (s16x2: |S| <= 16 * 128)
+            const int first = t0 + (int)((h - g) & 1);               // this half's first tile of the item: (g + first - t0) & 1 == h
+            const uint32_t *tb = nat32 + ((size_t)tile0 * PH * 8 + s) * 4 + (gq >> 1) + (size_t)sub * PW * 32;
+            uint32_t *outT = S.outT[h];
+            // The estimates a warp computed (its 32 vectors x its half of the queries) lie transposed in shared memory; the same warp
+            // writes them out: lane = (query pair, one of the warp's two chunks): 16 words in, 2 x 16 bytes out. No barrier: a warp
+            // reads back only what it wrote itself.
+            auto copy_out = [&](int t) {
+                __syncwarp();
+                if (lane < nh) {
+                    const int n = sub * nh + 2 * (lane >> 1), sc = 2 * (warp & 3) + (lane & 1);
+                    const int chunk = t * 8 + sc;
+                    if (chunk < n_real && n < nq) {
+                        uint32_t w[16];
 #pragma unroll
-                        for (int u = 0; u < 8; u++) { pa[u] = prmt(a[2 * u], a[2 * u + 1], 0x5410u); pc[u] = prmt(c[2 * u], c[2 * u + 1], 0x5410u); }
-                        if (n0 + 16 < N) {
-                            tmem_ld16(tmem + lane_base + D_COL0 + (2 * pb) * TC_NT + n0 + 16, a);
-                            tmem_ld16(tmem + lane_base + D_COL0 + (2 * pb + 1) * TC_NT + n0 + 16, c);
-                        } else {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&S.d_empty[pb]);
-                        }
+                        for (int kk = 0; kk < 16; kk++) w[kk] = outT[tc_out_addr(16 * sc + kk, n >> 2)];
 #pragma unroll
-                        for (int h = 0; h < 2; h++) {                 // 8 queries each
-                            const int n8 = n0 + 8 * h;
-                            uint32_t e2[4], fl = 0x80008000u;
+                        for (int j = 0; j < 2; j++) {
+                            if (n + j >= nq) break;
+                            const uint32_t sel = 0x0040u + 0x0011u * (uint32_t)((n & 2) + j);   // (w0.byte b, w1.byte b), b = (n + j) % 4
+                            uint32_t o[4];
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {             // two queries per step, s16x2
-                                const uint2 k = I.kq2[(n8 >> 1) + u];
-                                e2[u] = __vimin3_s16x2(__viaddmax_s16x2(pa[4 * h + u], pc[4 * h + u], 0xff80ff80u), 0x007f007fu, 0x007f007fu);
-                                fl = __vimax3_s16x2(fl, __vsub2(pa[4 * h + u], k.x), __vsub2(pc[4 * h + u], k.y));
+                            for (int q4 = 0; q4 < 4; q4++) {          // that byte of four consecutive rows
+                                const uint32_t lo = prmt(w[4 * q4], w[4 * q4 + 1], sel), hi = prmt(w[4 * q4 + 2], w[4 * q4 + 3], sel);
+                                o[q4] = prmt(lo, hi, 0x5410u);
                             }
-                            uint32_t o0 = prmt(e2[0], e2[1], 0x6420u), o1 = prmt(e2[2], e2[3], 0x6420u);
-                            if (__any_sync(FULL, (int)(int16_t)(fl & 0xffffu) > 0 || (int)(int16_t)(fl >> 16) > 0))
-                                tc_flagged8<PH>(S, I.kq2, make_uint4(pa[4 * h], pa[4 * h + 1], pa[4 * h + 2], pa[4 * h + 3]),
-                                                make_uint4(pc[4 * h], pc[4 * h + 1], pc[4 * h + 2], pc[4 * h + 3]), n8, nq, t - t0, row, o0, o1,
-                                                nat32, tile0 + t, B);
-                            outT[tc_out_addr(row, n8 >> 2)] = o0;
-                            outT[tc_out_addr(row, (n8 >> 2) + 1)] = o1;
+                            const long long off = I.dst[n + j] + 16LL * chunk;
+                            *reinterpret_cast<uint4 *>(est + off) = make_uint4(o[0], o[1], o[2], o[3]);
+                            if (cmin) {
+                                uint32_t m = __vmins4(__vmins4(o[0], o[1]), __vmins4(o[2], o[3]));
+                                m = __vmins4(m, m >> 16);
+                                m = __vmins4(m, m >> 8);
+                                cmin[off >> 4] = (uint8_t)(m & 0xffu);
+                            }
                         }
                     }
                 }
-                const long long c2_ = clock64();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&S.o_full[pb][k_tile & 1]);   // the expansion half writes the tile out
-                pk[0] += c1_ - c0_; pk[1] += c2_ - c1_;
+            };
+            for (int t = first; t < t1; t += 2, k_tile++) {
+                const uint32_t ph = (k_tile & 1);                    // the half's buffers complete one phase per own tile
+                const long long c0_ = clock64();
+                // ---- expand: this thread's vector, this warp's half of the sub-quantizer pairs ------------------------------
+                {
+                    uint32_t cur[2 * PW];
+#pragma unroll
+                    for (int p = 0; p < PW; p++) {
+                        cur[2 * p] = __ldg(tb + ((size_t)t * PH + p) * 32);
+                        cur[2 * p + 1] = __ldg(tb + ((size_t)t * PH + p) * 32 + 2);
+                    }
+#pragma unroll
+                    for (int p = 0; p < PW; p++) {
+                        uint32_t r[8];
+                        onehot_unit((cur[2 * p] >> sh) & 15u, r[0], r[1], r[2], r[3]);
+                        onehot_unit((cur[2 * p + 1] >> sh) & 15u, r[4], r[5], r[6], r[7]);
+                        tmem_st8(tmem + lane_base + h * A_COLS + 8 * (sub * PW + p), r);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.a_full[h]);
+                }
+                const long long c1_ = clock64();
+                // ---- while the MMA warp multiplies: write out this warp's part of the half's previous tile -----------------------
+                if (t != first) copy_out(t - 2);
+                const long long c2_ = clock64();
+                mbar_wait(&S.d_full[h], ph);
+                tc_fence_after();
+                const long long c3_ = clock64();
+                // ---- epilogue: this warp's half of the group's queries, 8 per step, loads one step ahead --------------------
+                {
+                    const int nb = sub * nh;
+                    uint32_t la[4], lc[4];                            // lane sums of two queries per register (s16x2: |S| <= 16 * 128)
+                    tmem_ld8_pack16(tmem + lane_base + D_COL0 + (2 * h) * TC_NT + nb, la);
+                    tmem_ld8_pack16(tmem + lane_base + D_COL0 + (2 * h + 1) * TC_NT + nb, lc);
+#pragma unroll 1
+                    for (int n0 = nb; n0 < nb + nh; n0 += 8) {
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        uint32_t pa[4], pc[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) { pa[u] = la[u]; pc[u] = lc[u]; }
+                        if (n0 + 8 < nb + nh) {
+                            tmem_ld8_pack16(tmem + lane_base + D_COL0 + (2 * h) * TC_NT + n0 + 8, la);
+                            tmem_ld8_pack16(tmem + lane_base + D_COL0 + (2 * h + 1) * TC_NT + n0 + 8, lc);
+                        }
+                        uint32_t e2[4], fl = 0x80008000u;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {                 // two queries per step; kq2 holds the NEGATED thresholds
+                            const uint2 k = I.kq2[(n0 >> 1) + u];
+                            e2[u] = __vimin3_s16x2(__viaddmax_s16x2(pa[u], pc[u], 0xff80ff80u), 0x007f007fu, 0x007f007fu);
+                            fl = __viaddmax_s16x2(pa[u], k.x, fl);
+                            fl = __viaddmax_s16x2(pc[u], k.y, fl);
+                        }
+                        uint32_t o0 = prmt(e2[0], e2[1], 0x6420u), o1 = prmt(e2[2], e2[3], 0x6420u);
+                        if (__any_sync(FULL, (int)(int16_t)(fl & 0xffffu) > 0 || (int)(int16_t)(fl >> 16) > 0))
+                            tc_flagged8<PH>(S, I.kq2, make_uint4(pa[0], pa[1], pa[2], pa[3]), make_uint4(pc[0], pc[1], pc[2], pc[3]), n0, nq,
+                                            t - t0, row, o0, o1, nat32, tile0 + t, B);
+                        outT[tc_out_addr(row, n0 >> 2)] = o0;
+                        outT[tc_out_addr(row, (n0 >> 2) + 1)] = o1;
+                    }
+                    tc_fence_before();                                // (orders the TMEM reads before the next tile's a_full arrive)
+                }
+                ck[0] += c1_ - c0_; ck[4] += c2_ - c1_; ck[1] += c3_ - c2_; ck[2] += clock64() - c3_;
             }
+            if (first < t1) copy_out(first + 2 * ((t1 - 1 - first) >> 1));      // the half's last tile of the item
             g += (uint32_t)(t1 - t0);
-            const long long f0_ = clock64();
-            for (uint32_t back = 1; back <= 2 && back <= k_tile; back++) {   // (waiting again for an older phase returns at once)
-                const uint32_t k = k_tile - back;
-                mbar_wait(&S.o_empty[pb][k & 1], (k >> 1) & 1);
-            }
             // the item's refold queue (both halves together): the reference's recurrence for the pairs whose certificate failed,
             // bytes patched in place (the refolded value is never above the provisional one: a chunk minimum can only go down)
-            asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
+            const long long f0_ = clock64();
+            asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_WORKERS) : "memory");
             {
                 const int nqd = min(S.n_queue, TC_QUEUE);
-                for (int i = ptid; i < nqd; i += 32 * TC_P_WARPS) {
+                for (int i = tid; i < nqd; i += 32 * TC_WORKERS) {
                     const uint32_t en = S.queue[i];
                     const int tt = t0 + (int)(en >> 16), r = (int)((en >> 8) & 0xffu), n = (int)(en & 0xffu);
                     if (tt * 8 + (r >> 4) >= n_real) continue;       // a padding vector of the last tile: never written
@@ -722,15 +677,18 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     est[off] = (uint8_t)e;
                     if (cmin) atomic_min_s8(cmin + (off >> 4), e);
                 }
-                asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
-                if (ptid == 0) { if (S.n_queue) atomicAdd(W.hdr + 2, S.n_queue); S.n_queue = 0; }
-                asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_P_WARPS) : "memory");
+                asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_WORKERS) : "memory");
+                if (tid == 0) { if (S.n_queue) atomicAdd(W.hdr + 2, S.n_queue); S.n_queue = 0; }
+                asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_WORKERS) : "memory");
             }
-            pk[4] += clock64() - f0_;
+            if (warp == 0 && lane == 0) atomicAdd(W.clk + CK_P_FLUSH, (unsigned long long)(clock64() - f0_));
             if (lane == 0) mbar_arrive(&S.item_empty[par]);
         }
-        if (warp == TC_E_WARPS && lane == 0)
-            for (int i = 0; i < 5; i++) atomicAdd(W.clk + CK_P_WAIT + i, (unsigned long long)pk[i]);
+        if (warp == 0 && lane == 0) {
+            atomicAdd(W.clk + CK_E_WORK, (unsigned long long)ck[0]); atomicAdd(W.clk + CK_P_WAIT, (unsigned long long)ck[1]);
+            atomicAdd(W.clk + CK_P_EPI, (unsigned long long)ck[2]); atomicAdd(W.clk + CK_P_BAR, (unsigned long long)ck[3]);
+            atomicAdd(W.clk + CK_P_COPY, (unsigned long long)ck[4]);
+        }
     }
     tc_fence_before();
     __syncthreads();
