@@ -260,12 +260,15 @@ TKB_API int tkb_ivf_scan_native_cm_dev(const void *native, const int64_t *list_c
  * tkb_ivf_scan_native_cm_dev: signed tables, avx accumulation order (ref: _fast_pq_256.pyx:126-156), M = 32. Pairs the
  * tensor-core path cannot certify are refolded step by step; queries whose LUT fails the per-query precondition are scanned
  * by the CUDA-core kernel inside the same call. workspace: tkb_ivf_scan_tc_workspace bytes, 16-byte aligned; afterwards its
- * third int32 holds the number of refolded (vector, query) pairs. Worth it when several queries probe the same list. */
+ * third int32 holds the number of refolded (vector, query) pairs. Worth it when several queries probe the same list.
+ * Inside the push exchange: est == NULL, seg_off = absolute addresses (tkb_ivf_plan_push_dev), cm_home / q_per_rank as for
+ * tkb_ivf_scan_native_push_cm_dev (cm_home may be NULL: no minima); otherwise cm_home == NULL, q_per_rank == 0. */
+TKB_API int tkb_ivf_scan_tc_supported(void);      /* 1: the current device has tcgen05 tensor cores (compute capability 10.x) */
 TKB_API int tkb_ivf_scan_tc_workspace(int Q, int P, int n_lists, int64_t *bytes);
 TKB_API int tkb_ivf_scan_tc_dev(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                         const uint8_t *tables, const int32_t *probes, int Q, int P,
-                        uint8_t *est, const int64_t *seg_off, uint8_t *cmin, int64_t max_chunks_per_query,
-                        void *workspace, int64_t workspace_bytes, void *stream);
+                        uint8_t *est, const int64_t *seg_off, uint8_t *cmin, const int64_t *cm_home, int q_per_rank,
+                        int64_t max_chunks_per_query, void *workspace, int64_t workspace_bytes, void *stream);
 /* The same scan inside the push exchange (est == NULL, seg_addr = absolute addresses from tkb_ivf_plan_push_dev): the
  * minima of a segment go to the home rank's minima region. cm_home int64[n_ranks] (device): for home rank h,
  * (address of its minima region) - (address of its estimate buffer >> 4), both as mapped in THIS process; the home rank of

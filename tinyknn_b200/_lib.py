@@ -48,8 +48,9 @@ SIGNATURES = {
     "tkb_ivf_replay_dev": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp],
     "tkb_replay_fresh_dev": [_vp, _i64, _i64, _i, _vp, _vp, _i, _i, _i, _vp],
     "tkb_ivf_replay_fresh_dev": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "tkb_ivf_scan_tc_supported": [],
     "tkb_ivf_scan_tc_workspace": [_i, _i, _i, _c.POINTER(_c.c_int64)],
-    "tkb_ivf_scan_tc_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp],
+    "tkb_ivf_scan_tc_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i64, _vp, _i64, _vp],
     "tkb_ivf_scan_native_cm_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp],
     "tkb_ivf_scan_native_push_cm_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i64, _i, _i, _vp, _i64, _vp],
     "tkb_ivf_replay_fresh_cm_dev": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
@@ -70,14 +71,25 @@ class TinyKnnError(RuntimeError):
 def _load():
     from . import build as _build
     if _build.needs_build():
-        # sources changed (or first use): rebuild in-tree when a compiler is around
+        # sources changed (or first use): rebuild in-tree when a compiler is around. One process at a time (torchrun starts
+        # every rank at once: they would all write the same object files), the others wait for the lock and find it built.
+        import fcntl
+        lock = open(LIB_PATH + ".lock", "w")
         try:
-            _build.build(force=True)
-        except Exception as e:                                   # noqa: BLE001
-            if not os.path.exists(LIB_PATH):
-                raise ImportError(
-                    "tinyknn_b200: %s is missing and could not be built (%s). Build it with "
-                    "`python -m tinyknn_b200.build` (nvcc, sm_100a). There is no CPU fallback." % (LIB_PATH, e))
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            if _build.needs_build():
+                try:
+                    _build.build(force=True)
+                except Exception as e:                               # noqa: BLE001
+                    # never load a library built from OTHER sources: a changed C signature under an unchanged symbol name would
+                    # get mis-typed ctypes arguments. TKB_ALLOW_STALE_LIB=1 overrides (no compiler on this machine, sources touched).
+                    if not os.path.exists(LIB_PATH) or os.environ.get("TKB_ALLOW_STALE_LIB", "0") == "0":
+                        raise ImportError(
+                            "tinyknn_b200: %s is missing or older than its sources and could not be built (%s). Build it with "
+                            "`python -m tinyknn_b200.build` (nvcc, sm_100a). There is no CPU fallback." % (LIB_PATH, e))
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+            lock.close()
     lib = ctypes.CDLL(LIB_PATH)
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export the symbol

@@ -296,6 +296,11 @@ int tkb_ivf_scan_native_dev(const void *native, const int64_t *list_chunk_off, c
                                   seg_off, max_chunks_per_query, order, signd, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int tkb_ivf_scan_tc_supported(void)
+{
+    return tc_supported();
+}
+
 int tkb_ivf_scan_tc_workspace(int Q, int P, int n_lists, int64_t *bytes)
 {
     return tc_workspace_bytes(Q, P, n_lists, bytes);
@@ -303,11 +308,11 @@ int tkb_ivf_scan_tc_workspace(int Q, int P, int n_lists, int64_t *bytes)
 
 int tkb_ivf_scan_tc_dev(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                         const uint8_t *tables, const int32_t *probes, int Q, int P,
-                        uint8_t *est, const int64_t *seg_off, uint8_t *cmin, int64_t max_chunks_per_query,
-                        void *workspace, int64_t workspace_bytes, void *stream)
+                        uint8_t *est, const int64_t *seg_off, uint8_t *cmin, const int64_t *cm_home, int q_per_rank,
+                        int64_t max_chunks_per_query, void *workspace, int64_t workspace_bytes, void *stream)
 {
-    return launch_ivf_scan_tc(native, list_chunk_off, list_size, n_lists, M, tables, probes, Q, P, est, seg_off, cmin,
-                              max_chunks_per_query, workspace, workspace_bytes, (cudaStream_t)stream);
+    return launch_ivf_scan_tc(native, list_chunk_off, list_size, n_lists, M, tables, probes, Q, P, est, seg_off, cmin, cm_home,
+                              q_per_rank, max_chunks_per_query, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int tkb_heap_fill_dev(int64_t *heap_idx, int32_t *heap_val, int64_t count, int signd, void *stream)

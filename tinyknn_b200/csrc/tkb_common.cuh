@@ -124,10 +124,12 @@ int launch_ivf_scan_native(const void *native, const int64_t *list_chunk_off, co
                            int64_t slot_stride, const int64_t *seg_off, int64_t max_chunks_per_query, int order, int signd,
                            void *workspace, int64_t workspace_bytes, cudaStream_t st, uint8_t *cmin = nullptr,
                            const int64_t *cm_home = nullptr, int q_per_rank = 0, const uint8_t *skip_q = nullptr);
+int tc_supported();
 int tc_workspace_bytes(int Q, int P, int n_lists, int64_t *bytes);
 int launch_ivf_scan_tc(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                        const uint8_t *tables, const int32_t *probes, int Q, int P, uint8_t *est, const int64_t *seg_off,
-                       uint8_t *cmin, int64_t max_chunks_per_query, void *workspace, int64_t workspace_bytes, cudaStream_t st);
+                       uint8_t *cmin, const int64_t *cm_home, int q_per_rank, int64_t max_chunks_per_query, void *workspace,
+                       int64_t workspace_bytes, cudaStream_t st);
 int launch_heap_fill(int64_t *heap_idx, int32_t *heap_val, int64_t count, int signd, cudaStream_t st);
 int launch_replay(const uint8_t *est, int64_t est_stride, int64_t n_chunks, int n, int64_t *heap_idx,
                   int32_t *heap_val, int Q, int R, int signd, const int64_t *labels, cudaStream_t st);

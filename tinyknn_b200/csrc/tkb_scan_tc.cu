@@ -305,7 +305,8 @@ struct TcItem {
     long long tile0;                            // first tile of the list in the code array
     int q_of[TC_NT];                            // query of group member i (-1: padding column)
     uint2 kq2[TC_NT / 2];                       // NEGATED certificate thresholds of query pairs: .x = (-k0[2i], -k0[2i+1]), .y = (-k1[..]), s16x2
-    long long dst[TC_NT];                       // est offset of its segment
+    long long dst[TC_NT];                       // est offset of its segment (an absolute address inside the push exchange)
+    unsigned long long cmb[TC_NT];              // base of the chunk minima its segment belongs to (0: none)
 };
 
 struct TcShared {
@@ -398,7 +399,8 @@ template <int PH>
 __global__ void __launch_bounds__(TC_THREADS2, 1)
 ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict__ list_chunk_off,
                    const int32_t *__restrict__ list_size, int n_lists, const uint8_t *__restrict__ tables, int P,
-                   uint8_t *__restrict__ est, const int64_t *__restrict__ seg_off, uint8_t *__restrict__ cmin, TcWork W)
+                   uint8_t *__restrict__ est, const int64_t *__restrict__ seg_off, uint8_t *__restrict__ cmin,
+                   const int64_t *__restrict__ cm_home, int q_per_rank, TcWork W)
 {
     constexpr int M = 2 * PH;
     constexpr int A_COLS = 8 * PH;                                   // 32-bit columns of one one-hot tile
@@ -473,6 +475,8 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     k0 = m.k0; k1 = m.k1;
                 }
                 I.q_of[i] = q; I.dst[i] = d;
+                // push exchange: the minima region of the query's home rank, addressed like the estimates (address >> 4)
+                I.cmb[i] = q < 0 ? 0ull : (cm_home ? (unsigned long long)cm_home[q / q_per_rank] : (unsigned long long)(uintptr_t)cmin);
                 reinterpret_cast<uint16_t *>(I.kq2)[4 * (i >> 1) + (i & 1)] = (uint16_t)(int16_t)(-k0);          // negated: the epilogue adds
                 reinterpret_cast<uint16_t *>(I.kq2)[4 * (i >> 1) + 2 + (i & 1)] = (uint16_t)(int16_t)(-k1);
             }
@@ -584,11 +588,12 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                             }
                             const long long off = I.dst[n + j] + 16LL * chunk;
                             *reinterpret_cast<uint4 *>(est + off) = make_uint4(o[0], o[1], o[2], o[3]);
-                            if (cmin) {
+                            uint8_t *cm = reinterpret_cast<uint8_t *>((uintptr_t)I.cmb[n + j]);
+                            if (cm) {
                                 uint32_t m = __vmins4(__vmins4(o[0], o[1]), __vmins4(o[2], o[3]));
                                 m = __vmins4(m, m >> 16);
                                 m = __vmins4(m, m >> 8);
-                                cmin[off >> 4] = (uint8_t)(m & 0xffu);
+                                cm[off >> 4] = (uint8_t)(m & 0xffu);
                             }
                         }
                     }
@@ -675,7 +680,8 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     const int e = tc_refold<PH>(nat32, tile0 + tt, r, B + (size_t)n * 16);
                     const long long off = I.dst[n] + 128LL * tt + r;
                     est[off] = (uint8_t)e;
-                    if (cmin) atomic_min_s8(cmin + (off >> 4), e);
+                    uint8_t *cm = reinterpret_cast<uint8_t *>((uintptr_t)I.cmb[n]);
+                    if (cm) atomic_min_s8(cm + (off >> 4), e);
                 }
                 asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_WORKERS) : "memory");
                 if (tid == 0) { if (S.n_queue) atomicAdd(W.hdr + 2, S.n_queue); S.n_queue = 0; }
@@ -698,6 +704,22 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
 #endif  // TKB_EMULATE
 
 // ---- host side -------------------------------------------------------------------------------------------------------
+// 1 when this build can run the tensor-core scan on the current device (an sm_100 GPU; never on the CPU emulator)
+int tc_supported()
+{
+#ifdef TKB_EMULATE
+    return 0;
+#else
+    static int ok = -1;
+    if (ok < 0) {
+        int dev = 0, major = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+        ok = major == 10 ? 1 : 0;
+    }
+    return ok;
+#endif
+}
+
 int tc_workspace_bytes(int Q, int P, int n_lists, int64_t *bytes)
 {
     TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists >= 0 && bytes, "bad extent");
@@ -707,7 +729,8 @@ int tc_workspace_bytes(int Q, int P, int n_lists, int64_t *bytes)
 
 int launch_ivf_scan_tc(const void *native, const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, int M,
                        const uint8_t *tables, const int32_t *probes, int Q, int P, uint8_t *est, const int64_t *seg_off,
-                       uint8_t *cmin, int64_t max_chunks_per_query, void *workspace, int64_t workspace_bytes, cudaStream_t st)
+                       uint8_t *cmin, const int64_t *cm_home, int q_per_rank, int64_t max_chunks_per_query, void *workspace,
+                       int64_t workspace_bytes, cudaStream_t st)
 {
 #ifdef TKB_EMULATE
     return set_err(TKB_ERR_INVALID, "the tensor-core scan needs an sm_100a device (not available on the CPU emulator)");
@@ -715,7 +738,9 @@ int launch_ivf_scan_tc(const void *native, const int64_t *list_chunk_off, const 
     TKB_REQUIRE(M == 32, "the tensor-core scan is built for M = 32 sub-quantizers (d = 128 rotated to 64)");
     TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists > 0, "bad extent");
     if (Q == 0 || P == 0) return TKB_OK;
-    TKB_REQUIRE(native && list_chunk_off && list_size && tables && probes && est && seg_off && workspace, "null pointer");
+    // est == NULL: the plan holds absolute addresses (push exchange: segments land in the home ranks' peer-mapped buffers)
+    TKB_REQUIRE(native && list_chunk_off && list_size && tables && probes && seg_off && workspace, "null pointer");
+    TKB_REQUIRE(!cm_home || (!est && !cmin && q_per_rank > 0), "per-home minima tables belong to the push exchange (est == NULL)");
     TKB_REQUIRE((int64_t)Q * P <= 0x7fffffffLL, "too many (query, probe) units for one launch");
     TKB_REQUIRE((uintptr_t)workspace % 16 == 0 && (uintptr_t)est % 16 == 0 && (uintptr_t)tables % 16 == 0, "pointers must be 16-byte aligned");
     int64_t need = 0;
@@ -745,12 +770,12 @@ int launch_ivf_scan_tc(const void *native, const int64_t *list_chunk_off, const 
     const size_t smem_req = smem > 120 * 1024 ? smem : 120 * 1024;
     TKB_CUDA(cudaFuncSetAttribute(ivf_scan_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
     ivf_scan_tc_kernel<16><<<n_sm, TC_THREADS2, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native), list_chunk_off, list_size,
-                                                                n_lists, tables, P, est, seg_off, cmin, W);
+                                                                n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W);
     TKB_LAUNCH_CHECK();
     // the (query, list) pairs the tensor-core path does not take (queries whose LUT fails the per-query precondition):
     // the CUDA-core kernel, which skips every query marked in skip_q
     return launch_ivf_scan_native(native, list_chunk_off, list_size, n_lists, M, tables, probes, Q, P, est, 0, W.seg_rest,
-                                  max_chunks_per_query, TKB_ORDER_AVX, 1, nullptr, 0, st, cmin, nullptr, 0, W.skip_q);
+                                  max_chunks_per_query, TKB_ORDER_AVX, 1, nullptr, 0, st, cmin, cm_home, q_per_rank, W.skip_q);
 #endif
 }
 

@@ -47,7 +47,7 @@ COARSE_FUSED = os.environ.get("TKB_COARSE_FUSED", "0") != "0"
 ASSIGN_DEVICE = os.environ.get("TKB_ASSIGN_DEVICE", "0") != "0"
 # List-major scan on the tensor cores (tkb_ivf_scan_tc_dev; csrc/tkb_scan_tc.cu): "0" never, "1" whenever the kernel applies
 # (M = 32, avx order), "auto" = when the batch puts at least TC_MIN_SHARE queries on an average list.
-TC_SCAN = os.environ.get("TKB_TC_SCAN", "0")
+TC_SCAN = os.environ.get("TKB_TC_SCAN", "auto")
 TC_MIN_SHARE = float(os.environ.get("TKB_TC_MIN_SHARE", "6"))
 _streams = {}
 _ws_cap = {}
@@ -99,7 +99,7 @@ def _fresh(name, shape, np_dtype):
 def _tc_applies(dev, Q, P):
     """The tensor-core scan is built for M = 32 in the avx accumulation order and pays off when several queries of the
     batch probe the same list."""
-    if TC_SCAN == "0" or dev["M"] != 32 or _fp._order() != 1 or _fp.SCAN_IMPL != "fast":
+    if TC_SCAN == "0" or dev["M"] != 32 or _fp._order() != 1 or _fp.SCAN_IMPL != "fast" or not lib.tkb_ivf_scan_tc_supported():
         return False
     return TC_SCAN == "1" or Q * P >= TC_MIN_SHARE * max(1, dev["C"])
 
@@ -449,8 +449,7 @@ class IVF:
         with self._stage("scan"):
             if _fp.SCAN_IMPL == "fast":
                 ws = buf("scan_ws", (64,), np.uint8)                     # its first 8 bytes count the recomputed chunks
-                use_tc = (push_cm is None and est is not None and seg_off is not None and codes_key == "codes"
-                          and _tc_applies(dev, Q, P))
+                use_tc = seg_off is not None and _tc_applies(dev, Q, P)
                 if use_tc:
                     import ctypes
                     need = ctypes.c_int64(0)
@@ -458,6 +457,7 @@ class IVF:
                     tws = buf("tc_ws", (need.value,), np.uint8)
                     check(lib.tkb_ivf_scan_tc_dev(D.ptr(dev[codes_key]), D.ptr(dev[off_key]), D.ptr(dev["list_size"]), n_lists, M,
                                                   D.ptr(tables), D.ptr(probes), Q, P, D.ptr(est), D.ptr(seg_off), D.ptr(cmin),
+                                                  None if push_cm is None else D.ptr(push_cm[0]), 0 if push_cm is None else push_cm[1],
                                                   max_q_chunks, D.ptr(tws), tws.numel(), st))
                     self._last["tc_ws"] = tws
                 elif push_cm is not None:                                # (per-home minima table, queries per rank)
