@@ -314,8 +314,9 @@ struct TcShared {
     uint32_t tmem_base;
     int n_queue;
     TcItem item[2];
-    uint32_t outT[2][128 * TC_OUT_STRIDE];      // [half]: row = vector, byte n = query n of the group (a warp reads back only what it wrote)
+    uint32_t outT[2][2][128 * TC_OUT_STRIDE];   // [half][tile parity, WIDE only]: row = vector, byte n = query n of the group
     uint32_t queue[TC_QUEUE];                   // (tile << 16) | (row << 8) | query column of the pairs whose certificate failed
+    uint8_t refold_mark[2][8][TC_NT];           // push exchange: (half, chunk of the tile, query) holds a pair that will be refolded
 };
 
 // the reference's fold of one (vector, query): codes from the code array, LUT rows from the slab
@@ -359,7 +360,7 @@ __device__ __forceinline__ void atomic_min_s8(uint8_t *addr, int v)
 template <int PH>
 __device__ __noinline__ void tc_flagged8(TcShared &S, const uint2 *kq2, uint4 pa, uint4 pc, int n0, int nq, int t_rel, int row,
                                          uint32_t &o0, uint32_t &o1, const uint32_t *__restrict__ nat32, long long tile,
-                                         const uint8_t *B)
+                                         const uint8_t *B, uint8_t *mark /* [8][TC_NT] of this half, or null */)
 {
     const uint32_t pas[4] = {pa.x, pa.y, pa.z, pa.w}, pcs[4] = {pc.x, pc.y, pc.z, pc.w};
     const int lane = threadIdx.x & 31;
@@ -385,8 +386,10 @@ __device__ __noinline__ void tc_flagged8(TcShared &S, const uint2 *kq2, uint4 pa
     while (mask) {
         const int u = __ffs(mask) - 1;
         mask &= mask - 1;
-        if (base < TC_QUEUE) S.queue[base] = ((uint32_t)t_rel << 16) | ((uint32_t)row << 8) | (uint32_t)(n0 + u);
-        else {
+        if (base < TC_QUEUE) {
+            S.queue[base] = ((uint32_t)t_rel << 16) | ((uint32_t)row << 8) | (uint32_t)(n0 + u);
+            if (mark) mark[(row >> 4) * TC_NT + n0 + u] = 1;
+        } else {
             const int e = tc_refold<PH>(nat32, tile, row, B + (size_t)(n0 + u) * 16);
             uint32_t &o = u < 4 ? o0 : o1;
             o = (o & ~(0xffu << (8 * (u & 3)))) | ((uint32_t)(e & 0xff) << (8 * (u & 3)));
@@ -395,7 +398,10 @@ __device__ __noinline__ void tc_flagged8(TcShared &S, const uint2 *kq2, uint4 pa
     }
 }
 
-template <int PH>
+// WIDE: the half writes a tile out together (one barrier per tile), 8 consecutive lanes = the 128 contiguous bytes a tile holds for
+// one query -- full lines for the peer-mapped buffers of the push exchange, where 32-byte stores waste NVLink; otherwise every warp
+// writes out what it computed itself (32-byte pieces, no barrier), which is faster into local memory.
+template <int PH, bool WIDE>
 __global__ void __launch_bounds__(TC_THREADS2, 1)
 ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict__ list_chunk_off,
                    const int32_t *__restrict__ list_size, int n_lists, const uint8_t *__restrict__ tables, int P,
@@ -424,6 +430,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             mbar_init(&S.d_full[b], 1);
         }
         S.n_queue = 0;
+        for (int i = 0; i < 2 * 8 * TC_NT; i++) (&S.refold_mark[0][0][0])[i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -563,13 +570,49 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             const uint8_t *B = Bslab + (size_t)par * SLAB;
             const int first = t0 + (int)((h - g) & 1);               // this half's first tile of the item: (g + first - t0) & 1 == h
             const uint32_t *tb = nat32 + ((size_t)tile0 * PH * 8 + s) * 4 + (gq >> 1) + (size_t)sub * PW * 32;
-            uint32_t *outT = S.outT[h];
+            const int htid = tid - 256 * h;                          // 0..255 inside the half
             // The estimates a warp computed (its 32 vectors x its half of the queries) lie transposed in shared memory; the same warp
             // writes them out: lane = (query pair, one of the warp's two chunks): 16 words in, 2 x 16 bytes out. No barrier: a warp
             // reads back only what it wrote itself.
-            auto copy_out = [&](int t) {
+            auto copy_out = [&](int t, const uint32_t *outT) {
+                if (WIDE) {
+                    // the whole half, after its barrier: a task = 2 queries x one chunk, the chunk fastest: 8 lanes write 128 contiguous bytes
+                    for (int task = htid; task < ((nq + 1) >> 1) * 8; task += 256) {
+                        const int n = 2 * (task >> 3), sc = task & 7;
+                        const int chunk = t * 8 + sc;
+                        if (chunk >= n_real) continue;
+                        uint32_t w[16];
+#pragma unroll
+                        for (int kk = 0; kk < 16; kk++) w[kk] = outT[tc_out_addr(16 * sc + kk, n >> 2)];
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            if (n + j >= nq) break;
+                            const uint32_t sel = 0x0040u + 0x0011u * (uint32_t)((n & 2) + j);
+                            uint32_t o[4];
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; q4++) {
+                                const uint32_t lo = prmt(w[4 * q4], w[4 * q4 + 1], sel), hi = prmt(w[4 * q4 + 2], w[4 * q4 + 3], sel);
+                                o[q4] = prmt(lo, hi, 0x5410u);
+                            }
+                            const long long off = I.dst[n + j] + 16LL * chunk;
+                            *reinterpret_cast<uint4 *>(est + off) = make_uint4(o[0], o[1], o[2], o[3]);
+                            uint8_t *cm = reinterpret_cast<uint8_t *>((uintptr_t)I.cmb[n + j]);
+                            if (cm) {
+                                uint32_t m = __vmins4(__vmins4(o[0], o[1]), __vmins4(o[2], o[3]));
+                                m = __vmins4(m, m >> 16);
+                                m = __vmins4(m, m >> 8);
+                                // the minima live in another GPU's memory, where the atomic minimum of the refold pass would be a round
+                                // trip over NVLink per pair: a chunk with a pair still to be refolded gets the smallest possible minimum
+                                // instead, which only makes the replay look at its 16 estimates (exact by then)
+                                if (cm_home && S.refold_mark[h][sc][n + j]) { m = 0x80u; S.refold_mark[h][sc][n + j] = 0; }
+                                cm[off >> 4] = (uint8_t)(m & 0xffu);
+                            }
+                        }
+                    }
+                    return;
+                }
                 __syncwarp();
-                if (lane < nh) {
+                if (lane < nh) {                                      // lane = (query pair, one of the warp's two chunks)
                     const int n = sub * nh + 2 * (lane >> 1), sc = 2 * (warp & 3) + (lane & 1);
                     const int chunk = t * 8 + sc;
                     if (chunk < n_real && n < nq) {
@@ -624,8 +667,9 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     if (lane == 0) mbar_arrive(&S.a_full[h]);
                 }
                 const long long c1_ = clock64();
-                // ---- while the MMA warp multiplies: write out this warp's part of the half's previous tile -----------------------
-                if (t != first) copy_out(t - 2);
+                // ---- while the MMA warp multiplies: write out (this warp's part of) the half's previous tile --------------------------
+                if (WIDE) asm volatile("bar.sync %0, 256;" ::"r"(1 + h) : "memory");   // everybody's epilogue of that tile is in outT
+                if (t != first) copy_out(t - 2, S.outT[h][WIDE ? (k_tile - 1) & 1 : 0]);
                 const long long c2_ = clock64();
                 mbar_wait(&S.d_full[h], ph);
                 tc_fence_after();
@@ -633,6 +677,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                 // ---- epilogue: this warp's half of the group's queries, 8 per step, loads one step ahead --------------------
                 {
                     const int nb = sub * nh;
+                    uint32_t *outT = S.outT[h][WIDE ? k_tile & 1 : 0];
                     uint32_t la[4], lc[4];                            // lane sums of two queries per register (s16x2: |S| <= 16 * 128)
                     tmem_ld8_pack16(tmem + lane_base + D_COL0 + (2 * h) * TC_NT + nb, la);
                     tmem_ld8_pack16(tmem + lane_base + D_COL0 + (2 * h + 1) * TC_NT + nb, lc);
@@ -657,7 +702,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                         uint32_t o0 = prmt(e2[0], e2[1], 0x6420u), o1 = prmt(e2[2], e2[3], 0x6420u);
                         if (__any_sync(FULL, (int)(int16_t)(fl & 0xffffu) > 0 || (int)(int16_t)(fl >> 16) > 0))
                             tc_flagged8<PH>(S, I.kq2, make_uint4(pa[0], pa[1], pa[2], pa[3]), make_uint4(pc[0], pc[1], pc[2], pc[3]), n0, nq,
-                                            t - t0, row, o0, o1, nat32, tile0 + t, B);
+                                            t - t0, row, o0, o1, nat32, tile0 + t, B, cm_home ? &S.refold_mark[h][0][0] : nullptr);
                         outT[tc_out_addr(row, n0 >> 2)] = o0;
                         outT[tc_out_addr(row, (n0 >> 2) + 1)] = o1;
                     }
@@ -665,7 +710,10 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                 }
                 ck[0] += c1_ - c0_; ck[4] += c2_ - c1_; ck[1] += c3_ - c2_; ck[2] += clock64() - c3_;
             }
-            if (first < t1) copy_out(first + 2 * ((t1 - 1 - first) >> 1));      // the half's last tile of the item
+            if (first < t1) {                                         // the half's last tile of the item
+                if (WIDE) asm volatile("bar.sync %0, 256;" ::"r"(1 + h) : "memory");
+                copy_out(first + 2 * ((t1 - 1 - first) >> 1), S.outT[h][WIDE ? (k_tile - 1) & 1 : 0]);
+            }
             g += (uint32_t)(t1 - t0);
             // the item's refold queue (both halves together): the reference's recurrence for the pairs whose certificate failed,
             // bytes patched in place (the refolded value is never above the provisional one: a chunk minimum can only go down)
@@ -681,7 +729,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     const long long off = I.dst[n] + 128LL * tt + r;
                     est[off] = (uint8_t)e;
                     uint8_t *cm = reinterpret_cast<uint8_t *>((uintptr_t)I.cmb[n]);
-                    if (cm) atomic_min_s8(cm + (off >> 4), e);
+                    if (cm && !cm_home) atomic_min_s8(cm + (off >> 4), e);
                 }
                 asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_WORKERS) : "memory");
                 if (tid == 0) { if (S.n_queue) atomicAdd(W.hdr + 2, S.n_queue); S.n_queue = 0; }
@@ -768,9 +816,15 @@ int launch_ivf_scan_tc(const void *native, const int64_t *list_chunk_off, const 
     // one CTA per SM (the kernel owns all 512 TMEM columns): the slab + the rest of the shared memory is padded past half an SM's
     const size_t smem = ((sizeof(TcShared) + 127) / 128) * 128 + 2 * (size_t)M * TC_NT * 16 + 128;
     const size_t smem_req = smem > 120 * 1024 ? smem : 120 * 1024;
-    TKB_CUDA(cudaFuncSetAttribute(ivf_scan_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
-    ivf_scan_tc_kernel<16><<<n_sm, TC_THREADS2, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native), list_chunk_off, list_size,
-                                                                n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W);
+    if (est == nullptr) {                         // push exchange: full 128-byte lines into the peer-mapped buffers
+        TKB_CUDA(cudaFuncSetAttribute(ivf_scan_tc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
+        ivf_scan_tc_kernel<16, true><<<n_sm, TC_THREADS2, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native), list_chunk_off,
+                                                                          list_size, n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W);
+    } else {
+        TKB_CUDA(cudaFuncSetAttribute(ivf_scan_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
+        ivf_scan_tc_kernel<16, false><<<n_sm, TC_THREADS2, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native), list_chunk_off,
+                                                                           list_size, n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W);
+    }
     TKB_LAUNCH_CHECK();
     // the (query, list) pairs the tensor-core path does not take (queries whose LUT fails the per-query precondition):
     // the CUDA-core kernel, which skips every query marked in skip_q
