@@ -622,7 +622,7 @@ def main():
         def scan_roof(ms, flagged):
             ab = scanned * (M // 2 + 1)
             return dict(kernel="ivf_scan_fast", achieved=ab / (ms * 1e-3) / 1e9, peak=peak, unit="GB/s",
-                        frac=ab / (ms * 1e-3) / 1e9 / peak, traffic=traffic_all.get("ivf_scan_fast"),
+                        frac=ab / (ms * 1e-3) / 1e9 / peak, traffic=traffic_all.get("ivf_scan_tc" if "tc_ws" in last else "ivf_scan_fast"),
                         algorithmic_bytes_per_launch=ab, kernel_ms=ms, codes_per_s=scanned / (ms * 1e-3), flagged_chunks=flagged)
 
         def counter(ws_key):

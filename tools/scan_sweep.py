@@ -86,6 +86,38 @@ def main():
                           frac=alg / (ms * 1e-3) / 1e9 / peak, algorithmic_bytes_per_launch=alg,
                           physical_lower_bound_bytes=code_bytes + pairs, flagged_chunks=flagged,
                           note="algorithmic bytes count the codes once per query; with Q > 1 the CTAs of a stripe share them in L2"))))
+        # the same estimates from the list-major tensor-core kernel (tkb_ivf_scan_tc_dev): the database as ONE inverted list that
+        # every query probes; bytes compared with the CUDA-core kernel's
+        if Q >= 16 and M == 32 and lib.tkb_ivf_scan_tc_supported():
+            import ctypes
+            tiles8 = -(-n_chunks // 8) * 8
+            off = torch.tensor([0, tiles8], dtype=torch.int64, device=dev)
+            size = torch.tensor([args.n], dtype=torch.int32, device=dev)
+            probes = torch.zeros((Q, 1), dtype=torch.int32, device=dev)
+            seg = (torch.arange(Q, dtype=torch.int64, device=dev) * (16 * n_chunks)).reshape(Q, 1).contiguous()
+            est2 = D.empty((Q, 16 * n_chunks), np.uint8)
+            need = ctypes.c_int64(0)
+            check(lib.tkb_ivf_scan_tc_workspace(Q, 1, 1, ctypes.byref(need)))
+            tws = D.empty((need.value,), np.uint8)
+            t_tc = []
+            for rep in range(args.reps + 1):
+                flush.zero_()
+                e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+                e0.record()
+                check(lib.tkb_ivf_scan_tc_dev(D.ptr(nat), D.ptr(off), D.ptr(size), 1, M, D.ptr(lut["tables"]), D.ptr(probes), Q, 1,
+                                              D.ptr(est2), D.ptr(seg), None, None, 0, n_chunks, D.ptr(tws), tws.numel(), st))
+                e1.record()
+                torch.cuda.synchronize()
+                if rep:
+                    t_tc.append(e0.elapsed_time(e1))
+            ms_tc = float(np.median(t_tc))
+            same = bool(torch.equal(est[:, :args.n], est2[:, :args.n]))
+            print(json.dumps(dict(
+                metric="PQ-scan codes/s", workload="FastPQ brute-force scan, %d x 128 synthetic codes (M=%d, %d B/vector), batch %d"
+                % (args.n, M, M // 2, Q), batch=Q, kernel="ivf_scan_tc (tcgen05.mma kind::i8, list-major)", value=pairs / (ms_tc * 1e-3),
+                unit="codes/s", ms=ms_tc, queries_per_s=Q / (ms_tc * 1e-3), speedup_over_cuda_core_scan=ms / ms_tc,
+                estimates_identical_to_cuda_core_scan=same, refolded_pairs=int(tws[:16].cpu().numpy().view(np.int32)[2]))))
+            del est2
         del est
     # CPU: the reference's kernel, one core, bounded sample
     try:
