@@ -68,9 +68,11 @@ def parse():
     ap.add_argument("--cpu-queries", type=int, default=2048,
                     help="workloads whose raw vectors stay on the GPU (10M/100M): the CPU arm cycles through this many queries of "
                          "the batch; the rows their rescoring reads are recorded in an untimed pass of the oracle and kept on the host")
-    ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
+    ap.add_argument("--exchange", default=os.environ.get("TKB_EXCHANGE", "push"), choices=["push", "pull", "nccl"],
                     help="--shard lists: 'push' = the scan kernel stores estimates into the home rank's HBM over NVLink peer "
-                         "memory (falls back to nccl when peer buffers cannot be mapped), 'nccl' = send buffer + all-to-all")
+                         "memory, 'pull' = estimates stay in the owner's HBM and the home rank's replay fetches chunk minima and "
+                         "candidate chunks over NVLink (both fall back to nccl when peer buffers cannot be mapped), "
+                         "'nccl' = send buffer + all-to-all")
     ap.add_argument("--no-e2e-pipeline", action="store_true",
                     help="skip e2e_pipelined (the same host-buffer loop with two batches in flight, query_batch(to_host='async'): "
                          "batch i+1 is submitted before batch i is collected)")
@@ -533,6 +535,12 @@ def main():
     sync_all()
     torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
+    if sharded:
+        engine.check_overflow()                        # pull exchange: no owner buffer overflowed in the timed steps (raises otherwise)
+        pb_ = engine.__dict__.get("_pb")
+        extra["peer_buffer_bytes"] = None if pb_ is None else int(pb_.nbytes)
+        extra["push_capacity_bytes"] = int(engine.push_capacity(Qn, min(args.n_probes, ivf.to_device()["C"])))
+        extra["pull_overflows"] = int(engine.__dict__.get("pull_overflows", 0))
     log("timed region done: %.3f ms/step" % (ms / args.steps))
     launches = _lib.launch_count() - calls0            # kernels launched by libtinyknn_b200.so in the timed region (counted in C)
     if graphed is not None:                            # replays do not pass through the C launch counter
@@ -549,6 +557,12 @@ def main():
     scan_log = list(ivf.__dict__.get("_scan_log") or [])
     blocks_per_step = max(1, len(scan_log) // n_prof)                # a batch larger than the estimate workspace runs in blocks
     scan_log = scan_log[-blocks_per_step:]
+    if "tc_ws" in last:                             # one more step with the role cycle counters compiled in (they cost registers: not in the timed steps)
+        os.environ["TKB_TC_CLOCKS"] = "1"
+        eager_run(dev_batches[(n_prof - 1) % 4], to_host=False, **one)
+        torch.cuda.synchronize()
+        os.environ.pop("TKB_TC_CLOCKS")
+        last["tc_ws_clk"] = ivf._last["tc_ws"][:32 + 8 * 13].clone()
     staged = None
     if "fused" in stages and not sharded:           # the stage-by-stage kernels of the same path, for the scan kernel's own roofline
         ivf.profile(True)
@@ -649,13 +663,13 @@ def main():
             roof = dict(bound="hbm", scanned_vectors_per_launch=scanned, launches_per_step=blocks_per_step,
                         **scan_roof(per_step(stages["scan"]), counter("patch_ws")))
         if "tc_ws" in last:
-            hdr = last["tc_ws"][:32].cpu().numpy().view(np.int32)
+            hdr = last["tc_ws_clk"][:32].cpu().numpy().view(np.int32)
             roof.update(kernel="ivf_scan_tc", tc_work_items=int(hdr[0]), tc_refolded_pairs=int(hdr[2]), tc_tiles=int(hdr[3]),
                         tc_mean_group_columns=16.0 * int(hdr[4]) / max(1, int(hdr[3])),
                         tc_role_cycles_per_tile={k_: round(float(v_) / max(1, int(hdr[3])) , 1) for k_, v_ in zip(
                             ("expand_wait", "expand_work", "mma_wait_a", "mma_wait_d", "mma_issue", "epi_wait", "epi_work", "epi_barrier",
                              "epi_copy", "epi_flush", "load_wait", "load_stage", "total"),
-                            last["tc_ws"][32:32 + 8 * 13].cpu().numpy().view(np.int64))},
+                            last["tc_ws_clk"][32:32 + 8 * 13].cpu().numpy().view(np.int64))},
                         note="list-major tensor-core scan (tcgen05.mma kind::i8): the code bytes are read once per list and batch, "
                              "so `achieved` (algorithmic bytes / time) is not bounded by the HBM peak; see `traffic`")
         code_bytes = dev["n_chunks_total"] * M * 8 if not sharded else extra.get("code_bytes_per_rank", 0)
@@ -674,8 +688,10 @@ def main():
                                                   cpu_queries=args.cpu_queries)
             cb["single_process"] = dict(value=cb1["value"], unit="queries/s", cores=1,
                                         note="the reference's own operating mode: one process, one thread (BASELINE.md 3, mode i)")
-        parallelism = (("lists sharded over %d ranks, %s" % (world, "estimates stored into the home rank's HBM by the scan kernel (NVLink peer memory)"
-                                                             if engine.last_exchange == "push" else "NCCL all-to-all of estimates"))
+        parallelism = (("lists sharded over %d ranks, %s" % (world, {
+            "push": "estimates stored into the home rank's HBM by the scan kernel (NVLink peer memory)",
+            "pull": "estimates kept in the owner's HBM, chunk minima and candidate chunks fetched by the home rank's replay (NVLink peer memory)",
+        }.get(engine.last_exchange, "NCCL all-to-all of estimates")))
                        if sharded else ("query-sharded replicas x%d" % world))
         l2 = ("estimate buffer rewritten every step and query batches rotate between steps; the codes %s (%d MB) %s"
               % ("this rank scans" if sharded else "of this workload", code_bytes >> 20,

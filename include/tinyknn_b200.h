@@ -153,6 +153,38 @@ TKB_API int tkb_ivf_plan_push_dev(const int32_t *probes, int Q, int P, const int
                           int n_lists, int rank, int n_ranks, int q_per_rank, const int64_t *home_base,
                           int64_t *seg_addr, int64_t *group_bytes, void *workspace, int64_t workspace_bytes, void *stream);
 
+/* Pull exchange (DESIGN.md "multi-GPU"): every rank scans the lists it OWNS into its OWN estimate buffer (TKB_PLAN_SEND layout:
+ * grouped by the home rank of the query, then (q, s); local stores at full speed, chunk minima next to them), the ranks
+ * exchange the G + 1 numbers (total, group bases) of their layouts, and the home rank's replay reads the chunk minima of its
+ * queries from a local copy (tkb_ivf_pull_minima_dev) and fetches only the chunks that can hold a candidate -- a few percent --
+ * from the owners' buffers through the peer mappings.
+ *   tkb_ivf_plan_pull_owner_dev: TKB_PLAN_SEND with a capacity guard: a segment that would end past `capacity` bytes gets
+ *       offset -1 (never written); group_bytes[n_ranks] still holds the full total, so an overflow is visible to every rank
+ *       after the exchange of those numbers.
+ *   tkb_ivf_plan_pull_home_dev: for the home queries [rank*q_per_rank, ...): seg_addr int64[q_per_rank][P] = the ABSOLUTE
+ *       address of segment (q, s) inside its owner's buffer = owner_base[o] + owner_groups[o][1 + rank] + offset inside the
+ *       (owner o, home rank) group. owner_base int64[n_ranks]: every rank's buffer as mapped in this process;
+ *       owner_groups int64[n_ranks][n_ranks + 1]: row o = group_bytes[n_ranks .. 2 n_ranks] of owner o's plan.
+ *   tkb_ivf_pull_minima_dev: copies the minima of every segment of the home queries from the owners
+ *       (cm_table[o] + (seg_addr >> 4)) to cmin_local[seg_local >> 4], seg_local = the compact single-GPU plan of the home
+ *       queries (tkb_ivf_plan_dev, n_ranks == 1).
+ *   tkb_ivf_replay_fresh_pull_dev: tkb_ivf_replay_fresh_cm_dev whose estimate reads go to seg_addr (absolute addresses),
+ *       while the minima are addressed through cm_seg_off (= seg_local). cmin == NULL: no minima, every chunk is fetched. */
+TKB_API int tkb_ivf_plan_pull_owner_dev(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner,
+                                int n_lists, int rank, int n_ranks, int q_per_rank, int64_t capacity,
+                                int64_t *seg_off, int64_t *group_bytes, void *workspace, int64_t workspace_bytes, void *stream);
+TKB_API int tkb_ivf_plan_pull_home_dev(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner,
+                               int n_lists, int rank, int n_ranks, int q_per_rank, const int64_t *owner_base,
+                               const int64_t *owner_groups, int64_t *seg_addr, int64_t *group_bytes, void *workspace,
+                               int64_t workspace_bytes, void *stream);
+TKB_API int tkb_ivf_pull_minima_dev(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner, int n_lists,
+                            const int64_t *seg_addr, const int64_t *seg_local, const int64_t *cm_table, uint8_t *cmin_local,
+                            void *stream);
+TKB_API int tkb_ivf_replay_fresh_pull_dev(const int64_t *seg_addr, const int64_t *cm_seg_off, const uint8_t *cmin,
+                                  const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, const int64_t *ids,
+                                  const int32_t *probes, int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int signd,
+                                  int unique_labels, int32_t *fallback, void *stream);
+
 /* Peer-visible device buffers for the push exchange: one process per GPU, so the buffers are shared as CUDA IPC handles
  * (64 bytes) that the caller moves between the processes of a box itself (torch.distributed all_gather in the host layer).
  * tkb_peer_alloc: cudaMalloc on the current device + its handle. tkb_peer_open: map another process's buffer into this one

@@ -109,6 +109,59 @@ def test_push_exchange_with_chunk_minima_single_gpu(monkeypatch):
             b.close()
 
 
+def test_pull_exchange_single_gpu(monkeypatch):
+    """The pull exchange driven rank by rank on one GPU: every "rank" scans the lists it owns into its own buffer (estimates +
+    chunk minima), the home side computes where its segments live in the owners' buffers, copies the minima into its compact
+    layout and replays with absolute addresses == the unsharded path, heaps included; with and without minima; and the
+    capacity guard leaves out exactly the segments that do not fit."""
+    import torch
+    from tinyknn_b200 import synth, ivf as ivf_mod, sharded as SH
+    X = synth.clustered(300_000 + 48, 64, 40, seed=9)
+    ivf = synth.build_ivf(X[:300_000], "euclidean", 12, seed=9)
+    qs = X[300_000:].contiguous()
+    G, k, n_probes = 3, 10, 6
+    Qh = qs.shape[0] // G
+    monkeypatch.setattr(ivf_mod, "CMIN_CHUNKS", 0)
+    ref = ivf.query_batch(qs, k, n_probes=n_probes, order="device", return_distances=True, sub_batches=1)
+    ref_heap = ivf._last["heap_idx"].cpu().numpy()
+    monkeypatch.setattr(ivf_mod, "CMIN_CHUNKS", 1)
+    shards = [SH.ShardedIVF(ivf, rank=r, world=G, drop_full_codes=False) for r in range(G)]
+    homes = [sh._home(qs[r * Qh:(r + 1) * Qh].contiguous(), n_probes) for r, sh in enumerate(shards)]
+    P = homes[0]["P"]
+    tables = torch.cat([h["lut"]["tables"] for h in homes])
+    probes = torch.cat([h["probes"] for h in homes])
+    cap = G * shards[0].push_capacity(Qh, P)                       # an owner serves the queries of all ranks
+    bufs = [SH.PeerBuffers(cap, rank=0, world=1, n_buf=1) for _ in range(G)]
+    try:
+        addr = np.array([b.local[0].address for b in bufs], dtype=np.int64)
+        owner_base = D.upload(addr)
+        cm_table = D.upload(addr + bufs[0].nbytes - (addr >> 4))
+        for use_cm in (True, False):
+            groups = torch.stack([sh._scan_pull(tables, probes, Qh, P, bufs[r].local[0], bufs[r].local_cmin[0] if use_cm else None, cap)
+                                  for r, sh in enumerate(shards)])
+            assert int(groups[:, 0].max()) <= cap
+            for b, sh in enumerate(shards):
+                seg_addr, seg_local, cmin = sh._pull_home(probes, homes[b], owner_base, groups, cm_table if use_cm else None)
+                assert (cmin is not None) == use_cm
+                ids, cnt, dst = sh._finish(homes[b], None, seg_addr, k, (n_probes + 1) * k + 1, cmin, seg_local)
+                sl = slice(b * Qh, (b + 1) * Qh)
+                assert np.array_equal(ivf._last["heap_idx"].cpu().numpy(), ref_heap[sl])
+                assert np.array_equal(ids.cpu().numpy(), ref[0][sl]) and np.array_equal(dst.cpu().numpy(), ref[2][sl])
+        # the guard: with room for half of rank 0's segments the plan drops the rest (offset -1) and still reports the full total
+        full = int(groups[0, 0])
+        g2 = shards[0]._scan_pull(tables, probes, Qh, P, bufs[0].local[0], None, full // 2)
+        seg = shards[0].ivf._last["scan_seg_off"].cpu().numpy()
+        sizes = np.asarray(ivf.to_device()["host_sizes"])
+        pr = probes.cpu().numpy()
+        nbytes = 16 * ((sizes[pr] + 15) // 16)
+        kept = seg >= 0
+        assert int(g2[0]) == full and kept.any() and not kept[np.asarray(shards[0].owner)[pr] == 0].all()
+        assert (seg[kept] + nbytes[kept]).max() <= full // 2
+    finally:
+        for b in bufs:
+            b.close()
+
+
 def test_saved_index_answers_identically(tmp_path):
     """save_index / load_index (memory-mapped) -> to_device -> query_batch == the original index."""
     np.random.seed(6)

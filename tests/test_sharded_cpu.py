@@ -327,6 +327,29 @@ def _emu_worker(rank, world, port, out):
         for _ in range(2):
             got = sh.query_batch(mine, 10, n_probes=5, return_distances=True, exchange="push")
             bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
+        # pull exchange: the estimates stay in the owner's buffer, the home rank's replay reads the other process's memory;
+        # with chunk minima (copied to the home rank first) and without, device results without a host copy, and an owner
+        # buffer that is too small (the guard leaves segments out, every rank repeats the batch through the push exchange)
+        for cm in (1, 0, 1):
+            ivf_mod.CMIN_CHUNKS = cm
+            got = sh.query_batch(mine, 10, n_probes=5, return_distances=True, exchange="pull")
+            bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
+            bad += sh.last_exchange != "pull"
+        got = sh.query_batch(mine, 10, n_probes=5, return_distances=True, exchange="pull", to_host=False)
+        sh.check_overflow()
+        bad += sum(not np.array_equal(a, b.cpu().numpy()) for a, b in zip(ref, got))
+        sh.pull_capacity = 4096
+        got = sh.query_batch(mine, 10, n_probes=5, return_distances=True, exchange="pull")
+        bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
+        bad += sh.__dict__.get("pull_overflows", 0) != 1 or sh.last_exchange != "push"
+        try:
+            sh.query_batch(mine, 10, n_probes=5, exchange="pull", to_host=False)
+            sh.check_overflow()
+            bad += 1                                                   # the deferred check must raise
+        except RuntimeError:
+            pass
+        sh.pull_capacity = None
+        ivf_mod.CMIN_CHUNKS = 1
         sh.close()
         # one index for the whole job: rank 1 loses its copy, the fingerprints differ, rank 0's index is broadcast
         dev = ivf.to_device()

@@ -34,6 +34,16 @@ def _worker(rank, world, port, out):
             bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
             used.append(sh.last_exchange)
         bad += used != ["nccl", "push", "push", "push"]               # peer memory must really have been used
+        # pull exchange: estimates stay with the owner, the home rank's replay reads them (and the minima) through the peer mapping
+        from tinyknn_b200 import ivf as ivf_mod
+        for cm in (1, 8192, 1):
+            ivf_mod.CMIN_CHUNKS = cm
+            got = sh.query_batch(mine, 10, n_probes=6, return_distances=True, exchange="pull")
+            bad += sum(not np.array_equal(a, b) for a, b in zip(ref, got))
+            bad += sh.last_exchange != "pull"
+        got = sh.query_batch(mine, 10, n_probes=6, return_distances=True, exchange="pull", to_host=False)
+        sh.check_overflow()
+        bad += sum(not np.array_equal(a, b.cpu().numpy()) for a, b in zip(ref, got))
         sh.close()
         np.save(out, np.array([bad]))
     finally:

@@ -33,6 +33,10 @@ SIGNATURES = {
     "tkb_ivf_scan_dev": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _i64, _vp, _i64, _i, _i, _vp],
     "tkb_ivf_plan_dev": [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _vp],
     "tkb_ivf_plan_push_dev": [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp],
+    "tkb_ivf_plan_pull_owner_dev": [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _i64, _vp],
+    "tkb_ivf_plan_pull_home_dev": [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "tkb_ivf_pull_minima_dev": [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],
+    "tkb_ivf_replay_fresh_pull_dev": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
     "tkb_peer_alloc": [_i64, _c.POINTER(_vp), _vp],
     "tkb_peer_open": [_vp, _c.POINTER(_vp)],
     "tkb_peer_close": [_vp],

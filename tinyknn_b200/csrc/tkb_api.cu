@@ -206,6 +206,43 @@ int tkb_ivf_plan_push_dev(const int32_t *probes, int Q, int P, const int32_t *li
                            seg_addr, group_bytes, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int tkb_ivf_plan_pull_owner_dev(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner,
+                                int n_lists, int rank, int n_ranks, int q_per_rank, int64_t capacity,
+                                int64_t *seg_off, int64_t *group_bytes, void *workspace, int64_t workspace_bytes, void *stream)
+{
+    TKB_REQUIRE(capacity > 0, "capacity must be positive");
+    return launch_ivf_plan(probes, Q, P, list_size, list_owner, n_lists, TKB_PLAN_SEND, rank, n_ranks, q_per_rank, nullptr, seg_off,
+                           group_bytes, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, capacity);
+}
+
+int tkb_ivf_plan_pull_home_dev(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner,
+                               int n_lists, int rank, int n_ranks, int q_per_rank, const int64_t *owner_base,
+                               const int64_t *owner_groups, int64_t *seg_addr, int64_t *group_bytes, void *workspace,
+                               int64_t workspace_bytes, void *stream)
+{
+    return launch_ivf_plan(probes, Q, P, list_size, list_owner, n_lists, 3 /* pull, home side */, rank, n_ranks, q_per_rank,
+                           owner_base, seg_addr, group_bytes, workspace, workspace_bytes, (cudaStream_t)stream, owner_groups, 0);
+}
+
+int tkb_ivf_pull_minima_dev(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner, int n_lists,
+                            const int64_t *seg_addr, const int64_t *seg_local, const int64_t *cm_table, uint8_t *cmin_local,
+                            void *stream)
+{
+    return launch_pull_minima(probes, Q, P, list_size, list_owner, n_lists, seg_addr, seg_local, cm_table, cmin_local,
+                              (cudaStream_t)stream);
+}
+
+int tkb_ivf_replay_fresh_pull_dev(const int64_t *seg_addr, const int64_t *cm_seg_off, const uint8_t *cmin,
+                                  const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, const int64_t *ids,
+                                  const int32_t *probes, int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int signd,
+                                  int unique_labels, int32_t *fallback, void *stream)
+{
+    TKB_REQUIRE(seg_addr, "null pointer");
+    TKB_REQUIRE(!cmin || cm_seg_off, "the chunk minima need the layout they are addressed by (cm_seg_off)");
+    return launch_ivf_replay_fresh(nullptr, 0, seg_addr, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
+                                   heap_val, R, signd, unique_labels, fallback, (cudaStream_t)stream, cmin, cm_seg_off);
+}
+
 // ---------------------------------------------------------------------------------------------
 // peer memory (one process per GPU; CUDA IPC handles travel through the caller's own channel)
 // ---------------------------------------------------------------------------------------------

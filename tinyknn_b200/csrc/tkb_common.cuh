@@ -108,7 +108,11 @@ int launch_ivf_scan(const uint64_t *codes, const int64_t *list_chunk_off, const 
                     int64_t slot_stride, const int64_t *seg_off, int64_t max_list_chunks, int order, int signd, cudaStream_t st);
 int launch_ivf_plan(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner, int n_lists,
                     int mode, int rank, int n_ranks, int q_per_rank, const int64_t *home_base, int64_t *seg_off,
-                    int64_t *group_bytes, void *workspace, int64_t workspace_bytes, cudaStream_t st);
+                    int64_t *group_bytes, void *workspace, int64_t workspace_bytes, cudaStream_t st,
+                    const int64_t *send_bases = nullptr, int64_t capacity = 0);
+int launch_pull_minima(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner, int n_lists,
+                       const int64_t *seg_addr, const int64_t *seg_local, const int64_t *cm_table, uint8_t *cmin_local,
+                       cudaStream_t st);
 int launch_encode(const void *rows, int rows_dtype, int64_t n_rows, int d, const int64_t *row_index, int64_t n_out,
                   const float *centers, const float *cnorm, int Dp, int dpb, const double *R, int Dpad, uint64_t *codes,
                   cudaStream_t st);
@@ -142,7 +146,8 @@ int launch_replay_fresh(const uint8_t *est, int64_t est_stride, int64_t n_chunks
 int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                             const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
                             int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int signd,
-                            int unique_labels, int *fallback, cudaStream_t st, const uint8_t *cmin = nullptr);
+                            int unique_labels, int *fallback, cudaStream_t st, const uint8_t *cmin = nullptr,
+                            const int64_t *cm_seg = nullptr);
 int launch_lut_build(const float *queries, int Q, int d, int normalize, float *q_out,
                      const float *centers, int Dp, int dpb, const double *R, int Dpad,
                      double sqrt_n_blocks, double log_n_blocks, int signd, uint8_t *tables,

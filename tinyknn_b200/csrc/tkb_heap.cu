@@ -379,8 +379,10 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                   const int32_t *__restrict__ list_size, int n_lists, const int64_t *__restrict__ ids,
                   const int32_t *__restrict__ probes, int Q, int P, int64_t *__restrict__ heap_idx,
                   int32_t *__restrict__ heap_val, int R, int *__restrict__ fallback, int QPC, int QCAP,
-                  const uint8_t *__restrict__ cmin, int qpw)
+                  const uint8_t *__restrict__ cmin, int qpw, const int64_t *__restrict__ cm_seg)
 {
+    // cm_seg (pull exchange): the compact layout the chunk minima are addressed by, while `seg_off` holds absolute addresses of
+    // segments that live in other GPUs' buffers (est == null); null: the minima follow seg_off
     extern __shared__ __align__(16) unsigned char rq_sm[];
     const int HS = 2 * R + 4;                                              // words per heap: slot i at word i+1, children of R-1 included
     uint32_t *H = reinterpret_cast<uint32_t *>(rq_sm);                     // [QPC][HS]
@@ -430,10 +432,11 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
             // the query's stream is one contiguous byte range of `est` when its segments lie back to back (the compact
             // single-GPU plan): chunk cc of the stream is est[qoff + 16 cc ..] and its minimum is cmin[qoff / 16 + cc]
             long long qoff = -1;
-            bool contig = ok && mode == 1 && seg_off != nullptr;
+            const int64_t *lay = cm_seg ? cm_seg : seg_off;
+            bool contig = ok && mode == 1 && lay != nullptr;
             for (int s = 0; contig && s < P; s++) {
                 if (c[s + 1] == c[s]) continue;
-                const long long o = seg_off[(size_t)q * P + s];
+                const long long o = lay[(size_t)q * P + s];
                 if (qoff < 0) qoff = o - 16LL * c[s];
                 if (o < 0 || o != qoff + 16LL * c[s]) contig = false;
             }
@@ -510,7 +513,8 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                             int lo = 0, hi = P;                              // segment with c[lo] <= cc < c[lo+1]
                             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (c[mid] <= cc) lo = mid; else hi = mid; }
                             const int rem = list_size[probes[(size_t)q * P + lo]] - 16 * (cc - c[lo]);
-                            ee = ldg_nc_u4(reinterpret_cast<const uint4 *>(eq + 16LL * cc));
+                            const uint8_t *ea = cm_seg ? est + seg_off[(size_t)q * P + lo] + 16LL * (cc - c[lo]) : eq + 16LL * cc;
+                            ee = ldg_nc_u4(reinterpret_cast<const uint4 *>(ea));
                             if (!SIGNED) { ee.x ^= 0x80808080u; ee.y ^= 0x80808080u; ee.z ^= 0x80808080u; ee.w ^= 0x80808080u; }
                             mm = cand_mask16<true>(ee, bound) & (rem >= 16 ? 0xffffu : ((1u << rem) - 1u));
                         }
@@ -871,7 +875,7 @@ template <bool SIGNED>
 static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t *seg_off, int64_t n_chunks0, int n0,
                      const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, const int64_t *ids,
                      const int32_t *probes, int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int *fallback,
-                     const RqGeom &g, cudaStream_t st, const uint8_t *cmin = nullptr)
+                     const RqGeom &g, cudaStream_t st, const uint8_t *cmin = nullptr, const int64_t *cm_seg = nullptr)
 {
     const unsigned blocks = (unsigned)((Q + g.qpc - 1) / g.qpc);
     if (g.v2) {
@@ -880,7 +884,7 @@ static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t
             TKB_CUDA(cudaFuncSetAttribute(replay_rq2_kernel<SIGNED, LANES, CMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
             replay_rq2_kernel<SIGNED, LANES, CMV><<<blocks, g.threads, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off, \
                                                                                      list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val,  \
-                                                                                     R, fallback, g.qpc, g.qcap, cmin, rq_qpw());               \
+                                                                                     R, fallback, g.qpc, g.qcap, cmin, rq_qpw(), cm_seg);       \
         } while (0)
         if (cmin) { if (g.lanes == 4) TKB_RQ2_LAUNCH(4, true); else TKB_RQ2_LAUNCH(8, true); }
         else      { if (g.lanes == 4) TKB_RQ2_LAUNCH(4, false); else TKB_RQ2_LAUNCH(8, false); }
@@ -917,10 +921,10 @@ template <bool SIGNED>
 static int ivf_replay_fresh_t(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                               const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
                               int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int *fallback,
-                              const RqGeom &g, cudaStream_t st, const uint8_t *cmin)
+                              const RqGeom &g, cudaStream_t st, const uint8_t *cmin, const int64_t *cm_seg)
 {
     if (int rc = launch_rq<SIGNED>(1, est, slot_stride, seg_off, 0, 0, list_chunk_off, list_size, n_lists, ids, probes,
-                                   Q, P, heap_idx, heap_val, R, fallback, g, st, cmin)) return rc;
+                                   Q, P, heap_idx, heap_val, R, fallback, g, st, cmin, cm_seg)) return rc;
     // queries whose probe list holds Python-wrapped (negative) entries: warp-per-query kernel with label dedupe
     ivf_replay_fallback_kernel<SIGNED><<<(unsigned)((Q + REPLAY_WARPS - 1) / REPLAY_WARPS), 32 * REPLAY_WARPS, 0, st>>>(
         est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val, R, fallback);
@@ -931,8 +935,9 @@ static int ivf_replay_fresh_t(const uint8_t *est, int64_t slot_stride, const int
 int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64_t *seg_off, const int64_t *list_chunk_off,
                             const int32_t *list_size, int n_lists, const int64_t *ids, const int32_t *probes,
                             int Q, int P, int64_t *heap_idx, int32_t *heap_val, int R, int signd,
-                            int unique_labels, int *fallback, cudaStream_t st, const uint8_t *cmin)
+                            int unique_labels, int *fallback, cudaStream_t st, const uint8_t *cmin, const int64_t *cm_seg)
 {
+    // est == null with a segment plan: seg_off holds absolute addresses (pull exchange; cm_seg = the layout of the minima)
     TKB_REQUIRE(Q >= 0 && R >= 0 && P >= 0 && n_lists > 0, "bad extent");
     if (Q == 0 || R == 0) return TKB_OK;
     TKB_REQUIRE(heap_idx && heap_val, "null pointer");
@@ -943,13 +948,14 @@ int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64
         return launch_ivf_replay(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
                                  heap_val, R, signd, st);
     }
-    TKB_REQUIRE(est && list_chunk_off && list_size && ids && probes, "null pointer");
+    TKB_REQUIRE((est || seg_off) && list_chunk_off && list_size && ids && probes, "null pointer");
     TKB_REQUIRE(slot_stride % 16 == 0 && (uintptr_t)est % 16 == 0, "est must be 16-byte aligned/strided");
     if (!g.v2) cmin = nullptr;                                             // only the pipelined kernel reads the chunk minima
+    if (!cmin) cm_seg = nullptr;
     if (signd) return ivf_replay_fresh_t<true>(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P,
-                                               heap_idx, heap_val, R, fallback, g, st, cmin);
+                                               heap_idx, heap_val, R, fallback, g, st, cmin, cm_seg);
     return ivf_replay_fresh_t<false>(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P,
-                                     heap_idx, heap_val, R, fallback, g, st, cmin);
+                                     heap_idx, heap_val, R, fallback, g, st, cmin, cm_seg);
 }
 
 }  // namespace tkb

@@ -15,6 +15,8 @@
 namespace tkb {
 
 constexpr int PLAN_MAX_RANKS = 16;
+constexpr int PLAN_CTA = 128;           // queries per CTA of the count / write kernels
+constexpr int TKB_PLAN_PULL_ = 3;       // internal: the home side of the pull exchange (tkb_ivf_plan_pull_home_dev)
 
 struct PlanArgs {
     const int32_t *probes;        // [Q][P] (global query numbering)
@@ -22,6 +24,9 @@ struct PlanArgs {
     const int32_t *list_owner;    // [n_lists] or null: every list is local
     int Q, P, n_lists, mode, rank, n_ranks, q_per_rank;
     const int64_t *home_base;     // TKB_PLAN_PUSH: [n_ranks] address of each home rank's receive buffer, as mapped here
+                                  // pull, home side: [n_ranks] address of each OWNER's estimate buffer, as mapped here
+    const int64_t *send_bases;    // pull, home side: [n_ranks][n_ranks + 1]; row r = (total, bases of the home groups) of owner r's buffer
+    int64_t capacity;             // TKB_PLAN_SEND with capacity > 0: a segment that would end past it is dropped (offset -1)
 };
 
 __device__ __forceinline__ int64_t plan_seg(const PlanArgs &a, int q, int s, int &group, bool *mine = nullptr)
@@ -49,30 +54,54 @@ __device__ __forceinline__ int64_t plan_seg(const PlanArgs &a, int q, int s, int
 // queries handled by this rank in `mode`: all of them when sending, the home block when receiving
 __device__ __forceinline__ void plan_range(const PlanArgs &a, int &q_lo, int &q_n)
 {
-    if (a.mode == TKB_PLAN_RECV && a.n_ranks > 1) { q_lo = a.rank * a.q_per_rank; q_n = min(a.q_per_rank, a.Q - q_lo); if (q_n < 0) q_n = 0; }
-    else { q_lo = 0; q_n = a.Q; }
+    if ((a.mode == TKB_PLAN_RECV || a.mode == TKB_PLAN_PULL_) && a.n_ranks > 1) {
+        q_lo = a.rank * a.q_per_rank; q_n = min(a.q_per_rank, a.Q - q_lo); if (q_n < 0) q_n = 0;
+    } else { q_lo = 0; q_n = a.Q; }
 }
 
-// phase 1: bytes per (query, group)
-__global__ void plan_count_kernel(PlanArgs a, int64_t *__restrict__ qtot /* [q_n][n_ranks] */)
+__device__ __forceinline__ void plan_query_totals(const PlanArgs &a, int q, int64_t (&tot)[PLAN_MAX_RANKS])
 {
-    int q_lo, q_n;
-    plan_range(a, q_lo, q_n);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= q_n) return;
-    int64_t tot[PLAN_MAX_RANKS];
 #pragma unroll
     for (int g = 0; g < PLAN_MAX_RANKS; g++) tot[g] = 0;
     for (int s = 0; s < a.P; s++) {
         int g;
-        const int64_t b = plan_seg(a, q_lo + i, s, g);
+        const int64_t b = plan_seg(a, q, s, g);
 #pragma unroll
         for (int k = 0; k < PLAN_MAX_RANKS; k++) if (k == g) tot[k] += b;
     }
-    for (int g = 0; g < a.n_ranks; g++) qtot[(size_t)i * a.n_ranks + g] = tot[g];
 }
 
-// phase 2 (one CTA): exclusive scan over the queries per group, then the group bases; qtot becomes qbase
+// phase 1: bytes per (query, group), left as the EXCLUSIVE prefix over the queries of the CTA (the first query of a CTA holds 0:
+// phase 2 puts the CTA's base there)
+__global__ void __launch_bounds__(PLAN_CTA) plan_count_kernel(PlanArgs a, int64_t *__restrict__ qtot /* [q_n][n_ranks] */)
+{
+    __shared__ int64_t s_w[PLAN_CTA / 32];
+    int q_lo, q_n;
+    plan_range(a, q_lo, q_n);
+    const int i = blockIdx.x * PLAN_CTA + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t tot[PLAN_MAX_RANKS];
+    if (i < q_n) plan_query_totals(a, q_lo + i, tot);
+    else {
+#pragma unroll
+        for (int g = 0; g < PLAN_MAX_RANKS; g++) tot[g] = 0;
+    }
+#pragma unroll
+    for (int g = 0; g < PLAN_MAX_RANKS; g++) {
+        if (g >= a.n_ranks) break;                               // uniform
+        int64_t incl = tot[g];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int64_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        int64_t before = 0;
+        for (int w = 0; w < warp; w++) before += s_w[w];
+        if (i < q_n) qtot[(size_t)i * a.n_ranks + g] = before + incl - tot[g];
+        __syncthreads();
+    }
+}
+
+// phase 2 (one CTA): exclusive scan over the CTAs of phase 1 per group, then the group bases. The total of a phase-1 CTA is the
+// prefix of its last query plus that query's own bytes (recomputed: P probes); its base goes into the slot of its first query.
 __global__ void __launch_bounds__(1024) plan_scan_kernel(PlanArgs a, int64_t *__restrict__ qtot, int64_t *__restrict__ group_bytes)
 {
     __shared__ int64_t part[1024];
@@ -80,11 +109,17 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(PlanArgs a, int64_t *__
     int q_lo, q_n;
     plan_range(a, q_lo, q_n);
     const int tid = threadIdx.x;
-    const int per = (q_n + 1023) / 1024;
-    const int lo = min(q_n, tid * per), hi = min(q_n, lo + per);
+    const int n_blocks = (q_n + PLAN_CTA - 1) / PLAN_CTA;
+    const int per = (n_blocks + 1023) / 1024;                      // phase-1 CTAs per thread (1 up to 131 072 queries)
+    const int lo = min(n_blocks, tid * per), hi = min(n_blocks, lo + per);
     for (int g = 0; g < a.n_ranks; g++) {
         int64_t sum = 0;
-        for (int i = lo; i < hi; i++) sum += qtot[(size_t)i * a.n_ranks + g];
+        for (int b = lo; b < hi; b++) {
+            const int last = min(q_n, (b + 1) * PLAN_CTA) - 1;
+            int64_t t = qtot[(size_t)last * a.n_ranks + g];
+            for (int s = 0; s < a.P; s++) { int gg; const int64_t by = plan_seg(a, q_lo + last, s, gg); if (gg == g) t += by; }
+            sum += t;
+        }
         part[tid] = sum;
         __syncthreads();
         for (int o = 1; o < 1024; o <<= 1) {                      // Hillis-Steele inclusive scan
@@ -93,12 +128,14 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(PlanArgs a, int64_t *__
             part[tid] += v;
             __syncthreads();
         }
-        int64_t run = part[tid] - sum;                            // exclusive prefix of this thread's block
+        int64_t run = part[tid] - sum;                            // exclusive prefix of this thread's CTAs
         if (tid == 1023) gbase[g + 1] = part[1023];
-        for (int i = lo; i < hi; i++) {
-            const int64_t b = qtot[(size_t)i * a.n_ranks + g];
-            qtot[(size_t)i * a.n_ranks + g] = run;
-            run += b;
+        for (int b = lo; b < hi; b++) {
+            const int last = min(q_n, (b + 1) * PLAN_CTA) - 1;
+            int64_t t = qtot[(size_t)last * a.n_ranks + g];
+            for (int s = 0; s < a.P; s++) { int gg; const int64_t by = plan_seg(a, q_lo + last, s, gg); if (gg == g) t += by; }
+            qtot[(size_t)b * PLAN_CTA * a.n_ranks + g] = run;
+            run += t;
         }
         __syncthreads();
     }
@@ -116,18 +153,29 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(PlanArgs a, int64_t *__
 }
 
 // phase 3: segment offsets
-__global__ void plan_write_kernel(PlanArgs a, const int64_t *__restrict__ qbase, const int64_t *__restrict__ group_bytes,
-                                  int64_t *__restrict__ seg_off /* [q_n][P] */)
+__global__ void __launch_bounds__(PLAN_CTA)
+plan_write_kernel(PlanArgs a, const int64_t *__restrict__ qbase, const int64_t *__restrict__ group_bytes,
+                  int64_t *__restrict__ seg_off /* [q_n][P] */)
 {
     int q_lo, q_n;
     plan_range(a, q_lo, q_n);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * PLAN_CTA + threadIdx.x;
     if (i >= q_n) return;
-    const bool push = a.mode == TKB_PLAN_PUSH;
+    const bool push = a.mode == TKB_PLAN_PUSH, pull = a.mode == TKB_PLAN_PULL_;
     int64_t run[PLAN_MAX_RANKS];
 #pragma unroll
-    for (int g = 0; g < PLAN_MAX_RANKS; g++)                      // push: absolute addresses inside the home rank's buffer
-        run[g] = g < a.n_ranks ? (push ? a.home_base[g] : group_bytes[a.n_ranks + 1 + g]) + qbase[(size_t)i * a.n_ranks + g] : 0;
+    for (int g = 0; g < PLAN_MAX_RANKS; g++) {
+        run[g] = 0;
+        if (g < a.n_ranks) {
+            // push: absolute addresses inside the home rank's buffer; pull: inside the owner's buffer, where the segments of
+            // this rank's queries start at the owner's base of home group `rank`
+            const int64_t base = push ? a.home_base[g]
+                               : pull ? a.home_base[g] + a.send_bases[(size_t)g * (a.n_ranks + 1) + 1 + a.rank]
+                                      : group_bytes[a.n_ranks + 1 + g];
+            run[g] = base + qbase[(size_t)blockIdx.x * PLAN_CTA * a.n_ranks + g] + (threadIdx.x ? qbase[(size_t)i * a.n_ranks + g] : 0);
+        }
+    }
+    const int64_t cap = (a.mode == TKB_PLAN_SEND && a.capacity > 0) ? a.capacity : INT64_MAX;
     for (int s = 0; s < a.P; s++) {
         int g;
         bool mine = true;
@@ -136,7 +184,7 @@ __global__ void plan_write_kernel(PlanArgs a, const int64_t *__restrict__ qbase,
         if (b > 0) {
 #pragma unroll
             for (int k = 0; k < PLAN_MAX_RANKS; k++) if (k == g) { off = run[k]; run[k] += b; }
-            if (!mine) off = -1;
+            if (!mine || off + b > cap) off = -1;
         }
         seg_off[(size_t)i * a.P + s] = off;
     }
@@ -144,18 +192,23 @@ __global__ void plan_write_kernel(PlanArgs a, const int64_t *__restrict__ qbase,
 
 int launch_ivf_plan(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner, int n_lists,
                     int mode, int rank, int n_ranks, int q_per_rank, const int64_t *home_base, int64_t *seg_off,
-                    int64_t *group_bytes, void *workspace, int64_t workspace_bytes, cudaStream_t st)
+                    int64_t *group_bytes, void *workspace, int64_t workspace_bytes, cudaStream_t st,
+                    const int64_t *send_bases, int64_t capacity)
 {
     TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists > 0, "bad extent");
-    TKB_REQUIRE(mode == TKB_PLAN_SEND || mode == TKB_PLAN_RECV || mode == TKB_PLAN_PUSH, "mode must be TKB_PLAN_SEND, _RECV or _PUSH");
+    TKB_REQUIRE(mode == TKB_PLAN_SEND || mode == TKB_PLAN_RECV || mode == TKB_PLAN_PUSH || mode == TKB_PLAN_PULL_,
+                "mode must be TKB_PLAN_SEND, _RECV or _PUSH");
     TKB_REQUIRE(mode != TKB_PLAN_PUSH || home_base, "TKB_PLAN_PUSH needs the receive-buffer addresses (home_base)");
+    TKB_REQUIRE(mode != TKB_PLAN_PULL_ || (home_base && send_bases), "the pull plan needs the owners' buffer addresses and group bases");
     TKB_REQUIRE(n_ranks >= 1 && n_ranks <= PLAN_MAX_RANKS && rank >= 0 && rank < n_ranks, "bad rank / n_ranks");
     TKB_REQUIRE(n_ranks == 1 || (q_per_rank > 0 && (int64_t)q_per_rank * n_ranks >= Q), "q_per_rank * n_ranks must cover Q");
     TKB_REQUIRE(n_ranks == 1 || list_owner, "list_owner is required when lists are sharded");
     TKB_REQUIRE(group_bytes, "null pointer");
-    PlanArgs a{probes, list_size, list_owner, Q, P, n_lists, mode, rank, n_ranks, q_per_rank, home_base};
+    PlanArgs a{probes, list_size, list_owner, Q, P, n_lists, mode, rank, n_ranks, q_per_rank, home_base, send_bases, capacity};
     int q_n = Q;
-    if (mode == TKB_PLAN_RECV && n_ranks > 1) { q_n = Q - rank * q_per_rank; if (q_n > q_per_rank) q_n = q_per_rank; if (q_n < 0) q_n = 0; }
+    if ((mode == TKB_PLAN_RECV || mode == TKB_PLAN_PULL_) && n_ranks > 1) {
+        q_n = Q - rank * q_per_rank; if (q_n > q_per_rank) q_n = q_per_rank; if (q_n < 0) q_n = 0;
+    }
     if (q_n == 0 || P == 0) {
         TKB_CUDA(cudaMemsetAsync(group_bytes, 0, sizeof(int64_t) * (2 * n_ranks + 1), st));
         return TKB_OK;
@@ -163,12 +216,54 @@ int launch_ivf_plan(const int32_t *probes, int Q, int P, const int32_t *list_siz
     TKB_REQUIRE(probes && list_size && seg_off, "null pointer");
     TKB_REQUIRE(workspace && workspace_bytes >= (int64_t)sizeof(int64_t) * q_n * n_ranks, "plan workspace too small (8 * queries * n_ranks bytes)");
     int64_t *qtot = reinterpret_cast<int64_t *>(workspace);
-    const unsigned blocks = (unsigned)((q_n + 127) / 128);
-    plan_count_kernel<<<blocks, 128, 0, st>>>(a, qtot);
+    const unsigned blocks = (unsigned)((q_n + PLAN_CTA - 1) / PLAN_CTA);
+    plan_count_kernel<<<blocks, PLAN_CTA, 0, st>>>(a, qtot);
     TKB_LAUNCH_CHECK();
     plan_scan_kernel<<<1, 1024, 0, st>>>(a, qtot, group_bytes);
     TKB_LAUNCH_CHECK();
-    plan_write_kernel<<<blocks, 128, 0, st>>>(a, qtot, group_bytes, seg_off);
+    plan_write_kernel<<<blocks, PLAN_CTA, 0, st>>>(a, qtot, group_bytes, seg_off);
+    TKB_LAUNCH_CHECK();
+    return TKB_OK;
+}
+
+// ---- pull exchange: the chunk minima of a home rank's queries, fetched from the owners' buffers ---------------------------------
+// One warp per (query, probe slot): the minima of the segment (one byte per chunk) are copied from the owner's minima region
+// (addressed, like everywhere, by the estimate address >> 4 through a per-owner table) to their place in the home rank's own
+// compact stream layout, where the replay reads them 16 chunks per load. Source and destination are byte-aligned only.
+__global__ void __launch_bounds__(256)
+pull_minima_kernel(const int32_t *__restrict__ probes, int64_t n_seg, const int32_t *__restrict__ list_size,
+                   const int32_t *__restrict__ list_owner, int n_lists, const int64_t *__restrict__ seg_addr,
+                   const int64_t *__restrict__ seg_local, const int64_t *__restrict__ cm_table, uint8_t *__restrict__ cmin_local)
+{
+    const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= n_seg) return;
+    int l = probes[e];
+    const int64_t src_a = seg_addr[e], dst_o = seg_local[e];
+    if (l == PROBE_SKIP || src_a < 0 || dst_o < 0) return;
+    if (l < 0) l += n_lists;
+    const int n = (list_size[l] + 15) >> 4;
+    const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)(cm_table[list_owner ? list_owner[l] : 0] + (src_a >> 4)));
+    uint8_t *dst = cmin_local + (dst_o >> 4);
+    for (int i0 = 0; i0 < n; i0 += 128) {
+        uint8_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int i = i0 + 32 * u + lane; v[u] = i < n ? src[i] : (uint8_t)0; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int i = i0 + 32 * u + lane; if (i < n) dst[i] = v[u]; }
+    }
+}
+
+int launch_pull_minima(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner, int n_lists,
+                       const int64_t *seg_addr, const int64_t *seg_local, const int64_t *cm_table, uint8_t *cmin_local,
+                       cudaStream_t st)
+{
+    TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists > 0, "bad extent");
+    if (Q == 0 || P == 0) return TKB_OK;
+    TKB_REQUIRE(probes && list_size && seg_addr && seg_local && cm_table && cmin_local, "null pointer");
+    const int64_t n_seg = (int64_t)Q * P;
+    pull_minima_kernel<<<(unsigned)((n_seg + 7) / 8), 256, 0, st>>>(probes, n_seg, list_size, list_owner, n_lists, seg_addr,
+                                                                    seg_local, cm_table, cmin_local);
     TKB_LAUNCH_CHECK();
     return TKB_OK;
 }

@@ -326,9 +326,12 @@ __device__ __noinline__ int tc_refold(const uint32_t *__restrict__ nat32, long l
     const int s = r >> 4, v = r & 15, gq = v >> 2, sh = 16 * (gq & 1) + 4 * (v & 3);
     const uint32_t *tb = nat32 + ((size_t)tile * PH * 8 + s) * 4 + (gq >> 1);
     int a0 = 0, a1 = 0;
-#pragma unroll 4
+    uint32_t wa[PH], wb[PH];                                        // all 2 PH code words in flight before the first lookup
+#pragma unroll
+    for (int p = 0; p < PH; p++) { wa[p] = __ldg(tb + (size_t)p * 32); wb[p] = __ldg(tb + (size_t)p * 32 + 2); }
+#pragma unroll
     for (int p = 0; p < PH; p++) {
-        const uint32_t ca = (__ldg(tb + (size_t)p * 32) >> sh) & 15u, cb = (__ldg(tb + (size_t)p * 32 + 2) >> sh) & 15u;
+        const uint32_t ca = (wa[p] >> sh) & 15u, cb = (wb[p] >> sh) & 15u;
         const int ta = (int)(int8_t)Bq[(size_t)(2 * p) * TC_NT * 16 + ca];
         const int tb2 = (int)(int8_t)Bq[(size_t)(2 * p + 1) * TC_NT * 16 + cb];
         if (p & 1) a1 = sat_add8<true>(sat_add8<true>(a1, ta), tb2);
@@ -401,7 +404,9 @@ __device__ __noinline__ void tc_flagged8(TcShared &S, const uint2 *kq2, uint4 pa
 // WIDE: the half writes a tile out together (one barrier per tile), 8 consecutive lanes = the 128 contiguous bytes a tile holds for
 // one query -- full lines for the peer-mapped buffers of the push exchange, where 32-byte stores waste NVLink; otherwise every warp
 // writes out what it computed itself (32-byte pieces, no barrier), which is faster into local memory.
-template <int PH, bool WIDE>
+// CLK: the cycle counters of the roles (TcClock) are kept only in the instance bench.py's stage pass asks for (TKB_TC_CLOCKS=1): they
+// cost a dozen registers in a kernel that sits at its register limit.
+template <int PH, bool WIDE, bool CLK>
 __global__ void __launch_bounds__(TC_THREADS2, 1)
 ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict__ list_chunk_off,
                    const int32_t *__restrict__ list_size, int n_lists, const uint8_t *__restrict__ tables, int P,
@@ -443,9 +448,9 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
         long long lk[2] = {0, 0};
         for (uint32_t it = 0;; it++) {
             const int par = it & 1;
-            const long long c0_ = clock64();
+            const long long c0_ = (CLK ? clock64() : 0LL);
             mbar_wait(&S.item_empty[par], ((it >> 1) & 1) ^ 1, 1000);
-            const long long c1_ = clock64();
+            const long long c1_ = (CLK ? clock64() : 0LL);
             lk[0] += c1_ - c0_;
             TcItem &I = S.item[par];
             int item = 0;
@@ -508,14 +513,14 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
             mbar_arrive(&S.item_full[par]);
-            lk[1] += clock64() - c1_;
+            lk[1] += (CLK ? clock64() : 0LL) - c1_;
         }
-        if (lane == 0) { atomicAdd(W.clk + CK_L_WAIT, (unsigned long long)lk[0]); atomicAdd(W.clk + CK_L_STAGE, (unsigned long long)lk[1]); }
+        if (CLK && lane == 0) { atomicAdd(W.clk + CK_L_WAIT, (unsigned long long)lk[0]); atomicAdd(W.clk + CK_L_STAGE, (unsigned long long)lk[1]); }
     } else if (warp == TC_WARPS - 2) {
         // ================================ MMA issuer =================================================================
         uint32_t g = 0;                                              // tiles issued so far (buffer = g & 1)
         long long mk[3] = {0, 0, 0};
-        const long long k0_ = clock64();
+        const long long k0_ = (CLK ? clock64() : 0LL);
         for (uint32_t it = 0;; it++) {
             const int par = it & 1;
             mbar_wait(&S.item_full[par], (it >> 1) & 1);
@@ -526,10 +531,10 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                 const uint32_t b0 = smem_u32(Bslab + (size_t)par * SLAB);
                 for (int t = I.t0; t < I.t1; t++, g++) {
                     const uint32_t b = g & 1, ph = (g >> 1) & 1;
-                    const long long c0_ = clock64();
+                    const long long c0_ = (CLK ? clock64() : 0LL);
                     mbar_wait(&S.a_full[b], ph);          // A[b] written AND D[b] read by the half (program order of its warps)
                     tc_fence_after();
-                    const long long c1_ = clock64(), c2_ = c1_;
+                    const long long c1_ = (CLK ? clock64() : 0LL), c2_ = c1_;
                     if (elect_one()) {
 #pragma unroll
                         for (int p = 0; p < PH; p++)
@@ -538,7 +543,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                         umma_commit(&S.d_full[b]);
                     }
                     __syncwarp();
-                    mk[0] += c1_ - c0_; mk[1] += c2_ - c1_; mk[2] += clock64() - c2_;
+                    mk[0] += c1_ - c0_; mk[1] += c2_ - c1_; mk[2] += (CLK ? clock64() : 0LL) - c2_;
                 }
             }
             if (lane == 0) {
@@ -547,9 +552,9 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                 mbar_arrive(&S.item_empty[par]);
             }
         }
-        if (lane == 0) {
+        if (CLK && lane == 0) {
             atomicAdd(W.clk + CK_M_WAIT_A, (unsigned long long)mk[0]); atomicAdd(W.clk + CK_M_WAIT_D, (unsigned long long)mk[1]);
-            atomicAdd(W.clk + CK_M_ISSUE, (unsigned long long)mk[2]); atomicAdd(W.clk + CK_TOTAL, (unsigned long long)(clock64() - k0_));
+            atomicAdd(W.clk + CK_M_ISSUE, (unsigned long long)mk[2]); atomicAdd(W.clk + CK_TOTAL, (unsigned long long)((CLK ? clock64() : 0LL) - k0_));
         }
     } else {
         // ================================ workers ====================================================================
@@ -643,17 +648,25 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                 }
                 __syncwarp();
             };
+            // the code words of the half's NEXT tile are fetched while the current one is multiplied and written out: the expansion
+            // never waits for global memory except at the first tile of an item
+            uint32_t nxt[2 * PW];
+            auto fetch = [&](int t) {
+#pragma unroll
+                for (int p = 0; p < PW; p++) {
+                    nxt[2 * p] = __ldg(tb + ((size_t)t * PH + p) * 32);
+                    nxt[2 * p + 1] = __ldg(tb + ((size_t)t * PH + p) * 32 + 2);
+                }
+            };
+            if (first < t1) fetch(first);
             for (int t = first; t < t1; t += 2, k_tile++) {
                 const uint32_t ph = (k_tile & 1);                    // the half's buffers complete one phase per own tile
-                const long long c0_ = clock64();
+                const long long c0_ = (CLK ? clock64() : 0LL);
                 // ---- expand: this thread's vector, this warp's half of the sub-quantizer pairs ------------------------------
                 {
                     uint32_t cur[2 * PW];
 #pragma unroll
-                    for (int p = 0; p < PW; p++) {
-                        cur[2 * p] = __ldg(tb + ((size_t)t * PH + p) * 32);
-                        cur[2 * p + 1] = __ldg(tb + ((size_t)t * PH + p) * 32 + 2);
-                    }
+                    for (int p = 0; p < 2 * PW; p++) cur[p] = nxt[p];
 #pragma unroll
                     for (int p = 0; p < PW; p++) {
                         uint32_t r[8];
@@ -661,19 +674,20 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                         onehot_unit((cur[2 * p + 1] >> sh) & 15u, r[4], r[5], r[6], r[7]);
                         tmem_st8(tmem + lane_base + h * A_COLS + 8 * (sub * PW + p), r);
                     }
+                    if (t + 2 < t1) fetch(t + 2);
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.a_full[h]);
                 }
-                const long long c1_ = clock64();
+                const long long c1_ = (CLK ? clock64() : 0LL);
                 // ---- while the MMA warp multiplies: write out (this warp's part of) the half's previous tile --------------------------
                 if (WIDE) asm volatile("bar.sync %0, 256;" ::"r"(1 + h) : "memory");   // everybody's epilogue of that tile is in outT
                 if (t != first) copy_out(t - 2, S.outT[h][WIDE ? (k_tile - 1) & 1 : 0]);
-                const long long c2_ = clock64();
+                const long long c2_ = (CLK ? clock64() : 0LL);
                 mbar_wait(&S.d_full[h], ph);
                 tc_fence_after();
-                const long long c3_ = clock64();
+                const long long c3_ = (CLK ? clock64() : 0LL);
                 // ---- epilogue: this warp's half of the group's queries, 8 per step, loads one step ahead --------------------
                 {
                     const int nb = sub * nh;
@@ -708,7 +722,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     }
                     tc_fence_before();                                // (orders the TMEM reads before the next tile's a_full arrive)
                 }
-                ck[0] += c1_ - c0_; ck[4] += c2_ - c1_; ck[1] += c3_ - c2_; ck[2] += clock64() - c3_;
+                ck[0] += c1_ - c0_; ck[4] += c2_ - c1_; ck[1] += c3_ - c2_; ck[2] += (CLK ? clock64() : 0LL) - c3_;
             }
             if (first < t1) {                                         // the half's last tile of the item
                 if (WIDE) asm volatile("bar.sync %0, 256;" ::"r"(1 + h) : "memory");
@@ -717,7 +731,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             g += (uint32_t)(t1 - t0);
             // the item's refold queue (both halves together): the reference's recurrence for the pairs whose certificate failed,
             // bytes patched in place (the refolded value is never above the provisional one: a chunk minimum can only go down)
-            const long long f0_ = clock64();
+            const long long f0_ = (CLK ? clock64() : 0LL);
             asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_WORKERS) : "memory");
             {
                 const int nqd = min(S.n_queue, TC_QUEUE);
@@ -735,10 +749,10 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                 if (tid == 0) { if (S.n_queue) atomicAdd(W.hdr + 2, S.n_queue); S.n_queue = 0; }
                 asm volatile("bar.sync 3, %0;" ::"n"(32 * TC_WORKERS) : "memory");
             }
-            if (warp == 0 && lane == 0) atomicAdd(W.clk + CK_P_FLUSH, (unsigned long long)(clock64() - f0_));
+            if (CLK && warp == 0 && lane == 0) atomicAdd(W.clk + CK_P_FLUSH, (unsigned long long)((CLK ? clock64() : 0LL) - f0_));
             if (lane == 0) mbar_arrive(&S.item_empty[par]);
         }
-        if (warp == 0 && lane == 0) {
+        if (CLK && warp == 0 && lane == 0) {
             atomicAdd(W.clk + CK_E_WORK, (unsigned long long)ck[0]); atomicAdd(W.clk + CK_P_WAIT, (unsigned long long)ck[1]);
             atomicAdd(W.clk + CK_P_EPI, (unsigned long long)ck[2]); atomicAdd(W.clk + CK_P_BAR, (unsigned long long)ck[3]);
             atomicAdd(W.clk + CK_P_COPY, (unsigned long long)ck[4]);
@@ -816,15 +830,20 @@ int launch_ivf_scan_tc(const void *native, const int64_t *list_chunk_off, const 
     // one CTA per SM (the kernel owns all 512 TMEM columns): the slab + the rest of the shared memory is padded past half an SM's
     const size_t smem = ((sizeof(TcShared) + 127) / 128) * 128 + 2 * (size_t)M * TC_NT * 16 + 128;
     const size_t smem_req = smem > 120 * 1024 ? smem : 120 * 1024;
+    const char *ce = getenv("TKB_TC_CLOCKS");
+    const bool clk = ce && ce[0] == '1';
+#define TKB_TC_LAUNCH(WIDE_, CLK_)                                                                                                     \
+    do {                                                                                                                               \
+        TKB_CUDA(cudaFuncSetAttribute(ivf_scan_tc_kernel<16, WIDE_, CLK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req)); \
+        ivf_scan_tc_kernel<16, WIDE_, CLK_><<<n_sm, TC_THREADS2, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native),          \
+            list_chunk_off, list_size, n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W);                                \
+    } while (0)
     if (est == nullptr) {                         // push exchange: full 128-byte lines into the peer-mapped buffers
-        TKB_CUDA(cudaFuncSetAttribute(ivf_scan_tc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
-        ivf_scan_tc_kernel<16, true><<<n_sm, TC_THREADS2, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native), list_chunk_off,
-                                                                          list_size, n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W);
+        if (clk) TKB_TC_LAUNCH(true, true); else TKB_TC_LAUNCH(true, false);
     } else {
-        TKB_CUDA(cudaFuncSetAttribute(ivf_scan_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
-        ivf_scan_tc_kernel<16, false><<<n_sm, TC_THREADS2, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native), list_chunk_off,
-                                                                           list_size, n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W);
+        if (clk) TKB_TC_LAUNCH(false, true); else TKB_TC_LAUNCH(false, false);
     }
+#undef TKB_TC_LAUNCH
     TKB_LAUNCH_CHECK();
     // the (query, list) pairs the tensor-core path does not take (queries whose LUT fails the per-query precondition):
     // the CUDA-core kernel, which skips every query marked in skip_q

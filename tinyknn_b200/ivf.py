@@ -478,15 +478,23 @@ class IVF:
                                            D.ptr(dev["list_size"]), n_lists, M, D.ptr(tables), D.ptr(probes), Q, P,
                                            D.ptr(est), 0, D.ptr(seg_off), max(dev["max_real_chunks"], 1), _fp._order(), 1, st))
 
-    def _replay_rescore(self, dev, qn, probes, Q, P, k, pass_1, est, seg_off, order, out=None, cmin=None, buf=_fresh):
+    def _replay_rescore(self, dev, qn, probes, Q, P, k, pass_1, est, seg_off, order, out=None, cmin=None, buf=_fresh,
+                        cm_seg=None, absolute=False):
         """Ordered exact heap replay over the probed lists, then exact rescoring and the k nearest
-        (ref: ivf.py:137-163). `probes`/`seg_off` are the rows of these Q queries."""
+        (ref: ivf.py:137-163). `probes`/`seg_off` are the rows of these Q queries. absolute: `seg_off` holds absolute
+        addresses (segments in other GPUs' peer-mapped buffers, sharded.py's pull exchange), `cm_seg` is the compact layout
+        the chunk minima `cmin` are addressed by."""
         st = D.stream_ptr()
         n_lists = dev["n_lists"]
         hi_, hv_ = buf("heap_idx", (Q, pass_1), np.int64), buf("heap_val", (Q, pass_1), np.int32)
         fb = buf("fallback", (Q,), np.int32)
         with self._stage("replay"):
-            if cmin is not None:
+            if absolute:
+                check(lib.tkb_ivf_replay_fresh_pull_dev(D.ptr(seg_off), D.ptr(cm_seg) if cmin is not None else None, D.ptr(cmin),
+                                                        D.ptr(dev["list_chunk_off"]), D.ptr(dev["list_size"]), n_lists,
+                                                        D.ptr(dev["ids"]), D.ptr(probes), Q, P, D.ptr(hi_), D.ptr(hv_), pass_1, 1,
+                                                        int(dev.get("unique_ids", False)), D.ptr(fb), st))
+            elif cmin is not None:
                 check(lib.tkb_ivf_replay_fresh_cm_dev(D.ptr(est), D.ptr(seg_off), D.ptr(cmin), D.ptr(dev["list_chunk_off"]),
                                                       D.ptr(dev["list_size"]), n_lists, D.ptr(dev["ids"]), D.ptr(probes), Q, P,
                                                       D.ptr(hi_), D.ptr(hv_), pass_1, 1, int(dev.get("unique_ids", False)),

@@ -20,6 +20,13 @@ the home rank's HBM (tkb_ivf_plan_push_dev gives it absolute addresses). No send
 for split sizes: the only collective after the all-gather is a one-element all-reduce that orders "every scan has
 finished" before the replays. exchange="nccl" keeps the all-to-all path.
 
+exchange="pull" keeps the estimates where they are computed: every rank scans the lists it owns into its OWN peer-visible
+buffer (local stores, the scan runs at its single-GPU speed, chunk minima next to the estimates), the ranks all-gather the
+G + 1 numbers that describe their layouts (that collective is also the "every scan has finished" barrier), the home rank
+copies the chunk minima of its queries (1/16 of the bytes) and its replay fetches from the owners, through the peer
+mappings, only the chunks that can hold a candidate -- a few percent at 100M. 100M x 128, 8 GPUs: the pushed estimates were
+9 GB per rank and step over NVLink and doubled the scan's time; the pull moves ~1 GB.
+
 Both sides of a (scanning rank, home rank) pair order the segments by (query, probe slot), so offsets are
 computed locally from replicated metadata (tkb_ivf_plan_dev) and never travel. Replicated per rank:
 centroids + centroid codes, list sizes/owners, `ids`, the raw vectors for rescoring; sharded: the PQ codes.
@@ -38,6 +45,7 @@ from ._lib import PLAN_SEND, PLAN_RECV, PLAN_PUSH, PROBE_SKIP
 
 # default exchange of ShardedIVF.query_batch: "push" (NVLink peer stores from the scan kernel) or "nccl" (all-to-all)
 EXCHANGE = os.environ.get("TKB_EXCHANGE", "push")
+# "pull": estimates stay in the owner's HBM, the home rank's replay fetches minima + candidate chunks over NVLink (see above)
 # chunk minima inside the push exchange (the home buffer carries a minima region): the home rank's replay of long probe
 # lists reads 1 byte per chunk instead of 16 (100M x 128, 2 GPUs: replay 9.9 -> ~4.5 ms per step). Validated on hardware in
 # round 2 (tests/test_gpu_build_and_batch.py, tests/test_sharded_gpu.py).
@@ -323,15 +331,61 @@ class ShardedIVF:
                   push_cm=None if cm_table is None else (cm_table, Qh))
         return gb[:G]
 
+    def _scan_pull(self, tables, probes, Qh, P, buf_est, buf_cmin, capacity):
+        """Pull exchange, owner side: scan, for ALL G*Qh queries, of the probed lists this rank owns into this rank's own
+        peer-visible buffer (layout: grouped by the home rank of the query, then (q, s)), chunk minima next to it.
+        Returns the device int64[G + 1] that describes the layout: (total bytes, base of every home group)."""
+        ivf, dev, G, r = self.ivf, self.dev, self.world, self.rank
+        Q = G * Qh
+        seg = D.empty((Q, P), np.int64)
+        gb = D.empty((2 * G + 1,), np.int64)
+        ws = D.empty((max(Q, 1) * G,), np.int64)
+        from ._lib import lib, check
+        with ivf._stage("plan"):
+            check(lib.tkb_ivf_plan_pull_owner_dev(D.ptr(probes), Q, P, D.ptr(dev["list_size"]), D.ptr(dev["list_owner"]),
+                                                  dev["n_lists"], r, G, Qh, int(capacity), D.ptr(seg), D.ptr(gb), D.ptr(ws),
+                                                  8 * ws.numel(), D.stream_ptr()))
+        ivf._scan(dev, tables, probes, Q, P, buf_est, seg, codes_key="local_codes", off_key="local_chunk_off", cmin=buf_cmin)
+        return gb[G:2 * G + 1]
+
+    def _pull_home(self, probes_all, home, owner_base, owner_groups, cm_table):
+        """Pull exchange, home side: where the segments of this rank's queries live in the owners' buffers (absolute
+        addresses), the compact local layout the minima are copied into, and that copy. Returns (seg_addr, seg_local, cmin)."""
+        ivf, dev, G, r = self.ivf, self.dev, self.world, self.rank
+        Qh, P = home["Qh"], home["P"]
+        from ._lib import lib, check
+        seg_local, _ = ivf._plan(dev, home["probes"], Qh, P)
+        seg_addr = D.empty((Qh, P), np.int64)
+        gb = D.empty((2 * G + 1,), np.int64)
+        ws = D.empty((max(Qh, 1) * G,), np.int64)
+        with ivf._stage("plan"):
+            check(lib.tkb_ivf_plan_pull_home_dev(D.ptr(probes_all), G * Qh, P, D.ptr(dev["list_size"]), D.ptr(dev["list_owner"]),
+                                                 dev["n_lists"], r, G, Qh, D.ptr(owner_base), D.ptr(owner_groups), D.ptr(seg_addr),
+                                                 D.ptr(gb), D.ptr(ws), 8 * ws.numel(), D.stream_ptr()))
+        cmin = None
+        if cm_table is not None:
+            need = self.push_capacity(Qh, P) // 16 + 64
+            cmin = self.__dict__.get("_pull_cmin")
+            if cmin is None or cmin.numel() < need:
+                self.__dict__["_pull_cmin"] = cmin = D.empty((need,), np.uint8)
+            with ivf._stage("pull_minima"):
+                check(lib.tkb_ivf_pull_minima_dev(D.ptr(home["probes"]), Qh, P, D.ptr(dev["list_size"]), D.ptr(dev["list_owner"]),
+                                                  dev["n_lists"], D.ptr(seg_addr), D.ptr(seg_local), D.ptr(cm_table), D.ptr(cmin),
+                                                  D.stream_ptr()))
+        return seg_addr, seg_local, cmin
+
     def push_capacity(self, Qh, P):
         """Upper bound of a home rank's receive buffer, from replicated metadata only (every rank computes the same
         number): Qh queries x the P largest lists, padded to chunks."""
         sizes = np.sort(16 * ((np.asarray(self.dev["host_sizes"], dtype=np.int64) + 15) // 16))[::-1]
         return int(max(Qh, 1) * max(int(sizes[:P].sum()), 16))
 
-    def _peers(self, Qh, P):
-        """The peer-mapped receive buffers for batches of this shape (collective when they have to be (re)allocated);
-        None when they would not fit comfortably (then the all-to-all path is used)."""
+    def _peers(self, Qh, P, pull=False):
+        """The peer-mapped buffers for batches of this shape (collective when they have to be (re)allocated); None when they
+        would not fit comfortably (then the all-to-all path is used). Push: a home rank's receive buffer, bounded by
+        `push_capacity`. Pull: an owner's buffer holds its lists' segments for the queries of ALL ranks -- the same bytes on
+        average, up to `world` times as many when every query probes this rank's lists; it gets what memory allows up to that
+        bound and the plan's capacity guard covers the rest (an overflowing batch is repeated through the push exchange)."""
         need = self.push_capacity(Qh, P)
         pb = self.__dict__.get("_pb")
         if pb is not None and pb.nbytes >= need:
@@ -339,15 +393,18 @@ class ShardedIVF:
         t = D.torch()
         t.cuda.empty_cache()                                  # the buffers come from cudaMalloc, not from torch's cache
         free, _ = t.cuda.mem_get_info()
-        fits = t.tensor([int(2 * need <= free // 3)], dtype=t.int32, device=D.device())
+        budget = (free // 2) // 2                             # two buffers (+ 1/16 for the minima) inside half of the free memory
+        room = t.tensor([int(budget * 16 // 17)], dtype=t.int64, device=D.device())
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_reduce(fits, op=dist.ReduceOp.MIN, group=self.group)
-        if not int(fits.item()):
+            dist.all_reduce(room, op=dist.ReduceOp.MIN, group=self.group)
+        room = int(room.item())
+        if room < need:
             return None
         if pb is not None:
             pb.close(self.group)
-        self.__dict__["_pb"] = pb = PeerBuffers(need, self.group, self.rank, self.world)
+        size = min(self.world * need, room) if pull else need
+        self.__dict__["_pb"] = pb = PeerBuffers(size, self.group, self.rank, self.world)
         return pb
 
     def close(self):
@@ -357,31 +414,75 @@ class ShardedIVF:
         if pb is not None:
             pb.close(self.group)
 
-    def _finish(self, home, est_r, seg_r, k, pass_1, cmin_r=None):
-        """Ordered heap replay over the received estimates, exact rescoring, k nearest (device tensors)."""
+    def _defer_overflow_check(self, groups, nbytes):
+        """to_host=False callers get device tensors and no synchronisation: the owners' totals are copied to pinned host
+        memory behind the batch and looked at once the copy has completed (`check_overflow()`, also called by every later
+        batch for the copies that are done by then)."""
+        t = D.torch()
+        host = t.empty((groups.shape[0],), dtype=t.int64).pin_memory()
+        host.copy_(groups[:, 0], non_blocking=True)
+        ev = t.cuda.Event()
+        ev.record()
+        self.__dict__.setdefault("_pending_checks", []).append((host, ev, int(nbytes)))
+        self.check_overflow(wait=False)
+
+    def check_overflow(self, wait=True):
+        """Raises if a `to_host=False` pull batch left segments out because an owner's buffer was too small (its results are
+        then incomplete; repeat it with exchange="push"). wait=False: only the batches whose totals have already arrived."""
+        pend = self.__dict__.get("_pending_checks", [])
+        keep = []
+        for host, ev, nbytes in pend:
+            if not wait and not ev.query():
+                keep.append((host, ev, nbytes))
+                continue
+            ev.synchronize()
+            if int(host.max()) > nbytes:
+                self.__dict__["_pending_checks"] = []
+                raise RuntimeError("pull exchange: an owner's estimate buffer overflowed (%d > %d bytes); the results of that "
+                                   "to_host=False batch are incomplete -- repeat it with exchange='push'" % (int(host.max()), nbytes))
+        self.__dict__["_pending_checks"] = keep
+
+    def _finish(self, home, est_r, seg_r, k, pass_1, cmin_r=None, cm_seg=None):
+        """Ordered heap replay over the received estimates, exact rescoring, k nearest (device tensors).
+        Pull exchange: est_r None, seg_r absolute addresses, cm_seg the compact layout of the minima."""
         return self.ivf._replay_rescore(self.dev, home["lut"]["q"], home["probes"], home["Qh"], home["P"], k, pass_1,
-                                        est_r, seg_r, "device", cmin=cmin_r)
+                                        est_r, seg_r, "device", cmin=cmin_r, cm_seg=cm_seg, absolute=est_r is None)
 
     def query_batch(self, queries, k, n_probes=1, pass_1=None, return_distances=False, to_host=True, exchange=None):
         """Collective. queries: this rank's f32 (Qh, d) block (same Qh on every rank). Selections use the
         device order (ascending distance, ties by heap slot). Returns the results of this rank's block.
-        exchange: "push" (scan stores into the home rank's HBM over NVLink peer memory), "nccl" (send buffer +
-        all-to-all) or None = the module default EXCHANGE; every rank must pass the same value."""
+        exchange: "push" (scan stores into the home rank's HBM over NVLink peer memory), "pull" (estimates stay with the
+        owner, the home rank's replay fetches minima and candidate chunks over NVLink), "nccl" (send buffer + all-to-all)
+        or None = the module default EXCHANGE; every rank must pass the same value."""
         ivf, G = self.ivf, self.world
         exchange = EXCHANGE if exchange is None else exchange
-        assert exchange in ("push", "nccl")
+        assert exchange in ("push", "pull", "nccl")
         if pass_1 is None:
             pass_1 = (n_probes + 1) * k + 1                                     # ref: ivf.py:135-136
         home = self._home(queries, n_probes)
         tables, probes = home["lut"]["tables"], home["probes"]
         Qh, P = home["Qh"], home["P"]
-        pb = self._peers(Qh, P) if (exchange == "push" and G > 1) else None
-        self.last_exchange = "push" if pb is not None else ("nccl" if G > 1 else "local")
+        pb = self._peers(Qh, P, exchange == "pull") if (exchange in ("push", "pull") and G > 1) else None
+        self.last_exchange = exchange if pb is not None else ("nccl" if G > 1 else "local")
         if G > 1:
             with ivf._stage("all_gather"):
                 tables = all_gather_rows(tables, self.group)
                 probes = all_gather_rows(probes, self.group)
-        if pb is not None:
+        groups = None
+        if pb is not None and exchange == "pull":
+            b = pb.turn
+            pb.turn = (b + 1) % pb.n_buf
+            from . import ivf as _ivf_mod
+            use_cm = (PUSH_CMIN and _ivf_mod.CMIN_CHUNKS > 0
+                      and P * max(self.dev["max_real_chunks"], 1) >= _ivf_mod.CMIN_CHUNKS)
+            # bytes of the owner buffer a batch may use: all of it, unless the caller set `pull_capacity` (tests of the guard)
+            cap = min(pb.nbytes, int(self.__dict__.get("pull_capacity") or pb.nbytes))
+            mine = self._scan_pull(tables, probes, Qh, P, pb.local[b], pb.local_cmin[b] if use_cm else None, cap)
+            with ivf._stage("barrier"):          # every rank's layout numbers; also orders "every scan kernel has completed"
+                groups = all_gather_rows(mine[None], self.group)                 # (G, G + 1)
+            seg_r, cm_seg, cmin_r = self._pull_home(probes, home, pb.bases[b], groups, pb.cm_tables[b] if use_cm else None)
+            est_r = None
+        elif pb is not None:
             import torch.distributed as dist
             b = pb.turn
             pb.turn = (b + 1) % pb.n_buf
@@ -402,7 +503,18 @@ class ShardedIVF:
             else:
                 est_r = est_s
             cmin_r = None
-        ids, cnt, dst = self._finish(home, est_r, seg_r, k, pass_1, cmin_r)
+        if groups is not None:
+            ids, cnt, dst = self._finish(home, None, seg_r, k, pass_1, cmin_r, cm_seg)
+            # an owner whose segments did not fit its buffer left them out (the plan's capacity guard): every rank sees the same
+            # totals, so every rank repeats the batch through the push exchange
+            if to_host:
+                if int(groups[:, 0].max().item()) > cap:
+                    self.pull_overflows = self.__dict__.get("pull_overflows", 0) + 1
+                    return self.query_batch(queries, k, n_probes, pass_1, return_distances, to_host, "push")
+            else:
+                self._defer_overflow_check(groups, cap)
+        else:
+            ids, cnt, dst = self._finish(home, est_r, seg_r, k, pass_1, cmin_r)
         if to_host:
             ids, cnt, dst = ids.cpu().numpy(), cnt.cpu().numpy(), dst.cpu().numpy()
         return (ids, cnt, dst) if return_distances else (ids, cnt)
