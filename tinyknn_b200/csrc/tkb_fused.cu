@@ -224,8 +224,19 @@ ivf_fused_kernel(const FusedArgs a)
             LutMeta m;
             m.eligible = fast_allowed && range <= 31 && N[0] <= 128 && N[1] <= 128;
             m.bias_tot = bias[0] + bias[1];
-            m.k0 = 127 - N[0] + bias[0];
-            m.k1 = 127 - N[1] + bias[1];
+            int kk[2] = {127, 127};                                  // certificate thresholds as in prepare_lut (tkb_scan_core.cuh)
+            {
+                int Pm[2] = {0, 0}, suf[2] = {N[0], N[1]};
+                bool found[2] = {false, false};
+                for (int j = 0; j < M; j++) {
+                    const int l = (j >> 1) & 1, *st = lutstat + 3 * (t * M + j);
+                    suf[l] -= st[1];
+                    Pm[l] += max(0, st[2] - st[0]);
+                    if (!found[l] && Pm[l] > 127) { found[l] = true; kk[l] = 127 - suf[l]; }
+                }
+            }
+            m.k0 = kk[0] + bias[0];
+            m.k1 = kk[1] + bias[1];
             meta[t] = m;
         }
         if (tid == 0) {

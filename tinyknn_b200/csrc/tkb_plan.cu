@@ -245,13 +245,31 @@ pull_minima_kernel(const int32_t *__restrict__ probes, int64_t n_seg, const int3
     const int n = (list_size[l] + 15) >> 4;
     const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)(cm_table[list_owner ? list_owner[l] : 0] + (src_a >> 4)));
     uint8_t *dst = cmin_local + (dst_o >> 4);
-    for (int i0 = 0; i0 < n; i0 += 128) {
-        uint8_t v[4];
+    // head bytes up to the first 4-byte boundary of the destination, then destination-aligned words assembled from the two
+    // aligned source words that hold their bytes (the second is the next lane's first: one 128-byte request per 32 words), then the tail
+    const int head = min(n, (int)((4 - ((uintptr_t)dst & 3)) & 3));
+    if (lane < head) dst[lane] = src[lane];
+    const int n_words = (n - head) >> 2;
+    const uint8_t *sa = src + head;
+    const int mis = (int)((uintptr_t)sa & 3);
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(sa - mis);
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+    for (int j0 = 0; j0 < n_words; j0 += 128) {
+        uint32_t lo[4], hi[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) { const int i = i0 + 32 * u + lane; v[u] = i < n ? src[i] : (uint8_t)0; }
+        for (int u = 0; u < 4; u++) {
+            const int j = j0 + 32 * u + lane;
+            lo[u] = hi[u] = 0;
+            if (j < n_words) { lo[u] = sw[j]; if (mis) hi[u] = sw[j + 1]; }
+        }
 #pragma unroll
-        for (int u = 0; u < 4; u++) { const int i = i0 + 32 * u + lane; if (i < n) dst[i] = v[u]; }
+        for (int u = 0; u < 4; u++) {
+            const int j = j0 + 32 * u + lane;
+            if (j < n_words) dw[j] = mis ? (lo[u] >> (8 * mis)) | (hi[u] << (32 - 8 * mis)) : lo[u];
+        }
     }
+    const int done = head + 4 * n_words;
+    if (lane < n - done) dst[done + lane] = src[done + lane];
 }
 
 int launch_pull_minima(const int32_t *probes, int Q, int P, const int32_t *list_size, const int32_t *list_owner, int n_lists,

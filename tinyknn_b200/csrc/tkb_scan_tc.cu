@@ -82,26 +82,46 @@ __host__ __device__ inline size_t tc_carve(void *base, int Q, int P, int n_lists
     return o;
 }
 
-// one warp per query: N_l = sum over the lane's rows of max(0, -min_c T[j][c]); eligible iff both <= 128
+// one warp per query: N_l = sum over the lane's rows of max(0, -min_c T[j][c]); eligible iff both <= 128 (no prefix of the fold
+// can go below -128). Threshold of the certificate (S_l <= k_l => no prefix can exceed 127, so the fold is the plain sum):
+// a prefix that ends at row k is at most Pmax_k = sum of the rows' largest positive entries so far, and at most
+// S_l + (negatives the rows AFTER k can still contribute). It can pass 127 only from the first row k* with Pmax_k* > 127 on, where
+// the second bound is largest: k_l = 127 - sum_{j > k*} max(0, -min_c T[j][c])  (127 when Pmax never passes 127: then S_l cannot either).
+// With the usual tables (row range ~25, minimum ~ -3) that is ~120 instead of 127 - N_l ~ 80: 500 times fewer pairs to refold.
 __global__ void tc_query_meta_kernel(const uint8_t *__restrict__ tables, int Q, int M, TcQueryMeta *__restrict__ qmeta,
                                      uint8_t *__restrict__ skip_q)
 {
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= Q) return;
-    int n0 = 0, n1 = 0;
+    int n0 = 0, n1 = 0, rneg = 0, rmax = 0;
     for (int j = lane; j < M; j += 32) {
         const uint4 r = reinterpret_cast<const uint4 *>(tables + (size_t)q * M * 16)[j];
         const uint32_t m4 = __vmins4(__vmins4(r.x, r.y), __vmins4(r.z, r.w));
         const uint32_t m2 = __vmins4(m4, m4 >> 16);
         const int mn = (int)(int8_t)(__vmins4(m2, m2 >> 8) & 0xffu);
+        const uint32_t x4 = __vmaxs4(__vmaxs4(r.x, r.y), __vmaxs4(r.z, r.w));
+        const uint32_t x2 = __vmaxs4(x4, x4 >> 16);
+        const int mx = (int)(int8_t)(__vmaxs4(x2, x2 >> 8) & 0xffu);
         const int c = mn < 0 ? -mn : 0;
         if ((j >> 1) & 1) n1 += c; else n0 += c;
+        rneg = c; rmax = mx > 0 ? mx : 0;                          // (row `lane` when M <= 32)
     }
     for (int o = 16; o > 0; o >>= 1) { n0 += __shfl_xor_sync(FULL, n0, o); n1 += __shfl_xor_sync(FULL, n1, o); }
+    int k0 = 127 - n0, k1 = 127 - n1;
+    if (M <= 32) {                                                   // every lane walks the rows in fold order (shuffles broadcast them)
+        int P0 = 0, P1 = 0, s0 = n0, s1 = n1;
+        bool f0 = false, f1 = false;
+        k0 = k1 = 127;
+        for (int j = 0; j < M; j++) {
+            const int rm = __shfl_sync(FULL, rmax, j), rn = __shfl_sync(FULL, rneg, j);
+            if ((j >> 1) & 1) { s1 -= rn; P1 += rm; if (!f1 && P1 > 127) { f1 = true; k1 = 127 - s1; } }
+            else              { s0 -= rn; P0 += rm; if (!f0 && P0 > 127) { f0 = true; k0 = 127 - s0; } }
+        }
+    }
     if (lane == 0) {
         TcQueryMeta m;
         m.elig = (n0 <= 128 && n1 <= 128) ? 1 : 0;
-        m.k0 = (int16_t)(127 - n0); m.k1 = (int16_t)(127 - n1); m.pad = 0;
+        m.k0 = (int16_t)k0; m.k1 = (int16_t)k1; m.pad = 0;
         qmeta[q] = m;
         skip_q[q] = (uint8_t)m.elig;             // the CUDA-core kernel skips the queries this kernel handles
     }
@@ -406,12 +426,15 @@ __device__ __noinline__ void tc_flagged8(TcShared &S, const uint2 *kq2, uint4 pa
 // writes out what it computed itself (32-byte pieces, no barrier), which is faster into local memory.
 // CLK: the cycle counters of the roles (TcClock) are kept only in the instance bench.py's stage pass asks for (TKB_TC_CLOCKS=1): they
 // cost a dozen registers in a kernel that sits at its register limit.
-template <int PH, bool WIDE, bool CLK>
+// DBG (tools/tc_probe.py, TKB_TC_DBG=<bits>): an instance whose phases can be switched off one by one to see what the others cost
+// (results are then wrong): 1 no copy-out, 2 copy-out without its global stores, 4 no epilogue arithmetic, 8 no expansion,
+// 16 no MMAs, 32 certificate failures ignored.
+template <int PH, bool WIDE, bool CLK, bool DBG = false>
 __global__ void __launch_bounds__(TC_THREADS2, 1)
 ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict__ list_chunk_off,
                    const int32_t *__restrict__ list_size, int n_lists, const uint8_t *__restrict__ tables, int P,
                    uint8_t *__restrict__ est, const int64_t *__restrict__ seg_off, uint8_t *__restrict__ cmin,
-                   const int64_t *__restrict__ cm_home, int q_per_rank, TcWork W)
+                   const int64_t *__restrict__ cm_home, int q_per_rank, TcWork W, int dbg)
 {
     constexpr int M = 2 * PH;
     constexpr int A_COLS = 8 * PH;                                   // 32-bit columns of one one-hot tile
@@ -536,6 +559,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     tc_fence_after();
                     const long long c1_ = (CLK ? clock64() : 0LL), c2_ = c1_;
                     if (elect_one()) {
+                        if (!(DBG && (dbg & 16)))
 #pragma unroll
                         for (int p = 0; p < PH; p++)
                             umma_i8_ts(tmem + D_COL0 + (2 * b + (p & 1)) * TC_NT, tmem + b * A_COLS + 8 * p,
@@ -635,6 +659,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                                 o[q4] = prmt(lo, hi, 0x5410u);
                             }
                             const long long off = I.dst[n + j] + 16LL * chunk;
+                            if (DBG && (dbg & 2)) { if ((o[0] ^ o[1] ^ o[2] ^ o[3]) == 0x12345678u) est[off] = 1; continue; }
                             *reinterpret_cast<uint4 *>(est + off) = make_uint4(o[0], o[1], o[2], o[3]);
                             uint8_t *cm = reinterpret_cast<uint8_t *>((uintptr_t)I.cmb[n + j]);
                             if (cm) {
@@ -667,6 +692,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     uint32_t cur[2 * PW];
 #pragma unroll
                     for (int p = 0; p < 2 * PW; p++) cur[p] = nxt[p];
+                    if (!(DBG && (dbg & 8)))
 #pragma unroll
                     for (int p = 0; p < PW; p++) {
                         uint32_t r[8];
@@ -683,13 +709,13 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                 const long long c1_ = (CLK ? clock64() : 0LL);
                 // ---- while the MMA warp multiplies: write out (this warp's part of) the half's previous tile --------------------------
                 if (WIDE) asm volatile("bar.sync %0, 256;" ::"r"(1 + h) : "memory");   // everybody's epilogue of that tile is in outT
-                if (t != first) copy_out(t - 2, S.outT[h][WIDE ? (k_tile - 1) & 1 : 0]);
+                if (t != first && !(DBG && (dbg & 1))) copy_out(t - 2, S.outT[h][WIDE ? (k_tile - 1) & 1 : 0]);
                 const long long c2_ = (CLK ? clock64() : 0LL);
                 mbar_wait(&S.d_full[h], ph);
                 tc_fence_after();
                 const long long c3_ = (CLK ? clock64() : 0LL);
                 // ---- epilogue: this warp's half of the group's queries, 8 per step, loads one step ahead --------------------
-                {
+                if (!(DBG && (dbg & 4))) {
                     const int nb = sub * nh;
                     uint32_t *outT = S.outT[h][WIDE ? k_tile & 1 : 0];
                     uint32_t la[4], lc[4];                            // lane sums of two queries per register (s16x2: |S| <= 16 * 128)
@@ -714,7 +740,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                             fl = __viaddmax_s16x2(pc[u], k.y, fl);
                         }
                         uint32_t o0 = prmt(e2[0], e2[1], 0x6420u), o1 = prmt(e2[2], e2[3], 0x6420u);
-                        if (__any_sync(FULL, (int)(int16_t)(fl & 0xffffu) > 0 || (int)(int16_t)(fl >> 16) > 0))
+                        if (!(DBG && (dbg & 32)) && __any_sync(FULL, (int)(int16_t)(fl & 0xffffu) > 0 || (int)(int16_t)(fl >> 16) > 0))
                             tc_flagged8<PH>(S, I.kq2, make_uint4(pa[0], pa[1], pa[2], pa[3]), make_uint4(pc[0], pc[1], pc[2], pc[3]), n0, nq,
                                             t - t0, row, o0, o1, nat32, tile0 + t, B, cm_home ? &S.refold_mark[h][0][0] : nullptr);
                         outT[tc_out_addr(row, n0 >> 2)] = o0;
@@ -722,11 +748,12 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     }
                     tc_fence_before();                                // (orders the TMEM reads before the next tile's a_full arrive)
                 }
+                if (DBG && (dbg & 4)) tc_fence_before();
                 ck[0] += c1_ - c0_; ck[4] += c2_ - c1_; ck[1] += c3_ - c2_; ck[2] += (CLK ? clock64() : 0LL) - c3_;
             }
             if (first < t1) {                                         // the half's last tile of the item
                 if (WIDE) asm volatile("bar.sync %0, 256;" ::"r"(1 + h) : "memory");
-                copy_out(first + 2 * ((t1 - 1 - first) >> 1), S.outT[h][WIDE ? (k_tile - 1) & 1 : 0]);
+                if (!(DBG && (dbg & 1))) copy_out(first + 2 * ((t1 - 1 - first) >> 1), S.outT[h][WIDE ? (k_tile - 1) & 1 : 0]);
             }
             g += (uint32_t)(t1 - t0);
             // the item's refold queue (both halves together): the reference's recurrence for the pairs whose certificate failed,
@@ -832,13 +859,19 @@ int launch_ivf_scan_tc(const void *native, const int64_t *list_chunk_off, const 
     const size_t smem_req = smem > 120 * 1024 ? smem : 120 * 1024;
     const char *ce = getenv("TKB_TC_CLOCKS");
     const bool clk = ce && ce[0] == '1';
+    const char *de = getenv("TKB_TC_DBG");
+    const int dbg = de ? atoi(de) : 0;
 #define TKB_TC_LAUNCH(WIDE_, CLK_)                                                                                                     \
     do {                                                                                                                               \
         TKB_CUDA(cudaFuncSetAttribute(ivf_scan_tc_kernel<16, WIDE_, CLK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req)); \
         ivf_scan_tc_kernel<16, WIDE_, CLK_><<<n_sm, TC_THREADS2, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native),          \
-            list_chunk_off, list_size, n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W);                                \
+            list_chunk_off, list_size, n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W, 0);                             \
     } while (0)
-    if (est == nullptr) {                         // push exchange: full 128-byte lines into the peer-mapped buffers
+    if (dbg && est != nullptr) {                  // probe instance (wrong results by design)
+        TKB_CUDA(cudaFuncSetAttribute(ivf_scan_tc_kernel<16, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
+        ivf_scan_tc_kernel<16, false, false, true><<<n_sm, TC_THREADS2, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native),
+            list_chunk_off, list_size, n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W, dbg);
+    } else if (est == nullptr) {                         // push exchange: full 128-byte lines into the peer-mapped buffers
         if (clk) TKB_TC_LAUNCH(true, true); else TKB_TC_LAUNCH(true, false);
     } else {
         if (clk) TKB_TC_LAUNCH(false, true); else TKB_TC_LAUNCH(false, false);
