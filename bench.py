@@ -68,7 +68,7 @@ def parse():
     ap.add_argument("--cpu-queries", type=int, default=2048,
                     help="workloads whose raw vectors stay on the GPU (10M/100M): the CPU arm cycles through this many queries of "
                          "the batch; the rows their rescoring reads are recorded in an untimed pass of the oracle and kept on the host")
-    ap.add_argument("--exchange", default=os.environ.get("TKB_EXCHANGE", "push"), choices=["push", "pull", "nccl"],
+    ap.add_argument("--exchange", default=os.environ.get("TKB_EXCHANGE", "pull"), choices=["push", "pull", "nccl"],
                     help="--shard lists: 'push' = the scan kernel stores estimates into the home rank's HBM over NVLink peer "
                          "memory, 'pull' = estimates stay in the owner's HBM and the home rank's replay fetches chunk minima and "
                          "candidate chunks over NVLink (both fall back to nccl when peer buffers cannot be mapped), "

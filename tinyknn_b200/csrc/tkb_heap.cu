@@ -398,6 +398,12 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
     const int q0 = blockIdx.x * QPC;
     const uint32_t flip = SIGNED ? 0u : 0x80u;                             // stored byte = value ^ flip
     const int init = 127;                                                  // stored form of the reference's 127 / 255
+    // qpw < 0: FREE-RUNNING warps. Warp w owns the queries [w |qpw|, (w + 1) |qpw|) of the CTA in both halves of a round, so
+    // a round ends with __syncwarp instead of two CTA barriers: no warp waits for the slowest producer of the CTA, and every
+    // warp (not just QPC / (32 / L) of them) has queries to consume. The ncu capture of round 2 showed 21 of 27 stall cycles
+    // per issue at those barriers -- but see rq_qpw_arg: measured slower, off by default.
+    const bool indep = qpw < 0;
+    const int QPW = indep ? -qpw : ((qpw > 0 && qpw <= 32 / L) ? qpw : 32 / L);
 
     for (int i = tid; i < QPC * HS; i += NTH) {
         const int j = i % HS;
@@ -448,7 +454,7 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
     for (;;) {
         // ---- produce (as in replay_rq_kernel; records are packed words) -----------------------------
         bool more = false;
-        for (int t = warp; t < QPC; t += n_warps) {
+        for (int t = indep ? warp * QPW : warp; t < (indep ? min(QPC, (warp + 1) * QPW) : QPC); t += indep ? 1 : n_warps) {
             const int *c = cum + (size_t)t * (P + 1);
             const int total = c[P];
             const int cursor = s_cursor[t];
@@ -623,13 +629,13 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
             if (lane == 0) { s_cursor[t] = end; s_seg[t] = sg; s_count[t] = count; s_round[t] = 1; qu[count] = RQ2_SENTINEL; qu[count + 1] = RQ2_SENTINEL; }
             more = true;
         }
-        if (!__syncthreads_or(more)) break;
+        if (indep) { __syncwarp(); if (!more) break; }                      // `more` is warp-uniform
+        else if (!__syncthreads_or(more)) break;
         // ---- consume: L lanes per query, 32/L queries per warp. The step is branch-free (the queries of a warp are in
         //      different states; divergent code would be issued once per state and the loop is issue-bound) -----------
         {
             // qpw queries per consumer warp (default 32 / L; fewer = less lock-step waste, more warps busy: the replay model
             // of tools/replay_model.py puts 8 lock-stepped queries at +26 % steps over one query per warp)
-            const int QPW = (qpw > 0 && qpw <= 32 / L) ? qpw : 32 / L;
             const int role = lane % L;
             for (int tb = warp * QPW; tb < QPC; tb += n_warps * QPW) {
                 const int t = tb + lane / L;
@@ -684,8 +690,9 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                 if (mine && role == 0) s_bound[t] = (int)rootm >> 24;
             }
         }
-        __syncthreads();
+        if (indep) __syncwarp(); else __syncthreads();
     }
+    if (indep) __syncthreads();                                            // every warp's queries are finished
 
     // ---- resolve labels and write the heap arrays --------------------------------------------------
     for (int i = tid; i < R * QPC; i += NTH) {
@@ -871,6 +878,20 @@ static int rq_qpw()
     return v;
 }
 
+// Free-running warps (TKB_RQ_INDEP=1, off by default): every warp of the CTA owns qpc / n_warps queries for both halves of a
+// round. Measured on a B200 (100M x 128): no CTA barrier stalls any more, but eight warps each walk the sift chain for two
+// queries where two warps walked it for eight, and the consume step is issue-bound: probe selection 0.32 -> 0.58 ms, lists
+// 4.00 -> 4.14 ms. Kept as an A/B switch. Returns the kernel's qpw argument: negative = free-running with that many queries per warp.
+static int rq_qpw_arg(const RqGeom &g, int lanes)
+{
+    static int indep = -1;
+    if (indep < 0) { const char *e = getenv("TKB_RQ_INDEP"); indep = e ? atoi(e) : 0; }
+    const int n_warps = g.threads / 32;
+    if (!indep || rq_qpw() || g.qpc % n_warps != 0) return rq_qpw();
+    const int per = g.qpc / n_warps;
+    return (per >= 1 && per <= 32 / lanes) ? -per : rq_qpw();
+}
+
 template <bool SIGNED>
 static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t *seg_off, int64_t n_chunks0, int n0,
                      const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, const int64_t *ids,
@@ -884,7 +905,7 @@ static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t
             TKB_CUDA(cudaFuncSetAttribute(replay_rq2_kernel<SIGNED, LANES, CMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
             replay_rq2_kernel<SIGNED, LANES, CMV><<<blocks, g.threads, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off, \
                                                                                      list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val,  \
-                                                                                     R, fallback, g.qpc, g.qcap, cmin, rq_qpw(), cm_seg);       \
+                                                                                     R, fallback, g.qpc, g.qcap, cmin, rq_qpw_arg(g, LANES), cm_seg); \
         } while (0)
         if (cmin) { if (g.lanes == 4) TKB_RQ2_LAUNCH(4, true); else TKB_RQ2_LAUNCH(8, true); }
         else      { if (g.lanes == 4) TKB_RQ2_LAUNCH(4, false); else TKB_RQ2_LAUNCH(8, false); }

@@ -254,16 +254,17 @@ pull_minima_kernel(const int32_t *__restrict__ probes, int64_t n_seg, const int3
     const int mis = (int)((uintptr_t)sa & 3);
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(sa - mis);
     uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
-    for (int j0 = 0; j0 < n_words; j0 += 128) {
-        uint32_t lo[4], hi[4];
+    constexpr int U = 8;                                           // 1 KB of a segment in flight per warp (the loads cross NVLink)
+    for (int j0 = 0; j0 < n_words; j0 += 32 * U) {
+        uint32_t lo[U], hi[U];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < U; u++) {
             const int j = j0 + 32 * u + lane;
             lo[u] = hi[u] = 0;
             if (j < n_words) { lo[u] = sw[j]; if (mis) hi[u] = sw[j + 1]; }
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < U; u++) {
             const int j = j0 + 32 * u + lane;
             if (j < n_words) dw[j] = mis ? (lo[u] >> (8 * mis)) | (hi[u] << (32 - 8 * mis)) : lo[u];
         }
