@@ -222,6 +222,22 @@ TKB_API int tkb_encode_dev(const void *rows, int rows_dtype, int64_t n_rows, int
 TKB_API int tkb_assign_dev(const void *rows, int dtype, int64_t n, int d, const void *centers, int C, const void *xnorm,
                    const void *cnorm, int k, int32_t *nearest, void *scratch, int64_t scratch_bytes, void *stream);
 
+/* k-means on the device for the two `fit` steps (build time; replaces the arithmetic of sklearn.cluster.KMeans in
+ * tinyknn/ivf.py:19-51 and tinyknn/fast_pq.py:106-145). PARITY UNPINNED by nature (the reference's k-means++ seeding draws from
+ * numpy's global random state); deterministic given (rows, initial centers): cluster sums are fixed-point integer atomics.
+ *   tkb_kmeans_dev: rows f32 [n][d], centers f32 [k][d] in (initial) / out, Lloyd iterations until no row changes its cluster or
+ *       max_iters; assign int32[n] out = nearest centre of every row for the returned centers (tkb_assign_dev's exact chains);
+ *       *iters_done (host) = iterations run; absmax >= max |rows[i][j]| (scales the fixed point). Synchronises the stream once
+ *       per iteration.
+ *   tkb_kmeans_pq_dev: the M = D / dpb independent 16-centre problems of FastPQ in one pass over the rows per iteration;
+ *       centers f32 [16][D] in FastPQ's layout (centre c of block m at [c][m*dpb .. (m+1)*dpb)) in / out; dpb <= 8;
+ *       workspace >= 16 KB + 160 * D bytes. */
+TKB_API int tkb_kmeans_workspace(int64_t n, int d, int k, int64_t *bytes);
+TKB_API int tkb_kmeans_dev(const float *rows, int64_t n, int d, int k, float *centers, int max_iters, double absmax, int32_t *assign,
+                   int *iters_done, void *workspace, int64_t workspace_bytes, void *stream);
+TKB_API int tkb_kmeans_pq_dev(const float *rows, int64_t n, int D, int dpb, float *centers, int iters, double absmax, void *workspace,
+                      int64_t workspace_bytes, void *stream);
+
 /* Device-native code layout for the fast scan (chosen at upload, round-trips to the reference layout).
  * tile = 8 chunks; the 16 bytes of (tile t, pair p, chunk slot s) sit at ((t*M/2 + p)*8 + s)*16 and hold
  * 8 halfwords: halfword g = codes of sub-quantizer 2p for vectors 4g..4g+3 (nibble i = vector 4g+i),

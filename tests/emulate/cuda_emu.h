@@ -176,6 +176,8 @@ inline float __fadd_rn(float a, float b) { return a + b; }          // compile w
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
+inline long long __double2ll_rn(double v) { return std::llrint(v); }      // (default rounding mode: to nearest even)
+inline int __float2int_rn(float v) { return (int)std::lrintf(v); }
 inline float __int_as_float(int v) { return emu::from_bits<float>((uint64_t)(uint32_t)v); }
 inline int __float_as_int(float v) { return (int)(uint32_t)emu::bits_of(v); }
 inline double __longlong_as_double(long long v) { return emu::from_bits<double>((uint64_t)v); }

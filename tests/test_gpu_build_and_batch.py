@@ -69,6 +69,84 @@ def test_assign_device_equals_knn_brute(n, d, C, dtype, metric):
 
 
 
+def _inertia(X, C):
+    d2 = (np.einsum("ij,ij->i", X, X)[:, None] + np.einsum("ij,ij->i", C, C)[None, :] - 2.0 * X @ C.T)
+    return float(d2.min(axis=1).sum())
+
+
+def test_fit_device_pq_codebooks_quality_and_determinism():
+    """FastPQ.fit(device=True): the M per-block k-means problems on the GPU (tkb_kmeans_pq_dev). Parity with the reference is
+    unpinned by nature (its fit is random); the clustering must be as good as sklearn's on the same blocks (inertia within
+    10 %), a deterministic function of (data, seed), and usable: transform + distance tables + top() find the true neighbours
+    as often as with the host fit."""
+    import sklearn.cluster
+    from tinyknn_b200 import FastPQ
+    rng = np.random.default_rng(5)
+    means = rng.normal(size=(40, 16)) * 3
+    X = (means[rng.integers(40, size=6000)] + rng.normal(size=(6000, 16))).astype(np.float32)
+    pq_a = FastPQ(2, rotate_dim=None).fit(X, device=True, seed=3)
+    pq_b = FastPQ(2, rotate_dim=None).fit(X, device=True, seed=3)
+    assert np.array_equal(pq_a.centers, pq_b.centers) and np.isfinite(pq_a.centers).all()
+    assert pq_a.centers.shape == (16, 16)
+    for m in range(8):
+        blk = X[:, 2 * m:2 * m + 2].astype(np.float64)
+        sk = sklearn.cluster.KMeans(16, n_init=2, random_state=0).fit(blk)
+        assert _inertia(blk, pq_a.centers[:, 2 * m:2 * m + 2].astype(np.float64)) <= 1.10 * sk.inertia_
+    pq_h = FastPQ(2, rotate_dim=None).fit(X, device=False)
+    qs = X[:200] + 0.05 * rng.normal(size=(200, 16)).astype(np.float32)
+    hits = []
+    for pq in (pq_a, pq_h):
+        td = pq.transform(X)
+        hits.append(sum(i in pq.distance_table(q).top(td, X, k=1, rescore=30) for i, q in enumerate(qs)))
+    assert hits[0] >= hits[1] - 10 and hits[0] >= 150
+
+
+def test_fit_device_ivf_centroids():
+    """IVF.fit(device=True): Lloyd's k-means on the GPU (tkb_kmeans_dev: the exact-chain assignment kernel + fixed-point sums).
+    Planted, well separated clusters are recovered, the returned assignment is the nearest centre of every row, the result is
+    deterministic, the inertia is sklearn's within 5 %, and the index built from it answers queries."""
+    import sklearn.cluster
+    from tinyknn_b200 import IVF
+    rng = np.random.default_rng(11)
+    k, d, n = 24, 20, 6000
+    means = rng.normal(size=(k, d)) * 6
+    lab = rng.integers(k, size=n)
+    X = (means[lab] + rng.normal(size=(n, d))).astype(np.float32)
+    a = IVF("euclidean", k).fit(X, device=True, seed=1)
+    b = IVF("euclidean", k).fit(X, device=True, seed=1)
+    assert np.array_equal(a.all_centers, b.all_centers) and a.all_centers.shape == (k, d)
+    assert 1 <= a.fit_iters <= 25
+    d2 = ((X[:, None, :].astype(np.float64) - a.all_centers[None].astype(np.float64)) ** 2).sum(2)
+    srt = np.sort(d2, axis=1)
+    clear = srt[:, 1] - srt[:, 0] > 1e-3 * srt[:, 1]                      # rows whose nearest centre is not a near-tie
+    assert np.array_equal(a._fit_assign[clear], d2.argmin(1)[clear])
+    near = ((means[:, None, :] - a.all_centers[None].astype(np.float64)) ** 2).sum(2).min(1)
+    assert (near < 1.0).all()                                             # every planted mean has a centre next to it
+    sk = sklearn.cluster.KMeans(k, n_init=1, random_state=0).fit(X.astype(np.float64))
+    assert _inertia(X.astype(np.float64), a.all_centers.astype(np.float64)) <= 1.05 * sk.inertia_
+    h = IVF("euclidean", k).fit(X, device=False)                          # the reference's sklearn path
+    found = []
+    for ivf in (a, h):
+        ivf.build(X, n_probes=1)
+        found.append(sum(i in ivf.query(X[i], k=10, n_probes=2) for i in range(100)))
+    assert found[0] >= found[1] - 10 and found[0] >= 50                   # as useful an index as the host fit's
+
+
+def test_kmeans_rejects_bad_arguments():
+    import ctypes
+    from tinyknn_b200._lib import lib
+    need = ctypes.c_int64(0)
+    assert lib.tkb_kmeans_workspace(100, 8, 4, ctypes.byref(need)) == 0 and need.value > 0
+    x = D.upload(np.zeros((100, 8), np.float32))
+    c = D.upload(np.zeros((4, 8), np.float32))
+    asg = D.empty((100,), np.int32)
+    ws = D.empty((need.value,), np.uint8)
+    assert lib.tkb_kmeans_dev(D.ptr(x), 100, 8, 4, D.ptr(c), 3, 1.0, D.ptr(asg), None, D.ptr(ws), 16, D.stream_ptr()) != 0   # workspace too small
+    assert lib.tkb_kmeans_dev(None, 100, 8, 4, D.ptr(c), 3, 1.0, D.ptr(asg), None, D.ptr(ws), ws.numel(), D.stream_ptr()) != 0
+    assert lib.tkb_kmeans_pq_dev(D.ptr(x), 100, 8, 3, D.ptr(c), 3, 1.0, D.ptr(ws), ws.numel(), D.stream_ptr()) != 0           # 8 % 3 != 0
+    assert lib.tkb_kmeans_pq_dev(D.ptr(x), 100, 8, 16, D.ptr(c), 3, 1.0, D.ptr(ws), ws.numel(), D.stream_ptr()) != 0          # dims_per_block > 8
+
+
 def test_push_exchange_with_chunk_minima_single_gpu(monkeypatch):
     """The push exchange with the minima region, driven rank by rank on one GPU over an index with long lists: every
     "rank" stores estimates AND chunk minima into the home buffers; the cm replay on the home rank == the unsharded path."""

@@ -43,6 +43,9 @@ SIGNATURES = {
     "tkb_peer_free": [_vp],
     "tkb_encode_dev": [_vp, _i, _i64, _i, _vp, _i64, _vp, _vp, _i, _i, _vp, _i, _vp, _vp],
     "tkb_assign_dev": [_vp, _i, _i64, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp],
+    "tkb_kmeans_workspace": [_i64, _i, _i, _c.POINTER(_c.c_int64)],
+    "tkb_kmeans_dev": [_vp, _i64, _i, _i, _vp, _i, _dbl, _vp, _c.POINTER(_c.c_int), _vp, _i64, _vp],
+    "tkb_kmeans_pq_dev": [_vp, _i64, _i, _i, _vp, _i, _dbl, _vp, _i64, _vp],
     "tkb_codes_to_native_dev": [_vp, _i64, _i, _vp, _vp],
     "tkb_codes_from_native_dev": [_vp, _i64, _i, _vp, _vp],
     "tkb_estimate_native_dev": [_vp, _i64, _i, _vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp],

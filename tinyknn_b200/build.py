@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtinyknn_b200.so")
-SOURCES = ["tkb_api.cu", "tkb_scan.cu", "tkb_scan_fast.cu", "tkb_scan_tc.cu", "tkb_heap.cu", "tkb_lut.cu", "tkb_rescore.cu", "tkb_plan.cu", "tkb_fused.cu", "tkb_encode.cu", "tkb_assign.cu", "tkb_coarse.cu"]
+SOURCES = ["tkb_api.cu", "tkb_scan.cu", "tkb_scan_fast.cu", "tkb_scan_tc.cu", "tkb_heap.cu", "tkb_lut.cu", "tkb_rescore.cu", "tkb_plan.cu", "tkb_fused.cu", "tkb_encode.cu", "tkb_assign.cu", "tkb_coarse.cu", "tkb_kmeans.cu"]
 HEADERS = [os.path.join(CSRC, "tkb_common.cuh"), os.path.join(CSRC, "tkb_scan_core.cuh"), os.path.join(CSRC, "tkb_rescore_core.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "tinyknn_b200.h")]
 

@@ -292,6 +292,22 @@ int tkb_peer_free(void *dev_ptr)
     return TKB_OK;
 }
 
+int tkb_kmeans_workspace(int64_t n, int d, int k, int64_t *bytes) { return kmeans_workspace_bytes(n, d, k, bytes); }
+
+int tkb_kmeans_dev(const float *rows, int64_t n, int d, int k, float *centers, int max_iters, double absmax, int32_t *assign,
+                   int *iters_done, void *workspace, int64_t workspace_bytes, void *stream)
+{
+    if (int rc = require_device()) return rc;
+    return launch_kmeans(rows, n, d, k, centers, max_iters, absmax, assign, iters_done, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int tkb_kmeans_pq_dev(const float *rows, int64_t n, int D, int dpb, float *centers, int iters, double absmax, void *workspace,
+                      int64_t workspace_bytes, void *stream)
+{
+    if (int rc = require_device()) return rc;
+    return launch_kmeans_pq(rows, n, D, dpb, centers, iters, absmax, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int tkb_encode_dev(const void *rows, int rows_dtype, int64_t n_rows, int d, const int64_t *row_index, int64_t n_out,
                    const float *centers, const float *cnorm, int Dp, int dpb, const double *R, int Dpad,
                    uint64_t *codes, void *stream)

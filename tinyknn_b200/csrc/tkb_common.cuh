@@ -118,6 +118,11 @@ int launch_encode(const void *rows, int rows_dtype, int64_t n_rows, int d, const
                   cudaStream_t st);
 int launch_assign(const void *rows, int dtype, int64_t n, int d, const void *centers, int C, const void *xnorm,
                   const void *cnorm, int k, int32_t *nearest, void *scratch, int64_t scratch_bytes, cudaStream_t st);
+int kmeans_workspace_bytes(int64_t n, int d, int k, int64_t *bytes);
+int launch_kmeans(const float *rows, int64_t n, int d, int k, float *centers, int max_iters, double absmax, int32_t *assign,
+                  int *iters_done, void *workspace, int64_t workspace_bytes, cudaStream_t st);
+int launch_kmeans_pq(const float *rows, int64_t n, int D, int dpb, float *centers, int iters, double absmax, void *workspace,
+                     int64_t workspace_bytes, cudaStream_t st);
 int launch_codes_to_native(const uint64_t *ref, int64_t n_chunks, int M, void *native, cudaStream_t st);
 int launch_codes_from_native(const void *native, int64_t n_chunks, int M, uint64_t *ref, cudaStream_t st);
 int launch_estimate_native(const void *native, int64_t n_chunks, int M, const uint8_t *tables, int Q, uint8_t *est,

@@ -10,6 +10,7 @@ What runs where:
     `tkb_gather_dists_dev`; only the reference's own `bottom_k` (np.argpartition over <= rescore floats)
     runs on the host, because its output ORDER is numpy-defined ("selection order").
 """
+import os
 import warnings
 from collections import namedtuple
 
@@ -60,6 +61,37 @@ _GAUSS_CODE = np.array(
        for t in np.linspace(0, 2 * np.pi, m, endpoint=False)])
 
 
+# `fit` on the GPU by default? (TKB_FIT_DEVICE=1; off: the reference's sklearn path, so that the reference's own tests see the
+# reference's own fit)
+FIT_DEVICE = os.environ.get("TKB_FIT_DEVICE", "0") != "0"
+
+
+def kmeans_pp_init(X, k, rng):
+    """Greedy k-means++ seeding (Arthur & Vassilvitskii; 2 + log k candidates per step, the one that lowers the potential most
+    is kept -- the variant sklearn uses) of k centres from the rows of X, numpy Generator `rng`. Rows may repeat when X has fewer
+    than k distinct ones."""
+    n = X.shape[0]
+    X64 = X.astype(np.float64)
+    xn = np.einsum("ij,ij->i", X64, X64)
+    out = np.empty((k, X.shape[1]), dtype=X.dtype)
+    first = int(rng.integers(n))
+    out[0] = X[first]
+    d2 = np.maximum(xn + xn[first] - 2.0 * X64 @ X64[first], 0.0)
+    trials = 2 + int(np.log(k))
+    for c in range(1, k):
+        tot = d2.sum()
+        if not tot > 0:
+            cand = rng.integers(n, size=1)
+        else:
+            cand = np.minimum(np.searchsorted(np.cumsum(d2), rng.random(trials) * tot), n - 1)
+        dc = np.maximum(xn[None, :] + xn[cand][:, None] - 2.0 * X64[cand] @ X64.T, 0.0)      # (trials, n)
+        pot = np.minimum(d2[None, :], dc)
+        best = int(np.argmin(pot.sum(axis=1)))
+        out[c] = X[cand[best]]
+        d2 = pot[best]
+    return out
+
+
 class FastPQ:
     def __init__(self, dims_per_block, use_kmeans=True, rotate_dim=64):
         self.dims_per_block = dims_per_block
@@ -70,7 +102,11 @@ class FastPQ:
         self.R = None                # f64 (min(rotate_dim, d_pad), d_pad) random orthonormal rows, or None
 
     # ------------------------------------------------------------------ build time (host) ----
-    def fit(self, data, verbose=False):
+    def fit(self, data, verbose=False, device=None, seed=0):
+        """ref: fast_pq.py:50-104. device=True: the per-block k-means runs on the GPU (`tkb_kmeans_pq_dev`, all blocks in one
+        pass over the rows per iteration; k-means++ seeding on a host subsample with numpy's Generator(seed)); None: the module
+        default FIT_DEVICE (TKB_FIT_DEVICE=1), else sklearn on the host like the reference. Parity unpinned either way: the
+        reference's own fit is random."""
         assert data.size > 0, "Can't fit no data"
         true_d = data.shape[1]
         dpb = self.dims_per_block
@@ -83,13 +119,34 @@ class FastPQ:
                 d = self.rotate_dim
                 self.R = self.R[:d]
             data = data @ self.R.T
-        books = self._fit_code(data, verbose=verbose)            # list of M arrays (16, dpb)
+        if (FIT_DEVICE if device is None else device) and self.use_kmeans:
+            books = self._fit_code_device(data, seed)
+        else:
+            books = self._fit_code(data, verbose=verbose)        # list of M arrays (16, dpb)
         self.centers = np.array(books, dtype=np.float32).transpose(1, 0, 2).reshape(16, d)
         self.sqrt_n_blocks = np.sqrt(d // dpb)
         return self
 
     def fit_transform(self, data, verbose=False):
         return self.fit(data, verbose).transform(data, verbose)
+
+    def _fit_code_device(self, data, seed=0, iters=25):
+        """The M codebooks of 16 centres by Lloyd's algorithm on the GPU (ref: fast_pq.py:106-145 fits one sklearn KMeans per
+        block). Returns the list of M arrays (16, dpb) `_fit_code` returns."""
+        X = np.ascontiguousarray(data, dtype=np.float32)
+        n, d = X.shape
+        dpb = self.dims_per_block
+        rng = np.random.default_rng(seed)
+        sub = X[rng.choice(n, min(n, 4096), replace=False)]
+        centers = np.empty((16, d), dtype=np.float32)
+        for m in range(d // dpb):
+            centers[:, m * dpb:(m + 1) * dpb] = kmeans_pp_init(sub[:, m * dpb:(m + 1) * dpb], 16, rng)
+        Xd, Cd = D.upload(X), D.upload(centers)
+        ws = D.empty((16384 + 160 * d,), np.uint8)
+        check(lib.tkb_kmeans_pq_dev(D.ptr(Xd), n, d, dpb, D.ptr(Cd), iters, float(np.abs(X).max()), D.ptr(ws), ws.numel(),
+                                    D.stream_ptr()))
+        centers = Cd.cpu().numpy()
+        return [centers[:, m * dpb:(m + 1) * dpb].copy() for m in range(d // dpb)]
 
     def _fit_code(self, data, verbose=False):
         n, d = data.shape

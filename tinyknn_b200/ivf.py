@@ -122,20 +122,51 @@ class IVF:
         self.ids = [None] * n_clusters
 
     # ------------------------------------------------------------------ build time (host) ----
-    def fit(self, X, verbose=False):
-        """Coarse centroids by k-means on the raw vectors, then the PQ codebooks (ref: ivf.py:19-51)."""
-        import sklearn.cluster
+    def fit(self, X, verbose=False, device=None, seed=0, max_iters=25):
+        """Coarse centroids by k-means on the raw vectors, then the PQ codebooks (ref: ivf.py:19-51). device=True: both on the
+        GPU (`tkb_kmeans_dev`: exact-chain assignment + fixed-point centroid sums, deterministic for a seed; `FastPQ.fit(device=
+        True)`); None: the module default (TKB_FIT_DEVICE=1), else sklearn on the host like the reference."""
         assert X.shape[0] >= 1
+        device = _fp.FIT_DEVICE if device is None else device
         with timer(verbose, "Fitting IVF cluster centers..."):
-            km = sklearn.cluster.KMeans(n_clusters=self.n_clusters, n_init=1, verbose=verbose)
             if self.metric == "angular":
                 X = X / np.linalg.norm(X, axis=1, keepdims=True)
-            self.all_centers = km.fit(X).cluster_centers_
+            if device:
+                self.all_centers = self._fit_centers_device(X, seed, max_iters)
+            else:
+                import sklearn.cluster
+                km = sklearn.cluster.KMeans(n_clusters=self.n_clusters, n_init=1, verbose=verbose)
+                self.all_centers = km.fit(X).cluster_centers_
             if self.metric == "angular":
                 self.all_centers /= np.linalg.norm(self.all_centers, axis=1, keepdims=True)
         with timer(verbose, "Fitting PQ to data..."):
-            self.pq.fit(X, verbose=verbose)
+            self.pq.fit(X, verbose=verbose, device=device, seed=seed)
         return self
+
+    def _fit_centers_device(self, X, seed=0, max_iters=25):
+        """Lloyd's k-means of the rows of X on the GPU. Seeding: k-means++ on a host subsample for up to 1024 clusters, distinct
+        random rows above. Returns f32 (n_clusters, d); `self.fit_iters` = iterations run."""
+        import ctypes
+        Xf = np.ascontiguousarray(X, dtype=np.float32)
+        n, d = Xf.shape
+        k = self.n_clusters
+        assert n >= k, f"n_samples={n} should be >= n_clusters={k}."
+        rng = np.random.default_rng(seed)
+        if k <= 1024:
+            init = _fp.kmeans_pp_init(Xf[rng.choice(n, min(n, max(4096, 8 * k)), replace=False)], k, rng)
+        else:
+            init = Xf[rng.choice(n, k, replace=False)]
+        Xd, Cd = D.upload(Xf), D.upload(np.ascontiguousarray(init, dtype=np.float32))
+        need = ctypes.c_int64(0)
+        check(lib.tkb_kmeans_workspace(n, d, k, ctypes.byref(need)))
+        ws = D.empty((need.value,), np.uint8)
+        assign = D.empty((n,), np.int32)
+        done = ctypes.c_int(0)
+        check(lib.tkb_kmeans_dev(D.ptr(Xd), n, d, k, D.ptr(Cd), int(max_iters), float(np.abs(Xf).max()), D.ptr(assign),
+                                 ctypes.byref(done), D.ptr(ws), ws.numel(), D.stream_ptr()))
+        self.fit_iters = int(done.value)
+        self._fit_assign = assign.cpu().numpy()
+        return Cd.cpu().numpy()
 
     def build(self, X, n_probes=2, verbose=False, device=None, assign_device=None):
         """Put every point into the lists of its n_probes nearest centroids (ref: ivf.py:53-104).
