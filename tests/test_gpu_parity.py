@@ -304,7 +304,12 @@ def test_ivf_query_matches_golden_and_oracle(golden):
                                  and np.array_equal(last["probes"][i], tr["top"]))
             print(f"IVF {name} n_probes={npr}: lut!= {bad_lut}, heap!= {bad_heap}, ids!=oracle {bad_or}, ids!=golden {bad_gold} of {len(qs)}")
             assert bad_lut == 0 and bad_heap == 0 and bad_or == 0
-            assert bad_gold <= max(1, len(qs) // 16)   # fixtures were generated on another CPU: argpartition order may differ
+            # What pins the ids is the line above: equality with the oracle -- the reference's algorithm driven by THIS host's
+            # numpy -- on every query. The golden id arrays were produced by the reference on the machine that generated the
+            # fixtures; np.argpartition's output order (which decides the visiting order of the probed lists and with it the
+            # heap, SURVEY.md 0.5 / DESIGN.md 4.5) is specific to the numpy build and CPU, so on another machine the reference
+            # itself may differ from them on a few queries. They are a drift alarm, not the acceptance test.
+            assert bad_gold <= max(1, len(qs) // 16)
             # single-query API == batch of one
             one = ivf.query(qs[0], 10, n_probes=npr)
             assert one.dtype == np.int64 and set(one) == set(ids[0][:cnt[0]])

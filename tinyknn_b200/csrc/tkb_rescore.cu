@@ -178,7 +178,11 @@ int launch_select_probes(const int64_t *heap_idx, const void *dists, int dtype, 
     TKB_REQUIRE(heap_idx && probes && (dists || R <= P), "null pointer");
     TKB_REQUIRE(dtype == TKB_DTYPE_F32 || dtype == TKB_DTYPE_F64, "dists dtype must be f32 or f64");
     const size_t smem = (size_t)SEL_WARPS * R;
-    TKB_REQUIRE(smem <= 48 * 1024, "heap too large for device-side selection");
+    TKB_REQUIRE(smem <= 200 * 1024, "heap too large for device-side selection (R <= 51 200)");
+    if (smem > 48 * 1024) {                      // large heaps (k = 100 with hundreds of probes): opt in to the SM's whole shared memory
+        TKB_CUDA(cudaFuncSetAttribute(select_probes_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TKB_CUDA(cudaFuncSetAttribute(select_probes_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     const unsigned blocks = (unsigned)((Q + SEL_WARPS - 1) / SEL_WARPS);
     if (dtype == TKB_DTYPE_F32)
         select_probes_kernel<float><<<blocks, 32 * SEL_WARPS, smem, st>>>(heap_idx, (const float *)dists, Q, R, P, probes);
@@ -196,7 +200,11 @@ int launch_select_topk(const int64_t *heap_idx, const void *dists, int dtype, in
     TKB_REQUIRE(heap_idx && dists && out_ids && out_count, "null pointer");
     TKB_REQUIRE(dtype == TKB_DTYPE_F32 || dtype == TKB_DTYPE_F64, "dists dtype must be f32 or f64");
     const size_t smem = (size_t)SEL_WARPS * R;
-    TKB_REQUIRE(smem <= 48 * 1024, "heap too large for device-side selection");
+    TKB_REQUIRE(smem <= 200 * 1024, "heap too large for device-side selection (R <= 51 200)");
+    if (smem > 48 * 1024) {
+        TKB_CUDA(cudaFuncSetAttribute(select_topk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TKB_CUDA(cudaFuncSetAttribute(select_topk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     const unsigned blocks = (unsigned)((Q + SEL_WARPS - 1) / SEL_WARPS);
     if (dtype == TKB_DTYPE_F32)
         select_topk_kernel<float><<<blocks, 32 * SEL_WARPS, smem, st>>>(heap_idx, (const float *)dists, Q, R, k, out_ids, (float *)out_dists, out_count);
