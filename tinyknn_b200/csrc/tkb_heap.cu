@@ -379,20 +379,21 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                   const int32_t *__restrict__ list_size, int n_lists, const int64_t *__restrict__ ids,
                   const int32_t *__restrict__ probes, int Q, int P, int64_t *__restrict__ heap_idx,
                   int32_t *__restrict__ heap_val, int R, int *__restrict__ fallback, int QPC, int QCAP,
-                  const uint8_t *__restrict__ cmin, int qpw, const int64_t *__restrict__ cm_seg)
+                  const uint8_t *__restrict__ cmin, int qpw, const int64_t *__restrict__ cm_seg, int ovl_arg)
 {
     // cm_seg (pull exchange): the compact layout the chunk minima are addressed by, while `seg_off` holds absolute addresses of
     // segments that live in other GPUs' buffers (est == null); null: the minima follow seg_off
     extern __shared__ __align__(16) unsigned char rq_sm[];
     const int HS = 2 * R + 4;                                              // words per heap: slot i at word i+1, children of R-1 included
     uint32_t *H = reinterpret_cast<uint32_t *>(rq_sm);                     // [QPC][HS]
-    uint32_t *QU = H + (size_t)QPC * HS;                                   // [QPC][QCAP+2]
-    int *cum = reinterpret_cast<int *>(QU + (size_t)QPC * (QCAP + 2));     // [QPC][P+1] real chunks before segment s
+    // ovl_arg: two queues of QCAP records per query (see the main loop); else one
+    uint32_t *QU = H + (size_t)QPC * HS;                                   // [1 or 2][QPC][QCAP+2]
+    int *cum = reinterpret_cast<int *>(QU + (size_t)(ovl_arg ? 2 : 1) * QPC * (QCAP + 2));     // [QPC][P+1] real chunks before segment s
     int *s_cursor = cum + (size_t)QPC * (P + 1);
-    int *s_seg = s_cursor + QPC, *s_bound = s_seg + QPC, *s_count = s_bound + QPC, *s_round = s_count + QPC;
+    int *s_seg = s_cursor + QPC, *s_bound = s_seg + QPC, *s_count = s_bound + QPC, *s_round = s_count + 2 * QPC;   // s_count: [2][QPC]
     // chunk-minimum path (cmin != null): est offset of the query's first chunk, or -1 when its segments are not back to back;
     // one list of flagged chunks per warp
-    long long *s_qoff = reinterpret_cast<long long *>(rq_sm + (((size_t)((unsigned char *)(s_round + QPC) - rq_sm) + 15) & ~(size_t)15));
+    long long *s_qoff = reinterpret_cast<long long *>(rq_sm + (((size_t)((unsigned char *)(s_round + QPC) - rq_sm) + 15) & ~(size_t)15));   // (s_round is the last int array)
     uint32_t *LST = reinterpret_cast<uint32_t *>(s_qoff + QPC);            // [n_warps][RQ_CM_BLOCK]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NTH = blockDim.x, n_warps = NTH / 32;   // 64, 128 or 256 threads
     const int q0 = blockIdx.x * QPC;
@@ -433,7 +434,7 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
         if (run >= (1 << 20) - 1) ok = false;                              // positions must fit 24 bits
         if (q < Q && fallback) fallback[q] = ok ? 0 : 1;
         if (!ok) for (int s = 0; s <= P; s++) c[s] = 0;
-        s_cursor[t] = 0; s_seg[t] = 0; s_bound[t] = init; s_count[t] = 0; s_round[t] = 0;
+        s_cursor[t] = 0; s_seg[t] = 0; s_bound[t] = init; s_count[t] = 0; s_count[QPC + t] = 0; s_round[t] = 0;
         if (CM && cmin) {
             // the query's stream is one contiguous byte range of `est` when its segments lie back to back (the compact
             // single-GPU plan): chunk cc of the stream is est[qoff + 16 cc ..] and its minimum is cmin[qoff / 16 + cc]
@@ -451,21 +452,33 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
     }
     __syncthreads();
 
-    for (;;) {
+    // OVERLAPPED ROUNDS (ovl): the ncu capture of round 2 shows 21 of 27 stall cycles per issued instruction at the two CTA
+    // barriers of a round -- the consumer warps walk the sift chain while the producers wait, and vice versa. With two queues per
+    // query the n_cons consumer warps replay the queues filled in the previous iteration WHILE the other warps filter the next
+    // windows into the other queues, against the bound as it was when the iteration began. Exact: the bound only falls, so a
+    // stale bound admits a superset, and the consumer applies the reference's own test to every record.
+    const int n_cons = (QPC + QPW - 1) / QPW;                              // warps that hold all the CTA's queries when consuming
+    const bool ovl = ovl_arg && !indep && n_cons < n_warps;
+    for (int r = 0;; r++) {
         // ---- produce (as in replay_rq_kernel; records are packed words) -----------------------------
+        const int pb = ovl ? (r & 1) : 0, cb = ovl ? (pb ^ 1) : 0;          // queue filled / queue replayed in this iteration
+        const bool prod_warp = !ovl || r == 0 || warp >= n_cons;
+        const int p_first = !prod_warp ? 0 : (indep ? warp * QPW : ((ovl && r > 0) ? warp - n_cons : warp));
+        const int p_step = indep ? 1 : ((ovl && r > 0) ? n_warps - n_cons : n_warps);
+        const int p_end = !prod_warp ? 0 : (indep ? min(QPC, (warp + 1) * QPW) : QPC);
         bool more = false;
-        for (int t = indep ? warp * QPW : warp; t < (indep ? min(QPC, (warp + 1) * QPW) : QPC); t += indep ? 1 : n_warps) {
+        for (int t = p_first; t < p_end; t += p_step) {
             const int *c = cum + (size_t)t * (P + 1);
             const int total = c[P];
             const int cursor = s_cursor[t];
-            if (cursor >= total) { if (lane == 0) s_count[t] = 0; continue; }
+            if (cursor >= total) { if (lane == 0) s_count[pb * QPC + t] = 0; continue; }
             const int q = q0 + t;
             const int bound = s_bound[t];                                  // stored form
             int W = s_round[t] == 0 ? ((R + 15) >> 4) + 1 : (cursor < 32 ? 32 : cursor);
             if (W > (1 << 16)) W = 1 << 16;
             int end = (total - cursor < W) ? total : cursor + W;
             int count = 0, sg = s_seg[t];
-            uint32_t *qu = QU + (size_t)t * (QCAP + 2);
+            uint32_t *qu = QU + ((size_t)pb * QPC + t) * (QCAP + 2);
             // PF steps of 32 chunks are fetched before the first is examined: a window is thousands of chunks long once the
             // bound has settled and almost nothing survives the filter, so the walk is a chain of load latencies otherwise
             constexpr int PF = 4;
@@ -626,23 +639,23 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                 }
                 if (cut) break;
             }
-            if (lane == 0) { s_cursor[t] = end; s_seg[t] = sg; s_count[t] = count; s_round[t] = 1; qu[count] = RQ2_SENTINEL; qu[count + 1] = RQ2_SENTINEL; }
+            if (lane == 0) { s_cursor[t] = end; s_seg[t] = sg; s_count[pb * QPC + t] = count; s_round[t] = 1; qu[count] = RQ2_SENTINEL; qu[count + 1] = RQ2_SENTINEL; }
             more = true;
         }
         if (indep) { __syncwarp(); if (!more) break; }                      // `more` is warp-uniform
-        else if (!__syncthreads_or(more)) break;
+        else if (!ovl && !__syncthreads_or(more)) break;
         // ---- consume: L lanes per query, 32/L queries per warp. The step is branch-free (the queries of a warp are in
         //      different states; divergent code would be issued once per state and the loop is issue-bound) -----------
         {
             // qpw queries per consumer warp (default 32 / L; fewer = less lock-step waste, more warps busy: the replay model
             // of tools/replay_model.py puts 8 lock-stepped queries at +26 % steps over one query per warp)
             const int role = lane % L;
-            for (int tb = warp * QPW; tb < QPC; tb += n_warps * QPW) {
+            for (int tb = (ovl && (r == 0 || warp >= n_cons)) ? QPC : warp * QPW; tb < QPC; tb += n_warps * QPW) {
                 const int t = tb + lane / L;
                 const bool mine = lane / L < QPW && t < QPC;
                 uint32_t *hw = H + (size_t)(mine ? t : 0) * HS;
-                const uint32_t *qu = QU + (size_t)(mine ? t : 0) * (QCAP + 2);
-                const int cnt = mine ? s_count[t] : 0;
+                const uint32_t *qu = QU + ((size_t)cb * QPC + (mine ? t : 0)) * (QCAP + 2);
+                const int cnt = mine ? s_count[cb * QPC + t] : 0;
                 // State replicated over the query's L lanes: queue cursor, bound frozen for the current chunk, last record seen.
                 // Values stay in the top byte of their 32-bit words and are compared there: for words a, b with the value in
                 // bits 24..31 (signed) and a 24-bit payload below, value(a) < value(b)  <=>  (int)a < (int)(b & 0xff000000),
@@ -690,7 +703,9 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                 if (mine && role == 0) s_bound[t] = (int)rootm >> 24;
             }
         }
-        if (indep) __syncwarp(); else __syncthreads();
+        if (indep) __syncwarp();
+        else if (ovl) { if (!__syncthreads_or(more)) break; }              // nothing was produced: the last queues have just been replayed
+        else __syncthreads();
     }
     if (indep) __syncthreads();                                            // every warp's queries are finished
 
@@ -805,7 +820,8 @@ static size_t rq_smem(int R, int P, int qpc, int qcap)
 
 static size_t rq2_smem(int R, int P, int qpc, int qcap, bool cm = false, int threads = RQ_THREADS)
 {
-    const size_t base = (size_t)qpc * (4 * (2 * (size_t)R + 4) + 4 * ((size_t)qcap + 2) + 4 * ((size_t)P + 1) + 20) + 16;
+    // (qcap + 4: two queues of qcap / 2 + 2 words when the rounds overlap; 24: five per-query ints, the count twice)
+    const size_t base = (size_t)qpc * (4 * (2 * (size_t)R + 4) + 4 * ((size_t)qcap + 4) + 4 * ((size_t)P + 1) + 24) + 16;
     // chunk-minimum path: s_qoff[qpc] + one list of RQ_CM_BLOCK chunk numbers per warp
     return cm ? base + 16 + 8 * (size_t)qpc + 4 * (size_t)(threads / 32) * RQ_CM_BLOCK : base;
 }
@@ -892,6 +908,14 @@ static int rq_qpw_arg(const RqGeom &g, int lanes)
     return (per >= 1 && per <= 32 / lanes) ? -per : rq_qpw();
 }
 
+// Overlapped rounds of the pipelined replay (TKB_RQ_OVERLAP, default 1): see the kernel's main loop.
+static int rq_ovl()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("TKB_RQ_OVERLAP"); v = e ? (atoi(e) != 0) : 1; }
+    return v;
+}
+
 template <bool SIGNED>
 static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t *seg_off, int64_t n_chunks0, int n0,
                      const int64_t *list_chunk_off, const int32_t *list_size, int n_lists, const int64_t *ids,
@@ -905,7 +929,7 @@ static int launch_rq(int mode, const uint8_t *est, int64_t stride, const int64_t
             TKB_CUDA(cudaFuncSetAttribute(replay_rq2_kernel<SIGNED, LANES, CMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
             replay_rq2_kernel<SIGNED, LANES, CMV><<<blocks, g.threads, g.smem, st>>>(mode, est, stride, seg_off, n_chunks0, n0, list_chunk_off, \
                                                                                      list_size, n_lists, ids, probes, Q, P, heap_idx, heap_val,  \
-                                                                                     R, fallback, g.qpc, g.qcap, cmin, rq_qpw_arg(g, LANES), cm_seg); \
+                                                                                     R, fallback, g.qpc, rq_ovl() ? g.qcap / 2 : g.qcap, cmin, rq_qpw_arg(g, LANES), cm_seg, rq_ovl()); \
         } while (0)
         if (cmin) { if (g.lanes == 4) TKB_RQ2_LAUNCH(4, true); else TKB_RQ2_LAUNCH(8, true); }
         else      { if (g.lanes == 4) TKB_RQ2_LAUNCH(4, false); else TKB_RQ2_LAUNCH(8, false); }

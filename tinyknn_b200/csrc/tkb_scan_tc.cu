@@ -322,6 +322,7 @@ constexpr int TC_QUEUE = 4096;                  // refold queue of one work item
 
 struct TcItem {
     int valid, list, nq, N, t0, t1, n_real, pad;
+    uint32_t nk0u, nk1u;                        // the SMALLEST thresholds of the group, negated, in both halves of an s16x2: the hot loop's test
     long long tile0;                            // first tile of the list in the code array
     int q_of[TC_NT];                            // query of group member i (-1: padding column)
     uint2 kq2[TC_NT / 2];                       // NEGATED certificate thresholds of query pairs: .x = (-k0[2i], -k0[2i+1]), .y = (-k1[..]), s16x2
@@ -498,6 +499,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                 I.valid = 1; I.list = l; I.nq = nq; I.N = N; I.t0 = t0; I.t1 = t1; I.n_real = n_real;
                 I.tile0 = list_chunk_off[l] >> 3;                    // lists start on a tile
             }
+            int kmin0 = 32767, kmin1 = 32767;
             for (int i = lane; i < TC_NT; i += 32) {
                 int q = -1;
                 long long d = 0;
@@ -508,12 +510,18 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     d = seg_off[e];
                     const TcQueryMeta m = W.qmeta[q];
                     k0 = m.k0; k1 = m.k1;
+                    kmin0 = min(kmin0, k0); kmin1 = min(kmin1, k1);
                 }
                 I.q_of[i] = q; I.dst[i] = d;
                 // push exchange: the minima region of the query's home rank, addressed like the estimates (address >> 4)
                 I.cmb[i] = q < 0 ? 0ull : (cm_home ? (unsigned long long)cm_home[q / q_per_rank] : (unsigned long long)(uintptr_t)cmin);
                 reinterpret_cast<uint16_t *>(I.kq2)[4 * (i >> 1) + (i & 1)] = (uint16_t)(int16_t)(-k0);          // negated: the epilogue adds
                 reinterpret_cast<uint16_t *>(I.kq2)[4 * (i >> 1) + 2 + (i & 1)] = (uint16_t)(int16_t)(-k1);
+            }
+            for (int o = 16; o > 0; o >>= 1) { kmin0 = min(kmin0, __shfl_xor_sync(FULL, kmin0, o)); kmin1 = min(kmin1, __shfl_xor_sync(FULL, kmin1, o)); }
+            if (lane == 0) {
+                I.nk0u = (uint32_t)((-kmin0) & 0xffff) * 0x00010001u;
+                I.nk1u = (uint32_t)((-kmin1) & 0xffff) * 0x00010001u;
             }
             __syncwarp();
             uint8_t *B = Bslab + (size_t)par * SLAB;
@@ -597,6 +605,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             const TcItem &I = S.item[par];
             if (!I.valid) break;
             const int t0 = I.t0, t1 = I.t1, N = I.N, nq = I.nq, n_real = I.n_real, nh = N >> 1;
+            const uint32_t nk0u = I.nk0u, nk1u = I.nk1u;
             const long long tile0 = I.tile0;
             const uint8_t *B = Bslab + (size_t)par * SLAB;
             const int first = t0 + (int)((h - g) & 1);               // this half's first tile of the item: (g + first - t0) & 1 == h
@@ -735,11 +744,11 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                         }
                         uint32_t e2[4], fl = 0x80008000u;
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {                 // two queries per step; kq2 holds the NEGATED thresholds
-                            const uint2 k = I.kq2[(n0 >> 1) + u];
+                        for (int u = 0; u < 4; u++) {                 // two queries per step. The test uses the group's smallest thresholds
+                            // (registers, no shared-memory load per pair): it can only flag more; tc_flagged8 applies each query's own
                             e2[u] = __vimin3_s16x2(__viaddmax_s16x2(pa[u], pc[u], 0xff80ff80u), 0x007f007fu, 0x007f007fu);
-                            fl = __viaddmax_s16x2(pa[u], k.x, fl);
-                            fl = __viaddmax_s16x2(pc[u], k.y, fl);
+                            fl = __viaddmax_s16x2(pa[u], nk0u, fl);
+                            fl = __viaddmax_s16x2(pc[u], nk1u, fl);
                         }
                         uint32_t o0 = prmt(e2[0], e2[1], 0x6420u), o1 = prmt(e2[2], e2[3], 0x6420u);
                         if (!(DBG && (dbg & 32)) && __any_sync(FULL, (int)(int16_t)(fl & 0xffffu) > 0 || (int)(int16_t)(fl >> 16) > 0))
