@@ -852,19 +852,31 @@ static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 
         if (lanes_env == 8) g.lanes = 8;
         static int qcap_mult = 0, smem_kb = 0, threads = 0;
         if (!qcap_mult) {
-            qcap_mult = rq_env("TKB_RQ_QCAP", 4, 1, 8); smem_kb = rq_env("TKB_RQ_SMEM_KB", 45, 8, 200);
+            qcap_mult = rq_env("TKB_RQ_QCAP", 4, 0, 8); smem_kb = rq_env("TKB_RQ_SMEM_KB", 45, 8, 200);
             threads = rq_env("TKB_RQ_THREADS", 256, 64, 256);
             if (threads != 64 && threads != 128) threads = 256;
         }
-        g.threads = threads;
-        g.qcap = qcap_mult * R < 128 ? 128 : qcap_mult * R;
+        // Long streams (the chunk-minimum path: 100M-vector indexes). The launch is a few waves of CTAs and every wave lasts as
+        // long as the sift chain of its queries, so what counts is how many queries are RESIDENT per SM, i.e. shared memory per
+        // query: queues of R records instead of 4 R, 128-thread CTAs of 8 queries (two consumer warps, two producer warps; the
+        // per-warp list of flagged chunks is 2 KB). Measured at 100M x 128, R = 331: 3.82 -> 2.68 ms (ncu: 2 500 CTAs of 4 queries,
+        // four per SM = 4.2 waves, one consumer warp per CTA busy). The environment switches still override.
+        const bool long_streams = cm;
+        int th = threads, qm = qcap_mult, kb = smem_kb;
+        if (long_streams) {
+            if (!getenv("TKB_RQ_THREADS")) th = 128;
+            if (!getenv("TKB_RQ_QCAP")) qm = 1;
+            if (!getenv("TKB_RQ_SMEM_KB")) kb = 36;
+        }
+        g.threads = th;
+        g.qcap = qm * R < 128 ? 128 : qm * R;
         // CTAs wanted before queries are packed 16 to a CTA (TKB_RQ_MIN_CTAS, default 2 x 148). The launch list of round 1
         // shows a 5 000-query launch (313 CTAs) taking almost as long as a 10 000-query one: worth an A/B at 4 x 148.
         static int min_ctas = 0;
         if (!min_ctas) { const char *e = getenv("TKB_RQ_MIN_CTAS"); min_ctas = e ? atoi(e) : 0; if (min_ctas <= 0) min_ctas = 2 * 148; }
         int qpc = 16;
         while (qpc > 1 && (Q + qpc - 1) / qpc < min_ctas) qpc >>= 1;
-        while (qpc > 1 && rq2_smem(R, P, qpc, g.qcap) > (size_t)smem_kb * 1024) qpc >>= 1;
+        while (qpc > 1 && rq2_smem(R, P, qpc, g.qcap) > (size_t)kb * 1024) qpc >>= 1;
         g.qpc = qpc; g.lpw = 0;
         g.smem = rq2_smem(R, P, qpc, g.qcap, cm, g.threads);
         if (g.smem <= 200 * 1024) return true;

@@ -1,5 +1,5 @@
 """Summaries of an `ncu --set full --import-source on` report for profiles/ (run in the build container; ncu reads the report
-without a GPU). Usage: python tools/ncu_summarize.py <report.ncu-rep> <profiles/prefix>
+without a GPU). Usage: python tools/ncu_summarize.py <report.ncu-rep> <profiles/prefix> [launch index for the SASS page, default 0]
 Writes <prefix>_raw.csv (every raw metric of every captured launch, one row per metric) and <prefix>_sass.txt (instruction mix by
 opcode, the tcgen05 / TMEM mnemonics found, the 40 SASS instructions with the most stall samples, executed instructions per
 400-byte region)."""
@@ -23,10 +23,17 @@ def main():
         w.writerow(["metric", "unit"] + ["launch %d" % i for i in range(len(launches))])
         for j, (h, u) in enumerate(zip(hdr, units)):
             w.writerow([h, u] + [l[j] for l in launches])
-    src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "sass"]))))
+    launch = sys.argv[3] if len(sys.argv) > 3 else "0"
+    src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--launch-skip", launch,
+                                           "--launch-count", "1"]))))
     name = src[0][1] if src and len(src[0]) > 1 else "?"
     h = src[1]
-    rows = src[2:]
+    rows = []
+    for r in src[2:]:                                   # (the page may repeat itself: stop at the next "Kernel Name" header)
+        if r and r[0] == "Kernel Name":
+            break
+        if len(r) == len(h):
+            rows.append(r)
     i_src, i_smp, i_ex = h.index("Source"), h.index("# Samples"), h.index("Instructions Executed")
     tot_ex = sum(int(r[i_ex]) for r in rows)
     tot_smp = sum(int(r[i_smp]) for r in rows)
