@@ -145,7 +145,7 @@ __global__ void tc_count_kernel(const int32_t *__restrict__ probes, const int64_
 // one CTA: exclusive prefix sums over the lists of (pairs) and (work items)
 __global__ void __launch_bounds__(1024)
 tc_offsets_kernel(const int *__restrict__ cnt, const int32_t *__restrict__ list_size, int n_lists, int *__restrict__ bucket_off,
-                  int *__restrict__ item_off, int *__restrict__ hdr)
+                  int *__restrict__ item_off, int *__restrict__ hdr, int tpi /* tiles per work item */)
 {
     __shared__ int s_a[1024], s_b[1024];
     const int tid = threadIdx.x, per = (n_lists + 1023) / 1024;
@@ -155,7 +155,7 @@ tc_offsets_kernel(const int *__restrict__ cnt, const int32_t *__restrict__ list_
         const int c = cnt[l];
         const int tiles = (((list_size[l] + 15) >> 4) + 7) >> 3;
         a += c;
-        b += ((c + TC_NT - 1) / TC_NT) * ((tiles + TC_TILES_PER_ITEM - 1) / TC_TILES_PER_ITEM);
+        b += ((c + TC_NT - 1) / TC_NT) * ((tiles + tpi - 1) / tpi);
     }
     s_a[tid] = a; s_b[tid] = b;
     __syncthreads();
@@ -171,7 +171,7 @@ tc_offsets_kernel(const int *__restrict__ cnt, const int32_t *__restrict__ list_
         const int tiles = (((list_size[l] + 15) >> 4) + 7) >> 3;
         bucket_off[l] = ra; item_off[l] = rb;
         ra += c;
-        rb += ((c + TC_NT - 1) / TC_NT) * ((tiles + TC_TILES_PER_ITEM - 1) / TC_TILES_PER_ITEM);
+        rb += ((c + TC_NT - 1) / TC_NT) * ((tiles + tpi - 1) / tpi);
     }
     if (tid == 1023) { bucket_off[n_lists] = s_a[1023]; item_off[n_lists] = s_b[1023]; hdr[0] = s_b[1023]; }
 }
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
 ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict__ list_chunk_off,
                    const int32_t *__restrict__ list_size, int n_lists, const uint8_t *__restrict__ tables, int P,
                    uint8_t *__restrict__ est, const int64_t *__restrict__ seg_off, uint8_t *__restrict__ cmin,
-                   const int64_t *__restrict__ cm_home, int q_per_rank, TcWork W, int dbg)
+                   const int64_t *__restrict__ cm_home, int q_per_rank, TcWork W, int dbg, int tpi)
 {
     constexpr int M = 2 * PH;
     constexpr int A_COLS = 8 * PH;                                   // 32-bit columns of one one-hot tile
@@ -490,7 +490,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (W.item_off[mid] <= item) lo = mid; else hi = mid; }
             const int l = lo;
             const int cnt = W.cnt[l], n_real = (list_size[l] + 15) >> 4, tiles = (n_real + 7) >> 3;
-            const int splits = (tiles + TC_TILES_PER_ITEM - 1) / TC_TILES_PER_ITEM;
+            const int splits = (tiles + tpi - 1) / tpi;
             const int local = item - W.item_off[l], g = local / splits, sp = local - g * splits;
             const int per = (tiles + splits - 1) / splits, t0 = sp * per, t1 = min(tiles, t0 + per);
             const int nq = min(TC_NT, cnt - g * TC_NT);
@@ -820,6 +820,16 @@ int tc_supported()
 #endif
 }
 
+static int n_sm_hint()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 int tc_workspace_bytes(int Q, int P, int n_lists, int64_t *bytes)
 {
     TKB_REQUIRE(Q >= 0 && P >= 0 && n_lists >= 0 && bytes, "bad extent");
@@ -855,7 +865,16 @@ int launch_ivf_scan_tc(const void *native, const int64_t *list_chunk_off, const 
     TKB_LAUNCH_CHECK();
     tc_count_kernel<<<(unsigned)((QP + 255) / 256), 256, 0, st>>>(probes, seg_off, QP, P, n_lists, W.qmeta, W.cnt, W.seg_rest);
     TKB_LAUNCH_CHECK();
-    tc_offsets_kernel<<<1, 1024, 0, st>>>(W.cnt, list_size, n_lists, W.bucket_off, W.item_off, W.hdr);
+    // Tiles per work item: 128 keeps the per-item costs (slab staging, pipeline fill) small on an index of thousands of lists.
+    // ONE list that every query probes (a brute-force scan; the encoded centroids of probe selection) has only Q / 64 groups
+    // x tiles / 128 items: smaller items there, about six per SM, so that the last round of items does not idle half the GPU.
+    int tpi = TC_TILES_PER_ITEM;
+    if (n_lists == 1 && P == 1) {
+        const int64_t tiles = (max_chunks_per_query + 7) / 8, groups = (Q + TC_NT - 1) / TC_NT;
+        int64_t want = (tiles * groups + 6LL * n_sm_hint() - 1) / (6LL * n_sm_hint());
+        tpi = (int)(want < 8 ? 8 : (want > TC_TILES_PER_ITEM ? TC_TILES_PER_ITEM : want));
+    }
+    tc_offsets_kernel<<<1, 1024, 0, st>>>(W.cnt, list_size, n_lists, W.bucket_off, W.item_off, W.hdr, tpi);
     TKB_LAUNCH_CHECK();
     tc_fill_kernel<<<(unsigned)((QP + 255) / 256), 256, 0, st>>>(probes, W.seg_rest, QP, n_lists, W.bucket_off, W.cursor, W.bucket);
     TKB_LAUNCH_CHECK();
@@ -876,12 +895,12 @@ int launch_ivf_scan_tc(const void *native, const int64_t *list_chunk_off, const 
     do {                                                                                                                               \
         TKB_CUDA(cudaFuncSetAttribute(ivf_scan_tc_kernel<16, WIDE_, CLK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req)); \
         ivf_scan_tc_kernel<16, WIDE_, CLK_><<<n_sm, TC_THREADS2, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native),          \
-            list_chunk_off, list_size, n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W, 0);                             \
+            list_chunk_off, list_size, n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W, 0, tpi);                        \
     } while (0)
     if (dbg && est != nullptr) {                  // probe instance (wrong results by design)
         TKB_CUDA(cudaFuncSetAttribute(ivf_scan_tc_kernel<16, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
         ivf_scan_tc_kernel<16, false, false, true><<<n_sm, TC_THREADS2, smem_req, st>>>(reinterpret_cast<const uint32_t *>(native),
-            list_chunk_off, list_size, n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W, dbg);
+            list_chunk_off, list_size, n_lists, tables, P, est, seg_off, cmin, cm_home, q_per_rank, W, dbg, tpi);
     } else if (est == nullptr) {                         // push exchange: full 128-byte lines into the peer-mapped buffers
         if (clk) TKB_TC_LAUNCH(true, true); else TKB_TC_LAUNCH(true, false);
     } else {

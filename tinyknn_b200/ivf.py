@@ -43,6 +43,8 @@ WORKSPACE_REUSE = os.environ.get("TKB_WORKSPACE_REUSE", "1") != "0"
 # Probe selection as one kernel (tkb_coarse_probes_dev) instead of scan / replay / gather / select. Opt-in until it has been
 # timed on hardware; results are identical (tests/test_gpu_build_and_batch.py, run on the emulator).
 COARSE_FUSED = os.environ.get("TKB_COARSE_FUSED", "0") != "0"
+# the centroid scan of probe selection through the tensor-core kernel (one list probed by every query) when that kernel applies
+COARSE_TC = os.environ.get("TKB_COARSE_TC", "1") != "0"
 # IVF.build: coarse assignment on the GPU (tkb_assign_dev). Opt-in until it has been validated on hardware.
 ASSIGN_DEVICE = os.environ.get("TKB_ASSIGN_DEVICE", "0") != "0"
 # List-major scan on the tensor cores (tkb_ivf_scan_tc_dev; csrc/tkb_scan_tc.cu): "0" never, "1" whenever the kernel applies
@@ -94,6 +96,11 @@ class _Workspace:
 
 def _fresh(name, shape, np_dtype):
     return D.empty(shape, np_dtype)
+
+
+def _tc_possible(dev):
+    """The tensor-core scan exists for this index on this device (M = 32, avx order, fast scan, sm_100)."""
+    return not (TC_SCAN == "0" or dev["M"] != 32 or _fp._order() != 1 or _fp.SCAN_IMPL != "fast" or not lib.tkb_ivf_scan_tc_supported())
 
 
 def _tc_applies(dev, Q, P):
@@ -433,7 +440,25 @@ class IVF:
             return probes
         est_c = buf("est_c", (Q, 16 * nck), np.uint8)
         with self._stage("coarse_scan"):
-            if _fp.SCAN_IMPL == "fast":
+            if COARSE_TC and Q >= 256 and nck >= 64 and _tc_possible(dev):
+                # every query scans ALL encoded centroids: one "list" that the whole batch probes -- the list-major tensor-core
+                # scan at its best (one expanded tile per 64 queries). Same bytes as tkb_estimate_native_dev.
+                import ctypes
+                key = ("coarse_tc", Q)
+                aux = dev.get(key)
+                if aux is None:
+                    t = D.torch()
+                    aux = dev[key] = dict(off=D.upload(np.array([0, -(-nck // 8) * 8], dtype=np.int64)),
+                                          size=D.upload(np.array([C], dtype=np.int32)),
+                                          probes=t.zeros((Q, 1), dtype=t.int32, device=D.device()),
+                                          seg=D.upload(np.arange(Q, dtype=np.int64) * (16 * nck)))
+                need = ctypes.c_int64(0)
+                check(lib.tkb_ivf_scan_tc_workspace(Q, 1, 1, ctypes.byref(need)))
+                tws = buf("coarse_tc_ws", (need.value,), np.uint8)
+                check(lib.tkb_ivf_scan_tc_dev(D.ptr(cc), D.ptr(aux["off"]), D.ptr(aux["size"]), 1, M, D.ptr(tables),
+                                              D.ptr(aux["probes"]), Q, 1, D.ptr(est_c), D.ptr(aux["seg"]), None, None, 0, nck,
+                                              D.ptr(tws), tws.numel(), st))
+            elif _fp.SCAN_IMPL == "fast":
                 ws = buf("coarse_ws", (64,), np.uint8)
                 check(lib.tkb_estimate_native_dev(D.ptr(cc), nck, M, D.ptr(tables), Q, D.ptr(est_c), 16 * nck,
                                                   _fp._order(), sg, D.ptr(ws), ws.numel(), st))

@@ -5,7 +5,7 @@ if [ "$T" = 1 ]; then
   timeout 600 python -m pytest tests/test_sharded_gpu.py tests/test_gpu_build_and_batch.py -x -q -m gpu -k "sharded or pull or push" > $out/pytest_pull.log 2>&1; tail -3 $out/pytest_pull.log
 fi
 for ex in ${EXCHANGES:-pull push}; do
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 --exchange $ex > $out/bench_n${N}_$ex.json 2> $out/bench_n${N}_$ex.err
+  timeout ${RUN_TIMEOUT:-600} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 --exchange $ex > $out/bench_n${N}_$ex.json 2> $out/bench_n${N}_$ex.err
   python - $out/bench_n${N}_$ex.json <<'PY'
 import json,sys
 try:
