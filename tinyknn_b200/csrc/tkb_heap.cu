@@ -368,7 +368,6 @@ replay_rq_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, cons
 // Preconditions on top of replay_rq_kernel's: stream positions < 2^24 - 1, depth of the heap <= 2L steps.
 // ------------------------------------------------------------------------------------------------
 constexpr int RQ_CM_BLOCK = 512;                  // chunks a warp tests per step of the chunk-minimum path (16 per lane)
-constexpr int RQ_CM_LIST = 1024;                  // listed chunks a warp collects before it fetches them
 constexpr int RQ_CM_MIN = 1024;                   // stream position (chunks) from which a round uses the chunk minima
 constexpr uint32_t RQ2_EMPTY = 0x00ffffffu;       // payload of a heap slot that was never filled
 constexpr uint32_t RQ2_SENTINEL = 0x80ffffffu;    // value -128
@@ -395,7 +394,7 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
     // chunk-minimum path (cmin != null): est offset of the query's first chunk, or -1 when its segments are not back to back;
     // one list of flagged chunks per warp
     long long *s_qoff = reinterpret_cast<long long *>(rq_sm + (((size_t)((unsigned char *)(s_round + QPC) - rq_sm) + 15) & ~(size_t)15));   // (s_round is the last int array)
-    uint32_t *LST = reinterpret_cast<uint32_t *>(s_qoff + QPC);            // [n_warps][RQ_CM_LIST]
+    uint32_t *LST = reinterpret_cast<uint32_t *>(s_qoff + QPC);            // [n_warps][RQ_CM_BLOCK]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NTH = blockDim.x, n_warps = NTH / 32;   // 64, 128 or 256 threads
     const int q0 = blockIdx.x * QPC;
     const uint32_t flip = SIGNED ? 0u : 0x80u;                             // stored byte = value ^ flip
@@ -491,7 +490,7 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                 const long long qoff = s_qoff[t];
                 const uint8_t *cmq = cmin + (qoff >> 4);
                 const uint8_t *eq = est + qoff;
-                uint32_t *lst = LST + (size_t)warp * RQ_CM_LIST;
+                uint32_t *lst = LST + (size_t)warp * RQ_CM_BLOCK;
                 const int skew = (int)((uintptr_t)(cmq + cursor) & 15);
                 bool cut = false;
                 auto load_cm = [&](int lc) {
@@ -502,33 +501,42 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                     }
                     return e;
                 };
-                // The chunks that may hold a candidate are LISTED (stream order) across blocks and fetched together: at most one
-                // round trip to the estimates per ~500 listed chunks instead of one per block of minima that has a candidate --
-                // the estimates may live in another GPU's memory (pull exchange), microseconds away. Two batches of 32 chunk
-                // loads are in flight while one is examined.
-                int F = 0;                                                   // chunks listed and not yet fetched
-                auto fetch_chunk = [&](int j, int &cc, int &rem, uint4 &ee) {
-                    cc = 0; rem = 0; ee = make_uint4(0, 0, 0, 0);
-                    if (j + lane < F) {
-                        cc = (int)lst[j + lane];
-                        int lo = 0, hi = P;                                  // segment with c[lo] <= cc < c[lo+1]
-                        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (c[mid] <= cc) lo = mid; else hi = mid; }
-                        rem = list_size[probes[(size_t)q * P + lo]] - 16 * (cc - c[lo]);
-                        const uint8_t *ea = cm_seg ? est + seg_off[(size_t)q * P + lo] + 16LL * (cc - c[lo]) : eq + 16LL * cc;
-                        ee = ldg_nc_u4(reinterpret_cast<const uint4 *>(ea));
-                        if (!SIGNED) { ee.x ^= 0x80808080u; ee.y ^= 0x80808080u; ee.z ^= 0x80808080u; ee.w ^= 0x80808080u; }
+                uint4 nxt = load_cm(cursor - skew + 16 * lane);
+                for (int b0 = cursor - skew; b0 < end && !cut; b0 += RQ_CM_BLOCK) {
+                    const int lc = b0 + 16 * lane;                           // this lane's 16 chunks: lc .. lc+15
+                    const uint4 e = nxt;
+                    nxt = load_cm(lc + RQ_CM_BLOCK);                         // the next block is in flight while this one is examined
+                    uint32_t m = 0;
+                    if (lc < end && lc + 16 > cursor) {
+                        m = cand_mask16<true>(e, bound);
+                        if (lc < cursor) m &= ~((1u << (cursor - lc)) - 1u);
+                        if (lc + 16 > end) m &= (1u << (end - lc)) - 1u;
                     }
-                };
-                auto flush = [&]() {                                         // examine the listed chunks; may cut the window
-                    int ccn, remn;
-                    uint4 een;
-                    fetch_chunk(0, ccn, remn, een);
+                    if (__ballot_sync(FULL, m != 0) == 0) continue;
+                    const int fc = __popc(m);
+                    int fi = fc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, fi, o); if (lane >= o) fi += v; }
+                    const int F = __shfl_sync(FULL, fi, 31);
+                    {
+                        int k = fi - fc;
+                        while (m) { const int v = __ffs(m) - 1; m &= m - 1; lst[k++] = (uint32_t)(lc + v); }
+                    }
+                    __syncwarp();
                     for (int j0 = 0; j0 < F; j0 += 32) {
-                        const int cc = ccn, rem = remn;
-                        const uint4 ee = een;
                         const bool act = j0 + lane < F;
-                        if (j0 + 32 < F) fetch_chunk(j0 + 32, ccn, remn, een);
-                        uint32_t mm = act ? (cand_mask16<true>(ee, bound) & (rem >= 16 ? 0xffffu : ((1u << rem) - 1u))) : 0u;
+                        const int cc = act ? (int)lst[j0 + lane] : 0;
+                        uint32_t mm = 0;
+                        uint4 ee = make_uint4(0, 0, 0, 0);
+                        if (act) {
+                            int lo = 0, hi = P;                              // segment with c[lo] <= cc < c[lo+1]
+                            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (c[mid] <= cc) lo = mid; else hi = mid; }
+                            const int rem = list_size[probes[(size_t)q * P + lo]] - 16 * (cc - c[lo]);
+                            const uint8_t *ea = cm_seg ? est + seg_off[(size_t)q * P + lo] + 16LL * (cc - c[lo]) : eq + 16LL * cc;
+                            ee = ldg_nc_u4(reinterpret_cast<const uint4 *>(ea));
+                            if (!SIGNED) { ee.x ^= 0x80808080u; ee.y ^= 0x80808080u; ee.z ^= 0x80808080u; ee.w ^= 0x80808080u; }
+                            mm = cand_mask16<true>(ee, bound) & (rem >= 16 ? 0xffffu : ((1u << rem) - 1u));
+                        }
                         if (__ballot_sync(FULL, mm != 0) == 0) continue;
                         const int cnt = __popc(mm);
                         int incl = cnt;
@@ -555,33 +563,8 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                         count += keep_tot;
                         if (cut) break;
                     }
-                    F = 0;
                     __syncwarp();
-                };
-                uint4 nxt = load_cm(cursor - skew + 16 * lane);
-                for (int b0 = cursor - skew; b0 < end && !cut; b0 += RQ_CM_BLOCK) {
-                    const int lc = b0 + 16 * lane;                           // this lane's 16 chunks: lc .. lc+15
-                    const uint4 e = nxt;
-                    nxt = load_cm(lc + RQ_CM_BLOCK);                         // the next block is in flight while this one is examined
-                    uint32_t m = 0;
-                    if (lc < end && lc + 16 > cursor) {
-                        m = cand_mask16<true>(e, bound);
-                        if (lc < cursor) m &= ~((1u << (cursor - lc)) - 1u);
-                        if (lc + 16 > end) m &= (1u << (end - lc)) - 1u;
-                    }
-                    if (__ballot_sync(FULL, m != 0) != 0) {
-                        const int fc = __popc(m);
-                        int fi = fc;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, fi, o); if (lane >= o) fi += v; }
-                        int k = F + fi - fc;
-                        while (m) { const int v = __ffs(m) - 1; m &= m - 1; lst[k++] = (uint32_t)(lc + v); }
-                        F += __shfl_sync(FULL, fi, 31);
-                        __syncwarp();
-                    }
-                    if (F > RQ_CM_LIST - RQ_CM_BLOCK) flush();                // the next block may list up to RQ_CM_BLOCK more
                 }
-                if (F > 0 && !cut) flush();
             } else
             for (int base0 = cursor; base0 < end; base0 += 32 * PF) {
                 uint4 ev[PF];
@@ -839,8 +822,8 @@ static size_t rq2_smem(int R, int P, int qpc, int qcap, bool cm = false, int thr
 {
     // (qcap + 4: two queues of qcap / 2 + 2 words when the rounds overlap; 24: five per-query ints, the count twice)
     const size_t base = (size_t)qpc * (4 * (2 * (size_t)R + 4) + 4 * ((size_t)qcap + 4) + 4 * ((size_t)P + 1) + 24) + 16;
-    // chunk-minimum path: s_qoff[qpc] + one list of RQ_CM_LIST chunk numbers per warp
-    return cm ? base + 16 + 8 * (size_t)qpc + 4 * (size_t)(threads / 32) * RQ_CM_LIST : base;
+    // chunk-minimum path: s_qoff[qpc] + one list of RQ_CM_BLOCK chunk numbers per warp
+    return cm ? base + 16 + 8 * (size_t)qpc + 4 * (size_t)(threads / 32) * RQ_CM_BLOCK : base;
 }
 
 // Launch geometry knobs of the pipelined replay (A/B switches; results do not depend on them): threads per CTA (TKB_RQ_THREADS:

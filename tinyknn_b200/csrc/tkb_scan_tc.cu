@@ -312,11 +312,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 //                            out its part of the half's previous tile] -> tcgen05.ld of D[h], certificate + clamp (s16x2 SIMD),
 //                            transposed tile in shared memory. While a half waits for its MMA or for tensor memory the other half
 //                            works: every scheduler holds four busy warps.
-//   warp 16      multiplies: one elected lane issues the tile's PH tcgen05.mma and commits them to the half's mbarrier
-//   warp 17      loads     : fetches the next work item, stages its LUT slab (double-buffered)
+//   warps 16, 17 multiply  : one per half; an elected lane issues the tile's PH tcgen05.mma and commits them to the half's mbarrier
+//   warp 18      loads     : fetches the next work item, stages its LUT slab (double-buffered)
 // A half reads D[h] and rewrites A[h] in program order, so the MMA warp needs no "empty" barriers: a_full[h] implies both.
 constexpr int TC_WORKERS = 16;
-constexpr int TC_WARPS = TC_WORKERS + 2;
+constexpr int TC_WARPS = TC_WORKERS + 3;      // + one MMA issuer per half + the loader
 constexpr int TC_THREADS2 = 32 * TC_WARPS;
 constexpr int TC_QUEUE = 4096;                  // refold queue of one work item
 
@@ -454,7 +454,7 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
     if (tid == 32) {
         for (int b = 0; b < 2; b++) {
             mbar_init(&S.item_full[b], 32);
-            mbar_init(&S.item_empty[b], TC_WORKERS + 1);
+            mbar_init(&S.item_empty[b], TC_WORKERS + 2);
             mbar_init(&S.a_full[b], TC_WORKERS / 2);
             mbar_init(&S.d_full[b], 1);
         }
@@ -547,9 +547,13 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             lk[1] += (CLK ? clock64() : 0LL) - c1_;
         }
         if (CLK && lane == 0) { atomicAdd(W.clk + CK_L_WAIT, (unsigned long long)lk[0]); atomicAdd(W.clk + CK_L_STAGE, (unsigned long long)lk[1]); }
-    } else if (warp == TC_WARPS - 2) {
-        // ================================ MMA issuer =================================================================
-        uint32_t g = 0;                                              // tiles issued so far (buffer = g & 1)
+    } else if (warp >= TC_WORKERS) {
+        // ================================ MMA issuers ================================================================
+        // One per half. A single issuer took the tiles in order, so a half whose tile was expanded first still waited for the other
+        // half's a_full (measured: ~400 cycles per tile between the end of the copy-out and d_full); with its own issuer a half's
+        // MMAs are issued the moment its tile is expanded, and the tensor pipe interleaves the two streams.
+        const int h = warp - TC_WORKERS;
+        uint32_t g = 0, k_tile = 0;                                  // tiles seen by the kernel / tiles of this half
         long long mk[3] = {0, 0, 0};
         const long long k0_ = (CLK ? clock64() : 0LL);
         for (uint32_t it = 0;; it++) {
@@ -560,10 +564,11 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
             {                                                         // the whole warp runs the loop, one elected lane issues
                 const uint32_t idesc = umma_idesc_i8(I.N);
                 const uint32_t b0 = smem_u32(Bslab + (size_t)par * SLAB);
-                for (int t = I.t0; t < I.t1; t++, g++) {
-                    const uint32_t b = g & 1, ph = (g >> 1) & 1;
+                const int first = I.t0 + (int)((h - g) & 1);
+                for (int t = first; t < I.t1; t += 2, k_tile++) {
+                    const uint32_t b = (uint32_t)h, ph = k_tile & 1;
                     const long long c0_ = (CLK ? clock64() : 0LL);
-                    // A[b] written AND D[b] read by the half (program order of its warps). The issuer waits ~70 % of the time in a
+                    // A[b] written AND D[b] read by the half (program order of its warps). The issuer waits most of the time in a
                     // kernel whose workers are issue-bound: it sleeps between polls instead of taking their slots
                     mbar_wait(&S.a_full[b], ph, 32);
                     tc_fence_after();
@@ -579,16 +584,19 @@ ivf_scan_tc_kernel(const uint32_t *__restrict__ nat32, const int64_t *__restrict
                     __syncwarp();
                     mk[0] += c1_ - c0_; mk[1] += c2_ - c1_; mk[2] += (CLK ? clock64() : 0LL) - c2_;
                 }
+                g += (uint32_t)(I.t1 - I.t0);
             }
             if (lane == 0) {
-                atomicAdd(W.hdr + 3, I.t1 - I.t0);
-                atomicAdd(W.hdr + 4, (I.t1 - I.t0) * (I.N >> 4));
+                if (h == 0) {
+                    atomicAdd(W.hdr + 3, I.t1 - I.t0);
+                    atomicAdd(W.hdr + 4, (I.t1 - I.t0) * (I.N >> 4));
+                }
                 mbar_arrive(&S.item_empty[par]);
             }
         }
-        if (CLK && lane == 0) {
-            atomicAdd(W.clk + CK_M_WAIT_A, (unsigned long long)mk[0]); atomicAdd(W.clk + CK_M_WAIT_D, (unsigned long long)mk[1]);
-            atomicAdd(W.clk + CK_M_ISSUE, (unsigned long long)mk[2]); atomicAdd(W.clk + CK_TOTAL, (unsigned long long)((CLK ? clock64() : 0LL) - k0_));
+        if (CLK && lane == 0 && h == 0) {                            // (half 0's issuer: its waits and issues are counted per tile of the kernel)
+            atomicAdd(W.clk + CK_M_WAIT_A, (unsigned long long)(2 * mk[0])); atomicAdd(W.clk + CK_M_WAIT_D, (unsigned long long)(2 * mk[1]));
+            atomicAdd(W.clk + CK_M_ISSUE, (unsigned long long)(2 * mk[2])); atomicAdd(W.clk + CK_TOTAL, (unsigned long long)((CLK ? clock64() : 0LL) - k0_));
         }
     } else {
         // ================================ workers ====================================================================
