@@ -200,7 +200,7 @@ def test_emulated_abi_reports_errors_like_the_real_one(emu):
 
 # too slow without a GPU (minutes each); they pass when run by hand, the async batches (2.5 min) and the CUDA-graph batch (13 min:
 # launches recorded with copies of their arguments and replayed, synchronising calls refused during the capture) included
-_SKIP_ON_EMULATOR = ("test_replay_deep_heaps and 70000", "test_glove_shape_full_size_properties", "test_graphed_batch_equals_eager",
+_SKIP_ON_EMULATOR = ("test_replay_deep_heaps and 70000", "test_glove_shape_full_size_properties", "test_sift_shape_full_size_both_orders", "test_graphed_batch_equals_eager",
                      "test_async_results_equal_sync", "test_estimate_large_bit_exact", "test_fast_scan_large_and_patch_rate",
                      "test_query_batch_with_chunk_minima_equals_plain", "test_encode_device_large_matches_oracle_and_scan_roundtrip")
 

@@ -269,8 +269,8 @@ def test_glove_shape_full_size_properties():
     S = O.IVFState.from_ivf(ivf)
     K = O.Kernels("port", "avx")
     qh = qs.cpu().numpy()
-    ids, cnt = ivf.query_batch(qh[:32], 10, n_probes=10, order="numpy")
-    for i in range(32):
+    ids, cnt = ivf.query_batch(qh[:128], 10, n_probes=10, order="numpy")
+    for i in range(128):
         assert set(ids[i][:cnt[i]]) == set(O.ivf_query(S, qh[i], 10, n_probes=10, kernels=K))
     # whole database, one list after the other, through FastPQ's own brute-force entry point
     packed = np.concatenate([td.packed for td in ivf.pq_transformed_points if isinstance(td, tuple)])
@@ -282,6 +282,41 @@ def test_glove_shape_full_size_properties():
         exp = np.zeros(2 * len(packed), np.uint64)
         O.estimate_pq(packed, np.ascontiguousarray(dt.tables), exp, True, "avx")
         assert np.array_equal(est.view(np.uint8), exp.view(np.uint8)[:len(est)])
+
+
+@pytest.mark.parametrize("order", ["avx", "sse"])
+def test_sift_shape_full_size_both_orders(order, monkeypatch):
+    """BASELINE.json configs[2] at full size (1 000 000 x 128 euclidean, 1024 lists; d = 128 is rotated to 64: M = 32) in both
+    accumulation orders (`_fast_pq_256.pyx` = avx, `_fast_pq.pyx` = sse): ids == oracle (the reference's selection order) on 96
+    queries, the throughput mode is idempotent and independent of sub-batching, and in the avx order the tensor-core scan and
+    the CUDA-core scan give the same heaps and ids for the whole batch."""
+    from tinyknn_b200 import synth, fast_pq, ivf as ivf_mod
+    n, nq = 1_000_000, 2048
+    X = synth.clustered(n + nq, 128, 2000, seed=12)
+    fast_pq.set_order(order)
+    try:
+        ivf = synth.build_ivf(X[:n], "euclidean", 1024, seed=12)
+        qs = X[n:].contiguous()
+        kw = dict(k=10, n_probes=10, order="device", return_distances=True)
+        a = ivf.query_batch(qs, **kw)
+        heaps = ivf._last["heap_idx"].cpu().numpy().copy()
+        for other in (ivf.query_batch(qs, **kw), ivf.query_batch(qs, sub_batches=1, **kw)):
+            assert all(np.array_equal(x, y) for x, y in zip(a, other))
+        assert (a[1] == 10).all() and (np.diff(a[2], axis=1) >= 0).all()
+        if order == "avx" and ivf_mod._tc_possible(ivf.to_device()):
+            monkeypatch.setattr(ivf_mod, "TC_SCAN", "0")                  # the same batch through the CUDA-core kernels only
+            b = ivf.query_batch(qs, sub_batches=1, **kw)
+            assert np.array_equal(ivf._last["heap_idx"].cpu().numpy(), heaps)
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+            monkeypatch.setattr(ivf_mod, "TC_SCAN", "auto")
+        S = O.IVFState.from_ivf(ivf)
+        K = O.Kernels("port", order)
+        qh = qs.cpu().numpy()
+        ids, cnt = ivf.query_batch(qh[:96], 10, n_probes=10, order="numpy")
+        for i in range(96):
+            assert set(ids[i][:cnt[i]]) == set(O.ivf_query(S, qh[i], 10, n_probes=10, kernels=K))
+    finally:
+        fast_pq.set_order("avx")
 
 
 def test_graphed_batch_equals_eager(golden):

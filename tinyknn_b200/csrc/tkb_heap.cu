@@ -390,7 +390,7 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
     uint32_t *QU = H + (size_t)QPC * HS;                                   // [1 or 2][QPC][QCAP+2]
     int *cum = reinterpret_cast<int *>(QU + (size_t)(ovl_arg ? 2 : 1) * QPC * (QCAP + 2));     // [QPC][P+1] real chunks before segment s
     int *s_cursor = cum + (size_t)QPC * (P + 1);
-    int *s_seg = s_cursor + QPC, *s_bound = s_seg + QPC, *s_count = s_bound + QPC, *s_round = s_count + 2 * QPC;   // s_count: [2][QPC]
+    int *s_seg = s_cursor + QPC, *s_bound = s_seg + QPC, *s_count = s_bound + 2 * QPC, *s_round = s_count + 2 * QPC;   // s_bound, s_count: [2][QPC]
     // chunk-minimum path (cmin != null): est offset of the query's first chunk, or -1 when its segments are not back to back;
     // one list of flagged chunks per warp
     long long *s_qoff = reinterpret_cast<long long *>(rq_sm + (((size_t)((unsigned char *)(s_round + QPC) - rq_sm) + 15) & ~(size_t)15));   // (s_round is the last int array)
@@ -434,7 +434,7 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
         if (run >= (1 << 20) - 1) ok = false;                              // positions must fit 24 bits
         if (q < Q && fallback) fallback[q] = ok ? 0 : 1;
         if (!ok) for (int s = 0; s <= P; s++) c[s] = 0;
-        s_cursor[t] = 0; s_seg[t] = 0; s_bound[t] = init; s_count[t] = 0; s_count[QPC + t] = 0; s_round[t] = 0;
+        s_cursor[t] = 0; s_seg[t] = 0; s_bound[t] = init; s_bound[QPC + t] = init; s_count[t] = 0; s_count[QPC + t] = 0; s_round[t] = 0;
         if (CM && cmin) {
             // the query's stream is one contiguous byte range of `est` when its segments lie back to back (the compact
             // single-GPU plan): chunk cc of the stream is est[qoff + 16 cc ..] and its minimum is cmin[qoff / 16 + cc]
@@ -473,7 +473,9 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
             const int cursor = s_cursor[t];
             if (cursor >= total) { if (lane == 0) s_count[pb * QPC + t] = 0; continue; }
             const int q = q0 + t;
-            const int bound = s_bound[t];                                  // stored form
+            // overlapped rounds: the bound the consumer left at the end of the PREVIOUS iteration (its own slot: the consumer of
+            // this iteration writes the other one, so there is no concurrent access and the filter does not depend on timing)
+            const int bound = s_bound[(ovl ? (r & 1) : 0) * QPC + t];      // stored form
             int W = s_round[t] == 0 ? ((R + 15) >> 4) + 1 : (cursor < 32 ? 32 : cursor);
             if (W > (1 << 16)) W = 1 << 16;
             int end = (total - cursor < W) ? total : cursor + W;
@@ -700,7 +702,7 @@ replay_rq2_kernel(int mode, const uint8_t *__restrict__ est, int64_t stride, con
                     __syncwarp();
                     rootm = hw[1] & 0xff000000u;
                 }
-                if (mine && role == 0) s_bound[t] = (int)rootm >> 24;
+                if (mine && role == 0) s_bound[(ovl ? ((r + 1) & 1) : 0) * QPC + t] = (int)rootm >> 24;
             }
         }
         if (indep) __syncwarp();
@@ -820,8 +822,8 @@ static size_t rq_smem(int R, int P, int qpc, int qcap)
 
 static size_t rq2_smem(int R, int P, int qpc, int qcap, bool cm = false, int threads = RQ_THREADS)
 {
-    // (qcap + 4: two queues of qcap / 2 + 2 words when the rounds overlap; 24: five per-query ints, the count twice)
-    const size_t base = (size_t)qpc * (4 * (2 * (size_t)R + 4) + 4 * ((size_t)qcap + 4) + 4 * ((size_t)P + 1) + 24) + 16;
+    // (qcap + 4: two queues of qcap / 2 + 2 words when the rounds overlap; 28: five per-query ints, bound and count twice)
+    const size_t base = (size_t)qpc * (4 * (2 * (size_t)R + 4) + 4 * ((size_t)qcap + 4) + 4 * ((size_t)P + 1) + 28) + 16;
     // chunk-minimum path: s_qoff[qpc] + one list of RQ_CM_BLOCK chunk numbers per warp
     return cm ? base + 16 + 8 * (size_t)qpc + 4 * (size_t)(threads / 32) * RQ_CM_BLOCK : base;
 }
