@@ -339,7 +339,7 @@ class IVF:
         Returns (ids, counts[, dists]): ids int64 (Q, k) padded with -1, counts int32 (Q,).
         With to_host=False (order="device" only) the results stay on the GPU as torch tensors; to_host="async" returns a
         `PendingBatch` at once (device-to-host copies into pinned memory are queued behind the kernels; `.result()` waits),
-        so that a caller can submit the next batch before it collects the previous one -- NOT YET RUN ON A GPU.
+        so that a caller can submit the next batch before it collects the previous one (bench.py's `e2e_pipelined`).
         sub_batches (order="device"): split the batch over side streams (None: automatic, 1: one stream).
         fused (order="device"): run everything after probe selection as one kernel (None: module default FUSED);
         False keeps the stage-by-stage kernels (scan / replay / gather / select), same results."""
@@ -418,7 +418,7 @@ class IVF:
         sequence of launches of one batch is captured once and replayed per call, which removes the host-side launch
         cost that a synchronous caller pays in front of every batch (about 26 launches). Returns a `GraphedBatch`;
         `graphed(...)(queries)` gives the same results as `query_batch(queries, k, n_probes, order="device")`.
-        NOT YET RUN ON A GPU (written after round 1's GPU budget was spent): tests/test_gpu_build_and_batch.py."""
+        Validated on a B200 (tests/test_gpu_build_and_batch.py); `bench.py --graph` times it."""
         return GraphedBatch(self, int(n_queries), int(k), int(n_probes), pass_1, sub_batches)
 
     # -- stages of one block of queries (shared with the list-sharded index, sharded.py) ----------------

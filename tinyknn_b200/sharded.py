@@ -44,7 +44,7 @@ from ._lib import PLAN_SEND, PLAN_RECV, PLAN_PUSH, PROBE_SKIP
 # ---------------------------------------------------------------------------------------------------------
 
 # default exchange of ShardedIVF.query_batch: "pull" (estimates stay with the owner, the home rank's replay fetches minima and
-# candidate chunks over NVLink: 100M x 128 on 8 GPUs 4.19 M q/s against 1.79 M for "push"), "push" (NVLink peer stores from the
+# candidate chunks over NVLink: 100M x 128 on 8 GPUs 4.30 M q/s against 1.79 M for "push"), "push" (NVLink peer stores from the
 # scan kernel) or "nccl" (all-to-all)
 EXCHANGE = os.environ.get("TKB_EXCHANGE", "pull")
 # "pull": estimates stay in the owner's HBM, the home rank's replay fetches minima + candidate chunks over NVLink (see above)
