@@ -838,7 +838,7 @@ static int rq_env(const char *name, int dflt, int lo, int hi)
     return (v < lo || v > hi) ? dflt : v;
 }
 
-static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 0, bool cm = false)
+static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 0, bool cm = false, bool remote = false)
 {
     if (R <= 0 || P <= 0) return false;
     static int v2_env = -1;
@@ -866,7 +866,9 @@ static bool rq_geometry(int Q, int R, int P, RqGeom &g, int64_t stream_chunks = 
         const bool long_streams = cm;
         int th = threads, qm = qcap_mult, kb = smem_kb;
         if (long_streams) {
-            if (!getenv("TKB_RQ_THREADS")) th = 128;
+            // estimates in other GPUs' memory (pull exchange): a producer waits microseconds for every fetch, so six producer
+            // warps per CTA instead of two (same residency: the shared memory still admits four CTAs); 2 GPUs: 3.47 -> 3.21 ms
+            if (!getenv("TKB_RQ_THREADS")) th = remote ? 256 : 128;
             if (!getenv("TKB_RQ_QCAP")) qm = 1;
             if (!getenv("TKB_RQ_SMEM_KB")) kb = 36;
         }
@@ -1002,7 +1004,7 @@ int launch_ivf_replay_fresh(const uint8_t *est, int64_t slot_stride, const int64
     TKB_REQUIRE(heap_idx && heap_val, "null pointer");
     TKB_REQUIRE(!cmin || ((uintptr_t)cmin % 16 == 0 && seg_off), "cmin must be 16-byte aligned and needs a segment plan");
     RqGeom g;
-    if (!unique_labels || P == 0 || P >= 0xffff || !fallback || !rq_geometry(Q, R, P, g, 0, cmin != nullptr)) {
+    if (!unique_labels || P == 0 || P >= 0xffff || !fallback || !rq_geometry(Q, R, P, g, 0, cmin != nullptr, cm_seg != nullptr)) {
         if (int rc = launch_heap_fill(heap_idx, heap_val, (int64_t)Q * R, signd, st)) return rc;
         return launch_ivf_replay(est, slot_stride, seg_off, list_chunk_off, list_size, n_lists, ids, probes, Q, P, heap_idx,
                                  heap_val, R, signd, st);
