@@ -240,6 +240,41 @@ def test_pull_exchange_single_gpu(monkeypatch):
             b.close()
 
 
+def test_pull_minima_copies_every_alignment():
+    """tkb_ivf_pull_minima_dev against numpy: segments of every length class (empty, shorter than a word, many 1 KB blocks) at
+    every byte alignment of source and destination, skipped probes, two owners; the bytes around every destination stay."""
+    from tinyknn_b200._lib import lib, check, PROBE_SKIP
+    rng = np.random.default_rng(4)
+    n_lists, Q, P = 40, 24, 7
+    sizes = rng.choice([0, 1, 15, 16, 17, 40, 63, 700, 4097, 9000, 33000], size=n_lists).astype(np.int32)
+    owner = rng.integers(0, 2, size=n_lists).astype(np.int32)
+    probes = np.stack([rng.permutation(n_lists)[:P] for _ in range(Q)]).astype(np.int32)
+    probes[3, 2] = PROBE_SKIP
+    nch = (sizes.astype(np.int64) + 15) // 16
+    src = [rng.integers(0, 256, size=200_000, dtype=np.uint8) for _ in range(2)]       # the two owners' minima regions
+    seg_addr = np.full((Q, P), -1, dtype=np.int64)
+    seg_local = np.full((Q, P), -1, dtype=np.int64)
+    run_local, expect = 5, np.full(400_000, 0xEE, dtype=np.uint8)
+    for q in range(Q):
+        for s_ in range(P):
+            l = probes[q, s_]
+            if l == PROBE_SKIP:
+                continue
+            a = int(rng.integers(0, 200_000 - nch[l] - 1))                              # any byte alignment of the source
+            seg_addr[q, s_] = 16 * a                                                    # "estimate address": minima index = address >> 4
+            run_local += int(rng.integers(0, 4))                                        # any byte alignment of the destination
+            seg_local[q, s_] = 16 * run_local
+            expect[run_local:run_local + nch[l]] = src[owner[l]][a:a + nch[l]]
+            run_local += int(nch[l])
+    d_src = [D.upload(x) for x in src]
+    cm_table = D.upload(np.array([D.ptr(x) for x in d_src], dtype=np.int64))
+    dst = D.upload(np.full(400_000, 0xEE, dtype=np.uint8))
+    d_probes, d_sizes, d_owner, d_addr, d_local = (D.upload(x) for x in (probes, sizes, owner, seg_addr, seg_local))   # named: they outlive the launch
+    check(lib.tkb_ivf_pull_minima_dev(D.ptr(d_probes), Q, P, D.ptr(d_sizes), D.ptr(d_owner), n_lists,
+                                      D.ptr(d_addr), D.ptr(d_local), D.ptr(cm_table), D.ptr(dst), D.stream_ptr()))
+    assert np.array_equal(dst.cpu().numpy(), expect)
+
+
 def test_saved_index_answers_identically(tmp_path):
     """save_index / load_index (memory-mapped) -> to_device -> query_batch == the original index."""
     np.random.seed(6)

@@ -256,17 +256,26 @@ pull_minima_kernel(const int32_t *__restrict__ probes, int64_t n_seg, const int3
     uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
     constexpr int U = 8;                                           // 1 KB of a segment in flight per warp (the loads cross NVLink)
     for (int j0 = 0; j0 < n_words; j0 += 32 * U) {
-        uint32_t lo[U], hi[U];
+        // every source word is loaded ONCE: the upper word a destination word needs is the next lane's (the next row's first
+        // lane's) lower word, passed by shuffle -- loads from a peer GPU are not cached in L1, so a second, shifted load of the
+        // same line would cross NVLink again
+        uint32_t lo[U + 1];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int j = j0 + 32 * u + lane;
-            lo[u] = hi[u] = 0;
-            if (j < n_words) { lo[u] = sw[j]; if (mis) hi[u] = sw[j + 1]; }
+            lo[u] = j < n_words + (mis ? 1 : 0) ? sw[j] : 0u;        // (word n_words holds the last bytes when the source is shifted)
+        }
+        {
+            const int j = j0 + 32 * U;                              // first word of the next block: the last lane's upper word
+            lo[U] = (mis && j <= n_words) ? sw[j] : 0u;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int j = j0 + 32 * u + lane;
-            if (j < n_words) dw[j] = mis ? (lo[u] >> (8 * mis)) | (hi[u] << (32 - 8 * mis)) : lo[u];
+            const uint32_t nxt_lane = __shfl_down_sync(FULL, lo[u], 1);
+            const uint32_t nxt_row = __shfl_sync(FULL, lo[u + 1], 0);
+            const uint32_t hi = lane == 31 ? nxt_row : nxt_lane;
+            if (j < n_words) dw[j] = mis ? (lo[u] >> (8 * mis)) | (hi << (32 - 8 * mis)) : lo[u];
         }
     }
     const int done = head + 4 * n_words;
