@@ -699,6 +699,63 @@ def test_plan_device_matches_host_restatement(G):
             assert np.array_equal(g[:G], gb) and g[G] == gb.sum() and np.array_equal(g[G + 1:], base)
 
 
+@pytest.mark.parametrize("Q", [129, 5000, 140_000])
+def test_plan_device_many_queries_matches_numpy(Q):
+    """The plan's scan over many count-kernel CTAs (and, above 131 072 queries, several CTAs per thread of the one scanning CTA):
+    send layout, capacity guard of the pull exchange's owner plan, home-side absolute addresses -- against vectorised numpy."""
+    from tinyknn_b200._lib import lib, check, PROBE_SKIP, PLAN_SEND
+    rng = np.random.default_rng(Q)
+    G, P, n_lists = 4, 3, 97
+    Qh = -(-Q // G)
+    sizes = rng.integers(0, 500, size=n_lists).astype(np.int32)
+    owner = rng.integers(0, G, size=n_lists).astype(np.int32)
+    probes = rng.integers(0, n_lists, size=(Q, P)).astype(np.int32)
+    probes[rng.integers(0, Q, size=max(1, Q // 50)), rng.integers(0, P, size=max(1, Q // 50))] = PROBE_SKIP
+    nbytes = np.where(probes == PROBE_SKIP, 0, 16 * ((sizes[np.maximum(probes, 0)].astype(np.int64) + 15) // 16))
+    own = np.where(probes == PROBE_SKIP, -1, owner[np.maximum(probes, 0)])
+    home = np.arange(Q) // Qh
+    d_probes, d_sizes, d_owner = D.upload(probes), D.upload(sizes), D.upload(owner)
+    r = 1
+    # owner side (send layout of rank r): grouped by the home rank of the query, then (q, s)
+    mine = (own == r) & (nbytes > 0)
+    b = np.where(mine, nbytes, 0)
+    group_bytes = np.array([b[home == g].sum() for g in range(G)], dtype=np.int64)
+    base = np.concatenate([[0], np.cumsum(group_bytes)[:-1]])
+    flat = b.reshape(-1)
+    excl = np.cumsum(flat) - flat                                   # (q, s) order; homes are contiguous query ranges
+    exp = np.where(mine.reshape(-1), excl, -1).reshape(Q, P)         # base[g] + offset inside the group == the global exclusive sum
+    d_seg, d_gb, d_ws = D.empty((Q, P), np.int64), D.empty((2 * G + 1,), np.int64), D.empty((Q * G,), np.int64)
+    check(lib.tkb_ivf_plan_dev(D.ptr(d_probes), Q, P, D.ptr(d_sizes), D.ptr(d_owner), n_lists, PLAN_SEND, r, G, Qh,
+                               D.ptr(d_seg), D.ptr(d_gb), D.ptr(d_ws), 8 * Q * G, D.stream_ptr()))
+    g = d_gb.cpu().numpy()
+    assert np.array_equal(g[:G], group_bytes) and g[G] == group_bytes.sum() and np.array_equal(g[G + 1:], base)
+    assert np.array_equal(d_seg.cpu().numpy(), exp)
+    cap = int(group_bytes.sum()) // 2 + 16                           # the guard: segments that would end past the capacity are dropped
+    check(lib.tkb_ivf_plan_pull_owner_dev(D.ptr(d_probes), Q, P, D.ptr(d_sizes), D.ptr(d_owner), n_lists, r, G, Qh, cap,
+                                          D.ptr(d_seg), D.ptr(d_gb), D.ptr(d_ws), 8 * Q * G, D.stream_ptr()))
+    assert np.array_equal(d_seg.cpu().numpy(), np.where((exp >= 0) & (exp + nbytes <= cap), exp, -1))
+    assert d_gb.cpu().numpy()[G] == group_bytes.sum()                # the full total is still reported
+    # home side of rank r: absolute addresses = owner's buffer + the owner's base of home group r + offset inside that group
+    lo, hi = r * Qh, min(Q, (r + 1) * Qh)
+    owner_base = (np.arange(G, dtype=np.int64) + 1) << 40
+    owner_groups = np.zeros((G, G + 1), dtype=np.int64)
+    expect = np.full((hi - lo, P), -1, dtype=np.int64)
+    for o in range(G):
+        bo = np.where((own == o) & (nbytes > 0), nbytes, 0)
+        gbo = np.array([bo[home == g].sum() for g in range(G)], dtype=np.int64)
+        owner_groups[o, 0] = gbo.sum()
+        owner_groups[o, 1:] = np.concatenate([[0], np.cumsum(gbo)[:-1]])
+        f = bo[lo:hi].reshape(-1)
+        e = (np.cumsum(f) - f).reshape(hi - lo, P)
+        sel = (own[lo:hi] == o) & (nbytes[lo:hi] > 0)
+        expect[sel] = owner_base[o] + owner_groups[o, 1 + r] + e[sel]
+    d_addr, d_gb2, d_ws2 = D.empty((hi - lo, P), np.int64), D.empty((2 * G + 1,), np.int64), D.empty((max(hi - lo, 1) * G,), np.int64)
+    d_ob, d_og = D.upload(owner_base), D.upload(owner_groups)
+    check(lib.tkb_ivf_plan_pull_home_dev(D.ptr(d_probes), Q, P, D.ptr(d_sizes), D.ptr(d_owner), n_lists, r, G, Qh, D.ptr(d_ob),
+                                         D.ptr(d_og), D.ptr(d_addr), D.ptr(d_gb2), D.ptr(d_ws2), 8 * max(hi - lo, 1) * G, D.stream_ptr()))
+    assert np.array_equal(d_addr.cpu().numpy(), expect)
+
+
 @pytest.mark.parametrize("G", [2, 3])
 def test_sharded_phases_equal_single_gpu(golden, G):
     """List-sharded query path driven rank by rank on ONE GPU (buffers moved by hand instead of NCCL): heaps,
