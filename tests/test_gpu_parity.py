@@ -200,6 +200,26 @@ def test_lut_bytes_match_reference(golden):
             np.testing.assert_allclose(lut["q_rot"].cpu().numpy(), z[name + "_qrot"], rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("d", [100, 7, 31, 64, 96, 128, 200])
+def test_angular_normalisation_equals_numpy_bit_for_bit(d):
+    """`q /= np.linalg.norm(q)` (ref: ivf.py:126-127) in the LUT kernel: the normalised queries equal numpy's on a host whose
+    OpenBLAS runs the SkylakeX sdot kernels (this pool; tests/test_oracle_pinned.py pins that arithmetic), for vector lengths on
+    both sides of the kernel's 32- and 64-element blocks."""
+    from threadpoolctl import threadpool_info
+    if "SkylakeX" not in [t.get("architecture") for t in threadpool_info() if t.get("internal_api") == "openblas"]:
+        pytest.skip("numpy's OpenBLAS does not run the SkylakeX kernels on this host")
+    rng = np.random.default_rng(d)
+    pq = tinyknn.FastPQ(2, rotate_dim=None)                       # codebooks do not matter here: any fitted state will do
+    Dpad = -(-d // 8) * 8
+    pq.centers = rng.standard_normal((16, Dpad)).astype(np.float32)
+    pq.sqrt_n_blocks = np.sqrt(Dpad // 2)
+    qs = (rng.standard_normal((500, d)) * rng.choice([1e-2, 1.0, 30.0], size=(500, 1))).astype(np.float32)
+    lut = pq.distance_tables(D.upload(qs), signed=True, normalize=True)
+    got = lut["q"].cpu().numpy()
+    exp = np.stack([q / np.linalg.norm(q) for q in qs])
+    assert got.tobytes() == exp.tobytes()
+
+
 def test_distance_table_object(golden):
     z = golden["lut"]
     for name in ("d128", "d100"):

@@ -283,6 +283,23 @@ def test_numpy_matmul_is_a_sequential_fma_chain():
             assert np.array_equal(out, a @ b.T), (dt.__name__, n, m, K)
 
 
+def test_numpy_f32_dot_is_openblas_skylakex_sdot():
+    """The assumption the LUT kernel's angular normalisation rests on (tkb_lut.cu; ref: ivf.py:127 `q /= np.linalg.norm(q)`):
+    `np.linalg.norm` of an f32 vector is sqrt(x.dot(x)) and the dot product is OpenBLAS's sdot, whose SkylakeX kernels sum in 64 /
+    32 lanes with a double-precision tail -- oracle.restate.sdot_openblas_skylakex. Pinned against numpy itself wherever numpy
+    runs those kernels (the hosts of this pool); skipped on a host whose OpenBLAS picked another core."""
+    from threadpoolctl import threadpool_info
+    arch = [d.get("architecture") for d in threadpool_info() if d.get("internal_api") == "openblas"]
+    if "SkylakeX" not in arch:
+        pytest.skip("numpy's OpenBLAS runs %s kernels here, not SkylakeX" % arch)
+    rng = np.random.default_rng(8)
+    for n in (1, 7, 31, 32, 33, 64, 96, 99, 100, 104, 128, 200, 1000):
+        for _ in range(60):
+            x = (rng.standard_normal(n) * rng.choice([1e-3, 1.0, 50.0])).astype(np.float32)
+            assert O.sdot_openblas_skylakex(x, x).tobytes() == x.dot(x).tobytes(), n
+            assert np.linalg.norm(x).tobytes() == np.sqrt(O.sdot_openblas_skylakex(x, x)).tobytes(), n
+
+
 def test_numpy_vector_times_matrix_is_a_four_lane_fma_chain(golden):
     """The assumption the LUT kernel's rotation rests on (tkb_lut.cu; ref: fast_pq.py:203-204 `q @ R.T`): for a float64 VECTOR
     numpy calls OpenBLAS's dgemv, which sums in four lanes (k mod 4), FMA, combined (a0 + a2) + (a1 + a3) -- pinned against

@@ -139,11 +139,39 @@ lut_build_kernel(const float *__restrict__ queries, int d, int normalize, float 
     for (int i = tid; i < Dpad; i += LUT_THREADS) qpad[i] = (i < d) ? qin[i] : 0.0f;
     __syncthreads();
     if (normalize) {
+        // `np.linalg.norm(q)` = sqrt(q.dot(q)) in f32, and q.dot(q) is OpenBLAS's sdot. Its arithmetic on the hosts of this pool
+        // (OpenBLAS 0.3.30, SkylakeX kernels -- threadpoolctl reports that core here and on the GPU boxes), established against
+        // numpy itself (tests/test_oracle_pinned.py, oracle/restate.py:sdot_openblas_skylakex; 100 % of 4 400 random vectors of
+        // eleven lengths): the first n & ~31 elements in a vector kernel -- blocks of 64 into four 16-lane FMA accumulators, each
+        // folded low half + high half into 8 lanes; a last block of 32 into those four 8-lane accumulators; ((a0 + a1) + a2) + a3;
+        // low 4 lanes + high 4 lanes; (h0 + h1) + (h2 + h3) -- then the remaining elements as separately rounded f32 products
+        // summed in DOUBLE, plus the kernel's value, rounded to f32 once. Round 2's bench found 1 LUT byte in 2 000 GloVe-shape
+        // queries off with a plain shuffle tree; this reproduces numpy's norm bit for bit on such hosts.
         if (tid < 32) {
-            float acc = 0.0f;
-            for (int i = tid; i < d; i += 32) acc = fmaf(qpad[i], qpad[i], acc);
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-            if (tid == 0) s_norm = sqrtf(acc);
+            const int n1 = d & ~31, n64 = n1 & ~63;
+            float r0 = 0.0f, r1 = 0.0f;                         // 16-lane accumulators 0,1 (lanes tid) and 2,3 (lanes tid + 32)
+            for (int i = 0; i < n64; i += 64) {
+                r0 = fmaf(qpad[i + tid], qpad[i + tid], r0);
+                r1 = fmaf(qpad[i + 32 + tid], qpad[i + 32 + tid], r1);
+            }
+            float f0 = __fadd_rn(r0, __shfl_down_sync(FULL, r0, 8));     // lanes 0..7: accumulator 0, lanes 16..23: accumulator 1
+            float f1 = __fadd_rn(r1, __shfl_down_sync(FULL, r1, 8));     // the same for accumulators 2 and 3
+            if (n1 > n64 && (tid & 15) < 8) {                   // the last block of 32: element 8 k + l into lane l of accumulator k
+                const int k0 = tid >> 4, l = tid & 7;
+                const float xa = qpad[n64 + 8 * k0 + l], xb = qpad[n64 + 16 + 8 * k0 + l];
+                f0 = fmaf(xa, xa, f0);
+                f1 = fmaf(xb, xb, f1);
+            }
+            const float a1 = __shfl_sync(FULL, f0, (tid & 7) + 16), a3 = __shfl_sync(FULL, f1, (tid & 7) + 16);
+            const float s8 = __fadd_rn(__fadd_rn(__fadd_rn(f0, a1), f1), a3);          // lanes 0..7
+            const float h4 = __fadd_rn(s8, __shfl_down_sync(FULL, s8, 4));             // lanes 0..3
+            const float p2 = __fadd_rn(h4, __shfl_down_sync(FULL, h4, 1));             // lane 0: h0 + h1, lane 2: h2 + h3
+            const float vec = __fadd_rn(p2, __shfl_down_sync(FULL, p2, 2));            // lane 0
+            if (tid == 0) {
+                double t = 0.0;
+                for (int i = n1; i < d; i++) t += (double)__fmul_rn(qpad[i], qpad[i]);
+                s_norm = sqrtf((float)(t + (double)(n1 ? vec : 0.0f)));
+            }
         }
         __syncthreads();
         const float nrm = s_norm;
